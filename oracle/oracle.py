@@ -1,0 +1,224 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE — see umt_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs import this module.  It never touches the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_NBB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_bp = C.POINTER(C.c_ubyte)
+
+
+def build(force: bool = False) -> None:
+    so = os.path.join(_HERE, "libumt_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("umt_oracle.c", "umt_oracle_gta.c")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale or not os.path.exists(os.path.join(_HERE, "_ref", "libnbb_ref.so")):
+        subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
+
+
+class _Mesh(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("ndim", "nzones", "ncornr", "nbelem", "maxcf", "maxCorner", "maxFaces")] + \
+               [(n, c_ip) for n in ("numCorner", "cOffSet", "zoneFaces", "zoneOpp", "faceOpp", "nCFaces", "cFP", "cEZ", "CToFace")] + \
+               [("BoundaryZone", c_bp), ("px", c_dp)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        _LIB = C.CDLL(os.path.join(_HERE, "libumt_oracle.so"))
+        _LIB.orc_quad_xyz.restype = C.c_int
+        _LIB.orc_quad_rz.restype = C.c_int
+        _LIB.orc_snnext.restype = C.c_int
+        _LIB.orc_bdy_exit.restype = C.c_int
+        _LIB.orc_max_threads.restype = C.c_int
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _bp(a):
+    return a.ctypes.data_as(c_bp)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class OMesh:
+    """Keeps the numpy arrays alive next to the C struct."""
+
+    def __init__(self, m):
+        self.m = m
+        self.keep = dict(
+            numCorner=_i32(m.numCorner), cOffSet=_i32(m.cOffSet), zoneFaces=_i32(m.zoneFaces),
+            zoneOpp=_i32(m.zoneOpp), faceOpp=_i32(m.faceOpp), nCFaces=_i32(m.nCFacesArray),
+            cFP=_i32(m.cFP), cEZ=_i32(m.cEZ), CToFace=_i32(m.CToFace),
+            BoundaryZone=np.ascontiguousarray(m.BoundaryZone, dtype=np.uint8),
+            px=np.ascontiguousarray(m.px, dtype=np.float64))
+        s = _Mesh()
+        for n in ("ndim", "nzones", "ncornr", "nbelem", "maxcf", "maxCorner", "maxFaces"):
+            setattr(s, n, int(getattr(m, n)))
+        for n in ("numCorner", "cOffSet", "zoneFaces", "zoneOpp", "faceOpp", "nCFaces", "cFP", "cEZ", "CToFace"):
+            setattr(s, n, _ip(self.keep[n]))
+        s.BoundaryZone = _bp(self.keep["BoundaryZone"])
+        s.px = _dp(self.keep["px"])
+        self.s = s
+
+    @property
+    def ref(self):
+        return C.byref(self.s)
+
+
+# ---------------------------------------------------------------------------
+def quad_xyz(npolar: int, nazimuthal: int, polaraxis: int = 1):
+    NA = 8 * npolar * nazimuthal
+    omega = np.zeros((NA, 3))
+    weight = np.zeros(NA)
+    n = lib().orc_quad_xyz(npolar, nazimuthal, polaraxis, _dp(omega), _dp(weight))
+    assert n == NA
+    return omega, weight
+
+
+def quad_rz(npolar: int, nazimuthal: int) -> Dict[str, np.ndarray]:
+    NA = 4 * npolar * (nazimuthal + 1)
+    q = dict(omega=np.zeros((NA, 2)), weight=np.zeros(NA), start=np.zeros(NA, np.uint8), finish=np.zeros(NA + 1, np.uint8),
+             level=np.zeros(NA, np.int32), alpha=np.zeros(NA), tau=np.zeros(NA), angDerivFac=np.zeros(NA),
+             quadTauW1=np.zeros(NA), quadTauW2=np.zeros(NA))
+    n = lib().orc_quad_rz(npolar, nazimuthal, _dp(q["omega"]), _dp(q["weight"]), _bp(q["start"]), _bp(q["finish"]),
+                          _ip(q["level"]), _dp(q["alpha"]), _dp(q["tau"]), _dp(q["angDerivFac"]),
+                          _dp(q["quadTauW1"]), _dp(q["quadTauW2"]))
+    assert n == NA
+    return q
+
+
+def geometry(om: OMesh) -> Dict[str, np.ndarray]:
+    m = om.m
+    nd, nc, mcf = m.ndim, m.ncornr, m.maxcf
+    g = dict(A_fp=np.zeros((nc, mcf, nd)), A_ez=np.zeros((nc, mcf, nd)), Volume=np.zeros(nc),
+             VolumeZone=np.zeros(m.nzones), A_bdy=np.zeros((max(m.nbelem, 1), nd)))
+    if nd == 3:
+        lib().orc_geometry_xyz(om.ref, _dp(g["A_fp"]), _dp(g["A_ez"]), _dp(g["Volume"]))
+        vol2 = np.zeros(nc)
+        lib().orc_volume_xyz(om.ref, _dp(vol2), _dp(g["VolumeZone"]), _dp(g["A_bdy"]))
+        g["Volume_getvolume"] = vol2
+    else:
+        g.update(Area=np.zeros(nc), RadiusFP=np.zeros((nc, 2)), RadiusEZ=np.zeros((nc, 2)), RadiusB=np.zeros(max(m.nbelem, 1)))
+        lib().orc_geometry_rz(om.ref, _dp(g["A_fp"]), _dp(g["A_ez"]), _dp(g["Area"]), _dp(g["Volume"]),
+                              _dp(g["RadiusFP"]), _dp(g["RadiusEZ"]), _dp(g["VolumeZone"]), _dp(g["A_bdy"]), _dp(g["RadiusB"]))
+    return g
+
+
+def schedule(om: OMesh, geom, omega: np.ndarray, skip: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """rtorder.F90: snnext for every angle (finishing directions are skipped)."""
+    m = om.m
+    NA = omega.shape[0]
+    nz, nc = m.nzones, m.ncornr
+    s = dict(nHyperPlanes=np.zeros(NA, np.int32), zonesInPlane=np.zeros((NA, nz), np.int32),
+             nextZ=np.zeros((NA, nz), np.int32), nextC=np.zeros((NA, nc), np.int32),
+             numCycles=np.zeros(NA, np.int32), cycleOffSet=np.zeros(NA, np.int32))
+    cl: List[np.ndarray] = []
+    tmp = np.zeros(nc, np.int32)
+    off = 0
+    om_c = np.ascontiguousarray(omega)
+    for a in range(NA):
+        s["cycleOffSet"][a] = off
+        if skip is not None and skip[a]:
+            continue
+        ncyc = C.c_int(0)
+        s["nHyperPlanes"][a] = lib().orc_snnext(om.ref, _dp(geom["A_fp"]), _dp(geom["A_ez"]), _dp(om_c[a]),
+                                                _ip(s["nextZ"][a]), _ip(s["nextC"][a]), _ip(s["zonesInPlane"][a]),
+                                                C.byref(ncyc), _ip(tmp))
+        s["numCycles"][a] = ncyc.value
+        cl.append(tmp[:ncyc.value].copy())
+        off += ncyc.value
+    s["cycleList"] = np.concatenate(cl + [np.zeros(1, np.int32)]).astype(np.int32)
+    s["totalCycles"] = off
+    return s
+
+
+def bdy_exit(om: OMesh, geom, omega_a: np.ndarray, is_shared=None, is_exit_shared=None) -> np.ndarray:
+    m = om.m
+    out = np.zeros((max(m.nbelem, 1), 2), np.int32)
+    n = lib().orc_bdy_exit(m.ndim, m.nbelem, _dp(geom["A_bdy"]), _ip(_i32(m.BdyToC)),
+                           _bp(is_shared) if is_shared is not None else None,
+                           _bp(is_exit_shared) if is_exit_shared is not None else None,
+                           _dp(np.ascontiguousarray(omega_a)), _ip(out))
+    return out[:n]
+
+
+def sweep_xyz(om, geom, sched, a, omega, weight, tau, STotal, Sigt, PsiA, Psi1, PsiBA, Phi, savePsi):
+    G = STotal.shape[-1]
+    lib().orc_sweep_xyz(om.ref, G, int(sched["nHyperPlanes"][a]), _ip(sched["zonesInPlane"][a]), _ip(sched["nextZ"][a]),
+                        _ip(sched["nextC"][a]), _dp(np.ascontiguousarray(omega[a])), C.c_double(weight[a]), C.c_double(tau),
+                        _dp(STotal), _dp(Sigt), _dp(geom["Volume"]), _dp(geom["A_fp"]), _dp(geom["A_ez"]),
+                        _dp(PsiA), _dp(Psi1), _dp(PsiBA), _dp(Phi), int(bool(savePsi)))
+
+
+def sweep_rz(om, geom, sched, a, q, tau, STotal, Sigt, Psi, Psi1, PsiM, PsiB, Phi, bdyList, savePsi):
+    """One SweepUCBrz call for angle index a (0-based) of quadrature dict q."""
+    G = STotal.shape[-1]
+    NA = q["omega"].shape[0]
+    setfin = bool(q["finish"][a + 1]) if a + 1 < NA + 1 else False
+    nxt = a + 1 if a + 1 < NA else a
+    lib().orc_sweep_rz(om.ref, G, int(sched["nHyperPlanes"][a]), _ip(sched["zonesInPlane"][a]), _ip(sched["nextZ"][a]),
+                       _ip(sched["nextC"][a]), _dp(np.ascontiguousarray(q["omega"][a])), C.c_double(q["weight"][a]),
+                       C.c_double(tau), C.c_double(q["angDerivFac"][a]), C.c_double(q["quadTauW1"][a]),
+                       C.c_double(q["quadTauW2"][a]), int(bool(q["start"][a])), int(setfin),
+                       _dp(STotal), _dp(Sigt), _dp(geom["Volume"]), _dp(geom["Area"]), _dp(geom["A_fp"]), _dp(geom["A_ez"]),
+                       _dp(geom["RadiusFP"]), _dp(geom["RadiusEZ"]), int(len(bdyList)), _ip(np.ascontiguousarray(bdyList, np.int32)),
+                       _dp(Psi[a]), _dp(Psi[nxt]), _dp(Psi1), _dp(PsiM), _dp(PsiB[a]), _dp(PsiB[nxt]), _dp(Phi), int(bool(savePsi)))
+
+
+def setsweep_xyz(om, geom, sched, omega, weight, tau, STotal, Sigt, Psi, PsiB, cyclePsi, savePsi, nthreads=0):
+    """SetSweep.F90 single flux pass + getPhiTotal, one angle per set, OpenMP over sets."""
+    m = om.m
+    NA = omega.shape[0]
+    G = STotal.shape[-1]
+    Phi = np.zeros((m.ncornr, G))
+    if cyclePsi is None:
+        cyclePsi = np.zeros((max(int(sched["totalCycles"]), 1), G))
+    lib().orc_setsweep_xyz(om.ref, G, NA, _ip(sched["nHyperPlanes"]), _ip(sched["zonesInPlane"]), _ip(sched["nextZ"]),
+                           _ip(sched["nextC"]), _ip(sched["numCycles"]), _ip(sched["cycleOffSet"]), _ip(sched["cycleList"]),
+                           _dp(cyclePsi), _dp(np.ascontiguousarray(omega)), _dp(np.ascontiguousarray(weight)), C.c_double(tau),
+                           _dp(STotal), _dp(Sigt), _dp(geom["Volume"]), _dp(geom["A_fp"]), _dp(geom["A_ez"]),
+                           _dp(Psi), _dp(PsiB), _dp(Phi), int(bool(savePsi)), int(nthreads))
+    return Phi
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()
+
+
+# ---------------------------------------------------------------------------
+# reference's own Planck integrator, compiled from /root/reference (oracle/_ref)
+# ---------------------------------------------------------------------------
+def planck_groups_ref(T: float, bounds: np.ndarray, k: float = 1.0, Bnorm: float = 1.0) -> np.ndarray:
+    global _NBB
+    if _NBB is None:
+        build()
+        _NBB = C.CDLL(os.path.join(_HERE, "_ref", "libnbb_ref.so"))
+    ng = len(bounds) - 1
+    B = np.zeros(ng)
+    b = np.ascontiguousarray(bounds, dtype=np.float64)
+    _NBB.NBB_integrateBlackBodyGroups(C.c_double(T), C.c_double(k), C.c_double(Bnorm), C.c_int(ng), _dp(b), _dp(B))
+    return B
