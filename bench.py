@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — Sn sweep throughput (unknowns/s = corners x angles x groups per second
+of one full ControlSweep: all angles, psi->phi reduction, psib exchange; schedule
+construction excluded) on N B200s, one mesh domain per GPU (weak scaling).
+
+  python bench.py --gpus 1 --steps K --warmup W
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the CPU path timed on the host cores
+
+Workload at N=1: BASELINE.json configs[4] per-domain size (3-D tiled mesh -d 20,20,20,
+-G 128, default product quadrature P2 A2 = 32 angles, 6.29e9 unknowns).  configs[2]
+(-P 4 -A 4, 128 angles) needs 201 GB for Psi alone and does not fit one B200.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from umt_b200 import mesh as M          # noqa: E402
+from umt_b200 import problem as PR      # noqa: E402
+
+
+def algorithmic_bytes_per_unknown(G, ndim=3, final=False):
+    """41 + 180/G (3-D, non-final sweep), 49 + 180/G with savePsi; RZ 58 + 128/G."""
+    if ndim == 3:
+        return (49.0 if final else 41.0) + 180.0 / G
+    return 58.0 + 128.0 / G
+
+
+def sweep_kernel_bytes_per_unknown(G, ndim=3):
+    """Bytes the sweep kernel itself must move: read STotal 8 + read Psi^n 8 +
+    write Psi1 8 + Sigt 8/cpz + geometry/G.  The phi tally is a separate streaming kernel."""
+    return (25.0 + 180.0 / G) if ndim == 3 else (42.0 + 128.0 / G)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            if self._stop.is_set():
+                break
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference's CPU path; the reference itself needs
+# Fortran + MPI + Conduit and cannot be built here) on a bounded sample of the workload
+# ---------------------------------------------------------------------------
+def cpu_sweep_rate(G, npolar, nazim, sample_dims, steps=1, warmup=0):
+    from oracle import oracle as O
+    from tests import common as T
+    m = M.tiled_mesh(sample_dims)
+    p = T.make_problem_3d(m, npolar, nazim, G, driver_like=True)
+    unknowns = m.ncornr * p.NA * G
+    cores = O.max_threads()
+    for _ in range(warmup):
+        T.oracle_sweep_3d(p, False, cores)
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        T.oracle_sweep_3d(p, False, cores)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return unknowns / dt, cores, dt, f"3-D tiled mesh -d {sample_dims[0]},{sample_dims[1]},{sample_dims[2]} -G {G} P{npolar} A{nazim} ({unknowns:.3e} unknowns per sweep), same problem data, one full SetSweep+getPhiTotal"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = args.cpu_dims
+    val, cores, dt, sample = cpu_sweep_rate(args.groups, args.polar, args.azimuthal, (d, d, d), steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": val, "unit": "unknowns/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "unknowns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (Fortran+MPI+Conduit) cannot be built in this image; this is the CPU restatement of SweepUCBxyz/SetSweep (oracle/), OpenMP over angle sets like SetSweep.F90:113-116",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    d = args.dims
+    return {"workload": f"BASELINE configs[4] per-domain: Blueprint 3D tiled mesh -B local -d {d},{d},{d} -G {args.groups} -P {args.polar} -A {args.azimuthal}, one domain per GPU, vacuum BCs, mini-app opacities (Sigt = 1/(c dt), STotal = 0), non-final sweep (savePsi = false)",
+            "zones_per_domain": 24 * d * d * d, "groups": args.groups, "angles": 8 * args.polar * args.azimuthal,
+            "l2_policy": "inputs (Psi 2x50 GB, STotal, Phi) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"spatial domains x{args.gpus}, psib exchange lagged one flux pass"}
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dims", type=int, default=20)
+    ap.add_argument("--groups", type=int, default=128)
+    ap.add_argument("--polar", type=int, default=2)
+    ap.add_argument("--azimuthal", type=int, default=2)
+    ap.add_argument("--cpu-dims", type=int, default=4, help="tiles per side of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from umt_b200 import teton
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    d, G = args.dims, args.groups
+    mesh = M.tiled_mesh((d, d, d), rank=rank, size=world)
+    ctx = teton.SweepContext.from_mesh(mesh, G, device=local)
+    ctx.compute_geometry(mesh.px)
+    NA = ctx.build_product_quadrature(args.polar, args.azimuthal, 1)
+    for b in mesh.boundaries:
+        if b.bc_type == M.BC_SHARED:
+            ctx.add_shared_boundary(b.neighbor, b.first_elem, b.n_elem)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(teton.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.set_comm(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    ctx.build_schedule()
+    nz, nc = mesh.nzones, mesh.ncornr
+    tau = PR.tau()
+    # pinned host buffers of what the Fortran caller hands over / gets back per ControlSweep
+    h_sigt = torch.full((nz, G), tau, dtype=torch.float64).pin_memory()
+    h_stotal = torch.zeros((nc, G), dtype=torch.float64).pin_memory()
+    h_phi = torch.empty((nc, G), dtype=torch.float64).pin_memory()
+    ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau)
+    ctx.init_teton(np.full(nz, PR.TR0), PR.group_bounds(G), PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
+    ctx.init_phi_total()
+    ctx.init_radiation_field()
+    unknowns = nc * NA * G
+    total_unknowns = unknowns * world
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident metric -----------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.sweep(False, args.flux_iters)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    sweep_ms = phi_ms = exch_ms = 0.0
+    launches = 0
+    iters = 0
+    for _ in range(args.steps):
+        iters += ctx.sweep(False, args.flux_iters)
+        tm = ctx.last_times()
+        sweep_ms += tm["sweep_ms"]; phi_ms += tm["phi_ms"]; exch_ms += tm["exchange_ms"]
+        launches += ctx.last_launches()
+    barrier()
+    wall = time.perf_counter() - t0
+    # wall clock between the two barrier+synchronize brackets; umt_sweep itself ends with an event
+    # synchronize on the library's stream, whose CUDA-event times are reported in kernel_ms
+    step_ms = max_over_ranks(wall * 1e3 / args.steps)
+    sweep_kernel_ms = max_over_ranks(sweep_ms / max(iters, 1))
+    value = total_unknowns / (step_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -----------------------------
+    h2d = h_sigt.numel() * 8 + h_stotal.numel() * 8
+    d2h = h_phi.numel() * 8
+    for _ in range(1):
+        ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau); ctx.sweep(False, args.flux_iters); ctx.download_phi(h_phi.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau)
+        ctx.sweep(False, args.flux_iters)
+        ctx.download_phi(h_phi.numpy())
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    if rank == 0:
+        sampler.stop()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        balg = sweep_kernel_bytes_per_unknown(G)
+        achieved = unknowns * balg / (sweep_kernel_ms * 1e-3) / 1e9
+        model41 = unknowns * algorithmic_bytes_per_unknown(G) / ((sweep_ms + phi_ms) / max(iters, 1) * 1e-3) / 1e9
+        line = {
+            "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": value, "unit": "unknowns/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": total_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "what": "umt_upload_state(Sigt,STotal) from pinned host + umt_sweep + umt_download_phi to pinned host"},
+            "gpu_launches": launches,
+            "flux_passes_per_step": iters / args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "sweep3d (persistent, all angles)", "bytes_per_unknown": balg, "kernel_ms": sweep_kernel_ms,
+                         "peak_source": peak_src,
+                         "whole_sweep_41B_model": {"bytes_per_unknown": algorithmic_bytes_per_unknown(G), "achieved": model41, "frac": model41 / peak}},
+            "kernel_ms": {"sweep": sweep_ms / args.steps, "phi": phi_ms / args.steps, "exchange": exch_ms / args.steps},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            cd = args.cpu_dims
+            v, cores, dt, sample = cpu_sweep_rate(G, args.polar, args.azimuthal, (cd, cd, cd), steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": v, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample + f", {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/*
+ * umt_sweep.h — C ABI of libumtsweep.so, the B200-native Sn sweep library.
+ *
+ * Drop-in seam: Teton's sweep dispatch rt/ControlSweep.F90:55-73
+ * (`useCUDASweep .and. .not. useGPU` => SetSweep_CUDA + getPhiTotal).  The
+ * reference's own C seam there is gpu_sweepucbxyz / gpu_streamsynchronize /
+ * gpu_devicesynchronize (gpu/GPU_SweepUCBxyz.cu:520-572, Fortran interface
+ * gpu/SweepUCBxyzToGPU.F90:30-91), a per-(set,angle) call that re-uploads every
+ * array.  This header replaces it with a context API whose state lives on the
+ * device; `umt_sweep` is one whole SetSweep + getPhiTotal.
+ *
+ * Conventions (same as Teton's Fortran callers, the BIND(C) routines in aux/):
+ *   - arrays are flat, column-major images of the Fortran arrays named in the
+ *     comments, group index fastest; integer ids inside arrays are 1-based;
+ *   - scalar arguments are passed by value here (the Fortran glue in
+ *     umt_b200/fortran/teton_b200_mod.F90 uses VALUE);
+ *   - every function returns 0 on success, non-zero on failure and never aborts
+ *     (the reference aborts through f90fatal/MPI_Abort, misc/f90errors.F90:40-68;
+ *     the Fortran glue maps non-zero to f90fatal).  umt_last_error() gives text.
+ *   - a context is used by one host thread at a time; contexts are independent.
+ */
+#ifndef UMT_SWEEP_H
+#define UMT_SWEEP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct umt_ctx umt_ctx;
+
+enum { UMT_OK = 0, UMT_ERR_ARG = 1, UMT_ERR_CUDA = 2, UMT_ERR_STATE = 3, UMT_ERR_NCCL = 4, UMT_ERR_SCHEDULE = 5 };
+
+/* ---- life cycle ------------------------------------------------------- */
+/* Sizes as in mods/Size_mod.F90:19-80 (ndim, nzones, ncornr, nbelem, maxcf,
+   maxCorner, ngr).  device = CUDA ordinal; fails (UMT_ERR_CUDA) without a GPU.
+   device = -1 makes a host-only context that can build quadratures and sweep
+   schedules (pure host work) but refuses every call that needs a kernel. */
+int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int nbelem,
+                   int maxcf, int maxCorner, int ngr, umt_ctx **ctx);
+int umt_ctx_destroy(umt_ctx *ctx);
+const char *umt_last_error(const umt_ctx *ctx); /* ctx may be NULL: last create error */
+const char *umt_version(void);
+
+/* ---- mesh connectivity: mods/Geometry_mod.F90:19-78, aux/setTetonZone.F90 ---- */
+/* numCorner(nz), cOffSet(nz), nCFacesArray(nc), cFP(maxcf,nc), cEZ(maxcf,nc).
+   The remaining arrays are only needed by umt_build_schedule / umt_compute_geometry
+   and may be NULL otherwise: zoneFaces(nz), zoneOpp(maxFaces,nz), faceOpp(maxFaces,nz),
+   CToFace(maxcf,nc), BoundaryZone(nz) (bytes), BdyToC(nbelem). */
+int umt_set_connectivity(umt_ctx *ctx, const int *numCorner, const int *cOffSet,
+                         const int *nCFacesArray, const int *cFP, const int *cEZ,
+                         int maxFaces, const int *zoneFaces, const int *zoneOpp,
+                         const int *faceOpp, const int *CToFace,
+                         const unsigned char *BoundaryZone, const int *BdyToC);
+
+/* ---- geometry: rt/geometryUCBxyz.F90, rt/geometryUCBrz.F90 ------------- */
+/* Upload Teton's own arrays: Volume(nc), A_fp(ndim,maxcf,nc), A_ez(ndim,maxcf,nc);
+   RZ only: Area(nc), RadiusFP(2,nc), RadiusEZ(2,nc); A_bdy(ndim,nbelem) optional
+   (needed by umt_build_schedule's exit lists and the exchange tallies). */
+int umt_set_geometry(umt_ctx *ctx, const double *Volume, const double *A_fp, const double *A_ez,
+                     const double *Area, const double *RadiusFP, const double *RadiusEZ,
+                     const double *A_bdy);
+/* ...or compute them on the device from corner coordinates px(ndim,nc)
+   (replaces getGeometry, control/initializeSets.F90:85). */
+int umt_compute_geometry(umt_ctx *ctx, const double *px);
+int umt_download_geometry(umt_ctx *ctx, double *Volume, double *A_fp, double *A_ez,
+                          double *Area, double *RadiusFP, double *RadiusEZ, double *A_bdy,
+                          double *VolumeZone);
+
+/* ---- quadrature: mods/AngleSet_mod.F90:34-125, rt/rtquad.F90 ------------ */
+/* omega(ndim,NA), weight(NA); RZ only: StartingDirection(NA), FinishingDirection(NA)
+   (bytes), angDerivFac/quadTauW1/quadTauW2(NA). */
+int umt_set_quadrature(umt_ctx *ctx, int nAngles, const double *omega, const double *weight,
+                       const unsigned char *startingDirection, const unsigned char *finishingDirection,
+                       const double *angDerivFac, const double *quadTauW1, const double *quadTauW2);
+/* Build the product quadrature (rt/quadProduct.F90 | rt/quadrz.F90 product branch +
+   rt/rtquad.F90 normalisation + rt/AngleCoef2D.F90) and install it.  Returns the
+   number of angles through *nAngles (3-D: 8*P*A, RZ: 4*P*(A+1)). */
+int umt_build_product_quadrature(umt_ctx *ctx, int npolar, int nazimuthal, int polaraxis, int *nAngles);
+int umt_get_quadrature(umt_ctx *ctx, double *omega, double *weight);
+
+/* ---- sweep schedule: snac/snnext.F90, mods/AngleSet_mod.F90 HypPlane/BdyExit ---- */
+/* Install Teton's schedule for one angle (1-based `angle`): nHyperPlanes,
+   zonesInPlane(nHyp), nextZ(nz) signed, nextC(nc), numCycles + cycleList(numCycles)
+   (global corner ids), exit list bdyList(2,nxBdy) (RZ sweeps and radiation-field init). */
+int umt_set_schedule(umt_ctx *ctx, int angle, int nHyperPlanes, const int *zonesInPlane,
+                     const int *nextZ, const int *nextC, int numCycles, const int *cycleList,
+                     int nxBdy, const int *bdyList);
+/* ...or let the library do rtorder/snnext/findexit on the host for every angle. */
+int umt_build_schedule(umt_ctx *ctx);
+int umt_get_schedule_info(umt_ctx *ctx, int angle, int *nHyperPlanes, int *numCycles, int *nBadZones);
+int umt_get_schedule(umt_ctx *ctx, int angle, int *zonesInPlane, int *nextZ, int *nextC, int *cycleList);
+
+/* ---- state: mods/SetData_mod.F90:13-73, mods/GroupSet_mod.F90:16-27 ------ */
+/* Whole-problem upload: Psi(ngr,nc,NA), PsiB(ngr,nb,NA), Sigt(ngr,nz), STotal(ngr,nc).
+   Any pointer may be NULL to leave that array untouched. */
+int umt_upload_state(umt_ctx *ctx, const double *Psi, const double *PsiB, const double *Sigt,
+                     const double *STotal, double tau);
+/* Per phase-space-set upload/download (Set%Psi(Groups,nc,NumAngles), Set%PsiB(Groups,nb,NumAngles)
+   with Set%g0, Set%angle0 0-based offsets). */
+int umt_upload_set(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles,
+                   const double *Psi, const double *PsiB);
+int umt_download_set(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles,
+                     double *Psi, double *PsiB);
+int umt_download_psi(umt_ctx *ctx, double *Psi);
+int umt_download_psib(umt_ctx *ctx, double *PsiB);
+int umt_download_phi(umt_ctx *ctx, double *PhiTotal); /* Rad%PhiTotal(ngr,nc) */
+
+/* Planck group integrals B_g(T) (misc/NormalizedBlackBody.cc:151-186, Clark 1987); pure host. */
+int umt_planck_groups(double T, double k, double Bnorm, int numGroups, const double *groupBounds, double *B);
+/* aux/InitTeton.F90:82-118: Psi(g,c,a) = max(wtiso*B_g(Trz(zone)), efloor) for every angle,
+   built on the device from the zone radiation temperatures Trz(nz) and group bounds gnu(ngr+1). */
+int umt_init_teton(umt_ctx *ctx, const double *Trz, const double *groupBounds, double speedLight,
+                   double radConstant, double wtiso, double efloor);
+
+/* control/initPhiTotal_OMPOL.F90 (Psi *= VolumeOld/Volume when volRatio != NULL, PhiTotal = sum w Psi)
+   and control/initializeRadiationField_OMPOL.F90:116-143 (exit PsiB <- Psi, cyclePsi <- Psi). */
+int umt_init_phi_total(umt_ctx *ctx, const double *volRatio);
+int umt_init_radiation_field(umt_ctx *ctx);
+
+/* ---- the hot path: rt/ControlSweep.F90:15-81 = SetSweep + getPhiTotal ---- */
+/* maxFluxIters / fluxTol: incidentFlux iteration control (SetSweep.F90:81-207,
+   rt/testFluxConv.F90:55-59).  *itersDone returns the number of flux passes. */
+int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone);
+/* Device time of the kernels of the last umt_sweep, in ms: [0] sweep kernel(s),
+   [1] psi->phi reduction, [2] exchange (pack/NCCL/unpack), [3] whole call. */
+int umt_last_sweep_times(umt_ctx *ctx, double *ms4);
+int umt_last_sweep_launches(umt_ctx *ctx, int *nLaunches);
+int umt_synchronize(umt_ctx *ctx);
+
+/* ---- domain decomposition: rt/findexit.F90:102-294, rt/SendFlux.F90, rt/RecvFlux.F90 ---- */
+/* One call per shared boundary (neighbour): its boundary elements are
+   firstBdyElem..firstBdyElem+nBdyElem-1 (1-based), matched element-by-element with
+   the neighbour's list (aux/checkSharedBoundary.F90). */
+int umt_add_shared_boundary(umt_ctx *ctx, int neighborRank, int firstBdyElem, int nBdyElem);
+/* myRank/nRanks and a 128-byte ncclUniqueId (same on all ranks; rank 0 gets it from
+   umt_nccl_unique_id).  NCCL is dlopen'ed; fails with UMT_ERR_NCCL if absent. */
+int umt_nccl_unique_id(unsigned char *id128);
+int umt_set_comm(umt_ctx *ctx, int myRank, int nRanks, const unsigned char *id128);
+
+/* ---- grey transport acceleration: snac/GTASweep.F90, snac/SweepGreyUCBxyz.F90 ---- */
+int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, const double *GreySigScat,
+                        const double *GreySigScatVol);
+int umt_gta_sweep(umt_ctx *ctx, const double *P, const double *GreySource, double *PsiB_gta,
+                  double *PhiInc, int withSource);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMT_SWEEP_H */

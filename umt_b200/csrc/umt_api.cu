@@ -1,0 +1,646 @@
+// Host side of the C ABI (include/umt_sweep.h): context, residency of Teton's
+// arrays in HBM, schedule -> work-item translation, the SetSweep/ControlSweep
+// controller, and the small streaming kernels around the sweep.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "umt_internal.h"
+
+static std::string g_create_error;
+
+extern "C" const char *umt_version(void) { return "umt_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char *umt_last_error(const umt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+#define NEED_DEVICE(ctx, what) do { if ((ctx)->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, what ": host-only context (device -1) cannot run kernels"); } while (0)
+
+template <class T>
+static int dev_alloc_copy(umt_ctx *ctx, T **dptr, const T *h, size_t n) {
+  if (ctx->device < 0) return UMT_OK;
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  if (n == 0) n = 1;
+  UMT_CUDA(ctx, cudaMalloc((void **)dptr, n * sizeof(T)));
+  if (h) UMT_CUDA(ctx, cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return UMT_OK;
+}
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int nbelem, int maxcf, int maxCorner,
+                              int ngr, umt_ctx **out) {
+  if (!out) return UMT_ERR_ARG;
+  *out = nullptr;
+  if (ndim < 2 || ndim > 3 || nzones < 1 || ncornr < 1 || nbelem < 0 || ngr < 1 || maxcf != ndim || maxCorner < 1) {
+    g_create_error = "umt_ctx_create: bad sizes";
+    return UMT_ERR_ARG;
+  }
+  if (device == -1) {   // host-only context: schedule / quadrature construction, no kernels
+    umt_ctx *hc = new umt_ctx;
+    hc->device = -1; hc->ndim = ndim; hc->nz = nzones; hc->nc = ncornr; hc->nb = nbelem;
+    hc->maxcf = maxcf; hc->maxCorner = maxCorner; hc->G = ngr;
+    *out = hc;
+    return UMT_OK;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_error = std::string("umt_ctx_create: no usable CUDA device (") + cudaGetErrorString(e) + ")";
+    return UMT_ERR_CUDA;
+  }
+  umt_ctx *ctx = new umt_ctx;
+  ctx->device = device; ctx->ndim = ndim; ctx->nz = nzones; ctx->nc = ncornr; ctx->nb = nbelem;
+  ctx->maxcf = maxcf; ctx->maxCorner = maxCorner; ctx->G = ngr;
+  e = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("umt_ctx_create: ") + cudaGetErrorString(e);
+    delete ctx;
+    return UMT_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return UMT_OK;
+}
+
+extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
+  if (!ctx) return UMT_OK;
+  if (ctx->device < 0) { delete ctx; return UMT_OK; }
+  cudaSetDevice(ctx->device);
+  void *ptrs[] = {ctx->d_numCorner, ctx->d_cOffSet, ctx->d_nCFaces, ctx->d_cFP, ctx->d_cEZ, ctx->d_Volume, ctx->d_Afp,
+                  ctx->d_Aez, ctx->d_Area, ctx->d_RadiusFP, ctx->d_RadiusEZ, ctx->d_omega, ctx->d_weight, ctx->d_nextZ,
+                  ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
+                  ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_psib, ctx->d_stotal,
+                  ctx->d_sigt, ctx->d_phi, ctx->d_psim};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  for (auto &s : ctx->shared) {
+    if (s.d_send_idx) cudaFree(s.d_send_idx);
+    if (s.d_recv_idx) cudaFree(s.d_recv_idx);
+    if (s.d_sendbuf) cudaFree(s.d_sendbuf);
+    if (s.d_recvbuf) cudaFree(s.d_recvbuf);
+  }
+  for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  delete ctx;
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// connectivity / geometry / quadrature
+// ---------------------------------------------------------------------------
+extern "C" int umt_set_connectivity(umt_ctx *ctx, const int *numCorner, const int *cOffSet, const int *nCFaces,
+                                    const int *cFP, const int *cEZ, int maxFaces, const int *zoneFaces,
+                                    const int *zoneOpp, const int *faceOpp, const int *CToFace,
+                                    const unsigned char *BoundaryZone, const int *BdyToC) {
+  if (!ctx || !numCorner || !cOffSet || !nCFaces || !cFP || !cEZ) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int nz = ctx->nz, nc = ctx->nc, mcf = ctx->maxcf;
+  ctx->h_numCorner.assign(numCorner, numCorner + nz);
+  ctx->h_cOffSet.assign(cOffSet, cOffSet + nz);
+  ctx->h_nCFaces.assign(nCFaces, nCFaces + nc);
+  ctx->h_cFP.assign(cFP, cFP + (size_t)mcf * nc);
+  ctx->h_cEZ.assign(cEZ, cEZ + (size_t)mcf * nc);
+  for (int z = 0; z < nz; z++) {
+    if (numCorner[z] < 1 || numCorner[z] > ctx->maxCorner || cOffSet[z] < 0 || cOffSet[z] + numCorner[z] > nc)
+      UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_connectivity: zone %d has bad numCorner/cOffSet", z + 1);
+  }
+  std::vector<int> fp0((size_t)mcf * nc), ez0((size_t)mcf * nc);
+  for (size_t i = 0; i < fp0.size(); i++) {
+    const int v = cFP[i], f = (int)(i % mcf), c = (int)(i / mcf);
+    if (f < nCFaces[c]) {
+      if (v < 1 || v > nc + ctx->nb) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_connectivity: cFP(%d,%d)=%d out of range", f + 1, c + 1, v);
+      if (cEZ[i] < 1 || cEZ[i] > ctx->maxCorner) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_connectivity: cEZ(%d,%d)=%d out of range", f + 1, c + 1, cEZ[i]);
+    }
+    fp0[i] = v - 1;
+    ez0[i] = cEZ[i] - 1;
+  }
+  TRY(dev_alloc_copy(ctx, &ctx->d_numCorner, numCorner, nz));
+  TRY(dev_alloc_copy(ctx, &ctx->d_cOffSet, cOffSet, nz));
+  TRY(dev_alloc_copy(ctx, &ctx->d_nCFaces, nCFaces, nc));
+  TRY(dev_alloc_copy(ctx, &ctx->d_cFP, fp0.data(), fp0.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_cEZ, ez0.data(), ez0.size()));
+  ctx->maxFaces = maxFaces;
+  if (zoneFaces && zoneOpp && faceOpp && CToFace) {
+    ctx->h_zoneFaces.assign(zoneFaces, zoneFaces + nz);
+    ctx->h_zoneOpp.assign(zoneOpp, zoneOpp + (size_t)maxFaces * nz);
+    ctx->h_faceOpp.assign(faceOpp, faceOpp + (size_t)maxFaces * nz);
+    ctx->h_CToFace.assign(CToFace, CToFace + (size_t)mcf * nc);
+  }
+  if (BoundaryZone) ctx->h_BoundaryZone.assign(BoundaryZone, BoundaryZone + nz);
+  if (BdyToC) ctx->h_BdyToC.assign(BdyToC, BdyToC + ctx->nb);
+  ctx->have_conn = true;
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+extern "C" int umt_set_geometry(umt_ctx *ctx, const double *Volume, const double *A_fp, const double *A_ez,
+                                const double *Area, const double *RadiusFP, const double *RadiusEZ, const double *A_bdy) {
+  if (!ctx || !Volume || !A_fp || !A_ez) return UMT_ERR_ARG;
+  if (ctx->ndim == 2 && (!Area || !RadiusFP || !RadiusEZ)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_geometry: RZ needs Area, RadiusFP, RadiusEZ");
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t nc = ctx->nc, nA = (size_t)ctx->ndim * ctx->maxcf * nc;
+  ctx->h_Volume.assign(Volume, Volume + nc);
+  ctx->h_Afp.assign(A_fp, A_fp + nA);
+  ctx->h_Aez.assign(A_ez, A_ez + nA);
+  TRY(dev_alloc_copy(ctx, &ctx->d_Volume, Volume, nc));
+  TRY(dev_alloc_copy(ctx, &ctx->d_Afp, A_fp, nA));
+  TRY(dev_alloc_copy(ctx, &ctx->d_Aez, A_ez, nA));
+  if (ctx->ndim == 2) {
+    ctx->h_Area.assign(Area, Area + nc);
+    ctx->h_RadiusFP.assign(RadiusFP, RadiusFP + 2 * nc);
+    ctx->h_RadiusEZ.assign(RadiusEZ, RadiusEZ + 2 * nc);
+    TRY(dev_alloc_copy(ctx, &ctx->d_Area, Area, nc));
+    TRY(dev_alloc_copy(ctx, &ctx->d_RadiusFP, RadiusFP, 2 * nc));
+    TRY(dev_alloc_copy(ctx, &ctx->d_RadiusEZ, RadiusEZ, 2 * nc));
+  }
+  if (A_bdy) { ctx->h_Abdy.assign(A_bdy, A_bdy + (size_t)ctx->ndim * ctx->nb); ctx->have_abdy = true; }
+  ctx->have_geom = true;
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+extern "C" int umt_set_quadrature(umt_ctx *ctx, int nAngles, const double *omega, const double *weight,
+                                  const unsigned char *start, const unsigned char *finish, const double *angDerivFac,
+                                  const double *w1, const double *w2) {
+  if (!ctx || nAngles < 1 || !omega || !weight) return UMT_ERR_ARG;
+  if (ctx->ndim == 2 && (!start || !finish || !angDerivFac || !w1 || !w2))
+    UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_quadrature: RZ needs starting/finishing flags and angular-derivative coefficients");
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->NA != nAngles && ctx->d_psi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_quadrature: angle count changed after state upload");
+  ctx->NA = nAngles;
+  ctx->h_omega.assign(omega, omega + (size_t)ctx->ndim * nAngles);
+  ctx->h_weight.assign(weight, weight + nAngles);
+  ctx->h_start.assign(nAngles, 0);
+  ctx->h_finish.assign(nAngles + 1, 0);
+  if (ctx->ndim == 2) {
+    ctx->h_start.assign(start, start + nAngles);
+    std::copy(finish, finish + nAngles, ctx->h_finish.begin());
+    ctx->h_angDerivFac.assign(angDerivFac, angDerivFac + nAngles);
+    ctx->h_tauW1.assign(w1, w1 + nAngles);
+    ctx->h_tauW2.assign(w2, w2 + nAngles);
+  }
+  TRY(dev_alloc_copy(ctx, &ctx->d_omega, omega, (size_t)ctx->ndim * nAngles));
+  TRY(dev_alloc_copy(ctx, &ctx->d_weight, weight, nAngles));
+  ctx->nHyp.assign(nAngles, 0); ctx->numCycles.assign(nAngles, 0); ctx->cycleOffSet.assign(nAngles, 0); ctx->nBad.assign(nAngles, 0);
+  ctx->zonesInPlane.assign(nAngles, {}); ctx->nextZ.assign(nAngles, {}); ctx->nextC.assign(nAngles, {});
+  ctx->cycleList.assign(nAngles, {}); ctx->bdyList.assign(nAngles, {});
+  ctx->have_quad = true;
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+extern "C" int umt_build_product_quadrature(umt_ctx *ctx, int npolar, int nazimuthal, int polaraxis, int *nAngles) {
+  if (!ctx) return UMT_ERR_ARG;
+  std::vector<double> om, w, adf, w1, w2;
+  std::vector<unsigned char> st, fi;
+  int r = umt_host_product_quadrature(ctx->ndim, npolar, nazimuthal, polaraxis, om, w, st, fi, adf, w1, w2);
+  if (r) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_build_product_quadrature: npolar, nazimuthal must be in 1..32, polaraxis in 1..3");
+  const int NA = (int)w.size();
+  if (nAngles) *nAngles = NA;
+  return umt_set_quadrature(ctx, NA, om.data(), w.data(), st.data(), fi.data(), adf.data(), w1.data(), w2.data());
+}
+
+extern "C" int umt_get_quadrature(umt_ctx *ctx, double *omega, double *weight) {
+  if (!ctx || !ctx->have_quad) return UMT_ERR_STATE;
+  if (omega) std::copy(ctx->h_omega.begin(), ctx->h_omega.end(), omega);
+  if (weight) std::copy(ctx->h_weight.begin(), ctx->h_weight.end(), weight);
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// schedule
+// ---------------------------------------------------------------------------
+extern "C" int umt_set_schedule(umt_ctx *ctx, int angle, int nHyperPlanes, const int *zonesInPlane, const int *nextZ,
+                                const int *nextC, int numCycles, const int *cycleList, int nxBdy, const int *bdyList) {
+  if (!ctx || !ctx->have_quad) return UMT_ERR_STATE;
+  if (angle < 1 || angle > ctx->NA || nHyperPlanes < 0 || numCycles < 0 || nxBdy < 0) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_schedule: bad argument");
+  const int a = angle - 1;
+  long total = 0;
+  for (int p = 0; p < nHyperPlanes; p++) total += zonesInPlane[p];
+  if (nHyperPlanes > 0 && total != ctx->nz) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "umt_set_schedule: angle %d planes hold %ld zones, expected %d", angle, total, ctx->nz);
+  ctx->nHyp[a] = nHyperPlanes;
+  ctx->zonesInPlane[a].assign(zonesInPlane, zonesInPlane + nHyperPlanes);
+  if (nHyperPlanes > 0) {
+    ctx->nextZ[a].assign(nextZ, nextZ + ctx->nz);
+    ctx->nextC[a].assign(nextC, nextC + ctx->nc);
+    int bad = 0;
+    for (int i = 0; i < ctx->nz; i++) {
+      int z = nextZ[i];
+      if (z == 0 || std::abs(z) > ctx->nz) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "umt_set_schedule: nextZ(%d,%d)=%d out of range", i + 1, angle, z);
+      bad += z < 0;
+    }
+    ctx->nBad[a] = bad;
+  } else {
+    ctx->nextZ[a].clear(); ctx->nextC[a].clear(); ctx->nBad[a] = 0;
+  }
+  ctx->numCycles[a] = numCycles;
+  ctx->cycleList[a].assign(cycleList, cycleList + numCycles);
+  ctx->bdyList[a].assign(bdyList, bdyList + 2 * (size_t)nxBdy);
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+extern "C" int umt_build_schedule(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (!ctx->have_conn || !ctx->have_geom || !ctx->have_quad || ctx->h_zoneOpp.empty())
+    UMT_FAIL(ctx, UMT_ERR_STATE, "umt_build_schedule: needs full connectivity (zoneOpp, faceOpp, CToFace), geometry and quadrature");
+  return umt_host_build_schedule(ctx);
+}
+
+extern "C" int umt_get_schedule_info(umt_ctx *ctx, int angle, int *nHyperPlanes, int *numCycles, int *nBadZones) {
+  if (!ctx || angle < 1 || angle > ctx->NA) return UMT_ERR_ARG;
+  if (nHyperPlanes) *nHyperPlanes = ctx->nHyp[angle - 1];
+  if (numCycles) *numCycles = ctx->numCycles[angle - 1];
+  if (nBadZones) *nBadZones = ctx->nBad[angle - 1];
+  return UMT_OK;
+}
+
+extern "C" int umt_get_schedule(umt_ctx *ctx, int angle, int *zonesInPlane, int *nextZ, int *nextC, int *cycleList) {
+  if (!ctx || angle < 1 || angle > ctx->NA) return UMT_ERR_ARG;
+  const int a = angle - 1;
+  if (zonesInPlane) std::copy(ctx->zonesInPlane[a].begin(), ctx->zonesInPlane[a].end(), zonesInPlane);
+  if (nextZ) std::copy(ctx->nextZ[a].begin(), ctx->nextZ[a].end(), nextZ);
+  if (nextC) std::copy(ctx->nextC[a].begin(), ctx->nextC[a].end(), nextC);
+  if (cycleList) std::copy(ctx->cycleList[a].begin(), ctx->cycleList[a].end(), cycleList);
+  return UMT_OK;
+}
+
+// Translate the per-angle hyperplane lists into the device work-item list.
+static int finalize_schedule(umt_ctx *ctx) {
+  if (!ctx->sched_dirty) return UMT_OK;
+  const int NA = ctx->NA, nz = ctx->nz, nc = ctx->nc;
+  int maxHyp = 0;
+  for (int a = 0; a < NA; a++) maxHyp = std::max(maxHyp, ctx->nHyp[a]);
+  if (maxHyp == 0) UMT_FAIL(ctx, UMT_ERR_STATE, "no sweep schedule installed (umt_set_schedule / umt_build_schedule)");
+  ctx->maxHyp = maxHyp;
+  std::vector<int> h_nextZ((size_t)NA * nz, 1);
+  std::vector<unsigned char> h_nextC((size_t)NA * nc, 0);
+  for (int a = 0; a < NA; a++) {
+    if (ctx->nHyp[a] == 0) continue;
+    std::copy(ctx->nextZ[a].begin(), ctx->nextZ[a].end(), h_nextZ.begin() + (size_t)a * nz);
+    for (int i = 0; i < nc; i++) {
+      int v = ctx->nextC[a][i];
+      if (v < 1 || v > ctx->maxCorner) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "nextC(%d,%d)=%d out of range", i + 1, a + 1, v);
+      h_nextC[(size_t)a * nc + i] = (unsigned char)(v - 1);
+    }
+  }
+  // work items: plane-major, angle-minor.  RZ angles of one xi-level are chained
+  // (PsiM dependency, SweepUCBrz.F90:212-240) so RZ uses a separate launcher.
+  int pairs_target = 512;
+  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairs_target = std::max(1, atoi(e));
+  const int zpi = std::max(1, pairs_target / ctx->G);
+  std::vector<WorkItem> items;
+  std::vector<std::vector<int>> nItemsPlane(NA);
+  std::vector<std::vector<int>> planeStart(NA);
+  for (int a = 0; a < NA; a++) {
+    nItemsPlane[a].resize(ctx->nHyp[a]);
+    planeStart[a].resize(ctx->nHyp[a] + 1, 0);
+    for (int p = 0; p < ctx->nHyp[a]; p++) {
+      planeStart[a][p + 1] = planeStart[a][p] + ctx->zonesInPlane[a][p];
+      nItemsPlane[a][p] = (ctx->zonesInPlane[a][p] + zpi - 1) / zpi;
+    }
+  }
+  for (int p = 0; p < maxHyp; p++)
+    for (int a = 0; a < NA; a++) {
+      if (p >= ctx->nHyp[a]) continue;
+      const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
+      for (int k = 0; k < nItemsPlane[a][p]; k++) {
+        WorkItem w;
+        w.angle = a;
+        w.zbeg = z0 + k * zpi;
+        w.zend = std::min(z0 + n, w.zbeg + zpi);
+        w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
+        w.wait_count = p > 0 ? nItemsPlane[a][p - 1] : 0;
+        w.signal_idx = a * maxHyp + p;
+        w.pad0 = w.pad1 = 0;
+        items.push_back(w);
+      }
+    }
+  ctx->nItems = (int)items.size();
+  ctx->nCounters = NA * maxHyp;
+  TRY(dev_alloc_copy(ctx, &ctx->d_nextZ, h_nextZ.data(), h_nextZ.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_nextC, h_nextC.data(), h_nextC.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_items, items.data(), items.size()));
+  TRY(dev_alloc_copy<int>(ctx, &ctx->d_counters, nullptr, 1 + (size_t)ctx->nCounters));
+  // cycle lists (control/constructDynMemory.F90:56-213)
+  std::vector<int> cl, ca;
+  int off = 0;
+  for (int a = 0; a < NA; a++) {
+    ctx->cycleOffSet[a] = off;
+    for (int v : ctx->cycleList[a]) {
+      if (v < 1 || v > nc) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "cycleList entry %d out of range (angle %d)", v, a + 1);
+      cl.push_back(v - 1); ca.push_back(a);
+    }
+    off += ctx->numCycles[a];
+  }
+  const bool cyclesChanged = off != ctx->totalCycles || !ctx->d_cyclePsi;
+  ctx->totalCycles = off;
+  TRY(dev_alloc_copy(ctx, &ctx->d_cycleList, cl.data(), cl.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_cycleAngle, ca.data(), ca.size()));
+  if (cyclesChanged) {
+    TRY(dev_alloc_copy<double>(ctx, &ctx->d_cyclePsi, nullptr, (size_t)std::max(off, 1) * ctx->G));
+    UMT_CUDA(ctx, cudaMemset(ctx->d_cyclePsi, 0, sizeof(double) * (size_t)std::max(off, 1) * ctx->G));
+  }
+  // exit lists (AngleSet BdyExit, rt/findexit.F90:296-349)
+  std::vector<int> eb, ec, ea;
+  ctx->exitOff.assign(NA + 1, 0);
+  for (int a = 0; a < NA; a++) {
+    const auto &bl = ctx->bdyList[a];
+    for (size_t i = 0; i + 1 < bl.size(); i += 2) {
+      if (bl[i] < 1 || bl[i] > ctx->nb || bl[i + 1] < 1 || bl[i + 1] > nc) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "bdyList entry out of range (angle %d)", a + 1);
+      eb.push_back(bl[i] - 1); ec.push_back(bl[i + 1] - 1); ea.push_back(a);
+    }
+    ctx->exitOff[a + 1] = (int)eb.size();
+  }
+  ctx->nExit = (int)eb.size();
+  TRY(dev_alloc_copy(ctx, &ctx->d_exitB, eb.data(), eb.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_exitC, ec.data(), ec.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_exitA, ea.data(), ea.size()));
+  ctx->sched_dirty = false;
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------
+static int ensure_state(umt_ctx *ctx) {
+  NEED_DEVICE(ctx, "device state");
+  if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "set the quadrature before uploading state");
+  if (ctx->d_psi) return UMT_OK;
+  const size_t G = ctx->G, nc = ctx->nc, nb = std::max(ctx->nb, 1), NA = ctx->NA;
+  ctx->psi_elems = G * nc * NA;
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi, sizeof(double) * ctx->psi_elems));
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi1, sizeof(double) * ctx->psi_elems));
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psib, sizeof(double) * G * nb * NA));
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_stotal, sizeof(double) * G * nc));
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_sigt, sizeof(double) * G * ctx->nz));
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_phi, sizeof(double) * G * nc));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_psi, 0, sizeof(double) * ctx->psi_elems));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_psi1, 0, sizeof(double) * ctx->psi_elems));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_psib, 0, sizeof(double) * G * nb * NA));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_stotal, 0, sizeof(double) * G * nc));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_sigt, 0, sizeof(double) * G * ctx->nz));
+  UMT_CUDA(ctx, cudaMemset(ctx->d_phi, 0, sizeof(double) * G * nc));
+  if (ctx->ndim == 2) {
+    UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psim, sizeof(double) * G * nc * NA));
+    UMT_CUDA(ctx, cudaMemset(ctx->d_psim, 0, sizeof(double) * G * nc * NA));
+  }
+  return UMT_OK;
+}
+
+extern "C" int umt_upload_state(umt_ctx *ctx, const double *Psi, const double *PsiB, const double *Sigt,
+                                const double *STotal, double tau) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb, NA = ctx->NA;
+  if (Psi) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_psi, Psi, sizeof(double) * G * nc * NA, cudaMemcpyHostToDevice, ctx->stream));
+  if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_psib, PsiB, sizeof(double) * G * nb * NA, cudaMemcpyHostToDevice, ctx->stream));
+  if (Sigt) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt, sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, ctx->stream));
+  if (STotal) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal, sizeof(double) * G * nc, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tau = tau;
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+static int set_copy(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles, double *Psi, double *PsiB, bool up) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  if (g0 < 0 || Groups < 1 || g0 + Groups > ctx->G || angle0 < 0 || NumAngles < 1 || angle0 + NumAngles > ctx->NA)
+    UMT_FAIL(ctx, UMT_ERR_ARG, "phase-space set (g0=%d,Groups=%d,angle0=%d,NumAngles=%d) outside problem", g0, Groups, angle0, NumAngles);
+  const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb;
+  const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  for (int a = 0; a < NumAngles; a++) {
+    if (Psi) {
+      double *d = ctx->d_psi + ((size_t)(angle0 + a) * nc) * G + g0, *h = Psi + (size_t)a * nc * Groups;
+      if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
+      else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
+    }
+    if (PsiB && nb) {
+      double *d = ctx->d_psib + ((size_t)(angle0 + a) * nb) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
+      if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
+      else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
+    }
+  }
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+extern "C" int umt_upload_set(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles, const double *Psi, const double *PsiB) {
+  return set_copy(ctx, g0, Groups, angle0, NumAngles, const_cast<double *>(Psi), const_cast<double *>(PsiB), true);
+}
+extern "C" int umt_download_set(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles, double *Psi, double *PsiB) {
+  return set_copy(ctx, g0, Groups, angle0, NumAngles, Psi, PsiB, false);
+}
+
+static int download(umt_ctx *ctx, double *h, const double *d, size_t n) {
+  if (!ctx || !h) return UMT_ERR_ARG;
+  NEED_DEVICE(ctx, "download");
+  if (!d) UMT_FAIL(ctx, UMT_ERR_STATE, "no device state to download");
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+extern "C" int umt_download_psi(umt_ctx *ctx, double *Psi) { return download(ctx, Psi, ctx ? ctx->d_psi : nullptr, ctx ? ctx->psi_elems : 0); }
+extern "C" int umt_download_psib(umt_ctx *ctx, double *PsiB) { return download(ctx, PsiB, ctx ? ctx->d_psib : nullptr, ctx ? (size_t)ctx->G * ctx->nb * ctx->NA : 0); }
+extern "C" int umt_download_phi(umt_ctx *ctx, double *Phi) { return download(ctx, Phi, ctx ? ctx->d_phi : nullptr, ctx ? (size_t)ctx->G * ctx->nc : 0); }
+
+extern "C" int umt_synchronize(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  NEED_DEVICE(ctx, "umt_synchronize");
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// streaming kernels around the sweep
+// ---------------------------------------------------------------------------
+// psi -> phi: PhiTotal(g,c) = sum_a w_a Psi1(g,c,a) in fixed angle order
+// (control/getPhiTotal_OMPOL.F90:134-160 + SweepUCBxyz.F90:270).  One thread per
+// pair of groups; every angle slab is read once, coalesced, 16 bytes per thread.
+__global__ void __launch_bounds__(256) phi_reduce_kernel(const double *__restrict__ psi, const double *__restrict__ w,
+                                                         const unsigned char *__restrict__ skip, double *__restrict__ phi,
+                                                         size_t n, int NA, double *__restrict__ psi_scale /* optional (nc) */, int G) {
+  const size_t i2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i2 >= n) return;
+  if (i2 + 1 < n) {
+    double2 s = make_double2(0.0, 0.0);
+    for (int a = 0; a < NA; a++) {
+      if (skip && skip[a]) continue;
+      const double2 v = __ldcs(reinterpret_cast<const double2 *>(psi + (size_t)a * n + i2));
+      const double wa = w[a];
+      s.x = s.x + wa * v.x;
+      s.y = s.y + wa * v.y;
+    }
+    *reinterpret_cast<double2 *>(phi + i2) = s;
+  } else {
+    double s = 0.0;
+    for (int a = 0; a < NA; a++) {
+      if (skip && skip[a]) continue;
+      s = s + w[a] * psi[(size_t)a * n + i2];
+    }
+    phi[i2] = s;
+  }
+}
+
+// Psi(:,c,a) *= VolumeOld(c)/Volume(c)   (initPhiTotal_OMPOL.F90:160-165)
+__global__ void scale_psi_kernel(double *psi, const double *ratio, size_t ncG, int G, int NA) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncG) return;
+  const double r = ratio[i / G];
+  for (int a = 0; a < NA; a++) psi[(size_t)a * ncG + i] *= r;
+}
+
+// K6: Psi1(:,c) <- cyclePsi(:,m)  /  cyclePsi(:,m) <- Psi1(:,c)   (constructDynMemory.F90:111-213)
+__global__ void cycle_copy_kernel(double *field /* (NA,nc,G) */, double *cyclePsi, const int *cycleList, const int *cycleAngle,
+                                  int total, int nc, int G, int toField) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)total * G) return;
+  const int m = (int)(i / G), g = (int)(i - (size_t)m * G);
+  const size_t f = ((size_t)cycleAngle[m] * nc + cycleList[m]) * G + g;
+  if (toField) field[f] = cyclePsi[i];
+  else cyclePsi[i] = field[f];
+}
+
+// PsiB(:,b,a) <- Psi(:,c,a) on exiting boundary elements (initializeRadiationField_OMPOL.F90:116-143)
+__global__ void exit_copy_kernel(const double *psi, double *psib, const int *eb, const int *ec, const int *ea, int nExit,
+                                 int nc, int nb, int G) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nExit * G) return;
+  const int m = (int)(i / G), g = (int)(i - (size_t)m * G);
+  psib[((size_t)ea[m] * nb + eb[m]) * G + g] = psi[((size_t)ea[m] * nc + ec[m]) * G + g];
+}
+
+static int launch_phi(umt_ctx *ctx, const double *field) {
+  const size_t n = (size_t)ctx->nc * ctx->G;
+  const size_t threads = (n + 1) / 2;
+  const int grid = (int)((threads + 255) / 256);
+  unsigned char *d_skip = nullptr;
+  if (ctx->ndim == 2) {
+    // starting / finishing directions carry zero weight (rt/rtquad.F90:107-127) and are not tallied
+    // (SweepUCBrz.F90:233-239); weight==0 makes the product exact, no skip array needed.
+  }
+  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field, ctx->d_weight, d_skip, ctx->d_phi, n, ctx->NA, nullptr, ctx->G);
+  UMT_CUDA(ctx, cudaGetLastError());
+  ctx->last_launches += 1;
+  return UMT_OK;
+}
+
+extern "C" int umt_init_phi_total(umt_ctx *ctx, const double *volRatio) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  if (volRatio) {
+    double *d_r = nullptr;
+    TRY(dev_alloc_copy(ctx, &d_r, volRatio, (size_t)ctx->nc));
+    const size_t n = (size_t)ctx->nc * ctx->G;
+    scale_psi_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, d_r, n, ctx->G, ctx->NA);
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_r);
+  }
+  TRY(launch_phi(ctx, ctx->d_psi));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  TRY(finalize_schedule(ctx));
+  if (ctx->nExit > 0) {
+    const size_t n = (size_t)ctx->nExit * ctx->G;
+    exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_psib, ctx->d_exitB, ctx->d_exitC,
+                                                                      ctx->d_exitA, ctx->nExit, ctx->nc, ctx->nb, ctx->G);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
+  if (ctx->totalCycles > 0) {
+    const size_t n = (size_t)ctx->totalCycles * ctx->G;
+    cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_cyclePsi, ctx->d_cycleList,
+                                                                       ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 0);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the controller: rt/ControlSweep.F90 -> snac/SetSweep.F90 -> getPhiTotal
+// ---------------------------------------------------------------------------
+int umt_exchange_begin_pass(umt_ctx *ctx);                      // exchange.cu
+int umt_exchange_test_convergence(umt_ctx *ctx, double tol, int *nNotConv);
+
+extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  NEED_DEVICE(ctx, "umt_sweep");
+  if (!ctx->have_conn || !ctx->have_geom || !ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep: connectivity, geometry and quadrature must be set");
+  if (!ctx->d_psi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep: no state uploaded (umt_upload_state)");
+  TRY(finalize_schedule(ctx));
+  if (maxFluxIters < 1) maxFluxIters = 1;
+  ctx->last_launches = 0;
+  float ms_sweep = 0.f, ms_phi = 0.f, ms_exch = 0.f, ms_all = 0.f;
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  int iter = 0;
+  const bool multi = !ctx->shared.empty();
+  for (;;) {
+    iter++;
+    UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (multi) TRY(umt_exchange_begin_pass(ctx));   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
+    UMT_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->totalCycles > 0) {                     // initFromCycleList
+      const size_t n = (size_t)ctx->totalCycles * ctx->G;
+      cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
+                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 1);
+      ctx->last_launches++;
+    }
+    if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx));
+    else TRY(umt_launch_sweeprz(ctx, savePsi));
+    if (ctx->totalCycles > 0) {                     // updateCycleList
+      const size_t n = (size_t)ctx->totalCycles * ctx->G;
+      cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
+                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 0);
+      ctx->last_launches++;
+    }
+    UMT_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    int nNotConv = 0;
+    if (multi) TRY(umt_exchange_test_convergence(ctx, fluxTol, &nNotConv));  // setIncidentFlux + testFluxConv + Allreduce(max)
+    UMT_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    float t;
+    cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]); ms_exch += t;
+    cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_sweep += t;
+    cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ms_exch += t;
+    if (savePsi) break;                              // SetSweep.F90:185-187
+    if (nNotConv == 0 || iter >= maxFluxIters) break;
+  }
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+  TRY(launch_phi(ctx, ctx->d_psi1));
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+  UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+  cudaEventElapsedTime(&ms_phi, ctx->ev[5], ctx->ev[6]);
+  cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
+  if (savePsi) std::swap(ctx->d_psi, ctx->d_psi1);   // Psi(:,:,Angle) <- Psi1 for every angle, without a copy
+  ctx->last_ms[0] = ms_sweep; ctx->last_ms[1] = ms_phi; ctx->last_ms[2] = ms_exch; ctx->last_ms[3] = ms_all;
+  if (itersDone) *itersDone = iter;
+  return UMT_OK;
+}
+
+extern "C" int umt_last_sweep_times(umt_ctx *ctx, double *ms4) {
+  if (!ctx || !ms4) return UMT_ERR_ARG;
+  for (int i = 0; i < 4; i++) ms4[i] = ctx->last_ms[i];
+  return UMT_OK;
+}
+extern "C" int umt_last_sweep_launches(umt_ctx *ctx, int *n) {
+  if (!ctx || !n) return UMT_ERR_ARG;
+  *n = ctx->last_launches;
+  return UMT_OK;
+}

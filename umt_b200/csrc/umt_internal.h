@@ -1,0 +1,111 @@
+// Internal state of libumtsweep.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/umt_sweep.h"
+
+struct WorkItem {       // one chunk of one hyperplane of one angle
+  int angle;            // 0-based angle
+  int zbeg, zend;       // range in nextZ(:,angle)
+  int wait_idx;         // counter to wait on (-1: none)
+  int wait_count;       // value it must reach
+  int signal_idx;       // counter to bump when done
+  int pad0, pad1;
+};
+
+struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
+  int neighbor;
+  int first;            // 0-based first boundary element
+  int n;
+  // per angle: send rows (boundary element, 0-based) and recv rows
+  std::vector<std::vector<int>> send_b, recv_b;
+  int *d_send_idx = nullptr, *d_recv_idx = nullptr;       // concatenated over angles
+  std::vector<int> send_off, recv_off;                     // per-angle offsets (NA+1)
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  size_t send_rows = 0, recv_rows = 0;
+};
+
+struct umt_ctx {
+  int device = 0;
+  int ndim = 0, nz = 0, nc = 0, nb = 0, maxcf = 0, maxCorner = 0, maxFaces = 0, G = 0;
+  int NA = 0;
+  double tau = 0.0;
+  std::string err;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev[8] = {};
+
+  // host copies (for schedule builder, exit lists, tallies)
+  std::vector<int> h_numCorner, h_cOffSet, h_nCFaces, h_cFP, h_cEZ, h_zoneFaces, h_zoneOpp, h_faceOpp, h_CToFace, h_BdyToC;
+  std::vector<unsigned char> h_BoundaryZone;
+  std::vector<double> h_Volume, h_Afp, h_Aez, h_Abdy, h_Area, h_RadiusFP, h_RadiusEZ, h_VolumeZone;
+  std::vector<double> h_omega, h_weight, h_angDerivFac, h_tauW1, h_tauW2;
+  std::vector<unsigned char> h_start, h_finish;
+  bool have_conn = false, have_geom = false, have_quad = false, have_abdy = false;
+
+  // schedule (host)
+  std::vector<int> nHyp, numCycles, cycleOffSet, nBad;
+  std::vector<std::vector<int>> zonesInPlane, nextZ, nextC, cycleList, bdyList;
+  bool sched_dirty = true;
+
+  // device: connectivity / geometry
+  int *d_numCorner = nullptr, *d_cOffSet = nullptr, *d_nCFaces = nullptr, *d_cFP = nullptr, *d_cEZ = nullptr;
+  double *d_Volume = nullptr, *d_Afp = nullptr, *d_Aez = nullptr, *d_Area = nullptr, *d_RadiusFP = nullptr, *d_RadiusEZ = nullptr;
+  double *d_omega = nullptr, *d_weight = nullptr;
+  // device: schedule
+  int *d_nextZ = nullptr;              // (NA, nz) signed 1-based
+  unsigned char *d_nextC = nullptr;    // (NA, nc) 0-based local corner
+  WorkItem *d_items = nullptr;
+  int nItems = 0, nCounters = 0, maxHyp = 0;
+  int *d_counters = nullptr;           // [0]=ticket, [1..] per (angle,plane)
+  int *d_cycleList = nullptr, *d_cycleAngle = nullptr;   // flattened (totalCycles): corner (0-based), angle
+  int totalCycles = 0;
+  double *d_cyclePsi = nullptr;
+  int *d_exitB = nullptr, *d_exitC = nullptr, *d_exitA = nullptr; int nExit = 0;  // flattened bdyList over angles
+  std::vector<int> exitOff;            // per-angle offsets into d_exit*
+  // device: state
+  double *d_psi = nullptr, *d_psi1 = nullptr, *d_psib = nullptr, *d_stotal = nullptr, *d_sigt = nullptr, *d_phi = nullptr;
+  double *d_psim = nullptr;            // RZ half-angle intensity (G,nc) per xi-level
+  size_t psi_elems = 0;
+
+  // exchange
+  std::vector<SharedBdy> shared;
+  int myRank = 0, nRanks = 1;
+  void *nccl_comm = nullptr;
+  bool exch_dirty = true;
+  std::vector<double> incFlux, incFluxOld;
+
+  // stats
+  double last_ms[4] = {0, 0, 0, 0};
+  int last_launches = 0;
+};
+
+#define UMT_FAIL(ctx, code, ...)                         \
+  do {                                                   \
+    char _b[512];                                        \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);               \
+    (ctx)->err = _b;                                     \
+    return (code);                                       \
+  } while (0)
+
+#define UMT_CUDA(ctx, call)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      UMT_FAIL(ctx, UMT_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+               cudaGetErrorString(_e));                                                \
+  } while (0)
+
+// kernels / host pieces implemented in other translation units
+int umt_launch_sweep3d(umt_ctx *ctx);
+int umt_launch_sweeprz(umt_ctx *ctx, int savePsi);
+int umt_host_build_schedule(umt_ctx *ctx);
+int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polaraxis,
+                                std::vector<double> &omega, std::vector<double> &weight,
+                                std::vector<unsigned char> &start, std::vector<unsigned char> &finish,
+                                std::vector<double> &angDerivFac, std::vector<double> &w1, std::vector<double> &w2);
+int umt_device_geometry(umt_ctx *ctx, const double *d_px);

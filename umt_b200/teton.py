@@ -1,0 +1,251 @@
+"""Host-side mirror of the C ABI in include/umt_sweep.h, for tests and bench.
+
+It plays the role of Teton's Fortran caller (rt/ControlSweep.F90:55-73 ->
+SetSweep_CUDA): it owns nothing but a context handle and passes flat arrays in
+Teton's layout.  There is no CPU fallback here: if libumtsweep.so is missing or no
+GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libumtsweep.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_bp = C.POINTER(C.c_ubyte)
+
+
+class UmtError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libumtsweep.so (built in-tree by __graft_entry__.build / make)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UmtError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.umt_last_error.restype = C.c_char_p
+        _lib.umt_last_error.argtypes = [C.c_void_p]
+        _lib.umt_version.restype = C.c_char_p
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def _bp(a):
+    return None if a is None else a.ctypes.data_as(c_bp)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class SweepContext:
+    """One mesh domain resident on one B200."""
+
+    def __init__(self, ndim, nzones, ncornr, nbelem, maxcf, maxCorner, ngr, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self.ndim, self.nz, self.nc, self.nb, self.maxcf, self.maxCorner, self.G = ndim, nzones, ncornr, nbelem, maxcf, maxCorner, ngr
+        self.NA = 0
+        rc = self.lib.umt_ctx_create(device, ndim, nzones, ncornr, nbelem, maxcf, maxCorner, ngr, C.byref(self.h))
+        if rc:
+            raise UmtError(f"umt_ctx_create -> {rc}: {self.lib.umt_last_error(None).decode()}")
+
+    # -- plumbing ----------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc:
+            raise UmtError(f"{what} -> {rc}: {self.lib.umt_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.umt_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_mesh(cls, mesh, ngr, device=0):
+        ctx = cls(mesh.ndim, mesh.nzones, mesh.ncornr, mesh.nbelem, mesh.maxcf, mesh.maxCorner, ngr, device)
+        ctx.set_connectivity(mesh)
+        return ctx
+
+    # -- setters -----------------------------------------------------------
+    def set_connectivity(self, m):
+        self._keep = [_i32(m.numCorner), _i32(m.cOffSet), _i32(m.nCFacesArray), _i32(m.cFP), _i32(m.cEZ),
+                      _i32(m.zoneFaces), _i32(m.zoneOpp), _i32(m.faceOpp), _i32(m.CToFace), _u8(m.BoundaryZone), _i32(m.BdyToC)]
+        k = self._keep
+        self._ck(self.lib.umt_set_connectivity(self.h, _ip(k[0]), _ip(k[1]), _ip(k[2]), _ip(k[3]), _ip(k[4]), int(m.maxFaces),
+                                               _ip(k[5]), _ip(k[6]), _ip(k[7]), _ip(k[8]), _bp(k[9]), _ip(k[10])), "umt_set_connectivity")
+
+    def set_geometry(self, Volume, A_fp, A_ez, Area=None, RadiusFP=None, RadiusEZ=None, A_bdy=None):
+        a = [_f64(x) for x in (Volume, A_fp, A_ez, Area, RadiusFP, RadiusEZ, A_bdy)]
+        self._ck(self.lib.umt_set_geometry(self.h, *[_dp(x) for x in a]), "umt_set_geometry")
+
+    def compute_geometry(self, px):
+        self._ck(self.lib.umt_compute_geometry(self.h, _dp(_f64(px))), "umt_compute_geometry")
+
+    def download_geometry(self):
+        nd, nc, mcf, nb, nz = self.ndim, self.nc, self.maxcf, self.nb, self.nz
+        g = dict(Volume=np.zeros(nc), A_fp=np.zeros((nc, mcf, nd)), A_ez=np.zeros((nc, mcf, nd)),
+                 A_bdy=np.zeros((max(nb, 1), nd)), VolumeZone=np.zeros(nz))
+        if nd == 2:
+            g.update(Area=np.zeros(nc), RadiusFP=np.zeros((nc, 2)), RadiusEZ=np.zeros((nc, 2)))
+        self._ck(self.lib.umt_download_geometry(self.h, _dp(g["Volume"]), _dp(g["A_fp"]), _dp(g["A_ez"]), _dp(g.get("Area")),
+                                                _dp(g.get("RadiusFP")), _dp(g.get("RadiusEZ")), _dp(g["A_bdy"]), _dp(g["VolumeZone"])),
+                 "umt_download_geometry")
+        return g
+
+    def set_quadrature(self, omega, weight, start=None, finish=None, angDerivFac=None, quadTauW1=None, quadTauW2=None):
+        omega = _f64(omega)
+        self.NA = omega.shape[0]
+        self._ck(self.lib.umt_set_quadrature(self.h, self.NA, _dp(omega), _dp(_f64(weight)), _bp(_u8(start)), _bp(_u8(finish)),
+                                             _dp(_f64(angDerivFac)), _dp(_f64(quadTauW1)), _dp(_f64(quadTauW2))), "umt_set_quadrature")
+
+    def build_product_quadrature(self, npolar, nazimuthal, polaraxis=1):
+        n = C.c_int(0)
+        self._ck(self.lib.umt_build_product_quadrature(self.h, npolar, nazimuthal, polaraxis, C.byref(n)), "umt_build_product_quadrature")
+        self.NA = n.value
+        return self.NA
+
+    def get_quadrature(self):
+        om = np.zeros((self.NA, self.ndim))
+        w = np.zeros(self.NA)
+        self._ck(self.lib.umt_get_quadrature(self.h, _dp(om), _dp(w)), "umt_get_quadrature")
+        return om, w
+
+    def set_schedule(self, angle, nHyp, zonesInPlane, nextZ, nextC, cycleList=None, bdyList=None):
+        cl = _i32(cycleList if cycleList is not None else np.zeros(0))
+        bl = _i32(bdyList if bdyList is not None else np.zeros((0, 2)))
+        self._ck(self.lib.umt_set_schedule(self.h, int(angle), int(nHyp), _ip(_i32(zonesInPlane)), _ip(_i32(nextZ)), _ip(_i32(nextC)),
+                                           int(len(cl)), _ip(cl), int(bl.size // 2), _ip(bl)), "umt_set_schedule")
+
+    def build_schedule(self):
+        self._ck(self.lib.umt_build_schedule(self.h), "umt_build_schedule")
+
+    def schedule_info(self, angle):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.umt_get_schedule_info(self.h, int(angle), C.byref(a), C.byref(b), C.byref(c)), "umt_get_schedule_info")
+        return a.value, b.value, c.value
+
+    def get_schedule(self, angle):
+        nh, ncyc, _ = self.schedule_info(angle)
+        zip_ = np.zeros(max(nh, 1), np.int32)
+        nz_ = np.zeros(self.nz, np.int32)
+        ncn = np.zeros(self.nc, np.int32)
+        cl = np.zeros(max(ncyc, 1), np.int32)
+        self._ck(self.lib.umt_get_schedule(self.h, int(angle), _ip(zip_), _ip(nz_), _ip(ncn), _ip(cl)), "umt_get_schedule")
+        return dict(nHyperPlanes=nh, zonesInPlane=zip_[:nh], nextZ=nz_, nextC=ncn, cycleList=cl[:ncyc])
+
+    # -- state -------------------------------------------------------------
+    def upload_state(self, Psi=None, PsiB=None, Sigt=None, STotal=None, tau=0.0):
+        self._ck(self.lib.umt_upload_state(self.h, _dp(_f64(Psi)), _dp(_f64(PsiB)), _dp(_f64(Sigt)), _dp(_f64(STotal)), C.c_double(tau)),
+                 "umt_upload_state")
+
+    def upload_set(self, g0, Groups, angle0, NumAngles, Psi=None, PsiB=None):
+        self._ck(self.lib.umt_upload_set(self.h, g0, Groups, angle0, NumAngles, _dp(_f64(Psi)), _dp(_f64(PsiB))), "umt_upload_set")
+
+    def download_set(self, g0, Groups, angle0, NumAngles):
+        Psi = np.zeros((NumAngles, self.nc, Groups))
+        PsiB = np.zeros((NumAngles, max(self.nb, 1), Groups))
+        self._ck(self.lib.umt_download_set(self.h, g0, Groups, angle0, NumAngles, _dp(Psi), _dp(PsiB)), "umt_download_set")
+        return Psi, PsiB[:, :self.nb]
+
+    def download_psi(self, out=None):
+        out = np.zeros((self.NA, self.nc, self.G)) if out is None else out
+        self._ck(self.lib.umt_download_psi(self.h, _dp(out)), "umt_download_psi")
+        return out
+
+    def download_psib(self):
+        out = np.zeros((self.NA, max(self.nb, 1), self.G))
+        if self.nb:
+            self._ck(self.lib.umt_download_psib(self.h, _dp(out)), "umt_download_psib")
+        return out[:, :self.nb]
+
+    def download_phi(self, out=None):
+        out = np.zeros((self.nc, self.G)) if out is None else out
+        self._ck(self.lib.umt_download_phi(self.h, _dp(out)), "umt_download_phi")
+        return out
+
+    def init_teton(self, Trz, groupBounds, speedLight, radConstant, wtiso, efloor=0.0):
+        self._ck(self.lib.umt_init_teton(self.h, _dp(_f64(Trz)), _dp(_f64(groupBounds)), C.c_double(speedLight), C.c_double(radConstant),
+                                         C.c_double(wtiso), C.c_double(efloor)), "umt_init_teton")
+
+    def init_phi_total(self, volRatio=None):
+        self._ck(self.lib.umt_init_phi_total(self.h, _dp(_f64(volRatio))), "umt_init_phi_total")
+
+    def init_radiation_field(self):
+        self._ck(self.lib.umt_init_radiation_field(self.h), "umt_init_radiation_field")
+
+    # -- hot path ------------------------------------------------------------
+    def sweep(self, savePsi=False, maxFluxIters=1, fluxTol=1e-6):
+        it = C.c_int(0)
+        self._ck(self.lib.umt_sweep(self.h, int(bool(savePsi)), int(maxFluxIters), C.c_double(fluxTol), C.byref(it)), "umt_sweep")
+        return it.value
+
+    def last_times(self):
+        t = np.zeros(4)
+        self._ck(self.lib.umt_last_sweep_times(self.h, _dp(t)), "umt_last_sweep_times")
+        return dict(sweep_ms=t[0], phi_ms=t[1], exchange_ms=t[2], total_ms=t[3])
+
+    def last_launches(self):
+        n = C.c_int(0)
+        self._ck(self.lib.umt_last_sweep_launches(self.h, C.byref(n)), "umt_last_sweep_launches")
+        return n.value
+
+    def synchronize(self):
+        self._ck(self.lib.umt_synchronize(self.h), "umt_synchronize")
+
+    # -- domain decomposition -----------------------------------------------
+    def add_shared_boundary(self, neighborRank, firstBdyElem, nBdyElem):
+        self._ck(self.lib.umt_add_shared_boundary(self.h, int(neighborRank), int(firstBdyElem), int(nBdyElem)), "umt_add_shared_boundary")
+
+    def set_comm(self, myRank, nRanks, id128: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128)
+        self._ck(self.lib.umt_set_comm(self.h, int(myRank), int(nRanks), buf), "umt_set_comm")
+
+
+def planck_groups(T, bounds, k=1.0, Bnorm=1.0):
+    lib = load_library()
+    b = _f64(bounds)
+    B = np.zeros(len(b) - 1)
+    rc = lib.umt_planck_groups(C.c_double(T), C.c_double(k), C.c_double(Bnorm), len(B), _dp(b), _dp(B))
+    if rc:
+        raise UmtError(f"umt_planck_groups -> {rc}")
+    return B
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.umt_nccl_unique_id(buf)
+    if rc:
+        raise UmtError(f"umt_nccl_unique_id -> {rc}")
+    return bytes(buf)
