@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--groups", type=int, default=128)
     ap.add_argument("--polar", type=int, default=2)
     ap.add_argument("--azimuthal", type=int, default=2)
-    ap.add_argument("--cpu-dims", type=int, default=4, help="tiles per side of the bounded CPU sample")
+    ap.add_argument("--cpu-dims", type=int, default=8, help="tiles per side of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
     args = ap.parse_args()

@@ -2,21 +2,35 @@
 //
 // Replaces snac/SweepUCBxyz.F90:11-322 (one angle, one set) *and* the angle loop
 // of snac/SetSweep.F90:113-170: one persistent kernel sweeps every angle of the
-// quadrature.  Work is a list of items (angle, hyperplane, chunk of zones) ordered
-// plane-major / angle-minor; CTAs pull items through an atomic ticket and wait on a
-// per-(angle,plane) completion counter, so the hyperplane dependency of one angle
-// is hidden behind the other angles' planes.  Group index is on consecutive
-// threads: every load/store of Psi, STotal, Psi1, PsiB is a contiguous G*8-byte row.
+// quadrature.  Work is a list of items (angle, hyperplane, chunk of zones); CTAs
+// pull items through an atomic ticket and wait on a per-(angle,plane) completion
+// counter, so the hyperplane dependency of one angle hides behind other angles.
+// Group index is on consecutive lanes: every load/store of Psi, STotal, Psi1, PsiB
+// is a contiguous G*8-byte row.
 //
-// Data flow per unknown (corner x angle x group): read STotal, read Psi(n), write
-// Psi1; Sigt once per zone; geometry once per (zone, angle).  Upstream Psi1 rows
-// were written a few planes earlier by other CTAs and are read through L2
-// (ld.global.cg) — L1 is not coherent across SMs.
+// Two kernels:
+//  * sweep3d_plan_kernel (the hot one): zones whose corners all have three faces
+//    (hexes, prisms, tets) run from a per-(zone,angle) "plan record" built once per
+//    schedule (plan_build_kernel): corners relabelled into solve order, omega.A
+//    products, upstream rows, the closure polynomials of SweepUCBxyz.F90:217-252 as
+//    group-independent coefficients.  A producer warp streams the records of the
+//    next items into shared memory with TMA bulk copies (cp.async.bulk + mbarrier),
+//    prefetches the item's Psi/STotal/Sigt rows into L2 and resolves the plane
+//    dependency, so the consumer warps never spin; consumers keep the whole 8-corner
+//    zone solve in registers (static indexing in solve-order space).
+//  * sweep3d_generic_kernel: any zone shape (nCFaces != 3, intra-zone cycles); also
+//    the per-zone slow path of the plan kernel.
+//
+// Upstream Psi1 rows were written a few planes earlier by other CTAs and are read
+// through L2 (ld.global.cg) — L1 is not coherent across SMs.
+#include <algorithm>
+#include <cstdlib>
+
 #include "umt_internal.h"
 
 namespace {
 
-constexpr int MAXC = 8;    // corners per zone handled by this kernel
+constexpr int MAXC = 8;    // corners per zone handled by these kernels
 constexpr int MAXCF = 3;   // corner faces
 constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 
@@ -31,6 +45,7 @@ struct Sweep3DParams {
   int *counters;
   const double *psi, *stotal, *sigt;
   double *psi1, *psib;
+  const ZoneRec *recs;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -39,9 +54,121 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
   return v;
 }
 
+// ---------------------------------------------------------------------------
+// generic zone solve: SweepUCBxyz.F90:103-306 for one (zone, group)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a, int zone0, int g) {
+  const int G = P.G, nc = P.nc;
+  const double om0 = P.omega[3 * a], om1 = P.omega[3 * a + 1], om2 = P.omega[3 * a + 2];
+  const double *psiA = P.psi + (size_t)a * nc * G;
+  double *psi1A = P.psi1 + (size_t)a * nc * G;
+  double *psibA = P.psib + (size_t)a * P.nb * G;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
+  const double sig = P.sigt[(size_t)zone * G + g];
+
+  double Q[MAXC], src[MAXC], sumArea[MAXC], vol[MAXC];
+  int nxez[MAXC], ez_exit[MAXC][MAXCF];
+  double coefpsi[MAXC][MAXCF];
+  for (int c = 0; c < nCorner; c++) {
+    const size_t r = (size_t)(c0 + c) * G + g;
+    const double source = P.stotal[r] + P.tau * psiA[r];
+    vol[c] = P.Volume[c0 + c];
+    Q[c] = source;
+    src[c] = vol[c] * source;
+    nxez[c] = 0;
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    const int nCF = P.nCFaces[cc];
+    double afp[MAXCF], psifp[MAXCF];
+    double sa = 0.0;
+    for (int f = 0; f < nCF; f++) {
+      const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
+      afp[f] = om0 * A[0] + om1 * A[1] + om2 * A[2];
+      psifp[f] = 0.0;
+      if (afp[f] > 0.0) {
+        sa += afp[f];
+      } else if (afp[f] < 0.0) {
+        const int row = P.cFP[cc * MAXCF + f];
+        psifp[f] = row < nc ? __ldcg(&psi1A[(size_t)row * G + g]) : __ldcg(&psibA[(size_t)(row - nc) * G + g]);
+        src[c] -= afp[f] * psifp[f];
+      }
+    }
+    for (int f = 0; f < nCF; f++) {
+      const double *A = P.Aez + ((size_t)cc * MAXCF + f) * 3;
+      const double aez = om0 * A[0] + om1 * A[1] + om2 * A[2];
+      const int cez = P.cEZ[cc * MAXCF + f];
+      if (cez > c) {
+        if (aez > 0.0) { ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = aez; nxez[c]++; }
+        else if (aez < 0.0) { ez_exit[cez][nxez[cez]] = c; coefpsi[cez][nxez[cez]] = -aez; nxez[cez]++; }
+      }
+      if (aez > 0.0) {
+        sa += aez;
+        double area_opp = 0.0, psi_opp = 0.0;
+        if (nCF == 3) {
+          const int ifp = (f + 1) % 3;
+          if (afp[ifp] < 0.0) { psi_opp = psifp[ifp]; area_opp = -afp[ifp]; }
+        } else {
+          int ifp = f;
+          for (int k = 0; k < nCF - 2; k++) {
+            ifp = (ifp + 1) % nCF;
+            if (afp[ifp] < 0.0) { area_opp -= afp[ifp]; psi_opp -= afp[ifp] * psifp[ifp]; }
+          }
+          if (area_opp > 0.0) psi_opp *= 1.0 / area_opp;
+        }
+        double sez;
+        if (area_opp > 0.0) {
+          const double aez2 = aez * aez, v = vol[c];
+          const double sigv = sig * v, sigv2 = sigv * sigv;
+          const double gnum = aez2 * (FOURALPHA * sigv2 + aez * (4.0 * sigv + 3.0 * aez));
+          const double gden = v * (4.0 * sigv * sigv2 + aez * (6.0 * sigv2 + 2.0 * aez * (2.0 * sigv + aez)));
+          sez = (v * gnum * (sig * psi_opp - Q[c]) + 0.5 * aez * gden * (Q[c] - Q[cez])) / (gnum + gden * sig);
+        } else {
+          sez = 0.5 * aez * (1.0 / sig) * (Q[c] - Q[cez]);
+        }
+        src[c] += sez;
+        src[cez] -= sez;
+      }
+    }
+    sumArea[c] = sa;
+  }
+  if (zone0 > 0) {
+    for (int i = 0; i < nCorner; i++) {
+      const int c = nextC[c0 + i];
+      const double p = src[c] / (sumArea[c] + sig * vol[c]);
+      src[c] = p;   // src now holds the corner flux
+      for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * p;
+    }
+  } else {
+    // intra-zone cycle: Jacobi on the previous Psi1 (SweepUCBxyz.F90:283-298)
+    for (int c = 0; c < nCorner; c++) {
+      const double old = __ldcg(&psi1A[(size_t)(c0 + c) * G + g]);
+      for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * old;
+    }
+    for (int c = 0; c < nCorner; c++) src[c] = src[c] / (sumArea[c] + sig * vol[c]);
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    psi1A[(size_t)cc * G + g] = src[c];
+    const int nCF = P.nCFaces[cc];
+    for (int f = 0; f < nCF; f++) {
+      const int row = P.cFP[cc * MAXCF + f];
+      if (row >= nc) {
+        const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
+        const double afp = om0 * A[0] + om1 * A[1] + om2 * A[2];
+        if (afp > 0.0) psibA[(size_t)(row - nc) * G + g] = src[c];
+      }
+    }
+  }
+}
+
+__device__ __noinline__ void solve_zone_slow(const Sweep3DParams &P, int a, int zone0, int g) { solve_zone_generic(P, a, zone0, g); }
+
 __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
   __shared__ int s_item;
-  const int G = P.G, nc = P.nc;
+  const int G = P.G;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
     __syncthreads();
@@ -52,117 +179,11 @@ __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
       while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(64);
     }
     __syncthreads();
-
-    const int a = w.angle;
-    const double om0 = P.omega[3 * a], om1 = P.omega[3 * a + 1], om2 = P.omega[3 * a + 2];
-    const double *psiA = P.psi + (size_t)a * nc * G;
-    double *psi1A = P.psi1 + (size_t)a * nc * G;
-    double *psibA = P.psib + (size_t)a * P.nb * G;
-    const int *nextZ = P.nextZ + (size_t)a * P.nz;
-    const unsigned char *nextC = P.nextC + (size_t)a * nc;
-
+    const int *nextZ = P.nextZ + (size_t)w.angle * P.nz;
     const int npairs = (w.zend - w.zbeg) * G;
     for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
       const int zi = idx / G, g = idx - zi * G;
-      const int zone0 = nextZ[w.zbeg + zi];
-      const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
-      const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
-      const double sig = P.sigt[(size_t)zone * G + g];
-
-      double Q[MAXC], src[MAXC], sumArea[MAXC], vol[MAXC];
-      int nxez[MAXC], ez_exit[MAXC][MAXCF];
-      double coefpsi[MAXC][MAXCF];
-      for (int c = 0; c < nCorner; c++) {
-        const size_t r = (size_t)(c0 + c) * G + g;
-        const double source = P.stotal[r] + P.tau * psiA[r];
-        vol[c] = P.Volume[c0 + c];
-        Q[c] = source;
-        src[c] = vol[c] * source;
-        nxez[c] = 0;
-      }
-      for (int c = 0; c < nCorner; c++) {
-        const int cc = c0 + c;
-        const int nCF = P.nCFaces[cc];
-        double afp[MAXCF], psifp[MAXCF];
-        double sa = 0.0;
-        for (int f = 0; f < nCF; f++) {
-          const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
-          afp[f] = om0 * A[0] + om1 * A[1] + om2 * A[2];
-          psifp[f] = 0.0;
-          if (afp[f] > 0.0) {
-            sa += afp[f];
-          } else if (afp[f] < 0.0) {
-            const int row = P.cFP[cc * MAXCF + f];
-            psifp[f] = row < nc ? __ldcg(&psi1A[(size_t)row * G + g]) : __ldcg(&psibA[(size_t)(row - nc) * G + g]);
-            src[c] -= afp[f] * psifp[f];
-          }
-        }
-        for (int f = 0; f < nCF; f++) {
-          const double *A = P.Aez + ((size_t)cc * MAXCF + f) * 3;
-          const double aez = om0 * A[0] + om1 * A[1] + om2 * A[2];
-          const int cez = P.cEZ[cc * MAXCF + f];
-          if (cez > c) {
-            if (aez > 0.0) { ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = aez; nxez[c]++; }
-            else if (aez < 0.0) { ez_exit[cez][nxez[cez]] = c; coefpsi[cez][nxez[cez]] = -aez; nxez[cez]++; }
-          }
-          if (aez > 0.0) {
-            sa += aez;
-            double area_opp = 0.0, psi_opp = 0.0;
-            if (nCF == 3) {
-              const int ifp = (f + 1) % 3;
-              if (afp[ifp] < 0.0) { psi_opp = psifp[ifp]; area_opp = -afp[ifp]; }
-            } else {
-              int ifp = f;
-              for (int k = 0; k < nCF - 2; k++) {
-                ifp = (ifp + 1) % nCF;
-                if (afp[ifp] < 0.0) { area_opp -= afp[ifp]; psi_opp -= afp[ifp] * psifp[ifp]; }
-              }
-              if (area_opp > 0.0) psi_opp *= 1.0 / area_opp;
-            }
-            double sez;
-            if (area_opp > 0.0) {
-              const double aez2 = aez * aez, v = vol[c];
-              const double sigv = sig * v, sigv2 = sigv * sigv;
-              const double gnum = aez2 * (FOURALPHA * sigv2 + aez * (4.0 * sigv + 3.0 * aez));
-              const double gden = v * (4.0 * sigv * sigv2 + aez * (6.0 * sigv2 + 2.0 * aez * (2.0 * sigv + aez)));
-              sez = (v * gnum * (sig * psi_opp - Q[c]) + 0.5 * aez * gden * (Q[c] - Q[cez])) / (gnum + gden * sig);
-            } else {
-              sez = 0.5 * aez * (1.0 / sig) * (Q[c] - Q[cez]);
-            }
-            src[c] += sez;
-            src[cez] -= sez;
-          }
-        }
-        sumArea[c] = sa;
-      }
-      if (zone0 > 0) {
-        for (int i = 0; i < nCorner; i++) {
-          const int c = nextC[c0 + i];
-          const double p = src[c] / (sumArea[c] + sig * vol[c]);
-          src[c] = p;   // src now holds the corner flux
-          for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * p;
-        }
-      } else {
-        // intra-zone cycle: Jacobi on the previous Psi1 (SweepUCBxyz.F90:283-298)
-        for (int c = 0; c < nCorner; c++) {
-          const double old = __ldcg(&psi1A[(size_t)(c0 + c) * G + g]);
-          for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * old;
-        }
-        for (int c = 0; c < nCorner; c++) src[c] = src[c] / (sumArea[c] + sig * vol[c]);
-      }
-      for (int c = 0; c < nCorner; c++) {
-        const int cc = c0 + c;
-        psi1A[(size_t)cc * G + g] = src[c];
-        const int nCF = P.nCFaces[cc];
-        for (int f = 0; f < nCF; f++) {
-          const int row = P.cFP[cc * MAXCF + f];
-          if (row >= nc) {
-            const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
-            const double afp = om0 * A[0] + om1 * A[1] + om2 * A[2];
-            if (afp > 0.0) psibA[(size_t)(row - nc) * G + g] = src[c];
-          }
-        }
-      }
+      solve_zone_generic(P, w.angle, nextZ[w.zbeg + zi], g);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -172,13 +193,387 @@ __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
   }
 }
 
-}  // namespace
+// ---------------------------------------------------------------------------
+// plan records
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int pair_bit(int p, int q) { return p * (15 - p) / 2 + (q - p - 1); }   // 0 <= p < q <= 7
 
-int umt_launch_sweep3d(umt_ctx *ctx) {
-  if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)
-    UMT_FAIL(ctx, UMT_ERR_ARG, "3-D sweep supports maxCorner <= %d and maxcf == %d (got %d, %d)", MAXC, MAXCF,
-             ctx->maxCorner, ctx->maxcf);
-  Sweep3DParams P;
+struct PlanBuildParams {
+  int nc, nb, nz, NA;
+  const int *numCorner, *cOffSet, *nCFaces, *cFP, *cEZ;
+  const double *Volume, *Afp, *Aez, *omega;
+  const int *nextZ;
+  const unsigned char *nextC;
+  ZoneRec *recs;
+  int *nSlow;
+};
+
+__device__ __forceinline__ double dot3_seq(const double *om, const double *A) {
+  // DOT_PRODUCT order, no contraction: the signs decide incoming/outgoing exactly as on the host
+  return __dadd_rn(__dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])), __dmul_rn(om[2], A[2]));
+}
+
+// one thread per (angle, position in sweep order)
+__global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)B.NA * B.nz) return;
+  const int a = (int)(t / B.nz);
+  ZoneRec &R = B.recs[t];
+  const int zone0 = B.nextZ[t];
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int NC = B.numCorner[zone], c0 = B.cOffSet[zone];
+  const double om[3] = {B.omega[3 * a], B.omega[3 * a + 1], B.omega[3 * a + 2]};
+  R.c0 = c0;
+  R.zone0 = zone0;
+  R.inMask = R.exitMask = R.edgeMask = 0u;
+  R.flags = (unsigned)NC;
+  bool slow = zone0 < 0 || NC > MAXC;
+  for (int c = 0; c < NC && !slow; c++) slow = B.nCFaces[c0 + c] != 3;
+  if (slow) {
+    R.flags |= ZREC_SLOW;
+    atomicAdd(B.nSlow, 1);
+    return;
+  }
+  const unsigned char *nextC = B.nextC + (size_t)a * B.nc + c0;
+  int pos[MAXC];
+  for (int c = 0; c < MAXC; c++) pos[c] = -1;
+  for (int i = 0; i < NC; i++) {
+    const int c = nextC[i];
+    if (c >= NC || pos[c] >= 0) slow = true; else pos[c] = i;
+    R.localc[i] = (unsigned char)c;
+  }
+  for (int i = NC; i < MAXC; i++) R.localc[i] = 0;
+  double afp[MAXC][3], aez[MAXC][3];
+  unsigned inMask = 0, exitMask = 0, edgeMask = 0;
+  for (int p = 0; p < NC && !slow; p++) {
+    const int c = R.localc[p], cc = c0 + c;
+    double sa = 0.0;
+    for (int f = 0; f < 3; f++) {
+      afp[p][f] = dot3_seq(om, B.Afp + ((size_t)cc * 3 + f) * 3);
+      const int row = B.cFP[cc * 3 + f];
+      R.rowfp[p][f] = row;
+      R.afp[p][f] = afp[p][f];
+      if (afp[p][f] > 0.0) {
+        sa += afp[p][f];
+        if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
+      } else if (afp[p][f] < 0.0) {
+        inMask |= 1u << (p * 3 + f);
+      }
+    }
+    for (int f = 0; f < 3; f++) {
+      aez[p][f] = dot3_seq(om, B.Aez + ((size_t)cc * 3 + f) * 3);
+      if (aez[p][f] > 0.0) sa += aez[p][f];
+    }
+    R.sumArea[p] = sa;
+    R.vol[p] = B.Volume[cc];
+  }
+  for (int p = NC; p < MAXC; p++) {
+    R.sumArea[p] = 1.0; R.vol[p] = 0.0;
+    for (int f = 0; f < 3; f++) { R.rowfp[p][f] = 0; R.afp[p][f] = 0.0; }
+  }
+  // edges in (p, q) lexicographic order = the order the sweep kernel consumes them
+  int slot = 0;
+  for (int p = 0; p < NC && !slow; p++) {
+    const int c = R.localc[p];
+    for (int q = p + 1; q < NC && !slow; q++) {
+      const int cq = R.localc[q];
+      int f = -1, fq = -1;
+      for (int k = 0; k < 3; k++) {
+        if (B.cEZ[(c0 + c) * 3 + k] == cq) { if (f >= 0) slow = true; f = k; }
+        if (B.cEZ[(c0 + cq) * 3 + k] == c) { if (fq >= 0) slow = true; fq = k; }
+      }
+      if (f < 0 && fq < 0) continue;
+      if (f < 0 || fq < 0) { slow = true; break; }
+      const bool sezFwd = aez[p][f] > 0.0, sezBwd = aez[q][fq] > 0.0;
+      // downstream push (coefpsi): decided by the lower local corner id, SweepUCBxyz.F90:168-179
+      const double alo = c < cq ? aez[p][f] : aez[q][fq];
+      const bool loIsP = c < cq;
+      const bool pushFwd = loIsP ? alo > 0.0 : alo < 0.0;
+      const bool pushBwd = loIsP ? alo < 0.0 : alo > 0.0;
+      if (sezBwd || pushBwd || sezFwd != pushFwd) { slow = true; break; }
+      if (!sezFwd) continue;
+      if (slot >= 12) { slow = true; break; }
+      const double av = aez[p][f], v = R.vol[p], a2 = av * av;
+      const int ifp = (f + 1) % 3;
+      const bool hasOpp = afp[p][ifp] < 0.0;
+      double *E = R.edge[slot];
+      E[0] = 3.0 * a2 * a2;          // gnum = k0 + k1 sigv + k2 sigv^2
+      E[1] = 4.0 * a2 * av;
+      E[2] = FOURALPHA * a2;
+      E[3] = 2.0 * a2 * av * v;      // gden = d0 + d1 sigv + d2 sigv^2 + d3 sigv^3
+      E[4] = 4.0 * a2 * v;
+      E[5] = 6.0 * av * v;
+      E[6] = 4.0 * v;
+      E[7] = 0.5 * av;
+      E[8] = alo > 0.0 ? alo : -alo;  // coefpsi
+      E[9] = 0.0;
+      R.oppj[slot] = (unsigned char)(ifp | (hasOpp ? 4 : 0));
+      edgeMask |= 1u << pair_bit(p, q);
+      slot++;
+    }
+  }
+  for (int s = slot; s < 12; s++) {
+    R.oppj[s] = 0;
+    for (int k = 0; k < 10; k++) R.edge[s][k] = 0.0;
+  }
+  if (slow) {
+    R.flags |= ZREC_SLOW;
+    atomicAdd(B.nSlow, 1);
+    return;
+  }
+  R.inMask = inMask; R.exitMask = exitMask; R.edgeMask = edgeMask;
+  if (exitMask) R.flags |= ZREC_HAS_EXIT;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier / TMA helpers (sm_90+ PTX)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "WAIT_%=:\n"
+      "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "  @p bra DONE_%=;\n"
+      "  bra WAIT_%=;\n"
+      "DONE_%=: }\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double rcp_fast(double x) {
+  // MUFU.RCP64H seed (2^-23) + two Newton steps: ~1 ulp for normal x > 0 (all denominators here are
+  // sums of positive areas and sigma*volume)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+constexpr int PLAN_STAGES = 3;
+constexpr int PLAN_ZMAX = 8;     // zones per item (records per stage)
+
+struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
+
+struct PlanSmem {
+  ZoneRec recs[PLAN_STAGES][PLAN_ZMAX];
+  StageMeta meta[PLAN_STAGES];
+  unsigned long long full[PLAN_STAGES], empty[PLAN_STAGES];
+};
+
+// fast zone solve in solve-order ("position") space; everything indexed statically
+__device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const ZoneRec *__restrict__ R, const double *__restrict__ psiA,
+                                                double *__restrict__ psi1A, double *__restrict__ psibA, int g) {
+  const int G = P.G, nc = P.nc;
+  const int c0 = R->c0;
+  const unsigned inMask = R->inMask, edgeMask = R->edgeMask, flags = R->flags;
+  const int NC = (int)(flags & 15u);
+  const int zone = R->zone0 - 1;
+  const double sig = ld_stream(P.sigt + (size_t)zone * G + g);
+  const double tau = P.tau;
+  const size_t base = (size_t)c0 * G + g;
+  const double *ps = psiA + base, *st = P.stotal + base;
+  double *out = psi1A + base;
+
+  double Q[MAXC], src[MAXC], SV[MAXC];
+#pragma unroll
+  for (int p = 0; p < MAXC; p++) {
+    if (p < NC) {
+      const int off = (int)R->localc[p] * G;
+      const double q = fma(tau, ld_stream(ps + off), ld_stream(st + off));
+      const double v = R->vol[p];
+      Q[p] = q;
+      src[p] = v * q;
+      SV[p] = sig * v;
+    } else {
+      Q[p] = 0.0; src[p] = 0.0; SV[p] = 0.0;
+    }
+  }
+  const double *E = &R->edge[0][0];
+  const unsigned char *oj = R->oppj;
+#pragma unroll
+  for (int p = 0; p < MAXC; p++) {
+    if (p < NC) {
+      // incident fluxes across FP faces (SweepUCBxyz.F90:139-161)
+      double pf0 = 0.0, pf1 = 0.0, pf2 = 0.0;
+      if (inMask & (1u << (p * 3 + 0))) {
+        const int row = R->rowfp[p][0];
+        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
+        pf0 = __ldcg(b + (size_t)row * G + g);
+        src[p] = fma(-R->afp[p][0], pf0, src[p]);
+      }
+      if (inMask & (1u << (p * 3 + 1))) {
+        const int row = R->rowfp[p][1];
+        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
+        pf1 = __ldcg(b + (size_t)row * G + g);
+        src[p] = fma(-R->afp[p][1], pf1, src[p]);
+      }
+      if (inMask & (1u << (p * 3 + 2))) {
+        const int row = R->rowfp[p][2];
+        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
+        pf2 = __ldcg(b + (size_t)row * G + g);
+        src[p] = fma(-R->afp[p][2], pf2, src[p]);
+      }
+      // EZ faces leaving this corner (SweepUCBxyz.F90:182-252)
+      const double *Ep = E;
+      const double qp = Q[p], sv = SV[p], vp = R->vol[p];
+#pragma unroll
+      for (int q = p + 1; q < MAXC; q++) {
+        if (edgeMask & (1u << pair_bit(p, q))) {
+          const double2 k01 = *reinterpret_cast<const double2 *>(E);
+          const double2 k2d0 = *reinterpret_cast<const double2 *>(E + 2);
+          const double2 d12 = *reinterpret_cast<const double2 *>(E + 4);
+          const double2 d3h = *reinterpret_cast<const double2 *>(E + 6);
+          const int jj = *oj;
+          const double dq = qp - Q[q];
+          double sez;
+          if (jj & 4) {
+            const int j = jj & 3;
+            const double po = j == 0 ? pf0 : (j == 1 ? pf1 : pf2);
+            const double gnum = fma(fma(k2d0.x, sv, k01.y), sv, k01.x);
+            const double gden = fma(fma(fma(d3h.x, sv, d12.y), sv, d12.x), sv, k2d0.y);
+            const double den = fma(gden, sig, gnum);
+            const double t1 = fma(sig, po, -qp);
+            const double num = fma(vp * gnum, t1, (d3h.y * gden) * dq);
+            sez = num * rcp_fast(den);
+          } else {
+            sez = d3h.y * dq * rcp_fast(sig);
+          }
+          src[p] += sez;
+          src[q] -= sez;
+          E += 10; oj++;
+        }
+      }
+      // corner flux and its push to the downstream corners (SweepUCBxyz.F90:261-281)
+      const double psi = src[p] * rcp_fast(R->sumArea[p] + sv);
+      out[(int)R->localc[p] * G] = psi;
+#pragma unroll
+      for (int q = p + 1; q < MAXC; q++) {
+        if (edgeMask & (1u << pair_bit(p, q))) {
+          src[q] = fma(Ep[8], psi, src[q]);
+          Ep += 10;
+        }
+      }
+      if (flags & ZREC_HAS_EXIT) {
+        const unsigned em = R->exitMask >> (p * 3);
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+          if (em & (1u << f)) psibA[(size_t)(R->rowfp[p][f] - nc) * G + g] = psi;
+      }
+    }
+  }
+}
+
+template <int NCW>
+__global__ void __launch_bounds__(NCW * 32 + 32) sweep3d_plan_kernel(Sweep3DParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PlanSmem &S = *reinterpret_cast<PlanSmem *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = P.G;
+  if (tid == 0) {
+    for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NCW) {
+    // ---------------- producer warp ----------------
+    bool more = true;
+    int issued = 0;
+    for (int k = 0;; k++) {
+      if (more) {
+        const int s = k % PLAN_STAGES;
+        if (k >= PLAN_STAGES) mbar_wait(&S.empty[s], ((k / PLAN_STAGES) - 1) & 1);
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&P.counters[0], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= P.nItems) {
+          more = false;
+          if (lane == 0) { S.meta[s].n = -1; mbar_arrive(&S.full[s]); mbar_arrive(&S.full[s]); }
+        } else {
+          const WorkItem w = P.items[t];
+          const int n = w.zend - w.zbeg;
+          const ZoneRec *src = P.recs + (size_t)w.angle * P.nz + w.zbeg;
+          if (lane == 0) {
+            S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
+            S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
+            mbar_arrive_expect_tx(&S.full[s], (unsigned)(n * sizeof(ZoneRec)));
+            tma_load_1d(&S.recs[s][0], src, (unsigned)(n * sizeof(ZoneRec)), &S.full[s]);
+          }
+          // pull the item's Psi^n / STotal / Sigt rows into L2 ahead of the consumers
+          if (lane < n && (G & 1) == 0) {
+            const int4 h = *reinterpret_cast<const int4 *>(src + lane);   // c0, zone0, inMask, exitMask
+            const unsigned flagsNC = src[lane].flags & 15u;
+            const int zone = (h.y < 0 ? -h.y : h.y) - 1;
+            const unsigned rowBytes = (unsigned)G * 8u;
+            l2_prefetch_bulk(P.psi + ((size_t)w.angle * P.nc + h.x) * G, rowBytes * flagsNC);
+            l2_prefetch_bulk(P.stotal + (size_t)h.x * G, rowBytes * flagsNC);
+            l2_prefetch_bulk(P.sigt + (size_t)zone * G, rowBytes);
+          }
+          issued = k + 1;
+        }
+      }
+      const int j = k - (PLAN_STAGES - 1);
+      if (j >= 0 && j < issued) {
+        const int s = j % PLAN_STAGES;
+        if (lane == 0) {
+          const int wi = S.meta[s].wait_idx, wc = S.meta[s].wait_count;
+          if (wi >= 0)
+            while (ld_acquire(&P.counters[1 + wi]) < wc) __nanosleep(32);
+          mbar_arrive(&S.full[s]);
+        }
+        __syncwarp();
+      }
+      if (!more && j + 1 >= issued) break;
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  for (int k = 0;; k++) {
+    const int s = k % PLAN_STAGES;
+    mbar_wait(&S.full[s], (k / PLAN_STAGES) & 1);
+    const StageMeta m = S.meta[s];
+    if (m.n < 0) break;
+    const int a = m.angle;
+    const double *psiA = P.psi + (size_t)a * P.nc * G;
+    double *psi1A = P.psi1 + (size_t)a * P.nc * G;
+    double *psibA = P.psib + (size_t)a * P.nb * G;
+    const int npairs = m.n * G;
+    for (int idx = tid; idx < npairs; idx += NCW * 32) {
+      const int zi = idx / G, g = idx - zi * G;
+      const ZoneRec *R = &S.recs[s][zi];
+      if (R->flags & ZREC_SLOW) solve_zone_slow(P, a, R->zone0, g);
+      else solve_zone_plan(P, R, psiA, psi1A, psibA, g);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&P.counters[1 + m.signal_idx], 1);
+      mbar_arrive(&S.empty[s]);
+    }
+  }
+}
+
+void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.nc = ctx->nc; P.nb = ctx->nb; P.nz = ctx->nz; P.G = ctx->G; P.NA = ctx->NA; P.nItems = ctx->nItems;
   P.tau = ctx->tau;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
@@ -186,15 +581,82 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
   P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
   P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1; P.psib = ctx->d_psib;
-  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
-  int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_generic_kernel, 128, 0));
-  if (occ < 1) occ = 1;
-  int grid = ctx->sm_count * occ;
-  if (grid > ctx->nItems) grid = ctx->nItems;
-  if (grid < 1) grid = 1;
-  sweep3d_generic_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+  P.recs = ctx->d_recs;
+}
+
+}  // namespace
+
+int umt_sweep3d_zones_per_item(const umt_ctx *ctx) {
+  if (ctx->use_plan) {
+    const int lanes = ctx->plan_ncw * 32;
+    int z = std::max(1, std::min(PLAN_ZMAX, 4 * lanes / std::max(ctx->G, 1)));   // ~4 rounds of the consumer warps
+    if (const char *e = getenv("UMT_ZONES_PER_ITEM")) z = std::max(1, std::min(PLAN_ZMAX, atoi(e)));
+    return z;
+  }
+  int pairs_target = 512;
+  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairs_target = std::max(1, atoi(e));
+  return std::max(1, pairs_target / ctx->G);
+}
+
+// Build the per-(zone, angle) plan records on the device (once per schedule / geometry / quadrature).
+int umt_build_plan3d(umt_ctx *ctx) {
+  const size_t n = (size_t)ctx->NA * ctx->nz;
+  if (ctx->d_recs) { cudaFree(ctx->d_recs); ctx->d_recs = nullptr; }
+  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_recs, n * sizeof(ZoneRec)));
+  int *d_nslow = nullptr;
+  UMT_CUDA(ctx, cudaMalloc((void **)&d_nslow, sizeof(int)));
+  UMT_CUDA(ctx, cudaMemset(d_nslow, 0, sizeof(int)));
+  PlanBuildParams B;
+  B.nc = ctx->nc; B.nb = ctx->nb; B.nz = ctx->nz; B.NA = ctx->NA;
+  B.numCorner = ctx->d_numCorner; B.cOffSet = ctx->d_cOffSet; B.nCFaces = ctx->d_nCFaces; B.cFP = ctx->d_cFP; B.cEZ = ctx->d_cEZ;
+  B.Volume = ctx->d_Volume; B.Afp = ctx->d_Afp; B.Aez = ctx->d_Aez; B.omega = ctx->d_omega;
+  B.nextZ = ctx->d_nextZ; B.nextC = ctx->d_nextC; B.recs = ctx->d_recs; B.nSlow = d_nslow;
+  plan_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(B);
   UMT_CUDA(ctx, cudaGetLastError());
+  UMT_CUDA(ctx, cudaMemcpyAsync(&ctx->plan_slow_zones, d_nslow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_nslow);
+  return UMT_OK;
+}
+
+template <int NCW>
+static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
+  const int threads = NCW * 32 + 32;
+  const size_t smem = sizeof(PlanSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel<NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int occ = 0;
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel<NCW>, threads, smem));
+  if (occ < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweep3d_plan_kernel does not fit on an SM");
+  if (const char *e = getenv("UMT_PLAN_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+  int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
+  sweep3d_plan_kernel<NCW><<<grid, threads, smem, ctx->stream>>>(P);
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}
+
+int umt_launch_sweep3d(umt_ctx *ctx) {
+  if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)
+    UMT_FAIL(ctx, UMT_ERR_ARG, "3-D sweep supports maxCorner <= %d and maxcf == %d (got %d, %d)", MAXC, MAXCF,
+             ctx->maxCorner, ctx->maxcf);
+  Sweep3DParams P;
+  fill_params(ctx, P);
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
+  if (ctx->use_plan) {
+    if (!ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
+    int r = ctx->plan_ncw == 8 ? launch_plan<8>(ctx, P) : launch_plan<4>(ctx, P);
+    if (r) return r;
+  } else {
+    int occ = 0;
+    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_generic_kernel, 128, 0));
+    if (occ < 1) occ = 1;
+    int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
+    sweep3d_generic_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
   ctx->last_launches += 1;
   return UMT_OK;
 }

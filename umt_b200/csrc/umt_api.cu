@@ -75,7 +75,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_Aez, ctx->d_Area, ctx->d_RadiusFP, ctx->d_RadiusEZ, ctx->d_omega, ctx->d_weight, ctx->d_nextZ,
                   ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_psib, ctx->d_stotal,
-                  ctx->d_sigt, ctx->d_phi, ctx->d_psim};
+                  ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto &s : ctx->shared) {
     if (s.d_send_idx) cudaFree(s.d_send_idx);
@@ -291,9 +291,21 @@ static int finalize_schedule(umt_ctx *ctx) {
   }
   // work items: plane-major, angle-minor.  RZ angles of one xi-level are chained
   // (PsiM dependency, SweepUCBrz.F90:212-240) so RZ uses a separate launcher.
-  int pairs_target = 512;
-  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairs_target = std::max(1, atoi(e));
-  const int zpi = std::max(1, pairs_target / ctx->G);
+  // plan kernel: every 3-D mesh with <= 8 corners per zone (zones it cannot plan take its slow path)
+  ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8;
+  if (const char *e = getenv("UMT_SWEEP3D")) if (!strcmp(e, "generic")) ctx->use_plan = false;
+  ctx->plan_ncw = 4;
+  if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
+  const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, 512 / ctx->G);
+  // Angles run in batches of K with staggered starts: a batch in its growing half overlaps the
+  // previous batch's shrinking half, so the work per level is steady while the Psi1 rows of
+  // the last few planes of every active angle stay L2-resident for their downstream zones.
+  int K = NA;
+  double stagger = 0.5;
+  if (ctx->use_plan) K = 8;
+  if (const char *e = getenv("UMT_ANGLE_BATCH")) K = std::max(1, atoi(e));
+  if (const char *e = getenv("UMT_BATCH_STAGGER")) stagger = std::max(0.0, atof(e));
+  const int delta = std::max(1, (int)(stagger * maxHyp));
   std::vector<WorkItem> items;
   std::vector<std::vector<int>> nItemsPlane(NA);
   std::vector<std::vector<int>> planeStart(NA);
@@ -305,9 +317,12 @@ static int finalize_schedule(umt_ctx *ctx) {
       nItemsPlane[a][p] = (ctx->zonesInPlane[a][p] + zpi - 1) / zpi;
     }
   }
-  for (int p = 0; p < maxHyp; p++)
+  const int nBatches = (NA + K - 1) / K;
+  const int nLevels = maxHyp + (nBatches - 1) * delta;
+  for (int lev = 0; lev < nLevels; lev++)
     for (int a = 0; a < NA; a++) {
-      if (p >= ctx->nHyp[a]) continue;
+      const int p = lev - (a / K) * delta;
+      if (p < 0 || p >= ctx->nHyp[a]) continue;
       const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
       for (int k = 0; k < nItemsPlane[a][p]; k++) {
         WorkItem w;
@@ -327,6 +342,7 @@ static int finalize_schedule(umt_ctx *ctx) {
   TRY(dev_alloc_copy(ctx, &ctx->d_nextC, h_nextC.data(), h_nextC.size()));
   TRY(dev_alloc_copy(ctx, &ctx->d_items, items.data(), items.size()));
   TRY(dev_alloc_copy<int>(ctx, &ctx->d_counters, nullptr, 1 + (size_t)ctx->nCounters));
+  if (ctx->use_plan && ctx->device >= 0) TRY(umt_build_plan3d(ctx));
   // cycle lists (control/constructDynMemory.F90:56-213)
   std::vector<int> cl, ca;
   int off = 0;

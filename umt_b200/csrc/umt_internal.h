@@ -17,6 +17,24 @@ struct WorkItem {       // one chunk of one hyperplane of one angle
   int pad0, pad1;
 };
 
+// Plan record of one (zone, angle) for the 3-D plan kernel (sweep3d.cu): the zone's
+// corners relabelled into solve order ("positions"), omega.A products, upstream rows and
+// the group-independent coefficients of the corner-balance closure.
+enum { ZREC_SLOW = 16u, ZREC_HAS_EXIT = 32u };   // flags bits above the corner count (bits 0..3)
+struct alignas(16) ZoneRec {
+  int c0, zone0;                 // first corner row of the zone; signed 1-based zone id from nextZ
+  unsigned inMask, exitMask;     // bit p*3+f: FP face f of position p is incident / exits through the boundary
+  unsigned edgeMask, flags;      // bit pair_bit(p,q): EZ face from position p into position q
+  unsigned char localc[8];       // local corner id at position p (nextC order)
+  unsigned char oppj[12];        // per edge slot: opposite FP face index | 4 if that face is incident
+  int pad;
+  int rowfp[8][3];               // Psi1 row behind FP face f (>= ncornr: boundary element row)
+  double afp[8][3];              // omega . A_fp
+  double vol[8], sumArea[8];
+  double edge[12][10];           // k0,k1,k2 (gnum), d0..d3 (gden), aez/2, coefpsi, pad
+};
+static_assert(sizeof(ZoneRec) == 1424, "ZoneRec layout");
+
 struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int neighbor;
   int first;            // 0-based first boundary element
@@ -62,6 +80,9 @@ struct umt_ctx {
   WorkItem *d_items = nullptr;
   int nItems = 0, nCounters = 0, maxHyp = 0;
   int *d_counters = nullptr;           // [0]=ticket, [1..] per (angle,plane)
+  ZoneRec *d_recs = nullptr;           // (NA, nz) plan records in sweep order
+  bool use_plan = false;
+  int plan_ncw = 4, plan_slow_zones = 0;
   int *d_cycleList = nullptr, *d_cycleAngle = nullptr;   // flattened (totalCycles): corner (0-based), angle
   int totalCycles = 0;
   double *d_cyclePsi = nullptr;
@@ -102,6 +123,8 @@ struct umt_ctx {
 
 // kernels / host pieces implemented in other translation units
 int umt_launch_sweep3d(umt_ctx *ctx);
+int umt_build_plan3d(umt_ctx *ctx);
+int umt_sweep3d_zones_per_item(const umt_ctx *ctx);
 int umt_launch_sweeprz(umt_ctx *ctx, int savePsi);
 int umt_host_build_schedule(umt_ctx *ctx);
 int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polaraxis,
