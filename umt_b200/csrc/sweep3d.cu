@@ -392,18 +392,24 @@ __device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const Zo
   const double *ps = psiA + base, *st = P.stotal + base;
   double *out = psi1A + base;
 
-  double Q[MAXC], src[MAXC], SV[MAXC];
+  // phase 0: every global load of the zone is issued up front (no load sits behind a branch):
+  // 2 x NC streaming rows (Psi^n, STotal) and the incident FP-face rows, predicated on the record's mask
+  double Q[MAXC], src[MAXC], pf[MAXC][3];
+  const double *bdyBase = psibA - (size_t)nc * G;
 #pragma unroll
   for (int p = 0; p < MAXC; p++) {
-    if (p < NC) {
-      const int off = (int)R->localc[p] * G;
-      const double q = fma(tau, ld_stream(ps + off), ld_stream(st + off));
-      const double v = R->vol[p];
-      Q[p] = q;
-      src[p] = v * q;
-      SV[p] = sig * v;
-    } else {
-      Q[p] = 0.0; src[p] = 0.0; SV[p] = 0.0;
+    const int off = (int)R->localc[p] * G;
+    double a = 0.0, b = 0.0;
+    if (p < NC) { a = ld_stream(ps + off); b = ld_stream(st + off); }
+    Q[p] = fma(tau, a, b);
+    src[p] = R->vol[p] * Q[p];
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const int row = R->rowfp[p][f];
+      const double *bp = (row < nc ? psi1A : bdyBase) + (size_t)row * G + g;
+      double v = 0.0;
+      if (inMask & (1u << (p * 3 + f))) v = __ldcg(bp);
+      pf[p][f] = v;
     }
   }
   const double *E = &R->edge[0][0];
@@ -411,29 +417,14 @@ __device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const Zo
 #pragma unroll
   for (int p = 0; p < MAXC; p++) {
     if (p < NC) {
-      // incident fluxes across FP faces (SweepUCBxyz.F90:139-161)
-      double pf0 = 0.0, pf1 = 0.0, pf2 = 0.0;
-      if (inMask & (1u << (p * 3 + 0))) {
-        const int row = R->rowfp[p][0];
-        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
-        pf0 = __ldcg(b + (size_t)row * G + g);
-        src[p] = fma(-R->afp[p][0], pf0, src[p]);
-      }
-      if (inMask & (1u << (p * 3 + 1))) {
-        const int row = R->rowfp[p][1];
-        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
-        pf1 = __ldcg(b + (size_t)row * G + g);
-        src[p] = fma(-R->afp[p][1], pf1, src[p]);
-      }
-      if (inMask & (1u << (p * 3 + 2))) {
-        const int row = R->rowfp[p][2];
-        const double *b = row < nc ? psi1A : psibA - (size_t)nc * G;
-        pf2 = __ldcg(b + (size_t)row * G + g);
-        src[p] = fma(-R->afp[p][2], pf2, src[p]);
-      }
-      // EZ faces leaving this corner (SweepUCBxyz.F90:182-252)
+      const double vp = R->vol[p], qp = Q[p], sv = sig * vp;
+      // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); pf is 0 on the other faces
+      const double pf0 = pf[p][0], pf1 = pf[p][1], pf2 = pf[p][2];
+      src[p] = fma(-R->afp[p][0], pf0, src[p]);
+      src[p] = fma(-R->afp[p][1], pf1, src[p]);
+      src[p] = fma(-R->afp[p][2], pf2, src[p]);
       const double *Ep = E;
-      const double qp = Q[p], sv = SV[p], vp = R->vol[p];
+      // EZ faces leaving this corner (SweepUCBxyz.F90:182-252)
 #pragma unroll
       for (int q = p + 1; q < MAXC; q++) {
         if (edgeMask & (1u << pair_bit(p, q))) {
