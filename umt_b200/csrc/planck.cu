@@ -41,7 +41,7 @@ __host__ __device__ inline void planck_groups(double T, double k, double Bnorm, 
 }
 
 // Psi(g,c,a) = max(wtiso * B_g(Tr(zone(c))), floor) for every angle (InitTeton.F90:95-118)
-__global__ void init_psi_kernel(double *psi, const double *trz, const int *c2z, const double *bounds, int G, int nc, int NA,
+__global__ void init_psi_kernel(double *psi, const double *trz, const int *c2z, const double *bounds, int G, int nc /* rows per angle */, int NA,
                                 double kb, double ac, double wtiso, double efloor) {
   extern __shared__ double sB[];   // (G) spectrum of this corner
   const int c = blockIdx.x;
@@ -75,7 +75,7 @@ extern "C" int umt_init_teton(umt_ctx *ctx, const double *Trz, const double *gro
   UMT_CUDA(ctx, cudaMemcpy(d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(d_tr, Trz, sizeof(double) * ctx->nz, cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(d_b, groupBounds, sizeof(double) * (ctx->G + 1), cudaMemcpyHostToDevice));
-  init_psi_kernel<<<ctx->nc, 128, sizeof(double) * ctx->G, ctx->stream>>>(ctx->d_psi, d_tr, d_c2z, d_b, ctx->G, ctx->nc, ctx->NA, 1.0,
+  init_psi_kernel<<<ctx->nc, 128, sizeof(double) * ctx->G, ctx->stream>>>(ctx->d_psi, d_tr, d_c2z, d_b, ctx->G, ctx->rows, ctx->NA, 1.0,
                                                                            speedLight * radConstant, wtiso, efloor);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

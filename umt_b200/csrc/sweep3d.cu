@@ -44,7 +44,7 @@ struct Sweep3DParams {
   const WorkItem *items;
   int *counters;
   const double *psi, *stotal, *sigt;
-  double *psi1, *psib;
+  double *psi1;
   const ZoneRec *recs;
 };
 
@@ -60,9 +60,10 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a, int zone0, int g) {
   const int G = P.G, nc = P.nc;
   const double om0 = P.omega[3 * a], om1 = P.omega[3 * a + 1], om2 = P.omega[3 * a + 2];
-  const double *psiA = P.psi + (size_t)a * nc * G;
-  double *psi1A = P.psi1 + (size_t)a * nc * G;
-  double *psibA = P.psib + (size_t)a * P.nb * G;
+  const size_t slab = (size_t)(nc + P.nb) * G;   // Psi, Psi1 are (G, nc+nb, NA): boundary rows follow the corner rows
+  const double *psiA = P.psi + (size_t)a * slab;
+  double *psi1A = P.psi1 + (size_t)a * slab;
+  double *psibA = psi1A + (size_t)nc * G;
   const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
@@ -196,8 +197,6 @@ __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
 // ---------------------------------------------------------------------------
 // plan records
 // ---------------------------------------------------------------------------
-__host__ __device__ constexpr int pair_bit(int p, int q) { return p * (15 - p) / 2 + (q - p - 1); }   // 0 <= p < q <= 7
-
 struct PlanBuildParams {
   int nc, nb, nz, NA;
   const int *numCorner, *cOffSet, *nCFaces, *cFP, *cEZ;
@@ -225,41 +224,44 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
   const double om[3] = {B.omega[3 * a], B.omega[3 * a + 1], B.omega[3 * a + 2]};
   R.c0 = c0;
   R.zone0 = zone0;
-  R.inMask = R.exitMask = R.edgeMask = 0u;
-  R.flags = (unsigned)NC;
+  R.exitMask = 0u;
+  R.flags = (unsigned)(NC & 15);
   bool slow = zone0 < 0 || NC > MAXC;
   for (int c = 0; c < NC && !slow; c++) slow = B.nCFaces[c0 + c] != 3;
-  if (slow) {
-    R.flags |= ZREC_SLOW;
-    atomicAdd(B.nSlow, 1);
-    return;
-  }
   const unsigned char *nextC = B.nextC + (size_t)a * B.nc + c0;
   int pos[MAXC];
   for (int c = 0; c < MAXC; c++) pos[c] = -1;
-  for (int i = 0; i < NC; i++) {
+  for (int i = 0; i < MAXC; i++) { R.localc[i] = 0; R.nIn[i] = 0; R.nOut[i] = 0; R.pad[i] = 0; R.vol[i] = 0.0; R.sumArea[i] = 1.0; }
+  for (int i = 0; i < NC && !slow; i++) {
     const int c = nextC[i];
     if (c >= NC || pos[c] >= 0) slow = true; else pos[c] = i;
     R.localc[i] = (unsigned char)c;
   }
-  for (int i = NC; i < MAXC; i++) R.localc[i] = 0;
   double afp[MAXC][3], aez[MAXC][3];
-  unsigned inMask = 0, exitMask = 0, edgeMask = 0;
+  signed char kOfFace[MAXC][3];
+  unsigned exitMask = 0;
+  int nInTot = 0;
   for (int p = 0; p < NC && !slow; p++) {
     const int c = R.localc[p], cc = c0 + c;
     double sa = 0.0;
+    int nin = 0;
     for (int f = 0; f < 3; f++) {
       afp[p][f] = dot3_seq(om, B.Afp + ((size_t)cc * 3 + f) * 3);
       const int row = B.cFP[cc * 3 + f];
-      R.rowfp[p][f] = row;
-      R.afp[p][f] = afp[p][f];
+      kOfFace[p][f] = -1;
+      R.exitRow[p][f] = row;
       if (afp[p][f] > 0.0) {
         sa += afp[p][f];
         if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
       } else if (afp[p][f] < 0.0) {
-        inMask |= 1u << (p * 3 + f);
+        if (nInTot >= 16) { slow = true; break; }
+        R.inRow[nInTot] = row;
+        R.inAfp[nInTot] = afp[p][f];
+        kOfFace[p][f] = (signed char)nin;
+        nin++; nInTot++;
       }
     }
+    R.nIn[p] = (unsigned char)nin;
     for (int f = 0; f < 3; f++) {
       aez[p][f] = dot3_seq(om, B.Aez + ((size_t)cc * 3 + f) * 3);
       if (aez[p][f] > 0.0) sa += aez[p][f];
@@ -267,14 +269,12 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
     R.sumArea[p] = sa;
     R.vol[p] = B.Volume[cc];
   }
-  for (int p = NC; p < MAXC; p++) {
-    R.sumArea[p] = 1.0; R.vol[p] = 0.0;
-    for (int f = 0; f < 3; f++) { R.rowfp[p][f] = 0; R.afp[p][f] = 0.0; }
-  }
-  // edges in (p, q) lexicographic order = the order the sweep kernel consumes them
+  for (int k = nInTot; k < 16; k++) { R.inRow[k] = 0; R.inAfp[k] = 0.0; }
+  // outgoing EZ faces grouped by upstream position, downstream position ascending
   int slot = 0;
   for (int p = 0; p < NC && !slow; p++) {
     const int c = R.localc[p];
+    int nout = 0;
     for (int q = p + 1; q < NC && !slow; q++) {
       const int cq = R.localc[q];
       int f = -1, fq = -1;
@@ -285,43 +285,33 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
       if (f < 0 && fq < 0) continue;
       if (f < 0 || fq < 0) { slow = true; break; }
       const bool sezFwd = aez[p][f] > 0.0, sezBwd = aez[q][fq] > 0.0;
-      // downstream push (coefpsi): decided by the lower local corner id, SweepUCBxyz.F90:168-179
-      const double alo = c < cq ? aez[p][f] : aez[q][fq];
+      // downstream push (coefpsi) is decided by the lower local corner id, SweepUCBxyz.F90:168-179
       const bool loIsP = c < cq;
+      const double alo = loIsP ? aez[p][f] : aez[q][fq];
       const bool pushFwd = loIsP ? alo > 0.0 : alo < 0.0;
       const bool pushBwd = loIsP ? alo < 0.0 : alo > 0.0;
       if (sezBwd || pushBwd || sezFwd != pushFwd) { slow = true; break; }
       if (!sezFwd) continue;
-      if (slot >= 12) { slow = true; break; }
-      const double av = aez[p][f], v = R.vol[p], a2 = av * av;
+      if (slot >= 12 || nout >= 3) { slow = true; break; }
+      const double av = aez[p][f];
       const int ifp = (f + 1) % 3;
-      const bool hasOpp = afp[p][ifp] < 0.0;
-      double *E = R.edge[slot];
-      E[0] = 3.0 * a2 * a2;          // gnum = k0 + k1 sigv + k2 sigv^2
-      E[1] = 4.0 * a2 * av;
-      E[2] = FOURALPHA * a2;
-      E[3] = 2.0 * a2 * av * v;      // gden = d0 + d1 sigv + d2 sigv^2 + d3 sigv^3
-      E[4] = 4.0 * a2 * v;
-      E[5] = 6.0 * av * v;
-      E[6] = 4.0 * v;
-      E[7] = 0.5 * av;
-      E[8] = alo > 0.0 ? alo : -alo;  // coefpsi
-      E[9] = 0.0;
-      R.oppj[slot] = (unsigned char)(ifp | (hasOpp ? 4 : 0));
-      edgeMask |= 1u << pair_bit(p, q);
-      slot++;
+      ZoneEdge &E = R.edge[slot];
+      E.ainv = 1.0 / av;
+      E.cp = alo > 0.0 ? alo : -alo;
+      E.ha = 0.5 * av;
+      E.qc = cq;
+      E.oppk = afp[p][ifp] < 0.0 ? (int)kOfFace[p][ifp] : -1;
+      slot++; nout++;
     }
+    R.nOut[p] = (unsigned char)nout;
   }
-  for (int s = slot; s < 12; s++) {
-    R.oppj[s] = 0;
-    for (int k = 0; k < 10; k++) R.edge[s][k] = 0.0;
-  }
+  for (int k = slot; k < 12; k++) { R.edge[k].ainv = 0.0; R.edge[k].cp = 0.0; R.edge[k].ha = 0.0; R.edge[k].qc = 0; R.edge[k].oppk = -1; }
   if (slow) {
     R.flags |= ZREC_SLOW;
     atomicAdd(B.nSlow, 1);
     return;
   }
-  R.inMask = inMask; R.exitMask = exitMask; R.edgeMask = edgeMask;
+  R.exitMask = exitMask;
   if (exitMask) R.flags |= ZREC_HAS_EXIT;
 }
 
@@ -365,119 +355,179 @@ __device__ __forceinline__ double rcp_fast(double x) {
   r = fma(r, e, r);
   return r;
 }
-__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+// NV consecutive groups per lane (1: any G; 2: even G, 16-byte loads/stores)
+template <int NV> struct Vd { double v[NV]; };
+template <int NV> __device__ __forceinline__ Vd<NV> ld_stream(const double *p) {
+  Vd<NV> r;
+  if (NV == 2) { const double2 t = __ldcs(reinterpret_cast<const double2 *>(p)); r.v[0] = t.x; r.v[NV - 1] = t.y; }
+  else r.v[0] = __ldcs(p);
+  return r;
+}
+template <int NV> __device__ __forceinline__ Vd<NV> ld_l2(const double *p) {
+  Vd<NV> r;
+  if (NV == 2) { const double2 t = __ldcg(reinterpret_cast<const double2 *>(p)); r.v[0] = t.x; r.v[NV - 1] = t.y; }
+  else r.v[0] = __ldcg(p);
+  return r;
+}
+template <int NV> __device__ __forceinline__ void st_vec(double *p, const Vd<NV> &x) {
+  if (NV == 2) *reinterpret_cast<double2 *>(p) = make_double2(x.v[0], x.v[NV - 1]);
+  else *p = x.v[0];
+}
 
 constexpr int PLAN_STAGES = 3;
 constexpr int PLAN_ZMAX = 8;     // zones per item (records per stage)
+constexpr int PLAN_NCW = 4;      // consumer warps per CTA
+constexpr int PLAN_LANES = PLAN_NCW * 32;
 
 struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
 
+template <int NV>
 struct PlanSmem {
   ZoneRec recs[PLAN_STAGES][PLAN_ZMAX];
+  Vd<NV> Q[MAXC][PLAN_LANES], S[MAXC][PLAN_LANES];   // per-lane zone state, indexed by local corner
   StageMeta meta[PLAN_STAGES];
   unsigned long long full[PLAN_STAGES], empty[PLAN_STAGES];
 };
 
-// fast zone solve in solve-order ("position") space; everything indexed statically
+// Zone solve from a plan record: one pass over the corners in solve order.  Per corner: incident FP
+// fluxes (loaded one corner ahead), the EZ closure terms of its outgoing faces, the corner flux, and
+// its push into the downstream corners.  Q and the running sources live in shared memory (one column
+// per lane) because the downstream corner of an edge is only known from the record.
+template <int NV>
 __device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const ZoneRec *__restrict__ R, const double *__restrict__ psiA,
-                                                double *__restrict__ psi1A, double *__restrict__ psibA, int g) {
-  const int G = P.G, nc = P.nc;
-  const int c0 = R->c0;
-  const unsigned inMask = R->inMask, edgeMask = R->edgeMask, flags = R->flags;
+                                                double *__restrict__ psi1A, int g, Vd<NV> *__restrict__ Qs, Vd<NV> *__restrict__ Ss) {
+  const int G = P.G;
+  const unsigned flags = R->flags;
   const int NC = (int)(flags & 15u);
-  const int zone = R->zone0 - 1;
-  const double sig = ld_stream(P.sigt + (size_t)zone * G + g);
   const double tau = P.tau;
-  const size_t base = (size_t)c0 * G + g;
+  const Vd<NV> sig = ld_stream<NV>(P.sigt + (size_t)(R->zone0 - 1) * G + g);
+  const size_t base = (size_t)R->c0 * G + g;
   const double *ps = psiA + base, *st = P.stotal + base;
   double *out = psi1A + base;
+  const double *up = psi1A + g;
 
-  // phase 0: every global load of the zone is issued up front (no load sits behind a branch):
-  // 2 x NC streaming rows (Psi^n, STotal) and the incident FP-face rows, predicated on the record's mask
-  double Q[MAXC], src[MAXC], pf[MAXC][3];
-  const double *bdyBase = psibA - (size_t)nc * G;
-#pragma unroll
-  for (int p = 0; p < MAXC; p++) {
-    const int off = (int)R->localc[p] * G;
-    double a = 0.0, b = 0.0;
-    if (p < NC) { a = ld_stream(ps + off); b = ld_stream(st + off); }
-    Q[p] = fma(tau, a, b);
-    src[p] = R->vol[p] * Q[p];
-#pragma unroll
-    for (int f = 0; f < 3; f++) {
-      const int row = R->rowfp[p][f];
-      const double *bp = (row < nc ? psi1A : bdyBase) + (size_t)row * G + g;
-      double v = 0.0;
-      if (inMask & (1u << (p * 3 + f))) v = __ldcg(bp);
-      pf[p][f] = v;
-    }
-  }
-  const double *E = &R->edge[0][0];
-  const unsigned char *oj = R->oppj;
+  // all streaming rows of the zone first
 #pragma unroll
   for (int p = 0; p < MAXC; p++) {
     if (p < NC) {
-      const double vp = R->vol[p], qp = Q[p], sv = sig * vp;
-      // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); pf is 0 on the other faces
-      const double pf0 = pf[p][0], pf1 = pf[p][1], pf2 = pf[p][2];
-      src[p] = fma(-R->afp[p][0], pf0, src[p]);
-      src[p] = fma(-R->afp[p][1], pf1, src[p]);
-      src[p] = fma(-R->afp[p][2], pf2, src[p]);
-      const double *Ep = E;
-      // EZ faces leaving this corner (SweepUCBxyz.F90:182-252)
+      const int c = R->localc[p];
+      const Vd<NV> a = ld_stream<NV>(ps + c * G), b = ld_stream<NV>(st + c * G);
+      const double v = R->vol[p];
+      Vd<NV> q, s;
 #pragma unroll
-      for (int q = p + 1; q < MAXC; q++) {
-        if (edgeMask & (1u << pair_bit(p, q))) {
-          const double2 k01 = *reinterpret_cast<const double2 *>(E);
-          const double2 k2d0 = *reinterpret_cast<const double2 *>(E + 2);
-          const double2 d12 = *reinterpret_cast<const double2 *>(E + 4);
-          const double2 d3h = *reinterpret_cast<const double2 *>(E + 6);
-          const int jj = *oj;
-          const double dq = qp - Q[q];
-          double sez;
-          if (jj & 4) {
-            const int j = jj & 3;
-            const double po = j == 0 ? pf0 : (j == 1 ? pf1 : pf2);
-            const double gnum = fma(fma(k2d0.x, sv, k01.y), sv, k01.x);
-            const double gden = fma(fma(fma(d3h.x, sv, d12.y), sv, d12.x), sv, k2d0.y);
-            const double den = fma(gden, sig, gnum);
-            const double t1 = fma(sig, po, -qp);
-            const double num = fma(vp * gnum, t1, (d3h.y * gden) * dq);
-            sez = num * rcp_fast(den);
-          } else {
-            sez = d3h.y * dq * rcp_fast(sig);
-          }
-          src[p] += sez;
-          src[q] -= sez;
-          E += 10; oj++;
-        }
-      }
-      // corner flux and its push to the downstream corners (SweepUCBxyz.F90:261-281)
-      const double psi = src[p] * rcp_fast(R->sumArea[p] + sv);
-      out[(int)R->localc[p] * G] = psi;
-#pragma unroll
-      for (int q = p + 1; q < MAXC; q++) {
-        if (edgeMask & (1u << pair_bit(p, q))) {
-          src[q] = fma(Ep[8], psi, src[q]);
-          Ep += 10;
-        }
-      }
-      if (flags & ZREC_HAS_EXIT) {
-        const unsigned em = R->exitMask >> (p * 3);
-#pragma unroll
-        for (int f = 0; f < 3; f++)
-          if (em & (1u << f)) psibA[(size_t)(R->rowfp[p][f] - nc) * G + g] = psi;
-      }
+      for (int i = 0; i < NV; i++) { q.v[i] = fma(tau, a.v[i], b.v[i]); s.v[i] = v * q.v[i]; }
+      Qs[c * PLAN_LANES] = q;
+      Ss[c * PLAN_LANES] = s;
     }
+  }
+  Vd<NV> rsig;
+#pragma unroll
+  for (int i = 0; i < NV; i++) rsig.v[i] = rcp_fast(sig.v[i]);
+
+  const int *inRow = R->inRow;
+  const double *inAfp = R->inAfp;
+  const ZoneEdge *E = R->edge;
+  Vd<NV> pfN[3];
+  {
+    const int n0 = R->nIn[0];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) pfN[k].v[i] = 0.0;
+      if (k < n0) pfN[k] = ld_l2<NV>(up + (size_t)inRow[k] * G);
+    }
+  }
+#pragma unroll 1
+  for (int p = 0; p < NC; p++) {
+    Vd<NV> pfC[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pfC[k] = pfN[k];
+    const int nin = R->nIn[p], nout = R->nOut[p];
+    if (p + 1 < NC) {   // incident rows of the next corner, in flight while this one is solved
+      const int nn = R->nIn[p + 1];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (k < nn) pfN[k] = ld_l2<NV>(up + (size_t)inRow[nin + k] * G);
+    }
+    const int c = R->localc[p];
+    Vd<NV> s = Ss[c * PLAN_LANES];
+    const Vd<NV> qp = Qs[c * PLAN_LANES];
+    const double vp = R->vol[p];
+    Vd<NV> sv;
+#pragma unroll
+    for (int i = 0; i < NV; i++) sv.v[i] = sig.v[i] * vp;
+    // incident fluxes across FP faces (SweepUCBxyz.F90:139-161)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nin) {
+        const double af = inAfp[k];
+#pragma unroll
+        for (int i = 0; i < NV; i++) s.v[i] = fma(-af, pfC[k].v[i], s.v[i]);
+      }
+    // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), with x = sigma V / aez:
+    //   sez = V [N(x)(sigma psi_opp - Q) + D(x)(Q - Q_cez)/2] / (N(x) + x D(x)),
+    //   N = 1.82 x^2 + 4 x + 3,  D = 4 x^3 + 6 x^2 + 4 x + 2   (gnum = aez^4 N, gden = V aez^3 D)
+    Vd<NV> sezk[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nout) {
+        const ZoneEdge e = E[k];
+        const Vd<NV> qq = Qs[e.qc * PLAN_LANES];
+        if (e.oppk >= 0) {
+          const Vd<NV> po = e.oppk == 0 ? pfC[0] : (e.oppk == 1 ? pfC[1] : pfC[2]);
+#pragma unroll
+          for (int i = 0; i < NV; i++) {
+            const double x = sv.v[i] * e.ainv;
+            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+            const double den = fma(x, D, N);
+            const double t1 = fma(sig.v[i], po.v[i], -qp.v[i]);
+            const double num = fma(N, t1, (0.5 * D) * (qp.v[i] - qq.v[i]));
+            sezk[k].v[i] = (vp * num) * rcp_fast(den);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; i++) sezk[k].v[i] = (e.ha * (qp.v[i] - qq.v[i])) * rsig.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NV; i++) s.v[i] += sezk[k].v[i];
+      }
+    // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
+    const double sa = R->sumArea[p];
+    Vd<NV> psi;
+#pragma unroll
+    for (int i = 0; i < NV; i++) psi.v[i] = s.v[i] * rcp_fast(sa + sv.v[i]);
+    st_vec<NV>(out + c * G, psi);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nout) {
+        const int qi = E[k].qc * PLAN_LANES;
+        const double cp = E[k].cp;
+        Vd<NV> t = Ss[qi];
+#pragma unroll
+        for (int i = 0; i < NV; i++) t.v[i] = fma(cp, psi.v[i], t.v[i] - sezk[k].v[i]);
+        Ss[qi] = t;
+      }
+    if (flags & ZREC_HAS_EXIT) {
+      const unsigned em = R->exitMask >> (p * 3);
+#pragma unroll
+      for (int f = 0; f < 3; f++)
+        if (em & (1u << f)) st_vec<NV>(psi1A + (size_t)R->exitRow[p][f] * G + g, psi);
+    }
+    E += nout;
+    inRow += nin;
+    inAfp += nin;
   }
 }
 
-template <int NCW>
-__global__ void __launch_bounds__(NCW * 32 + 32) sweep3d_plan_kernel(Sweep3DParams P) {
+template <int NV, bool UNI>
+__global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PlanSmem &S = *reinterpret_cast<PlanSmem *>(smem_raw);
+  PlanSmem<NV> &S = *reinterpret_cast<PlanSmem<NV> *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = P.G;
+  const size_t slab = (size_t)(P.nc + P.nb) * G;
   if (tid == 0) {
     for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -485,7 +535,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32) sweep3d_plan_kernel(Sweep3DPara
   }
   __syncthreads();
 
-  if (warp == NCW) {
+  if (warp == PLAN_NCW) {
     // ---------------- producer warp ----------------
     bool more = true;
     int issued = 0;
@@ -511,12 +561,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32) sweep3d_plan_kernel(Sweep3DPara
           }
           // pull the item's Psi^n / STotal / Sigt rows into L2 ahead of the consumers
           if (lane < n && (G & 1) == 0) {
-            const int4 h = *reinterpret_cast<const int4 *>(src + lane);   // c0, zone0, inMask, exitMask
-            const unsigned flagsNC = src[lane].flags & 15u;
+            const int4 h = *reinterpret_cast<const int4 *>(src + lane);   // c0, zone0, flags, exitMask
+            const unsigned nCorner = (unsigned)h.z & 15u;
             const int zone = (h.y < 0 ? -h.y : h.y) - 1;
             const unsigned rowBytes = (unsigned)G * 8u;
-            l2_prefetch_bulk(P.psi + ((size_t)w.angle * P.nc + h.x) * G, rowBytes * flagsNC);
-            l2_prefetch_bulk(P.stotal + (size_t)h.x * G, rowBytes * flagsNC);
+            l2_prefetch_bulk(P.psi + (size_t)w.angle * slab + (size_t)h.x * G, rowBytes * nCorner);
+            l2_prefetch_bulk(P.stotal + (size_t)h.x * G, rowBytes * nCorner);
             l2_prefetch_bulk(P.sigt + (size_t)zone * G, rowBytes);
           }
           issued = k + 1;
@@ -539,23 +589,33 @@ __global__ void __launch_bounds__(NCW * 32 + 32) sweep3d_plan_kernel(Sweep3DPara
   }
 
   // ---------------- consumer warps ----------------
+  const int Gv = G / NV;   // lanes per zone
+  Vd<NV> *Qs = &S.Q[0][tid], *Ss = &S.S[0][tid];
   for (int k = 0;; k++) {
     const int s = k % PLAN_STAGES;
     mbar_wait(&S.full[s], (k / PLAN_STAGES) & 1);
     const StageMeta m = S.meta[s];
     if (m.n < 0) break;
     const int a = m.angle;
-    const double *psiA = P.psi + (size_t)a * P.nc * G;
-    double *psi1A = P.psi1 + (size_t)a * P.nc * G;
-    double *psibA = P.psib + (size_t)a * P.nb * G;
-    const int npairs = m.n * G;
-    for (int idx = tid; idx < npairs; idx += NCW * 32) {
-      const int zi = idx / G, g = idx - zi * G;
-      const ZoneRec *R = &S.recs[s][zi];
-      if (R->flags & ZREC_SLOW) solve_zone_slow(P, a, R->zone0, g);
-      else solve_zone_plan(P, R, psiA, psi1A, psibA, g);
+    const double *psiA = P.psi + (size_t)a * slab;
+    double *psi1A = P.psi1 + (size_t)a * slab;
+    const int npairs = m.n * Gv;
+    for (int idx0 = 0; idx0 < npairs; idx0 += PLAN_LANES) {
+      int idx = idx0 + tid;
+      int zi = idx / Gv;
+      if (UNI) zi = __shfl_sync(0xffffffffu, zi, 0);   // Gv % 32 == 0: the warp sits inside one zone
+      if (idx < npairs) {
+        const int g = (idx - zi * Gv) * NV;
+        const ZoneRec *R = &S.recs[s][zi];
+        if (R->flags & ZREC_SLOW) {
+#pragma unroll
+          for (int i = 0; i < NV; i++) solve_zone_slow(P, a, R->zone0, g + i);
+        } else {
+          solve_zone_plan<NV>(P, R, psiA, psi1A, g, Qs, Ss);
+        }
+      }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(PLAN_LANES) : "memory");
     if (tid == 0) {
       __threadfence();
       atomicAdd(&P.counters[1 + m.signal_idx], 1);
@@ -571,7 +631,7 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
   P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
-  P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1; P.psib = ctx->d_psib;
+  P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1;
   P.recs = ctx->d_recs;
 }
 
@@ -579,8 +639,8 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
 
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx) {
   if (ctx->use_plan) {
-    const int lanes = ctx->plan_ncw * 32;
-    int z = std::max(1, std::min(PLAN_ZMAX, 4 * lanes / std::max(ctx->G, 1)));   // ~4 rounds of the consumer warps
+    const int nv = (ctx->G % 2 == 0) ? 2 : 1;
+    int z = std::max(1, std::min(PLAN_ZMAX, 4 * PLAN_LANES * nv / std::max(ctx->G, 1)));   // ~4 rounds of the consumer warps
     if (const char *e = getenv("UMT_ZONES_PER_ITEM")) z = std::max(1, std::min(PLAN_ZMAX, atoi(e)));
     return z;
   }
@@ -610,21 +670,17 @@ int umt_build_plan3d(umt_ctx *ctx) {
   return UMT_OK;
 }
 
-template <int NCW>
+template <int NV, bool UNI>
 static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
-  const int threads = NCW * 32 + 32;
-  const size_t smem = sizeof(PlanSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel<NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const int threads = PLAN_LANES + 32;
+  const size_t smem = sizeof(PlanSmem<NV>);
+  UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel<NV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel<NCW>, threads, smem));
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel<NV, UNI>, threads, smem));
   if (occ < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweep3d_plan_kernel does not fit on an SM");
   if (const char *e = getenv("UMT_PLAN_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
   int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
-  sweep3d_plan_kernel<NCW><<<grid, threads, smem, ctx->stream>>>(P);
+  sweep3d_plan_kernel<NV, UNI><<<grid, threads, smem, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   return UMT_OK;
 }
@@ -638,7 +694,12 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   if (ctx->use_plan) {
     if (!ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
-    int r = ctx->plan_ncw == 8 ? launch_plan<8>(ctx, P) : launch_plan<4>(ctx, P);
+    int nv = (ctx->G % 2 == 0) ? 2 : 1;
+    if (const char *e = getenv("UMT_PLAN_NV")) if (atoi(e) == 1) nv = 1;
+    const bool uni = ((ctx->G / nv) % 32) == 0;
+    int r;
+    if (nv == 2) r = uni ? launch_plan<2, true>(ctx, P) : launch_plan<2, false>(ctx, P);
+    else r = uni ? launch_plan<1, true>(ctx, P) : launch_plan<1, false>(ctx, P);
     if (r) return r;
   } else {
     int occ = 0;

@@ -74,7 +74,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
   void *ptrs[] = {ctx->d_numCorner, ctx->d_cOffSet, ctx->d_nCFaces, ctx->d_cFP, ctx->d_cEZ, ctx->d_Volume, ctx->d_Afp,
                   ctx->d_Aez, ctx->d_Area, ctx->d_RadiusFP, ctx->d_RadiusEZ, ctx->d_omega, ctx->d_weight, ctx->d_nextZ,
                   ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
-                  ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_psib, ctx->d_stotal,
+                  ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
                   ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto &s : ctx->shared) {
@@ -388,17 +388,19 @@ static int ensure_state(umt_ctx *ctx) {
   NEED_DEVICE(ctx, "device state");
   if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "set the quadrature before uploading state");
   if (ctx->d_psi) return UMT_OK;
-  const size_t G = ctx->G, nc = ctx->nc, nb = std::max(ctx->nb, 1), NA = ctx->NA;
-  ctx->psi_elems = G * nc * NA;
+  // Psi and Psi1 are both (G, ncornr+nbelem, NA): like Set%Psi1 in the reference (SetData_mod.F90:164)
+  // the boundary-element rows follow the corner rows, so a cFP value addresses either kind of
+  // upstream row directly; Set%PsiB(:,:,a) *is* the tail of the buffer currently playing Psi1.
+  const size_t G = ctx->G, nc = ctx->nc, NA = ctx->NA;
+  ctx->rows = ctx->nc + ctx->nb;
+  ctx->psi_elems = G * ctx->rows * NA;
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi, sizeof(double) * ctx->psi_elems));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi1, sizeof(double) * ctx->psi_elems));
-  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psib, sizeof(double) * G * nb * NA));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_stotal, sizeof(double) * G * nc));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_sigt, sizeof(double) * G * ctx->nz));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_phi, sizeof(double) * G * nc));
   UMT_CUDA(ctx, cudaMemset(ctx->d_psi, 0, sizeof(double) * ctx->psi_elems));
   UMT_CUDA(ctx, cudaMemset(ctx->d_psi1, 0, sizeof(double) * ctx->psi_elems));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_psib, 0, sizeof(double) * G * nb * NA));
   UMT_CUDA(ctx, cudaMemset(ctx->d_stotal, 0, sizeof(double) * G * nc));
   UMT_CUDA(ctx, cudaMemset(ctx->d_sigt, 0, sizeof(double) * G * ctx->nz));
   UMT_CUDA(ctx, cudaMemset(ctx->d_phi, 0, sizeof(double) * G * nc));
@@ -414,9 +416,9 @@ extern "C" int umt_upload_state(umt_ctx *ctx, const double *Psi, const double *P
   if (!ctx) return UMT_ERR_ARG;
   if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   TRY(ensure_state(ctx));
-  const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb, NA = ctx->NA;
-  if (Psi) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_psi, Psi, sizeof(double) * G * nc * NA, cudaMemcpyHostToDevice, ctx->stream));
-  if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_psib, PsiB, sizeof(double) * G * nb * NA, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb, NA = ctx->NA, pitch = G * ctx->rows * 8;
+  if (Psi) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi, pitch, Psi, G * nc * 8, G * nc * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
+  if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + G * nc, pitch, PsiB, G * nb * 8, G * nb * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
   if (Sigt) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt, sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, ctx->stream));
   if (STotal) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal, sizeof(double) * G * nc, cudaMemcpyHostToDevice, ctx->stream));
   ctx->tau = tau;
@@ -434,12 +436,12 @@ static int set_copy(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles,
   const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   for (int a = 0; a < NumAngles; a++) {
     if (Psi) {
-      double *d = ctx->d_psi + ((size_t)(angle0 + a) * nc) * G + g0, *h = Psi + (size_t)a * nc * Groups;
+      double *d = ctx->d_psi + ((size_t)(angle0 + a) * ctx->rows) * G + g0, *h = Psi + (size_t)a * nc * Groups;
       if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
       else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
     }
     if (PsiB && nb) {
-      double *d = ctx->d_psib + ((size_t)(angle0 + a) * nb) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
+      double *d = ctx->d_psi1 + ((size_t)(angle0 + a) * ctx->rows + nc) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
       if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
       else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
     }
@@ -455,18 +457,28 @@ extern "C" int umt_download_set(umt_ctx *ctx, int g0, int Groups, int angle0, in
   return set_copy(ctx, g0, Groups, angle0, NumAngles, Psi, PsiB, false);
 }
 
-static int download(umt_ctx *ctx, double *h, const double *d, size_t n) {
+// rows x NA strided download: `width` doubles per angle starting `offset` doubles into each angle slab
+static int download(umt_ctx *ctx, double *h, const double *d, size_t offset, size_t width, size_t count, size_t pitch) {
   if (!ctx || !h) return UMT_ERR_ARG;
   NEED_DEVICE(ctx, "download");
   if (!d) UMT_FAIL(ctx, UMT_ERR_STATE, "no device state to download");
   if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  UMT_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (width && count) UMT_CUDA(ctx, cudaMemcpy2DAsync(h, width * 8, d + offset, pitch * 8, width * 8, count, cudaMemcpyDeviceToHost, ctx->stream));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return UMT_OK;
 }
-extern "C" int umt_download_psi(umt_ctx *ctx, double *Psi) { return download(ctx, Psi, ctx ? ctx->d_psi : nullptr, ctx ? ctx->psi_elems : 0); }
-extern "C" int umt_download_psib(umt_ctx *ctx, double *PsiB) { return download(ctx, PsiB, ctx ? ctx->d_psib : nullptr, ctx ? (size_t)ctx->G * ctx->nb * ctx->NA : 0); }
-extern "C" int umt_download_phi(umt_ctx *ctx, double *Phi) { return download(ctx, Phi, ctx ? ctx->d_phi : nullptr, ctx ? (size_t)ctx->G * ctx->nc : 0); }
+extern "C" int umt_download_psi(umt_ctx *ctx, double *Psi) {
+  if (!ctx) return UMT_ERR_ARG;
+  return download(ctx, Psi, ctx->d_psi, 0, (size_t)ctx->G * ctx->nc, ctx->NA, (size_t)ctx->G * ctx->rows);
+}
+extern "C" int umt_download_psib(umt_ctx *ctx, double *PsiB) {
+  if (!ctx) return UMT_ERR_ARG;
+  return download(ctx, PsiB, ctx->d_psi1, (size_t)ctx->G * ctx->nc, (size_t)ctx->G * ctx->nb, ctx->NA, (size_t)ctx->G * ctx->rows);
+}
+extern "C" int umt_download_phi(umt_ctx *ctx, double *Phi) {
+  if (!ctx) return UMT_ERR_ARG;
+  return download(ctx, Phi, ctx->d_phi, 0, (size_t)ctx->G * ctx->nc, 1, (size_t)ctx->G * ctx->nc);
+}
 
 extern "C" int umt_synchronize(umt_ctx *ctx) {
   if (!ctx) return UMT_ERR_ARG;
@@ -484,40 +496,43 @@ extern "C" int umt_synchronize(umt_ctx *ctx) {
 // pair of groups; every angle slab is read once, coalesced, 16 bytes per thread.
 __global__ void __launch_bounds__(256) phi_reduce_kernel(const double *__restrict__ psi, const double *__restrict__ w,
                                                          const unsigned char *__restrict__ skip, double *__restrict__ phi,
-                                                         size_t n, int NA, double *__restrict__ psi_scale /* optional (nc) */, int G) {
+                                                         size_t n, int NA, size_t stride /* doubles between angle slabs */) {
   const size_t i2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (i2 >= n) return;
-  if (i2 + 1 < n) {
+  if (i2 + 1 < n && (stride & 1) == 0) {
     double2 s = make_double2(0.0, 0.0);
+#pragma unroll 8
     for (int a = 0; a < NA; a++) {
       if (skip && skip[a]) continue;
-      const double2 v = __ldcs(reinterpret_cast<const double2 *>(psi + (size_t)a * n + i2));
+      const double2 v = __ldcs(reinterpret_cast<const double2 *>(psi + (size_t)a * stride + i2));
       const double wa = w[a];
       s.x = s.x + wa * v.x;
       s.y = s.y + wa * v.y;
     }
     *reinterpret_cast<double2 *>(phi + i2) = s;
   } else {
-    double s = 0.0;
-    for (int a = 0; a < NA; a++) {
-      if (skip && skip[a]) continue;
-      s = s + w[a] * psi[(size_t)a * n + i2];
+    for (size_t i = i2; i < n && i < i2 + 2; i++) {
+      double s = 0.0;
+      for (int a = 0; a < NA; a++) {
+        if (skip && skip[a]) continue;
+        s = s + w[a] * psi[(size_t)a * stride + i];
+      }
+      phi[i] = s;
     }
-    phi[i2] = s;
   }
 }
 
 // Psi(:,c,a) *= VolumeOld(c)/Volume(c)   (initPhiTotal_OMPOL.F90:160-165)
-__global__ void scale_psi_kernel(double *psi, const double *ratio, size_t ncG, int G, int NA) {
+__global__ void scale_psi_kernel(double *psi, const double *ratio, size_t ncG, int G, int NA, size_t stride) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncG) return;
   const double r = ratio[i / G];
-  for (int a = 0; a < NA; a++) psi[(size_t)a * ncG + i] *= r;
+  for (int a = 0; a < NA; a++) psi[(size_t)a * stride + i] *= r;
 }
 
 // K6: Psi1(:,c) <- cyclePsi(:,m)  /  cyclePsi(:,m) <- Psi1(:,c)   (constructDynMemory.F90:111-213)
-__global__ void cycle_copy_kernel(double *field /* (NA,nc,G) */, double *cyclePsi, const int *cycleList, const int *cycleAngle,
-                                  int total, int nc, int G, int toField) {
+__global__ void cycle_copy_kernel(double *field /* (NA,rows,G) */, double *cyclePsi, const int *cycleList, const int *cycleAngle,
+                                  int total, int nc /* rows per angle */, int G, int toField) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)total * G) return;
   const int m = (int)(i / G), g = (int)(i - (size_t)m * G);
@@ -527,12 +542,12 @@ __global__ void cycle_copy_kernel(double *field /* (NA,nc,G) */, double *cyclePs
 }
 
 // PsiB(:,b,a) <- Psi(:,c,a) on exiting boundary elements (initializeRadiationField_OMPOL.F90:116-143)
-__global__ void exit_copy_kernel(const double *psi, double *psib, const int *eb, const int *ec, const int *ea, int nExit,
-                                 int nc, int nb, int G) {
+__global__ void exit_copy_kernel(const double *psi, double *psi1, const int *eb, const int *ec, const int *ea, int nExit,
+                                 int nc, int rows, int G) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)nExit * G) return;
   const int m = (int)(i / G), g = (int)(i - (size_t)m * G);
-  psib[((size_t)ea[m] * nb + eb[m]) * G + g] = psi[((size_t)ea[m] * nc + ec[m]) * G + g];
+  psi1[((size_t)ea[m] * rows + nc + eb[m]) * G + g] = psi[((size_t)ea[m] * rows + ec[m]) * G + g];
 }
 
 static int launch_phi(umt_ctx *ctx, const double *field) {
@@ -544,7 +559,7 @@ static int launch_phi(umt_ctx *ctx, const double *field) {
     // starting / finishing directions carry zero weight (rt/rtquad.F90:107-127) and are not tallied
     // (SweepUCBrz.F90:233-239); weight==0 makes the product exact, no skip array needed.
   }
-  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field, ctx->d_weight, d_skip, ctx->d_phi, n, ctx->NA, nullptr, ctx->G);
+  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field, ctx->d_weight, d_skip, ctx->d_phi, n, ctx->NA, (size_t)ctx->rows * ctx->G);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches += 1;
   return UMT_OK;
@@ -558,7 +573,7 @@ extern "C" int umt_init_phi_total(umt_ctx *ctx, const double *volRatio) {
     double *d_r = nullptr;
     TRY(dev_alloc_copy(ctx, &d_r, volRatio, (size_t)ctx->nc));
     const size_t n = (size_t)ctx->nc * ctx->G;
-    scale_psi_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, d_r, n, ctx->G, ctx->NA);
+    scale_psi_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, d_r, n, ctx->G, ctx->NA, (size_t)ctx->rows * ctx->G);
     UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_r);
   }
@@ -574,14 +589,14 @@ extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
   TRY(finalize_schedule(ctx));
   if (ctx->nExit > 0) {
     const size_t n = (size_t)ctx->nExit * ctx->G;
-    exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_psib, ctx->d_exitB, ctx->d_exitC,
-                                                                      ctx->d_exitA, ctx->nExit, ctx->nc, ctx->nb, ctx->G);
+    exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_psi1, ctx->d_exitB, ctx->d_exitC,
+                                                                      ctx->d_exitA, ctx->nExit, ctx->nc, ctx->rows, ctx->G);
     UMT_CUDA(ctx, cudaGetLastError());
   }
   if (ctx->totalCycles > 0) {
     const size_t n = (size_t)ctx->totalCycles * ctx->G;
     cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_cyclePsi, ctx->d_cycleList,
-                                                                       ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 0);
+                                                                       ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 0);
     UMT_CUDA(ctx, cudaGetLastError());
   }
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -615,7 +630,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
     if (ctx->totalCycles > 0) {                     // initFromCycleList
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
       cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
-                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 1);
+                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 1);
       ctx->last_launches++;
     }
     if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx));
@@ -623,7 +638,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
     if (ctx->totalCycles > 0) {                     // updateCycleList
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
       cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
-                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->nc, ctx->G, 0);
+                                                                         ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 0);
       ctx->last_launches++;
     }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -644,7 +659,16 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
   cudaEventElapsedTime(&ms_phi, ctx->ev[5], ctx->ev[6]);
   cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
-  if (savePsi) std::swap(ctx->d_psi, ctx->d_psi1);   // Psi(:,:,Angle) <- Psi1 for every angle, without a copy
+  if (savePsi) {
+    // Psi(:,:,Angle) <- Psi1 for every angle without a copy: the buffers trade roles, and the
+    // boundary rows (PsiB) move over to the buffer that plays Psi1 from now on
+    std::swap(ctx->d_psi, ctx->d_psi1);
+    if (ctx->nb > 0) {
+      const size_t G = ctx->G, pitch = G * ctx->rows * 8, off = G * ctx->nc;
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + off, pitch, ctx->d_psi + off, pitch, G * ctx->nb * 8, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+      UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   ctx->last_ms[0] = ms_sweep; ctx->last_ms[1] = ms_phi; ctx->last_ms[2] = ms_exch; ctx->last_ms[3] = ms_all;
   if (itersDone) *itersDone = iter;
   return UMT_OK;

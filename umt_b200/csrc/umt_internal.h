@@ -17,23 +17,27 @@ struct WorkItem {       // one chunk of one hyperplane of one angle
   int pad0, pad1;
 };
 
-// Plan record of one (zone, angle) for the 3-D plan kernel (sweep3d.cu): the zone's
-// corners relabelled into solve order ("positions"), omega.A products, upstream rows and
-// the group-independent coefficients of the corner-balance closure.
+// Plan record of one (zone, angle) for the 3-D plan kernel (sweep3d.cu): the zone's corners
+// relabelled into solve order ("positions"), omega.A products, upstream rows and the
+// group-independent pieces of the corner-balance closure, as compact lists in position order.
 enum { ZREC_SLOW = 16u, ZREC_HAS_EXIT = 32u };   // flags bits above the corner count (bits 0..3)
+struct ZoneEdge {                // EZ face carrying flux from position p into a later position
+  double ainv, cp, ha;           // 1/aez, coefpsi (SweepUCBxyz.F90:168-179), aez/2
+  int qc, oppk;                  // local corner id of the downstream corner; index of the opposite incident FP face in p's list, -1 if none
+};
 struct alignas(16) ZoneRec {
   int c0, zone0;                 // first corner row of the zone; signed 1-based zone id from nextZ
-  unsigned inMask, exitMask;     // bit p*3+f: FP face f of position p is incident / exits through the boundary
-  unsigned edgeMask, flags;      // bit pair_bit(p,q): EZ face from position p into position q
+  unsigned flags, exitMask;      // NC | ZREC_*; bit p*3+f: FP face f of position p exits through the boundary
   unsigned char localc[8];       // local corner id at position p (nextC order)
-  unsigned char oppj[12];        // per edge slot: opposite FP face index | 4 if that face is incident
-  int pad;
-  int rowfp[8][3];               // Psi1 row behind FP face f (>= ncornr: boundary element row)
-  double afp[8][3];              // omega . A_fp
-  double vol[8], sumArea[8];
-  double edge[12][10];           // k0,k1,k2 (gnum), d0..d3 (gden), aez/2, coefpsi, pad
+  unsigned char nIn[8], nOut[8]; // incident FP faces / outgoing EZ faces of position p
+  unsigned char pad[8];
+  double vol[8], sumArea[8];     // by position
+  int inRow[16];                 // Psi1 row behind each incident FP face (>= ncornr: boundary-element row)
+  double inAfp[16];              // omega . A_fp (< 0) of that face
+  ZoneEdge edge[12];
+  int exitRow[8][3];             // boundary-element row behind exiting FP face f of position p
 };
-static_assert(sizeof(ZoneRec) == 1424, "ZoneRec layout");
+static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 848, "ZoneRec layout");
 
 struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int neighbor;
@@ -89,7 +93,9 @@ struct umt_ctx {
   int *d_exitB = nullptr, *d_exitC = nullptr, *d_exitA = nullptr; int nExit = 0;  // flattened bdyList over angles
   std::vector<int> exitOff;            // per-angle offsets into d_exit*
   // device: state
-  double *d_psi = nullptr, *d_psi1 = nullptr, *d_psib = nullptr, *d_stotal = nullptr, *d_sigt = nullptr, *d_phi = nullptr;
+  // d_psi, d_psi1: (NA, rows = nc+nb, G); the nb tail rows of d_psi1 are Set%PsiB
+  double *d_psi = nullptr, *d_psi1 = nullptr, *d_stotal = nullptr, *d_sigt = nullptr, *d_phi = nullptr;
+  int rows = 0;
   double *d_psim = nullptr;            // RZ half-angle intensity (G,nc) per xi-level
   size_t psi_elems = 0;
 
