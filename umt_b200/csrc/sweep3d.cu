@@ -24,6 +24,7 @@
 // Upstream Psi1 rows were written a few planes earlier by other CTAs and are read
 // through L2 (ld.global.cg) — L1 is not coherent across SMs.
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
 
 #include "umt_internal.h"
@@ -35,7 +36,7 @@ constexpr int MAXCF = 3;   // corner faces
 constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 
 struct Sweep3DParams {
-  int nc, nb, nz, G, NA, nItems;
+  int nc, nb, nz, G, NA, nItems, zonesPerItem;
   double tau;
   const int *numCorner, *cOffSet, *nCFaces, *cFP /* 0-based row; >= nc: boundary */, *cEZ /* 0-based */;
   const double *Volume, *Afp, *Aez, *omega;
@@ -46,6 +47,7 @@ struct Sweep3DParams {
   const double *psi, *stotal, *sigt;
   double *psi1;
   const ZoneRec *recs;
+  const int2 *zinfo;       // (NA, nz) in sweep order: first corner row, zone | numCorner << 28
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
   double afp[MAXC][3], aez[MAXC][3];
   signed char kOfFace[MAXC][3];
   unsigned exitMask = 0;
-  int nInTot = 0;
+  for (int p = 0; p < MAXC; p++)
+    for (int k = 0; k < 3; k++) { R.inRow[p][k] = 0; R.inAfp[p][k] = 0.0; R.exitRow[p][k] = 0; }
   for (int p = 0; p < NC && !slow; p++) {
     const int c = R.localc[p], cc = c0 + c;
     double sa = 0.0;
@@ -254,11 +257,10 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
         sa += afp[p][f];
         if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
       } else if (afp[p][f] < 0.0) {
-        if (nInTot >= 16) { slow = true; break; }
-        R.inRow[nInTot] = row;
-        R.inAfp[nInTot] = afp[p][f];
+        R.inRow[p][nin] = row;
+        R.inAfp[p][nin] = afp[p][f];
         kOfFace[p][f] = (signed char)nin;
-        nin++; nInTot++;
+        nin++;
       }
     }
     R.nIn[p] = (unsigned char)nin;
@@ -269,7 +271,6 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
     R.sumArea[p] = sa;
     R.vol[p] = B.Volume[cc];
   }
-  for (int k = nInTot; k < 16; k++) { R.inRow[k] = 0; R.inAfp[k] = 0.0; }
   // outgoing EZ faces grouped by upstream position, downstream position ascending
   int slot = 0;
   for (int p = 0; p < NC && !slow; p++) {
@@ -356,177 +357,181 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
-// NV consecutive groups per lane (1: any G; 2: even G, 16-byte loads/stores)
-template <int NV> struct Vd { double v[NV]; };
-template <int NV> __device__ __forceinline__ Vd<NV> ld_stream(const double *p) {
-  Vd<NV> r;
-  if (NV == 2) { const double2 t = __ldcs(reinterpret_cast<const double2 *>(p)); r.v[0] = t.x; r.v[NV - 1] = t.y; }
-  else r.v[0] = __ldcs(p);
-  return r;
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "  mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "  selp.u32 %0, 1, 0, p; }\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
-template <int NV> __device__ __forceinline__ Vd<NV> ld_l2(const double *p) {
-  Vd<NV> r;
-  if (NV == 2) { const double2 t = __ldcg(reinterpret_cast<const double2 *>(p)); r.v[0] = t.x; r.v[NV - 1] = t.y; }
-  else r.v[0] = __ldcg(p);
-  return r;
-}
-template <int NV> __device__ __forceinline__ void st_vec(double *p, const Vd<NV> &x) {
-  if (NV == 2) *reinterpret_cast<double2 *>(p) = make_double2(x.v[0], x.v[NV - 1]);
-  else *p = x.v[0];
+// L2 eviction-priority policies (the encodings CUTLASS names TMA::CacheHintSm90::EVICT_FIRST / EVICT_LAST)
+constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
-constexpr int PLAN_STAGES = 3;
-constexpr int PLAN_ZMAX = 8;     // zones per item (records per stage)
+// two consecutive groups per lane: 16-byte loads/stores, the record decode is shared by both
+struct V2 { double x, y; };
+__device__ __forceinline__ V2 ld_l2(const double *p) {   // upstream Psi1 rows: written by other SMs, L1 must be bypassed
+  V2 r;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_keep(double *p, const V2 &v) {   // Psi1 rows: wanted again from L2 by the downstream zones
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(L2_EVICT_LAST) : "memory");
+}
+
+constexpr int PLAN_STAGES = 2;
+constexpr int PLAN_ZMAX = 8;     // zones per item (one round of the consumer warps)
 constexpr int PLAN_NCW = 4;      // consumer warps per CTA
 constexpr int PLAN_LANES = PLAN_NCW * 32;
 
 struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
 
-template <int NV>
+// One pipeline stage = one work item: its plan records and the TMA landing area of its
+// Psi^n / STotal / Sigt rows, [zone][corner][G] (a zone's corner rows are contiguous in HBM, so
+// each is one bulk copy).  The consumers turn the Psi^n area into Q and the STotal area into the
+// running sources in place: each lane only ever touches its own two columns.
+struct PlanStage {
+  V2 psi[MAXC * PLAN_LANES], st[MAXC * PLAN_LANES], sigt[PLAN_LANES];
+};
 struct PlanSmem {
-  ZoneRec recs[PLAN_STAGES][PLAN_ZMAX];
-  Vd<NV> Q[MAXC][PLAN_LANES], S[MAXC][PLAN_LANES];   // per-lane zone state, indexed by local corner
+  PlanStage stage[PLAN_STAGES];
   StageMeta meta[PLAN_STAGES];
   unsigned long long full[PLAN_STAGES], empty[PLAN_STAGES];
+  ZoneRec recs[1];   // [PLAN_STAGES][zonesPerItem], sized at launch
 };
+static size_t plan_smem_bytes(int zonesPerItem) { return offsetof(PlanSmem, recs) + (size_t)PLAN_STAGES * zonesPerItem * sizeof(ZoneRec); }
 
 // Zone solve from a plan record: one pass over the corners in solve order.  Per corner: incident FP
 // fluxes (loaded one corner ahead), the EZ closure terms of its outgoing faces, the corner flux, and
 // its push into the downstream corners.  Q and the running sources live in shared memory (one column
-// per lane) because the downstream corner of an edge is only known from the record.
-template <int NV>
-__device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const ZoneRec *__restrict__ R, const double *__restrict__ psiA,
-                                                double *__restrict__ psi1A, int g, Vd<NV> *__restrict__ Qs, Vd<NV> *__restrict__ Ss) {
+// per lane, stride Gv between corners) because the downstream corner of an edge is only known from the record.
+__device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const ZoneRec *__restrict__ R, double *__restrict__ psi1A, int g,
+                                                V2 *__restrict__ Qs, V2 *__restrict__ Ss, const V2 sig, const int Gv) {
   const int G = P.G;
   const unsigned flags = R->flags;
   const int NC = (int)(flags & 15u);
   const double tau = P.tau;
-  const Vd<NV> sig = ld_stream<NV>(P.sigt + (size_t)(R->zone0 - 1) * G + g);
-  const size_t base = (size_t)R->c0 * G + g;
-  const double *ps = psiA + base, *st = P.stotal + base;
-  double *out = psi1A + base;
+  double *out = psi1A + (size_t)R->c0 * G + g;
   const double *up = psi1A + g;
 
-  // all streaming rows of the zone first
+  // Q = STotal + tau Psi^n, src = V Q (SweepUCBxyz.F90:119-126), in place over the landed rows
 #pragma unroll
   for (int p = 0; p < MAXC; p++) {
     if (p < NC) {
-      const int c = R->localc[p];
-      const Vd<NV> a = ld_stream<NV>(ps + c * G), b = ld_stream<NV>(st + c * G);
+      const int ci = (int)R->localc[p] * Gv;
+      const V2 a = Qs[ci], b = Ss[ci];
       const double v = R->vol[p];
-      Vd<NV> q, s;
-#pragma unroll
-      for (int i = 0; i < NV; i++) { q.v[i] = fma(tau, a.v[i], b.v[i]); s.v[i] = v * q.v[i]; }
-      Qs[c * PLAN_LANES] = q;
-      Ss[c * PLAN_LANES] = s;
+      V2 q, s;
+      q.x = fma(tau, a.x, b.x); q.y = fma(tau, a.y, b.y);
+      s.x = v * q.x; s.y = v * q.y;
+      Qs[ci] = q;
+      Ss[ci] = s;
     }
   }
-  Vd<NV> rsig;
-#pragma unroll
-  for (int i = 0; i < NV; i++) rsig.v[i] = rcp_fast(sig.v[i]);
+  V2 rsig;
+  rsig.x = rcp_fast(sig.x); rsig.y = rcp_fast(sig.y);
 
-  const int *inRow = R->inRow;
-  const double *inAfp = R->inAfp;
   const ZoneEdge *E = R->edge;
-  Vd<NV> pfN[3];
+  V2 pfN[3];
   {
     const int n0 = R->nIn[0];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-#pragma unroll
-      for (int i = 0; i < NV; i++) pfN[k].v[i] = 0.0;
-      if (k < n0) pfN[k] = ld_l2<NV>(up + (size_t)inRow[k] * G);
+      pfN[k].x = 0.0; pfN[k].y = 0.0;
+      if (k < n0) pfN[k] = ld_l2(up + (size_t)R->inRow[0][k] * G);
     }
   }
 #pragma unroll 1
   for (int p = 0; p < NC; p++) {
-    Vd<NV> pfC[3];
+    V2 pfC[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) pfC[k] = pfN[k];
-    const int nin = R->nIn[p], nout = R->nOut[p];
+    const int nout = R->nOut[p];
     if (p + 1 < NC) {   // incident rows of the next corner, in flight while this one is solved
       const int nn = R->nIn[p + 1];
 #pragma unroll
       for (int k = 0; k < 3; k++)
-        if (k < nn) pfN[k] = ld_l2<NV>(up + (size_t)inRow[nin + k] * G);
+        if (k < nn) pfN[k] = ld_l2(up + (size_t)R->inRow[p + 1][k] * G);
     }
     const int c = R->localc[p];
-    Vd<NV> s = Ss[c * PLAN_LANES];
-    const Vd<NV> qp = Qs[c * PLAN_LANES];
+    V2 s = Ss[c * Gv];
+    const V2 qp = Qs[c * Gv];
     const double vp = R->vol[p];
-    Vd<NV> sv;
+    V2 sv;
+    sv.x = sig.x * vp; sv.y = sig.y * vp;
+    // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); unused slots carry afp = 0 and a finite pf
 #pragma unroll
-    for (int i = 0; i < NV; i++) sv.v[i] = sig.v[i] * vp;
-    // incident fluxes across FP faces (SweepUCBxyz.F90:139-161)
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      if (k < nin) {
-        const double af = inAfp[k];
-#pragma unroll
-        for (int i = 0; i < NV; i++) s.v[i] = fma(-af, pfC[k].v[i], s.v[i]);
-      }
+    for (int k = 0; k < 3; k++) {
+      const double af = R->inAfp[p][k];
+      s.x = fma(-af, pfC[k].x, s.x); s.y = fma(-af, pfC[k].y, s.y);
+    }
     // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), with x = sigma V / aez:
     //   sez = V [N(x)(sigma psi_opp - Q) + D(x)(Q - Q_cez)/2] / (N(x) + x D(x)),
     //   N = 1.82 x^2 + 4 x + 3,  D = 4 x^3 + 6 x^2 + 4 x + 2   (gnum = aez^4 N, gden = V aez^3 D)
-    Vd<NV> sezk[3];
+    V2 sezk[3];
 #pragma unroll
     for (int k = 0; k < 3; k++)
       if (k < nout) {
         const ZoneEdge e = E[k];
-        const Vd<NV> qq = Qs[e.qc * PLAN_LANES];
+        const V2 qq = Qs[e.qc * Gv];
         if (e.oppk >= 0) {
-          const Vd<NV> po = e.oppk == 0 ? pfC[0] : (e.oppk == 1 ? pfC[1] : pfC[2]);
-#pragma unroll
-          for (int i = 0; i < NV; i++) {
-            const double x = sv.v[i] * e.ainv;
+          const V2 po = e.oppk == 0 ? pfC[0] : (e.oppk == 1 ? pfC[1] : pfC[2]);
+          {
+            const double x = sv.x * e.ainv;
             const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
             const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
-            const double den = fma(x, D, N);
-            const double t1 = fma(sig.v[i], po.v[i], -qp.v[i]);
-            const double num = fma(N, t1, (0.5 * D) * (qp.v[i] - qq.v[i]));
-            sezk[k].v[i] = (vp * num) * rcp_fast(den);
+            const double num = fma(N, fma(sig.x, po.x, -qp.x), (0.5 * D) * (qp.x - qq.x));
+            sezk[k].x = (vp * num) * rcp_fast(fma(x, D, N));
+          }
+          {
+            const double x = sv.y * e.ainv;
+            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+            const double num = fma(N, fma(sig.y, po.y, -qp.y), (0.5 * D) * (qp.y - qq.y));
+            sezk[k].y = (vp * num) * rcp_fast(fma(x, D, N));
           }
         } else {
-#pragma unroll
-          for (int i = 0; i < NV; i++) sezk[k].v[i] = (e.ha * (qp.v[i] - qq.v[i])) * rsig.v[i];
+          sezk[k].x = (e.ha * (qp.x - qq.x)) * rsig.x;
+          sezk[k].y = (e.ha * (qp.y - qq.y)) * rsig.y;
         }
-#pragma unroll
-        for (int i = 0; i < NV; i++) s.v[i] += sezk[k].v[i];
+        s.x += sezk[k].x; s.y += sezk[k].y;
       }
     // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
     const double sa = R->sumArea[p];
-    Vd<NV> psi;
-#pragma unroll
-    for (int i = 0; i < NV; i++) psi.v[i] = s.v[i] * rcp_fast(sa + sv.v[i]);
-    st_vec<NV>(out + c * G, psi);
+    V2 psi;
+    psi.x = s.x * rcp_fast(sa + sv.x);
+    psi.y = s.y * rcp_fast(sa + sv.y);
+    st_keep(out + c * G, psi);
 #pragma unroll
     for (int k = 0; k < 3; k++)
       if (k < nout) {
-        const int qi = E[k].qc * PLAN_LANES;
+        const int qi = E[k].qc * Gv;
         const double cp = E[k].cp;
-        Vd<NV> t = Ss[qi];
-#pragma unroll
-        for (int i = 0; i < NV; i++) t.v[i] = fma(cp, psi.v[i], t.v[i] - sezk[k].v[i]);
+        V2 t = Ss[qi];
+        t.x = fma(cp, psi.x, t.x - sezk[k].x);
+        t.y = fma(cp, psi.y, t.y - sezk[k].y);
         Ss[qi] = t;
       }
     if (flags & ZREC_HAS_EXIT) {
       const unsigned em = R->exitMask >> (p * 3);
 #pragma unroll
       for (int f = 0; f < 3; f++)
-        if (em & (1u << f)) st_vec<NV>(psi1A + (size_t)R->exitRow[p][f] * G + g, psi);
+        if (em & (1u << f)) st_keep(psi1A + (size_t)R->exitRow[p][f] * G + g, psi);
     }
     E += nout;
-    inRow += nin;
-    inAfp += nin;
   }
 }
 
-template <int NV, bool UNI>
 __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PlanSmem<NV> &S = *reinterpret_cast<PlanSmem<NV> *>(smem_raw);
+  PlanSmem &S = *reinterpret_cast<PlanSmem *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int G = P.G;
+  const int G = P.G, Gv = G >> 1;   // lanes per zone
+  const int zr = P.zonesPerItem;
   const size_t slab = (size_t)(P.nc + P.nb) * G;
   if (tid == 0) {
     for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], 1); }
@@ -537,82 +542,91 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
 
   if (warp == PLAN_NCW) {
     // ---------------- producer warp ----------------
+    // issue(k): ticket -> item -> TMA of its records and Psi^n/STotal/Sigt rows into stage k%S (needs the stage empty);
+    // release(j): the item's upstream plane is complete -> second arrival on full[j%S].  Releases go first.
     bool more = true;
-    int issued = 0;
-    for (int k = 0;; k++) {
-      if (more) {
-        const int s = k % PLAN_STAGES;
-        if (k >= PLAN_STAGES) mbar_wait(&S.empty[s], ((k / PLAN_STAGES) - 1) & 1);
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&P.counters[0], 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= P.nItems) {
-          more = false;
-          if (lane == 0) { S.meta[s].n = -1; mbar_arrive(&S.full[s]); mbar_arrive(&S.full[s]); }
-        } else {
-          const WorkItem w = P.items[t];
-          const int n = w.zend - w.zbeg;
-          const ZoneRec *src = P.recs + (size_t)w.angle * P.nz + w.zbeg;
-          if (lane == 0) {
-            S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
-            S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
-            mbar_arrive_expect_tx(&S.full[s], (unsigned)(n * sizeof(ZoneRec)));
-            tma_load_1d(&S.recs[s][0], src, (unsigned)(n * sizeof(ZoneRec)), &S.full[s]);
-          }
-          // pull the item's Psi^n / STotal / Sigt rows into L2 ahead of the consumers
-          if (lane < n && (G & 1) == 0) {
-            const int4 h = *reinterpret_cast<const int4 *>(src + lane);   // c0, zone0, flags, exitMask
-            const unsigned nCorner = (unsigned)h.z & 15u;
-            const int zone = (h.y < 0 ? -h.y : h.y) - 1;
-            const unsigned rowBytes = (unsigned)G * 8u;
-            l2_prefetch_bulk(P.psi + (size_t)w.angle * slab + (size_t)h.x * G, rowBytes * nCorner);
-            l2_prefetch_bulk(P.stotal + (size_t)h.x * G, rowBytes * nCorner);
-            l2_prefetch_bulk(P.sigt + (size_t)zone * G, rowBytes);
-          }
-          issued = k + 1;
-        }
-      }
-      const int j = k - (PLAN_STAGES - 1);
-      if (j >= 0 && j < issued) {
-        const int s = j % PLAN_STAGES;
+    int nIssued = 0, nReleased = 0;
+    const unsigned rowBytes = (unsigned)G * 8u;
+    for (;;) {
+      bool progressed = false;
+      if (nReleased < nIssued) {
+        const int s = nReleased % PLAN_STAGES;
+        int ok = 1;
         if (lane == 0) {
-          const int wi = S.meta[s].wait_idx, wc = S.meta[s].wait_count;
-          if (wi >= 0)
-            while (ld_acquire(&P.counters[1 + wi]) < wc) __nanosleep(32);
-          mbar_arrive(&S.full[s]);
+          const int wi = S.meta[s].wait_idx;
+          ok = wi < 0 || ld_acquire(&P.counters[1 + wi]) >= S.meta[s].wait_count;
+          if (ok) mbar_arrive(&S.full[s]);
         }
-        __syncwarp();
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) { nReleased++; progressed = true; }
       }
-      if (!more && j + 1 >= issued) break;
+      if (more && nIssued - nReleased < PLAN_STAGES) {
+        const int k = nIssued, s = k % PLAN_STAGES;
+        int free_ = 1;
+        if (k >= PLAN_STAGES) {
+          if (lane == 0) free_ = mbar_test(&S.empty[s], ((k / PLAN_STAGES) - 1) & 1);
+          free_ = __shfl_sync(0xffffffffu, free_, 0);
+        }
+        if (free_) {
+          progressed = true;
+          int t = 0;
+          if (lane == 0) t = atomicAdd(&P.counters[0], 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= P.nItems) {
+            more = false;
+            if (lane == 0) { S.meta[s].n = -1; mbar_arrive(&S.full[s]); mbar_arrive(&S.full[s]); }
+          } else {
+            const WorkItem w = P.items[t];
+            const int n = w.zend - w.zbeg;
+            const size_t first = (size_t)w.angle * P.nz + w.zbeg;
+            int2 zi = make_int2(0, 0);
+            unsigned bytes = 0;
+            if (lane < n) {
+              zi = P.zinfo[first + lane];                       // c0, zone | NC << 28
+              bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
+            }
+            bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
+            PlanStage &st = S.stage[s];
+            if (lane == 0) {
+              S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
+              S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
+              mbar_arrive_expect_tx(&S.full[s], bytes);
+              tma_load_1d_hint(&S.recs[s * zr], P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[s], L2_EVICT_FIRST);
+            }
+            __syncwarp();
+            if (lane < n) {
+              const unsigned nCorner = (unsigned)zi.y >> 28;
+              const int zone = zi.y & 0x0fffffff;
+              tma_load_1d_hint(&st.psi[lane * MAXC * Gv], P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
+              tma_load_1d_hint(&st.st[lane * MAXC * Gv], P.stotal + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
+              tma_load_1d_hint(&st.sigt[lane * Gv], P.sigt + (size_t)zone * G, rowBytes, &S.full[s], L2_EVICT_FIRST);
+            }
+            nIssued++;
+          }
+        }
+      }
+      if (!more && nReleased == nIssued) break;
+      if (!progressed) __nanosleep(64);
     }
     return;
   }
 
   // ---------------- consumer warps ----------------
-  const int Gv = G / NV;   // lanes per zone
-  Vd<NV> *Qs = &S.Q[0][tid], *Ss = &S.S[0][tid];
+  const int zi = tid / Gv, li = tid - zi * Gv;   // my zone of the item, my column in it
   for (int k = 0;; k++) {
     const int s = k % PLAN_STAGES;
     mbar_wait(&S.full[s], (k / PLAN_STAGES) & 1);
     const StageMeta m = S.meta[s];
     if (m.n < 0) break;
-    const int a = m.angle;
-    const double *psiA = P.psi + (size_t)a * slab;
-    double *psi1A = P.psi1 + (size_t)a * slab;
-    const int npairs = m.n * Gv;
-    for (int idx0 = 0; idx0 < npairs; idx0 += PLAN_LANES) {
-      int idx = idx0 + tid;
-      int zi = idx / Gv;
-      if (UNI) zi = __shfl_sync(0xffffffffu, zi, 0);   // Gv % 32 == 0: the warp sits inside one zone
-      if (idx < npairs) {
-        const int g = (idx - zi * Gv) * NV;
-        const ZoneRec *R = &S.recs[s][zi];
-        if (R->flags & ZREC_SLOW) {
-#pragma unroll
-          for (int i = 0; i < NV; i++) solve_zone_slow(P, a, R->zone0, g + i);
-        } else {
-          solve_zone_plan<NV>(P, R, psiA, psi1A, g, Qs, Ss);
-        }
+    if (zi < m.n) {
+      PlanStage &st = S.stage[s];
+      const ZoneRec *R = &S.recs[s * zr + zi];
+      double *psi1A = P.psi1 + (size_t)m.angle * slab;
+      if (R->flags & ZREC_SLOW) {
+        solve_zone_slow(P, m.angle, R->zone0, 2 * li);
+        solve_zone_slow(P, m.angle, R->zone0, 2 * li + 1);
+      } else {
+        solve_zone_plan(P, R, psi1A, 2 * li, &st.psi[zi * MAXC * Gv + li], &st.st[zi * MAXC * Gv + li], st.sigt[zi * Gv + li], Gv);
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(PLAN_LANES) : "memory");
@@ -627,21 +641,21 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
 void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.nc = ctx->nc; P.nb = ctx->nb; P.nz = ctx->nz; P.G = ctx->G; P.NA = ctx->NA; P.nItems = ctx->nItems;
   P.tau = ctx->tau;
+  P.zonesPerItem = ctx->zones_per_item;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
   P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
   P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1;
-  P.recs = ctx->d_recs;
+  P.recs = ctx->d_recs; P.zinfo = ctx->d_zinfo;
 }
 
 }  // namespace
 
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx) {
-  if (ctx->use_plan) {
-    const int nv = (ctx->G % 2 == 0) ? 2 : 1;
-    int z = std::max(1, std::min(PLAN_ZMAX, 4 * PLAN_LANES * nv / std::max(ctx->G, 1)));   // ~4 rounds of the consumer warps
-    if (const char *e = getenv("UMT_ZONES_PER_ITEM")) z = std::max(1, std::min(PLAN_ZMAX, atoi(e)));
+  if (ctx->use_plan) {   // one round of the consumer warps: 2 groups per lane
+    int z = std::max(1, std::min(PLAN_ZMAX, 2 * PLAN_LANES / std::max(ctx->G, 1)));
+    if (const char *e = getenv("UMT_ZONES_PER_ITEM")) z = std::max(1, std::min(z, atoi(e)));
     return z;
   }
   int pairs_target = 512;
@@ -670,17 +684,16 @@ int umt_build_plan3d(umt_ctx *ctx) {
   return UMT_OK;
 }
 
-template <int NV, bool UNI>
 static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
   const int threads = PLAN_LANES + 32;
-  const size_t smem = sizeof(PlanSmem<NV>);
-  UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel<NV, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = plan_smem_bytes(ctx->zones_per_item);
+  UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel<NV, UNI>, threads, smem));
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel, threads, smem));
   if (occ < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweep3d_plan_kernel does not fit on an SM");
   if (const char *e = getenv("UMT_PLAN_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
   int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
-  sweep3d_plan_kernel<NV, UNI><<<grid, threads, smem, ctx->stream>>>(P);
+  sweep3d_plan_kernel<<<grid, threads, smem, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   return UMT_OK;
 }
@@ -694,12 +707,7 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   if (ctx->use_plan) {
     if (!ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
-    int nv = (ctx->G % 2 == 0) ? 2 : 1;
-    if (const char *e = getenv("UMT_PLAN_NV")) if (atoi(e) == 1) nv = 1;
-    const bool uni = ((ctx->G / nv) % 32) == 0;
-    int r;
-    if (nv == 2) r = uni ? launch_plan<2, true>(ctx, P) : launch_plan<2, false>(ctx, P);
-    else r = uni ? launch_plan<1, true>(ctx, P) : launch_plan<1, false>(ctx, P);
+    int r = launch_plan(ctx, P);
     if (r) return r;
   } else {
     int occ = 0;

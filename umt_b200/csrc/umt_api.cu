@@ -75,7 +75,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_Aez, ctx->d_Area, ctx->d_RadiusFP, ctx->d_RadiusEZ, ctx->d_omega, ctx->d_weight, ctx->d_nextZ,
                   ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
-                  ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs};
+                  ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (auto &s : ctx->shared) {
     if (s.d_send_idx) cudaFree(s.d_send_idx);
@@ -292,11 +292,12 @@ static int finalize_schedule(umt_ctx *ctx) {
   // work items: plane-major, angle-minor.  RZ angles of one xi-level are chained
   // (PsiM dependency, SweepUCBrz.F90:212-240) so RZ uses a separate launcher.
   // plan kernel: every 3-D mesh with <= 8 corners per zone (zones it cannot plan take its slow path)
-  ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8;
+  ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8 && ctx->G % 2 == 0 && ctx->G <= 256;
   if (const char *e = getenv("UMT_SWEEP3D")) if (!strcmp(e, "generic")) ctx->use_plan = false;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
   const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, 512 / ctx->G);
+  ctx->zones_per_item = zpi;
   // Angles run in batches of K with staggered starts: a batch in its growing half overlaps the
   // previous batch's shrinking half, so the work per level is steady while the Psi1 rows of
   // the last few planes of every active angle stay L2-resident for their downstream zones.
@@ -342,7 +343,16 @@ static int finalize_schedule(umt_ctx *ctx) {
   TRY(dev_alloc_copy(ctx, &ctx->d_nextC, h_nextC.data(), h_nextC.size()));
   TRY(dev_alloc_copy(ctx, &ctx->d_items, items.data(), items.size()));
   TRY(dev_alloc_copy<int>(ctx, &ctx->d_counters, nullptr, 1 + (size_t)ctx->nCounters));
-  if (ctx->use_plan && ctx->device >= 0) TRY(umt_build_plan3d(ctx));
+  if (ctx->use_plan && ctx->device >= 0) {
+    std::vector<int2> zinfo((size_t)NA * nz);
+    for (int a = 0; a < NA; a++)
+      for (int i = 0; i < nz; i++) {
+        const int z = std::abs(h_nextZ[(size_t)a * nz + i]) - 1;
+        zinfo[(size_t)a * nz + i] = make_int2(ctx->h_cOffSet[z], z | (ctx->h_numCorner[z] << 28));
+      }
+    TRY(dev_alloc_copy(ctx, &ctx->d_zinfo, zinfo.data(), zinfo.size()));
+    TRY(umt_build_plan3d(ctx));
+  }
   // cycle lists (control/constructDynMemory.F90:56-213)
   std::vector<int> cl, ca;
   int off = 0;

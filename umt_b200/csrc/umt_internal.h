@@ -32,12 +32,12 @@ struct alignas(16) ZoneRec {
   unsigned char nIn[8], nOut[8]; // incident FP faces / outgoing EZ faces of position p
   unsigned char pad[8];
   double vol[8], sumArea[8];     // by position
-  int inRow[16];                 // Psi1 row behind each incident FP face (>= ncornr: boundary-element row)
-  double inAfp[16];              // omega . A_fp (< 0) of that face
+  int inRow[8][3];               // Psi1 row behind the k-th incident FP face of position p (>= ncornr: boundary-element row)
+  double inAfp[8][3];            // omega . A_fp (< 0) of that face; 0 in unused slots
   ZoneEdge edge[12];
   int exitRow[8][3];             // boundary-element row behind exiting FP face f of position p
 };
-static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 848, "ZoneRec layout");
+static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 944, "ZoneRec layout");
 
 struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int neighbor;
@@ -85,8 +85,9 @@ struct umt_ctx {
   int nItems = 0, nCounters = 0, maxHyp = 0;
   int *d_counters = nullptr;           // [0]=ticket, [1..] per (angle,plane)
   ZoneRec *d_recs = nullptr;           // (NA, nz) plan records in sweep order
+  int2 *d_zinfo = nullptr;             // (NA, nz) first corner row, zone | numCorner << 28 (what the TMA producer needs)
   bool use_plan = false;
-  int plan_ncw = 4, plan_slow_zones = 0;
+  int plan_ncw = 4, plan_slow_zones = 0, zones_per_item = 1;
   int *d_cycleList = nullptr, *d_cycleAngle = nullptr;   // flattened (totalCycles): corner (0-based), angle
   int totalCycles = 0;
   double *d_cyclePsi = nullptr;
