@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
 // plan records
 // ---------------------------------------------------------------------------
 struct PlanBuildParams {
-  int nc, nb, nz, NA;
+  int nc, nb, nz, NA, G;
   const int *numCorner, *cOffSet, *nCFaces, *cFP, *cEZ;
   const double *Volume, *Afp, *Aez, *omega;
   const int *nextZ;
@@ -231,53 +231,51 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
   bool slow = zone0 < 0 || NC > MAXC;
   for (int c = 0; c < NC && !slow; c++) slow = B.nCFaces[c0 + c] != 3;
   const unsigned char *nextC = B.nextC + (size_t)a * B.nc + c0;
-  int pos[MAXC];
-  for (int c = 0; c < MAXC; c++) pos[c] = -1;
-  for (int i = 0; i < MAXC; i++) { R.localc[i] = 0; R.nIn[i] = 0; R.nOut[i] = 0; R.pad[i] = 0; R.vol[i] = 0.0; R.sumArea[i] = 1.0; }
+  const int G = B.G;
+  int pos[MAXC], localc[MAXC];
+  for (int c = 0; c < MAXC; c++) { pos[c] = -1; localc[c] = 0; }
+  for (int i = 0; i < MAXC; i++) {
+    R.nIn[i] = 0; R.nOut[i] = 0; R.crow[i] = c0 * G; R.coff[i] = 0; R.vol[i] = 0.0; R.sumArea[i] = 1.0;
+    for (int k = 0; k < 3; k++) { R.inOff[i][k] = 0; R.inAfp[i][k] = 0.0; R.exitOff[i][k] = 0; }
+  }
+  for (int k = 0; k < 12; k++) { R.edge[k].ainv = 0.0; R.edge[k].cp = 0.0; R.edge[k].ha = 0.0; R.edge[k].qoff = 0; R.edge[k].hasOpp = 0; }
   for (int i = 0; i < NC && !slow; i++) {
     const int c = nextC[i];
     if (c >= NC || pos[c] >= 0) slow = true; else pos[c] = i;
-    R.localc[i] = (unsigned char)c;
+    localc[i] = c;
   }
   double afp[MAXC][3], aez[MAXC][3];
-  signed char kOfFace[MAXC][3];
   unsigned exitMask = 0;
-  for (int p = 0; p < MAXC; p++)
-    for (int k = 0; k < 3; k++) { R.inRow[p][k] = 0; R.inAfp[p][k] = 0.0; R.exitRow[p][k] = 0; }
   for (int p = 0; p < NC && !slow; p++) {
-    const int c = R.localc[p], cc = c0 + c;
+    const int c = localc[p], cc = c0 + c;
     double sa = 0.0;
-    int nin = 0;
     for (int f = 0; f < 3; f++) {
       afp[p][f] = dot3_seq(om, B.Afp + ((size_t)cc * 3 + f) * 3);
       const int row = B.cFP[cc * 3 + f];
-      kOfFace[p][f] = -1;
-      R.exitRow[p][f] = row;
+      R.exitOff[p][f] = row * G;
       if (afp[p][f] > 0.0) {
         sa += afp[p][f];
         if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
-      } else if (afp[p][f] < 0.0) {
-        R.inRow[p][nin] = row;
-        R.inAfp[p][nin] = afp[p][f];
-        kOfFace[p][f] = (signed char)nin;
-        nin++;
       }
     }
-    R.nIn[p] = (unsigned char)nin;
     for (int f = 0; f < 3; f++) {
       aez[p][f] = dot3_seq(om, B.Aez + ((size_t)cc * 3 + f) * 3);
       if (aez[p][f] > 0.0) sa += aez[p][f];
     }
     R.sumArea[p] = sa;
     R.vol[p] = B.Volume[cc];
+    R.crow[p] = cc * G;
+    R.coff[p] = c * (G / 2) * 16;
   }
   // outgoing EZ faces grouped by upstream position, downstream position ascending
   int slot = 0;
   for (int p = 0; p < NC && !slow; p++) {
-    const int c = R.localc[p];
+    const int c = localc[p];
     int nout = 0;
+    bool used[3] = {false, false, false};       // FP faces already placed in an incident slot
+    int slotFace[3] = {-1, -1, -1};
     for (int q = p + 1; q < NC && !slow; q++) {
-      const int cq = R.localc[q];
+      const int cq = localc[q];
       int f = -1, fq = -1;
       for (int k = 0; k < 3; k++) {
         if (B.cEZ[(c0 + c) * 3 + k] == cq) { if (f >= 0) slow = true; f = k; }
@@ -295,18 +293,33 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
       if (!sezFwd) continue;
       if (slot >= 12 || nout >= 3) { slow = true; break; }
       const double av = aez[p][f];
-      const int ifp = (f + 1) % 3;
+      const int ifp = (f + 1) % 3;             // the FP face "opposite" EZ face f (SweepUCBxyz.F90:187-194)
       ZoneEdge &E = R.edge[slot];
       E.ainv = 1.0 / av;
       E.cp = alo > 0.0 ? alo : -alo;
       E.ha = 0.5 * av;
-      E.qc = cq;
-      E.oppk = afp[p][ifp] < 0.0 ? (int)kOfFace[p][ifp] : -1;
+      E.qoff = cq * (G / 2) * 16;
+      E.hasOpp = afp[p][ifp] < 0.0 ? 1 : 0;
+      if (E.hasOpp) { slotFace[nout] = ifp; used[ifp] = true; }   // incident slot k serves edge k
       slot++; nout++;
     }
     R.nOut[p] = (unsigned char)nout;
+    // the other incident faces take the free slots
+    for (int f = 0; f < 3; f++) {
+      if (!(afp[p][f] < 0.0) || used[f]) continue;
+      for (int k = 0; k < 3; k++)
+        if (slotFace[k] < 0) { slotFace[k] = f; used[f] = true; break; }
+    }
+    int nin = 0;
+    for (int k = 0; k < 3; k++)
+      if (slotFace[k] >= 0) {
+        const int f = slotFace[k];
+        R.inOff[p][k] = B.cFP[(c0 + c) * 3 + f] * G;
+        R.inAfp[p][k] = afp[p][f];
+        nin = k + 1;
+      }
+    R.nIn[p] = (unsigned char)nin;
   }
-  for (int k = slot; k < 12; k++) { R.edge[k].ainv = 0.0; R.edge[k].cp = 0.0; R.edge[k].ha = 0.0; R.edge[k].qc = 0; R.edge[k].oppk = -1; }
   if (slow) {
     R.flags |= ZREC_SLOW;
     atomicAdd(B.nSlow, 1);
@@ -405,124 +418,132 @@ struct PlanSmem {
 };
 static size_t plan_smem_bytes(int zonesPerItem) { return offsetof(PlanSmem, recs) + (size_t)PLAN_STAGES * zonesPerItem * sizeof(ZoneRec); }
 
-// Zone solve from a plan record: one pass over the corners in solve order.  Per corner: incident FP
-// fluxes (loaded one corner ahead), the EZ closure terms of its outgoing faces, the corner flux, and
-// its push into the downstream corners.  Q and the running sources live in shared memory (one column
-// per lane, stride Gv between corners) because the downstream corner of an edge is only known from the record.
-__device__ __forceinline__ void solve_zone_plan(const Sweep3DParams &P, const ZoneRec *__restrict__ R, double *__restrict__ psi1A, int g,
-                                                V2 *__restrict__ Qs, V2 *__restrict__ Ss, const V2 sig, const int Gv) {
-  const int G = P.G;
+__device__ __forceinline__ V2 lds_v2(unsigned addr) {
+  V2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_v2(unsigned addr, const V2 &v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// One corner of the zone solve (position p of the record's solve order): incident FP fluxes (pfC, loaded
+// while the previous corner was solved), the EZ closure terms of its outgoing faces, the corner flux and
+// its push into the downstream corners; it also puts the next corner's incident rows in flight (pfN).
+// Q and the running sources live in shared memory (one 16-byte column per lane) because the downstream
+// corner of an edge is only known from the record.
+__device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const ZoneEdge *__restrict__ &E, const int p, const int NC,
+                                            const V2 (&pfC)[3], V2 (&pfN)[3], const double *__restrict__ up, double *__restrict__ upw,
+                                            const unsigned qs, const unsigned ss, const V2 sig, const V2 rsig, const unsigned flags) {
+  const int nout = R->nOut[p];
+  if (p + 1 < NC) {   // incident rows of the next corner
+    const int nn = R->nIn[p + 1];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k < nn) pfN[k] = ld_l2(up + R->inOff[p + 1][k]);
+  }
+  const unsigned co = (unsigned)R->coff[p];
+  V2 s = lds_v2(ss + co);
+  const V2 qp = lds_v2(qs + co);
+  const double vp = R->vol[p];
+  V2 sv;
+  sv.x = sig.x * vp; sv.y = sig.y * vp;
+  // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); unused slots carry afp = 0 and a finite pf
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double af = R->inAfp[p][k];
+    s.x = fma(-af, pfC[k].x, s.x); s.y = fma(-af, pfC[k].y, s.y);
+  }
+  // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), with x = sigma V / aez:
+  //   sez = V [N(x)(sigma psi_opp - Q) + D(x)(Q - Q_cez)/2] / (N(x) + x D(x)),
+  //   N = 1.82 x^2 + 4 x + 3,  D = 4 x^3 + 6 x^2 + 4 x + 2   (gnum = aez^4 N, gden = V aez^3 D)
+  V2 sezk[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (k < nout) {
+      const ZoneEdge e = E[k];
+      const V2 qq = lds_v2(qs + (unsigned)e.qoff);
+      if (e.hasOpp) {
+        const V2 po = pfC[k];
+        {
+          const double x = sv.x * e.ainv;
+          const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+          const double num = fma(N, fma(sig.x, po.x, -qp.x), (0.5 * D) * (qp.x - qq.x));
+          sezk[k].x = (vp * num) * rcp_fast(fma(x, D, N));
+        }
+        {
+          const double x = sv.y * e.ainv;
+          const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+          const double num = fma(N, fma(sig.y, po.y, -qp.y), (0.5 * D) * (qp.y - qq.y));
+          sezk[k].y = (vp * num) * rcp_fast(fma(x, D, N));
+        }
+      } else {
+        sezk[k].x = (e.ha * (qp.x - qq.x)) * rsig.x;
+        sezk[k].y = (e.ha * (qp.y - qq.y)) * rsig.y;
+      }
+      s.x += sezk[k].x; s.y += sezk[k].y;
+    }
+  // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
+  const double sa = R->sumArea[p];
+  V2 psi;
+  psi.x = s.x * rcp_fast(sa + sv.x);
+  psi.y = s.y * rcp_fast(sa + sv.y);
+  st_keep(upw + R->crow[p], psi);
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (k < nout) {
+      const unsigned qa = ss + (unsigned)E[k].qoff;
+      const double cp = E[k].cp;
+      V2 t = lds_v2(qa);
+      t.x = fma(cp, psi.x, t.x - sezk[k].x);
+      t.y = fma(cp, psi.y, t.y - sezk[k].y);
+      sts_v2(qa, t);
+    }
+  if (flags & ZREC_HAS_EXIT) {
+    const unsigned em = R->exitMask >> (p * 3);
+#pragma unroll
+    for (int f = 0; f < 3; f++)
+      if (em & (1u << f)) st_keep(upw + R->exitOff[p][f], psi);
+  }
+  E += nout;
+}
+
+__device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ psi1Ag,
+                                                const unsigned qs, const unsigned ss, const V2 sig) {
   const unsigned flags = R->flags;
   const int NC = (int)(flags & 15u);
-  const double tau = P.tau;
-  double *out = psi1A + (size_t)R->c0 * G + g;
-  const double *up = psi1A + g;
-
   // Q = STotal + tau Psi^n, src = V Q (SweepUCBxyz.F90:119-126), in place over the landed rows
 #pragma unroll
   for (int p = 0; p < MAXC; p++) {
     if (p < NC) {
-      const int ci = (int)R->localc[p] * Gv;
-      const V2 a = Qs[ci], b = Ss[ci];
+      const unsigned co = (unsigned)R->coff[p];
+      const V2 a = lds_v2(qs + co), b = lds_v2(ss + co);
       const double v = R->vol[p];
       V2 q, s;
       q.x = fma(tau, a.x, b.x); q.y = fma(tau, a.y, b.y);
       s.x = v * q.x; s.y = v * q.y;
-      Qs[ci] = q;
-      Ss[ci] = s;
+      sts_v2(qs + co, q);
+      sts_v2(ss + co, s);
     }
   }
   V2 rsig;
   rsig.x = rcp_fast(sig.x); rsig.y = rcp_fast(sig.y);
-
   const ZoneEdge *E = R->edge;
-  V2 pfN[3];
+  V2 pfA[3], pfB[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { pfA[k].x = pfA[k].y = 0.0; pfB[k].x = pfB[k].y = 0.0; }
   {
     const int n0 = R->nIn[0];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      pfN[k].x = 0.0; pfN[k].y = 0.0;
-      if (k < n0) pfN[k] = ld_l2(up + (size_t)R->inRow[0][k] * G);
-    }
+    for (int k = 0; k < 3; k++)
+      if (k < n0) pfA[k] = ld_l2(psi1Ag + R->inOff[0][k]);
   }
 #pragma unroll 1
-  for (int p = 0; p < NC; p++) {
-    V2 pfC[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) pfC[k] = pfN[k];
-    const int nout = R->nOut[p];
-    if (p + 1 < NC) {   // incident rows of the next corner, in flight while this one is solved
-      const int nn = R->nIn[p + 1];
-#pragma unroll
-      for (int k = 0; k < 3; k++)
-        if (k < nn) pfN[k] = ld_l2(up + (size_t)R->inRow[p + 1][k] * G);
-    }
-    const int c = R->localc[p];
-    V2 s = Ss[c * Gv];
-    const V2 qp = Qs[c * Gv];
-    const double vp = R->vol[p];
-    V2 sv;
-    sv.x = sig.x * vp; sv.y = sig.y * vp;
-    // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); unused slots carry afp = 0 and a finite pf
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double af = R->inAfp[p][k];
-      s.x = fma(-af, pfC[k].x, s.x); s.y = fma(-af, pfC[k].y, s.y);
-    }
-    // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), with x = sigma V / aez:
-    //   sez = V [N(x)(sigma psi_opp - Q) + D(x)(Q - Q_cez)/2] / (N(x) + x D(x)),
-    //   N = 1.82 x^2 + 4 x + 3,  D = 4 x^3 + 6 x^2 + 4 x + 2   (gnum = aez^4 N, gden = V aez^3 D)
-    V2 sezk[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      if (k < nout) {
-        const ZoneEdge e = E[k];
-        const V2 qq = Qs[e.qc * Gv];
-        if (e.oppk >= 0) {
-          const V2 po = e.oppk == 0 ? pfC[0] : (e.oppk == 1 ? pfC[1] : pfC[2]);
-          {
-            const double x = sv.x * e.ainv;
-            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
-            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
-            const double num = fma(N, fma(sig.x, po.x, -qp.x), (0.5 * D) * (qp.x - qq.x));
-            sezk[k].x = (vp * num) * rcp_fast(fma(x, D, N));
-          }
-          {
-            const double x = sv.y * e.ainv;
-            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
-            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
-            const double num = fma(N, fma(sig.y, po.y, -qp.y), (0.5 * D) * (qp.y - qq.y));
-            sezk[k].y = (vp * num) * rcp_fast(fma(x, D, N));
-          }
-        } else {
-          sezk[k].x = (e.ha * (qp.x - qq.x)) * rsig.x;
-          sezk[k].y = (e.ha * (qp.y - qq.y)) * rsig.y;
-        }
-        s.x += sezk[k].x; s.y += sezk[k].y;
-      }
-    // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
-    const double sa = R->sumArea[p];
-    V2 psi;
-    psi.x = s.x * rcp_fast(sa + sv.x);
-    psi.y = s.y * rcp_fast(sa + sv.y);
-    st_keep(out + c * G, psi);
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      if (k < nout) {
-        const int qi = E[k].qc * Gv;
-        const double cp = E[k].cp;
-        V2 t = Ss[qi];
-        t.x = fma(cp, psi.x, t.x - sezk[k].x);
-        t.y = fma(cp, psi.y, t.y - sezk[k].y);
-        Ss[qi] = t;
-      }
-    if (flags & ZREC_HAS_EXIT) {
-      const unsigned em = R->exitMask >> (p * 3);
-#pragma unroll
-      for (int f = 0; f < 3; f++)
-        if (em & (1u << f)) st_keep(psi1A + (size_t)R->exitRow[p][f] * G + g, psi);
-    }
-    E += nout;
+  for (int p = 0; p < NC; p += 2) {
+    plan_corner(R, E, p, NC, pfA, pfB, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags);
+    if (p + 1 < NC) plan_corner(R, E, p + 1, NC, pfB, pfA, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags);
   }
 }
 
@@ -534,7 +555,7 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
   const int zr = P.zonesPerItem;
   const size_t slab = (size_t)(P.nc + P.nb) * G;
   if (tid == 0) {
-    for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], PLAN_NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -564,8 +585,12 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
         const int k = nIssued, s = k % PLAN_STAGES;
         int free_ = 1;
         if (k >= PLAN_STAGES) {
-          if (lane == 0) free_ = mbar_test(&S.empty[s], ((k / PLAN_STAGES) - 1) & 1);
-          free_ = __shfl_sync(0xffffffffu, free_, 0);
+          const unsigned par = ((k / PLAN_STAGES) - 1) & 1;
+          if (nReleased == nIssued) mbar_wait(&S.empty[s], par);   // nothing else to do: sleep on the barrier
+          else {
+            if (lane == 0) free_ = mbar_test(&S.empty[s], par);
+            free_ = __shfl_sync(0xffffffffu, free_, 0);
+          }
         }
         if (free_) {
           progressed = true;
@@ -606,33 +631,37 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
         }
       }
       if (!more && nReleased == nIssued) break;
-      if (!progressed) __nanosleep(64);
+      if (!progressed) __nanosleep(256);
     }
     return;
   }
 
-  // ---------------- consumer warps ----------------
+  // ---------------- consumer warps: each runs on its own, no CTA-wide barrier ----------------
   const int zi = tid / Gv, li = tid - zi * Gv;   // my zone of the item, my column in it
+  const double tau = P.tau;
   for (int k = 0;; k++) {
     const int s = k % PLAN_STAGES;
     mbar_wait(&S.full[s], (k / PLAN_STAGES) & 1);
     const StageMeta m = S.meta[s];
     if (m.n < 0) break;
+    const bool active = (warp * 32) < m.n * Gv;   // does this warp hold lanes of the item?
     if (zi < m.n) {
       PlanStage &st = S.stage[s];
       const ZoneRec *R = &S.recs[s * zr + zi];
-      double *psi1A = P.psi1 + (size_t)m.angle * slab;
+      double *psi1Ag = P.psi1 + (size_t)m.angle * slab + 2 * li;
       if (R->flags & ZREC_SLOW) {
         solve_zone_slow(P, m.angle, R->zone0, 2 * li);
         solve_zone_slow(P, m.angle, R->zone0, 2 * li + 1);
       } else {
-        solve_zone_plan(P, R, psi1A, 2 * li, &st.psi[zi * MAXC * Gv + li], &st.st[zi * MAXC * Gv + li], st.sigt[zi * Gv + li], Gv);
+        solve_zone_plan(tau, R, psi1Ag, smem_u32(&st.psi[zi * MAXC * Gv + li]), smem_u32(&st.st[zi * MAXC * Gv + li]), st.sigt[zi * Gv + li]);
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(PLAN_LANES) : "memory");
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(&P.counters[1 + m.signal_idx], 1);
+    __syncwarp();
+    if (lane == 0) {
+      if (active) {
+        __threadfence();
+        atomicAdd(&P.counters[1 + m.signal_idx], 1);
+      }
       mbar_arrive(&S.empty[s]);
     }
   }
@@ -672,7 +701,7 @@ int umt_build_plan3d(umt_ctx *ctx) {
   UMT_CUDA(ctx, cudaMalloc((void **)&d_nslow, sizeof(int)));
   UMT_CUDA(ctx, cudaMemset(d_nslow, 0, sizeof(int)));
   PlanBuildParams B;
-  B.nc = ctx->nc; B.nb = ctx->nb; B.nz = ctx->nz; B.NA = ctx->NA;
+  B.nc = ctx->nc; B.nb = ctx->nb; B.nz = ctx->nz; B.NA = ctx->NA; B.G = ctx->G;
   B.numCorner = ctx->d_numCorner; B.cOffSet = ctx->d_cOffSet; B.nCFaces = ctx->d_nCFaces; B.cFP = ctx->d_cFP; B.cEZ = ctx->d_cEZ;
   B.Volume = ctx->d_Volume; B.Afp = ctx->d_Afp; B.Aez = ctx->d_Aez; B.omega = ctx->d_omega;
   B.nextZ = ctx->d_nextZ; B.nextC = ctx->d_nextC; B.recs = ctx->d_recs; B.nSlow = d_nslow;

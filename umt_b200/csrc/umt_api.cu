@@ -292,7 +292,8 @@ static int finalize_schedule(umt_ctx *ctx) {
   // work items: plane-major, angle-minor.  RZ angles of one xi-level are chained
   // (PsiM dependency, SweepUCBrz.F90:212-240) so RZ uses a separate launcher.
   // plan kernel: every 3-D mesh with <= 8 corners per zone (zones it cannot plan take its slow path)
-  ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8 && ctx->G % 2 == 0 && ctx->G <= 256;
+  ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8 && ctx->G % 2 == 0 && ctx->G <= 256 &&
+                  (double)(ctx->nc + ctx->nb) * ctx->G < 2147483647.0;   // record offsets are 32-bit elements
   if (const char *e = getenv("UMT_SWEEP3D")) if (!strcmp(e, "generic")) ctx->use_plan = false;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
@@ -318,6 +319,18 @@ static int finalize_schedule(umt_ctx *ctx) {
       nItemsPlane[a][p] = (ctx->zonesInPlane[a][p] + zpi - 1) / zpi;
     }
   }
+  // completion counters count items (generic kernel: one CTA-wide signal per item) or, for the plan
+  // kernel, consumer warps (each warp holding lanes of the item signals on its own)
+  const int Gv = std::max(1, ctx->G / 2);
+  auto signals = [&](int nZonesInItem) { return ctx->use_plan ? (nZonesInItem * Gv + 31) / 32 : 1; };
+  std::vector<std::vector<int>> planeSignals(NA);
+  for (int a = 0; a < NA; a++) {
+    planeSignals[a].assign(ctx->nHyp[a], 0);
+    for (int p = 0; p < ctx->nHyp[a]; p++) {
+      const int n = ctx->zonesInPlane[a][p];
+      for (int k = 0; k < nItemsPlane[a][p]; k++) planeSignals[a][p] += signals(std::min(zpi, n - k * zpi));
+    }
+  }
   const int nBatches = (NA + K - 1) / K;
   const int nLevels = maxHyp + (nBatches - 1) * delta;
   for (int lev = 0; lev < nLevels; lev++)
@@ -331,7 +344,7 @@ static int finalize_schedule(umt_ctx *ctx) {
         w.zbeg = z0 + k * zpi;
         w.zend = std::min(z0 + n, w.zbeg + zpi);
         w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
-        w.wait_count = p > 0 ? nItemsPlane[a][p - 1] : 0;
+        w.wait_count = p > 0 ? planeSignals[a][p - 1] : 0;
         w.signal_idx = a * maxHyp + p;
         w.pad0 = w.pad1 = 0;
         items.push_back(w);

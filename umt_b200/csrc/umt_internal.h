@@ -23,21 +23,21 @@ struct WorkItem {       // one chunk of one hyperplane of one angle
 enum { ZREC_SLOW = 16u, ZREC_HAS_EXIT = 32u };   // flags bits above the corner count (bits 0..3)
 struct ZoneEdge {                // EZ face carrying flux from position p into a later position
   double ainv, cp, ha;           // 1/aez, coefpsi (SweepUCBxyz.F90:168-179), aez/2
-  int qc, oppk;                  // local corner id of the downstream corner; index of the opposite incident FP face in p's list, -1 if none
-};
+  int qoff, hasOpp;              // byte offset of the downstream corner's column in the landing area; 1 if the opposite
+};                               // FP face is incident (it is then slot k of p's incident list for p's k-th edge)
 struct alignas(16) ZoneRec {
   int c0, zone0;                 // first corner row of the zone; signed 1-based zone id from nextZ
   unsigned flags, exitMask;      // NC | ZREC_*; bit p*3+f: FP face f of position p exits through the boundary
-  unsigned char localc[8];       // local corner id at position p (nextC order)
-  unsigned char nIn[8], nOut[8]; // incident FP faces / outgoing EZ faces of position p
-  unsigned char pad[8];
+  unsigned char nIn[8], nOut[8]; // highest used incident slot + 1 / outgoing EZ faces of position p
+  int crow[8];                   // (c0 + local corner of position p) * G: element offset of its Psi/Psi1 row in the angle slab
+  int coff[8];                   // byte offset of that corner's column in the landing area (local corner * G/2 * 16)
   double vol[8], sumArea[8];     // by position
-  int inRow[8][3];               // Psi1 row behind the k-th incident FP face of position p (>= ncornr: boundary-element row)
+  int inOff[8][3];               // element offset (row * G) of the Psi1 row behind incident slot k (rows >= ncornr: boundary elements)
   double inAfp[8][3];            // omega . A_fp (< 0) of that face; 0 in unused slots
   ZoneEdge edge[12];
-  int exitRow[8][3];             // boundary-element row behind exiting FP face f of position p
+  int exitOff[8][3];             // element offset of the boundary-element row behind exiting FP face f of position p
 };
-static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 944, "ZoneRec layout");
+static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 992, "ZoneRec layout");
 
 struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int neighbor;
