@@ -36,7 +36,8 @@ constexpr int MAXCF = 3;   // corner faces
 constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 
 struct Sweep3DParams {
-  int nc, nb, nz, G, NA, nItems, zonesPerItem;
+  int nc, nb, nz, G, NA, nItems;
+  int wpe, nEngines, nStages, stageBytes, offSt, offSigt, offRecs;   // PlanGeom
   double tau;
   const int *numCorner, *cOffSet, *nCFaces, *cFP /* 0-based row; >= nc: boundary */, *cEZ /* 0-based */;
   const double *Volume, *Afp, *Aez, *omega;
@@ -396,27 +397,60 @@ __device__ __forceinline__ void st_keep(double *p, const V2 &v) {   // Psi1 rows
   asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(L2_EVICT_LAST) : "memory");
 }
 
-constexpr int PLAN_STAGES = 2;
-constexpr int PLAN_ZMAX = 8;     // zones per item (one round of the consumer warps)
+#ifndef PLAN_MINB
+#define PLAN_MINB 3            // CTAs per SM the plan kernel is compiled for (register cap 65536 / (160 * PLAN_MINB))
+#endif
+constexpr int PLAN_MAX_STAGES = 8;
+constexpr int PLAN_ZMAX = 8;     // zones per item at most
 constexpr int PLAN_NCW = 4;      // consumer warps per CTA
 constexpr int PLAN_LANES = PLAN_NCW * 32;
 
+// How the consumer warps of a CTA are grouped for a given group count (host side, once per context).
+// An "engine" is the set of warps that solves one work item: the lanes of one zone (two groups per
+// lane), or for small G one warp holding several zones.  Engines run independently of each other on
+// their own pipeline stages; with NE engines and NE+1 stages only one stage per CTA is a landing
+// buffer in flight, the others are being computed on.
+struct PlanGeom {
+  int wpe;          // warps per engine (1, 2 or 4)
+  int nEngines;     // PLAN_NCW / wpe
+  int zpi;          // zones per item
+  int nStages;
+  int stageBytes;   // psi | st | sigt | recs
+  int offSt, offSigt, offRecs;
+  size_t smemBytes;
+};
+static PlanGeom plan_geom(int G) {
+  PlanGeom g;
+  const int Gv = G / 2;
+  g.wpe = Gv > 64 ? 4 : (Gv > 32 ? 2 : 1);   // an engine must hold a whole zone (Gv lanes)
+  g.nEngines = PLAN_NCW / g.wpe;
+  const int LE = 32 * g.wpe;
+  g.zpi = std::max(1, std::min(PLAN_ZMAX, LE / std::max(Gv, 1)));
+  if (const char *e = getenv("UMT_ZONES_PER_ITEM")) g.zpi = std::max(1, std::min(g.zpi, atoi(e)));
+  g.offSt = LE * MAXC * 16;
+  g.offSigt = 2 * g.offSt;
+  g.offRecs = g.offSigt + LE * 16;
+  g.stageBytes = (g.offRecs + g.zpi * (int)sizeof(ZoneRec) + 127) / 128 * 128;
+  // as many landing stages as still let PLAN_MINB CTAs share an SM (228 KB, 1 KB reserved per CTA)
+  const int budget = (228 * 1024) / PLAN_MINB - 2048;
+  g.nStages = std::max(g.nEngines + 1, std::min(g.nEngines + 3, (budget - 1024) / g.stageBytes));
+  if (const char *e = getenv("UMT_PLAN_STAGES")) g.nStages = std::max(g.nEngines + 1, std::min(PLAN_MAX_STAGES, atoi(e)));
+  g.smemBytes = 1024 + (size_t)g.nStages * g.stageBytes;
+  return g;
+}
+
 struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
 
-// One pipeline stage = one work item: its plan records and the TMA landing area of its
-// Psi^n / STotal / Sigt rows, [zone][corner][G] (a zone's corner rows are contiguous in HBM, so
-// each is one bulk copy).  The consumers turn the Psi^n area into Q and the STotal area into the
-// running sources in place: each lane only ever touches its own two columns.
-struct PlanStage {
-  V2 psi[MAXC * PLAN_LANES], st[MAXC * PLAN_LANES], sigt[PLAN_LANES];
+// Shared memory: barriers and per-stage metadata in the first KB, then the stages.  One stage = one
+// work item: the TMA landing area of its Psi^n / STotal / Sigt rows, [zone][corner][G] (a zone's corner
+// rows are contiguous in HBM, so each is one bulk copy), and its plan records.  The consumers turn the
+// Psi^n area into Q and the STotal area into the running sources in place: a lane only ever touches
+// its own 16-byte column.
+struct PlanCtl {
+  unsigned long long full[PLAN_MAX_STAGES], empty[PLAN_MAX_STAGES];
+  StageMeta meta[PLAN_MAX_STAGES];
 };
-struct PlanSmem {
-  PlanStage stage[PLAN_STAGES];
-  StageMeta meta[PLAN_STAGES];
-  unsigned long long full[PLAN_STAGES], empty[PLAN_STAGES];
-  ZoneRec recs[1];   // [PLAN_STAGES][zonesPerItem], sized at launch
-};
-static size_t plan_smem_bytes(int zonesPerItem) { return offsetof(PlanSmem, recs) + (size_t)PLAN_STAGES * zonesPerItem * sizeof(ZoneRec); }
+static_assert(sizeof(PlanCtl) <= 1024, "PlanCtl must fit the control block");
 
 __device__ __forceinline__ V2 lds_v2(unsigned addr) {
   V2 r;
@@ -547,15 +581,16 @@ __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec 
   }
 }
 
-__global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DParams P) {
+__global__ void __launch_bounds__(PLAN_LANES + 32, PLAN_MINB) sweep3d_plan_kernel(Sweep3DParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PlanSmem &S = *reinterpret_cast<PlanSmem *>(smem_raw);
+  PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw);
+  unsigned char *stages = smem_raw + 1024;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = P.G, Gv = G >> 1;   // lanes per zone
-  const int zr = P.zonesPerItem;
+  const int NS = P.nStages, NE = P.nEngines, wpe = P.wpe;
   const size_t slab = (size_t)(P.nc + P.nb) * G;
   if (tid == 0) {
-    for (int s = 0; s < PLAN_STAGES; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], PLAN_NCW); }
+    for (int s = 0; s < NS; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], wpe); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -563,15 +598,44 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
 
   if (warp == PLAN_NCW) {
     // ---------------- producer warp ----------------
-    // issue(k): ticket -> item -> TMA of its records and Psi^n/STotal/Sigt rows into stage k%S (needs the stage empty);
-    // release(j): the item's upstream plane is complete -> second arrival on full[j%S].  Releases go first.
-    bool more = true;
-    int nIssued = 0, nReleased = 0;
+    // Per CTA-local sequence number k (stage k % NS, engine k % NE):
+    //   issue(k):   ticket -> item -> TMA of its records and Psi^n/STotal/Sigt rows (needs item k-NS signalled);
+    //   release(k): the item's upstream plane is complete -> second arrival on full[k % NS];
+    //   signal(k):  its engine has arrived on empty[k % NS] -> publish the Psi1 rows (fence) and bump the
+    //               plane's completion counter, so no consumer warp ever waits on a fence.
+    // After the last ticket every engine gets one sentinel.
+    int nIssued = 0, nReleased = 0, nSignaled = 0, sentinels = -1;   // sentinels < 0: tickets remain
     const unsigned rowBytes = (unsigned)G * 8u;
+    // the next item is fetched (ticket, descriptor, zone info) while the current ones are in flight
+    int prepT = 0;
+    WorkItem prepW;
+    int2 prepZ = make_int2(0, 0);
+    auto prepare = [&]() {
+      if (lane == 0) prepT = atomicAdd(&P.counters[0], 1);
+      prepT = __shfl_sync(0xffffffffu, prepT, 0);
+      if (prepT < P.nItems) {
+        prepW = P.items[prepT];
+        if (lane < prepW.zend - prepW.zbeg) prepZ = P.zinfo[(size_t)prepW.angle * P.nz + prepW.zbeg + lane];
+      }
+    };
+    prepare();
     for (;;) {
       bool progressed = false;
+      if (nSignaled < nReleased) {
+        const int s = nSignaled % NS;
+        int done = 0;
+        if (lane == 0) {
+          done = mbar_test(&S.empty[s], (nSignaled / NS) & 1);
+          if (done) {
+            __threadfence();
+            atomicAdd(&P.counters[1 + S.meta[s].signal_idx], 1);
+          }
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) { nSignaled++; progressed = true; }
+      }
       if (nReleased < nIssued) {
-        const int s = nReleased % PLAN_STAGES;
+        const int s = nReleased % NS;
         int ok = 1;
         if (lane == 0) {
           const int wi = S.meta[s].wait_idx;
@@ -581,96 +645,88 @@ __global__ void __launch_bounds__(PLAN_LANES + 32) sweep3d_plan_kernel(Sweep3DPa
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (ok) { nReleased++; progressed = true; }
       }
-      if (more && nIssued - nReleased < PLAN_STAGES) {
-        const int k = nIssued, s = k % PLAN_STAGES;
-        int free_ = 1;
-        if (k >= PLAN_STAGES) {
-          const unsigned par = ((k / PLAN_STAGES) - 1) & 1;
-          if (nReleased == nIssued) mbar_wait(&S.empty[s], par);   // nothing else to do: sleep on the barrier
-          else {
-            if (lane == 0) free_ = mbar_test(&S.empty[s], par);
-            free_ = __shfl_sync(0xffffffffu, free_, 0);
-          }
-        }
-        if (free_) {
-          progressed = true;
-          int t = 0;
-          if (lane == 0) t = atomicAdd(&P.counters[0], 1);
-          t = __shfl_sync(0xffffffffu, t, 0);
-          if (t >= P.nItems) {
-            more = false;
+      const int k = nIssued + (sentinels > 0 ? NE - sentinels : 0);   // next sequence number to fill
+      if (sentinels != 0 && (k < NS || nSignaled > k - NS || (sentinels > 0 && nSignaled == nIssued))) {
+        // stage k % NS is free (a sentinel's stage is never handed back, so once every real item is
+        // signalled the remaining stages are free as well)
+        const int s = k % NS;
+        if (sentinels < 0 && prepT >= P.nItems) sentinels = NE;
+        if (sentinels > 0) {
+          if (k < NS || nSignaled > k - NS || nSignaled == nIssued) {
             if (lane == 0) { S.meta[s].n = -1; mbar_arrive(&S.full[s]); mbar_arrive(&S.full[s]); }
-          } else {
-            const WorkItem w = P.items[t];
-            const int n = w.zend - w.zbeg;
-            const size_t first = (size_t)w.angle * P.nz + w.zbeg;
-            int2 zi = make_int2(0, 0);
-            unsigned bytes = 0;
-            if (lane < n) {
-              zi = P.zinfo[first + lane];                       // c0, zone | NC << 28
-              bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
-            }
-            bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
-            PlanStage &st = S.stage[s];
-            if (lane == 0) {
-              S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
-              S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
-              mbar_arrive_expect_tx(&S.full[s], bytes);
-              tma_load_1d_hint(&S.recs[s * zr], P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[s], L2_EVICT_FIRST);
-            }
-            __syncwarp();
-            if (lane < n) {
-              const unsigned nCorner = (unsigned)zi.y >> 28;
-              const int zone = zi.y & 0x0fffffff;
-              tma_load_1d_hint(&st.psi[lane * MAXC * Gv], P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
-              tma_load_1d_hint(&st.st[lane * MAXC * Gv], P.stotal + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
-              tma_load_1d_hint(&st.sigt[lane * Gv], P.sigt + (size_t)zone * G, rowBytes, &S.full[s], L2_EVICT_FIRST);
-            }
-            nIssued++;
+            sentinels--;
+            progressed = true;
           }
+        } else {
+          progressed = true;
+          const WorkItem w = prepW;
+          const int2 zi = prepZ;
+          const int n = w.zend - w.zbeg;
+          const size_t first = (size_t)w.angle * P.nz + w.zbeg;
+          unsigned bytes = 0;
+          if (lane < n) bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
+          bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
+          unsigned char *st = stages + (size_t)s * P.stageBytes;
+          if (lane == 0) {
+            S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
+            S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
+            mbar_arrive_expect_tx(&S.full[s], bytes);
+            tma_load_1d_hint(st + P.offRecs, P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[s], L2_EVICT_FIRST);
+          }
+          __syncwarp();
+          if (lane < n) {
+            const unsigned nCorner = (unsigned)zi.y >> 28;
+            const int zone = zi.y & 0x0fffffff;
+            tma_load_1d_hint(st + (size_t)lane * MAXC * Gv * 16, P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
+            tma_load_1d_hint(st + P.offSt + (size_t)lane * MAXC * Gv * 16, P.stotal + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
+            tma_load_1d_hint(st + P.offSigt + (size_t)lane * Gv * 16, P.sigt + (size_t)zone * G, rowBytes, &S.full[s], L2_EVICT_FIRST);
+          }
+          nIssued++;
+          prepare();
         }
       }
-      if (!more && nReleased == nIssued) break;
-      if (!progressed) __nanosleep(256);
+      if (sentinels == 0 && nSignaled == nIssued) break;
+      if (!progressed) {
+        if (nReleased == nIssued && nSignaled < nReleased) mbar_wait(&S.empty[nSignaled % NS], (nSignaled / NS) & 1);   // sleep on the oldest engine
+        else __nanosleep(128);
+      }
     }
     return;
   }
 
-  // ---------------- consumer warps: each runs on its own, no CTA-wide barrier ----------------
-  const int zi = tid / Gv, li = tid - zi * Gv;   // my zone of the item, my column in it
+  // ---------------- consumer warps: engines of wpe warps, each on its own stages ----------------
+  const int eng = warp / wpe, elane = (warp - eng * wpe) * 32 + lane;   // my engine, my lane in it
+  const int zi = elane / Gv, li = elane - zi * Gv;                     // my zone of the item, my column in it
   const double tau = P.tau;
-  for (int k = 0;; k++) {
-    const int s = k % PLAN_STAGES;
-    mbar_wait(&S.full[s], (k / PLAN_STAGES) & 1);
+  for (int k = eng;; k += NE) {
+    const int s = k % NS;
+    mbar_wait(&S.full[s], (k / NS) & 1);
     const StageMeta m = S.meta[s];
     if (m.n < 0) break;
-    const bool active = (warp * 32) < m.n * Gv;   // does this warp hold lanes of the item?
     if (zi < m.n) {
-      PlanStage &st = S.stage[s];
-      const ZoneRec *R = &S.recs[s * zr + zi];
+      unsigned char *st = stages + (size_t)s * P.stageBytes;
+      const ZoneRec *R = reinterpret_cast<const ZoneRec *>(st + P.offRecs) + zi;
       double *psi1Ag = P.psi1 + (size_t)m.angle * slab + 2 * li;
       if (R->flags & ZREC_SLOW) {
         solve_zone_slow(P, m.angle, R->zone0, 2 * li);
         solve_zone_slow(P, m.angle, R->zone0, 2 * li + 1);
       } else {
-        solve_zone_plan(tau, R, psi1Ag, smem_u32(&st.psi[zi * MAXC * Gv + li]), smem_u32(&st.st[zi * MAXC * Gv + li]), st.sigt[zi * Gv + li]);
+        const unsigned col = (unsigned)(zi * MAXC * Gv + li) * 16u;
+        const V2 sig = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li) * 16);
+        solve_zone_plan(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig);
       }
     }
     __syncwarp();
-    if (lane == 0) {
-      if (active) {
-        __threadfence();
-        atomicAdd(&P.counters[1 + m.signal_idx], 1);
-      }
-      mbar_arrive(&S.empty[s]);
-    }
+    if (lane == 0) mbar_arrive(&S.empty[s]);
   }
 }
 
 void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.nc = ctx->nc; P.nb = ctx->nb; P.nz = ctx->nz; P.G = ctx->G; P.NA = ctx->NA; P.nItems = ctx->nItems;
   P.tau = ctx->tau;
-  P.zonesPerItem = ctx->zones_per_item;
+  const PlanGeom pg = plan_geom(ctx->G);
+  P.wpe = pg.wpe; P.nEngines = pg.nEngines; P.nStages = pg.nStages; P.stageBytes = pg.stageBytes;
+  P.offSt = pg.offSt; P.offSigt = pg.offSigt; P.offRecs = pg.offRecs;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
@@ -682,11 +738,7 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
 }  // namespace
 
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx) {
-  if (ctx->use_plan) {   // one round of the consumer warps: 2 groups per lane
-    int z = std::max(1, std::min(PLAN_ZMAX, 2 * PLAN_LANES / std::max(ctx->G, 1)));
-    if (const char *e = getenv("UMT_ZONES_PER_ITEM")) z = std::max(1, std::min(z, atoi(e)));
-    return z;
-  }
+  if (ctx->use_plan) return plan_geom(ctx->G).zpi;
   int pairs_target = 512;
   if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairs_target = std::max(1, atoi(e));
   return std::max(1, pairs_target / ctx->G);
@@ -715,7 +767,7 @@ int umt_build_plan3d(umt_ctx *ctx) {
 
 static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
   const int threads = PLAN_LANES + 32;
-  const size_t smem = plan_smem_bytes(ctx->zones_per_item);
+  const size_t smem = plan_geom(ctx->G).smemBytes;
   UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel, threads, smem));

@@ -322,7 +322,7 @@ static int finalize_schedule(umt_ctx *ctx) {
   // completion counters count items (generic kernel: one CTA-wide signal per item) or, for the plan
   // kernel, consumer warps (each warp holding lanes of the item signals on its own)
   const int Gv = std::max(1, ctx->G / 2);
-  auto signals = [&](int nZonesInItem) { return ctx->use_plan ? (nZonesInItem * Gv + 31) / 32 : 1; };
+  auto signals = [&](int nZonesInItem) { (void)nZonesInItem; (void)Gv; return 1; };   // one signal per item in both kernels
   std::vector<std::vector<int>> planeSignals(NA);
   for (int a = 0; a < NA; a++) {
     planeSignals[a].assign(ctx->nHyp[a], 0);
