@@ -30,7 +30,8 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
         double v[3];   // (polar-axis component, next axis, third axis)
         v[0] = ct;
         v[1] = st * azi.x[ia];
-        v[2] = std::sqrt(1.0 - v[0] * v[0] - v[1] * v[1]);   // keeps |omega| = 1 to rounding
+        // keeps |omega| = 1 to rounding; subtraction order as quadProduct.F90:97-111 (x, y, z order of the two known components)
+        v[2] = polaraxis == 3 ? std::sqrt(1.0 - v[1] * v[1] - v[0] * v[0]) : std::sqrt(1.0 - v[0] * v[0] - v[1] * v[1]);
         double o[3];
         for (int k = 0; k < 3; k++) o[(polaraxis - 1 + k) % 3] = v[k];
         const double w = polar.w[ip] * azi.w[ia];
