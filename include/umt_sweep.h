@@ -130,12 +130,37 @@ int umt_synchronize(umt_ctx *ctx);
 /* ---- domain decomposition: rt/findexit.F90:102-294, rt/SendFlux.F90, rt/RecvFlux.F90 ---- */
 /* One call per shared boundary (neighbour): its boundary elements are
    firstBdyElem..firstBdyElem+nBdyElem-1 (1-based), matched element-by-element with
-   the neighbour's list (aux/checkSharedBoundary.F90). */
+   the neighbour's list (aux/checkSharedBoundary.F90).  Shared boundaries are indexed
+   0,1,... in the order they were added (sharedIndex below). */
 int umt_add_shared_boundary(umt_ctx *ctx, int neighborRank, int firstBdyElem, int nBdyElem);
 /* myRank/nRanks and a 128-byte ncclUniqueId (same on all ranks; rank 0 gets it from
-   umt_nccl_unique_id).  NCCL is dlopen'ed; fails with UMT_ERR_NCCL if absent. */
+   umt_nccl_unique_id).  NCCL is dlopen'ed; fails with UMT_ERR_NCCL if absent.  The psib
+   rows then travel GPU-to-GPU with ncclSend/ncclRecv (replaces the persistent MPI
+   requests of rt/initcomm.F90:88-101). */
 int umt_nccl_unique_id(unsigned char *id128);
 int umt_set_comm(umt_ctx *ctx, int myRank, int nRanks, const unsigned char *id128);
+/* In-process alternative: the n contexts become ranks 0..n-1 of one group (several domains
+   per process, e.g. on one GPU); collective calls (umt_build_exchange, umt_sweep) must then be
+   made from n host threads, one per context. */
+int umt_connect_local(umt_ctx **ctxs, int n);
+/* Rank only (host-only contexts that build exchange lists without a communicator). */
+int umt_set_rank(umt_ctx *ctx, int myRank, int nRanks);
+/* rt/findexit.F90:128-205: each side of a shared boundary classifies half of the angles of an
+   angle set (lower rank the first half) as incident (-1) / exiting (+1) by the sign of
+   omega . A_bdy and the two halves are exchanged.  incTest is (nBdyElem, NA) bytes, zero for
+   the angles the other side decides.  umt_build_exchange trades them through the communicator;
+   a caller with its own transport (MPI, gloo) passes the neighbour's array in instead. */
+int umt_get_incident_test(umt_ctx *ctx, int sharedIndex, signed char *incTest);
+int umt_set_incident_test(umt_ctx *ctx, int sharedIndex, const signed char *incTestNeighbor);
+/* ListSend / ListRecv of every (shared boundary, angle) (findexit.F90:193-287) + device buffers. Collective. */
+int umt_build_exchange(umt_ctx *ctx);
+int umt_get_exchange_counts(umt_ctx *ctx, int sharedIndex, int *nSend /* (NA) */, int *nRecv /* (NA) */);
+int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, int *listSend, int *listRecv);
+/* CSet%IncFlux / IncFluxOld per comm set after the last umt_sweep (rt/setIncidentFlux.F90:128-146):
+   one bin per angle in 3-D, per xi-level in 2-D. */
+int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incFluxOld);
+/* adqtEpsilon*speed_light*rad_constant*tr4floor of rt/testFluxConv.F90:73 (default 0). */
+int umt_set_flux_floor(umt_ctx *ctx, double floorFlux);
 
 /* ---- grey transport acceleration: snac/GTASweep.F90, snac/SweepGreyUCBxyz.F90 ---- */
 int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, const double *GreySigScat,

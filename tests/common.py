@@ -95,3 +95,185 @@ def mixed_err(a, b, rtol=1e-12, atol_scale=1e-14):
         return 0.0
     scale = float(np.max(np.abs(b)))
     return float(np.max(np.abs(a - b) / (rtol * np.abs(b) + atol_scale * scale + 1e-300)))
+
+
+# ---------------------------------------------------------------------------
+# RZ
+# ---------------------------------------------------------------------------
+def make_problem_rz(mesh, npolar=2, nazimuthal=2, G=4, seed=1234, tau=None, driver_like=False):
+    p = Problem()
+    p.mesh = mesh
+    p.om = O.OMesh(mesh)
+    p.geom = O.geometry(p.om)
+    p.q = O.quad_rz(npolar, nazimuthal)
+    p.omega, p.weight = p.q["omega"], p.q["weight"]
+    p.NA = len(p.weight)
+    p.sched = O.schedule(p.om, p.geom, p.omega, p.q["finish"])
+    p.G = G
+    p.bdy = [O.bdy_exit(p.om, p.geom, p.omega[a]) for a in range(p.NA)]
+    rng = np.random.default_rng(seed)
+    nc, nb, nz = mesh.ncornr, mesh.nbelem, mesh.nzones
+    if driver_like:
+        p.tau = 1.0 / (SPEED_LIGHT * 1e-3) if tau is None else tau
+        p.Sigt = np.full((nz, G), p.tau)
+        p.STotal = np.zeros((nc, G))
+        p.Psi = np.tile(np.linspace(1.0, 2.0, G), (p.NA, nc, 1)).copy()
+        p.PsiB = np.zeros((p.NA, nb, G))
+    else:
+        p.tau = 3.0 if tau is None else tau
+        p.Sigt = p.tau + 20.0 * rng.random((nz, G))
+        p.STotal = rng.random((nc, G))
+        p.Psi = 0.5 + rng.random((p.NA, nc, G))
+        p.PsiB = 0.5 + rng.random((p.NA, nb, G))
+    return p
+
+
+def oracle_sweep_rz(p, savePsi):
+    """SetSweep.F90:81-170 for one comm set holding every angle in quadrature order (single domain),
+    then getPhiTotal; mutates p.Psi (if savePsi) and p.PsiB; returns PhiTotal."""
+    m = p.mesh
+    Phi = np.zeros((m.ncornr, p.G))
+    PsiM = np.zeros((m.ncornr, p.G))
+    Psi1 = np.zeros((m.ncornr + m.nbelem, p.G))
+    for a in range(p.NA):
+        if p.q["finish"][a]:
+            continue
+        O.sweep_rz(p.om, p.geom, p.sched, a, p.q, p.tau, p.STotal, p.Sigt, p.Psi, Psi1, PsiM, p.PsiB, Phi, p.bdy[a], savePsi)
+    return Phi
+
+
+def gpu_context_rz(p, device=0, own_schedule=False, own_geometry=False, own_quadrature=None):
+    from umt_b200.teton import SweepContext
+    m = p.mesh
+    ctx = SweepContext.from_mesh(m, p.G, device)
+    g, q = p.geom, p.q
+    if own_geometry:
+        ctx.compute_geometry(m.px)
+    else:
+        ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], g["Area"], g["RadiusFP"], g["RadiusEZ"], g["A_bdy"])
+    if own_quadrature:
+        ctx.build_product_quadrature(*own_quadrature)
+    else:
+        ctx.set_quadrature(q["omega"], q["weight"], q["start"], q["finish"][:p.NA], q["angDerivFac"], q["quadTauW1"], q["quadTauW2"])
+    if own_schedule:
+        ctx.build_schedule()
+    else:
+        s = p.sched
+        for a in range(p.NA):
+            off, n = s["cycleOffSet"][a], s["numCycles"][a]
+            nh = s["nHyperPlanes"][a]
+            ctx.set_schedule(a + 1, nh, s["zonesInPlane"][a][:nh], s["nextZ"][a], s["nextC"][a], s["cycleList"][off:off + n], p.bdy[a])
+    ctx.upload_state(p.Psi, p.PsiB, p.Sigt, p.STotal, p.tau)
+    return ctx
+
+
+# ---------------------------------------------------------------------------
+# several spatial domains (one per rank), psib exchange lagged one flux pass
+# ---------------------------------------------------------------------------
+def shared_boundaries(mesh):
+    return [b for b in mesh.boundaries if b.bc_type == M.BC_SHARED]
+
+
+def oracle_exchange_lists(problems):
+    """findexit.F90:102-294 for every rank: lists[r][k][a] = (send elements, recv elements), 1-based boundary
+    elements of rank r's k-th shared boundary.  3-D: every angle is its own angle set, so NumAngles/2 = 0 and
+    the higher rank of a pair classifies (the lower rank negates what it receives)."""
+    out = []
+    for r, p in enumerate(problems):
+        per_b = []
+        for b in shared_boundaries(p.mesh):
+            q = problems[b.neighbor]
+            bq = [x for x in shared_boundaries(q.mesh) if x.neighbor == r][0]
+            assert bq.n_elem == b.n_elem
+            mine = p.geom["A_bdy"][b.first_elem - 1:b.first_elem - 1 + b.n_elem] @ p.omega.T      # (n, NA)
+            theirs = q.geom["A_bdy"][bq.first_elem - 1:bq.first_elem - 1 + bq.n_elem] @ q.omega.T
+            t = np.sign(mine) if r > b.neighbor else -np.sign(theirs)
+            per_a = []
+            for a in range(p.NA):
+                el = np.arange(b.first_elem, b.first_elem + b.n_elem)
+                per_a.append((el[t[:, a] > 0], el[t[:, a] < 0]))
+            per_b.append(per_a)
+        out.append(per_b)
+    return out
+
+
+def oracle_multi_sweep_3d(problems, lists, savePsi, maxFluxIters=1, fluxTol=1e-6, state=None):
+    """SetSweep.F90 on every rank in lock step; returns (PhiTotal per rank, flux passes done, IncFlux per rank)."""
+    N = len(problems)
+    NA = problems[0].NA
+
+    def exit_currents():
+        """setIncidentFlux.F90:84-108 on every rank: ExitFlux[r][k][a]"""
+        res = []
+        for r, p in enumerate(problems):
+            per_b = []
+            for k, b in enumerate(shared_boundaries(p.mesh)):
+                ex = np.zeros(NA)
+                for a in range(NA):
+                    el = lists[r][k][a][0]
+                    dot = p.geom["A_bdy"][el - 1] @ p.omega[a]
+                    ex[a] = p.weight[a] * float((dot * p.PsiB[a, el - 1].sum(axis=1)).sum())
+                per_b.append(ex)
+            res.append(per_b)
+        return res
+
+    def incident(ex):
+        inc = []
+        for r, p in enumerate(problems):
+            v = np.zeros(NA)
+            for b in shared_boundaries(p.mesh):
+                q = problems[b.neighbor]
+                kq = [i for i, x in enumerate(shared_boundaries(q.mesh)) if x.neighbor == r][0]
+                v += ex[b.neighbor][kq]
+            inc.append(v)
+        return inc
+
+    inc = incident(exit_currents())
+    it = 0
+    while True:
+        it += 1
+        # SendFlux/RecvFlux: every rank's exiting rows (as they are now) land in the neighbours' incident rows
+        snap = [p.PsiB.copy() for p in problems]
+        for r, p in enumerate(problems):
+            for k, b in enumerate(shared_boundaries(p.mesh)):
+                q = problems[b.neighbor]
+                kq = [i for i, x in enumerate(shared_boundaries(q.mesh)) if x.neighbor == r][0]
+                for a in range(NA):
+                    recv = lists[r][k][a][1]
+                    send = lists[b.neighbor][kq][a][0]
+                    assert len(recv) == len(send)
+                    p.PsiB[a, recv - 1] = snap[b.neighbor][a, send - 1]
+        phis = [oracle_sweep_3d(p, savePsi) for p in problems]
+        inc_old, inc = inc, incident(exit_currents())
+        if savePsi:
+            break
+        notconv = 0
+        for r in range(N):
+            for a in range(NA):
+                tot = inc[r][a]
+                rel = abs(inc[r][a] - inc_old[r][a]) / inc[r][a] if tot != 0.0 else 0.0
+                notconv += not (rel <= fluxTol)
+        if notconv == 0 or it >= maxFluxIters:
+            break
+    return phis, it, inc
+
+
+def run_local_group(contexts, fn):
+    """Call fn(rank, ctx) from one host thread per context (the in-process communicator needs it)."""
+    import threading
+    out, err = [None] * len(contexts), [None] * len(contexts)
+
+    def work(r):
+        try:
+            out[r] = fn(r, contexts[r])
+        except BaseException as e:   # noqa: BLE001
+            err[r] = e
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(contexts))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out

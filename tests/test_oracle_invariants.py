@@ -218,3 +218,32 @@ def test_planck_groups_match_reference_source():
     B = O.planck_groups_ref(0.05, b)   # k = Bnorm = 1: the groups add up to T^4
     assert (B >= 0).all()
     assert abs(B.sum() / 0.05 ** 4 - 1.0) <= 1e-6
+
+
+@pytest.mark.parametrize("name,mk", MESHES_2D)
+def test_uniform_solution_preserved_rz(name, mk):
+    """Same balance in r-z: the angular-derivative terms (PsiM chain, AngleCoef2D.F90) cancel for an
+    isotropic, uniform field, including the starting/finishing-direction bookkeeping."""
+    m = mk()
+    p = T.make_problem_rz(m, 2, 3, 3)
+    psi0 = np.linspace(0.7, 1.9, 3)
+    p.Psi[:] = psi0
+    p.PsiB[:] = psi0
+    p.STotal[:] = (np.repeat(p.Sigt, m.numCorner, axis=0) - p.tau) * psi0
+    phi = T.oracle_sweep_rz(p, True)
+    assert np.abs(p.Psi / psi0 - 1).max() <= 1e-11
+    assert np.abs(phi / (2 * math.pi * psi0) - 1).max() <= 1e-11
+    assert np.abs(p.PsiB / psi0 - 1).max() <= 1e-11
+
+
+def test_schedule_validity_rz():
+    m = M.tiled_mesh((3, 3, 0))
+    p = T.make_problem_rz(m, 2, 2, 1)
+    nz = m.nzones
+    for a in range(p.NA):
+        nh = p.sched["nHyperPlanes"][a]
+        if p.q["finish"][a]:
+            assert nh == 0   # finishing directions are not swept (rtorder.F90)
+            continue
+        assert p.sched["zonesInPlane"][a][:nh].sum() == nz
+        assert np.array_equal(np.sort(np.abs(p.sched["nextZ"][a])), np.arange(1, nz + 1))

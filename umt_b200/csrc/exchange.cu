@@ -1,0 +1,623 @@
+// Boundary-flux (psib) exchange between spatial domains, one domain per context.
+//
+// Replaces rt/findexit.F90:102-294 (incident/exiting classification of shared boundary
+// elements, ListSend / ListRecv), rt/InitExchange.F90, rt/SendFlux.F90:68-80,
+// rt/TestSend.F90, rt/RecvFlux.F90:64-78 (pack, persistent MPI send/recv, unpack),
+// rt/setIncidentFlux.F90:71-146 (per-bin exit currents exchanged with the neighbours) and
+// rt/testFluxConv.F90:55-105 (relative change of the incident currents) plus the
+// MPI_Allreduce(max nNotConv) of snac/SetSweep.F90:199.
+//
+// B200 design: the exiting rows of every angle toward one neighbour are packed by one kernel
+// into one contiguous send buffer (the same kernel tallies the exit currents, so PsiB is read
+// once), all neighbours are served by a single ncclGroup of ncclSend/ncclRecv over NVLink
+// (device to device, no host staging), and one kernel scatters the received rows into the
+// incident PsiB rows.  Semantics are the reference's with one angle per comm set: pass k
+// sweeps with what the neighbours produced in pass k-1 (lagged one flux pass).
+//
+// Transports: NCCL (dlopen'ed; one rank per GPU) and an in-process group of contexts
+// (several domains in one process, e.g. on one GPU: tests, or more domains than GPUs).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+
+#include "umt_internal.h"
+
+// ---------------------------------------------------------------------------
+// transports
+// ---------------------------------------------------------------------------
+struct UmtTransport {
+  virtual ~UmtTransport() {}
+  // send `sendBytes[s]` bytes from sendPtr[s] to neighbour s, receive recvBytes[s] into recvPtr[s]; device pointers
+  virtual int exchange(umt_ctx *ctx, const std::vector<const void *> &sendPtr, const std::vector<size_t> &sendBytes,
+                       const std::vector<void *> &recvPtr, const std::vector<size_t> &recvBytes) = 0;
+  virtual int allreduce_max(umt_ctx *ctx, int *d_value) = 0;   // in place, device int
+};
+
+namespace {
+
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool load() {
+    if (h) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names)
+      if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) { error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define SYM(field, name) do { *(void **)(&field) = dlsym(h, name); if (!field) { error = std::string("dlsym ") + name; h = nullptr; return false; } } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+#define UMT_NCCL(ctx, call)                                                                                       \
+  do {                                                                                                            \
+    ncclResult_t _r = (call);                                                                                     \
+    if (_r != ncclSuccess) UMT_FAIL(ctx, UMT_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(_r));          \
+  } while (0)
+
+struct NcclTransport : UmtTransport {
+  ncclComm_t comm = nullptr;
+  ~NcclTransport() override { if (comm) g_nccl.CommDestroy(comm); }
+  int exchange(umt_ctx *ctx, const std::vector<const void *> &sp, const std::vector<size_t> &sb, const std::vector<void *> &rp,
+               const std::vector<size_t> &rb) override {
+    UMT_NCCL(ctx, g_nccl.GroupStart());
+    for (size_t s = 0; s < ctx->shared.size(); s++) {
+      const int peer = ctx->shared[s].neighbor;
+      if (sb[s]) UMT_NCCL(ctx, g_nccl.Send(sp[s], sb[s], ncclInt8, peer, comm, ctx->stream));
+      if (rb[s]) UMT_NCCL(ctx, g_nccl.Recv(rp[s], rb[s], ncclInt8, peer, comm, ctx->stream));
+    }
+    UMT_NCCL(ctx, g_nccl.GroupEnd());
+    return UMT_OK;
+  }
+  int allreduce_max(umt_ctx *ctx, int *d_value) override {
+    UMT_NCCL(ctx, g_nccl.AllReduce(d_value, d_value, 1, ncclInt32, ncclMax, comm, ctx->stream));
+    return UMT_OK;
+  }
+};
+
+// Contexts of one process acting as ranks 0..n-1 (each driven by its own host thread).
+struct LocalGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, arrived = 0;
+  unsigned long generation = 0;
+  std::vector<umt_ctx *> members;
+  int redux = 0;
+  int refs = 0;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned long gen = generation;
+    if (++arrived == n) { arrived = 0; generation++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  }
+};
+
+struct LocalTransport : UmtTransport {
+  LocalGroup *grp = nullptr;
+  std::vector<void *> recvPtrNow;   // where my neighbours must deliver in the current exchange (read by them)
+  std::vector<size_t> recvBytesNow;
+  ~LocalTransport() override {
+    bool last;
+    { std::lock_guard<std::mutex> lk(grp->m); last = --grp->refs == 0; }
+    if (last) delete grp;
+  }
+  int exchange(umt_ctx *ctx, const std::vector<const void *> &sp, const std::vector<size_t> &sb, const std::vector<void *> &rp,
+               const std::vector<size_t> &rb) override {
+    recvPtrNow = rp; recvBytesNow = rb;
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // my send buffers are packed, my receive buffers are free
+    grp->barrier();
+    for (size_t s = 0; s < ctx->shared.size(); s++) {
+      umt_ctx *peer = grp->members[ctx->shared[s].neighbor];
+      auto *pt = static_cast<LocalTransport *>(peer->transport);
+      int t = -1;
+      for (size_t k = 0; k < peer->shared.size(); k++)
+        if (peer->shared[k].neighbor == ctx->myRank) t = (int)k;
+      if (t < 0 || pt->recvBytesNow[t] != sb[s])
+        UMT_FAIL(ctx, UMT_ERR_STATE, "local exchange: rank %d and rank %d disagree on the message size of their shared boundary", ctx->myRank, ctx->shared[s].neighbor);
+      if (sb[s]) UMT_CUDA(ctx, cudaMemcpyAsync(pt->recvPtrNow[t], sp[s], sb[s], cudaMemcpyDefault, ctx->stream));
+    }
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    grp->barrier();
+    return UMT_OK;
+  }
+  int allreduce_max(umt_ctx *ctx, int *d_value) override {
+    int v = 0;
+    UMT_CUDA(ctx, cudaMemcpyAsync(&v, d_value, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    { std::lock_guard<std::mutex> lk(grp->m); grp->redux = std::max(grp->redux, v); }
+    grp->barrier();
+    { std::lock_guard<std::mutex> lk(grp->m); v = grp->redux; }
+    grp->barrier();
+    if (ctx->myRank == 0) { std::lock_guard<std::mutex> lk(grp->m); grp->redux = 0; }
+    grp->barrier();
+    UMT_CUDA(ctx, cudaMemcpyAsync(d_value, &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UMT_OK;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+// K7a: sendbuf(:, i) <- PsiB(:, b_i, a_i) for the rows of one chunk, and the chunk's share of the exit current
+// sum_i w_a (omega_a . A_bdy(b_i)) sum_g PsiB(g, b_i, a)   (SendFlux.F90:68-77 + setIncidentFlux.F90:84-108)
+__global__ void __launch_bounds__(256) pack_tally_kernel(const double *__restrict__ psi1, const long long *__restrict__ srcRow,
+                                                         const double *__restrict__ coef, const PackChunk *__restrict__ chunks,
+                                                         double *__restrict__ sendbuf, double *__restrict__ partial, int G) {
+  const PackChunk ch = chunks[blockIdx.x];
+  double acc = 0.0;
+  const long long n = (long long)(ch.rowEnd - ch.rowBeg) * G;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = ch.rowBeg + (int)(i / G), g = (int)(i % G);
+    const double v = __ldcg(&psi1[srcRow[r] * G + g]);
+    sendbuf[(size_t)r * G + g] = v;
+    acc += coef[r] * v;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[ch.slot] = red[0];
+}
+
+// exit current per angle = its chunks' partial sums in chunk order (deterministic)
+__global__ void tally_finish_kernel(const double *partial, const int *nChunksOfAngle, int maxChunks, double *exitFlux, int NA) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= NA) return;
+  double s = 0.0;
+  for (int k = 0; k < nChunksOfAngle[a]; k++) s += partial[(size_t)a * maxChunks + k];
+  exitFlux[a] = s;
+}
+
+// K7b: PsiB(:, b_i, a_i) <- recvbuf(:, i)   (RecvFlux.F90:68-78)
+__global__ void __launch_bounds__(256) unpack_kernel(double *__restrict__ psi1, const long long *__restrict__ dstRow,
+                                                     const double *__restrict__ recvbuf, long long n, int G) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = i / G;
+  psi1[dstRow[r] * G + (i - r * G)] = recvbuf[i];
+}
+
+// setIncidentFlux.F90:128-146 + testFluxConv.F90:55-105 with one bin per comm set.
+// incRecv: (nShared, NA) exit currents received from the neighbours.
+__global__ void flux_conv_kernel(const double *incRecv, int nShared, int NA, const int *binOfAngle, int nBins, double *incFlux,
+                                 double *incFluxOld, double tol, double floorFlux, int *nNotConv) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int b = 0; b < nBins; b++) { incFluxOld[b] = incFlux[b]; incFlux[b] = 0.0; }
+  for (int s = 0; s < nShared; s++)
+    for (int a = 0; a < NA; a++) incFlux[binOfAngle[a]] += incRecv[(size_t)s * NA + a];
+  int notConv = 0;
+  for (int b = 0; b < nBins; b++) {
+    const double total = incFlux[b];   // one bin per comm set: totalIncFlux is the bin itself
+    double rel = 0.0;
+    if (!(fabs(total) < floorFlux) && total != 0.0) {
+      const double weight = incFlux[b] / total;
+      if (weight > 0.001) rel = fabs(incFlux[b] - incFluxOld[b]) / incFlux[b];
+    }
+    if (!(rel <= tol)) notConv++;
+  }
+  *nNotConv = notConv;
+}
+
+template <class T>
+int upload(umt_ctx *ctx, T **d, const std::vector<T> &h) {
+  if (*d) { cudaFree(*d); *d = nullptr; }
+  UMT_CUDA(ctx, cudaMalloc((void **)d, sizeof(T) * std::max<size_t>(h.size(), 1)));
+  if (!h.empty()) UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return UMT_OK;
+}
+
+// angle sets as the reference forms them without reflecting boundaries (control/decomposeAngleSets.F90:
+// 3-D every angle its own set :280-285, 2-D one set per xi-level :150-172): [set0, set1) of angle a
+void angle_set_range(const umt_ctx *ctx, int a, int &a0, int &a1) {
+  if (ctx->ndim == 3 || ctx->h_level.empty()) { a0 = a; a1 = a + 1; return; }
+  a0 = a; a1 = a + 1;
+  while (a0 > 0 && ctx->h_level[a0 - 1] == ctx->h_level[a]) a0--;
+  while (a1 < ctx->NA && ctx->h_level[a1] == ctx->h_level[a]) a1++;
+}
+
+// does *this* rank compute the incident test of angle a on the boundary shared with `neighbor`?
+// findexit.F90:137-143: the lower rank takes the first half of the angle set, the higher rank the rest.
+bool i_decide(const umt_ctx *ctx, int neighbor, int a) {
+  int a0, a1;
+  angle_set_range(ctx, a, a0, a1);
+  const int half = (a1 - a0) / 2;
+  const bool firstHalf = a - a0 < half;
+  return ctx->myRank < neighbor ? firstHalf : !firstHalf;
+}
+
+int need_abdy(umt_ctx *ctx) {
+  if (ctx->have_abdy) return UMT_OK;
+  if (!ctx->have_geom || !ctx->have_conn) UMT_FAIL(ctx, UMT_ERR_STATE, "exchange setup needs connectivity and geometry");
+  const int nd = ctx->ndim;
+  ctx->h_Abdy.assign((size_t)nd * std::max(ctx->nb, 1), 0.0);
+  for (int c = 0; c < ctx->nc; c++)
+    for (int f = 0; f < ctx->h_nCFaces[c]; f++) {
+      const int v = ctx->h_cFP[(size_t)c * ctx->maxcf + f];
+      if (v > ctx->nc)
+        for (int d = 0; d < nd; d++) ctx->h_Abdy[(size_t)(v - ctx->nc - 1) * nd + d] = ctx->h_Afp[((size_t)c * ctx->maxcf + f) * nd + d];
+    }
+  ctx->have_abdy = true;
+  return UMT_OK;
+}
+
+}  // namespace
+
+void umt_exchange_release(umt_ctx *ctx) {
+  for (auto &s : ctx->shared) {
+    void *p[] = {s.d_send_row, s.d_recv_row, s.d_send_coef, s.d_chunks, s.d_partial, s.d_nChunksOfAngle, s.d_sendbuf, s.d_recvbuf};
+    for (void *q : p) if (q) cudaFree(q);
+    s.d_send_row = s.d_recv_row = nullptr; s.d_send_coef = nullptr; s.d_chunks = nullptr; s.d_partial = nullptr;
+    s.d_nChunksOfAngle = nullptr; s.d_sendbuf = s.d_recvbuf = nullptr;
+  }
+  void *p[] = {ctx->d_exitFlux, ctx->d_incRecv, ctx->d_incFlux, ctx->d_incFluxOld, ctx->d_binOfAngle, ctx->d_nNotConv};
+  for (void *q : p) if (q) cudaFree(q);
+  ctx->d_exitFlux = ctx->d_incRecv = ctx->d_incFlux = ctx->d_incFluxOld = nullptr; ctx->d_binOfAngle = nullptr; ctx->d_nNotConv = nullptr;
+  delete ctx->transport;
+  ctx->transport = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// setup API
+// ---------------------------------------------------------------------------
+extern "C" int umt_add_shared_boundary(umt_ctx *ctx, int neighborRank, int firstBdyElem, int nBdyElem) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (neighborRank < 0 || firstBdyElem < 1 || nBdyElem < 1 || firstBdyElem - 1 + nBdyElem > ctx->nb)
+    UMT_FAIL(ctx, UMT_ERR_ARG, "umt_add_shared_boundary: elements %d..%d outside 1..%d", firstBdyElem, firstBdyElem + nBdyElem - 1, ctx->nb);
+  for (const auto &s : ctx->shared)
+    if (s.neighbor == neighborRank) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_add_shared_boundary: neighbour %d already has a shared boundary", neighborRank);
+  SharedBdy s;
+  s.neighbor = neighborRank; s.first = firstBdyElem - 1; s.n = nBdyElem;
+  ctx->shared.push_back(s);
+  ctx->exch_dirty = true;
+  ctx->sched_dirty = true;   // exit lists put shared elements last
+  return UMT_OK;
+}
+
+extern "C" int umt_set_rank(umt_ctx *ctx, int myRank, int nRanks) {
+  if (!ctx || myRank < 0 || nRanks < 1 || myRank >= nRanks) return UMT_ERR_ARG;
+  ctx->myRank = myRank; ctx->nRanks = nRanks;
+  ctx->exch_dirty = true;
+  return UMT_OK;
+}
+
+// findexit.F90:128-160: sign of omega . A_bdy for the angles this rank decides, (nBdyElem, NA) bytes, 0 elsewhere
+extern "C" int umt_get_incident_test(umt_ctx *ctx, int sharedIndex, signed char *incTest) {
+  if (!ctx || !incTest || sharedIndex < 0 || sharedIndex >= (int)ctx->shared.size()) return UMT_ERR_ARG;
+  if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_get_incident_test: quadrature not set");
+  int r = need_abdy(ctx);
+  if (r) return r;
+  const SharedBdy &s = ctx->shared[sharedIndex];
+  const int nd = ctx->ndim;
+  std::memset(incTest, 0, (size_t)s.n * ctx->NA);
+  for (int a = 0; a < ctx->NA; a++) {
+    if (!i_decide(ctx, s.neighbor, a)) continue;
+    for (int b = 0; b < s.n; b++) {
+      double dot = 0.0;
+      for (int d = 0; d < nd; d++) dot += ctx->h_omega[(size_t)a * nd + d] * ctx->h_Abdy[(size_t)(s.first + b) * nd + d];
+      incTest[(size_t)a * s.n + b] = dot < 0.0 ? -1 : (dot > 0.0 ? 1 : 0);
+    }
+  }
+  return UMT_OK;
+}
+
+// the neighbour's umt_get_incident_test output for the same boundary (its signs are the opposite of mine: findexit.F90:205)
+extern "C" int umt_set_incident_test(umt_ctx *ctx, int sharedIndex, const signed char *incTestNeighbor) {
+  if (!ctx || !incTestNeighbor || sharedIndex < 0 || sharedIndex >= (int)ctx->shared.size()) return UMT_ERR_ARG;
+  SharedBdy &s = ctx->shared[sharedIndex];
+  s.incTestR.assign(incTestNeighbor, incTestNeighbor + (size_t)s.n * ctx->NA);
+  ctx->exch_dirty = true;
+  return UMT_OK;
+}
+
+extern "C" int umt_nccl_unique_id(unsigned char *id128) {
+  if (!id128) return UMT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_nccl_mutex);
+  if (!g_nccl.load()) return UMT_ERR_NCCL;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return UMT_ERR_NCCL;
+  std::memcpy(id128, &id, 128);
+  return UMT_OK;
+}
+
+extern "C" int umt_set_comm(umt_ctx *ctx, int myRank, int nRanks, const unsigned char *id128) {
+  if (!ctx || !id128 || myRank < 0 || myRank >= nRanks) return UMT_ERR_ARG;
+  if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm: host-only context");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  {
+    std::lock_guard<std::mutex> lk(g_nccl_mutex);
+    if (!g_nccl.load()) UMT_FAIL(ctx, UMT_ERR_NCCL, "NCCL not available: %s", g_nccl.error.c_str());
+  }
+  delete ctx->transport;
+  ctx->transport = nullptr;
+  auto *t = new NcclTransport;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&t->comm, nRanks, id, myRank);
+  if (r != ncclSuccess) { delete t; UMT_FAIL(ctx, UMT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+  ctx->transport = t;
+  ctx->myRank = myRank; ctx->nRanks = nRanks;
+  ctx->nccl_comm = t->comm;
+  ctx->exch_dirty = true;
+  return UMT_OK;
+}
+
+// contexts of this process become ranks 0..n-1 of an in-process group (each must then be driven by its own thread)
+extern "C" int umt_connect_local(umt_ctx **ctxs, int n) {
+  if (!ctxs || n < 1) return UMT_ERR_ARG;
+  LocalGroup *g = new LocalGroup;
+  g->n = n; g->members.assign(ctxs, ctxs + n); g->refs = n;
+  for (int r = 0; r < n; r++) {
+    umt_ctx *c = ctxs[r];
+    if (!c || c->device < 0) { delete g; return UMT_ERR_ARG; }
+    delete c->transport;
+    auto *t = new LocalTransport;
+    t->grp = g;
+    c->transport = t;
+    c->myRank = r; c->nRanks = n; c->exch_dirty = true;
+  }
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// lists, buffers
+// ---------------------------------------------------------------------------
+static int exchange_incident_tests(umt_ctx *ctx) {
+  // every shared boundary without a neighbour test yet gets it through the transport
+  bool missing = false;
+  for (auto &s : ctx->shared) missing = missing || s.incTestR.size() != (size_t)s.n * ctx->NA;
+  if (!missing) return UMT_OK;
+  if (!ctx->transport) UMT_FAIL(ctx, UMT_ERR_STATE, "shared boundaries need umt_set_comm / umt_connect_local, or umt_set_incident_test from the caller");
+  const size_t nS = ctx->shared.size();
+  std::vector<signed char *> dS(nS, nullptr), dR(nS, nullptr);
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  int rc = UMT_OK;
+  for (size_t k = 0; k < nS && !rc; k++) {
+    SharedBdy &s = ctx->shared[k];
+    const size_t n = (size_t)s.n * ctx->NA;
+    std::vector<signed char> mine(n);
+    rc = umt_get_incident_test(ctx, (int)k, mine.data());
+    if (!rc && (cudaMalloc((void **)&dS[k], n) != cudaSuccess || cudaMalloc((void **)&dR[k], n) != cudaSuccess)) { ctx->err = "cudaMalloc (incident test)"; rc = UMT_ERR_CUDA; }
+    if (!rc) cudaMemcpy(dS[k], mine.data(), n, cudaMemcpyHostToDevice);
+    sp[k] = dS[k]; rp[k] = dR[k]; sb[k] = rb[k] = n;
+  }
+  if (!rc) rc = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "incident test exchange failed"; rc = UMT_ERR_CUDA; }
+  for (size_t k = 0; k < nS; k++) {
+    if (!rc) {
+      SharedBdy &s = ctx->shared[k];
+      s.incTestR.resize((size_t)s.n * ctx->NA);
+      cudaMemcpy(s.incTestR.data(), dR[k], s.incTestR.size(), cudaMemcpyDeviceToHost);
+    }
+    if (dS[k]) cudaFree(dS[k]);
+    if (dR[k]) cudaFree(dR[k]);
+  }
+  return rc;
+}
+
+// ListSend / ListRecv per (shared boundary, angle): findexit.F90:193-287
+static int build_lists(umt_ctx *ctx) {
+  int r = need_abdy(ctx);
+  if (r) return r;
+  const int NA = ctx->NA;
+  for (size_t k = 0; k < ctx->shared.size(); k++) {
+    SharedBdy &s = ctx->shared[k];
+    if (s.incTestR.size() != (size_t)s.n * NA) UMT_FAIL(ctx, UMT_ERR_STATE, "shared boundary %zu: neighbour's incident test missing", k);
+    std::vector<signed char> mine((size_t)s.n * NA);
+    r = umt_get_incident_test(ctx, (int)k, mine.data());
+    if (r) return r;
+    s.send_b.assign(NA, {}); s.recv_b.assign(NA, {});
+    for (int a = 0; a < NA; a++) {
+      const bool me = i_decide(ctx, s.neighbor, a);
+      for (int b = 0; b < s.n; b++) {
+        const int t = me ? mine[(size_t)a * s.n + b] : -s.incTestR[(size_t)a * s.n + b];
+        if (t < 0) s.recv_b[a].push_back(s.first + b);
+        else if (t > 0) s.send_b[a].push_back(s.first + b);
+      }
+    }
+  }
+  return UMT_OK;
+}
+
+extern "C" int umt_get_exchange_counts(umt_ctx *ctx, int sharedIndex, int *nSend /* (NA) */, int *nRecv /* (NA) */) {
+  if (!ctx || sharedIndex < 0 || sharedIndex >= (int)ctx->shared.size()) return UMT_ERR_ARG;
+  const SharedBdy &s = ctx->shared[sharedIndex];
+  if ((int)s.send_b.size() != ctx->NA) UMT_FAIL(ctx, UMT_ERR_STATE, "exchange lists not built (umt_build_exchange)");
+  for (int a = 0; a < ctx->NA; a++) {
+    if (nSend) nSend[a] = (int)s.send_b[a].size();
+    if (nRecv) nRecv[a] = (int)s.recv_b[a].size();
+  }
+  return UMT_OK;
+}
+
+// ListSend(1,:) / ListRecv of one angle (1-based angle, 1-based boundary elements like the reference)
+extern "C" int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, int *listSend, int *listRecv) {
+  if (!ctx || sharedIndex < 0 || sharedIndex >= (int)ctx->shared.size() || angle < 1 || angle > ctx->NA) return UMT_ERR_ARG;
+  const SharedBdy &s = ctx->shared[sharedIndex];
+  if ((int)s.send_b.size() != ctx->NA) UMT_FAIL(ctx, UMT_ERR_STATE, "exchange lists not built (umt_build_exchange)");
+  if (listSend) for (size_t i = 0; i < s.send_b[angle - 1].size(); i++) listSend[i] = s.send_b[angle - 1][i] + 1;
+  if (listRecv) for (size_t i = 0; i < s.recv_b[angle - 1].size(); i++) listRecv[i] = s.recv_b[angle - 1][i] + 1;
+  return UMT_OK;
+}
+
+extern "C" int umt_build_exchange(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_build_exchange: quadrature not set");
+  if (ctx->shared.empty()) { ctx->exch_dirty = false; return UMT_OK; }
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  int r = UMT_OK;
+  if (ctx->device >= 0) r = exchange_incident_tests(ctx);
+  if (!r) r = build_lists(ctx);
+  if (r) return r;
+  if (ctx->device < 0) { ctx->exch_dirty = false; return UMT_OK; }   // host-only: lists only
+  const int NA = ctx->NA, nd = ctx->ndim, G = ctx->G;
+  const int ROWS_PER_CHUNK = std::max(1, 4096 / G);
+  for (auto &s : ctx->shared) {
+    std::vector<long long> srow, rrow;
+    std::vector<double> coef;
+    std::vector<PackChunk> chunks;
+    std::vector<int> nChunksOfAngle(NA, 0);
+    int maxChunks = 1;
+    for (int a = 0; a < NA; a++) maxChunks = std::max(maxChunks, ((int)s.send_b[a].size() + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK);
+    s.send_off.assign(NA + 1, 0); s.recv_off.assign(NA + 1, 0);
+    for (int a = 0; a < NA; a++) {
+      const double *om = &ctx->h_omega[(size_t)a * nd];
+      const int beg = (int)srow.size();
+      for (int b : s.send_b[a]) {
+        double dot = 0.0;
+        for (int d = 0; d < nd; d++) dot += om[d] * ctx->h_Abdy[(size_t)b * nd + d];
+        srow.push_back((long long)a * ctx->rows_total() + ctx->nc + b);
+        coef.push_back(ctx->h_weight[a] * dot);
+      }
+      for (int b : s.recv_b[a]) rrow.push_back((long long)a * ctx->rows_total() + ctx->nc + b);
+      const int end = (int)srow.size();
+      for (int c0 = beg, k = 0; c0 < end; c0 += ROWS_PER_CHUNK, k++) {
+        chunks.push_back({c0, std::min(end, c0 + ROWS_PER_CHUNK), a * maxChunks + k, 0});
+        nChunksOfAngle[a] = k + 1;
+      }
+      s.send_off[a + 1] = (int)srow.size(); s.recv_off[a + 1] = (int)rrow.size();
+    }
+    s.send_rows = srow.size(); s.recv_rows = rrow.size();
+    s.nChunks = (int)chunks.size(); s.maxChunks = maxChunks;
+    if ((r = upload(ctx, &s.d_send_row, srow))) return r;
+    if ((r = upload(ctx, &s.d_recv_row, rrow))) return r;
+    if ((r = upload(ctx, &s.d_send_coef, coef))) return r;
+    if ((r = upload(ctx, &s.d_chunks, chunks))) return r;
+    if ((r = upload(ctx, &s.d_nChunksOfAngle, nChunksOfAngle))) return r;
+    if (s.d_partial) cudaFree(s.d_partial);
+    if (s.d_sendbuf) cudaFree(s.d_sendbuf);
+    if (s.d_recvbuf) cudaFree(s.d_recvbuf);
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_partial, sizeof(double) * (size_t)NA * maxChunks));
+    UMT_CUDA(ctx, cudaMemset(s.d_partial, 0, sizeof(double) * (size_t)NA * maxChunks));
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_sendbuf, sizeof(double) * std::max<size_t>(s.send_rows * G, 1)));
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_recvbuf, sizeof(double) * std::max<size_t>(s.recv_rows * G, 1)));
+  }
+  const size_t nS = ctx->shared.size();
+  // flux-convergence bins: one per comm set (3-D: angle, 2-D: xi-level)
+  std::vector<int> bin(NA);
+  for (int a = 0; a < NA; a++) bin[a] = nd == 3 ? a : ctx->h_level[a];
+  ctx->nBins = nd == 3 ? NA : ctx->nLevels;
+  if ((r = upload(ctx, &ctx->d_binOfAngle, bin))) return r;
+  void **arrs[] = {(void **)&ctx->d_exitFlux, (void **)&ctx->d_incRecv, (void **)&ctx->d_incFlux, (void **)&ctx->d_incFluxOld};
+  const size_t sizes[] = {nS * NA, nS * NA, (size_t)ctx->nBins, (size_t)ctx->nBins};
+  for (int i = 0; i < 4; i++) {
+    if (*arrs[i]) cudaFree(*arrs[i]);
+    UMT_CUDA(ctx, cudaMalloc(arrs[i], sizeof(double) * std::max<size_t>(sizes[i], 1)));
+    UMT_CUDA(ctx, cudaMemset(*arrs[i], 0, sizeof(double) * std::max<size_t>(sizes[i], 1)));
+  }
+  if (!ctx->d_nNotConv) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_nNotConv, sizeof(int)));
+  ctx->exch_dirty = false;
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-pass pieces used by umt_sweep
+// ---------------------------------------------------------------------------
+static int ready(umt_ctx *ctx) {
+  if (ctx->exch_dirty) { int r = umt_build_exchange(ctx); if (r) return r; }
+  if (!ctx->transport) UMT_FAIL(ctx, UMT_ERR_STATE, "domain has shared boundaries but no communicator (umt_set_comm / umt_connect_local)");
+  return UMT_OK;
+}
+
+// pack the exiting rows of every angle for every neighbour and tally the exit currents; then trade the
+// currents with the neighbours and update IncFlux / IncFluxOld (setIncidentFlux)
+int umt_exchange_tally(umt_ctx *ctx, double tol) {
+  int r = ready(ctx);
+  if (r) return r;
+  const int NA = ctx->NA, G = ctx->G;
+  const size_t nS = ctx->shared.size();
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    if (s.nChunks > 0) {
+      pack_tally_kernel<<<s.nChunks, 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
+      ctx->last_launches++;
+    }
+    tally_finish_kernel<<<(NA + 127) / 128, 128, 0, ctx->stream>>>(s.d_partial, s.d_nChunksOfAngle, s.maxChunks, ctx->d_exitFlux + k * NA, NA);
+    ctx->last_launches++;
+    sp[k] = ctx->d_exitFlux + k * NA; rp[k] = ctx->d_incRecv + k * NA; sb[k] = rb[k] = sizeof(double) * NA;
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (r) return r;
+  flux_conv_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, ctx->d_incFlux,
+                                              ctx->d_incFluxOld, tol, ctx->fluxFloor, ctx->d_nNotConv);
+  UMT_CUDA(ctx, cudaGetLastError());
+  ctx->last_launches++;
+  return UMT_OK;
+}
+
+// SendFlux / RecvFlux for every angle: what the neighbours packed after their previous sweep lands in my incident rows
+int umt_exchange_begin_pass(umt_ctx *ctx) {
+  int r = ready(ctx);
+  if (r) return r;
+  const int G = ctx->G;
+  const size_t nS = ctx->shared.size();
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    sp[k] = s.d_sendbuf; rp[k] = s.d_recvbuf;
+    sb[k] = sizeof(double) * s.send_rows * G; rb[k] = sizeof(double) * s.recv_rows * G;
+  }
+  r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (r) return r;
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    const long long n = (long long)s.recv_rows * G;
+    if (n > 0) {
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_recv_row, s.d_recvbuf, n, G);
+      ctx->last_launches++;
+    }
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}
+
+// Allreduce(max) of the nNotConv the last umt_exchange_tally left on the device (SetSweep.F90:189-199)
+int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv) {
+  int r = ctx->transport->allreduce_max(ctx, ctx->d_nNotConv);
+  if (r) return r;
+  UMT_CUDA(ctx, cudaMemcpyAsync(nNotConv, ctx->d_nNotConv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+extern "C" int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incFluxOld) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (!ctx->d_incFlux) UMT_FAIL(ctx, UMT_ERR_STATE, "no exchange state");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (incFlux) UMT_CUDA(ctx, cudaMemcpy(incFlux, ctx->d_incFlux, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
+  if (incFluxOld) UMT_CUDA(ctx, cudaMemcpy(incFluxOld, ctx->d_incFluxOld, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+extern "C" int umt_set_flux_floor(umt_ctx *ctx, double floorFlux) {
+  if (!ctx) return UMT_ERR_ARG;
+  ctx->fluxFloor = floorFlux;
+  return UMT_OK;
+}

@@ -1,0 +1,270 @@
+// 2-D (r,z) upstream-corner-balance sweep for sm_100a.
+//
+// Replaces snac/SweepUCBrz.F90:11-282 (one angle, one set) and the angle loop of
+// snac/SetSweep.F90:113-170 for ndim == 2.  One persistent kernel sweeps every
+// non-finishing angle.  Work items are (angle, hyperplane, chunk of zones); CTAs
+// pull them through an atomic ticket.  Two dependencies gate an item:
+//   * its own angle's previous hyperplane (upstream Psi1 across FP faces);
+//   * the angular-derivative chain: angles of one xi-level are coupled through the
+//     half-angle intensity PsiM(:,c) (SweepUCBrz.F90:212-240), so zone z of angle
+//     k+1 of a level needs zone z of angle k.  The host turns that into "the latest
+//     plane of the previous angle that holds a zone of this plane is complete"
+//     (planes of one angle complete in order), so consecutive angles of a level
+//     pipeline through the mesh instead of running back to back, and the 4P levels
+//     are independent of each other.
+// One thread owns one (zone, group): group index on consecutive lanes, so all loads
+// and stores of Psi, STotal, Psi1, PsiM, PsiB are contiguous G*8-byte rows.
+// Exiting boundary fluxes (SweepUCBrz.F90:245-266) and the finishing direction's
+// Psi/PsiB <- PsiM are written by the thread that owns the corner.
+#include <algorithm>
+#include <cstdlib>
+
+#include "umt_internal.h"
+
+namespace {
+
+constexpr int MAXC2 = 8;   // corners per zone (quads: 4; general polygons up to 8)
+constexpr double FOURALPHA = 1.82;   // SweepUCBrz.F90:88
+
+struct SweepRZParams {
+  int nc, nb, nz, G, NA, nItems;
+  double tau;
+  const int *numCorner, *cOffSet, *cFP /* 0-based row; >= nc: boundary */, *cEZ /* 0-based */;
+  const double *Volume, *Area, *Afp, *Aez, *RadiusFP, *RadiusEZ, *omega;
+  const double *angDerivFac, *tauW1, *tauW2;
+  const unsigned char *start, *finishNext;   // finishNext[a] = FinishingDirection(a+1)
+  const int *level;                          // xi-level of each angle
+  const int *nextZ;
+  const unsigned char *nextC;
+  const WorkItem *items;
+  int *counters;
+  const double *psi, *stotal, *sigt;
+  double *psi1, *psim;
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// SweepUCBrz.F90:103-243 for one (zone, group)
+__device__ __forceinline__ void solve_zone_rz(const SweepRZParams &P, int a, int zone0, int g) {
+  const int G = P.G, nc = P.nc;
+  const double om0 = P.omega[2 * a], om1 = P.omega[2 * a + 1];
+  const size_t slab = (size_t)(nc + P.nb) * G;
+  const double *psiA = P.psi + (size_t)a * slab;
+  double *psi1A = P.psi1 + (size_t)a * slab;
+  double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
+  const double sig = P.sigt[(size_t)zone * G + g];
+  const double fac = P.angDerivFac[a];
+
+  double Q[MAXC2], src[MAXC2], sumArea[MAXC2];
+  int nxez[MAXC2], ez_exit[MAXC2][2];
+  double coefpsi[MAXC2][2];
+  for (int c = 0; c < nCorner; c++) {
+    const size_t r = (size_t)(c0 + c) * G + g;
+    const double source = P.stotal[r] + P.tau * psiA[r];
+    Q[c] = source;
+    src[c] = P.Volume[c0 + c] * source;
+    sumArea[c] = fac * P.Area[c0 + c];
+    nxez[c] = 0;
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    for (int f = 0; f < 2; f++) {
+      const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
+      const double *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
+      const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
+      const double aez = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
+      double psifp = 0.0;
+      if (afp < 0.0) {
+        const int row = P.cFP[cc * 2 + f];
+        psifp = __ldcg(&psi1A[(size_t)row * G + g]);
+        const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
+        sumArea[c] -= R_afp;
+        src[c] -= R_afp * psifp;
+      }
+      if (aez > 0.0) {
+        const double R = P.RadiusEZ[cc * 2 + f];
+        const int cez = P.cEZ[cc * 2 + f];
+        const double area = P.Area[cc];
+        ez_exit[c][nxez[c]] = cez;
+        coefpsi[c][nxez[c]] = R * aez;
+        nxez[c]++;
+        sumArea[cez] += R * aez;
+        double sez;
+        if (afp < 0.0) {
+          const double sigA = sig * area, sigA2 = sigA * sigA;
+          const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+          const double gden = area * (4.0 * sigA * sigA2 + aez * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+          sez = R * (area * gnum * (sig * psifp - Q[c]) + 0.5 * aez * gden * (Q[c] - Q[cez])) / (gnum + gden * sig);
+        } else {
+          sez = 0.5 * R * aez * (Q[c] - Q[cez]) / sig;
+        }
+        src[c] += sez;
+        src[cez] -= sez;
+      }
+    }
+  }
+  for (int i = 0; i < nCorner; i++) {
+    const int c = nextC[c0 + i];
+    const size_t r = (size_t)(c0 + c) * G + g;
+    const double p = (src[c] + P.Area[c0 + c] * fac * psimL[r]) / (sumArea[c] + sig * P.Volume[c0 + c]);
+    src[c] = p;   // src now holds the corner flux
+    for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * p;
+  }
+  // half-angle intensity for the next angle of the level; exiting boundary fluxes; finishing direction
+  const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
+  double *psi1N = psi1A + slab;   // slab of angle a+1 (only touched when it is a finishing direction)
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    const size_t r = (size_t)cc * G + g;
+    const double p = src[c];
+    const double pm = starting ? p : P.tauW1[a] * p - P.tauW2[a] * psimL[r];
+    psimL[r] = pm;
+    psi1A[r] = p;
+    if (fin) psi1N[r] = pm;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
+    for (int f = 0; f < 2; f++) {
+      const int row = P.cFP[cc * 2 + f];
+      if (row >= nc) {
+        const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
+        const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
+        if (afp > 0.0) {
+          psi1A[(size_t)row * G + g] = p;             // PsiB(:,b,Angle)   <- Psi1(:,c)
+          if (fin) psi1N[(size_t)row * G + g] = pm;   // PsiB(:,b,Angle+1) <- PsiM(:,c)
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) sweeprz_kernel(SweepRZParams P) {
+  __shared__ int s_item;
+  const int G = P.G;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= P.nItems) break;
+    const WorkItem w = P.items[it];
+    if (threadIdx.x == 0) {
+      if (w.wait_idx >= 0)
+        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(64);
+      if (w.pad0 >= 0)   // second dependency: the previous angle of this xi-level (PsiM chain)
+        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(64);
+    }
+    __syncthreads();
+    const int *nextZ = P.nextZ + (size_t)w.angle * P.nz;
+    const int npairs = (w.zend - w.zbeg) * G;
+    for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
+      const int zi = idx / G, g = idx - zi * G;
+      solve_zone_rz(P, w.angle, nextZ[w.zbeg + zi], g);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+    }
+  }
+}
+
+}  // namespace
+
+// Work items of the RZ sweep in a topological order of both dependencies (host side, once per schedule).
+int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
+  const int NA = ctx->NA, nz = ctx->nz;
+  int maxHyp = 0;
+  for (int a = 0; a < NA; a++) maxHyp = std::max(maxHyp, ctx->nHyp[a]);
+  // xi-levels: a level starts at a starting direction; finishing directions are not swept
+  std::vector<int> level(NA, 0), prev(NA, -1);
+  int lev = -1, last = -1;
+  for (int a = 0; a < NA; a++) {
+    if (ctx->h_start[a] || lev < 0) { lev++; last = -1; }
+    level[a] = lev;
+    if (ctx->nHyp[a] == 0) continue;
+    prev[a] = last;
+    last = a;
+  }
+  ctx->h_level = level;
+  ctx->nLevels = lev + 1;
+  std::vector<std::vector<int>> planeOf(NA), nItemsPlane(NA), planeStart(NA), tdone(NA), dep2(NA);
+  struct Key { int t, a, p; };
+  std::vector<Key> keys;
+  for (int a = 0; a < NA; a++) {
+    const int nh = ctx->nHyp[a];
+    if (nh == 0) continue;
+    planeOf[a].assign(nz, 0);
+    planeStart[a].assign(nh + 1, 0);
+    nItemsPlane[a].assign(nh, 0);
+    tdone[a].assign(nh, 0);
+    dep2[a].assign(nh, -1);
+    for (int p = 0; p < nh; p++) {
+      const int n = ctx->zonesInPlane[a][p];
+      planeStart[a][p + 1] = planeStart[a][p] + n;
+      nItemsPlane[a][p] = (n + zpi - 1) / zpi;
+      for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) planeOf[a][std::abs(ctx->nextZ[a][i]) - 1] = p;
+    }
+    const int pa = prev[a];
+    for (int p = 0; p < nh; p++) {
+      int t = p > 0 ? tdone[a][p - 1] : 0;
+      if (pa >= 0) {
+        int q = 0;
+        for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) q = std::max(q, planeOf[pa][std::abs(ctx->nextZ[a][i]) - 1]);
+        dep2[a][p] = q;
+        t = std::max(t, tdone[pa][q]);
+      }
+      tdone[a][p] = t + 1;
+      keys.push_back({t + 1, a, p});
+    }
+  }
+  std::stable_sort(keys.begin(), keys.end(), [](const Key &x, const Key &y) { return x.t < y.t; });
+  items.clear();
+  for (const Key &k : keys) {
+    const int a = k.a, p = k.p;
+    const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
+    for (int j = 0; j < nItemsPlane[a][p]; j++) {
+      WorkItem w;
+      w.angle = a;
+      w.zbeg = z0 + j * zpi;
+      w.zend = std::min(z0 + n, w.zbeg + zpi);
+      w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
+      w.wait_count = p > 0 ? nItemsPlane[a][p - 1] : 0;
+      w.signal_idx = a * maxHyp + p;
+      w.pad0 = dep2[a][p] >= 0 ? prev[a] * maxHyp + dep2[a][p] : -1;
+      w.pad1 = dep2[a][p] >= 0 ? nItemsPlane[prev[a]][dep2[a][p]] : 0;
+      items.push_back(w);
+    }
+  }
+  return UMT_OK;
+}
+
+int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
+  if (ctx->maxCorner > MAXC2 || ctx->maxcf != 2)
+    UMT_FAIL(ctx, UMT_ERR_ARG, "RZ sweep supports maxCorner <= %d and maxcf == 2 (got %d, %d)", MAXC2, ctx->maxCorner, ctx->maxcf);
+  if (!ctx->d_level || !ctx->d_psim) UMT_FAIL(ctx, UMT_ERR_STATE, "RZ sweep: schedule/state not finalized");
+  SweepRZParams P;
+  P.nc = ctx->nc; P.nb = ctx->nb; P.nz = ctx->nz; P.G = ctx->G; P.NA = ctx->NA; P.nItems = ctx->nItems;
+  P.tau = ctx->tau;
+  P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
+  P.Volume = ctx->d_Volume; P.Area = ctx->d_Area; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez;
+  P.RadiusFP = ctx->d_RadiusFP; P.RadiusEZ = ctx->d_RadiusEZ; P.omega = ctx->d_omega;
+  P.angDerivFac = ctx->d_angDerivFac; P.tauW1 = ctx->d_tauW1; P.tauW2 = ctx->d_tauW2;
+  P.start = ctx->d_start; P.finishNext = ctx->d_finishNext; P.level = ctx->d_level;
+  P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
+  P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1; P.psim = ctx->d_psim;
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
+  // Set%PsiM = 0 at the start of every flux pass (SetSweep.F90:94-96)
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * (size_t)ctx->nLevels * ctx->nc * ctx->G, ctx->stream));
+  int occ = 0;
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweeprz_kernel, 128, 0));
+  if (occ < 1) occ = 1;
+  const int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
+  sweeprz_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+  UMT_CUDA(ctx, cudaGetLastError());
+  ctx->last_launches += 1;
+  return UMT_OK;
+}

@@ -75,14 +75,10 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_Aez, ctx->d_Area, ctx->d_RadiusFP, ctx->d_RadiusEZ, ctx->d_omega, ctx->d_weight, ctx->d_nextZ,
                   ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
-                  ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo};
+                  ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo, ctx->d_angDerivFac, ctx->d_tauW1, ctx->d_tauW2,
+                  ctx->d_start, ctx->d_finishNext, ctx->d_level};
   for (void *p : ptrs) if (p) cudaFree(p);
-  for (auto &s : ctx->shared) {
-    if (s.d_send_idx) cudaFree(s.d_send_idx);
-    if (s.d_recv_idx) cudaFree(s.d_recv_idx);
-    if (s.d_sendbuf) cudaFree(s.d_sendbuf);
-    if (s.d_recvbuf) cudaFree(s.d_recvbuf);
-  }
+  umt_exchange_release(ctx);
   for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -186,6 +182,21 @@ extern "C" int umt_set_quadrature(umt_ctx *ctx, int nAngles, const double *omega
   }
   TRY(dev_alloc_copy(ctx, &ctx->d_omega, omega, (size_t)ctx->ndim * nAngles));
   TRY(dev_alloc_copy(ctx, &ctx->d_weight, weight, nAngles));
+  if (ctx->ndim == 2) {
+    // xi-levels: a level begins at every starting direction (rt/rtquad.F90:107-127)
+    ctx->h_level.assign(nAngles, 0);
+    int lev = -1;
+    for (int a = 0; a < nAngles; a++) { if (ctx->h_start[a] || lev < 0) lev++; ctx->h_level[a] = lev; }
+    ctx->nLevels = lev + 1;
+    std::vector<unsigned char> finNext(nAngles);
+    for (int a = 0; a < nAngles; a++) finNext[a] = ctx->h_finish[a + 1];
+    TRY(dev_alloc_copy(ctx, &ctx->d_angDerivFac, angDerivFac, nAngles));
+    TRY(dev_alloc_copy(ctx, &ctx->d_tauW1, w1, nAngles));
+    TRY(dev_alloc_copy(ctx, &ctx->d_tauW2, w2, nAngles));
+    TRY(dev_alloc_copy(ctx, &ctx->d_start, ctx->h_start.data(), nAngles));
+    TRY(dev_alloc_copy(ctx, &ctx->d_finishNext, finNext.data(), nAngles));
+    TRY(dev_alloc_copy(ctx, &ctx->d_level, ctx->h_level.data(), nAngles));
+  }
   ctx->nHyp.assign(nAngles, 0); ctx->numCycles.assign(nAngles, 0); ctx->cycleOffSet.assign(nAngles, 0); ctx->nBad.assign(nAngles, 0);
   ctx->zonesInPlane.assign(nAngles, {}); ctx->nextZ.assign(nAngles, {}); ctx->nextC.assign(nAngles, {});
   ctx->cycleList.assign(nAngles, {}); ctx->bdyList.assign(nAngles, {});
@@ -297,7 +308,9 @@ static int finalize_schedule(umt_ctx *ctx) {
   if (const char *e = getenv("UMT_SWEEP3D")) if (!strcmp(e, "generic")) ctx->use_plan = false;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
-  const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, 512 / ctx->G);
+  int pairsRZ = 256;
+  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairsRZ = std::max(1, atoi(e));
+  const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, pairsRZ / ctx->G);
   ctx->zones_per_item = zpi;
   // Angles run in batches of K with staggered starts: a batch in its growing half overlaps the
   // previous batch's shrinking half, so the work per level is steady while the Psi1 rows of
@@ -332,7 +345,8 @@ static int finalize_schedule(umt_ctx *ctx) {
     }
   }
   const int nBatches = (NA + K - 1) / K;
-  const int nLevels = maxHyp + (nBatches - 1) * delta;
+  const int nLevels = ctx->ndim == 2 ? 0 : maxHyp + (nBatches - 1) * delta;
+  if (ctx->ndim == 2) TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering
   for (int lev = 0; lev < nLevels; lev++)
     for (int a = 0; a < NA; a++) {
       const int p = lev - (a / K) * delta;
@@ -428,8 +442,9 @@ static int ensure_state(umt_ctx *ctx) {
   UMT_CUDA(ctx, cudaMemset(ctx->d_sigt, 0, sizeof(double) * G * ctx->nz));
   UMT_CUDA(ctx, cudaMemset(ctx->d_phi, 0, sizeof(double) * G * nc));
   if (ctx->ndim == 2) {
-    UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psim, sizeof(double) * G * nc * NA));
-    UMT_CUDA(ctx, cudaMemset(ctx->d_psim, 0, sizeof(double) * G * nc * NA));
+    const size_t nl = (size_t)std::max(ctx->nLevels, 1);   // Set%PsiM(G,nc), one per xi-level (levels sweep concurrently)
+    UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psim, sizeof(double) * G * nc * nl));
+    UMT_CUDA(ctx, cudaMemset(ctx->d_psim, 0, sizeof(double) * G * nc * nl));
   }
   return UMT_OK;
 }
@@ -629,8 +644,6 @@ extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
 // ---------------------------------------------------------------------------
 // the controller: rt/ControlSweep.F90 -> snac/SetSweep.F90 -> getPhiTotal
 // ---------------------------------------------------------------------------
-int umt_exchange_begin_pass(umt_ctx *ctx);                      // exchange.cu
-int umt_exchange_test_convergence(umt_ctx *ctx, double tol, int *nNotConv);
 
 extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone) {
   if (!ctx) return UMT_ERR_ARG;
@@ -645,6 +658,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   int iter = 0;
   const bool multi = !ctx->shared.empty();
+  if (multi) TRY(umt_exchange_tally(ctx, fluxTol));   // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74); packs the exiting rows
   for (;;) {
     iter++;
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -666,7 +680,10 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
     }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     int nNotConv = 0;
-    if (multi) TRY(umt_exchange_test_convergence(ctx, fluxTol, &nNotConv));  // setIncidentFlux + testFluxConv + Allreduce(max)
+    if (multi) {                                     // setIncidentFlux + testFluxConv + Allreduce(max nNotConv)
+      TRY(umt_exchange_tally(ctx, fluxTol));
+      TRY(umt_exchange_test_convergence(ctx, &nNotConv));
+    }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
     float t;

@@ -39,13 +39,21 @@ struct alignas(16) ZoneRec {
 };
 static_assert(sizeof(ZoneEdge) == 32 && sizeof(ZoneRec) == 992, "ZoneRec layout");
 
+struct PackChunk { int rowBeg, rowEnd, slot, pad; };   // send rows of one (neighbour, angle) handled by one CTA; slot = angle * maxChunks + chunk
+struct UmtTransport;    // exchange.cu: NCCL or in-process
 struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int neighbor;
   int first;            // 0-based first boundary element
   int n;
+  std::vector<signed char> incTestR;                       // the neighbour's sign(omega.A_bdy) for the angles it decides, (n, NA)
   // per angle: send rows (boundary element, 0-based) and recv rows
   std::vector<std::vector<int>> send_b, recv_b;
-  int *d_send_idx = nullptr, *d_recv_idx = nullptr;       // concatenated over angles
+  long long *d_send_row = nullptr, *d_recv_row = nullptr;  // row index into the (NA, nc+nb) slab array, concatenated over angles
+  double *d_send_coef = nullptr;                           // w_a (omega_a . A_bdy) per send row
+  PackChunk *d_chunks = nullptr;
+  int *d_nChunksOfAngle = nullptr;
+  double *d_partial = nullptr;                             // (NA, maxChunks) partial exit currents
+  int nChunks = 0, maxChunks = 1;
   std::vector<int> send_off, recv_off;                     // per-angle offsets (NA+1)
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
   size_t send_rows = 0, recv_rows = 0;
@@ -78,6 +86,12 @@ struct umt_ctx {
   int *d_numCorner = nullptr, *d_cOffSet = nullptr, *d_nCFaces = nullptr, *d_cFP = nullptr, *d_cEZ = nullptr;
   double *d_Volume = nullptr, *d_Afp = nullptr, *d_Aez = nullptr, *d_Area = nullptr, *d_RadiusFP = nullptr, *d_RadiusEZ = nullptr;
   double *d_omega = nullptr, *d_weight = nullptr;
+  // RZ only: angular-derivative coefficients, starting flags, FinishingDirection(a+1), xi-level of each angle
+  double *d_angDerivFac = nullptr, *d_tauW1 = nullptr, *d_tauW2 = nullptr;
+  unsigned char *d_start = nullptr, *d_finishNext = nullptr;
+  int *d_level = nullptr;
+  std::vector<int> h_level;
+  int nLevels = 0;
   // device: schedule
   int *d_nextZ = nullptr;              // (NA, nz) signed 1-based
   unsigned char *d_nextC = nullptr;    // (NA, nc) 0-based local corner
@@ -104,8 +118,14 @@ struct umt_ctx {
   std::vector<SharedBdy> shared;
   int myRank = 0, nRanks = 1;
   void *nccl_comm = nullptr;
+  UmtTransport *transport = nullptr;
   bool exch_dirty = true;
-  std::vector<double> incFlux, incFluxOld;
+  double *d_exitFlux = nullptr, *d_incRecv = nullptr;      // (nShared, NA) exit currents sent / received
+  double *d_incFlux = nullptr, *d_incFluxOld = nullptr;    // (nBins) CSet%IncFlux, IncFluxOld
+  int *d_binOfAngle = nullptr, *d_nNotConv = nullptr;
+  int nBins = 0;
+  double fluxFloor = 0.0;
+  int rows_total() const { return nc + nb; }
 
   // stats
   double last_ms[4] = {0, 0, 0, 0};
@@ -133,9 +153,14 @@ int umt_launch_sweep3d(umt_ctx *ctx);
 int umt_build_plan3d(umt_ctx *ctx);
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx);
 int umt_launch_sweeprz(umt_ctx *ctx, int savePsi);
+int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zonesPerItem);
 int umt_host_build_schedule(umt_ctx *ctx);
 int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polaraxis,
                                 std::vector<double> &omega, std::vector<double> &weight,
                                 std::vector<unsigned char> &start, std::vector<unsigned char> &finish,
                                 std::vector<double> &angDerivFac, std::vector<double> &w1, std::vector<double> &w2);
 int umt_device_geometry(umt_ctx *ctx, const double *d_px);
+void umt_exchange_release(umt_ctx *ctx);
+int umt_exchange_tally(umt_ctx *ctx, double tol);
+int umt_exchange_begin_pass(umt_ctx *ctx);
+int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);

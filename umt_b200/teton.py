@@ -231,6 +231,41 @@ class SweepContext:
         buf = (C.c_ubyte * 128).from_buffer_copy(id128)
         self._ck(self.lib.umt_set_comm(self.h, int(myRank), int(nRanks), buf), "umt_set_comm")
 
+    def set_rank(self, myRank, nRanks):
+        self._ck(self.lib.umt_set_rank(self.h, int(myRank), int(nRanks)), "umt_set_rank")
+
+    def get_incident_test(self, sharedIndex, nBdyElem):
+        out = np.zeros((self.NA, nBdyElem), np.int8)
+        self._ck(self.lib.umt_get_incident_test(self.h, int(sharedIndex), out.ctypes.data_as(C.c_void_p)), "umt_get_incident_test")
+        return out
+
+    def set_incident_test(self, sharedIndex, incTestNeighbor):
+        a = np.ascontiguousarray(incTestNeighbor, dtype=np.int8)
+        self._ck(self.lib.umt_set_incident_test(self.h, int(sharedIndex), a.ctypes.data_as(C.c_void_p)), "umt_set_incident_test")
+
+    def build_exchange(self):
+        self._ck(self.lib.umt_build_exchange(self.h), "umt_build_exchange")
+
+    def exchange_counts(self, sharedIndex):
+        ns, nr = np.zeros(self.NA, np.int32), np.zeros(self.NA, np.int32)
+        self._ck(self.lib.umt_get_exchange_counts(self.h, int(sharedIndex), _ip(ns), _ip(nr)), "umt_get_exchange_counts")
+        return ns, nr
+
+    def exchange_lists(self, sharedIndex, angle):
+        ns, nr = self.exchange_counts(sharedIndex)
+        ls, lr = np.zeros(max(ns[angle - 1], 1), np.int32), np.zeros(max(nr[angle - 1], 1), np.int32)
+        self._ck(self.lib.umt_get_exchange_lists(self.h, int(sharedIndex), int(angle), _ip(ls), _ip(lr)), "umt_get_exchange_lists")
+        return ls[:ns[angle - 1]], lr[:nr[angle - 1]]
+
+    def incident_flux(self, nBins=None):
+        n = nBins if nBins is not None else self.NA
+        a, b = np.zeros(n), np.zeros(n)
+        self._ck(self.lib.umt_get_incident_flux(self.h, _dp(a), _dp(b)), "umt_get_incident_flux")
+        return a, b
+
+    def set_flux_floor(self, v):
+        self._ck(self.lib.umt_set_flux_floor(self.h, C.c_double(v)), "umt_set_flux_floor")
+
 
 def planck_groups(T, bounds, k=1.0, Bnorm=1.0):
     lib = load_library()
@@ -240,6 +275,15 @@ def planck_groups(T, bounds, k=1.0, Bnorm=1.0):
     if rc:
         raise UmtError(f"umt_planck_groups -> {rc}")
     return B
+
+
+def connect_local(contexts):
+    """The contexts become ranks 0..n-1 of an in-process group (drive each from its own thread)."""
+    lib = load_library()
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = lib.umt_connect_local(arr, len(contexts))
+    if rc:
+        raise UmtError(f"umt_connect_local -> {rc}")
 
 
 def nccl_unique_id() -> bytes:
