@@ -162,11 +162,40 @@ int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incFluxOld);
 /* adqtEpsilon*speed_light*rad_constant*tr4floor of rt/testFluxConv.F90:73 (default 0). */
 int umt_set_flux_floor(umt_ctx *ctx, double floorFlux);
 
-/* ---- grey transport acceleration: snac/GTASweep.F90, snac/SweepGreyUCBxyz.F90 ---- */
+/* ---- grey transport acceleration (3-D, "new" GTA solver): rt/GTASolver.F90, snac/GTASweep.F90 ---- */
+/* GTA angle set (level-symmetric S2, 8 ordinates: rt/quadxyz.F90), its sweep order (rtorder/snnext) and device arrays.
+   Needs full connectivity and geometry. */
+int umt_gta_setup(umt_ctx *ctx);
+int umt_gta_get_quadrature(umt_ctx *ctx, double *omega /* (3,8) */, double *weight /* (8) */);
+/* GTA%GreySigTotal, GreySigScat, GreySigScatVol (ncornr) from the caller (GreySigtInv = 1/GreySigTotal) ... */
 int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, const double *GreySigScat,
                         const double *GreySigScatVol);
+/* ... or rt/setGTAOpacity.F90:10-113 (setGTAOpacityNEW) on the device from Mat%Siga, Mat%Sigs (ngr,nzones),
+   Mat%Eta (ncornr) and GTA%Chi (ngr,ncornr); Chi is returned rescaled and kept on the device.  Uses tau of umt_upload_state. */
+int umt_gta_compute_opacity(umt_ctx *ctx, const double *Siga, const double *Sigs, const double *Eta, double *Chi);
+int umt_gta_get_opacity(umt_ctx *ctx, double *GreySigTotal, double *GreySigScat, double *GreySigScatVol, double *GreySigtInv);
+/* rt/getCollisionRate.F90:10-97 on the device-resident PhiTotal: GTA%GreySource(c) = sum_g (Eta siga + sigs) PhiTotal
+   (residualFlag 1: minus its previous value).  GreySource may be NULL (result stays on the device). */
+int umt_collision_rate(umt_ctx *ctx, const double *Eta, const double *Siga, const double *Sigs, int residualFlag,
+                       double *GreySource);
+int umt_gta_set_source(umt_ctx *ctx, const double *GreySource);
+/* snac/InitSweepGreyUCBxyz.F90: within-zone transfer matrices GTA%TT(maxCorner, ncornr); TT may be NULL. */
+int umt_gta_init_tt(umt_ctx *ctx, double *TT);
+/* snac/GTASweep.F90 (GTA%ID = 1) + snac/SweepGreyUCBxyz.F90 KernelNew for all 8 angles: TsaSource = wtiso (GreySigScat P +
+   GreySource); GreySource NULL keeps the device copy, withSource 0 sweeps with GreySource = 0.
+   PsiB_gta (nbelem, 8) in/out (may be NULL = 0), PhiInc (ncornr) out. */
 int umt_gta_sweep(umt_ctx *ctx, const double *P, const double *GreySource, double *PsiB_gta,
                   double *PhiInc, int withSource);
+/* rt/GreySweep.F90:12-48 (GreySweepNEW): sweep + snac/UpdateScalarIntensity.F90 per-zone LU/solve; P, PsiB_gta in/out.
+   The withSource call decomposes TT in place (once per umt_gta_init_tt). */
+int umt_gta_grey_sweep(umt_ctx *ctx, double *P, double *PsiB_gta, int withSource);
+/* rt/GTASolver.F90:42-425: BiCGSTAB for the grey corrections from the device-resident PhiTotal and GreySource
+   (epsPoint/maxIters = the "grey" iteration control, epsGrey = GTA%epsGrey, enforceHardMax = GTA%enforceHardGTAIterMax). */
+int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double epsGrey, int enforceHardMax, int *nGreyIter,
+                  double *maxRelErrGrey);
+int umt_gta_get_correction(umt_ctx *ctx, double *GreyCorrection);
+/* rt/addGreyCorrections.F90:70-91: PhiTotal(g,c) += GreyCorrection(c) Chi(g,c) on the device. */
+int umt_add_grey_corrections(umt_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -222,3 +222,92 @@ def planck_groups_ref(T: float, bounds: np.ndarray, k: float = 1.0, Bnorm: float
     b = np.ascontiguousarray(bounds, dtype=np.float64)
     _NBB.NBB_integrateBlackBodyGroups(C.c_double(T), C.c_double(k), C.c_double(Bnorm), C.c_int(ng), _dp(b), _dp(B))
     return B
+
+
+# ---------------------------------------------------------------------------
+# grey transport acceleration (umt_oracle_gta.c), 3-D, "new" GTA solver
+# ---------------------------------------------------------------------------
+class _Gta(C.Structure):
+    _fields_ = [("M", C.POINTER(_Mesh)), ("nAng", C.c_int), ("nHyperPlanes", c_ip), ("zonesInPlane", c_ip), ("nextZ", c_ip),
+                ("nextC", c_ip), ("omega", c_dp), ("weight", c_dp), ("Volume", c_dp), ("A_fp", c_dp), ("A_ez", c_dp),
+                ("GreySigTotal", c_dp), ("GreySigtInv", c_dp), ("GreySigScat", c_dp), ("GreySigScatVol", c_dp),
+                ("GreySource", c_dp), ("TT", c_dp), ("wtiso", C.c_double)]
+
+
+def gta_quad_xyz():
+    omega, weight = np.zeros((8, 3)), np.zeros(8)
+    lib().orc_gta_quad_xyz(_dp(omega), _dp(weight))
+    return omega, weight
+
+
+def gta_set_opacity(om: OMesh, geom, tau, Siga, Sigs, Eta, Chi):
+    """setGTAOpacityNEW; Chi (nc,ngr) is rescaled in place.  Returns dict of grey opacities."""
+    nc = om.m.ncornr
+    ngr = Siga.shape[-1]
+    o = dict(GreySigTotal=np.zeros(nc), GreySigScat=np.zeros(nc), GreySigScatVol=np.zeros(nc), GreySigtInv=np.zeros(nc))
+    lib().orc_gta_set_opacity(om.ref, ngr, C.c_double(tau), _dp(Siga), _dp(Sigs), _dp(Eta), _dp(Chi), _dp(geom["Volume"]),
+                              _dp(o["GreySigTotal"]), _dp(o["GreySigScat"]), _dp(o["GreySigScatVol"]), _dp(o["GreySigtInv"]))
+    return o
+
+
+def collision_rate(om: OMesh, Eta, Siga, Sigs, PhiTotal, GreySource, residualFlag):
+    lib().orc_collision_rate(om.ref, Siga.shape[-1], _dp(Eta), _dp(Siga), _dp(Sigs), _dp(PhiTotal), _dp(GreySource), int(residualFlag))
+    return GreySource
+
+
+class GtaProblem:
+    """Keeps every array the C struct points at alive."""
+
+    def __init__(self, om: OMesh, geom, sched, omega, weight, opac, GreySource, wtiso):
+        self.om, self.geom, self.sched = om, geom, sched
+        self.omega = np.ascontiguousarray(omega)
+        self.weight = np.ascontiguousarray(weight)
+        self.opac = {k: np.ascontiguousarray(v) for k, v in opac.items()}
+        self.GreySource = np.ascontiguousarray(GreySource, dtype=np.float64).copy()
+        self.TT = np.zeros((om.m.ncornr, om.m.maxCorner))
+        s = _Gta()
+        s.M = C.pointer(om.s)
+        s.nAng = len(weight)
+        s.nHyperPlanes, s.zonesInPlane, s.nextZ, s.nextC = (_ip(sched[k]) for k in ("nHyperPlanes", "zonesInPlane", "nextZ", "nextC"))
+        s.omega, s.weight = _dp(self.omega), _dp(self.weight)
+        s.Volume, s.A_fp, s.A_ez = _dp(geom["Volume"]), _dp(geom["A_fp"]), _dp(geom["A_ez"])
+        for k in ("GreySigTotal", "GreySigtInv", "GreySigScat", "GreySigScatVol"):
+            setattr(s, k, _dp(self.opac[k]))
+        s.GreySource, s.TT, s.wtiso = _dp(self.GreySource), _dp(self.TT), wtiso
+        self.s = s
+
+    def init_tt(self):
+        o = self.opac
+        lib().orc_gta_init_tt(self.om.ref, len(self.weight), _dp(self.omega), _dp(self.weight), _dp(self.geom["Volume"]),
+                              _dp(self.geom["A_fp"]), _dp(self.geom["A_ez"]), _dp(o["GreySigTotal"]), _dp(self.TT))
+        return self.TT
+
+    def grey_sweep(self, PsiB, P, withSource):
+        """GreySweepNEW: P (nc) and PsiB (nAng, nb) in/out."""
+        lib().orc_gta_grey_sweep(C.byref(self.s), _dp(PsiB), _dp(P), int(bool(withSource)))
+
+    def sweep_angle(self, a, TsaSource, PsiBa, PhiInc):
+        m = self.om.m
+        tPsi, pInc = np.zeros(m.ncornr + m.nbelem), np.zeros(m.ncornr)
+        s, o = self.sched, self.opac
+        lib().orc_gta_sweep_angle(self.om.ref, int(s["nHyperPlanes"][a]), _ip(s["zonesInPlane"][a]), _ip(s["nextZ"][a]), _ip(s["nextC"][a]),
+                                  _dp(self.omega[a]), C.c_double(self.weight[a]), _dp(self.geom["Volume"]), _dp(self.geom["A_fp"]),
+                                  _dp(self.geom["A_ez"]), _dp(o["GreySigTotal"]), _dp(o["GreySigtInv"]), _dp(TsaSource), _dp(tPsi), _dp(pInc),
+                                  _dp(PsiBa), _dp(PhiInc))
+        return tPsi, pInc
+
+    def solve(self, PhiTotal, epsPoint=1e-6, maxIters=21, epsGrey=0.1, enforceHardMax=False):
+        """GTASolver; returns (GreyCorrection, nGreyIter, maxRelErrGrey).  Consumes GreySource and TT."""
+        nc = self.om.m.ncornr
+        corr = np.zeros(nc)
+        err = C.c_double(0.0)
+        lib().orc_gta_solver.restype = C.c_int
+        n = lib().orc_gta_solver(C.byref(self.s), PhiTotal.shape[-1], _dp(PhiTotal), _dp(self.geom["VolumeZone"]), C.c_double(epsPoint),
+                                 int(maxIters), C.c_double(epsGrey), int(bool(enforceHardMax)), _dp(corr), C.byref(err))
+        return corr, n, err.value
+
+
+def add_grey_corrections(GreyCorrection, Chi, PhiTotal):
+    nc, ngr = PhiTotal.shape
+    lib().orc_add_grey_corrections(ngr, nc, _dp(GreyCorrection), _dp(Chi), _dp(PhiTotal))
+    return PhiTotal

@@ -1,0 +1,136 @@
+"""GPU parity of the grey-transport-acceleration path (3-D, "new" GTA solver) against the oracle's restatement of
+setGTAOpacityNEW, getCollisionRate, InitGreySweepUCBxyz, GTASweep + SweepGreyUCBxyz KernelNew, GreySweepNEW
+(ScalarIntensityDecompose/Solve), GTASolver (BiCGSTAB) and addGreyCorrections.  The mini-app build never runs GTA
+(LinearSolver.F90:87-121), so opacities are synthetic (seeded)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import common as T
+from umt_b200 import mesh as M
+from umt_b200 import problem as PR
+from umt_b200.teton import SweepContext
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _setup(mesh, G=4, seed=7, scat=20.0):
+    om = O.OMesh(mesh)
+    g = O.geometry(om)
+    omega, w = O.gta_quad_xyz()
+    sched = O.schedule(om, g, omega)
+    rng = np.random.default_rng(seed)
+    nz, nc = mesh.nzones, mesh.ncornr
+    tau = PR.tau(1e-3)
+    Siga = 5 * rng.random((nz, G))
+    Sigs = scat * rng.random((nz, G))
+    Eta = 0.5 * rng.random(nc)
+    Chi = rng.random((nc, G))
+    Chi /= Chi.sum(1, keepdims=True)
+    Phi = rng.random((nc, G))
+    ctx = SweepContext.from_mesh(mesh, G)
+    ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], A_bdy=g["A_bdy"])
+    ctx.build_product_quadrature(1, 1, 1)
+    ctx.upload_state(np.tile(Phi / (4 * np.pi), (8, 1, 1)), None, np.full((nz, G), tau), np.zeros((nc, G)), tau)
+    ctx.init_phi_total()          # PhiTotal on the device = sum_a w_a Psi = Phi
+    ctx.gta_setup()
+    return dict(om=om, g=g, omega=omega, w=w, sched=sched, tau=tau, Siga=Siga, Sigs=Sigs, Eta=Eta, Chi=Chi, Phi=Phi, ctx=ctx, mesh=mesh)
+
+
+MESHES = [("tiled", lambda: M.tiled_mesh((2, 2, 2))), ("unstruct", lambda: M.unstruct_box_mesh(2)), ("box", lambda: M.box_mesh((3, 4, 5)))]
+
+
+@pytest.mark.parametrize("name,mk", MESHES)
+def test_gta_pieces_match_oracle(name, mk):
+    s = _setup(mk())
+    ctx, om, g = s["ctx"], s["om"], s["g"]
+    nc, nb = s["mesh"].ncornr, s["mesh"].nbelem
+    om_d, w_d = ctx.gta_quadrature()
+    assert np.array_equal(om_d, s["omega"]) and np.array_equal(w_d, s["w"])
+    assert T.relerr(ctx.download_phi(), s["Phi"]) <= 1e-13
+    # opacities (setGTAOpacityNEW) and the rescaled Chi
+    chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()
+    op = O.gta_set_opacity(om, g, s["tau"], s["Siga"], s["Sigs"], s["Eta"], chi_ref)
+    op_d = ctx.gta_compute_opacity(s["Siga"], s["Sigs"], s["Eta"], chi_dev)
+    for k in op:
+        assert T.relerr(op_d[k], op[k]) <= TOL, k
+    assert T.relerr(chi_dev, chi_ref) <= TOL
+    # collision rate (getCollisionRate, both flags)
+    gs = O.collision_rate(om, s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    gs_d = ctx.collision_rate(s["Eta"], s["Siga"], s["Sigs"], 0)
+    assert T.relerr(gs_d, gs) <= TOL
+    # transfer matrices (InitGreySweepUCBxyz)
+    P = O.GtaProblem(om, g, s["sched"], s["omega"], s["w"], op, gs, PR.wtiso(3))
+    TT = P.init_tt().copy()
+    TT_d = ctx.gta_init_tt()
+    assert np.abs(TT_d - TT).max() <= TOL * np.abs(TT).max()
+    # one GTASweep (all 8 angles): PhiInc and the exiting boundary fluxes, with non-zero incident PsiB
+    rng = np.random.default_rng(3)
+    Pvec = rng.random(nc)
+    PsiB0 = rng.random((8, nb))
+    tsa = PR.wtiso(3) * (op["GreySigScat"] * Pvec + gs)
+    PhiInc = np.zeros(nc)
+    PsiB_ref = PsiB0.copy()
+    for a in range(8):
+        P.sweep_angle(a, tsa, PsiB_ref[a], PhiInc)
+    PhiInc_d, PsiB_d = ctx.gta_sweep(Pvec, gs, PsiB0.copy(), True)
+    assert T.mixed_err(PhiInc_d, PhiInc, TOL) <= 1.0
+    assert T.mixed_err(PsiB_d, PsiB_ref, TOL) <= 1.0
+    # GreySweepNEW with and without source (LU decomposition of I - TT sigma_s, then solves)
+    Pr, Br = np.zeros(nc), np.zeros((8, nb))
+    Pd, Bd = np.zeros(nc), np.zeros((8, nb))
+    P.grey_sweep(Br, Pr, True)
+    ctx.gta_grey_sweep(Pd, Bd, True)
+    assert T.mixed_err(Pd, Pr, 1e-11) <= 1.0 and T.mixed_err(Bd, Br, 1e-11) <= 1.0
+    P.GreySource[:] = 0
+    ctx.gta_set_source(np.zeros(nc))
+    P.grey_sweep(Br, Pr, False)
+    ctx.gta_grey_sweep(Pd, Bd, False)
+    assert T.mixed_err(Pd, Pr, 1e-11) <= 1.0 and T.mixed_err(Bd, Br, 1e-11) <= 1.0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,mk", MESHES[:2])
+def test_gta_solver_matches_oracle(name, mk):
+    s = _setup(mk())
+    ctx, om, g = s["ctx"], s["om"], s["g"]
+    nc = s["mesh"].ncornr
+    chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()
+    op = O.gta_set_opacity(om, g, s["tau"], s["Siga"], s["Sigs"], s["Eta"], chi_ref)
+    ctx.gta_compute_opacity(s["Siga"], s["Sigs"], s["Eta"], chi_dev)
+    gs = O.collision_rate(om, s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    ctx.collision_rate(s["Eta"], s["Siga"], s["Sigs"], 0)
+    P = O.GtaProblem(om, g, s["sched"], s["omega"], s["w"], op, gs, PR.wtiso(3))
+    corr, n, err = P.solve(s["Phi"])
+    corr_d, n_d, err_d = ctx.gta_solve()
+    assert n_d == n and n > 3
+    # Krylov recurrences amplify rounding differences (FMA contraction, reduction order): 1e-8 of the correction's scale
+    assert np.abs(corr_d - corr).max() <= 1e-8 * np.abs(corr).max()
+    assert abs(err_d - err) <= 1e-6 * max(err, 1e-30) + 1e-12
+    # addGreyCorrections: PhiTotal += correction * Chi
+    phi_ref = O.add_grey_corrections(corr, chi_ref, s["Phi"].copy())
+    ctx.add_grey_corrections()
+    assert np.abs(ctx.download_phi() - phi_ref).max() <= 1e-8 * np.abs(phi_ref).max()
+    ctx.close()
+
+
+def test_gta_no_scattering_exits_immediately():
+    """GreySigScat = 0 everywhere: scat_prod1 of the residual is 0, the solver returns the first sweep (GTASolver.F90:232-237)."""
+    s = _setup(M.box_mesh((3, 3, 3)), scat=0.0)
+    ctx, om, g = s["ctx"], s["om"], s["g"]
+    nc = s["mesh"].ncornr
+    s["Siga"][:] = s["Siga"][:, :1]      # grey absorber, no re-emission: greysigt == greysiga
+    s["Eta"][:] = 0.0
+    chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()
+    op = O.gta_set_opacity(om, g, s["tau"], s["Siga"], s["Sigs"], s["Eta"], chi_ref)
+    ctx.gta_compute_opacity(s["Siga"], s["Sigs"], s["Eta"], chi_dev)
+    assert (op["GreySigScat"] == 0).all()
+    gs = O.collision_rate(om, s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    ctx.collision_rate(s["Eta"], s["Siga"], s["Sigs"], 0)
+    P = O.GtaProblem(om, g, s["sched"], s["omega"], s["w"], op, gs, PR.wtiso(3))
+    corr, n, _ = P.solve(s["Phi"])
+    corr_d, n_d, _ = ctx.gta_solve()
+    assert n == 1 and n_d == 1
+    assert T.mixed_err(corr_d, corr, 1e-11) <= 1.0
+    ctx.close()

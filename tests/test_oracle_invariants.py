@@ -247,3 +247,69 @@ def test_schedule_validity_rz():
             continue
         assert p.sched["zonesInPlane"][a][:nh].sum() == nz
         assert np.array_equal(np.sort(np.abs(p.sched["nextZ"][a])), np.arange(1, nz + 1))
+
+
+def _gta_problem(mesh, G=4, seed=7):
+    om = O.OMesh(mesh)
+    g = O.geometry(om)
+    omega, w = O.gta_quad_xyz()
+    sched = O.schedule(om, g, omega)
+    rng = np.random.default_rng(seed)
+    nz, nc = mesh.nzones, mesh.ncornr
+    tau = PR.tau(1e-3)
+    Siga, Sigs, Eta = 5 * rng.random((nz, G)), 20 * rng.random((nz, G)), 0.5 * rng.random(nc)
+    Chi = rng.random((nc, G))
+    Chi /= Chi.sum(1, keepdims=True)
+    Phi = rng.random((nc, G))
+    op = O.gta_set_opacity(om, g, tau, Siga, Sigs, Eta, Chi)
+    gs = O.collision_rate(om, Eta, Siga, Sigs, Phi, np.zeros(nc), 0)
+    return om, g, sched, omega, w, op, gs, Phi, Chi
+
+
+def test_gta_quadrature_and_opacity():
+    """S2 level-symmetric GTA set: 8 ordinates (+-1/sqrt 3), weights pi/2; setGTAOpacityNEW leaves Chi normalised
+    with sum_g Chi = 1 / sum(Chi/sigt) scaling and 0 <= GreySigScat < GreySigTotal."""
+    omega, w = O.gta_quad_xyz()
+    assert np.abs(np.abs(omega) - 0.577350269189625).max() == 0 and np.abs(w - math.pi / 2).max() <= 1e-15
+    om, g, sched, omega, w, op, gs, Phi, Chi = _gta_problem(M.tiled_mesh((2, 2, 1)))
+    assert (op["GreySigScat"] >= 0).all() and (op["GreySigScat"] < op["GreySigTotal"]).all()
+    assert np.abs(op["GreySigtInv"] * op["GreySigTotal"] - 1).max() <= 1e-15
+    assert np.abs(Chi.sum(1) - 1).max() <= 1e-14
+
+
+@pytest.mark.parametrize("mk", [lambda: M.tiled_mesh((2, 2, 2)), lambda: M.unstruct_box_mesh(2)])
+def test_gta_solver_solves_the_grey_system(mk):
+    """GTASolver's BiCGSTAB answer x satisfies x - M x = b, where b is the first (withSource) grey sweep and M the
+    source-free sweep operator (GTASolver.F90:219-402), checked by applying the operator once more."""
+    mesh = mk()
+    om, g, sched, omega, w, op, gs, Phi, _ = _gta_problem(mesh)
+    nc, nb = mesh.ncornr, mesh.nbelem
+    P = O.GtaProblem(om, g, sched, omega, w, op, gs, PR.wtiso(3))
+    corr, n, err = P.solve(Phi, epsPoint=1e-10, maxIters=200)
+    assert 3 < n < 100 and err < 1e-10
+    Q = O.GtaProblem(om, g, sched, omega, w, op, gs, PR.wtiso(3))
+    Q.init_tt()
+    b, bB = np.zeros(nc), np.zeros((8, nb))
+    Q.grey_sweep(bB, b, True)
+    Q.GreySource[:] = 0
+    Mx, MB = corr.copy(), np.zeros((8, nb))
+    Q.grey_sweep(MB, Mx, False)
+    assert np.abs(b - (corr - Mx)).max() <= 1e-8 * np.abs(b).max()
+
+
+def test_gta_transfer_matrix_is_the_sweep_response():
+    """InitGreySweepUCBxyz: sum_a w_a Pvv is the within-zone response, so for a zone-local unit source and no incident
+    flux the angle-integrated corner fluxes of one GTASweep equal TT applied to wtiso * source."""
+    mesh = M.box_mesh((1, 1, 1))
+    om, g, sched, omega, w, op, gs, Phi, _ = _gta_problem(mesh)
+    P = O.GtaProblem(om, g, sched, omega, w, op, gs, PR.wtiso(3))
+    TT = P.init_tt().copy()                      # TT[c1, c] = TT(c+1, c1+1)
+    nc = mesh.ncornr
+    for k in range(nc):
+        tsa = np.zeros(nc)
+        tsa[k] = 1.0
+        phi = np.zeros(nc)
+        for a in range(8):
+            tPsi, _ = P.sweep_angle(a, tsa, np.zeros(mesh.nbelem), np.zeros(nc))
+            phi += w[a] * tPsi[:nc]
+        assert np.abs(phi - TT[:, k]).max() <= 1e-13 * np.abs(TT).max()

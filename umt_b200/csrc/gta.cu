@@ -1,0 +1,884 @@
+// Grey transport acceleration (GTA) on the device: 3-D, the "new" GTA solver (the variant the
+// reference's own GPU path implements, gpu/SweepGreyUCBxyz_OMPOL.F90 / rt/GTASolver_OMPOL.F90).
+//
+//   rt/setGTAOpacity.F90:10-113 (setGTAOpacityNEW)             -> gta_opacity_kernel
+//   rt/getCollisionRate.F90:10-97                              -> collision_rate_kernel
+//   snac/GTASweep.F90:9-168 (GTA%ID == 1)                      -> gta_device_sweep (TsaSource, angle loop)
+//   snac/SweepGreyUCBxyz.F90:12-355 (KernelNew)                -> gta_sweep_kernel
+//   snac/InitSweepGreyUCBxyz.F90:10-253                        -> gta_init_tt_kernel
+//   snac/UpdateScalarIntensity.F90:11-170                      -> gta_scalar_kernel
+//   rt/GreySweep.F90:12-48 (GreySweepNEW)                      -> gta_grey_sweep
+//   rt/scat_prod.F90, scat_prod1.F90, rt/GTASolver.F90:42-425  -> umt_gta_solve (BiCGSTAB, host loop, device vectors)
+//   rt/addGreyCorrections.F90:70-91                            -> add_corrections_kernel
+//
+// The grey sweep has one group, so the parallel axes are zones-in-plane x the 8 S2 ordinates: one thread
+// owns one (zone, angle) and solves its corners; the same ticket / per-(angle, plane) counter scheme as the
+// multigroup sweep runs all 8 angles in one persistent launch.  The incident-only part pInc is kept per
+// angle and summed in fixed angle order (deterministic PhiInc, no float atomics).  All vectors of the
+// Krylov iteration stay on the device; only the scalars of the inner products come back to the host.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "umt_internal.h"
+
+namespace {
+
+constexpr int MAXC = 8, MAXCF = 3;
+constexpr double FOURALPHA = 1.82;
+constexpr double PI = 3.14159265358979323846;
+
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double dot3(const double *om, const double *A) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])), __dmul_rn(om[2], A[2]));
+}
+
+struct GtaSweepParams {
+  int nc, nb, nz, nItems;
+  const int *numCorner, *cOffSet, *nCFaces, *cFP, *cEZ;
+  const double *Volume, *Afp, *Aez, *omega;
+  const int *nextZ;
+  const unsigned char *nextC;
+  const WorkItem *items;
+  int *counters;
+  const double *sigTotal, *sigtInv, *tsa;
+  double *tpsi, *pinc;
+};
+
+// SweepGreyUCBxyzKernelNew for one (zone, angle)
+__device__ void gta_solve_zone(const GtaSweepParams &P, int a, int zone0) {
+  const int nc = P.nc;
+  const double om[3] = {P.omega[3 * a], P.omega[3 * a + 1], P.omega[3 * a + 2]};
+  double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
+  double *pincA = P.pinc + (size_t)a * nc;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
+  double Q[MAXC], src[MAXC], denom[MAXC], pinc[MAXC];
+  int nxez[MAXC], ez_exit[MAXC][MAXCF];
+  double coefpsi[MAXC][MAXCF];
+  for (int c = 0; c < nCorner; c++) {
+    const double t = P.tsa[c0 + c];
+    Q[c] = P.sigtInv[c0 + c] * t;
+    src[c] = P.Volume[c0 + c] * t;
+    pinc[c] = 0.0;
+    nxez[c] = 0;
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    const double sigv = P.Volume[cc] * P.sigTotal[cc];
+    double dn = sigv;
+    const int nCF = P.nCFaces[cc];
+    double afp[MAXCF], psifp[MAXCF];
+    for (int f = 0; f < nCF; f++) {
+      afp[f] = dot3(om, P.Afp + ((size_t)cc * MAXCF + f) * 3);
+      psifp[f] = 0.0;
+      if (afp[f] > 0.0) dn += afp[f];
+      else if (afp[f] < 0.0) {
+        psifp[f] = __ldcg(&tpsi[P.cFP[cc * MAXCF + f]]);
+        src[c] -= afp[f] * psifp[f];
+        pinc[c] -= afp[f] * psifp[f];
+      }
+    }
+    for (int f = 0; f < nCF; f++) {
+      const double aez = dot3(om, P.Aez + ((size_t)cc * MAXCF + f) * 3);
+      const int cez = P.cEZ[cc * MAXCF + f];
+      if (cez > c) {
+        if (aez > 0.0) { ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = aez; nxez[c]++; }
+        else if (aez < 0.0) { ez_exit[cez][nxez[cez]] = c; coefpsi[cez][nxez[cez]] = -aez; nxez[cez]++; }
+      }
+      if (aez > 0.0) {
+        double psi_opp = 0.0, area_opp = 0.0;
+        dn += aez;
+        int ifp = (f + 1) % nCF;
+        if (afp[ifp] < 0.0) { area_opp = -afp[ifp]; psi_opp = -afp[ifp] * psifp[ifp]; }
+        for (int k = 2; k <= nCF - 2; k++) {
+          ifp = (ifp + 1) % nCF;
+          if (afp[ifp] < 0.0) { area_opp -= afp[ifp]; psi_opp -= afp[ifp] * psifp[ifp]; }
+        }
+        double sez;
+        if (area_opp > 0.0) {
+          psi_opp = psi_opp / area_opp;
+          const double sigv2 = sigv * sigv;
+          const double gnum = aez * aez * (FOURALPHA * sigv2 + aez * (4.0 * sigv + 3.0 * aez));
+          const double gtau = gnum / (gnum + 4.0 * sigv2 * sigv2 + aez * sigv * (6.0 * sigv2 + 2.0 * aez * (2.0 * sigv + aez)));
+          sez = gtau * sigv * (psi_opp - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - Q[cez]);
+          pinc[c] += gtau * sigv * psi_opp;
+          pinc[cez] -= gtau * sigv * psi_opp;
+        } else {
+          sez = 0.5 * aez * (Q[c] - Q[cez]);
+        }
+        src[c] += sez;
+        src[cez] -= sez;
+      }
+    }
+    denom[c] = dn;
+  }
+  for (int i = 0; i < nCorner; i++) {
+    const int c = nextC[c0 + i];
+    const double p = src[c] / denom[c];
+    const double q = pinc[c] / denom[c];
+    src[c] = p;
+    pinc[c] = q;
+    for (int k = 0; k < nxez[c]; k++) {
+      src[ez_exit[c][k]] += coefpsi[c][k] * p;
+      pinc[ez_exit[c][k]] += coefpsi[c][k] * q;
+    }
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    tpsi[cc] = src[c];
+    pincA[cc] = pinc[c];
+    const int nCF = P.nCFaces[cc];
+    for (int f = 0; f < nCF; f++) {
+      const int row = P.cFP[cc * MAXCF + f];
+      if (row >= nc && dot3(om, P.Afp + ((size_t)cc * MAXCF + f) * 3) > 0.0) tpsi[row] = src[c];   // PsiB(b, Angle) <- tPsi
+    }
+  }
+}
+
+__global__ void __launch_bounds__(64) gta_sweep_kernel(GtaSweepParams P) {
+  __shared__ int s_item;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= P.nItems) break;
+    const WorkItem w = P.items[it];
+    if (threadIdx.x == 0 && w.wait_idx >= 0)
+      while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(32);
+    __syncthreads();
+    const int *nextZ = P.nextZ + (size_t)w.angle * P.nz;
+    for (int zi = w.zbeg + threadIdx.x; zi < w.zend; zi += blockDim.x) gta_solve_zone(P, w.angle, nextZ[zi]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+    }
+  }
+}
+
+// TsaSource = wtiso (GreySigScat P + GreySource)   (GTASweep.F90:84-89)
+__global__ void gta_tsa_kernel(const double *P, const double *sigScat, const double *greySource, double wtiso, double *tsa, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) tsa[c] = wtiso * (sigScat[c] * P[c] + greySource[c]);
+}
+
+// PhiInc = sum_a w_a pInc_a in angle order (SweepGreyUCBxyz.F90:126-128)
+__global__ void gta_phiinc_kernel(const double *pinc, const double *w, int nAng, int nc, double *phiInc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double s = 0.0;
+  for (int a = 0; a < nAng; a++) s = s + w[a] * pinc[(size_t)a * nc + c];
+  phiInc[c] = s;
+}
+
+struct ZoneParams {
+  int nz, nc, mC, nAng;
+  const int *numCorner, *cOffSet, *nCFaces, *cEZ;
+  const double *Volume, *Afp, *Aez, *omega, *weight, *sigTotal, *sigScat, *greySource, *phiInc;
+  double *TT, *P;
+  double wtiso;
+};
+
+// InitGreySweepUCBxyz: TT(:, corners of zone) = sum over the GTA angles of w Pvv
+__global__ void __launch_bounds__(64) gta_init_tt_kernel(ZoneParams Z) {
+  const int zone = blockIdx.x * blockDim.x + threadIdx.x;
+  if (zone >= Z.nz) return;
+  const int nCorner = Z.numCorner[zone], c0 = Z.cOffSet[zone], mC = Z.mC;
+  double T[MAXC][MAXC];   // T[c][c1] accumulates TT(c, c0+c1)
+  for (int i = 0; i < MAXC; i++) for (int j = 0; j < MAXC; j++) T[i][j] = 0.0;
+  for (int a = 0; a < Z.nAng; a++) {
+    const double om[3] = {Z.omega[3 * a], Z.omega[3 * a + 1], Z.omega[3 * a + 2]};
+    const double quadwt = Z.weight[a];
+    int nxez[MAXC], need[MAXC], ez_exit[MAXC][MAXCF];
+    double denom[MAXC], coefpsi[MAXC][MAXCF], Sigt[MAXC], Pvv[MAXC][MAXC];   // Pvv[row][col]
+    for (int i = 0; i < MAXC; i++) { nxez[i] = 0; need[i] = 0; for (int j = 0; j < MAXC; j++) Pvv[i][j] = 0.0; }
+    for (int c = 0; c < nCorner; c++) { Pvv[c][c] = Z.Volume[c0 + c]; Sigt[c] = Z.sigTotal[c0 + c]; }
+    for (int c = 0; c < nCorner; c++) {
+      const int cc = c0 + c;
+      const double sigv = Z.Volume[cc] * Sigt[c];
+      double dn = sigv;
+      const int nCF = Z.nCFaces[cc];
+      double afp[MAXCF];
+      for (int f = 0; f < nCF; f++) {
+        afp[f] = dot3(om, Z.Afp + ((size_t)cc * MAXCF + f) * 3);
+        if (afp[f] > 0.0) dn += afp[f];
+      }
+      for (int f = 0; f < nCF; f++) {
+        const double aez = dot3(om, Z.Aez + ((size_t)cc * MAXCF + f) * 3);
+        const int cez = Z.cEZ[cc * MAXCF + f];
+        if (cez > c) {
+          if (aez > 0.0) { need[cez]++; ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = aez; nxez[c]++; }
+          else if (aez < 0.0) { need[c]++; ez_exit[cez][nxez[cez]] = c; coefpsi[cez][nxez[cez]] = -aez; nxez[cez]++; }
+        }
+        if (aez > 0.0) {
+          dn += aez;
+          double area_opp = 0.0;
+          if (nCF == 3) {
+            const int ifp = (f + 1) % 3;
+            if (afp[ifp] < 0.0) area_opp = -afp[ifp];
+          } else {
+            int ifp = f;
+            for (int k = 1; k <= nCF - 2; k++) { ifp = (ifp + 1) % nCF; if (afp[ifp] < 0.0) area_opp -= afp[ifp]; }
+          }
+          double B1, B2;
+          if (area_opp > 0.0) {
+            const double sigv2 = sigv * sigv;
+            const double gnum = aez * aez * (FOURALPHA * sigv2 + aez * (4.0 * sigv + 3.0 * aez));
+            const double gtau = gnum / (gnum + 4.0 * sigv2 * sigv2 + aez * sigv * (6.0 * sigv2 + 2.0 * aez * (2.0 * sigv + aez)));
+            const double B0 = 0.5 * aez * (1.0 - gtau);
+            B1 = (B0 - gtau * sigv) / Sigt[c];
+            B2 = B0 / Sigt[cez];
+          } else {
+            B1 = 0.5 * aez / Sigt[c];
+            B2 = 0.5 * aez / Sigt[cez];
+          }
+          Pvv[c][c] += B1; Pvv[cez][c] -= B2; Pvv[c][cez] -= B1; Pvv[cez][cez] += B2;
+        }
+      }
+      denom[c] = dn;
+    }
+    for (int i = 0; i < nCorner; i++) {
+      int c = 0;   // minloc: first minimum
+      for (int k = 1; k < nCorner; k++) if (need[k] < need[c]) c = k;
+      const double dInv = 1.0 / denom[c];
+      for (int c1 = 0; c1 < nCorner; c1++) Pvv[c1][c] = dInv * Pvv[c1][c];
+      for (int k = 0; k < nxez[c]; k++) {
+        const int cez = ez_exit[c][k];
+        const double coef = coefpsi[c][k];
+        need[cez]--;
+        for (int c1 = 0; c1 < nCorner; c1++) Pvv[c1][cez] += coef * Pvv[c1][c];
+      }
+      need[c] = 99;
+    }
+    for (int c1 = 0; c1 < nCorner; c1++)
+      for (int c = 0; c < nCorner; c++) T[c][c1] = T[c][c1] + quadwt * Pvv[c][c1];
+  }
+  for (int c1 = 0; c1 < nCorner; c1++)
+    for (int c = 0; c < mC; c++) Z.TT[(size_t)(c0 + c1) * mC + c] = c < nCorner ? T[c][c1] : 0.0;
+}
+
+// ScalarIntensityDecompose + ScalarIntensitySolve for one zone
+__global__ void __launch_bounds__(64) gta_scalar_kernel(ZoneParams Z, int withSource) {
+  const int zone = blockIdx.x * blockDim.x + threadIdx.x;
+  if (zone >= Z.nz) return;
+  const int n = Z.numCorner[zone], c0 = Z.cOffSet[zone], mC = Z.mC;
+  double Phi[MAXC];
+  double *TT = Z.TT;
+#define TTF(i, j) TT[(size_t)(c0 + (j)) * mC + (i)]   /* TT(i+1, c0+j+1) */
+  if (withSource) {
+    for (int c = 0; c < n; c++) {
+      double ph = Z.phiInc[c0 + c];
+      for (int cc = 0; cc < n; cc++) {
+        ph = ph + TTF(cc, c) * Z.wtiso * Z.greySource[c0 + cc];
+        TTF(cc, c) = -Z.wtiso * Z.sigScat[c0 + cc] * TTF(cc, c);
+      }
+      Phi[c] = ph;
+      TTF(c, c) = 1.0 + TTF(c, c);
+    }
+    for (int i = 0; i < n; i++) {
+      double t = 0.0;
+      for (int k = 0; k < i; k++) t = t + TTF(k, i) * TTF(i, k);
+      TTF(i, i) = TTF(i, i) - t;
+      const double diagInv = 1.0 / TTF(i, i);
+      for (int j = i + 1; j < n; j++) {
+        t = 0.0;
+        double v = 0.0;
+        for (int k = 0; k < i; k++) { t = t + TTF(k, i) * TTF(j, k); v = v + TTF(k, j) * TTF(i, k); }
+        TTF(j, i) = TTF(j, i) - t;
+        TTF(i, j) = diagInv * (TTF(i, j) - v);
+      }
+    }
+  } else {
+    for (int c = 0; c < n; c++) Phi[c] = Z.phiInc[c0 + c];
+  }
+  for (int j = 1; j < n; j++) {
+    double t = 0.0;
+    for (int i = 0; i < j; i++) t = t - TTF(i, j) * Phi[i];
+    Phi[j] = Phi[j] + t;
+  }
+  Phi[n - 1] = Phi[n - 1] / TTF(n - 1, n - 1);
+  for (int k = n - 2; k >= 0; k--) {
+    double t = 0.0;
+    for (int i = k + 1; i < n; i++) t = t + Phi[i] * TTF(i, k);
+    Phi[k] = (Phi[k] - t) / TTF(k, k);
+  }
+  for (int c = 0; c < n; c++) Z.P[c0 + c] = Phi[c];
+#undef TTF
+}
+
+// setGTAOpacityNEW per corner; Chi (nc, G) rescaled in place
+__global__ void gta_opacity_kernel(int nc, int G, double tau, const int *c2z, const double *siga, const double *sigs, const double *eta,
+                                   const double *Volume, double *chi, double *sigTotal, double *sigScat, double *sigScatVol, double *sigtInv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int zone = c2z[c];
+  double SigtInvAve = 0.0, Sigt2InvAve = 0.0, SigaAve = 0.0;
+  for (int g = 0; g < G; g++) {
+    const double a = siga[(size_t)zone * G + g], s = sigs[(size_t)zone * G + g];
+    const double SigtInv = 1.0 / (a + s + tau);
+    const double x = chi[(size_t)c * G + g];
+    SigtInvAve = SigtInvAve + x * SigtInv;
+    Sigt2InvAve = Sigt2InvAve + x * SigtInv * SigtInv;
+    SigaAve = SigaAve + x * a * SigtInv;
+    chi[(size_t)c * G + g] = x * SigtInv;
+  }
+  double greysigt, greysiga, greysigs;
+  if (SigtInvAve > 0.0) {
+    for (int g = 0; g < G; g++) chi[(size_t)c * G + g] = chi[(size_t)c * G + g] / SigtInvAve;
+    greysigt = SigtInvAve / Sigt2InvAve;
+    greysiga = tau + (1.0 - eta[c]) * SigaAve / SigtInvAve;
+    greysigs = greysigt - greysiga;
+  } else {
+    greysigt = tau; greysiga = tau; greysigs = 0.0;
+  }
+  const double scatRatio = greysigs / greysigt;
+  if (scatRatio <= 1.0e-10) { sigScat[c] = 0.0; sigTotal[c] = greysiga; }
+  else { sigScat[c] = greysigs; sigTotal[c] = greysigt; }
+  sigScatVol[c] = sigScat[c] * Volume[c];
+  sigtInv[c] = 1.0 / sigTotal[c];
+}
+
+// getCollisionRate
+__global__ void collision_rate_kernel(int nc, int G, const int *c2z, const double *eta, const double *siga, const double *sigs,
+                                      const double *phi, double *greySource, int residualFlag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int zone = c2z[c];
+  double s = 0.0;
+  for (int g = 0; g < G; g++) s = s + (eta[c] * siga[(size_t)zone * G + g] + sigs[(size_t)zone * G + g]) * phi[(size_t)c * G + g];
+  greySource[c] = residualFlag == 0 ? s : s - greySource[c];
+}
+
+// PhiTotal(g,c) += GreyCorrection(c) Chi(g,c)
+__global__ void add_corrections_kernel(size_t n, int G, const double *corr, const double *chi, double *phi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) phi[i] = phi[i] + corr[i / G] * chi[i];
+}
+
+// radEnergy(zone) = sum_c V_c sum_g PhiTotal(g,c) / VolumeZone   (GTASolver.F90:128-142)
+__global__ void rad_energy_kernel(int nz, int G, const int *numCorner, const int *cOffSet, const double *Volume, const double *phi,
+                                  double *volZone, double *radEnergy) {
+  const int zone = blockIdx.x * blockDim.x + threadIdx.x;
+  if (zone >= nz) return;
+  double e = 0.0, vz = 0.0;
+  for (int c = cOffSet[zone]; c < cOffSet[zone] + numCorner[zone]; c++) {
+    double sumRad = 0.0;
+    for (int g = 0; g < G; g++) sumRad = sumRad + phi[(size_t)c * G + g];
+    e = e + Volume[c] * sumRad;
+    vz = vz + Volume[c];
+  }
+  volZone[zone] = vz;
+  radEnergy[zone] = e / vz;
+}
+
+// deterministic reductions: per-block partials in block order, then one thread adds them up in order
+__global__ void __launch_bounds__(256) dot_partial_kernel(const double *x, const double *y, const double *w, int n, double *partial) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (y ? x[i] * y[i] : x[i]) * w[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void sum_partials_kernel(const double *partial, int n, double *out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; i++) s += partial[i]; *out = s; }
+}
+
+// zone corrections and the error norms of GTASolver.F90:331-375; partial[0..nb)=errL2, [nb..2nb)=phiL2, [2nb..3nb)=max rel err
+__global__ void __launch_bounds__(256) zone_error_kernel(int nz, const int *numCorner, const int *cOffSet, const double *Volume,
+                                                         const double *volZone, const double *corr, const double *radEnergy,
+                                                         double *pzOld, double *partial) {
+  __shared__ double r0[256], r1[256], r2[256];
+  double e = 0.0, p = 0.0, m = 0.0;
+  for (int zone = blockIdx.x * blockDim.x + threadIdx.x; zone < nz; zone += gridDim.x * blockDim.x) {
+    double pz = 0.0;
+    for (int c = cOffSet[zone]; c < cOffSet[zone] + numCorner[zone]; c++) pz = pz + Volume[c] * corr[c];
+    pz = pz / volZone[zone];
+    const double errZone = pz - pzOld[zone];
+    e += volZone[zone] * (errZone * errZone);
+    const double phiNew = radEnergy[zone] + pz;
+    p += volZone[zone] * (phiNew * phiNew);
+    if (phiNew != 0.0) m = fmax(m, fabs(errZone / phiNew));
+    if (phiNew != phiNew || errZone != errZone) m = CUDART_INF;   // NaN: the reference aborts here
+    pzOld[zone] = pz;
+  }
+  r0[threadIdx.x] = e; r1[threadIdx.x] = p; r2[threadIdx.x] = m;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) { r0[threadIdx.x] += r0[threadIdx.x + k]; r1[threadIdx.x] += r1[threadIdx.x + k]; r2[threadIdx.x] = fmax(r2[threadIdx.x], r2[threadIdx.x + k]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partial[blockIdx.x] = r0[0]; partial[gridDim.x + blockIdx.x] = r1[0]; partial[2 * gridDim.x + blockIdx.x] = r2[0]; }
+}
+__global__ void zone_error_finish_kernel(const double *partial, int nb, double *out3) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double e = 0.0, p = 0.0, m = 0.0;
+    for (int i = 0; i < nb; i++) { e += partial[i]; p += partial[nb + i]; m = fmax(m, partial[2 * nb + i]); }
+    out3[0] = e; out3[1] = p; out3[2] = m;
+  }
+}
+
+// Krylov vector updates (GTASolver.F90:259-322); evaluation order as written there
+__global__ void k_sub(double *out, const double *a, const double *b, size_t n) {             // out = a - b
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] - b[i];
+}
+__global__ void k_axmy(double *y, double alpha, const double *x, size_t n) {                  // y = y - alpha x
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = y[i] - alpha * x[i];
+}
+__global__ void k_corr(double *corr, double alpha, const double *D, double omega, const double *R, size_t n, int withR) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) corr[i] = withR ? corr[i] + alpha * D[i] + omega * R[i] : corr[i] + alpha * D[i];
+}
+__global__ void k_dir(double *D, const double *R, double beta, double omega, const double *A, size_t n) {   // D = R + beta (D - omega A)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) D[i] = R[i] + beta * (D[i] - omega * A[i]);
+}
+
+inline unsigned nblk(size_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+template <class T>
+int dalloc(umt_ctx *ctx, T **p, size_t n, bool zero = true) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  UMT_CUDA(ctx, cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
+  if (zero) UMT_CUDA(ctx, cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(n, 1)));
+  return UMT_OK;
+}
+
+constexpr int RED_BLOCKS = 296;   // 2 per SM
+
+int need_gta(umt_ctx *ctx) {
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  if (!ctx->gta.have_opacity) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA opacities not set (umt_gta_set_opacity / umt_gta_compute_opacity)");
+  return UMT_OK;
+}
+
+void zone_params(umt_ctx *ctx, ZoneParams &Z, double *P) {
+  GtaState &g = ctx->gta;
+  Z.nz = ctx->nz; Z.nc = ctx->nc; Z.mC = ctx->maxCorner; Z.nAng = g.nAng;
+  Z.numCorner = ctx->d_numCorner; Z.cOffSet = ctx->d_cOffSet; Z.nCFaces = ctx->d_nCFaces; Z.cEZ = ctx->d_cEZ;
+  Z.Volume = ctx->d_Volume; Z.Afp = ctx->d_Afp; Z.Aez = ctx->d_Aez; Z.omega = g.d_omega; Z.weight = g.d_weight;
+  Z.sigTotal = g.d_sigTotal; Z.sigScat = g.d_sigScat; Z.greySource = g.d_greySource; Z.phiInc = g.d_phiInc;
+  Z.TT = g.d_TT; Z.P = P;
+  Z.wtiso = 1.0 / (4.0 * PI);
+}
+
+// GTASweep (GTA%ID = 1): d_P (nc) in; d_PsiB (nAng, nb) in/out; leaves PhiInc in g.d_phiInc
+int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nb = ctx->nb, rows = nc + nb;
+  gta_tsa_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(d_P, g.d_sigScat, g.d_greySource, 1.0 / (4.0 * PI), g.d_tsaSource, nc);
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_tpsi, 0, sizeof(double) * (size_t)rows * g.nAng, ctx->stream));
+  if (nb > 0)
+    UMT_CUDA(ctx, cudaMemcpy2DAsync(g.d_tpsi + nc, sizeof(double) * rows, d_PsiB, sizeof(double) * nb, sizeof(double) * nb, g.nAng,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_counters, 0, sizeof(int) * (1 + g.nCounters), ctx->stream));
+  GtaSweepParams P;
+  P.nc = nc; P.nb = nb; P.nz = ctx->nz; P.nItems = g.nItems;
+  P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces; P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
+  P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = g.d_omega;
+  P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
+  P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc;
+  int occ = 0;
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gta_sweep_kernel, 64, 0));
+  const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), g.nItems));
+  gta_sweep_kernel<<<grid, 64, 0, ctx->stream>>>(P);
+  UMT_CUDA(ctx, cudaGetLastError());
+  gta_phiinc_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(g.d_pinc, g.d_weight, g.nAng, nc, g.d_phiInc);
+  if (nb > 0)
+    UMT_CUDA(ctx, cudaMemcpy2DAsync(d_PsiB, sizeof(double) * nb, g.d_tpsi + nc, sizeof(double) * rows, sizeof(double) * nb, g.nAng,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+  return UMT_OK;
+}
+
+// GreySweepNEW: sweep, then the per-zone solves; d_P in/out
+int gta_grey_sweep(umt_ctx *ctx, double *d_P, double *d_PsiB, int withSource) {
+  TRY(gta_device_sweep(ctx, d_P, d_PsiB));
+  ZoneParams Z;
+  zone_params(ctx, Z, d_P);
+  if (withSource) {
+    if (ctx->gta.tt_decomposed) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA transfer matrices already decomposed: call umt_gta_init_tt before another withSource sweep");
+    ctx->gta.tt_decomposed = true;
+  }
+  gta_scalar_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z, withSource);
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}
+
+int device_dot(umt_ctx *ctx, const double *x, const double *y, double *result) {
+  GtaState &g = ctx->gta;
+  dot_partial_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(x, y, g.d_sigScatVol, ctx->nc, g.d_red);
+  sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
+  UMT_CUDA(ctx, cudaMemcpyAsync(result, g.d_red + 3 * RED_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+}  // namespace
+
+void umt_gta_release(umt_ctx *ctx) {
+  GtaState &g = ctx->gta;
+  void *p[] = {g.d_omega, g.d_weight, g.d_nextZ, g.d_nextC, g.d_items, g.d_counters, g.d_sigTotal, g.d_sigtInv, g.d_sigScat, g.d_sigScatVol,
+               g.d_greySource, g.d_tsaSource, g.d_phiInc, g.d_correction, g.d_chi, g.d_TT, g.d_tpsi, g.d_pinc, g.d_vec[0], g.d_vec[1], g.d_vec[2],
+               g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB};
+  for (void *q : p) if (q) cudaFree(q);
+  g = GtaState();
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+// GTA angle set (level-symmetric S2, rt/quadxyz.F90 + rtquad.F90:95-105), its sweep order, work items, device arrays
+extern "C" int umt_gta_setup(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: the GTA kernels are 3-D only so far");
+  if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: host-only context");
+  if (!ctx->have_conn || !ctx->have_geom || ctx->h_zoneOpp.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: needs full connectivity and geometry");
+  if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  g.nAng = 8;
+  const double mu = 0.577350269189625;   // QuadratureData_mod.F90:711-713
+  const int sx[8] = {1, -1, -1, 1, 1, -1, -1, 1}, sy[8] = {1, 1, -1, -1, 1, 1, -1, -1}, sz[8] = {1, 1, 1, 1, -1, -1, -1, -1};
+  g.omega.resize(24); g.weight.resize(8);
+  double sum = 0.0;
+  for (int a = 0; a < 8; a++) {
+    g.omega[3 * a] = sx[a] * mu; g.omega[3 * a + 1] = sy[a] * mu; g.omega[3 * a + 2] = sz[a] * mu;
+    g.weight[a] = 0.5 * PI * 1.0;
+    sum += g.weight[a];
+  }
+  const double fac = 1.0 / ((1.0 / (4.0 * PI)) * sum);
+  for (double &w : g.weight) w = fac * w;
+  TRY(umt_host_build_order(ctx, g.omega.data(), g.nAng, g.nHyp, g.zonesInPlane, g.nextZ, g.nextC));
+  const int nz = ctx->nz, nc = ctx->nc, nb = ctx->nb;
+  g.maxHyp = *std::max_element(g.nHyp.begin(), g.nHyp.end());
+  std::vector<int> h_nextZ((size_t)g.nAng * nz);
+  std::vector<unsigned char> h_nextC((size_t)g.nAng * nc);
+  std::vector<WorkItem> items;
+  const int zpi = 64;
+  std::vector<std::vector<int>> start(g.nAng), nIt(g.nAng);
+  for (int a = 0; a < g.nAng; a++) {
+    std::copy(g.nextZ[a].begin(), g.nextZ[a].end(), h_nextZ.begin() + (size_t)a * nz);
+    for (int i = 0; i < nc; i++) h_nextC[(size_t)a * nc + i] = (unsigned char)(g.nextC[a][i] - 1);
+    start[a].assign(g.nHyp[a] + 1, 0); nIt[a].assign(g.nHyp[a], 0);
+    for (int p = 0; p < g.nHyp[a]; p++) { start[a][p + 1] = start[a][p] + g.zonesInPlane[a][p]; nIt[a][p] = (g.zonesInPlane[a][p] + zpi - 1) / zpi; }
+  }
+  for (int p = 0; p < g.maxHyp; p++)
+    for (int a = 0; a < g.nAng; a++) {
+      if (p >= g.nHyp[a]) continue;
+      for (int k = 0; k < nIt[a][p]; k++) {
+        WorkItem w;
+        w.angle = a; w.zbeg = start[a][p] + k * zpi; w.zend = std::min(start[a][p + 1], w.zbeg + zpi);
+        w.wait_idx = p > 0 ? a * g.maxHyp + p - 1 : -1; w.wait_count = p > 0 ? nIt[a][p - 1] : 0;
+        w.signal_idx = a * g.maxHyp + p; w.pad0 = -1; w.pad1 = 0;
+        items.push_back(w);
+      }
+    }
+  g.nItems = (int)items.size(); g.nCounters = g.nAng * g.maxHyp;
+  TRY(dalloc(ctx, &g.d_omega, 24)); TRY(dalloc(ctx, &g.d_weight, 8));
+  TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));
+  TRY(dalloc(ctx, &g.d_items, items.size())); TRY(dalloc(ctx, &g.d_counters, 1 + (size_t)g.nCounters));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_omega, g.omega.data(), sizeof(double) * 24, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_weight, g.weight.data(), sizeof(double) * 8, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_nextZ, h_nextZ.data(), sizeof(int) * h_nextZ.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_nextC, h_nextC.data(), h_nextC.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice));
+  double **percorner[] = {&g.d_sigTotal, &g.d_sigtInv, &g.d_sigScat, &g.d_sigScatVol, &g.d_greySource, &g.d_tsaSource, &g.d_phiInc, &g.d_correction,
+                          &g.d_vec[0], &g.d_vec[1], &g.d_vec[2], &g.d_vec[3], &g.d_P};
+  for (double **p : percorner) TRY(dalloc(ctx, p, nc));
+  double **perbdy[] = {&g.d_vecB[0], &g.d_vecB[1], &g.d_vecB[2], &g.d_vecB[3], &g.d_PB};
+  for (double **p : perbdy) TRY(dalloc(ctx, p, (size_t)g.nAng * nb));
+  TRY(dalloc(ctx, &g.d_chi, (size_t)nc * ctx->G));
+  TRY(dalloc(ctx, &g.d_TT, (size_t)nc * ctx->maxCorner));
+  TRY(dalloc(ctx, &g.d_tpsi, (size_t)g.nAng * (nc + nb)));
+  TRY(dalloc(ctx, &g.d_pinc, (size_t)g.nAng * nc));
+  TRY(dalloc(ctx, &g.d_radEnergy, nz)); TRY(dalloc(ctx, &g.d_pzOld, nz)); TRY(dalloc(ctx, &g.d_volZone, nz));
+  TRY(dalloc(ctx, &g.d_red, 3 * RED_BLOCKS + 8));
+  g.ready = true; g.have_opacity = false; g.tt_decomposed = false;
+  return UMT_OK;
+}
+
+extern "C" int umt_gta_get_quadrature(umt_ctx *ctx, double *omega, double *weight) {
+  if (!ctx || !ctx->gta.ready) return UMT_ERR_STATE;
+  if (omega) std::copy(ctx->gta.omega.begin(), ctx->gta.omega.end(), omega);
+  if (weight) std::copy(ctx->gta.weight.begin(), ctx->gta.weight.end(), weight);
+  return UMT_OK;
+}
+
+// GTA%GreySigTotal, GreySigScat, GreySigScatVol handed over by the caller (GreySigtInv = 1 / GreySigTotal)
+extern "C" int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, const double *GreySigScat, const double *GreySigScatVol) {
+  if (!ctx || !GreySigTotal || !GreySigScat || !GreySigScatVol) return UMT_ERR_ARG;
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc;
+  std::vector<double> inv(nc);
+  for (int c = 0; c < nc; c++) inv[c] = 1.0 / GreySigTotal[c];
+  UMT_CUDA(ctx, cudaMemcpy(g.d_sigTotal, GreySigTotal, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_sigScat, GreySigScat, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_sigScatVol, GreySigScatVol, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_sigtInv, inv.data(), sizeof(double) * nc, cudaMemcpyHostToDevice));
+  g.have_opacity = true;
+  return UMT_OK;
+}
+
+static int upload_c2z(umt_ctx *ctx, int **d_c2z) {
+  std::vector<int> c2z(ctx->nc);
+  for (int z = 0; z < ctx->nz; z++)
+    for (int c = 0; c < ctx->h_numCorner[z]; c++) c2z[ctx->h_cOffSet[z] + c] = z;
+  UMT_CUDA(ctx, cudaMalloc((void **)d_c2z, sizeof(int) * ctx->nc));
+  UMT_CUDA(ctx, cudaMemcpy(*d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
+  return UMT_OK;
+}
+
+// setGTAOpacityNEW on the device from Mat%Siga, Mat%Sigs (ngr,nz), Mat%Eta (nc), GTA%Chi (ngr,nc); Chi comes back rescaled
+extern "C" int umt_gta_compute_opacity(umt_ctx *ctx, const double *Siga, const double *Sigs, const double *Eta, double *Chi) {
+  if (!ctx || !Siga || !Sigs || !Eta || !Chi) return UMT_ERR_ARG;
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nz = ctx->nz, G = ctx->G;
+  double *d_a = nullptr, *d_s = nullptr, *d_e = nullptr;
+  int *d_c2z = nullptr;
+  int rc = upload_c2z(ctx, &d_c2z);
+  if (!rc) rc = dalloc(ctx, &d_a, (size_t)nz * G, false);
+  if (!rc) rc = dalloc(ctx, &d_s, (size_t)nz * G, false);
+  if (!rc) rc = dalloc(ctx, &d_e, nc, false);
+  if (!rc) {
+    cudaMemcpy(d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
+    cudaMemcpy(g.d_chi, Chi, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
+    gta_opacity_kernel<<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, G, ctx->tau, d_c2z, d_a, d_s, d_e, ctx->d_Volume, g.d_chi, g.d_sigTotal,
+                                                             g.d_sigScat, g.d_sigScatVol, g.d_sigtInv);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(Chi, g.d_chi, sizeof(double) * (size_t)nc * G, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { ctx->err = std::string("umt_gta_compute_opacity: ") + cudaGetErrorString(e); rc = UMT_ERR_CUDA; }
+  }
+  cudaFree(d_a); cudaFree(d_s); cudaFree(d_e); cudaFree(d_c2z);
+  if (!rc) g.have_opacity = true;
+  return rc;
+}
+
+extern "C" int umt_gta_get_opacity(umt_ctx *ctx, double *GreySigTotal, double *GreySigScat, double *GreySigScatVol, double *GreySigtInv) {
+  if (!ctx) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  GtaState &g = ctx->gta;
+  const size_t n = sizeof(double) * ctx->nc;
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (GreySigTotal) UMT_CUDA(ctx, cudaMemcpy(GreySigTotal, g.d_sigTotal, n, cudaMemcpyDeviceToHost));
+  if (GreySigScat) UMT_CUDA(ctx, cudaMemcpy(GreySigScat, g.d_sigScat, n, cudaMemcpyDeviceToHost));
+  if (GreySigScatVol) UMT_CUDA(ctx, cudaMemcpy(GreySigScatVol, g.d_sigScatVol, n, cudaMemcpyDeviceToHost));
+  if (GreySigtInv) UMT_CUDA(ctx, cudaMemcpy(GreySigtInv, g.d_sigtInv, n, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+// getCollisionRate on the device-resident PhiTotal: GreySource (nc) stays on the device and is also returned if asked
+extern "C" int umt_collision_rate(umt_ctx *ctx, const double *Eta, const double *Siga, const double *Sigs, int residualFlag, double *GreySource) {
+  if (!ctx || !Eta || !Siga || !Sigs) return UMT_ERR_ARG;
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  if (!ctx->d_phi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_collision_rate: no PhiTotal on the device");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nz = ctx->nz, G = ctx->G;
+  double *d_a = nullptr, *d_s = nullptr, *d_e = nullptr;
+  int *d_c2z = nullptr;
+  int rc = upload_c2z(ctx, &d_c2z);
+  if (!rc) rc = dalloc(ctx, &d_a, (size_t)nz * G, false);
+  if (!rc) rc = dalloc(ctx, &d_s, (size_t)nz * G, false);
+  if (!rc) rc = dalloc(ctx, &d_e, nc, false);
+  if (!rc) {
+    cudaMemcpy(d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
+    collision_rate_kernel<<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, G, d_c2z, d_e, d_a, d_s, ctx->d_phi, g.d_greySource, residualFlag);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && GreySource) e = cudaMemcpy(GreySource, g.d_greySource, sizeof(double) * nc, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { ctx->err = std::string("umt_collision_rate: ") + cudaGetErrorString(e); rc = UMT_ERR_CUDA; }
+  }
+  cudaFree(d_a); cudaFree(d_s); cudaFree(d_e); cudaFree(d_c2z);
+  return rc;
+}
+
+extern "C" int umt_gta_set_source(umt_ctx *ctx, const double *GreySource) {
+  if (!ctx || !GreySource) return UMT_ERR_ARG;
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaMemcpy(ctx->gta.d_greySource, GreySource, sizeof(double) * ctx->nc, cudaMemcpyHostToDevice));
+  return UMT_OK;
+}
+
+extern "C" int umt_gta_init_tt(umt_ctx *ctx, double *TT /* (maxCorner, nc) or NULL */) {
+  if (!ctx) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZoneParams Z;
+  zone_params(ctx, Z, ctx->gta.d_P);
+  gta_init_tt_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z);
+  UMT_CUDA(ctx, cudaGetLastError());
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->gta.tt_decomposed = false;
+  if (TT) UMT_CUDA(ctx, cudaMemcpy(TT, ctx->gta.d_TT, sizeof(double) * (size_t)ctx->nc * ctx->maxCorner, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+// GTASweep (snac/GTASweep.F90, GTA%ID = 1) for all 8 angles: TsaSource = wtiso (GreySigScat P + GreySource); GreySource NULL keeps
+// the device copy, withSource = 0 sweeps with GreySource = 0.  PsiB_gta (nbelem, 8) in/out, PhiInc (nc) out.
+extern "C" int umt_gta_sweep(umt_ctx *ctx, const double *P, const double *GreySource, double *PsiB_gta, double *PhiInc, int withSource) {
+  if (!ctx || !P) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nb = ctx->nb;
+  if (GreySource) UMT_CUDA(ctx, cudaMemcpy(g.d_greySource, GreySource, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  if (!withSource) UMT_CUDA(ctx, cudaMemset(g.d_greySource, 0, sizeof(double) * nc));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  if (nb > 0) {
+    if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
+    else UMT_CUDA(ctx, cudaMemset(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng));
+  }
+  TRY(gta_device_sweep(ctx, g.d_P, g.d_PB));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (PhiInc) UMT_CUDA(ctx, cudaMemcpy(PhiInc, g.d_phiInc, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, cudaMemcpy(PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+// GreySweepNEW (rt/GreySweep.F90:12-48): P (nc) and PsiB_gta (nbelem, 8) in/out
+extern "C" int umt_gta_grey_sweep(umt_ctx *ctx, double *P, double *PsiB_gta, int withSource) {
+  if (!ctx || !P) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nb = ctx->nb;
+  UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  if (nb > 0) {
+    if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
+    else UMT_CUDA(ctx, cudaMemset(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng));
+  }
+  TRY(gta_grey_sweep(ctx, g.d_P, g.d_PB, withSource));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  UMT_CUDA(ctx, cudaMemcpy(P, g.d_P, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, cudaMemcpy(PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+// GTASolver (rt/GTASolver.F90:42-425), single domain: BiCGSTAB on the grey corrections with the device-resident PhiTotal
+// and GreySource (umt_collision_rate / umt_gta_set_source).  GreyCorrection stays on the device (umt_gta_get_correction,
+// umt_add_grey_corrections).
+extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double epsGrey, int enforceHardMax, int *nGreyIterOut, double *maxRelErrOut) {
+  if (!ctx) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  if (!ctx->d_phi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: no PhiTotal on the device");
+  if (!ctx->shared.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: multi-domain GTA exchange is not implemented yet");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc, nz = ctx->nz;
+  const size_t nB = (size_t)ctx->nb * g.nAng;
+  const double adqtSmall = 1.e-150;
+  cudaStream_t st = ctx->stream;
+  double *R = g.d_vec[0], *D = g.d_vec[1], *A = g.d_vec[2], *AS = g.d_vec[3];
+  double *RB = g.d_vecB[0], *DB = g.d_vecB[1], *AB = g.d_vecB[2], *ASB = g.d_vecB[3];
+  rad_energy_kernel<<<nblk(nz, 128), 128, 0, st>>>(nz, ctx->G, ctx->d_numCorner, ctx->d_cOffSet, ctx->d_Volume, ctx->d_phi, g.d_volZone, g.d_radEnergy);
+  TRY(umt_gta_init_tt(ctx, nullptr));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_correction, 0, sizeof(double) * nc, st));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_pzOld, 0, sizeof(double) * nz, st));
+  UMT_CUDA(ctx, cudaMemsetAsync(R, 0, sizeof(double) * nc, st));
+  if (nB) UMT_CUDA(ctx, cudaMemsetAsync(RB, 0, sizeof(double) * nB, st));
+  int nGreyIter = 1;
+  TRY(gta_grey_sweep(ctx, R, RB, 1));
+  UMT_CUDA(ctx, cudaMemcpyAsync(D, R, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+  if (nB) UMT_CUDA(ctx, cudaMemcpyAsync(DB, RB, sizeof(double) * nB, cudaMemcpyDeviceToDevice, st));
+  double rrOld = 0.0, maxRelErrGrey = 0.0;
+  TRY(device_dot(ctx, R, nullptr, &rrOld));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_greySource, 0, sizeof(double) * nc, st));
+  for (;;) {
+    if (std::fabs(rrOld) < adqtSmall) {
+      if (nGreyIter <= 2) UMT_CUDA(ctx, cudaMemcpyAsync(g.d_correction, R, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+      break;
+    }
+    nGreyIter += 2;
+    UMT_CUDA(ctx, cudaMemcpyAsync(A, D, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+    if (nB) UMT_CUDA(ctx, cudaMemcpyAsync(AB, DB, sizeof(double) * nB, cudaMemcpyDeviceToDevice, st));
+    TRY(gta_grey_sweep(ctx, A, AB, 0));
+    k_sub<<<nblk(nc), 256, 0, st>>>(A, D, A, nc);
+    if (nB) k_sub<<<nblk(nB), 256, 0, st>>>(AB, DB, AB, nB);
+    double dAd = 0.0;
+    TRY(device_dot(ctx, A, nullptr, &dAd));
+    if (std::fabs(dAd) < adqtSmall) break;
+    const double alpha = rrOld / dAd;
+    k_axmy<<<nblk(nc), 256, 0, st>>>(R, alpha, A, nc);
+    if (nB) k_axmy<<<nblk(nB), 256, 0, st>>>(RB, alpha, AB, nB);
+    UMT_CUDA(ctx, cudaMemcpyAsync(AS, R, sizeof(double) * nc, cudaMemcpyDeviceToDevice, st));
+    if (nB) UMT_CUDA(ctx, cudaMemcpyAsync(ASB, RB, sizeof(double) * nB, cudaMemcpyDeviceToDevice, st));
+    TRY(gta_grey_sweep(ctx, AS, ASB, 0));
+    k_sub<<<nblk(nc), 256, 0, st>>>(AS, R, AS, nc);
+    if (nB) k_sub<<<nblk(nB), 256, 0, st>>>(ASB, RB, ASB, nB);
+    double omegaNum = 0.0, omegaDen = 0.0;
+    TRY(device_dot(ctx, AS, R, &omegaNum));
+    TRY(device_dot(ctx, AS, AS, &omegaDen));
+    if (std::fabs(omegaDen) < adqtSmall || std::fabs(omegaNum) < adqtSmall) {
+      k_corr<<<nblk(nc), 256, 0, st>>>(g.d_correction, alpha, D, 0.0, R, nc, 0);
+      break;
+    }
+    const double omegaCG = omegaNum / omegaDen;
+    k_corr<<<nblk(nc), 256, 0, st>>>(g.d_correction, alpha, D, omegaCG, R, nc, 1);
+    k_axmy<<<nblk(nc), 256, 0, st>>>(R, omegaCG, AS, nc);
+    if (nB) k_axmy<<<nblk(nB), 256, 0, st>>>(RB, omegaCG, ASB, nB);
+    double rr = 0.0;
+    TRY(device_dot(ctx, R, nullptr, &rr));
+    const double beta = (rr * alpha) / (rrOld * omegaCG);
+    k_dir<<<nblk(nc), 256, 0, st>>>(D, R, beta, omegaCG, A, nc);
+    if (nB) k_dir<<<nblk(nB), 256, 0, st>>>(DB, RB, beta, omegaCG, AB, nB);
+    zone_error_kernel<<<RED_BLOCKS, 256, 0, st>>>(nz, ctx->d_numCorner, ctx->d_cOffSet, ctx->d_Volume, g.d_volZone, g.d_correction, g.d_radEnergy,
+                                                  g.d_pzOld, g.d_red);
+    zone_error_finish_kernel<<<1, 32, 0, st>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
+    double e3[3];
+    UMT_CUDA(ctx, cudaMemcpyAsync(e3, g.d_red + 3 * RED_BLOCKS, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+    UMT_CUDA(ctx, cudaStreamSynchronize(st));
+    if (std::isinf(e3[2])) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: grey solver encountered a NaN (iteration %d)", nGreyIter);
+    const double relErrL2 = e3[1] != 0.0 ? std::sqrt(std::fabs(e3[0] / e3[1])) : 0.0;
+    maxRelErrGrey = std::max(e3[2], relErrL2);
+    if (enforceHardMax && nGreyIter >= maxIters) break;
+    else if ((maxRelErrGrey < epsPoint || nGreyIter >= maxIters) && maxRelErrGrey < epsGrey) break;
+    else if (nGreyIter >= 100 * maxIters) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: grey solver is not converging (%d iterations)", nGreyIter);
+    rrOld = rr;
+  }
+  UMT_CUDA(ctx, cudaStreamSynchronize(st));
+  if (nGreyIterOut) *nGreyIterOut = nGreyIter;
+  if (maxRelErrOut) *maxRelErrOut = maxRelErrGrey;
+  return UMT_OK;
+}
+
+extern "C" int umt_gta_get_correction(umt_ctx *ctx, double *GreyCorrection) {
+  if (!ctx || !GreyCorrection) return UMT_ERR_ARG;
+  if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaMemcpy(GreyCorrection, ctx->gta.d_correction, sizeof(double) * ctx->nc, cudaMemcpyDeviceToHost));
+  return UMT_OK;
+}
+
+// addGreyCorrections.F90:70-91: PhiTotal += GreyCorrection * Chi on the device (Chi from umt_gta_compute_opacity)
+extern "C" int umt_add_grey_corrections(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  TRY(need_gta(ctx));
+  if (!ctx->d_phi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_add_grey_corrections: no PhiTotal on the device");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->nc * ctx->G;
+  add_corrections_kernel<<<nblk(n), 256, 0, ctx->stream>>>(n, ctx->G, ctx->gta.d_correction, ctx->gta.d_chi, ctx->d_phi);
+  UMT_CUDA(ctx, cudaGetLastError());
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}

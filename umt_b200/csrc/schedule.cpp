@@ -286,6 +286,36 @@ class OrderBuilder {
 
 }  // namespace
 
+static void fill_view(umt_ctx *ctx, MeshView &M) {
+  M.ndim = ctx->ndim; M.nz = ctx->nz; M.nc = ctx->nc; M.nb = ctx->nb; M.mcf = ctx->maxcf; M.mf = ctx->maxFaces; M.maxCorner = ctx->maxCorner;
+  M.numCorner = ctx->h_numCorner.data(); M.cOffSet = ctx->h_cOffSet.data(); M.nCFaces = ctx->h_nCFaces.data();
+  M.cFP = ctx->h_cFP.data(); M.cEZ = ctx->h_cEZ.data(); M.zoneFaces = ctx->h_zoneFaces.data();
+  M.zoneOpp = ctx->h_zoneOpp.data(); M.faceOpp = ctx->h_faceOpp.data(); M.CToFace = ctx->h_CToFace.data();
+  M.bzone = ctx->h_BoundaryZone.empty() ? nullptr : ctx->h_BoundaryZone.data();
+  M.Afp = ctx->h_Afp.data(); M.Aez = ctx->h_Aez.data();
+}
+
+// sweep order of an arbitrary set of ordinates (the GTA angle set: rtorder.F90 runs snnext for it as well)
+int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vector<int> &nHyp, std::vector<std::vector<int>> &zonesInPlane,
+                         std::vector<std::vector<int>> &nextZ, std::vector<std::vector<int>> &nextC) {
+  MeshView M;
+  fill_view(ctx, M);
+  nHyp.assign(nAng, 0); zonesInPlane.assign(nAng, {}); nextZ.assign(nAng, {}); nextC.assign(nAng, {});
+  std::vector<AngleSchedule> res(nAng);
+  std::vector<std::thread> pool;
+  for (int a = 0; a < nAng; a++)
+    pool.emplace_back([&, a]() { OrderBuilder ob(M, omegas + (size_t)a * ctx->ndim); ob.run(res[a]); });
+  for (auto &t : pool) t.join();
+  for (int a = 0; a < nAng; a++) {
+    if (!res[a].error.empty()) UMT_FAIL(ctx, UMT_ERR_SCHEDULE, "GTA sweep order, angle %d: %s", a + 1, res[a].error.c_str());
+    nHyp[a] = res[a].nHyp;
+    zonesInPlane[a] = std::move(res[a].zonesInPlane);
+    nextZ[a] = std::move(res[a].nextZ);
+    nextC[a] = std::move(res[a].nextC);
+  }
+  return UMT_OK;
+}
+
 int umt_host_build_schedule(umt_ctx *ctx) {
   const int NA = ctx->NA, nd = ctx->ndim;
   MeshView M;

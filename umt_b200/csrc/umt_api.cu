@@ -79,6 +79,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_start, ctx->d_finishNext, ctx->d_level};
   for (void *p : ptrs) if (p) cudaFree(p);
   umt_exchange_release(ctx);
+  umt_gta_release(ctx);
   for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

@@ -59,6 +59,34 @@ struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   size_t send_rows = 0, recv_rows = 0;
 };
 
+// grey transport acceleration state (gta.cu): 3-D, "new" GTA solver
+struct GtaState {
+  bool ready = false;
+  int nAng = 0;
+  std::vector<double> omega, weight;
+  std::vector<int> nHyp;
+  std::vector<std::vector<int>> zonesInPlane, nextZ, nextC;
+  double *d_omega = nullptr, *d_weight = nullptr;
+  int *d_nextZ = nullptr;              // (nAng, nz) signed 1-based
+  unsigned char *d_nextC = nullptr;    // (nAng, nc) 0-based local corner
+  WorkItem *d_items = nullptr;
+  int nItems = 0, nCounters = 0, maxHyp = 0;
+  int *d_counters = nullptr;
+  // opacities and sources (nc)
+  double *d_sigTotal = nullptr, *d_sigtInv = nullptr, *d_sigScat = nullptr, *d_sigScatVol = nullptr;
+  double *d_greySource = nullptr, *d_tsaSource = nullptr, *d_phiInc = nullptr, *d_correction = nullptr;
+  double *d_chi = nullptr;             // (nc, G)
+  double *d_TT = nullptr;              // (nc, maxCorner, maxCorner): TT(cc, c0+c) at [(c0+c)*mC + cc]
+  bool have_opacity = false, tt_decomposed = false;
+  double *d_tpsi = nullptr;            // (nAng, nc+nb): tPsi per angle; the nb tail rows are PsiB(:, angle)
+  double *d_pinc = nullptr;            // (nAng, nc)
+  double *d_vec[4] = {nullptr, nullptr, nullptr, nullptr};    // BiCGSTAB: residual, direction, action, actionS (nc)
+  double *d_vecB[4] = {nullptr, nullptr, nullptr, nullptr};   // their boundary parts (nAng, nb)
+  double *d_radEnergy = nullptr, *d_pzOld = nullptr, *d_volZone = nullptr;   // (nz)
+  double *d_red = nullptr;             // reduction scratch
+  double *d_P = nullptr, *d_PB = nullptr;   // staging for the host-facing sweep calls
+};
+
 struct umt_ctx {
   int device = 0;
   int ndim = 0, nz = 0, nc = 0, nb = 0, maxcf = 0, maxCorner = 0, maxFaces = 0, G = 0;
@@ -127,6 +155,8 @@ struct umt_ctx {
   double fluxFloor = 0.0;
   int rows_total() const { return nc + nb; }
 
+  GtaState gta;
+
   // stats
   double last_ms[4] = {0, 0, 0, 0};
   int last_launches = 0;
@@ -161,6 +191,9 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
                                 std::vector<double> &angDerivFac, std::vector<double> &w1, std::vector<double> &w2);
 int umt_device_geometry(umt_ctx *ctx, const double *d_px);
 void umt_exchange_release(umt_ctx *ctx);
+void umt_gta_release(umt_ctx *ctx);
+int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vector<int> &nHyp, std::vector<std::vector<int>> &zonesInPlane,
+                         std::vector<std::vector<int>> &nextZ, std::vector<std::vector<int>> &nextC);
 int umt_exchange_tally(umt_ctx *ctx, double tol);
 int umt_exchange_begin_pass(umt_ctx *ctx);
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);

@@ -223,6 +223,61 @@ class SweepContext:
     def synchronize(self):
         self._ck(self.lib.umt_synchronize(self.h), "umt_synchronize")
 
+    # -- grey transport acceleration ------------------------------------------
+    def gta_setup(self):
+        self._ck(self.lib.umt_gta_setup(self.h), "umt_gta_setup")
+
+    def gta_quadrature(self):
+        om, w = np.zeros((8, 3)), np.zeros(8)
+        self._ck(self.lib.umt_gta_get_quadrature(self.h, _dp(om), _dp(w)), "umt_gta_get_quadrature")
+        return om, w
+
+    def gta_set_opacity(self, GreySigTotal, GreySigScat, GreySigScatVol):
+        self._ck(self.lib.umt_gta_set_opacity(self.h, _dp(_f64(GreySigTotal)), _dp(_f64(GreySigScat)), _dp(_f64(GreySigScatVol))), "umt_gta_set_opacity")
+
+    def gta_compute_opacity(self, Siga, Sigs, Eta, Chi):
+        """Chi (nc, ngr) is rescaled in place (must be a contiguous float64 array)."""
+        assert Chi.dtype == np.float64 and Chi.flags.c_contiguous
+        self._ck(self.lib.umt_gta_compute_opacity(self.h, _dp(_f64(Siga)), _dp(_f64(Sigs)), _dp(_f64(Eta)), _dp(Chi)), "umt_gta_compute_opacity")
+        o = dict(GreySigTotal=np.zeros(self.nc), GreySigScat=np.zeros(self.nc), GreySigScatVol=np.zeros(self.nc), GreySigtInv=np.zeros(self.nc))
+        self._ck(self.lib.umt_gta_get_opacity(self.h, _dp(o["GreySigTotal"]), _dp(o["GreySigScat"]), _dp(o["GreySigScatVol"]), _dp(o["GreySigtInv"])),
+                 "umt_gta_get_opacity")
+        return o
+
+    def collision_rate(self, Eta, Siga, Sigs, residualFlag=0):
+        out = np.zeros(self.nc)
+        self._ck(self.lib.umt_collision_rate(self.h, _dp(_f64(Eta)), _dp(_f64(Siga)), _dp(_f64(Sigs)), int(residualFlag), _dp(out)), "umt_collision_rate")
+        return out
+
+    def gta_set_source(self, GreySource):
+        self._ck(self.lib.umt_gta_set_source(self.h, _dp(_f64(GreySource))), "umt_gta_set_source")
+
+    def gta_init_tt(self):
+        TT = np.zeros((self.nc, self.maxCorner))
+        self._ck(self.lib.umt_gta_init_tt(self.h, _dp(TT)), "umt_gta_init_tt")
+        return TT
+
+    def gta_sweep(self, P, GreySource=None, PsiB=None, withSource=True):
+        PhiInc = np.zeros(self.nc)
+        PsiB = np.zeros((8, max(self.nb, 1))) if PsiB is None else PsiB
+        self._ck(self.lib.umt_gta_sweep(self.h, _dp(_f64(P)), _dp(_f64(GreySource)), _dp(PsiB), _dp(PhiInc), int(bool(withSource))), "umt_gta_sweep")
+        return PhiInc, PsiB
+
+    def gta_grey_sweep(self, P, PsiB, withSource):
+        """GreySweepNEW: P (nc) and PsiB (8, nb) are updated in place."""
+        self._ck(self.lib.umt_gta_grey_sweep(self.h, _dp(P), _dp(PsiB), int(bool(withSource))), "umt_gta_grey_sweep")
+
+    def gta_solve(self, epsPoint=1e-6, maxIters=21, epsGrey=0.1, enforceHardMax=False):
+        n, e = C.c_int(0), C.c_double(0.0)
+        self._ck(self.lib.umt_gta_solve(self.h, C.c_double(epsPoint), int(maxIters), C.c_double(epsGrey), int(bool(enforceHardMax)), C.byref(n), C.byref(e)),
+                 "umt_gta_solve")
+        corr = np.zeros(self.nc)
+        self._ck(self.lib.umt_gta_get_correction(self.h, _dp(corr)), "umt_gta_get_correction")
+        return corr, n.value, e.value
+
+    def add_grey_corrections(self):
+        self._ck(self.lib.umt_add_grey_corrections(self.h), "umt_add_grey_corrections")
+
     # -- domain decomposition -----------------------------------------------
     def add_shared_boundary(self, neighborRank, firstBdyElem, nBdyElem):
         self._ck(self.lib.umt_add_shared_boundary(self.h, int(neighborRank), int(firstBdyElem), int(nBdyElem)), "umt_add_shared_boundary")
