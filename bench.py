@@ -86,6 +86,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def profiled_traffic_per_unknown():
+    """dram__bytes_read.sum + dram__bytes_write.sum of sweep3d_plan_kernel divided by the unknowns of that launch, from the
+    committed ncu capture of this very workload (profiles/r01_sweep3d_d20_G128_ncu_summary.txt: -d 20,20,20 -G 128, 6.29e9 unknowns per launch)."""
+    p = os.path.join(ROOT, "profiles", "r01_sweep3d_d20_G128_ncu_summary.txt")
+    try:
+        rd = wr = None
+        for line in open(p):
+            if "dram__bytes_read.sum [Gbyte]" in line:
+                rd = float(line.split("=")[1])
+            if "dram__bytes_write.sum [Gbyte]" in line:
+                wr = float(line.split("=")[1])
+        return (rd + wr) * 1e9 / (24 * 20 ** 3 * 8 * 32 * 128), os.path.relpath(p, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -120,7 +136,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    d = args.cpu_dims
+    d = args.cpu_dims or 8
     val, cores, dt, sample = cpu_sweep_rate(args.groups, args.polar, args.azimuthal, (d, d, d), steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": val, "unit": "unknowns/s",
@@ -153,7 +169,7 @@ def main():
     ap.add_argument("--groups", type=int, default=128)
     ap.add_argument("--polar", type=int, default=2)
     ap.add_argument("--azimuthal", type=int, default=2)
-    ap.add_argument("--cpu-dims", type=int, default=8, help="tiles per side of the bounded CPU sample")
+    ap.add_argument("--cpu-dims", type=int, default=0, help="tiles per side of the bounded CPU sample (default: 10 for the cpu_baseline leg, 8 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
     args = ap.parse_args()
@@ -221,19 +237,20 @@ def main():
         sampler.start()
     barrier()
     t0 = time.perf_counter()
-    sweep_ms = phi_ms = exch_ms = 0.0
+    sweep_ms = phi_ms = exch_ms = dev_ms = 0.0
     launches = 0
     iters = 0
     for _ in range(args.steps):
         iters += ctx.sweep(False, args.flux_iters)
         tm = ctx.last_times()
-        sweep_ms += tm["sweep_ms"]; phi_ms += tm["phi_ms"]; exch_ms += tm["exchange_ms"]
+        sweep_ms += tm["sweep_ms"]; phi_ms += tm["phi_ms"]; exch_ms += tm["exchange_ms"]; dev_ms += tm["total_ms"]
         launches += ctx.last_launches()
     barrier()
     wall = time.perf_counter() - t0
     # wall clock between the two barrier+synchronize brackets; umt_sweep itself ends with an event
     # synchronize on the library's stream, whose CUDA-event times are reported in kernel_ms
     step_ms = max_over_ranks(wall * 1e3 / args.steps)
+    device_step_ms = max_over_ranks(dev_ms / args.steps)   # CUDA events on the library's stream around each whole umt_sweep
     sweep_kernel_ms = max_over_ranks(sweep_ms / max(iters, 1))
     value = total_unknowns / (step_ms * 1e-3)
 
@@ -257,6 +274,7 @@ def main():
         peak, peak_src = measured_peak()
         balg = sweep_kernel_bytes_per_unknown(G)
         achieved = unknowns * balg / (sweep_kernel_ms * 1e-3) / 1e9
+        tpu, tsrc = profiled_traffic_per_unknown()
         model41 = unknowns * algorithmic_bytes_per_unknown(G) / ((sweep_ms + phi_ms) / max(iters, 1) * 1e-3) / 1e9
         line = {
             "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": value, "unit": "unknowns/s",
@@ -267,17 +285,20 @@ def main():
                     "ms_per_step": e2e_ms, "what": "umt_upload_state(Sigt,STotal) from pinned host + umt_sweep + umt_download_phi to pinned host"},
             "gpu_launches": launches,
             "flux_passes_per_step": iters / args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (tpu * unknowns / 1e9) if tpu else None, "traffic_unit": "GB per launch",
+                         "traffic_source": (f"ncu dram read+write {tpu:.1f} B/unknown measured at -d 20,20,20 -G 128 P2 A2 ({tsrc}), scaled by this launch's unknowns" if tpu else None),
                          "kernel": "sweep3d (persistent, all angles)", "bytes_per_unknown": balg, "kernel_ms": sweep_kernel_ms,
                          "peak_source": peak_src,
                          "whole_sweep_41B_model": {"bytes_per_unknown": algorithmic_bytes_per_unknown(G), "achieved": model41, "frac": model41 / peak}},
             "kernel_ms": {"sweep": sweep_ms / args.steps, "phi": phi_ms / args.steps, "exchange": exch_ms / args.steps},
+            "device_ms_per_step": device_step_ms,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:
-            cd = args.cpu_dims
-            v, cores, dt, sample = cpu_sweep_rate(G, args.polar, args.azimuthal, (cd, cd, cd), steps=1, warmup=0)
-            line["cpu_baseline"] = {"value": v, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample + f", {dt:.1f} s"}
+            cd = args.cpu_dims or 10
+            v, cores, dt, sample = cpu_sweep_rate(G, args.polar, args.azimuthal, (cd, cd, cd), steps=3, warmup=0)
+            line["cpu_baseline"] = {"value": v, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample + f", 3 sweeps of {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

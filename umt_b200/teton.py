@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libumtsweep.so")
+LIB_PATH = os.environ.get("UMT_LIB") or os.path.join(_HERE, "libumtsweep.so")   # UMT_LIB: A/B builds of the same library
 _lib = None
 
 c_dp = C.POINTER(C.c_double)
