@@ -127,6 +127,14 @@ int umt_last_sweep_times(umt_ctx *ctx, double *ms4);
 int umt_last_sweep_launches(umt_ctx *ctx, int *nLaunches);
 int umt_synchronize(umt_ctx *ctx);
 
+/* ---- reflecting boundaries: snac/snreflect.F90, rt/findReflectedAngles.F90 ---- */
+/* One call per reflecting boundary (one plane each, as the reference requires): before an angle incident on it is swept,
+   PsiB(:,b,Minc) <- PsiB(:,b,Mref) for its mirror angle Mref (snac/reflectAxis.F90, axis-aligned planes).  Angles are swept in
+   stages so that Mref precedes Minc. */
+int umt_add_reflecting_boundary(umt_ctx *ctx, int firstBdyElem, int nBdyElem);
+int umt_get_reflected_angles(umt_ctx *ctx, int reflIndex, int *mref /* (NA) 1-based, -1 = not incident */);
+int umt_get_reflect_stages(umt_ctx *ctx, int *stageOf /* (NA) */);
+
 /* ---- domain decomposition: rt/findexit.F90:102-294, rt/SendFlux.F90, rt/RecvFlux.F90 ---- */
 /* One call per shared boundary (neighbour): its boundary elements are
    firstBdyElem..firstBdyElem+nBdyElem-1 (1-based), matched element-by-element with

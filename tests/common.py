@@ -277,3 +277,80 @@ def run_local_group(contexts, fn):
         if e is not None:
             raise e
     return out
+
+
+# ---------------------------------------------------------------------------
+# reflecting boundaries (snreflect.F90 + findReflectedAngles.F90 / reflectAxis.F90, axis-aligned planes)
+# ---------------------------------------------------------------------------
+def reflecting_boundaries(mesh):
+    return [b for b in mesh.boundaries if b.bc_type == M.BC_REFL]
+
+
+def oracle_reflected_angles(p):
+    """mref[k][a] = 0-based mirror angle of angle a on the k-th reflecting boundary (-1: not incident)."""
+    out = []
+    for b in reflecting_boundaries(p.mesh):
+        A = p.geom["A_bdy"][b.first_elem - 1]
+        nmax = int(np.argmax(np.abs(A)))
+        mref = np.full(p.NA, -1)
+        for a in range(p.NA):
+            if p.omega[a] @ A < -1e-15:
+                for ia in range(p.NA):   # reflectAxis.F90:101-113, last match wins
+                    if abs(p.omega[ia, nmax] + p.omega[a, nmax]) < 1e-6 and all(
+                            abs(p.omega[ia, d] - p.omega[a, d]) < 1e-6 for d in range(3) if d != nmax):
+                        mref[a] = ia
+                assert mref[a] >= 0
+        out.append(mref)
+    return out
+
+
+def reflect_stages(mrefs, NA):
+    """stage(a) = 1 + max stage of its mirror images; back edges (facing planes) are lagged.  Same DFS as csrc/reflect.cu."""
+    deps = [[int(m[a]) for m in mrefs if m[a] >= 0] for a in range(NA)]
+    stage, state = [0] * NA, [0] * NA
+    for root in range(NA):
+        if state[root]:
+            continue
+        st = [[root, 0]]
+        state[root] = 1
+        while st:
+            a, i = st[-1]
+            if i < len(deps[a]):
+                st[-1][1] += 1
+                m = deps[a][i]
+                if state[m] == 0:
+                    state[m] = 1
+                    st.append([m, 0])
+                elif state[m] == 2:
+                    stage[a] = max(stage[a], stage[m] + 1)
+            else:
+                state[a] = 2
+                st.pop()
+                if st:
+                    stage[st[-1][0]] = max(stage[st[-1][0]], stage[a] + 1)
+    return stage
+
+
+def oracle_sweep_3d_reflecting(p, savePsi):
+    """SetSweep angle loop with snreflect before each angle; angles ordered by reflection stage, the copies of a
+    stage made before its sweeps (what one persistent launch per stage does).  No mesh cycles expected."""
+    assert p.sched["totalCycles"] == 0
+    m = p.mesh
+    mrefs = oracle_reflected_angles(p)
+    stage = reflect_stages(mrefs, p.NA)
+    refl = reflecting_boundaries(m)
+    PhiSets = np.zeros((p.NA, m.ncornr, p.G))
+    Psi1 = np.zeros((m.ncornr + m.nbelem, p.G))
+    for s in range(max(stage) + 1):
+        angles = [a for a in range(p.NA) if stage[a] == s]
+        for a in angles:
+            for k, b in enumerate(refl):
+                if mrefs[k][a] >= 0:
+                    sl = slice(b.first_elem - 1, b.first_elem - 1 + b.n_elem)
+                    p.PsiB[a, sl] = p.PsiB[mrefs[k][a], sl]
+        for a in angles:
+            O.sweep_xyz(p.om, p.geom, p.sched, a, p.omega, p.weight, p.tau, p.STotal, p.Sigt, p.Psi[a], Psi1, p.PsiB[a], PhiSets[a], savePsi)
+    Phi = np.zeros((m.ncornr, p.G))
+    for a in range(p.NA):
+        Phi = Phi + PhiSets[a]
+    return Phi, stage, mrefs

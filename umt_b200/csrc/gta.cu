@@ -547,6 +547,7 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: host-only context");
   if (!ctx->have_conn || !ctx->have_geom || ctx->h_zoneOpp.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: needs full connectivity and geometry");
   if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
+  if (!ctx->refl.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: reflecting boundaries are not supported by the GTA sweep yet");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   g.nAng = 8;

@@ -773,7 +773,7 @@ static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel, threads, smem));
   if (occ < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweep3d_plan_kernel does not fit on an SM");
   if (const char *e = getenv("UMT_PLAN_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
-  int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
+  int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
   sweep3d_plan_kernel<<<grid, threads, smem, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   return UMT_OK;
@@ -786,18 +786,28 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
   Sweep3DParams P;
   fill_params(ctx, P);
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
-  if (ctx->use_plan) {
-    if (!ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
-    int r = launch_plan(ctx, P);
+  if (ctx->use_plan && !ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
+  // one launch per reflection stage (a single stage unless the domain has reflecting boundaries)
+  for (int s = 0; s < ctx->nStages; s++) {
+    const int begin = ctx->stageItemBegin[s], end = ctx->stageItemBegin[s + 1];
+    if (end == begin) continue;
+    if (s > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
+    int r = umt_launch_reflect(ctx, s);   // snreflect for the incident angles of this stage
     if (r) return r;
-  } else {
-    int occ = 0;
-    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_generic_kernel, 128, 0));
-    if (occ < 1) occ = 1;
-    int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
-    sweep3d_generic_kernel<<<grid, 128, 0, ctx->stream>>>(P);
-    UMT_CUDA(ctx, cudaGetLastError());
+    P.items = ctx->d_items + begin;
+    P.nItems = end - begin;
+    if (ctx->use_plan) {
+      r = launch_plan(ctx, P);
+      if (r) return r;
+    } else {
+      int occ = 0;
+      UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_generic_kernel, 128, 0));
+      if (occ < 1) occ = 1;
+      int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
+      sweep3d_generic_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+      UMT_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->last_launches += 1;
   }
-  ctx->last_launches += 1;
   return UMT_OK;
 }

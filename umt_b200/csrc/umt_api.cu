@@ -76,7 +76,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_nextC, ctx->d_items, ctx->d_counters, ctx->d_cycleList, ctx->d_cycleAngle, ctx->d_cyclePsi,
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
                   ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo, ctx->d_angDerivFac, ctx->d_tauW1, ctx->d_tauW2,
-                  ctx->d_start, ctx->d_finishNext, ctx->d_level};
+                  ctx->d_start, ctx->d_finishNext, ctx->d_level, ctx->d_reflOps};
   for (void *p : ptrs) if (p) cudaFree(p);
   umt_exchange_release(ctx);
   umt_gta_release(ctx);
@@ -345,26 +345,42 @@ static int finalize_schedule(umt_ctx *ctx) {
       for (int k = 0; k < nItemsPlane[a][p]; k++) planeSignals[a][p] += signals(std::min(zpi, n - k * zpi));
     }
   }
-  const int nBatches = (NA + K - 1) / K;
-  const int nLevels = ctx->ndim == 2 ? 0 : maxHyp + (nBatches - 1) * delta;
-  if (ctx->ndim == 2) TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering
-  for (int lev = 0; lev < nLevels; lev++)
-    for (int a = 0; a < NA; a++) {
-      const int p = lev - (a / K) * delta;
-      if (p < 0 || p >= ctx->nHyp[a]) continue;
-      const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
-      for (int k = 0; k < nItemsPlane[a][p]; k++) {
-        WorkItem w;
-        w.angle = a;
-        w.zbeg = z0 + k * zpi;
-        w.zend = std::min(z0 + n, w.zbeg + zpi);
-        w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
-        w.wait_count = p > 0 ? planeSignals[a][p - 1] : 0;
-        w.signal_idx = a * maxHyp + p;
-        w.pad0 = w.pad1 = 0;
-        items.push_back(w);
-      }
+  // Reflecting boundaries couple angles (snac/snreflect.F90): an incident angle needs the exiting flux of its mirror
+  // image.  Angles are therefore swept in stages (umt_reflect_stages); all angles of a stage are independent.
+  TRY(umt_reflect_stages(ctx));
+  ctx->stageItemBegin.assign(ctx->nStages + 1, 0);
+  if (ctx->ndim == 2) {
+    if (ctx->nStages > 1) UMT_FAIL(ctx, UMT_ERR_STATE, "reflecting boundaries are not supported by the RZ sweep yet");
+    TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering
+  } else {
+    for (int s = 0; s < ctx->nStages; s++) {
+      std::vector<int> ang;
+      for (int a2 = 0; a2 < NA; a2++) if (ctx->stageOf[a2] == s) ang.push_back(a2);
+      const int nA = (int)ang.size();
+      const int nBatches = (nA + K - 1) / K;
+      const int nLevels = maxHyp + (nBatches - 1) * delta;
+      for (int lev = 0; lev < nLevels; lev++)
+        for (int ia = 0; ia < nA; ia++) {
+          const int a = ang[ia];
+          const int p = lev - (ia / K) * delta;
+          if (p < 0 || p >= ctx->nHyp[a]) continue;
+          const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
+          for (int k = 0; k < nItemsPlane[a][p]; k++) {
+            WorkItem w;
+            w.angle = a;
+            w.zbeg = z0 + k * zpi;
+            w.zend = std::min(z0 + n, w.zbeg + zpi);
+            w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
+            w.wait_count = p > 0 ? planeSignals[a][p - 1] : 0;
+            w.signal_idx = a * maxHyp + p;
+            w.pad0 = w.pad1 = 0;
+            items.push_back(w);
+          }
+        }
+      ctx->stageItemBegin[s + 1] = (int)items.size();
     }
+  }
+  if (ctx->ndim == 2) ctx->stageItemBegin[ctx->nStages] = (int)items.size();
   ctx->nItems = (int)items.size();
   ctx->nCounters = NA * maxHyp;
   TRY(dev_alloc_copy(ctx, &ctx->d_nextZ, h_nextZ.data(), h_nextZ.size()));

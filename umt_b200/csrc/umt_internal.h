@@ -142,6 +142,15 @@ struct umt_ctx {
   double *d_psim = nullptr;            // RZ half-angle intensity (G,nc) per xi-level
   size_t psi_elems = 0;
 
+  // reflecting boundaries (snac/snreflect.F90, rt/findReflectedAngles.F90): per boundary the mirror angle of every
+  // incident angle (-1: not incident); stageOf[a] orders the angles so that a mirror image is swept first
+  struct ReflBdy { int first, n; std::vector<int> mref; };
+  std::vector<ReflBdy> refl;
+  std::vector<int> stageOf, stageItemBegin;
+  int nStages = 1;
+  int4 *d_reflOps = nullptr;           // (minc, mref, first, n) grouped by stage
+  std::vector<int> reflOpBegin;        // per-stage offsets into d_reflOps
+
   // exchange
   std::vector<SharedBdy> shared;
   int myRank = 0, nRanks = 1;
@@ -191,6 +200,8 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
                                 std::vector<double> &angDerivFac, std::vector<double> &w1, std::vector<double> &w2);
 int umt_device_geometry(umt_ctx *ctx, const double *d_px);
 void umt_exchange_release(umt_ctx *ctx);
+int umt_reflect_stages(umt_ctx *ctx);
+int umt_launch_reflect(umt_ctx *ctx, int stage);
 void umt_gta_release(umt_ctx *ctx);
 int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vector<int> &nHyp, std::vector<std::vector<int>> &zonesInPlane,
                          std::vector<std::vector<int>> &nextZ, std::vector<std::vector<int>> &nextC);

@@ -324,8 +324,9 @@ def decompose(rank: int, size: int, ndims: int):
     return domainid, domains
 
 
-def _box_sides(ndim, domainid, domains, lo, hi, tol):
-    """side ids 0..2*ndim-1 = (x-, x+, y-, y+, z-, z+); shared where a neighbour exists."""
+def _box_sides(ndim, domainid, domains, lo, hi, tol, reflecting=()):
+    """side ids 0..2*ndim-1 = (x-, x+, y-, y+, z-, z+); shared where a neighbour exists,
+    reflecting (bcType_refl) where asked on an outer side, vacuum otherwise."""
     sides = []
     for d in range(ndim):
         for s in (0, 1):
@@ -335,7 +336,7 @@ def _box_sides(ndim, domainid, domains, lo, hi, tol):
                 r = nb[0] + domains[0] * (nb[1] + domains[1] * nb[2])
                 sides.append((BC_SHARED, r))
             else:
-                sides.append((BC_VAC, -1))
+                sides.append((BC_REFL if (2 * d + s) in reflecting else BC_VAC, -1))
 
     def classify(fc, _nodes):
         out = np.full(len(fc), -1, np.int64)
@@ -352,7 +353,7 @@ def _box_sides(ndim, domainid, domains, lo, hi, tol):
 # ---------------------------------------------------------------------------
 
 def tiled_mesh(dims: Sequence[int], rank: int = 0, size: int = 1,
-               extents=(0., 1., 0., 1., 0., 1.)) -> TetonMesh:
+               extents=(0., 1., 0., 1., 0., 1.), reflecting=()) -> TetonMesh:
     """The driver's ``-B local -d nx,ny,nz`` mesh (test_driver.cc:1787-1816):
     every domain holds nx x ny tiles (x nz layers); the unit box is split
     between ``size`` domains by ``decompose``.  nz == 0 gives the 2-D (r,z) mesh."""
@@ -384,7 +385,7 @@ def tiled_mesh(dims: Sequence[int], rank: int = 0, size: int = 1,
     if ndim == 2:
         coords = np.stack([x2, y2], axis=1)
         nkey = np.stack([gkx, gky], axis=1)
-        sides, classify = _box_sides(2, domainid, domains, dlo, dhi, tol)
+        sides, classify = _box_sides(2, domainid, domains, dlo, dhi, tol, reflecting)
         m = build_teton_mesh(coords, quads, classify, sides, nkey)
     else:
         zs = dlo[2] + np.arange(nzl + 1) * (side_len[2] / nzl)
@@ -393,7 +394,7 @@ def tiled_mesh(dims: Sequence[int], rank: int = 0, size: int = 1,
                          np.repeat(np.arange(nzl + 1) + domainid[2] * nzl, n2)], axis=1)
         lay = np.arange(nzl)[:, None, None] * n2
         hexes = np.concatenate([quads[None] + lay, quads[None] + lay + n2], axis=2).reshape(-1, 8)
-        sides, classify = _box_sides(3, domainid, domains, dlo, dhi, tol)
+        sides, classify = _box_sides(3, domainid, domains, dlo, dhi, tol, reflecting)
         m = build_teton_mesh(coords, hexes, classify, sides, nkey)
     m.info.update(kind="tiled", dims=(nx, ny, nzl), rank=rank, size=size,
                   domainid=domainid, domains=domains)
@@ -401,7 +402,7 @@ def tiled_mesh(dims: Sequence[int], rank: int = 0, size: int = 1,
 
 
 def box_mesh(n: Sequence[int], lengths=None, rank: int = 0, size: int = 1,
-             warp: float = 0.0, seed: int = 0) -> TetonMesh:
+             warp: float = 0.0, seed: int = 0, reflecting=()) -> TetonMesh:
     """Structured quad/hex box (n cells per side).  ``warp`` > 0 displaces the
     interior nodes randomly (seeded) by that fraction of a cell so that faces
     become non-planar and corner faces on one zone face can change sign — the
@@ -455,7 +456,7 @@ def box_mesh(n: Sequence[int], lengths=None, rank: int = 0, size: int = 1,
         I, J, K = I.ravel(), J.ravel(), K.ravel()
         zones = np.stack([nid(I, J, K), nid(I + 1, J, K), nid(I + 1, J + 1, K), nid(I, J + 1, K),
                           nid(I, J, K + 1), nid(I + 1, J, K + 1), nid(I + 1, J + 1, K + 1), nid(I, J + 1, K + 1)], axis=1)
-    sides, classify = _box_sides(ndim, domainid, domains, dlo, dhi, 1e-9 * float(h.min()))
+    sides, classify = _box_sides(ndim, domainid, domains, dlo, dhi, 1e-9 * float(h.min()), reflecting)
     m = build_teton_mesh(coords, zones, classify, sides, nkey)
     m.info.update(kind="box", dims=tuple(n), rank=rank, size=size, domainid=domainid, domains=domains, warp=warp)
     return m

@@ -278,6 +278,20 @@ class SweepContext:
     def add_grey_corrections(self):
         self._ck(self.lib.umt_add_grey_corrections(self.h), "umt_add_grey_corrections")
 
+    # -- reflecting boundaries ------------------------------------------------
+    def add_reflecting_boundary(self, firstBdyElem, nBdyElem):
+        self._ck(self.lib.umt_add_reflecting_boundary(self.h, int(firstBdyElem), int(nBdyElem)), "umt_add_reflecting_boundary")
+
+    def reflected_angles(self, reflIndex):
+        m = np.zeros(self.NA, np.int32)
+        self._ck(self.lib.umt_get_reflected_angles(self.h, int(reflIndex), _ip(m)), "umt_get_reflected_angles")
+        return m
+
+    def reflect_stages(self):
+        s = np.zeros(self.NA, np.int32)
+        self._ck(self.lib.umt_get_reflect_stages(self.h, _ip(s)), "umt_get_reflect_stages")
+        return s
+
     # -- domain decomposition -----------------------------------------------
     def add_shared_boundary(self, neighborRank, firstBdyElem, nBdyElem):
         self._ck(self.lib.umt_add_shared_boundary(self.h, int(neighborRank), int(firstBdyElem), int(nBdyElem)), "umt_add_shared_boundary")
