@@ -170,6 +170,13 @@ int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incFluxOld);
 /* adqtEpsilon*speed_light*rad_constant*tr4floor of rt/testFluxConv.F90:73 (default 0). */
 int umt_set_flux_floor(umt_ctx *ctx, double floorFlux);
 
+/* ---- scattering + emission source build (extension; the mini-app reference never fills GSet%STotal, mods/GroupSet_mod.F90:74-77) ---- */
+/* STotal(g,c) = wtiso [ sigs(g,z) PhiTotal(g,c) + Chi(g,c) Eta(c) sum_g' siga(g',z) PhiTotal(g',c) + EmissionRate(g,c) ] from the
+   device-resident PhiTotal into the device-resident GSet%STotal; EmissionRate (Mat%EmissionRate(ngr,ncornr)) and STotalOut may be NULL.
+   Consistent with rt/getCollisionRate.F90:60-75 and the Chi redistribution of rt/addGreyCorrections.F90:85-86.  Parity unpinned. */
+int umt_build_source(umt_ctx *ctx, const double *Siga, const double *Sigs, const double *Eta, const double *Chi,
+                     const double *EmissionRate, double *STotalOut);
+
 /* ---- grey transport acceleration (3-D, "new" GTA solver): rt/GTASolver.F90, snac/GTASweep.F90 ---- */
 /* GTA angle set (level-symmetric S2, 8 ordinates: rt/quadxyz.F90), its sweep order (rtorder/snnext) and device arrays.
    Needs full connectivity and geometry. */

@@ -134,3 +134,26 @@ def test_gta_no_scattering_exits_immediately():
     assert n == 1 and n_d == 1
     assert T.mixed_err(corr_d, corr, 1e-11) <= 1.0
     ctx.close()
+
+
+@pytest.mark.parametrize("G", [4, 33, 128])
+def test_source_build_extension(G):
+    """umt_build_source (extension, parity unpinned — the mini-app reference never fills STotal): numpy restatement of its
+    formula; and consistency with getCollisionRate: sum_g STotal / wtiso - sum_g emission = collision rate when sum_g Chi = 1."""
+    s = _setup(M.box_mesh((3, 3, 2)), G=G)
+    ctx, mesh = s["ctx"], s["mesh"]
+    nc = mesh.ncornr
+    rng = np.random.default_rng(11)
+    emis = rng.random((nc, G))
+    c2z = np.repeat(np.arange(mesh.nzones), mesh.numCorner)
+    wt = PR.wtiso(3)
+    ref = wt * (s["Sigs"][c2z] * s["Phi"] + s["Chi"] * (s["Eta"] * (s["Siga"][c2z] * s["Phi"]).sum(1))[:, None] + emis)
+    got = ctx.build_source(s["Siga"], s["Sigs"], s["Eta"], s["Chi"], emis)
+    assert T.relerr(got, ref) <= 1e-12
+    coll = O.collision_rate(s["om"], s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    assert np.abs(got.sum(1) / wt - emis.sum(1) - coll).max() <= 1e-11 * np.abs(coll).max()
+    # the sweep consumes it: one sweep with the built source runs and stays finite
+    ctx.build_schedule()
+    ctx.sweep(False)
+    assert np.isfinite(ctx.download_phi()).all()
+    ctx.close()

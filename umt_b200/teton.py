@@ -223,6 +223,12 @@ class SweepContext:
     def synchronize(self):
         self._ck(self.lib.umt_synchronize(self.h), "umt_synchronize")
 
+    def build_source(self, Siga, Sigs, Eta, Chi, EmissionRate=None):
+        out = np.zeros((self.nc, self.G))
+        self._ck(self.lib.umt_build_source(self.h, _dp(_f64(Siga)), _dp(_f64(Sigs)), _dp(_f64(Eta)), _dp(_f64(Chi)), _dp(_f64(EmissionRate)), _dp(out)),
+                 "umt_build_source")
+        return out
+
     # -- grey transport acceleration ------------------------------------------
     def gta_setup(self):
         self._ck(self.lib.umt_gta_setup(self.h), "umt_gta_setup")
