@@ -114,6 +114,7 @@ int umt_init_teton(umt_ctx *ctx, const double *Trz, const double *groupBounds, d
 
 /* control/initPhiTotal_OMPOL.F90 (Psi *= VolumeOld/Volume when volRatio != NULL, PhiTotal = sum w Psi)
    and control/initializeRadiationField_OMPOL.F90:116-143 (exit PsiB <- Psi, cyclePsi <- Psi). */
+int umt_set_boundary_sources(umt_ctx *ctx);   /* control/setBoundarySources.F90:42 without source profiles: PsiB = 0 */
 int umt_init_phi_total(umt_ctx *ctx, const double *volRatio);
 int umt_init_radiation_field(umt_ctx *ctx);
 
@@ -169,6 +170,13 @@ int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, int *listSe
 int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incFluxOld);
 /* adqtEpsilon*speed_light*rad_constant*tr4floor of rt/testFluxConv.F90:73 (default 0). */
 int umt_set_flux_floor(umt_ctx *ctx, double floorFlux);
+
+/* ---- end-of-cycle edits on the device-resident fields: aux/rtedit.F90:142-232, control/BoundaryEdit.F90, setEnergyDensity.F90 ---- */
+/* out5 = {EnergyRadiation, TrMax, PowerEscape, PowerIncident (0 without source boundaries), sum_zones sum_c V_c sum_g PhiTotal};
+   optional (NULL to skip): Mat%trz(nzones), RadEdit%RadPowerEscape(ngr), Rad%RadEnergyDensity(nzones, ngr).  3-D only so far for the
+   boundary edit.  Escape currents use Set%Psi at the boundary corners as the reference does (call after the savePsi sweep). */
+int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConstant, double tr4floor, double *out5, double *trz,
+                    double *RadPowerEscape, double *RadEnergyDensity);
 
 /* ---- scattering + emission source build (extension; the mini-app reference never fills GSet%STotal, mods/GroupSet_mod.F90:74-77) ---- */
 /* STotal(g,c) = wtiso [ sigs(g,z) PhiTotal(g,c) + Chi(g,c) Eta(c) sum_g' siga(g',z) PhiTotal(g',c) + EmissionRate(g,c) ] from the

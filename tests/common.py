@@ -354,3 +354,32 @@ def oracle_sweep_3d_reflecting(p, savePsi):
     for a in range(p.NA):
         Phi = Phi + PhiSets[a]
     return Phi, stage, mrefs
+
+
+# ---------------------------------------------------------------------------
+# one mini-app time step on the oracle (what umt_b200/cycle.py drives through the C ABI)
+# ---------------------------------------------------------------------------
+def oracle_cycle_3d(p, dt, tr4floor):
+    """radtr.F90 for the mini-app: PsiB = 0, PhiTotal = sum w psi, exit PsiB <- psi, EnergyRadBOC, 2 temperature
+    iterations + the savePsi sweep, then rtedit's EnergyRadiation / TrMax / PowerEscape / EnergyCheck."""
+    m = p.mesh
+    V = p.geom["Volume"]
+    p.PsiB[:] = 0.0
+    phi0 = np.einsum("a,acg->cg", p.weight, p.Psi)
+    for a in range(p.NA):
+        for b, c in p.bdy[a]:
+            p.PsiB[a, b - 1] = p.Psi[a, c - 1]
+    e_boc = float((V[:, None] * phi0).sum()) / SPEED_LIGHT
+    for _ in range(2):
+        oracle_sweep_3d(p, False)
+    phi = oracle_sweep_3d(p, True)
+    erad_z = np.add.reduceat((V[:, None] * phi).sum(1), m.cOffSet)
+    e_rad = float(erad_z.sum()) / SPEED_LIGHT
+    trz = np.sqrt(np.sqrt(np.maximum(erad_z / (p.geom["VolumeZone"] * RAD_CONSTANT * SPEED_LIGHT), tr4floor)))
+    esc = np.zeros(p.G)
+    for a in range(p.NA):
+        for b, c in p.bdy[a]:
+            esc += p.weight[a] * float(p.geom["A_bdy"][b - 1] @ p.omega[a]) * p.Psi[a, c - 1]
+    d_erad = e_rad - e_boc
+    return dict(EnergyRadiation=e_rad, TrMax=float(trz.max()), PowerEscape=float(esc.sum()), RadPowerEscape=esc, trz=trz,
+                EnergyRadBOC=e_boc, EnergyCheck=dt * (0.0 - float(esc.sum())) - d_erad, phi=phi)

@@ -435,6 +435,8 @@ static int finalize_schedule(umt_ctx *ctx) {
   return UMT_OK;
 }
 
+int umt_finalize_schedule(umt_ctx *ctx) { return finalize_schedule(ctx); }
+
 // ---------------------------------------------------------------------------
 // state
 // ---------------------------------------------------------------------------
@@ -634,6 +636,19 @@ extern "C" int umt_init_phi_total(umt_ctx *ctx, const double *volRatio) {
   }
   TRY(launch_phi(ctx, ctx->d_psi));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+// control/setBoundarySources.F90:42 with no source profiles: Set%PsiB(:,:,:) = 0
+extern "C" int umt_set_boundary_sources(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  if (ctx->nb > 0) {
+    const size_t G = ctx->G;
+    UMT_CUDA(ctx, cudaMemset2DAsync(ctx->d_psi1 + G * ctx->nc, G * ctx->rows * 8, 0, G * ctx->nb * 8, ctx->NA, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return UMT_OK;
 }
 

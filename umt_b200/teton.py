@@ -198,6 +198,9 @@ class SweepContext:
         self._ck(self.lib.umt_init_teton(self.h, _dp(_f64(Trz)), _dp(_f64(groupBounds)), C.c_double(speedLight), C.c_double(radConstant),
                                          C.c_double(wtiso), C.c_double(efloor)), "umt_init_teton")
 
+    def set_boundary_sources(self):
+        self._ck(self.lib.umt_set_boundary_sources(self.h), "umt_set_boundary_sources")
+
     def init_phi_total(self, volRatio=None):
         self._ck(self.lib.umt_init_phi_total(self.h, _dp(_f64(volRatio))), "umt_init_phi_total")
 
@@ -222,6 +225,16 @@ class SweepContext:
 
     def synchronize(self):
         self._ck(self.lib.umt_synchronize(self.h), "umt_synchronize")
+
+    def cycle_edits(self, speedLight, radConstant, tr4floor, want_trz=False, want_density=False):
+        out = np.zeros(5)
+        trz = np.zeros(self.nz) if want_trz else None
+        esc = np.zeros(self.G)
+        dens = np.zeros((self.G, self.nz)) if want_density else None
+        self._ck(self.lib.umt_cycle_edits(self.h, C.c_double(speedLight), C.c_double(radConstant), C.c_double(tr4floor), _dp(out), _dp(trz), _dp(esc), _dp(dens)),
+                 "umt_cycle_edits")
+        return dict(EnergyRadiation=out[0], TrMax=out[1], PowerEscape=out[2], PowerIncident=out[3], RadPowerEscape=esc, trz=trz,
+                    RadEnergyDensity=None if dens is None else dens.T)
 
     def build_source(self, Siga, Sigs, Eta, Chi, EmissionRate=None):
         out = np.zeros((self.nc, self.G))
