@@ -400,9 +400,15 @@ __device__ __forceinline__ void st_keep(double *p, const V2 &v) {   // Psi1 rows
 #ifndef PLAN_MINB
 #define PLAN_MINB 3            // CTAs per SM the plan kernel is compiled for (register cap 65536 / (160 * PLAN_MINB))
 #endif
+#ifndef PLAN_MINB2
+#define PLAN_MINB2 2           // same for the variant with 4 groups per lane (NH = 2)
+#endif
 constexpr int PLAN_MAX_STAGES = 8;
 constexpr int PLAN_ZMAX = 8;     // zones per item at most
-constexpr int PLAN_NCW = 4;      // consumer warps per CTA
+#ifndef PLAN_NCW_DEF
+#define PLAN_NCW_DEF 4
+#endif
+constexpr int PLAN_NCW = PLAN_NCW_DEF;      // consumer warps per CTA
 constexpr int PLAN_LANES = PLAN_NCW * 32;
 
 // How the consumer warps of a CTA are grouped for a given group count (host side, once per context).
@@ -419,20 +425,20 @@ struct PlanGeom {
   int offSt, offSigt, offRecs;
   size_t smemBytes;
 };
-static PlanGeom plan_geom(int G) {
+static PlanGeom plan_geom(int G, int NH) {
   PlanGeom g;
-  const int Gv = G / 2;
-  g.wpe = Gv > 64 ? 4 : (Gv > 32 ? 2 : 1);   // an engine must hold a whole zone (Gv lanes)
+  const int Gv = G / 2, LZ = std::max(Gv / NH, 1);   // 16-byte columns per zone; lanes per zone (a lane owns NH columns)
+  g.wpe = LZ > 64 ? 4 : (LZ > 32 ? 2 : 1);   // an engine must hold a whole zone (LZ lanes)
   g.nEngines = PLAN_NCW / g.wpe;
   const int LE = 32 * g.wpe;
-  g.zpi = std::max(1, std::min(PLAN_ZMAX, LE / std::max(Gv, 1)));
+  g.zpi = std::max(1, std::min(PLAN_ZMAX, LE / LZ));
   if (const char *e = getenv("UMT_ZONES_PER_ITEM")) g.zpi = std::max(1, std::min(g.zpi, atoi(e)));
-  g.offSt = LE * MAXC * 16;
+  g.offSt = NH * LE * MAXC * 16;
   g.offSigt = 2 * g.offSt;
-  g.offRecs = g.offSigt + LE * 16;
+  g.offRecs = g.offSigt + NH * LE * 16;
   g.stageBytes = (g.offRecs + g.zpi * (int)sizeof(ZoneRec) + 127) / 128 * 128;
-  // as many landing stages as still let PLAN_MINB CTAs share an SM (228 KB, 1 KB reserved per CTA)
-  const int budget = (228 * 1024) / PLAN_MINB - 2048;
+  // as many landing stages as still let the CTAs the kernel is compiled for share an SM (228 KB, 1 KB reserved per CTA)
+  const int budget = (228 * 1024) / (NH == 1 ? PLAN_MINB : PLAN_MINB2) - 2048;
   g.nStages = std::max(g.nEngines + 1, std::min(g.nEngines + 3, (budget - 1024) / g.stageBytes));
   if (const char *e = getenv("UMT_PLAN_STAGES")) g.nStages = std::max(g.nEngines + 1, std::min(PLAN_MAX_STAGES, atoi(e)));
   g.smemBytes = 1024 + (size_t)g.nStages * g.stageBytes;
@@ -464,88 +470,118 @@ __device__ __forceinline__ void sts_v2(unsigned addr, const V2 &v) {
 // One corner of the zone solve (position p of the record's solve order): incident FP fluxes (pfC, loaded
 // while the previous corner was solved), the EZ closure terms of its outgoing faces, the corner flux and
 // its push into the downstream corners; it also puts the next corner's incident rows in flight (pfN).
-// Q and the running sources live in shared memory (one 16-byte column per lane) because the downstream
-// corner of an edge is only known from the record.
+// Q and the running sources live in shared memory (16-byte columns, a lane only touches its own) because the
+// downstream corner of an edge is only known from the record.  A lane owns NH columns (2 NH groups) that lie
+// LZ columns apart (hs bytes in shared memory, hg doubles in global memory): every access of a warp stays a
+// contiguous run of 16-byte words, and the NH independent dependency chains interleave in the FP64 pipe.
+template <int NH>
 __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const ZoneEdge *__restrict__ &E, const int p, const int NC,
-                                            const V2 (&pfC)[3], V2 (&pfN)[3], const double *__restrict__ up, double *__restrict__ upw,
-                                            const unsigned qs, const unsigned ss, const V2 sig, const V2 rsig, const unsigned flags) {
+                                            const V2 (&pfC)[3][NH], V2 (&pfN)[3][NH], const double *__restrict__ up, double *__restrict__ upw,
+                                            const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const V2 (&rsig)[NH], const unsigned flags,
+                                            const unsigned hs, const int hg) {
   const int nout = R->nOut[p];
   if (p + 1 < NC) {   // incident rows of the next corner
     const int nn = R->nIn[p + 1];
 #pragma unroll
     for (int k = 0; k < 3; k++)
-      if (k < nn) pfN[k] = ld_l2(up + R->inOff[p + 1][k]);
+      if (k < nn) {
+        const double *src = up + R->inOff[p + 1][k];
+#pragma unroll
+        for (int h = 0; h < NH; h++) pfN[k][h] = ld_l2(src + h * hg);
+      }
   }
   const unsigned co = (unsigned)R->coff[p];
-  V2 s = lds_v2(ss + co);
-  const V2 qp = lds_v2(qs + co);
   const double vp = R->vol[p];
-  V2 sv;
-  sv.x = sig.x * vp; sv.y = sig.y * vp;
+  V2 s[NH], qp[NH], sv[NH];
+#pragma unroll
+  for (int h = 0; h < NH; h++) {
+    s[h] = lds_v2(ss + co + h * hs);
+    qp[h] = lds_v2(qs + co + h * hs);
+    sv[h].x = sig[h].x * vp; sv[h].y = sig[h].y * vp;
+  }
   // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); unused slots carry afp = 0 and a finite pf
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const double af = R->inAfp[p][k];
-    s.x = fma(-af, pfC[k].x, s.x); s.y = fma(-af, pfC[k].y, s.y);
+#pragma unroll
+    for (int h = 0; h < NH; h++) { s[h].x = fma(-af, pfC[k][h].x, s[h].x); s[h].y = fma(-af, pfC[k][h].y, s[h].y); }
   }
   // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), with x = sigma V / aez:
   //   sez = V [N(x)(sigma psi_opp - Q) + D(x)(Q - Q_cez)/2] / (N(x) + x D(x)),
   //   N = 1.82 x^2 + 4 x + 3,  D = 4 x^3 + 6 x^2 + 4 x + 2   (gnum = aez^4 N, gden = V aez^3 D)
-  V2 sezk[3];
+  V2 sezk[3][NH];
 #pragma unroll
   for (int k = 0; k < 3; k++)
     if (k < nout) {
       const ZoneEdge e = E[k];
-      const V2 qq = lds_v2(qs + (unsigned)e.qoff);
       if (e.hasOpp) {
-        const V2 po = pfC[k];
-        {
-          const double x = sv.x * e.ainv;
-          const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
-          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
-          const double num = fma(N, fma(sig.x, po.x, -qp.x), (0.5 * D) * (qp.x - qq.x));
-          sezk[k].x = (vp * num) * rcp_fast(fma(x, D, N));
-        }
-        {
-          const double x = sv.y * e.ainv;
-          const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
-          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
-          const double num = fma(N, fma(sig.y, po.y, -qp.y), (0.5 * D) * (qp.y - qq.y));
-          sezk[k].y = (vp * num) * rcp_fast(fma(x, D, N));
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+          const V2 qq = lds_v2(qs + (unsigned)e.qoff + h * hs);
+          const V2 po = pfC[k][h];
+          {
+            const double x = sv[h].x * e.ainv;
+            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+            const double num = fma(N, fma(sig[h].x, po.x, -qp[h].x), (0.5 * D) * (qp[h].x - qq.x));
+            sezk[k][h].x = (vp * num) * rcp_fast(fma(x, D, N));
+          }
+          {
+            const double x = sv[h].y * e.ainv;
+            const double N = fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+            const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+            const double num = fma(N, fma(sig[h].y, po.y, -qp[h].y), (0.5 * D) * (qp[h].y - qq.y));
+            sezk[k][h].y = (vp * num) * rcp_fast(fma(x, D, N));
+          }
         }
       } else {
-        sezk[k].x = (e.ha * (qp.x - qq.x)) * rsig.x;
-        sezk[k].y = (e.ha * (qp.y - qq.y)) * rsig.y;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+          const V2 qq = lds_v2(qs + (unsigned)e.qoff + h * hs);
+          sezk[k][h].x = (e.ha * (qp[h].x - qq.x)) * rsig[h].x;
+          sezk[k][h].y = (e.ha * (qp[h].y - qq.y)) * rsig[h].y;
+        }
       }
-      s.x += sezk[k].x; s.y += sezk[k].y;
+#pragma unroll
+      for (int h = 0; h < NH; h++) { s[h].x += sezk[k][h].x; s[h].y += sezk[k][h].y; }
     }
   // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
   const double sa = R->sumArea[p];
-  V2 psi;
-  psi.x = s.x * rcp_fast(sa + sv.x);
-  psi.y = s.y * rcp_fast(sa + sv.y);
-  st_keep(upw + R->crow[p], psi);
+  V2 psi[NH];
+#pragma unroll
+  for (int h = 0; h < NH; h++) {
+    psi[h].x = s[h].x * rcp_fast(sa + sv[h].x);
+    psi[h].y = s[h].y * rcp_fast(sa + sv[h].y);
+    st_keep(upw + R->crow[p] + h * hg, psi[h]);
+  }
 #pragma unroll
   for (int k = 0; k < 3; k++)
     if (k < nout) {
       const unsigned qa = ss + (unsigned)E[k].qoff;
       const double cp = E[k].cp;
-      V2 t = lds_v2(qa);
-      t.x = fma(cp, psi.x, t.x - sezk[k].x);
-      t.y = fma(cp, psi.y, t.y - sezk[k].y);
-      sts_v2(qa, t);
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        V2 t = lds_v2(qa + h * hs);
+        t.x = fma(cp, psi[h].x, t.x - sezk[k][h].x);
+        t.y = fma(cp, psi[h].y, t.y - sezk[k][h].y);
+        sts_v2(qa + h * hs, t);
+      }
     }
   if (flags & ZREC_HAS_EXIT) {
     const unsigned em = R->exitMask >> (p * 3);
 #pragma unroll
     for (int f = 0; f < 3; f++)
-      if (em & (1u << f)) st_keep(upw + R->exitOff[p][f], psi);
+      if (em & (1u << f)) {
+#pragma unroll
+        for (int h = 0; h < NH; h++) st_keep(upw + R->exitOff[p][f] + h * hg, psi[h]);
+      }
   }
   E += nout;
 }
 
+template <int NH>
 __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ psi1Ag,
-                                                const unsigned qs, const unsigned ss, const V2 sig) {
+                                                const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const unsigned hs, const int hg) {
   const unsigned flags = R->flags;
   const int NC = (int)(flags & 15u);
   // Q = STotal + tau Psi^n, src = V Q (SweepUCBxyz.F90:119-126), in place over the landed rows
@@ -553,35 +589,45 @@ __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec 
   for (int p = 0; p < MAXC; p++) {
     if (p < NC) {
       const unsigned co = (unsigned)R->coff[p];
-      const V2 a = lds_v2(qs + co), b = lds_v2(ss + co);
       const double v = R->vol[p];
-      V2 q, s;
-      q.x = fma(tau, a.x, b.x); q.y = fma(tau, a.y, b.y);
-      s.x = v * q.x; s.y = v * q.y;
-      sts_v2(qs + co, q);
-      sts_v2(ss + co, s);
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        const V2 a = lds_v2(qs + co + h * hs), b = lds_v2(ss + co + h * hs);
+        V2 q, s;
+        q.x = fma(tau, a.x, b.x); q.y = fma(tau, a.y, b.y);
+        s.x = v * q.x; s.y = v * q.y;
+        sts_v2(qs + co + h * hs, q);
+        sts_v2(ss + co + h * hs, s);
+      }
     }
   }
-  V2 rsig;
-  rsig.x = rcp_fast(sig.x); rsig.y = rcp_fast(sig.y);
-  const ZoneEdge *E = R->edge;
-  V2 pfA[3], pfB[3];
+  V2 rsig[NH];
 #pragma unroll
-  for (int k = 0; k < 3; k++) { pfA[k].x = pfA[k].y = 0.0; pfB[k].x = pfB[k].y = 0.0; }
+  for (int h = 0; h < NH; h++) { rsig[h].x = rcp_fast(sig[h].x); rsig[h].y = rcp_fast(sig[h].y); }
+  const ZoneEdge *E = R->edge;
+  V2 pfA[3][NH], pfB[3][NH];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int h = 0; h < NH; h++) { pfA[k][h].x = pfA[k][h].y = 0.0; pfB[k][h].x = pfB[k][h].y = 0.0; }
   {
     const int n0 = R->nIn[0];
 #pragma unroll
     for (int k = 0; k < 3; k++)
-      if (k < n0) pfA[k] = ld_l2(psi1Ag + R->inOff[0][k]);
+      if (k < n0) {
+#pragma unroll
+        for (int h = 0; h < NH; h++) pfA[k][h] = ld_l2(psi1Ag + R->inOff[0][k] + h * hg);
+      }
   }
 #pragma unroll 1
   for (int p = 0; p < NC; p += 2) {
-    plan_corner(R, E, p, NC, pfA, pfB, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags);
-    if (p + 1 < NC) plan_corner(R, E, p + 1, NC, pfB, pfA, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags);
+    plan_corner<NH>(R, E, p, NC, pfA, pfB, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags, hs, hg);
+    if (p + 1 < NC) plan_corner<NH>(R, E, p + 1, NC, pfB, pfA, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags, hs, hg);
   }
 }
 
-__global__ void __launch_bounds__(PLAN_LANES + 32, PLAN_MINB) sweep3d_plan_kernel(Sweep3DParams P) {
+template <int NH>
+__global__ void __launch_bounds__(PLAN_LANES + 32, (NH == 1 ? PLAN_MINB : PLAN_MINB2)) sweep3d_plan_kernel(Sweep3DParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw);
   unsigned char *stages = smem_raw + 1024;
@@ -696,7 +742,10 @@ __global__ void __launch_bounds__(PLAN_LANES + 32, PLAN_MINB) sweep3d_plan_kerne
 
   // ---------------- consumer warps: engines of wpe warps, each on its own stages ----------------
   const int eng = warp / wpe, elane = (warp - eng * wpe) * 32 + lane;   // my engine, my lane in it
-  const int zi = elane / Gv, li = elane - zi * Gv;                     // my zone of the item, my column in it
+  const int LZ = Gv / NH;                                              // lanes per zone; a lane owns columns li + h LZ
+  const int zi = elane / LZ, li = elane - zi * LZ;                     // my zone of the item, my first column in it
+  const unsigned hs = (unsigned)LZ * 16u;
+  const int hg = 2 * LZ;
   const double tau = P.tau;
   for (int k = eng;; k += NE) {
     const int s = k % NS;
@@ -708,12 +757,16 @@ __global__ void __launch_bounds__(PLAN_LANES + 32, PLAN_MINB) sweep3d_plan_kerne
       const ZoneRec *R = reinterpret_cast<const ZoneRec *>(st + P.offRecs) + zi;
       double *psi1Ag = P.psi1 + (size_t)m.angle * slab + 2 * li;
       if (R->flags & ZREC_SLOW) {
-        solve_zone_slow(P, m.angle, R->zone0, 2 * li);
-        solve_zone_slow(P, m.angle, R->zone0, 2 * li + 1);
+        for (int h = 0; h < NH; h++) {
+          solve_zone_slow(P, m.angle, R->zone0, 2 * (li + h * LZ));
+          solve_zone_slow(P, m.angle, R->zone0, 2 * (li + h * LZ) + 1);
+        }
       } else {
         const unsigned col = (unsigned)(zi * MAXC * Gv + li) * 16u;
-        const V2 sig = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li) * 16);
-        solve_zone_plan(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig);
+        V2 sig[NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) sig[h] = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li + h * LZ) * 16);
+        solve_zone_plan<NH>(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
       }
     }
     __syncwarp();
@@ -724,7 +777,7 @@ __global__ void __launch_bounds__(PLAN_LANES + 32, PLAN_MINB) sweep3d_plan_kerne
 void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.nc = ctx->nc; P.nb = ctx->nb; P.nz = ctx->nz; P.G = ctx->G; P.NA = ctx->NA; P.nItems = ctx->nItems;
   P.tau = ctx->tau;
-  const PlanGeom pg = plan_geom(ctx->G);
+  const PlanGeom pg = plan_geom(ctx->G, ctx->plan_nh);
   P.wpe = pg.wpe; P.nEngines = pg.nEngines; P.nStages = pg.nStages; P.stageBytes = pg.stageBytes;
   P.offSt = pg.offSt; P.offSigt = pg.offSigt; P.offRecs = pg.offRecs;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
@@ -738,7 +791,7 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
 }  // namespace
 
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx) {
-  if (ctx->use_plan) return plan_geom(ctx->G).zpi;
+  if (ctx->use_plan) return plan_geom(ctx->G, ctx->plan_nh).zpi;
   int pairs_target = 512;
   if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairs_target = std::max(1, atoi(e));
   return std::max(1, pairs_target / ctx->G);
@@ -767,14 +820,15 @@ int umt_build_plan3d(umt_ctx *ctx) {
 
 static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
   const int threads = PLAN_LANES + 32;
-  const size_t smem = plan_geom(ctx->G).smemBytes;
-  UMT_CUDA(ctx, cudaFuncSetAttribute(sweep3d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = plan_geom(ctx->G, ctx->plan_nh).smemBytes;
+  void (*kern)(Sweep3DParams) = ctx->plan_nh == 2 ? sweep3d_plan_kernel<2> : sweep3d_plan_kernel<1>;
+  UMT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep3d_plan_kernel, threads, smem));
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweep3d_plan_kernel does not fit on an SM");
   if (const char *e = getenv("UMT_PLAN_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
   int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
-  sweep3d_plan_kernel<<<grid, threads, smem, ctx->stream>>>(P);
+  kern<<<grid, threads, smem, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   return UMT_OK;
 }

@@ -130,6 +130,7 @@ struct umt_ctx {
   int2 *d_zinfo = nullptr;             // (NA, nz) first corner row, zone | numCorner << 28 (what the TMA producer needs)
   bool use_plan = false;
   int plan_ncw = 4, plan_slow_zones = 0, zones_per_item = 1;
+  int plan_nh = 1;                     // 16-byte columns (pairs of groups) per lane in the plan kernel: 1 or 2
   int *d_cycleList = nullptr, *d_cycleAngle = nullptr;   // flattened (totalCycles): corner (0-based), angle
   int totalCycles = 0;
   double *d_cyclePsi = nullptr;
