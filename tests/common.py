@@ -174,10 +174,25 @@ def shared_boundaries(mesh):
     return [b for b in mesh.boundaries if b.bc_type == M.BC_SHARED]
 
 
+def angle_set_range(p, a):
+    """angle set of angle a as the reference forms it without reflecting boundaries (decomposeAngleSets.F90): 3-D every
+    angle its own set, 2-D one set per xi-level."""
+    if p.mesh.ndim == 3:
+        return a, a + 1
+    lev = p.q["level"]
+    a0, a1 = a, a + 1
+    while a0 > 0 and lev[a0 - 1] == lev[a]:
+        a0 -= 1
+    while a1 < p.NA and lev[a1] == lev[a]:
+        a1 += 1
+    return a0, a1
+
+
 def oracle_exchange_lists(problems):
     """findexit.F90:102-294 for every rank: lists[r][k][a] = (send elements, recv elements), 1-based boundary
-    elements of rank r's k-th shared boundary.  3-D: every angle is its own angle set, so NumAngles/2 = 0 and
-    the higher rank of a pair classifies (the lower rank negates what it receives)."""
+    elements of rank r's k-th shared boundary.  Of every angle set the lower rank of a pair classifies the first
+    NumAngles/2 angles, the higher rank the rest, and each side negates what it receives (3-D: sets of one angle, so
+    the higher rank classifies everything)."""
     out = []
     for r, p in enumerate(problems):
         per_b = []
@@ -187,20 +202,28 @@ def oracle_exchange_lists(problems):
             assert bq.n_elem == b.n_elem
             mine = p.geom["A_bdy"][b.first_elem - 1:b.first_elem - 1 + b.n_elem] @ p.omega.T      # (n, NA)
             theirs = q.geom["A_bdy"][bq.first_elem - 1:bq.first_elem - 1 + bq.n_elem] @ q.omega.T
-            t = np.sign(mine) if r > b.neighbor else -np.sign(theirs)
             per_a = []
             for a in range(p.NA):
+                a0, a1 = angle_set_range(p, a)
+                first_half = (a - a0) < (a1 - a0) // 2
+                i_decide = first_half if r < b.neighbor else not first_half
+                t = np.sign(mine[:, a]) if i_decide else -np.sign(theirs[:, a])
                 el = np.arange(b.first_elem, b.first_elem + b.n_elem)
-                per_a.append((el[t[:, a] > 0], el[t[:, a] < 0]))
+                per_a.append((el[t > 0], el[t < 0]))
             per_b.append(per_a)
         out.append(per_b)
     return out
 
 
-def oracle_multi_sweep_3d(problems, lists, savePsi, maxFluxIters=1, fluxTol=1e-6, state=None):
-    """SetSweep.F90 on every rank in lock step; returns (PhiTotal per rank, flux passes done, IncFlux per rank)."""
+def oracle_multi_sweep(problems, lists, savePsi, maxFluxIters=1, fluxTol=1e-6):
+    """SetSweep.F90 on every rank in lock step (psib lagged one flux pass); returns (PhiTotal per rank, flux passes done,
+    IncFlux per rank, one bin per comm set: angle in 3-D, xi-level in 2-D)."""
     N = len(problems)
     NA = problems[0].NA
+    nd = problems[0].mesh.ndim
+    bin_of = np.arange(NA) if nd == 3 else np.asarray(problems[0].q["level"]) - 1
+    nBins = int(bin_of.max()) + 1
+    sweep = oracle_sweep_3d if nd == 3 else oracle_sweep_rz
 
     def exit_currents():
         """setIncidentFlux.F90:84-108 on every rank: ExitFlux[r][k][a]"""
@@ -220,11 +243,11 @@ def oracle_multi_sweep_3d(problems, lists, savePsi, maxFluxIters=1, fluxTol=1e-6
     def incident(ex):
         inc = []
         for r, p in enumerate(problems):
-            v = np.zeros(NA)
+            v = np.zeros(nBins)
             for b in shared_boundaries(p.mesh):
                 q = problems[b.neighbor]
                 kq = [i for i, x in enumerate(shared_boundaries(q.mesh)) if x.neighbor == r][0]
-                v += ex[b.neighbor][kq]
+                np.add.at(v, bin_of, ex[b.neighbor][kq])
             inc.append(v)
         return inc
 
@@ -243,19 +266,22 @@ def oracle_multi_sweep_3d(problems, lists, savePsi, maxFluxIters=1, fluxTol=1e-6
                     send = lists[b.neighbor][kq][a][0]
                     assert len(recv) == len(send)
                     p.PsiB[a, recv - 1] = snap[b.neighbor][a, send - 1]
-        phis = [oracle_sweep_3d(p, savePsi) for p in problems]
+        phis = [sweep(p, savePsi) for p in problems]
         inc_old, inc = inc, incident(exit_currents())
         if savePsi:
             break
         notconv = 0
         for r in range(N):
-            for a in range(NA):
-                tot = inc[r][a]
-                rel = abs(inc[r][a] - inc_old[r][a]) / inc[r][a] if tot != 0.0 else 0.0
+            for bn in range(nBins):
+                tot = inc[r][bn]
+                rel = abs(inc[r][bn] - inc_old[r][bn]) / inc[r][bn] if tot != 0.0 else 0.0
                 notconv += not (rel <= fluxTol)
         if notconv == 0 or it >= maxFluxIters:
             break
     return phis, it, inc
+
+
+oracle_multi_sweep_3d = oracle_multi_sweep
 
 
 def run_local_group(contexts, fn):

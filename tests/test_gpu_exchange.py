@@ -54,6 +54,35 @@ def test_lagged_exchange_matches_oracle(N, dims):
         c.close()
 
 
+@pytest.mark.parametrize("N,dims", [(2, (3, 3, 0)), (4, (3, 3, 0))])
+def test_lagged_exchange_rz(N, dims):
+    """BASELINE configs[1] shape: 2-D (r,z) tiled mesh, 2 x 2 domains; angle sets are xi-levels (the lower rank classifies the
+    first half of each level), one flux-convergence bin per level."""
+    problems = [T.make_problem_rz(M.tiled_mesh(dims, rank=r, size=N), 2, 2, 4, seed=100 + r) for r in range(N)]
+    ctxs = []
+    for p in problems:
+        ctx = T.gpu_context_rz(p)
+        for b in T.shared_boundaries(p.mesh):
+            ctx.add_shared_boundary(b.neighbor, b.first_elem, b.n_elem)
+        ctxs.append(ctx)
+    teton.connect_local(ctxs)
+    T.run_local_group(ctxs, lambda r, c: c.build_exchange())
+    lists = T.oracle_exchange_lists(problems)
+    _check_lists(problems, ctxs, lists)
+    nBins = int(problems[0].q["level"].max())
+    for save, iters in ((False, 1), (False, 4), (True, 2)):
+        phis, it_ref, inc_ref = T.oracle_multi_sweep(problems, lists, save, iters, 1e-6)
+        its = T.run_local_group(ctxs, lambda r, c: c.sweep(save, iters, 1e-6))
+        assert its == [it_ref] * N
+        for r, (p, ctx) in enumerate(zip(problems, ctxs)):
+            assert T.relerr(ctx.download_phi(), phis[r]) <= TOL
+            assert T.mixed_err(ctx.download_psib(), p.PsiB, TOL) <= 1.0
+            inc, _old = ctx.incident_flux(nBins)
+            assert np.abs(inc - inc_ref[r]).max() <= 1e-12 * max(np.abs(inc_ref[r]).max(), 1e-300)
+    for c in ctxs:
+        c.close()
+
+
 def test_flux_iteration_converges_to_single_domain_solution():
     """With enough flux passes the decomposed problem reproduces the single-domain sweep: the exchange
     moves the right rows to the right corners.  box mesh 4x4x8 split 1x1x2 vs the same mesh on one domain."""

@@ -24,6 +24,8 @@
 namespace {
 
 constexpr int MAXC2 = 8;   // corners per zone (quads: 4; general polygons up to 8)
+constexpr int RZ_BLOCK = 64;   // threads per CTA = (zone, group) pairs per work item: small items keep the per-plane latency low
+                               // (measured on the 40x40-tile r-z mesh, G = 64: 64 pairs 24.5 ms, 128 pairs 36 ms)
 constexpr double FOURALPHA = 1.82;   // SweepUCBrz.F90:88
 
 struct SweepRZParams {
@@ -48,62 +50,106 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
   return v;
 }
 
-// SweepUCBrz.F90:103-243 for one (zone, group)
-__device__ __forceinline__ void solve_zone_rz(const SweepRZParams &P, int a, int zone0, int g) {
+// Everything of one (zone, group) solve that does not depend on other work items: loaded and computed while the CTA's
+// dependencies are still being resolved, so that after the wait only the upstream fluxes and PsiM remain to be read.
+template <int MC>
+struct ZoneStatic {
+  double Q[MC], srcInit[MC], sumArea[MC], volSig[MC], areaFac[MC];
+  double afp[MC][2], aez[MC][2], Rafp[MC][2], Raez[MC][2];
+  int row[MC][2], cez[MC][2];
+  int nCorner, c0;
+  double sig;
+};
+
+template <int MC>
+__device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, int zone0, int g, ZoneStatic<MC> &Z) {
   const int G = P.G, nc = P.nc;
   const double om0 = P.omega[2 * a], om1 = P.omega[2 * a + 1];
   const size_t slab = (size_t)(nc + P.nb) * G;
   const double *psiA = P.psi + (size_t)a * slab;
-  double *psi1A = P.psi1 + (size_t)a * slab;
-  double *psimL = P.psim + (size_t)P.level[a] * nc * G;
-  const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
   const double sig = P.sigt[(size_t)zone * G + g];
   const double fac = P.angDerivFac[a];
+  Z.nCorner = nCorner; Z.c0 = c0; Z.sig = sig;
+#pragma unroll
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      const size_t r = (size_t)(c0 + c) * G + g;
+      const double source = P.stotal[r] + P.tau * psiA[r];
+      const double area = P.Area[c0 + c], vol = P.Volume[c0 + c];
+      Z.Q[c] = source;
+      Z.srcInit[c] = vol * source;
+      Z.sumArea[c] = fac * area;
+      Z.volSig[c] = sig * vol;
+      Z.areaFac[c] = area * fac;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      const int cc = c0 + c;
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
+        const double *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
+        const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
+        const double aez = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
+        Z.afp[c][f] = afp; Z.aez[c][f] = aez;
+        Z.row[c][f] = P.cFP[cc * 2 + f];
+        Z.cez[c][f] = P.cEZ[cc * 2 + f];
+        Z.Rafp[c][f] = 0.0; Z.Raez[c][f] = 0.0;
+        if (afp < 0.0) {
+          Z.Rafp[c][f] = P.RadiusFP[cc * 2 + f] * afp;
+          Z.sumArea[c] -= Z.Rafp[c][f];
+        }
+        if (aez > 0.0) {
+          Z.Raez[c][f] = P.RadiusEZ[cc * 2 + f] * aez;
+          Z.sumArea[Z.cez[c][f]] += Z.Raez[c][f];
+        }
+      }
+    }
+  }
+}
 
-  double Q[MAXC2], src[MAXC2], sumArea[MAXC2];
-  int nxez[MAXC2], ez_exit[MAXC2][2];
-  double coefpsi[MAXC2][2];
-  for (int c = 0; c < nCorner; c++) {
-    const size_t r = (size_t)(c0 + c) * G + g;
-    const double source = P.stotal[r] + P.tau * psiA[r];
-    Q[c] = source;
-    src[c] = P.Volume[c0 + c] * source;
-    sumArea[c] = fac * P.Area[c0 + c];
-    nxez[c] = 0;
+// SweepUCBrz.F90:103-243 for one (zone, group), second half: upstream fluxes, closure, corner solves, PsiM, exits.
+// Accumulation order into src is the reference's (corner-major, face-minor).
+template <int MC>
+__device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int g, const ZoneStatic<MC> &Z) {
+  const int G = P.G, nc = P.nc;
+  const size_t slab = (size_t)(nc + P.nb) * G;
+  double *psi1A = P.psi1 + (size_t)a * slab;
+  double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  const int nCorner = Z.nCorner, c0 = Z.c0;
+  const double sig = Z.sig;
+  double src[MC], psifp[MC][2], pm[MC];
+#pragma unroll
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      src[c] = Z.srcInit[c];
+      pm[c] = psimL[(size_t)(c0 + c) * G + g];
+#pragma unroll
+      for (int f = 0; f < 2; f++) psifp[c][f] = Z.afp[c][f] < 0.0 ? __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]) : 0.0;
+    }
   }
   for (int c = 0; c < nCorner; c++) {
-    const int cc = c0 + c;
+    const double area = P.Area[c0 + c];
+#pragma unroll
     for (int f = 0; f < 2; f++) {
-      const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
-      const double *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
-      const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
-      const double aez = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
-      double psifp = 0.0;
-      if (afp < 0.0) {
-        const int row = P.cFP[cc * 2 + f];
-        psifp = __ldcg(&psi1A[(size_t)row * G + g]);
-        const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
-        sumArea[c] -= R_afp;
-        src[c] -= R_afp * psifp;
-      }
+      const double afp = Z.afp[c][f], aez = Z.aez[c][f];
+      if (afp < 0.0) src[c] -= Z.Rafp[c][f] * psifp[c][f];
       if (aez > 0.0) {
-        const double R = P.RadiusEZ[cc * 2 + f];
-        const int cez = P.cEZ[cc * 2 + f];
-        const double area = P.Area[cc];
-        ez_exit[c][nxez[c]] = cez;
-        coefpsi[c][nxez[c]] = R * aez;
-        nxez[c]++;
-        sumArea[cez] += R * aez;
+        const int cez = Z.cez[c][f];
         double sez;
         if (afp < 0.0) {
+          const double R = P.RadiusEZ[(c0 + c) * 2 + f];
           const double sigA = sig * area, sigA2 = sigA * sigA;
           const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
           const double gden = area * (4.0 * sigA * sigA2 + aez * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
-          sez = R * (area * gnum * (sig * psifp - Q[c]) + 0.5 * aez * gden * (Q[c] - Q[cez])) / (gnum + gden * sig);
+          sez = R * (area * gnum * (sig * psifp[c][f] - Z.Q[c]) + 0.5 * aez * gden * (Z.Q[c] - Z.Q[cez])) / (gnum + gden * sig);
         } else {
-          sez = 0.5 * R * aez * (Q[c] - Q[cez]) / sig;
+          sez = 0.5 * Z.Raez[c][f] * (Z.Q[c] - Z.Q[cez]) / sig;
         }
         src[c] += sez;
         src[cez] -= sez;
@@ -112,37 +158,38 @@ __device__ __forceinline__ void solve_zone_rz(const SweepRZParams &P, int a, int
   }
   for (int i = 0; i < nCorner; i++) {
     const int c = nextC[c0 + i];
-    const size_t r = (size_t)(c0 + c) * G + g;
-    const double p = (src[c] + P.Area[c0 + c] * fac * psimL[r]) / (sumArea[c] + sig * P.Volume[c0 + c]);
+    const double p = (src[c] + Z.areaFac[c] * pm[c]) / (Z.sumArea[c] + Z.volSig[c]);
     src[c] = p;   // src now holds the corner flux
-    for (int k = 0; k < nxez[c]; k++) src[ez_exit[c][k]] += coefpsi[c][k] * p;
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+      if (Z.aez[c][f] > 0.0) src[Z.cez[c][f]] += Z.Raez[c][f] * p;
   }
   // half-angle intensity for the next angle of the level; exiting boundary fluxes; finishing direction
   const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
   double *psi1N = psi1A + slab;   // slab of angle a+1 (only touched when it is a finishing direction)
+  const double w1 = P.tauW1[a], w2 = P.tauW2[a];
   for (int c = 0; c < nCorner; c++) {
     const int cc = c0 + c;
     const size_t r = (size_t)cc * G + g;
     const double p = src[c];
-    const double pm = starting ? p : P.tauW1[a] * p - P.tauW2[a] * psimL[r];
-    psimL[r] = pm;
+    const double pmn = starting ? p : w1 * p - w2 * pm[c];
+    psimL[r] = pmn;
     psi1A[r] = p;
-    if (fin) psi1N[r] = pm;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
+    if (fin) psi1N[r] = pmn;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
+#pragma unroll
     for (int f = 0; f < 2; f++) {
-      const int row = P.cFP[cc * 2 + f];
-      if (row >= nc) {
-        const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
-        const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
-        if (afp > 0.0) {
-          psi1A[(size_t)row * G + g] = p;             // PsiB(:,b,Angle)   <- Psi1(:,c)
-          if (fin) psi1N[(size_t)row * G + g] = pm;   // PsiB(:,b,Angle+1) <- PsiM(:,c)
-        }
+      const int row = Z.row[c][f];
+      if (row >= nc && Z.afp[c][f] > 0.0) {
+        psi1A[(size_t)row * G + g] = p;             // PsiB(:,b,Angle)   <- Psi1(:,c)
+        if (fin) psi1N[(size_t)row * G + g] = pmn;  // PsiB(:,b,Angle+1) <- PsiM(:,c)
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(128) sweeprz_kernel(SweepRZParams P) {
+// One (zone, group) pair per thread (items hold at most blockDim pairs): the static half runs before the dependency wait.
+template <int MC>
+__global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
   __shared__ int s_item;
   const int G = P.G;
   for (;;) {
@@ -151,19 +198,26 @@ __global__ void __launch_bounds__(128) sweeprz_kernel(SweepRZParams P) {
     const int it = s_item;
     if (it >= P.nItems) break;
     const WorkItem w = P.items[it];
-    if (threadIdx.x == 0) {
+    const int npairs = (w.zend - w.zbeg) * G;
+    const int zi = threadIdx.x / G, g = threadIdx.x - zi * G;
+    const bool fits = npairs <= (int)blockDim.x;   // false only for G > blockDim (one zone per item, several groups per thread)
+    const bool active = fits && (int)threadIdx.x < npairs;
+    ZoneStatic<MC> Z;
+    if (active) zone_static_rz<MC>(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + w.zbeg + zi], g, Z);
+    if (threadIdx.x == blockDim.x - 1) {   // the last thread polls (it is the one most likely to have no pair)
       if (w.wait_idx >= 0)
-        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(64);
+        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
       if (w.pad0 >= 0)   // second dependency: the previous angle of this xi-level (PsiM chain)
-        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(64);
+        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
     }
     __syncthreads();
-    const int *nextZ = P.nextZ + (size_t)w.angle * P.nz;
-    const int npairs = (w.zend - w.zbeg) * G;
-    for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
-      const int zi = idx / G, g = idx - zi * G;
-      solve_zone_rz(P, w.angle, nextZ[w.zbeg + zi], g);
-    }
+    if (active) zone_solve_rz<MC>(P, w.angle, g, Z);
+    if (!fits)
+      for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
+        const int z2 = idx / G, g2 = idx - z2 * G;
+        zone_static_rz<MC>(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + w.zbeg + z2], g2, Z);
+        zone_solve_rz<MC>(P, w.angle, g2, Z);
+      }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -259,11 +313,12 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   // Set%PsiM = 0 at the start of every flux pass (SetSweep.F90:94-96)
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * (size_t)ctx->nLevels * ctx->nc * ctx->G, ctx->stream));
+  void (*kern)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_kernel<4> : sweeprz_kernel<MAXC2>;
   int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweeprz_kernel, 128, 0));
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RZ_BLOCK, 0));
   if (occ < 1) occ = 1;
   const int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
-  sweeprz_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+  kern<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches += 1;
   return UMT_OK;

@@ -313,8 +313,8 @@ static int finalize_schedule(umt_ctx *ctx) {
   if (const char *e = getenv("UMT_PLAN_NH")) ctx->plan_nh = (atoi(e) == 2 && ctx->G % 4 == 0) ? 2 : 1;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
-  int pairsRZ = 256;
-  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairsRZ = std::max(1, atoi(e));
+  int pairsRZ = 64;   // one (zone, group) pair per thread of the 64-thread RZ CTA (sweeprz.cu RZ_BLOCK)
+  if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairsRZ = std::max(1, std::min(64, atoi(e)));
   const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, pairsRZ / ctx->G);
   ctx->zones_per_item = zpi;
   // Angles run in batches of K with staggered starts: a batch in its growing half overlaps the
