@@ -145,19 +145,136 @@ __device__ void gta_solve_zone(const GtaSweepParams &P, int a, int zone0) {
   }
 }
 
-__global__ void __launch_bounds__(64) gta_sweep_kernel(GtaSweepParams P) {
+// The same zone solve spread over one warp: lane = (corner, face slot) = (lane >> 2, lane & 3), so the 24 corner faces of a hex
+// load their area vectors, connectivity and upstream fluxes in parallel (coalesced: a zone's corners are contiguous), the closure
+// terms of all EZ faces are evaluated at once, each corner *pulls* the contribution of the neighbour across each of its EZ faces
+// (deterministic, no atomics), and only the 8 corner solves remain sequential (warp shuffles).  Needs three faces on every corner
+// and at most 8 corners; other zones take gta_solve_zone on lane 0.
+struct GtaZoneStatic {   // everything that does not depend on other work items (loaded before the dependency wait)
+  double afp, aez, vol, sigv, q, tsaVol;
+  int cez, row, zone0, nCorner, c0;
+  bool fast;
+};
+
+__device__ __forceinline__ void gta_zone_static(const GtaSweepParams &P, int a, int zone0, int lane, GtaZoneStatic &Z) {
+  const double om[3] = {P.omega[3 * a], P.omega[3 * a + 1], P.omega[3 * a + 2]};
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
+  const int c = lane >> 2, f = lane & 3;
+  Z.zone0 = zone0; Z.nCorner = nCorner; Z.c0 = c0;
+  const bool threeFaces = lane >= nCorner || P.nCFaces[c0 + lane] == 3;
+  Z.fast = nCorner <= MAXC && __all_sync(0xffffffffu, threeFaces);
+  Z.afp = 0.0; Z.aez = 0.0; Z.vol = 0.0; Z.sigv = 0.0; Z.q = 0.0; Z.tsaVol = 0.0; Z.cez = c < MAXC ? c : 0; Z.row = 0;
+  if (!Z.fast) return;
+  if (c < nCorner) {
+    const int cc = c0 + c;
+    const double t = P.tsa[cc];
+    Z.vol = P.Volume[cc];
+    Z.sigv = Z.vol * P.sigTotal[cc];
+    Z.q = P.sigtInv[cc] * t;
+    Z.tsaVol = Z.vol * t;
+    if (f < 3) {
+      Z.afp = dot3(om, P.Afp + ((size_t)cc * MAXCF + f) * 3);
+      Z.aez = dot3(om, P.Aez + ((size_t)cc * MAXCF + f) * 3);
+      Z.cez = P.cEZ[cc * MAXCF + f];
+      Z.row = P.cFP[cc * MAXCF + f];
+    }
+  }
+}
+
+__device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int a, int lane, const GtaZoneStatic &Z) {
+  const unsigned FULL = 0xffffffffu;
+  const int nc = P.nc;
+  double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
+  double *pincA = P.pinc + (size_t)a * nc;
+  const int nCorner = Z.nCorner, c0 = Z.c0;
+  const int c = lane >> 2, f = lane & 3;
+  const bool valid = c < nCorner && f < 3;
+  const double afp = Z.afp, aez = Z.aez, sigv = Z.sigv, q = Z.q;
+  const int cez = Z.cez;
+  const double psifp = (valid && afp < 0.0) ? __ldcg(&tpsi[Z.row]) : 0.0;
+  int myNext = lane < nCorner ? P.nextC[(size_t)a * nc + c0 + lane] : 0;
+  // the FP face "opposite" EZ face f is face (f+1) mod 3 of the same corner (SweepGreyUCBxyz.F90:263-270)
+  const int lop = (lane & ~3) | (f == 2 ? 0 : f + 1);
+  const double afpo = __shfl_sync(FULL, afp, lop), psio = __shfl_sync(FULL, psifp, lop);
+  const double qcez = __shfl_sync(FULL, q, cez << 2);
+  double dsrc = 0.0, dpinc = 0.0, dden = 0.0, sez = 0.0, ginc = 0.0;
+  if (valid) {
+    if (afp > 0.0) dden += afp;
+    else if (afp < 0.0) { dsrc -= afp * psifp; dpinc -= afp * psifp; }
+    if (aez > 0.0) {
+      dden += aez;
+      if (afpo < 0.0) {
+        const double area_opp = -afpo;
+        const double psi_opp = (-afpo * psio) / area_opp;
+        const double sigv2 = sigv * sigv;
+        const double gnum = aez * aez * (FOURALPHA * sigv2 + aez * (4.0 * sigv + 3.0 * aez));
+        const double gtau = gnum / (gnum + 4.0 * sigv2 * sigv2 + aez * sigv * (6.0 * sigv2 + 2.0 * aez * (2.0 * sigv + aez)));
+        sez = gtau * sigv * (psi_opp - q) + 0.5 * aez * (1.0 - gtau) * (q - qcez);
+        ginc = gtau * sigv * psi_opp;
+      } else {
+        sez = 0.5 * aez * (q - qcez);
+      }
+      dsrc += sez;
+      dpinc += ginc;
+    }
+  }
+  // pull what the neighbour across my EZ face pushes into my corner: its face whose cEZ points back at me
+  int fb = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int ck = __shfl_sync(FULL, cez, (cez << 2) | k);
+    if (ck == c) fb = k;
+  }
+  const int ln = (cez << 2) | fb;
+  const double sez_n = __shfl_sync(FULL, sez, ln), ginc_n = __shfl_sync(FULL, ginc, ln), aez_n = __shfl_sync(FULL, aez, ln);
+  if (valid && aez_n > 0.0) { dsrc -= sez_n; dpinc -= ginc_n; }
+  // per-corner sums over its face lanes (slot 3 carries zeros)
+  dsrc += __shfl_xor_sync(FULL, dsrc, 1); dsrc += __shfl_xor_sync(FULL, dsrc, 2);
+  dpinc += __shfl_xor_sync(FULL, dpinc, 1); dpinc += __shfl_xor_sync(FULL, dpinc, 2);
+  dden += __shfl_xor_sync(FULL, dden, 1); dden += __shfl_xor_sync(FULL, dden, 2);
+  double src = Z.tsaVol + dsrc, pinc = dpinc;
+  const double denom = sigv + dden;
+  // corner solves in nextC order, each pushed into its downstream corners (SweepGreyUCBxyz.F90:320-335)
+  for (int i = 0; i < nCorner; i++) {
+    const int cs = __shfl_sync(FULL, myNext, i);
+    const double d_c = __shfl_sync(FULL, denom, cs << 2);
+    const double psi = __shfl_sync(FULL, src, cs << 2) / d_c;
+    const double pin = __shfl_sync(FULL, pinc, cs << 2) / d_c;
+    if (c == cs) { src = psi; pinc = pin; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double ak = __shfl_sync(FULL, aez, (cs << 2) | k);
+      const int tk = __shfl_sync(FULL, cez, (cs << 2) | k);
+      if (ak > 0.0 && c == tk && c != cs) { src += ak * psi; pinc += ak * pin; }
+    }
+  }
+  if (c < nCorner && f == 0) { tpsi[c0 + c] = src; pincA[c0 + c] = pinc; }
+  if (valid && Z.row >= nc && afp > 0.0) tpsi[Z.row] = src;   // PsiB(b, Angle) <- tPsi
+}
+
+constexpr int GTA_WARPS = 8;   // warps per CTA = zones per work item
+
+__global__ void __launch_bounds__(GTA_WARPS * 32) gta_sweep_kernel(GtaSweepParams P) {
   __shared__ int s_item;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
     __syncthreads();
     const int it = s_item;
     if (it >= P.nItems) break;
     const WorkItem w = P.items[it];
-    if (threadIdx.x == 0 && w.wait_idx >= 0)
-      while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(32);
+    const int zi = w.zbeg + warp;
+    const bool active = zi < w.zend;
+    GtaZoneStatic Z;
+    if (active) gta_zone_static(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + zi], lane, Z);
+    if (threadIdx.x == blockDim.x - 1 && w.wait_idx >= 0)
+      while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
     __syncthreads();
-    const int *nextZ = P.nextZ + (size_t)w.angle * P.nz;
-    for (int zi = w.zbeg + threadIdx.x; zi < w.zend; zi += blockDim.x) gta_solve_zone(P, w.angle, nextZ[zi]);
+    if (active) {
+      if (Z.fast) gta_zone_solve_warp(P, w.angle, lane, Z);
+      else if (lane == 0) gta_solve_zone(P, w.angle, Z.zone0);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -492,9 +609,9 @@ int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
   P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc;
   int occ = 0;
-  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gta_sweep_kernel, 64, 0));
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gta_sweep_kernel, GTA_WARPS * 32, 0));
   const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), g.nItems));
-  gta_sweep_kernel<<<grid, 64, 0, ctx->stream>>>(P);
+  gta_sweep_kernel<<<grid, GTA_WARPS * 32, 0, ctx->stream>>>(P);
   UMT_CUDA(ctx, cudaGetLastError());
   gta_phiinc_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(g.d_pinc, g.d_weight, g.nAng, nc, g.d_phiInc);
   if (nb > 0)
@@ -568,7 +685,7 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   std::vector<int> h_nextZ((size_t)g.nAng * nz);
   std::vector<unsigned char> h_nextC((size_t)g.nAng * nc);
   std::vector<WorkItem> items;
-  const int zpi = 64;
+  const int zpi = GTA_WARPS;   // one zone per warp of the sweep CTA
   std::vector<std::vector<int>> start(g.nAng), nIt(g.nAng);
   for (int a = 0; a < g.nAng; a++) {
     std::copy(g.nextZ[a].begin(), g.nextZ[a].end(), h_nextZ.begin() + (size_t)a * nz);
