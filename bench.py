@@ -119,6 +119,7 @@ def measured_peak():
 def cpu_sweep_rate(G, npolar, nazim, sample_dims, steps=1, warmup=0):
     from oracle import oracle as O
     from tests import common as T
+    fast = O.use_fast_build()   # -O3 -march=native build of the restatement, compiled on this machine
     m = M.tiled_mesh(sample_dims)
     p = T.make_problem_3d(m, npolar, nazim, G, driver_like=True)
     unknowns = m.ncornr * p.NA * G
@@ -129,7 +130,7 @@ def cpu_sweep_rate(G, npolar, nazim, sample_dims, steps=1, warmup=0):
     for _ in range(max(steps, 1)):
         T.oracle_sweep_3d(p, False, cores)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return unknowns / dt, cores, dt, f"3-D tiled mesh -d {sample_dims[0]},{sample_dims[1]},{sample_dims[2]} -G {G} P{npolar} A{nazim} ({unknowns:.3e} unknowns per sweep), same problem data, one full SetSweep+getPhiTotal"
+    return unknowns / dt, cores, dt, f"3-D tiled mesh -d {sample_dims[0]},{sample_dims[1]},{sample_dims[2]} -G {G} P{npolar} A{nazim} ({unknowns:.3e} unknowns per sweep), same problem data, one full SetSweep+getPhiTotal, oracle built {'-O3 -march=native -fopenmp' if fast else '-O2 -fopenmp -ffp-contract=off'}"
 
 
 def run_reference(args):

@@ -35,11 +35,24 @@ class _Mesh(C.Structure):
                [("BoundaryZone", c_bp), ("px", c_dp)]
 
 
+def use_fast_build() -> bool:
+    """bench.py's CPU legs: switch to the -O3 -march=native build of the same sources (built here, on the machine that runs
+    it).  Returns False (and keeps the strict build) if it cannot be built.  Must be called before the first lib()."""
+    global _LIB
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "fast"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _LIB = None
+        os.environ["UMT_ORACLE_LIB"] = os.path.join(_HERE, "_ref", "libumt_oracle_fast.so")
+        return True
+    except Exception:
+        return False
+
+
 def lib():
     global _LIB
     if _LIB is None:
         build()
-        _LIB = C.CDLL(os.path.join(_HERE, "libumt_oracle.so"))
+        _LIB = C.CDLL(os.environ.get("UMT_ORACLE_LIB") or os.path.join(_HERE, "libumt_oracle.so"))
         _LIB.orc_quad_xyz.restype = C.c_int
         _LIB.orc_quad_rz.restype = C.c_int
         _LIB.orc_snnext.restype = C.c_int
