@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/exp4_pytest.log 2>&1; tail -5 gpurun_out/exp4_pytest.log
+for v in default c2 c2w6; do
+  if [ $v = default ]; then unset UMT_LIB; else export UMT_LIB=$PWD/umt_b200/ab/libumtsweep_$v.so; fi
+  timeout 300 python tools/perf_sweep.py 20 128 2>&1 | tail -1
+done
+unset UMT_LIB
+UMT_PLAN_CANON=0 timeout 300 python tools/perf_sweep.py 20 128 2>&1 | tail -1

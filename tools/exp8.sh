@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/exp8_pytest.log 2>&1; tail -3 gpurun_out/exp8_pytest.log
+for v in default c2 c2w6 c1w8 c1w10 c1w12; do
+  if [ $v = default ]; then unset UMT_LIB; else export UMT_LIB=$PWD/umt_b200/ab/libumtsweep_$v.so; fi
+  timeout 300 python tools/perf_sweep.py 20 128 2>&1 | tail -1
+done

@@ -37,7 +37,7 @@ constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 
 struct Sweep3DParams {
   int nc, nb, nz, G, NA, nItems;
-  int wpe, nEngines, nStages, stageBytes, offSt, offSigt, offRecs;   // PlanGeom
+  int wpe, nEngines, nStages, stageBytes, offSt, offSigt, offRecs, zpi;   // PlanGeom
   double tau;
   const int *numCorner, *cOffSet, *nCFaces, *cFP /* 0-based row; >= nc: boundary */, *cEZ /* 0-based */;
   const double *Volume, *Afp, *Aez, *omega;
@@ -207,12 +207,144 @@ struct PlanBuildParams {
   const int *nextZ;
   const unsigned char *nextC;
   ZoneRec *recs;
-  int *nSlow;
+  int *nSlow;     // [0] zones on the slow path, [1] zones on the canonical (register-resident) path
+  int canon;      // try the canonical order
 };
 
 __device__ __forceinline__ double dot3_seq(const double *om, const double *A) {
   // DOT_PRODUCT order, no contraction: the signs decide incoming/outgoing exactly as on the host
   return __dadd_rn(__dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])), __dmul_rn(om[2], A[2]));
+}
+
+// The in-zone corner graph of a hexahedron swept in a generic direction is the cube DAG: one source corner,
+// its three neighbours, their three pairwise common neighbours, one sink.  "Canonical" solve order numbers
+// them 0 | 1 2 3 | 4 5 6 | 7 with 4 = common(1,2), 5 = common(1,3), 6 = common(2,3), which makes the
+// downstream position of every outgoing EZ face a compile-time constant (solve_zone_canon keeps the whole
+// zone in registers).  Any topological order of the DAG gives the reference's corner fluxes (only the order
+// in which the pushes into a corner are added differs from nextC's).
+__host__ __device__ constexpr int cn_nout(int p) { return p == 0 ? 3 : (p < 4 ? 2 : (p < 7 ? 1 : 0)); }
+__host__ __device__ constexpr int cn_dst(int p, int k) { return p == 0 ? 1 + k : (p == 1 ? 4 + k : (p == 2 ? (k == 0 ? 4 : 6) : (p == 3 ? 5 + k : 7))); }
+__host__ __device__ constexpr int cn_e0(int p) { return p == 0 ? 0 : (p == 1 ? 3 : (p == 2 ? 5 : (p == 3 ? 7 : 5 + p))); }
+
+// canonical order of the zone's corners from the signs of omega.A_ez, or false if the graph is not the cube DAG
+__device__ bool canonical_order(const PlanBuildParams &B, int c0, const double (&aezL)[MAXC][3], int (&order)[MAXC]) {
+  int out[MAXC][3], nout[MAXC], indeg[MAXC];
+  for (int c = 0; c < MAXC; c++) { nout[c] = 0; indeg[c] = 0; }
+  for (int c = 0; c < MAXC; c++)
+    for (int f = 0; f < 3; f++)
+      if (aezL[c][f] > 0.0) {
+        const int q = B.cEZ[(c0 + c) * 3 + f];
+        if (q < 0 || q >= MAXC) return false;
+        out[c][nout[c]++] = q; indeg[q]++;
+      }
+  int src = -1;
+  for (int c = 0; c < MAXC; c++)
+    if (indeg[c] == 0) { if (src >= 0) return false; src = c; }
+  if (src < 0 || nout[src] != 3) return false;
+  int n1[3] = {out[src][0], out[src][1], out[src][2]};
+  for (int i = 0; i < 3; i++)      // ascending local corner id: deterministic
+    for (int j = i + 1; j < 3; j++)
+      if (n1[j] < n1[i]) { const int t = n1[i]; n1[i] = n1[j]; n1[j] = t; }
+  for (int i = 0; i < 3; i++) if (indeg[n1[i]] != 1 || nout[n1[i]] != 2) return false;
+  auto common = [&](int x, int y) {
+    int r = -1, cnt = 0;
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) if (out[x][i] == out[y][j]) { r = out[x][i]; cnt++; }
+    return cnt == 1 ? r : -1;
+  };
+  const int m4 = common(n1[0], n1[1]), m5 = common(n1[0], n1[2]), m6 = common(n1[1], n1[2]);
+  if (m4 < 0 || m5 < 0 || m6 < 0 || m4 == m5 || m4 == m6 || m5 == m6) return false;
+  const int ms[3] = {m4, m5, m6};
+  for (int i = 0; i < 3; i++) if (indeg[ms[i]] != 2 || nout[ms[i]] != 1) return false;
+  const int sink = out[m4][0];
+  if (out[m5][0] != sink || out[m6][0] != sink || indeg[sink] != 3 || nout[sink] != 0) return false;
+  order[0] = src; order[1] = n1[0]; order[2] = n1[1]; order[3] = n1[2]; order[4] = m4; order[5] = m5; order[6] = m6; order[7] = sink;
+  return true;
+}
+
+// the record of one (zone, angle) with the corners taken in the order localc[]; false: the zone needs the slow path
+__device__ bool build_record(const PlanBuildParams &B, ZoneRec &R, const int NC, const int c0, const double (&om)[3], const int (&localc)[MAXC],
+                             const double (&afpL)[MAXC][3], const double (&aezL)[MAXC][3]) {
+  const int G = B.G;
+  for (int i = 0; i < MAXC; i++) {
+    R.nIn[i] = 0; R.nOut[i] = 0; R.crow[i] = c0 * G; R.coff[i] = 0; R.vol[i] = 0.0; R.sumArea[i] = 1.0;
+    for (int k = 0; k < 3; k++) { R.inOff[i][k] = 0; R.inAfp[i][k] = 0.0; R.exitOff[i][k] = 0; }
+  }
+  for (int k = 0; k < 12; k++) { R.edge[k].ainv = 0.0; R.edge[k].cp = 0.0; R.edge[k].ha = 0.0; R.edge[k].qoff = 0; R.edge[k].hasOpp = 0; }
+  unsigned exitMask = 0;
+  for (int p = 0; p < NC; p++) {
+    const int c = localc[p], cc = c0 + c;
+    double sa = 0.0;
+    for (int f = 0; f < 3; f++) {
+      const int row = B.cFP[cc * 3 + f];
+      R.exitOff[p][f] = row * G;
+      if (afpL[c][f] > 0.0) {
+        sa += afpL[c][f];
+        if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
+      }
+    }
+    for (int f = 0; f < 3; f++)
+      if (aezL[c][f] > 0.0) sa += aezL[c][f];
+    R.sumArea[p] = sa;
+    R.vol[p] = B.Volume[cc];
+    R.crow[p] = cc * G;
+    R.coff[p] = c * (G / 2) * 16;
+  }
+  // outgoing EZ faces grouped by upstream position, downstream position ascending
+  int slot = 0;
+  for (int p = 0; p < NC; p++) {
+    const int c = localc[p];
+    int nout = 0;
+    bool used[3] = {false, false, false};       // FP faces already placed in an incident slot
+    int slotFace[3] = {-1, -1, -1};
+    for (int q = p + 1; q < NC; q++) {
+      const int cq = localc[q];
+      int f = -1, fq = -1;
+      for (int k = 0; k < 3; k++) {
+        if (B.cEZ[(c0 + c) * 3 + k] == cq) { if (f >= 0) return false; f = k; }
+        if (B.cEZ[(c0 + cq) * 3 + k] == c) { if (fq >= 0) return false; fq = k; }
+      }
+      if (f < 0 && fq < 0) continue;
+      if (f < 0 || fq < 0) return false;
+      const bool sezFwd = aezL[c][f] > 0.0, sezBwd = aezL[cq][fq] > 0.0;
+      // downstream push (coefpsi) is decided by the lower local corner id, SweepUCBxyz.F90:168-179
+      const bool loIsP = c < cq;
+      const double alo = loIsP ? aezL[c][f] : aezL[cq][fq];
+      const bool pushFwd = loIsP ? alo > 0.0 : alo < 0.0;
+      const bool pushBwd = loIsP ? alo < 0.0 : alo > 0.0;
+      if (sezBwd || pushBwd || sezFwd != pushFwd) return false;
+      if (!sezFwd) continue;
+      if (slot >= 12 || nout >= 3) return false;
+      const double av = aezL[c][f];
+      const int ifp = (f + 1) % 3;             // the FP face "opposite" EZ face f (SweepUCBxyz.F90:187-194)
+      ZoneEdge &E = R.edge[slot];
+      E.ainv = 1.0 / av;
+      E.cp = alo > 0.0 ? alo : -alo;
+      E.ha = 0.5 * av;
+      E.qoff = cq * (G / 2) * 16;
+      E.hasOpp = afpL[c][ifp] < 0.0 ? 1 : 0;
+      if (E.hasOpp) { slotFace[nout] = ifp; used[ifp] = true; }   // incident slot k serves edge k
+      slot++; nout++;
+    }
+    R.nOut[p] = (unsigned char)nout;
+    // the other incident faces take the free slots
+    for (int f = 0; f < 3; f++) {
+      if (!(afpL[c][f] < 0.0) || used[f]) continue;
+      for (int k = 0; k < 3; k++)
+        if (slotFace[k] < 0) { slotFace[k] = f; used[f] = true; break; }
+    }
+    int nin = 0;
+    for (int k = 0; k < 3; k++)
+      if (slotFace[k] >= 0) {
+        const int f = slotFace[k];
+        R.inOff[p][k] = B.cFP[(c0 + c) * 3 + f] * G;
+        R.inAfp[p][k] = afpL[c][f];
+        nin = k + 1;
+      }
+    R.nIn[p] = (unsigned char)nin;
+  }
+  R.exitMask = exitMask;
+  if (exitMask) R.flags |= ZREC_HAS_EXIT;
+  return true;
 }
 
 // one thread per (angle, position in sweep order)
@@ -231,103 +363,40 @@ __global__ void __launch_bounds__(128) plan_build_kernel(PlanBuildParams B) {
   R.flags = (unsigned)(NC & 15);
   bool slow = zone0 < 0 || NC > MAXC;
   for (int c = 0; c < NC && !slow; c++) slow = B.nCFaces[c0 + c] != 3;
-  const unsigned char *nextC = B.nextC + (size_t)a * B.nc + c0;
-  const int G = B.G;
-  int pos[MAXC], localc[MAXC];
-  for (int c = 0; c < MAXC; c++) { pos[c] = -1; localc[c] = 0; }
-  for (int i = 0; i < MAXC; i++) {
-    R.nIn[i] = 0; R.nOut[i] = 0; R.crow[i] = c0 * G; R.coff[i] = 0; R.vol[i] = 0.0; R.sumArea[i] = 1.0;
-    for (int k = 0; k < 3; k++) { R.inOff[i][k] = 0; R.inAfp[i][k] = 0.0; R.exitOff[i][k] = 0; }
+  double afpL[MAXC][3], aezL[MAXC][3];   // by local corner
+  for (int c = 0; c < MAXC; c++)
+    for (int f = 0; f < 3; f++) { afpL[c][f] = 0.0; aezL[c][f] = 0.0; }
+  for (int c = 0; c < NC && !slow; c++)
+    for (int f = 0; f < 3; f++) {
+      afpL[c][f] = dot3_seq(om, B.Afp + ((size_t)(c0 + c) * 3 + f) * 3);
+      aezL[c][f] = dot3_seq(om, B.Aez + ((size_t)(c0 + c) * 3 + f) * 3);
+    }
+  int localc[MAXC];
+  if (!slow && NC == MAXC && B.canon && canonical_order(B, c0, aezL, localc) && build_record(B, R, NC, c0, om, localc, afpL, aezL)) {
+    // fast path needs exactly the static edge table
+    bool ok = true;
+    for (int p = 0; p < MAXC && ok; p++) {
+      ok = R.nOut[p] == cn_nout(p);
+      for (int k = 0; k < cn_nout(p) && ok; k++) ok = R.edge[cn_e0(p) + k].qoff == localc[cn_dst(p, k)] * (B.G / 2) * 16;
+    }
+    if (ok) { R.flags |= ZREC_CANON; atomicAdd(B.nSlow + 1, 1); return; }
+    R.exitMask = 0u; R.flags = (unsigned)(NC & 15);
   }
-  for (int k = 0; k < 12; k++) { R.edge[k].ainv = 0.0; R.edge[k].cp = 0.0; R.edge[k].ha = 0.0; R.edge[k].qoff = 0; R.edge[k].hasOpp = 0; }
+  // the schedule's own corner order (nextC)
+  const unsigned char *nextC = B.nextC + (size_t)a * B.nc + c0;
+  int pos[MAXC];
+  for (int c = 0; c < MAXC; c++) { pos[c] = -1; localc[c] = 0; }
   for (int i = 0; i < NC && !slow; i++) {
     const int c = nextC[i];
     if (c >= NC || pos[c] >= 0) slow = true; else pos[c] = i;
     localc[i] = c;
   }
-  double afp[MAXC][3], aez[MAXC][3];
-  unsigned exitMask = 0;
-  for (int p = 0; p < NC && !slow; p++) {
-    const int c = localc[p], cc = c0 + c;
-    double sa = 0.0;
-    for (int f = 0; f < 3; f++) {
-      afp[p][f] = dot3_seq(om, B.Afp + ((size_t)cc * 3 + f) * 3);
-      const int row = B.cFP[cc * 3 + f];
-      R.exitOff[p][f] = row * G;
-      if (afp[p][f] > 0.0) {
-        sa += afp[p][f];
-        if (row >= B.nc) exitMask |= 1u << (p * 3 + f);
-      }
-    }
-    for (int f = 0; f < 3; f++) {
-      aez[p][f] = dot3_seq(om, B.Aez + ((size_t)cc * 3 + f) * 3);
-      if (aez[p][f] > 0.0) sa += aez[p][f];
-    }
-    R.sumArea[p] = sa;
-    R.vol[p] = B.Volume[cc];
-    R.crow[p] = cc * G;
-    R.coff[p] = c * (G / 2) * 16;
-  }
-  // outgoing EZ faces grouped by upstream position, downstream position ascending
-  int slot = 0;
-  for (int p = 0; p < NC && !slow; p++) {
-    const int c = localc[p];
-    int nout = 0;
-    bool used[3] = {false, false, false};       // FP faces already placed in an incident slot
-    int slotFace[3] = {-1, -1, -1};
-    for (int q = p + 1; q < NC && !slow; q++) {
-      const int cq = localc[q];
-      int f = -1, fq = -1;
-      for (int k = 0; k < 3; k++) {
-        if (B.cEZ[(c0 + c) * 3 + k] == cq) { if (f >= 0) slow = true; f = k; }
-        if (B.cEZ[(c0 + cq) * 3 + k] == c) { if (fq >= 0) slow = true; fq = k; }
-      }
-      if (f < 0 && fq < 0) continue;
-      if (f < 0 || fq < 0) { slow = true; break; }
-      const bool sezFwd = aez[p][f] > 0.0, sezBwd = aez[q][fq] > 0.0;
-      // downstream push (coefpsi) is decided by the lower local corner id, SweepUCBxyz.F90:168-179
-      const bool loIsP = c < cq;
-      const double alo = loIsP ? aez[p][f] : aez[q][fq];
-      const bool pushFwd = loIsP ? alo > 0.0 : alo < 0.0;
-      const bool pushBwd = loIsP ? alo < 0.0 : alo > 0.0;
-      if (sezBwd || pushBwd || sezFwd != pushFwd) { slow = true; break; }
-      if (!sezFwd) continue;
-      if (slot >= 12 || nout >= 3) { slow = true; break; }
-      const double av = aez[p][f];
-      const int ifp = (f + 1) % 3;             // the FP face "opposite" EZ face f (SweepUCBxyz.F90:187-194)
-      ZoneEdge &E = R.edge[slot];
-      E.ainv = 1.0 / av;
-      E.cp = alo > 0.0 ? alo : -alo;
-      E.ha = 0.5 * av;
-      E.qoff = cq * (G / 2) * 16;
-      E.hasOpp = afp[p][ifp] < 0.0 ? 1 : 0;
-      if (E.hasOpp) { slotFace[nout] = ifp; used[ifp] = true; }   // incident slot k serves edge k
-      slot++; nout++;
-    }
-    R.nOut[p] = (unsigned char)nout;
-    // the other incident faces take the free slots
-    for (int f = 0; f < 3; f++) {
-      if (!(afp[p][f] < 0.0) || used[f]) continue;
-      for (int k = 0; k < 3; k++)
-        if (slotFace[k] < 0) { slotFace[k] = f; used[f] = true; break; }
-    }
-    int nin = 0;
-    for (int k = 0; k < 3; k++)
-      if (slotFace[k] >= 0) {
-        const int f = slotFace[k];
-        R.inOff[p][k] = B.cFP[(c0 + c) * 3 + f] * G;
-        R.inAfp[p][k] = afp[p][f];
-        nin = k + 1;
-      }
-    R.nIn[p] = (unsigned char)nin;
-  }
+  if (!slow) slow = !build_record(B, R, NC, c0, om, localc, afpL, aezL);
   if (slow) {
-    R.flags |= ZREC_SLOW;
+    R.exitMask = 0u;
+    R.flags = (unsigned)(NC & 15) | ZREC_SLOW;
     atomicAdd(B.nSlow, 1);
-    return;
   }
-  R.exitMask = exitMask;
-  if (exitMask) R.flags |= ZREC_HAS_EXIT;
 }
 
 // ---------------------------------------------------------------------------
@@ -398,17 +467,18 @@ __device__ __forceinline__ void st_keep(double *p, const V2 &v) {   // Psi1 rows
 }
 
 #ifndef PLAN_MINB
-#define PLAN_MINB 3            // CTAs per SM the plan kernel is compiled for (register cap 65536 / (160 * PLAN_MINB))
+#define PLAN_MINB 2            // CTAs per SM the plan kernel is compiled for (register cap 65536 / (192 * PLAN_MINB))
 #endif
 #ifndef PLAN_MINB2
 #define PLAN_MINB2 2           // same for the variant with 4 groups per lane (NH = 2)
 #endif
-constexpr int PLAN_MAX_STAGES = 8;
+constexpr int PLAN_MAX_STAGES = 12;
 constexpr int PLAN_ZMAX = 8;     // zones per item at most
 #ifndef PLAN_NCW_DEF
 #define PLAN_NCW_DEF 4
 #endif
 constexpr int PLAN_NCW = PLAN_NCW_DEF;      // consumer warps per CTA
+constexpr int PLAN_CTL_BYTES = 768;         // barriers + per-stage metadata ahead of the stages
 constexpr int PLAN_LANES = PLAN_NCW * 32;
 
 // How the consumer warps of a CTA are grouped for a given group count (host side, once per context).
@@ -438,25 +508,31 @@ static PlanGeom plan_geom(int G, int NH) {
   g.offRecs = g.offSigt + NH * LE * 16;
   g.stageBytes = (g.offRecs + g.zpi * (int)sizeof(ZoneRec) + 127) / 128 * 128;
   // as many landing stages as still let the CTAs the kernel is compiled for share an SM (228 KB, 1 KB reserved per CTA)
-  const int budget = (228 * 1024) / (NH == 1 ? PLAN_MINB : PLAN_MINB2) - 2048;
-  g.nStages = std::max(g.nEngines + 1, std::min(g.nEngines + 3, (budget - 1024) / g.stageBytes));
+  const int budget = (228 * 1024) / (NH == 1 ? PLAN_MINB : PLAN_MINB2) - 1024;
+  g.nStages = std::min(PLAN_MAX_STAGES, std::max(g.nEngines + 1, std::min(g.nEngines + 3, (budget - PLAN_CTL_BYTES) / g.stageBytes)));
   if (const char *e = getenv("UMT_PLAN_STAGES")) g.nStages = std::max(g.nEngines + 1, std::min(PLAN_MAX_STAGES, atoi(e)));
-  g.smemBytes = 1024 + (size_t)g.nStages * g.stageBytes;
+  g.smemBytes = PLAN_CTL_BYTES + (size_t)g.nStages * g.stageBytes;
   return g;
 }
 
 struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
 
-// Shared memory: barriers and per-stage metadata in the first KB, then the stages.  One stage = one
+// Shared memory: barriers and per-stage metadata in the first PLAN_CTL_BYTES, then the stages.  One stage = one
 // work item: the TMA landing area of its Psi^n / STotal / Sigt rows, [zone][corner][G] (a zone's corner
 // rows are contiguous in HBM, so each is one bulk copy), and its plan records.  The consumers turn the
 // Psi^n area into Q and the STotal area into the running sources in place: a lane only ever touches
 // its own 16-byte column.
+constexpr int PLAN_RING = 32;    // completion-signal ring between the loader and the signaller warp
 struct PlanCtl {
   unsigned long long full[PLAN_MAX_STAGES], empty[PLAN_MAX_STAGES];
   StageMeta meta[PLAN_MAX_STAGES];
+  int sigRing[PLAN_RING];        // signal_idx of the CTA's item k at k % PLAN_RING
+  volatile int issuedCount;      // real items issued so far (loader -> signaller)
+  volatile int doneFlag;         // loader finished: issuedCount is final
+  volatile int nSignaled;        // items whose completion is published (signaller -> loader)
+  int pad;
 };
-static_assert(sizeof(PlanCtl) <= 1024, "PlanCtl must fit the control block");
+static_assert(sizeof(PlanCtl) <= PLAN_CTL_BYTES, "PlanCtl must fit the control block");
 
 __device__ __forceinline__ V2 lds_v2(unsigned addr) {
   V2 r;
@@ -626,116 +702,318 @@ __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec 
   }
 }
 
+// Psi1 rows of other zones are never re-read by the zone that stores them, so these stores need not order the
+// compiler's loads (no "memory" clobber): the incident rows of later corners may be fetched ahead of them.
+__device__ __forceinline__ void st_keep_free(double *p, const V2 &v) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(L2_EVICT_LAST));
+}
+__device__ __forceinline__ V2 ldcg_v2(const double *p) {
+  const double2 t = __ldcg(reinterpret_cast<const double2 *>(p));
+  V2 r; r.x = t.x; r.y = t.y;
+  return r;
+}
+
+// Zone solve for records in canonical cube order (ZREC_CANON): the downstream position of every EZ face is a
+// compile-time constant, so Q, the running sources and the corner fluxes of all eight corners stay in registers,
+// the code is one straight line (the three corners of a level are independent chains the scheduler interleaves)
+// and shared memory is only read: the landed Psi^n / STotal columns once each, plus the record fields.
+// An edge whose opposite FP face is not incident uses the same closure with N = 0, which is algebraically the
+// reference's sez = aez (Q - Q_cez) / (2 sigma) (SweepUCBxyz.F90:254-256).
 template <int NH>
-__global__ void __launch_bounds__(PLAN_LANES + 32, (NH == 1 ? PLAN_MINB : PLAN_MINB2)) sweep3d_plan_kernel(Sweep3DParams P) {
+__device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ psi1Ag,
+                                                 const unsigned char *__restrict__ colPsi, const unsigned char *__restrict__ colSt,
+                                                 const V2 (&sig)[NH], const unsigned hs, const int hg) {
+  V2 Q[MAXC][NH], S[MAXC][NH];
+  V2 pf[MAXC][3][NH];   // only the slots k < cn_nout(p) exist
+  // incident rows of the source corner and of the first level
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int nin = R->nIn[p];
+#pragma unroll
+    for (int k = 0; k < cn_nout(p); k++) {
+      const double *src = psi1Ag + R->inOff[p][k];
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        pf[p][k][h].x = 0.0; pf[p][k][h].y = 0.0;
+        if (k < nin) pf[p][k][h] = ldcg_v2(src + h * hg);
+      }
+    }
+  }
+  // Q = STotal + tau Psi^n, src = V Q (SweepUCBxyz.F90:119-126)
+#pragma unroll
+  for (int p = 0; p < MAXC; p++) {
+    const unsigned co = (unsigned)R->coff[p];
+    const double v = R->vol[p];
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      const V2 a = *reinterpret_cast<const V2 *>(colPsi + co + h * hs), b = *reinterpret_cast<const V2 *>(colSt + co + h * hs);
+      Q[p][h].x = fma(tau, a.x, b.x); Q[p][h].y = fma(tau, a.y, b.y);
+      S[p][h].x = v * Q[p][h].x; S[p][h].y = v * Q[p][h].y;
+    }
+  }
+  const unsigned flags = R->flags;
+#pragma unroll
+  for (int p = 0; p < MAXC; p++) {
+    if (p == 1) {   // second level's incident rows go in flight while the first level is solved
+#pragma unroll
+      for (int pp = 4; pp < 7; pp++) {
+        const int nin = R->nIn[pp];
+        const double *src = psi1Ag + R->inOff[pp][0];
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+          pf[pp][0][h].x = 0.0; pf[pp][0][h].y = 0.0;
+          if (0 < nin) pf[pp][0][h] = ldcg_v2(src + h * hg);
+        }
+      }
+    }
+    const double vp = R->vol[p];
+    V2 s[NH], sv[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) { s[h] = S[p][h]; sv[h].x = sig[h].x * vp; sv[h].y = sig[h].y * vp; }
+    // incident fluxes across FP faces (SweepUCBxyz.F90:139-161); unused slots carry afp = 0 and pf = 0
+#pragma unroll
+    for (int k = 0; k < cn_nout(p); k++) {
+      const double af = R->inAfp[p][k];
+#pragma unroll
+      for (int h = 0; h < NH; h++) { s[h].x = fma(-af, pf[p][k][h].x, s[h].x); s[h].y = fma(-af, pf[p][k][h].y, s[h].y); }
+    }
+    // an incident face that is not opposite to an outgoing EZ face (distorted zones only) sits in a slot past the edges
+    if (cn_nout(p) < 3 && (int)R->nIn[p] > cn_nout(p)) {
+#pragma unroll
+      for (int k = cn_nout(p); k < 3; k++)
+        if (k < (int)R->nIn[p]) {
+          const double af = R->inAfp[p][k];
+          const double *src = psi1Ag + R->inOff[p][k];
+#pragma unroll
+          for (int h = 0; h < NH; h++) {
+            const V2 v = ldcg_v2(src + h * hg);
+            s[h].x = fma(-af, v.x, s[h].x); s[h].y = fma(-af, v.y, s[h].y);
+          }
+        }
+    }
+    // EZ faces leaving this corner (SweepUCBxyz.F90:182-252), x = sigma V / aez (see plan_corner)
+    V2 sezk[3][NH];
+#pragma unroll
+    for (int k = 0; k < cn_nout(p); k++) {
+      const ZoneEdge &e = R->edge[cn_e0(p) + k];
+      const int q = cn_dst(p, k);
+      const double ainv = e.ainv, nmul = e.hasOpp ? 1.0 : 0.0;
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        const V2 po = pf[p][k][h];
+        {
+          const double x = sv[h].x * ainv;
+          const double N = nmul * fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+          const double num = fma(N, fma(sig[h].x, po.x, -Q[p][h].x), (0.5 * D) * (Q[p][h].x - Q[q][h].x));
+          sezk[k][h].x = (vp * num) * rcp_fast(fma(x, D, N));
+        }
+        {
+          const double x = sv[h].y * ainv;
+          const double N = nmul * fma(fma(FOURALPHA, x, 4.0), x, 3.0);
+          const double D = fma(fma(fma(4.0, x, 6.0), x, 4.0), x, 2.0);
+          const double num = fma(N, fma(sig[h].y, po.y, -Q[p][h].y), (0.5 * D) * (Q[p][h].y - Q[q][h].y));
+          sezk[k][h].y = (vp * num) * rcp_fast(fma(x, D, N));
+        }
+        s[h].x += sezk[k][h].x; s[h].y += sezk[k][h].y;
+      }
+    }
+    // corner flux, then its push into the downstream corners (SweepUCBxyz.F90:261-281)
+    const double sa = R->sumArea[p];
+    V2 psi[NH];
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      psi[h].x = s[h].x * rcp_fast(sa + sv[h].x);
+      psi[h].y = s[h].y * rcp_fast(sa + sv[h].y);
+      st_keep_free(psi1Ag + R->crow[p] + h * hg, psi[h]);
+    }
+#pragma unroll
+    for (int k = 0; k < cn_nout(p); k++) {
+      const int q = cn_dst(p, k);
+      const double cp = R->edge[cn_e0(p) + k].cp;
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        S[q][h].x = fma(cp, psi[h].x, S[q][h].x - sezk[k][h].x);
+        S[q][h].y = fma(cp, psi[h].y, S[q][h].y - sezk[k][h].y);
+      }
+    }
+    if (flags & ZREC_HAS_EXIT) {
+      const unsigned em = R->exitMask >> (p * 3);
+#pragma unroll
+      for (int f = 0; f < 3; f++)
+        if (em & (1u << f)) {
+#pragma unroll
+          for (int h = 0; h < NH; h++) st_keep_free(psi1Ag + R->exitOff[p][f] + h * hg, psi[h]);
+        }
+    }
+  }
+}
+
+#ifdef PLAN_MAXNREG   // explicit register cap instead of the CTAs-per-SM hint (A/B builds)
+#define PLAN_BOUNDS(NH) __maxnreg__(PLAN_MAXNREG)
+#else
+#define PLAN_BOUNDS(NH) __launch_bounds__(PLAN_LANES + 64, (NH == 1 ? PLAN_MINB : PLAN_MINB2))
+#endif
+template <int NH>
+__global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw);
-  unsigned char *stages = smem_raw + 1024;
+  unsigned char *stages = smem_raw + PLAN_CTL_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = P.G, Gv = G >> 1;   // lanes per zone
   const int NS = P.nStages, NE = P.nEngines, wpe = P.wpe;
   const size_t slab = (size_t)(P.nc + P.nb) * G;
   if (tid == 0) {
     for (int s = 0; s < NS; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], wpe); }
+    S.issuedCount = 0; S.doneFlag = 0; S.nSignaled = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
   if (warp == PLAN_NCW) {
-    // ---------------- producer warp ----------------
+    // ---------------- loader warp ----------------
     // Per CTA-local sequence number k (stage k % NS, engine k % NE):
-    //   issue(k):   ticket -> item -> TMA of its records and Psi^n/STotal/Sigt rows (needs item k-NS signalled);
-    //   release(k): the item's upstream plane is complete -> second arrival on full[k % NS];
-    //   signal(k):  its engine has arrived on empty[k % NS] -> publish the Psi1 rows (fence) and bump the
-    //               plane's completion counter, so no consumer warp ever waits on a fence.
+    //   issue(k):   next queued item -> TMA of its records and Psi^n/STotal/Sigt rows (needs item k-NS finished by its engine);
+    //   release(k): the item's upstream plane is complete -> second arrival on full[k % NS].
+    // The signaller warp (below) publishes completions, so neither this warp nor a consumer warp ever waits on a fence.
     // After the last ticket every engine gets one sentinel.
-    int nIssued = 0, nReleased = 0, nSignaled = 0, sentinels = -1;   // sentinels < 0: tickets remain
+    // Everything with global-memory latency on this warp's critical path is amortised: tickets are taken QB at a
+    // time, the lanes fetch the QB descriptors and their zones' info in parallel, the next batch is fetched (one
+    // dependent step per loop turn) while the current one is issued, a plane already seen complete is not polled
+    // again, and stage indices/parities are kept incrementally (no integer division).
+    int nIssued = 0, nReleased = 0, sentinels = -1;   // sentinels < 0: items remain
+    int kFill = 0, sFill = 0;                 // next sequence number to fill and its stage
+    unsigned parPrev = 1;                     // parity of empty[sFill] completed by the stage's previous occupant (item kFill - NS)
+    int sRel = 0;                             // stage of the next release
+    int lastOk = -1;                          // wait_idx last seen complete
     const unsigned rowBytes = (unsigned)G * 8u;
-    // the next item is fetched (ticket, descriptor, zone info) while the current ones are in flight
-    int prepT = 0;
-    WorkItem prepW;
-    int2 prepZ = make_int2(0, 0);
-    auto prepare = [&]() {
-      if (lane == 0) prepT = atomicAdd(&P.counters[0], 1);
-      prepT = __shfl_sync(0xffffffffu, prepT, 0);
-      if (prepT < P.nItems) {
-        prepW = P.items[prepT];
-        if (lane < prepW.zend - prepW.zbeg) prepZ = P.zinfo[(size_t)prepW.angle * P.nz + prepW.zbeg + lane];
+    const int zpi = P.zpi, QB = min(8, 32 / zpi);
+    const int myItem = lane / zpi, myZone = lane - myItem * zpi;
+    WorkItem qW, nW;                          // lane l: descriptor of item l / zpi of the current / next batch
+    int2 qZ = make_int2(0, 0), nZ = make_int2(0, 0);   // info of zone l % zpi of that item
+    int qCount = 0, qPos = 0, nCount = 0, nPhase = 0, nT = 0;
+    bool exhausted = false;                   // no tickets left beyond the next batch
+    qW.angle = qW.zbeg = qW.zend = qW.wait_idx = qW.wait_count = qW.signal_idx = 0; nW = qW;
+    auto fetch_step = [&]() {                 // one dependent step of fetching the next batch
+      if (nPhase == 0) {
+        if (lane == 0) nT = atomicAdd(&P.counters[0], QB);
+        nPhase = 1;
+      } else if (nPhase == 1) {
+        nT = __shfl_sync(0xffffffffu, nT, 0);
+        nCount = max(0, min(QB, P.nItems - nT));
+        if (myItem < nCount) nW = P.items[nT + myItem];
+        nPhase = 2;
+      } else if (nPhase == 2) {
+        if (myItem < nCount && myZone < nW.zend - nW.zbeg) nZ = P.zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
+        nPhase = 3;
       }
     };
-    prepare();
     for (;;) {
       bool progressed = false;
-      if (nSignaled < nReleased) {
-        const int s = nSignaled % NS;
-        int done = 0;
-        if (lane == 0) {
-          done = mbar_test(&S.empty[s], (nSignaled / NS) & 1);
-          if (done) {
-            __threadfence();
-            atomicAdd(&P.counters[1 + S.meta[s].signal_idx], 1);
-          }
-        }
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done) { nSignaled++; progressed = true; }
+      if (qPos == qCount && !exhausted) {     // current batch used up: take over the next one
+        while (nPhase < 3) fetch_step();
+        qW = nW; qZ = nZ; qCount = nCount; qPos = 0; nPhase = 0;
+        if (qCount < QB) exhausted = true;    // the ticket ran past the item list
       }
+      if (!exhausted && nPhase < 3) fetch_step();
       if (nReleased < nIssued) {
-        const int s = nReleased % NS;
         int ok = 1;
         if (lane == 0) {
-          const int wi = S.meta[s].wait_idx;
-          ok = wi < 0 || ld_acquire(&P.counters[1 + wi]) >= S.meta[s].wait_count;
-          if (ok) mbar_arrive(&S.full[s]);
+          const int wi = S.meta[sRel].wait_idx;
+          ok = wi < 0 || wi == lastOk || ld_acquire(&P.counters[1 + wi]) >= S.meta[sRel].wait_count;
+          if (ok) { mbar_arrive(&S.full[sRel]); lastOk = wi; }
         }
         ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (ok) { nReleased++; progressed = true; }
-      }
-      const int k = nIssued + (sentinels > 0 ? NE - sentinels : 0);   // next sequence number to fill
-      if (sentinels != 0 && (k < NS || nSignaled > k - NS || (sentinels > 0 && nSignaled == nIssued))) {
-        // stage k % NS is free (a sentinel's stage is never handed back, so once every real item is
-        // signalled the remaining stages are free as well)
-        const int s = k % NS;
-        if (sentinels < 0 && prepT >= P.nItems) sentinels = NE;
-        if (sentinels > 0) {
-          if (k < NS || nSignaled > k - NS || nSignaled == nIssued) {
-            if (lane == 0) { S.meta[s].n = -1; mbar_arrive(&S.full[s]); mbar_arrive(&S.full[s]); }
-            sentinels--;
-            progressed = true;
-          }
-        } else {
-          progressed = true;
-          const WorkItem w = prepW;
-          const int2 zi = prepZ;
-          const int n = w.zend - w.zbeg;
-          const size_t first = (size_t)w.angle * P.nz + w.zbeg;
-          unsigned bytes = 0;
-          if (lane < n) bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
-          bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
-          unsigned char *st = stages + (size_t)s * P.stageBytes;
-          if (lane == 0) {
-            S.meta[s].angle = w.angle; S.meta[s].n = n; S.meta[s].signal_idx = w.signal_idx;
-            S.meta[s].wait_idx = w.wait_idx; S.meta[s].wait_count = w.wait_count;
-            mbar_arrive_expect_tx(&S.full[s], bytes);
-            tma_load_1d_hint(st + P.offRecs, P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[s], L2_EVICT_FIRST);
-          }
-          __syncwarp();
-          if (lane < n) {
-            const unsigned nCorner = (unsigned)zi.y >> 28;
-            const int zone = zi.y & 0x0fffffff;
-            tma_load_1d_hint(st + (size_t)lane * MAXC * Gv * 16, P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
-            tma_load_1d_hint(st + P.offSt + (size_t)lane * MAXC * Gv * 16, P.stotal + (size_t)zi.x * G, rowBytes * nCorner, &S.full[s], L2_EVICT_FIRST);
-            tma_load_1d_hint(st + P.offSigt + (size_t)lane * Gv * 16, P.sigt + (size_t)zone * G, rowBytes, &S.full[s], L2_EVICT_FIRST);
-          }
-          nIssued++;
-          prepare();
+        if (ok) {
+          nReleased++; progressed = true;
+          if (++sRel == NS) sRel = 0;
         }
       }
-      if (sentinels == 0 && nSignaled == nIssued) break;
-      if (!progressed) {
-        if (nReleased == nIssued && nSignaled < nReleased) mbar_wait(&S.empty[nSignaled % NS], (nSignaled / NS) & 1);   // sleep on the oldest engine
-        else __nanosleep(128);
+      if (sentinels < 0 && exhausted && qPos == qCount) sentinels = NE;
+      if (sentinels != 0) {
+        int free_ = 1;
+        if (lane == 0) free_ = (kFill < NS || mbar_test(&S.empty[sFill], parPrev)) && (sentinels > 0 || nIssued - S.nSignaled < PLAN_RING);
+        free_ = __shfl_sync(0xffffffffu, free_, 0);
+        if (free_) {
+          if (sentinels > 0) {
+            if (lane == 0) { S.meta[sFill].n = -1; mbar_arrive(&S.full[sFill]); mbar_arrive(&S.full[sFill]); }
+            sentinels--;
+          } else {
+            const int srcLane = qPos * zpi;
+            WorkItem w;
+            w.angle = __shfl_sync(0xffffffffu, qW.angle, srcLane); w.zbeg = __shfl_sync(0xffffffffu, qW.zbeg, srcLane);
+            w.zend = __shfl_sync(0xffffffffu, qW.zend, srcLane); w.wait_idx = __shfl_sync(0xffffffffu, qW.wait_idx, srcLane);
+            w.wait_count = __shfl_sync(0xffffffffu, qW.wait_count, srcLane); w.signal_idx = __shfl_sync(0xffffffffu, qW.signal_idx, srcLane);
+            int2 zi;
+            zi.x = __shfl_sync(0xffffffffu, qZ.x, (srcLane + lane) & 31); zi.y = __shfl_sync(0xffffffffu, qZ.y, (srcLane + lane) & 31);
+            qPos++;
+            const int n = w.zend - w.zbeg;
+            const size_t first = (size_t)w.angle * P.nz + w.zbeg;
+            unsigned bytes = 0;
+            if (lane < n) bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
+            bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
+            unsigned char *st = stages + (size_t)sFill * P.stageBytes;
+            if (lane == 0) {
+              S.meta[sFill].angle = w.angle; S.meta[sFill].n = n;
+              S.meta[sFill].wait_idx = w.wait_idx; S.meta[sFill].wait_count = w.wait_count;
+              S.sigRing[nIssued & (PLAN_RING - 1)] = w.signal_idx;
+              __threadfence_block();
+              S.issuedCount = nIssued + 1;
+              mbar_arrive_expect_tx(&S.full[sFill], bytes);
+              tma_load_1d_hint(st + P.offRecs, P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[sFill], L2_EVICT_FIRST);
+            }
+            __syncwarp();
+            if (lane < n) {
+              const unsigned nCorner = (unsigned)zi.y >> 28;
+              const int zone = zi.y & 0x0fffffff;
+              tma_load_1d_hint(st + (size_t)lane * MAXC * Gv * 16, P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, rowBytes * nCorner, &S.full[sFill], L2_EVICT_FIRST);
+              tma_load_1d_hint(st + P.offSt + (size_t)lane * MAXC * Gv * 16, P.stotal + (size_t)zi.x * G, rowBytes * nCorner, &S.full[sFill], L2_EVICT_FIRST);
+              tma_load_1d_hint(st + P.offSigt + (size_t)lane * Gv * 16, P.sigt + (size_t)zone * G, rowBytes, &S.full[sFill], L2_EVICT_FIRST);
+            }
+            nIssued++;
+          }
+          progressed = true;
+          kFill++;
+          if (++sFill == NS) { sFill = 0; parPrev ^= 1u; }
+        }
       }
+      if (sentinels == 0 && nReleased == nIssued) break;
+      if (!progressed) __nanosleep(32);
+    }
+    if (lane == 0) { __threadfence_block(); S.doneFlag = 1; }
+    return;
+  }
+
+  if (warp == PLAN_NCW + 1) {
+    // ---------------- signaller warp ----------------
+    // signal(k): item k's engine has arrived on empty[k % NS] -> make its Psi1 rows visible device-wide (one fence for
+    // every item found complete) and bump the completion counter of each item's plane.
+    if (lane != 0) return;
+    int k = 0, sg = 0;
+    unsigned par = 0;
+    for (;;) {
+      const int done = S.doneFlag;
+      __threadfence_block();
+      const int issued = S.issuedCount;
+      if (k >= issued) {
+        if (done) break;
+        __nanosleep(64);
+        continue;
+      }
+      mbar_wait(&S.empty[sg], par);            // the oldest unpublished item
+      int m = 1, s2 = sg + 1;
+      unsigned p2 = par;
+      if (s2 == NS) { s2 = 0; p2 ^= 1u; }
+      while (k + m < issued && mbar_test(&S.empty[s2], p2)) {   // and whatever finished behind it
+        m++;
+        if (++s2 == NS) { s2 = 0; p2 ^= 1u; }
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      for (int j = 0; j < m; j++)
+        asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + S.sigRing[(k + j) & (PLAN_RING - 1)]]) : "memory");
+      k += m; sg = s2; par = p2;
+      S.nSignaled = k;
     }
     return;
   }
@@ -766,7 +1044,8 @@ __global__ void __launch_bounds__(PLAN_LANES + 32, (NH == 1 ? PLAN_MINB : PLAN_M
         V2 sig[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) sig[h] = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li + h * LZ) * 16);
-        solve_zone_plan<NH>(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
+        if (R->flags & ZREC_CANON) solve_zone_canon<NH>(tau, R, psi1Ag, st + col, st + P.offSt + col, sig, hs, hg);
+        else solve_zone_plan<NH>(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
       }
     }
     __syncwarp();
@@ -779,7 +1058,7 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.tau = ctx->tau;
   const PlanGeom pg = plan_geom(ctx->G, ctx->plan_nh);
   P.wpe = pg.wpe; P.nEngines = pg.nEngines; P.nStages = pg.nStages; P.stageBytes = pg.stageBytes;
-  P.offSt = pg.offSt; P.offSigt = pg.offSigt; P.offRecs = pg.offRecs;
+  P.offSt = pg.offSt; P.offSigt = pg.offSigt; P.offRecs = pg.offRecs; P.zpi = pg.zpi;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
@@ -803,23 +1082,27 @@ int umt_build_plan3d(umt_ctx *ctx) {
   if (ctx->d_recs) { cudaFree(ctx->d_recs); ctx->d_recs = nullptr; }
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_recs, n * sizeof(ZoneRec)));
   int *d_nslow = nullptr;
-  UMT_CUDA(ctx, cudaMalloc((void **)&d_nslow, sizeof(int)));
-  UMT_CUDA(ctx, cudaMemset(d_nslow, 0, sizeof(int)));
+  UMT_CUDA(ctx, cudaMalloc((void **)&d_nslow, 2 * sizeof(int)));
+  UMT_CUDA(ctx, cudaMemset(d_nslow, 0, 2 * sizeof(int)));
   PlanBuildParams B;
   B.nc = ctx->nc; B.nb = ctx->nb; B.nz = ctx->nz; B.NA = ctx->NA; B.G = ctx->G;
   B.numCorner = ctx->d_numCorner; B.cOffSet = ctx->d_cOffSet; B.nCFaces = ctx->d_nCFaces; B.cFP = ctx->d_cFP; B.cEZ = ctx->d_cEZ;
   B.Volume = ctx->d_Volume; B.Afp = ctx->d_Afp; B.Aez = ctx->d_Aez; B.omega = ctx->d_omega;
   B.nextZ = ctx->d_nextZ; B.nextC = ctx->d_nextC; B.recs = ctx->d_recs; B.nSlow = d_nslow;
+  B.canon = 1;   // UMT_PLAN_CANON=0: every zone through the list-driven path (A/B runs, tests of that path)
+  if (const char *e = getenv("UMT_PLAN_CANON")) B.canon = atoi(e) != 0;
   plan_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(B);
   UMT_CUDA(ctx, cudaGetLastError());
-  UMT_CUDA(ctx, cudaMemcpyAsync(&ctx->plan_slow_zones, d_nslow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  int h_n[2] = {0, 0};
+  UMT_CUDA(ctx, cudaMemcpyAsync(h_n, d_nslow, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->plan_slow_zones = h_n[0]; ctx->plan_canon_zones = h_n[1];
   cudaFree(d_nslow);
   return UMT_OK;
 }
 
 static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
-  const int threads = PLAN_LANES + 32;
+  const int threads = PLAN_LANES + 64;   // consumers + loader warp + signaller warp
   const size_t smem = plan_geom(ctx->G, ctx->plan_nh).smemBytes;
   void (*kern)(Sweep3DParams) = ctx->plan_nh == 2 ? sweep3d_plan_kernel<2> : sweep3d_plan_kernel<1>;
   UMT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

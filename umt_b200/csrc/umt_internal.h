@@ -20,7 +20,7 @@ struct WorkItem {       // one chunk of one hyperplane of one angle
 // Plan record of one (zone, angle) for the 3-D plan kernel (sweep3d.cu): the zone's corners
 // relabelled into solve order ("positions"), omega.A products, upstream rows and the
 // group-independent pieces of the corner-balance closure, as compact lists in position order.
-enum { ZREC_SLOW = 16u, ZREC_HAS_EXIT = 32u };   // flags bits above the corner count (bits 0..3)
+enum { ZREC_SLOW = 16u, ZREC_HAS_EXIT = 32u, ZREC_CANON = 64u };   // flags bits above the corner count (bits 0..3); CANON: see sweep3d.cu
 struct ZoneEdge {                // EZ face carrying flux from position p into a later position
   double ainv, cp, ha;           // 1/aez, coefpsi (SweepUCBxyz.F90:168-179), aez/2
   int qoff, hasOpp;              // byte offset of the downstream corner's column in the landing area; 1 if the opposite
@@ -129,7 +129,7 @@ struct umt_ctx {
   ZoneRec *d_recs = nullptr;           // (NA, nz) plan records in sweep order
   int2 *d_zinfo = nullptr;             // (NA, nz) first corner row, zone | numCorner << 28 (what the TMA producer needs)
   bool use_plan = false;
-  int plan_ncw = 4, plan_slow_zones = 0, zones_per_item = 1;
+  int plan_ncw = 4, plan_slow_zones = 0, plan_canon_zones = 0, zones_per_item = 1;
   int plan_nh = 1;                     // 16-byte columns (pairs of groups) per lane in the plan kernel: 1 or 2
   int *d_cycleList = nullptr, *d_cycleAngle = nullptr;   // flattened (totalCycles): corner (0-based), angle
   int totalCycles = 0;
