@@ -88,8 +88,8 @@ class ClockSampler(threading.Thread):
 
 def profiled_traffic_per_unknown():
     """dram__bytes_read.sum + dram__bytes_write.sum of sweep3d_plan_kernel divided by the unknowns of that launch, from the
-    committed ncu capture of this very workload (profiles/r01_sweep3d_d20_G128_ncu_summary.txt: -d 20,20,20 -G 128, 6.29e9 unknowns per launch)."""
-    p = os.path.join(ROOT, "profiles", "r01_sweep3d_d20_G128_ncu_summary.txt")
+    committed ncu capture of this very workload (profiles/r01b_sweep3d_d20_G128_ncu_summary.txt: -d 20,20,20 -G 128, 6.29e9 unknowns per launch)."""
+    p = os.path.join(ROOT, "profiles", "r01b_sweep3d_d20_G128_ncu_summary.txt")
     try:
         rd = wr = None
         for line in open(p):

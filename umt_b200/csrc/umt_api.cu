@@ -63,6 +63,14 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
     return UMT_ERR_CUDA;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  // L2 set-aside for evict_last lines: the sweep stores Psi1 rows with an evict_last hint so that the downstream zones find
+  // them in L2; without a persisting carve-out the hint has nothing to hold on to.  UMT_L2_PERSIST_MB overrides (0 = off).
+  {
+    size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);   // 64 MB of the 126 MB: more slows the streaming kernels
+    if (const char *ev = getenv("UMT_L2_PERSIST_MB")) want = std::min(want, (size_t)std::max(0, atoi(ev)) << 20);
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    if (getenv("UMT_VERBOSE")) fprintf(stderr, "umt: persisting L2 max %d MB, set-aside %zu MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
+  }
   *out = ctx;
   return UMT_OK;
 }
@@ -307,9 +315,9 @@ static int finalize_schedule(umt_ctx *ctx) {
   ctx->use_plan = ctx->ndim == 3 && ctx->maxcf == 3 && ctx->maxCorner <= 8 && ctx->G % 2 == 0 && ctx->G <= 256 &&
                   (double)(ctx->nc + ctx->nb) * ctx->G < 2147483647.0;   // record offsets are 32-bit elements
   if (const char *e = getenv("UMT_SWEEP3D")) if (!strcmp(e, "generic")) ctx->use_plan = false;
-  // two 16-byte columns (4 groups) per lane pay off for mid-size group counts (measured at -d 20: G=64 +20 %, G=32 +11 %,
-  // G=128 -33 %, G=16 -30 %); UMT_PLAN_NH overrides
-  ctx->plan_nh = (ctx->G % 4 == 0 && ctx->G >= 32 && ctx->G <= 64) ? 2 : 1;
+  // one 16-byte column (2 groups) per lane: with the register-resident canonical solve the 4-groups-per-lane variant spills
+  // (measured at -d 20: G=128 39.7 vs 88 ms, G=64 24.0 vs 52.5, G=32 16.3 vs 40.5, G=16 15.5 vs 20.1); UMT_PLAN_NH=2 selects it
+  ctx->plan_nh = 1;
   if (const char *e = getenv("UMT_PLAN_NH")) ctx->plan_nh = (atoi(e) == 2 && ctx->G % 4 == 0) ? 2 : 1;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
@@ -322,7 +330,7 @@ static int finalize_schedule(umt_ctx *ctx) {
   // the last few planes of every active angle stay L2-resident for their downstream zones.
   int K = NA;
   double stagger = 0.5;
-  if (ctx->use_plan) K = 8;
+  if (ctx->use_plan) K = 4;   // measured at -d 20 G=128: K=4 41.2 ms, K=8 42.5 ms, K=2 52 ms (too few ready items per level)
   if (const char *e = getenv("UMT_ANGLE_BATCH")) K = std::max(1, atoi(e));
   if (const char *e = getenv("UMT_BATCH_STAGGER")) stagger = std::max(0.0, atof(e));
   const int delta = std::max(1, (int)(stagger * maxHyp));
