@@ -409,3 +409,122 @@ def oracle_cycle_3d(p, dt, tr4floor):
     d_erad = e_rad - e_boc
     return dict(EnergyRadiation=e_rad, TrMax=float(trz.max()), PowerEscape=float(esc.sum()), RadPowerEscape=esc, trz=trz,
                 EnergyRadBOC=e_boc, EnergyCheck=dt * (0.0 - float(esc.sum())) - d_erad, phi=phi)
+
+
+# ---------------------------------------------------------------------------
+# multi-domain GTA (GTASweep.F90:66-76,139-146 exchange + GTASolver.F90 with its MPIAllReduce calls), lock step on every rank
+# ---------------------------------------------------------------------------
+def oracle_gta_exchange_lists(meshes, geoms, omega):
+    """findexit.F90:102-294 on the GTA angle set (3-D, no reflecting boundaries: sets of one angle, so of every pair the
+    higher rank classifies): lists[r][k][a] = (send, recv) positions a*nb+b (0-based) in the flattened (8, nbelem) PsiB."""
+    out = []
+    for r, m in enumerate(meshes):
+        per_b = []
+        for b in shared_boundaries(m):
+            mq = meshes[b.neighbor]
+            bq = [x for x in shared_boundaries(mq) if x.neighbor == r][0]
+            mine = geoms[r]["A_bdy"][b.first_elem - 1:b.first_elem - 1 + b.n_elem] @ omega.T
+            theirs = geoms[b.neighbor]["A_bdy"][bq.first_elem - 1:bq.first_elem - 1 + bq.n_elem] @ omega.T
+            per_a = []
+            for a in range(len(omega)):
+                t = np.sign(mine[:, a]) if r > b.neighbor else -np.sign(theirs[:, a])
+                el = a * m.nbelem + np.arange(b.first_elem - 1, b.first_elem - 1 + b.n_elem)
+                per_a.append((el[t > 0], el[t < 0]))
+            per_b.append(per_a)
+        out.append(per_b)
+    return out
+
+
+def oracle_gta_multi_solve(meshes, Ps, lists, Phis, geoms, epsPoint=1e-6, maxIters=21, epsGrey=0.1):
+    """GTASolver.F90:42-425 on N domains: Ps[r] is rank r's oracle GtaProblem (consumed), Phis[r] its PhiTotal (nc, ngr).
+    Returns (GreyCorrection per rank, nGreyIter, maxRelErrGrey).  With N = 1 this is orc_gta_solver restated in numpy."""
+    N = len(meshes)
+    nA = 8
+
+    def exchange(B):   # SendFlux/RecvFlux of every angle: exiting elements -> the neighbour's incident elements (lagged)
+        snap = [b.copy() for b in B]
+        for r, m in enumerate(meshes):
+            for k, sb in enumerate(shared_boundaries(m)):
+                kq = [i for i, x in enumerate(shared_boundaries(meshes[sb.neighbor])) if x.neighbor == r][0]
+                for a in range(nA):
+                    recv, send = lists[r][k][a][1], lists[sb.neighbor][kq][a][0]
+                    assert len(recv) == len(send)
+                    B[r].reshape(-1)[recv] = snap[sb.neighbor].reshape(-1)[send]
+
+    def grey_sweep(B, X, withSource):
+        exchange(B)
+        for r in range(N):
+            Ps[r].grey_sweep(B[r], X[r], withSource)
+
+    def prod1(X):
+        return sum(float((X[r] * Ps[r].opac["GreySigScatVol"]).sum()) for r in range(N))
+
+    def prod(X, Y):
+        return sum(float((X[r] * Y[r] * Ps[r].opac["GreySigScatVol"]).sum()) for r in range(N))
+
+    zone_of = [np.repeat(np.arange(m.nzones), m.numCorner) for m in meshes]
+    vol = [g["Volume"] for g in geoms]
+    volz = [g["VolumeZone"] for g in geoms]
+    radE = [np.bincount(zone_of[r], weights=vol[r] * Phis[r].sum(axis=1), minlength=meshes[r].nzones) / volz[r] for r in range(N)]
+    for r in range(N):
+        Ps[r].init_tt()
+    corr = [np.zeros(m.ncornr) for m in meshes]
+    pzOld = [np.zeros(m.nzones) for m in meshes]
+    R = [np.zeros(m.ncornr) for m in meshes]
+    RB = [np.zeros((nA, m.nbelem)) for m in meshes]
+    n = 1
+    grey_sweep(RB, R, True)
+    D, DB = [x.copy() for x in R], [x.copy() for x in RB]
+    rrOld = prod1(R)
+    for r in range(N):
+        Ps[r].GreySource[:] = 0.0
+    err = 0.0
+    while True:
+        if abs(rrOld) < 1e-150:
+            if n <= 2:
+                corr = [x.copy() for x in R]
+            break
+        n += 2
+        A, AB = [x.copy() for x in D], [x.copy() for x in DB]
+        grey_sweep(AB, A, False)
+        A = [D[r] - A[r] for r in range(N)]
+        AB = [DB[r] - AB[r] for r in range(N)]
+        dAd = prod1(A)
+        if abs(dAd) < 1e-150:
+            break
+        alpha = rrOld / dAd
+        R = [R[r] - alpha * A[r] for r in range(N)]
+        RB = [RB[r] - alpha * AB[r] for r in range(N)]
+        AS, ASB = [x.copy() for x in R], [x.copy() for x in RB]
+        grey_sweep(ASB, AS, False)
+        AS = [R[r] - AS[r] for r in range(N)]
+        ASB = [RB[r] - ASB[r] for r in range(N)]
+        oNum, oDen = prod(AS, R), prod(AS, AS)
+        if abs(oDen) < 1e-150 or abs(oNum) < 1e-150:
+            corr = [corr[r] + alpha * D[r] for r in range(N)]
+            break
+        om = oNum / oDen
+        corr = [corr[r] + alpha * D[r] + om * R[r] for r in range(N)]
+        R = [R[r] - om * AS[r] for r in range(N)]
+        RB = [RB[r] - om * ASB[r] for r in range(N)]
+        rr = prod1(R)
+        beta = (rr * alpha) / (rrOld * om)
+        D = [R[r] + beta * (D[r] - om * A[r]) for r in range(N)]
+        DB = [RB[r] + beta * (DB[r] - om * AB[r]) for r in range(N)]
+        err = 0.0
+        for r in range(N):   # local error norms, then MPIAllReduce(max)
+            pz = np.bincount(zone_of[r], weights=vol[r] * corr[r], minlength=meshes[r].nzones) / volz[r]
+            ez = pz - pzOld[r]
+            phiNew = radE[r] + pz
+            errL2, phiL2 = float((volz[r] * ez * ez).sum()), float((volz[r] * phiNew * phiNew).sum())
+            nzm = phiNew != 0.0
+            relPoint = float(np.abs(ez[nzm] / phiNew[nzm]).max()) if nzm.any() else 0.0
+            relL2 = np.sqrt(abs(errL2 / phiL2)) if phiL2 != 0.0 else 0.0
+            err = max(err, relPoint, relL2)
+            pzOld[r] = pz
+        if (err < epsPoint or n >= maxIters) and err < epsGrey:
+            break
+        if n >= 100 * maxIters:
+            raise RuntimeError("oracle_gta_multi_solve: not converging")
+        rrOld = rr
+    return corr, n, err

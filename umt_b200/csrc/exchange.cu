@@ -36,6 +36,7 @@ struct UmtTransport {
   virtual int exchange(umt_ctx *ctx, const std::vector<const void *> &sendPtr, const std::vector<size_t> &sendBytes,
                        const std::vector<void *> &recvPtr, const std::vector<size_t> &recvBytes) = 0;
   virtual int allreduce_max(umt_ctx *ctx, int *d_value) = 0;   // in place, device int
+  virtual int allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) = 0;   // in place, device doubles; op 0 sum, 1 max
 };
 
 namespace {
@@ -93,6 +94,10 @@ struct NcclTransport : UmtTransport {
     UMT_NCCL(ctx, g_nccl.AllReduce(d_value, d_value, 1, ncclInt32, ncclMax, comm, ctx->stream));
     return UMT_OK;
   }
+  int allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) override {
+    UMT_NCCL(ctx, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, op ? ncclMax : ncclSum, comm, ctx->stream));
+    return UMT_OK;
+  }
 };
 
 // Contexts of one process acting as ranks 0..n-1 (each driven by its own host thread).
@@ -103,6 +108,7 @@ struct LocalGroup {
   unsigned long generation = 0;
   std::vector<umt_ctx *> members;
   int redux = 0;
+  std::vector<double> fbuf;   // (n ranks, count) staging of allreduce_f64
   int refs = 0;
   void barrier() {
     std::unique_lock<std::mutex> lk(m);
@@ -151,6 +157,27 @@ struct LocalTransport : UmtTransport {
     if (ctx->myRank == 0) { std::lock_guard<std::mutex> lk(grp->m); grp->redux = 0; }
     grp->barrier();
     UMT_CUDA(ctx, cudaMemcpyAsync(d_value, &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UMT_OK;
+  }
+  int allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) override {
+    std::vector<double> v(n);
+    UMT_CUDA(ctx, cudaMemcpyAsync(v.data(), d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+      std::lock_guard<std::mutex> lk(grp->m);
+      if (grp->fbuf.size() < (size_t)grp->n * n) grp->fbuf.resize((size_t)grp->n * n);
+    }
+    grp->barrier();   // everybody sees the buffer at its final size
+    { std::lock_guard<std::mutex> lk(grp->m); std::copy(v.begin(), v.end(), grp->fbuf.begin() + (size_t)ctx->myRank * n); }
+    grp->barrier();
+    for (int i = 0; i < n; i++) {   // rank order: every rank gets the same bits
+      double a = grp->fbuf[i];
+      for (int r = 1; r < grp->n; r++) { const double b = grp->fbuf[(size_t)r * n + i]; a = op ? std::max(a, b) : a + b; }
+      v[i] = a;
+    }
+    grp->barrier();   // nobody overwrites the buffer while another rank still reads it
+    UMT_CUDA(ctx, cudaMemcpyAsync(d_vals, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UMT_OK;
   }
@@ -268,8 +295,10 @@ int need_abdy(umt_ctx *ctx) {
 
 void umt_exchange_release(umt_ctx *ctx) {
   for (auto &s : ctx->shared) {
-    void *p[] = {s.d_send_row, s.d_recv_row, s.d_send_coef, s.d_chunks, s.d_partial, s.d_nChunksOfAngle, s.d_sendbuf, s.d_recvbuf};
+    void *p[] = {s.d_send_row, s.d_recv_row, s.d_send_coef, s.d_chunks, s.d_partial, s.d_nChunksOfAngle, s.d_sendbuf, s.d_recvbuf,
+                 s.d_gsend, s.d_grecv, s.d_gsendbuf, s.d_grecvbuf};
     for (void *q : p) if (q) cudaFree(q);
+    s.d_gsend = s.d_grecv = nullptr; s.d_gsendbuf = s.d_grecvbuf = nullptr;
     s.d_send_row = s.d_recv_row = nullptr; s.d_send_coef = nullptr; s.d_chunks = nullptr; s.d_partial = nullptr;
     s.d_nChunksOfAngle = nullptr; s.d_sendbuf = s.d_recvbuf = nullptr;
   }
@@ -620,4 +649,103 @@ extern "C" int umt_set_flux_floor(umt_ctx *ctx, double floorFlux) {
   if (!ctx) return UMT_ERR_ARG;
   ctx->fluxFloor = floorFlux;
   return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// grey (GTA) exchange: GTASweep.F90:139-146 with the restored communication order -- every angle's exiting PsiB
+// elements go to the neighbour's incident elements before the grey sweeps (lagged one grey sweep, one double per row)
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void gather_kernel(const double *__restrict__ src, const int *__restrict__ idx, double *__restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+__global__ void scatter_kernel(double *__restrict__ dst, const int *__restrict__ idx, const double *__restrict__ in, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = in[i];
+}
+}  // namespace
+
+// findexit.F90:128-287 for the GTA angle set (every S2 angle its own angle set without reflecting boundaries, so of each
+// pair of ranks the higher one classifies and the lower one negates what it receives).  Collective over the domains.
+int umt_gta_build_exchange(umt_ctx *ctx) {
+  if (ctx->shared.empty()) return UMT_OK;
+  if (!ctx->transport) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA on a decomposed mesh needs a communicator (umt_set_comm / umt_connect_local) before umt_gta_setup");
+  int r = need_abdy(ctx);
+  if (r) return r;
+  const GtaState &g = ctx->gta;
+  const int nA = g.nAng, nd = ctx->ndim, nb = ctx->nb;
+  const size_t nS = ctx->shared.size();
+  std::vector<std::vector<signed char>> mine(nS), theirs(nS);
+  std::vector<signed char *> dS(nS, nullptr), dR(nS, nullptr);
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  int rc = UMT_OK;
+  for (size_t k = 0; k < nS && !rc; k++) {
+    const SharedBdy &s = ctx->shared[k];
+    const size_t n = (size_t)s.n * nA;
+    mine[k].assign(n, 0);
+    if (ctx->myRank > s.neighbor)
+      for (int a = 0; a < nA; a++)
+        for (int b = 0; b < s.n; b++) {
+          double dot = 0.0;
+          for (int d = 0; d < nd; d++) dot += g.omega[(size_t)a * nd + d] * ctx->h_Abdy[(size_t)(s.first + b) * nd + d];
+          mine[k][(size_t)a * s.n + b] = dot < 0.0 ? -1 : (dot > 0.0 ? 1 : 0);
+        }
+    if (cudaMalloc((void **)&dS[k], n) != cudaSuccess || cudaMalloc((void **)&dR[k], n) != cudaSuccess) { ctx->err = "cudaMalloc (GTA incident test)"; rc = UMT_ERR_CUDA; }
+    if (!rc) cudaMemcpy(dS[k], mine[k].data(), n, cudaMemcpyHostToDevice);
+    sp[k] = dS[k]; rp[k] = dR[k]; sb[k] = rb[k] = n;
+  }
+  if (!rc) rc = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "GTA incident test exchange failed"; rc = UMT_ERR_CUDA; }
+  for (size_t k = 0; k < nS; k++) {
+    if (!rc) { theirs[k].resize(mine[k].size()); cudaMemcpy(theirs[k].data(), dR[k], theirs[k].size(), cudaMemcpyDeviceToHost); }
+    if (dS[k]) cudaFree(dS[k]);
+    if (dR[k]) cudaFree(dR[k]);
+  }
+  if (rc) return rc;
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    const bool me = ctx->myRank > s.neighbor;
+    std::vector<int> snd, rcv;
+    for (int a = 0; a < nA; a++)
+      for (int b = 0; b < s.n; b++) {
+        const int t = me ? mine[k][(size_t)a * s.n + b] : -theirs[k][(size_t)a * s.n + b];
+        if (t < 0) rcv.push_back(a * nb + s.first + b);
+        else if (t > 0) snd.push_back(a * nb + s.first + b);
+      }
+    s.gsend_n = snd.size(); s.grecv_n = rcv.size();
+    if ((r = upload(ctx, &s.d_gsend, snd))) return r;
+    if ((r = upload(ctx, &s.d_grecv, rcv))) return r;
+    if (s.d_gsendbuf) cudaFree(s.d_gsendbuf);
+    if (s.d_grecvbuf) cudaFree(s.d_grecvbuf);
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_gsendbuf, sizeof(double) * std::max<size_t>(s.gsend_n, 1)));
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_grecvbuf, sizeof(double) * std::max<size_t>(s.grecv_n, 1)));
+  }
+  return UMT_OK;
+}
+
+int umt_gta_exchange(umt_ctx *ctx, double *d_PsiB) {
+  if (ctx->shared.empty()) return UMT_OK;
+  const size_t nS = ctx->shared.size();
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    if (!s.d_gsend) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA exchange lists not built (umt_gta_setup after the shared boundaries and the communicator)");
+    if (s.gsend_n) gather_kernel<<<(unsigned)((s.gsend_n + 255) / 256), 256, 0, ctx->stream>>>(d_PsiB, s.d_gsend, s.d_gsendbuf, (int)s.gsend_n);
+    sp[k] = s.d_gsendbuf; rp[k] = s.d_grecvbuf; sb[k] = sizeof(double) * s.gsend_n; rb[k] = sizeof(double) * s.grecv_n;
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  int r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (r) return r;
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    if (s.grecv_n) scatter_kernel<<<(unsigned)((s.grecv_n + 255) / 256), 256, 0, ctx->stream>>>(d_PsiB, s.d_grecv, s.d_grecvbuf, (int)s.grecv_n);
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}
+
+int umt_allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) {
+  if (ctx->nRanks <= 1 || !ctx->transport) return UMT_OK;
+  return ctx->transport->allreduce_f64(ctx, d_vals, n, op);
 }

@@ -596,6 +596,7 @@ void zone_params(umt_ctx *ctx, ZoneParams &Z, double *P) {
 int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nb = ctx->nb, rows = nc + nb;
+  TRY(umt_gta_exchange(ctx, d_PsiB));   // SendFlux / RecvFlux of every angle (GTASweep.F90:139-146): lagged one grey sweep
   gta_tsa_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(d_P, g.d_sigScat, g.d_greySource, 1.0 / (4.0 * PI), g.d_tsaSource, nc);
   UMT_CUDA(ctx, cudaMemsetAsync(g.d_tpsi, 0, sizeof(double) * (size_t)rows * g.nAng, ctx->stream));
   if (nb > 0)
@@ -638,6 +639,7 @@ int device_dot(umt_ctx *ctx, const double *x, const double *y, double *result) {
   GtaState &g = ctx->gta;
   dot_partial_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(x, y, g.d_sigScatVol, ctx->nc, g.d_red);
   sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
+  TRY(umt_allreduce_f64(ctx, g.d_red + 3 * RED_BLOCKS, 1, 0));   // MPIAllReduce(sum) of scat_prod / scat_prod1
   UMT_CUDA(ctx, cudaMemcpyAsync(result, g.d_red + 3 * RED_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return UMT_OK;
@@ -725,6 +727,7 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   TRY(dalloc(ctx, &g.d_radEnergy, nz)); TRY(dalloc(ctx, &g.d_pzOld, nz)); TRY(dalloc(ctx, &g.d_volZone, nz));
   TRY(dalloc(ctx, &g.d_red, 3 * RED_BLOCKS + 8));
   g.ready = true; g.have_opacity = false; g.tt_decomposed = false;
+  TRY(umt_gta_build_exchange(ctx));   // decomposed mesh: collective over the domains
   return UMT_OK;
 }
 
@@ -893,14 +896,13 @@ extern "C" int umt_gta_grey_sweep(umt_ctx *ctx, double *P, double *PsiB_gta, int
   return UMT_OK;
 }
 
-// GTASolver (rt/GTASolver.F90:42-425), single domain: BiCGSTAB on the grey corrections with the device-resident PhiTotal
+// GTASolver (rt/GTASolver.F90:42-425): BiCGSTAB on the grey corrections with the device-resident PhiTotal
 // and GreySource (umt_collision_rate / umt_gta_set_source).  GreyCorrection stays on the device (umt_gta_get_correction,
 // umt_add_grey_corrections).
 extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double epsGrey, int enforceHardMax, int *nGreyIterOut, double *maxRelErrOut) {
   if (!ctx) return UMT_ERR_ARG;
   TRY(need_gta(ctx));
   if (!ctx->d_phi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: no PhiTotal on the device");
-  if (!ctx->shared.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: multi-domain GTA exchange is not implemented yet");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nz = ctx->nz;
@@ -969,6 +971,12 @@ extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double
     if (std::isinf(e3[2])) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: grey solver encountered a NaN (iteration %d)", nGreyIter);
     const double relErrL2 = e3[1] != 0.0 ? std::sqrt(std::fabs(e3[0] / e3[1])) : 0.0;
     maxRelErrGrey = std::max(e3[2], relErrL2);
+    if (ctx->nRanks > 1 && ctx->transport) {   // MPIAllReduce(maxRelErrGrey, "max") (GTASolver.F90:380-381)
+      UMT_CUDA(ctx, cudaMemcpyAsync(g.d_red + 3 * RED_BLOCKS + 4, &maxRelErrGrey, sizeof(double), cudaMemcpyHostToDevice, st));
+      TRY(umt_allreduce_f64(ctx, g.d_red + 3 * RED_BLOCKS + 4, 1, 1));
+      UMT_CUDA(ctx, cudaMemcpyAsync(&maxRelErrGrey, g.d_red + 3 * RED_BLOCKS + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
+      UMT_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     if (enforceHardMax && nGreyIter >= maxIters) break;
     else if ((maxRelErrGrey < epsPoint || nGreyIter >= maxIters) && maxRelErrGrey < epsGrey) break;
     else if (nGreyIter >= 100 * maxIters) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: grey solver is not converging (%d iterations)", nGreyIter);

@@ -57,6 +57,10 @@ struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   std::vector<int> send_off, recv_off;                     // per-angle offsets (NA+1)
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
   size_t send_rows = 0, recv_rows = 0;
+  // grey (GTA) exchange: positions in the (8, nbelem) PsiB array of the exiting / incident elements, all angles concatenated
+  int *d_gsend = nullptr, *d_grecv = nullptr;
+  double *d_gsendbuf = nullptr, *d_grecvbuf = nullptr;
+  size_t gsend_n = 0, grecv_n = 0;
 };
 
 // grey transport acceleration state (gta.cu): 3-D, "new" GTA solver
@@ -209,3 +213,6 @@ int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vect
 int umt_exchange_tally(umt_ctx *ctx, double tol);
 int umt_exchange_begin_pass(umt_ctx *ctx);
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);
+int umt_gta_build_exchange(umt_ctx *ctx);                    // collective: GTA ListSend / ListRecv (findexit.F90 on the GTA angle set)
+int umt_gta_exchange(umt_ctx *ctx, double *d_PsiB);          // SendFlux / RecvFlux of GTASweep.F90:139-146 for all 8 angles
+int umt_allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op /* 0 sum, 1 max */);   // MPIAllReduce over the domains
