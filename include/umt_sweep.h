@@ -189,7 +189,7 @@ int umt_build_source(umt_ctx *ctx, const double *Siga, const double *Sigs, const
 /* GTA angle set (level-symmetric S2, 8 ordinates: rt/quadxyz.F90), its sweep order (rtorder/snnext) and device arrays.
    Needs full connectivity and geometry. */
 int umt_gta_setup(umt_ctx *ctx);
-int umt_gta_get_quadrature(umt_ctx *ctx, double *omega /* (3,8) */, double *weight /* (8) */);
+int umt_gta_get_quadrature(umt_ctx *ctx, double *omega /* (ndim,8) */, double *weight /* (8) */);
 /* GTA%GreySigTotal, GreySigScat, GreySigScatVol (ncornr) from the caller (GreySigtInv = 1/GreySigTotal) ... */
 int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, const double *GreySigScat,
                         const double *GreySigScatVol);

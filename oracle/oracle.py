@@ -244,13 +244,26 @@ class _Gta(C.Structure):
     _fields_ = [("M", C.POINTER(_Mesh)), ("nAng", C.c_int), ("nHyperPlanes", c_ip), ("zonesInPlane", c_ip), ("nextZ", c_ip),
                 ("nextC", c_ip), ("omega", c_dp), ("weight", c_dp), ("Volume", c_dp), ("A_fp", c_dp), ("A_ez", c_dp),
                 ("GreySigTotal", c_dp), ("GreySigtInv", c_dp), ("GreySigScat", c_dp), ("GreySigScatVol", c_dp),
-                ("GreySource", c_dp), ("TT", c_dp), ("wtiso", C.c_double)]
+                ("GreySource", c_dp), ("TT", c_dp), ("wtiso", C.c_double),
+                ("Area", c_dp), ("RadiusFP", c_dp), ("RadiusEZ", c_dp), ("angDerivFac", c_dp), ("quadTauW1", c_dp), ("quadTauW2", c_dp),
+                ("start", c_bp), ("finish", c_bp)]
 
 
 def gta_quad_xyz():
     omega, weight = np.zeros((8, 3)), np.zeros(8)
     lib().orc_gta_quad_xyz(_dp(omega), _dp(weight))
     return omega, weight
+
+
+def gta_quad_rz() -> Dict[str, np.ndarray]:
+    """the GTA angle set in r-z (level-symmetric S2: two xi-levels of start, mu<0, mu>0, finish) with its angular-derivative coefficients"""
+    NA = 8
+    q = dict(omega=np.zeros((NA, 2)), weight=np.zeros(NA), start=np.zeros(NA, np.uint8), finish=np.zeros(NA + 1, np.uint8),
+             level=np.zeros(NA, np.int32), angDerivFac=np.zeros(NA), quadTauW1=np.zeros(NA), quadTauW2=np.zeros(NA))
+    n = lib().orc_gta_quad_rz(_dp(q["omega"]), _dp(q["weight"]), _bp(q["start"]), _bp(q["finish"]), _ip(q["level"]),
+                              _dp(q["angDerivFac"]), _dp(q["quadTauW1"]), _dp(q["quadTauW2"]))
+    assert n == NA
+    return q
 
 
 def gta_set_opacity(om: OMesh, geom, tau, Siga, Sigs, Eta, Chi):
@@ -271,8 +284,9 @@ def collision_rate(om: OMesh, Eta, Siga, Sigs, PhiTotal, GreySource, residualFla
 class GtaProblem:
     """Keeps every array the C struct points at alive."""
 
-    def __init__(self, om: OMesh, geom, sched, omega, weight, opac, GreySource, wtiso):
-        self.om, self.geom, self.sched = om, geom, sched
+    def __init__(self, om: OMesh, geom, sched, omega, weight, opac, GreySource, wtiso, q=None):
+        """q: the r-z angle-set dict of gta_quad_rz() (2-D meshes)"""
+        self.om, self.geom, self.sched, self.q = om, geom, sched, q
         self.omega = np.ascontiguousarray(omega)
         self.weight = np.ascontiguousarray(weight)
         self.opac = {k: np.ascontiguousarray(v) for k, v in opac.items()}
@@ -287,10 +301,21 @@ class GtaProblem:
         for k in ("GreySigTotal", "GreySigtInv", "GreySigScat", "GreySigScatVol"):
             setattr(s, k, _dp(self.opac[k]))
         s.GreySource, s.TT, s.wtiso = _dp(self.GreySource), _dp(self.TT), wtiso
+        if q is not None:
+            s.Area, s.RadiusFP, s.RadiusEZ = _dp(geom["Area"]), _dp(geom["RadiusFP"]), _dp(geom["RadiusEZ"])
+            s.angDerivFac, s.quadTauW1, s.quadTauW2 = _dp(q["angDerivFac"]), _dp(q["quadTauW1"]), _dp(q["quadTauW2"])
+            s.start, s.finish = _bp(q["start"]), _bp(q["finish"])
         self.s = s
 
     def init_tt(self):
         o = self.opac
+        if self.q is not None:
+            q, g = self.q, self.geom
+            lib().orc_gta_init_tt_rz(self.om.ref, len(self.weight), _ip(self.sched["nextC"]), _dp(self.omega), _dp(self.weight), _bp(q["start"]),
+                                     _bp(q["finish"]), _dp(q["angDerivFac"]), _dp(q["quadTauW1"]), _dp(q["quadTauW2"]), _dp(g["Volume"]),
+                                     _dp(g["Area"]), _dp(g["A_fp"]), _dp(g["A_ez"]), _dp(g["RadiusFP"]), _dp(g["RadiusEZ"]),
+                                     _dp(o["GreySigTotal"]), _dp(self.TT))
+            return self.TT
         lib().orc_gta_init_tt(self.om.ref, len(self.weight), _dp(self.omega), _dp(self.weight), _dp(self.geom["Volume"]),
                               _dp(self.geom["A_fp"]), _dp(self.geom["A_ez"]), _dp(o["GreySigTotal"]), _dp(self.TT))
         return self.TT
@@ -307,6 +332,18 @@ class GtaProblem:
                                   _dp(self.omega[a]), C.c_double(self.weight[a]), _dp(self.geom["Volume"]), _dp(self.geom["A_fp"]),
                                   _dp(self.geom["A_ez"]), _dp(o["GreySigTotal"]), _dp(o["GreySigtInv"]), _dp(TsaSource), _dp(tPsi), _dp(pInc),
                                   _dp(PsiBa), _dp(PhiInc))
+        return tPsi, pInc
+
+    def sweep_angle_rz(self, a, TsaSource, PsiBa, PhiInc, tPsiM, tInc):
+        """SweepGreyUCBrz for angle a (not a finishing direction); tPsiM / tInc (nc) carry the half-angle values along the xi-level"""
+        m = self.om.m
+        tPsi, pInc = np.zeros(m.ncornr + m.nbelem), np.zeros(m.ncornr)
+        s, o, q, g = self.sched, self.opac, self.q, self.geom
+        lib().orc_gta_sweep_angle_rz(self.om.ref, int(s["nHyperPlanes"][a]), _ip(s["zonesInPlane"][a]), _ip(s["nextZ"][a]), _ip(s["nextC"][a]),
+                                     _dp(self.omega[a]), C.c_double(self.weight[a]), C.c_double(q["angDerivFac"][a]), C.c_double(q["quadTauW1"][a]),
+                                     C.c_double(q["quadTauW2"][a]), int(q["start"][a]), _dp(g["Volume"]), _dp(g["Area"]), _dp(g["A_fp"]),
+                                     _dp(g["A_ez"]), _dp(g["RadiusFP"]), _dp(g["RadiusEZ"]), _dp(o["GreySigTotal"]), _dp(o["GreySigtInv"]),
+                                     _dp(TsaSource), _dp(tPsi), _dp(pInc), _dp(tPsiM), _dp(tInc), _dp(PsiBa), _dp(PhiInc))
         return tPsi, pInc
 
     def solve(self, PhiTotal, epsPoint=1e-6, maxIters=21, epsGrey=0.1, enforceHardMax=False):

@@ -189,6 +189,50 @@ int orc_quad_rz(int npolar, int nazimuthal, double *omega /* (2,NA) */, double *
   return NA;
 }
 
+/* rtquad.F90:95-127 normalisation and start/finish flags, AngleSet_mod.F90:325-335 xi-levels, AngleCoef2D.F90 and
+   AngleSet_mod.F90:337-347 for any r-z ordinate set given level by level (same statements as the tail of orc_quad_rz; used for
+   the level-symmetric GTA set) */
+int orc_rz_angle_coefs(int NA, const double *omega, double *weight, unsigned char *start, unsigned char *finish, int *angleToLevel,
+                       double *alpha, double *tauc, double *angDerivFac, double *quadTauW1, double *quadTauW2) {
+  const double pi = 3.14159265358979323846;
+  rtquad_normalize(NA, 1.0 / (2.0 * pi), weight, start, finish);
+  int nLevels = 0;
+  for (int n = 0; n < NA; n++) { if (start[n]) nLevels++; angleToLevel[n] = nLevels; }
+  int a = 0;
+  while (a < NA) {
+    int a1 = a, lev = angleToLevel[a];
+    int a2 = a1; while (a2 + 1 < NA && angleToLevel[a2 + 1] == lev) a2++;
+    double weightLevel = 0.0, Phimh = pi, Mumh = omega[0];
+    for (int k = a1; k <= a2; k++) weightLevel += weight[k];
+    for (int k = a1; k <= a2; k++) {
+      if (start[k]) {
+        alpha[k] = 0.0; tauc[k] = 0.0;
+        if (k != a1) die("Mu not increasing in xi-level, AngleCoef2D");
+        Phimh = pi; Mumh = omega[2 * k];
+      } else if (finish[k]) {
+        alpha[k] = 0.0; tauc[k] = 0.0;
+      } else {
+        alpha[k] = alpha[k - 1] - weight[k] * omega[2 * k];
+        double Phiph = Phimh - weight[k] * pi / weightLevel;
+        double Muph = sqrt(1.0 - omega[2 * k + 1] * omega[2 * k + 1]) * cos(Phiph);
+        if (omega[2 * k] < Mumh || omega[2 * k] > Muph) die("Mu not between limits, AngleCoef2D");
+        tauc[k] = (omega[2 * k] - Mumh) / (Muph - Mumh);
+        Phimh = Phiph; Mumh = Muph;
+      }
+    }
+    a = a2 + 1;
+  }
+  for (int n = 0; n < NA; n++) {
+    if (start[n] || finish[n]) { angDerivFac[n] = 0.0; quadTauW1[n] = 1.0; quadTauW2[n] = 0.0; }
+    else {
+      angDerivFac[n] = omega[2 * n] + alpha[n] / (weight[n] * tauc[n]);
+      quadTauW1[n] = 1.0 / tauc[n];
+      quadTauW2[n] = (1.0 - tauc[n]) / tauc[n];
+    }
+  }
+  return NA;
+}
+
 /* ------------------------------------------------------------------ */
 /* Geometry: mods/Geometry_mod.F90:344-441, rt/geometryUCBxyz.F90,     */
 /* rt/volumeUCBxyz.F90, rt/geometryUCBrz.F90, rt/volumeUCBrz.F90        */

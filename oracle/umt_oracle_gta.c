@@ -12,6 +12,10 @@
  *   + snac/UpdateScalarIntensity.F90:11-170              -> orc_gta_grey_sweep
  *   rt/scat_prod.F90 / scat_prod1.F90, rt/GTASolver.F90:42-425 (BiCGSTAB) -> orc_gta_solver
  *   rt/addGreyCorrections.F90:70-91 (scalar part)        -> orc_add_grey_corrections
+ * and their r-z counterparts:
+ *   rt/quadrz.F90:82-160 (level-symmetric S2) + rtquad.F90:95-127 + AngleCoef2D.F90 + AngleSet_mod.F90:337-347 -> orc_gta_quad_rz
+ *   snac/SweepGreyUCBrz.F90:12-133,137-330 (KernelNew)   -> orc_gta_sweep_angle_rz
+ *   snac/InitSweepGreyUCBrz.F90:10-235                   -> orc_gta_init_tt_rz
  * Arrays are Fortran memory images with 1-based ids, as in umt_oracle.c.
  */
 #include <math.h>
@@ -282,7 +286,20 @@ typedef struct {
   double *GreySource;   /* (nc) */
   double *TT;           /* (maxCorner,nc) — decomposed in place by the first (withSource) sweep */
   double wtiso;
+  /* r-z only (M->ndim == 2): omega is (2,nAng), A_fp/A_ez are (2,2,nc) */
+  const double *Area, *RadiusFP, *RadiusEZ, *angDerivFac, *quadTauW1, *quadTauW2;
+  const unsigned char *start, *finish;
 } orc_gta;
+
+void orc_gta_sweep_angle_rz(const orc_mesh *M, int nHyperPlanes, const int *zonesInPlane, const int *nextZ, const int *nextC,
+                            const double *omega, double quadwt, double fac, double quadTauW1, double quadTauW2, int StartingDirection,
+                            const double *Volume, const double *Area, const double *A_fp, const double *A_ez, const double *RadiusFP,
+                            const double *RadiusEZ, const double *GreySigTotal, const double *GreySigtInv, const double *TsaSource,
+                            double *tPsi, double *pInc, double *tPsiM, double *tInc, double *PsiBa, double *PhiInc);
+void orc_gta_init_tt_rz(const orc_mesh *M, int nAng, const int *nextC, const double *omegas, const double *weights, const unsigned char *start,
+                        const unsigned char *finish, const double *angDerivFac, const double *quadTauW1, const double *quadTauW2,
+                        const double *Volume, const double *Area, const double *A_fp, const double *A_ez, const double *RadiusFP,
+                        const double *RadiusEZ, const double *GreySigTotal, double *TT);
 
 /* ScalarIntensityDecompose + ScalarIntensitySolve for one zone */
 static void scalar_intensity(const orc_gta *S, int zone, const double *PhiInc, double *P, int withSource) {
@@ -340,6 +357,18 @@ void orc_gta_grey_sweep(const orc_gta *S, double *PsiB, double *P, int withSourc
   double *TsaSource = malloc(sizeof(double) * nc), *PhiInc = calloc(nc, sizeof(double));
   double *tPsi = malloc(sizeof(double) * (nc + nb)), *pInc = malloc(sizeof(double) * nc);
   for (int c = 0; c < nc; c++) TsaSource[c] = S->wtiso * (S->GreySigScat[c] * P[c] + S->GreySource[c]);
+  if (M->ndim == 2) {
+    /* GTASweep.F90:113-119: tPsiM = tInc = 0, then every non-finishing angle in turn (:149-159) */
+    double *tPsiM = calloc(nc, sizeof(double)), *tInc = calloc(nc, sizeof(double));
+    for (int a = 0; a < S->nAng; a++) {
+      if (S->finish[a]) continue;
+      orc_gta_sweep_angle_rz(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
+                             S->nextC + (size_t)nc * a, S->omega + 2 * a, S->weight[a], S->angDerivFac[a], S->quadTauW1[a],
+                             S->quadTauW2[a], S->start[a], S->Volume, S->Area, S->A_fp, S->A_ez, S->RadiusFP, S->RadiusEZ,
+                             S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, tPsiM, tInc, PsiB + (size_t)nb * a, PhiInc);
+    }
+    free(tPsiM); free(tInc);
+  } else
   for (int a = 0; a < S->nAng; a++)
     orc_gta_sweep_angle(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
                         S->nextC + (size_t)nc * a, S->omega + 3 * a, S->weight[a], S->Volume, S->A_fp, S->A_ez,
@@ -379,7 +408,11 @@ int orc_gta_solver(orc_gta *S, int ngr, const double *PhiTotal, const double *Vo
     }
     radEnergy[zone - 1] = radEnergy[zone - 1] / VolumeZone[zone - 1];
   }
-  orc_gta_init_tt(M, nA, S->omega, S->weight, S->Volume, S->A_fp, S->A_ez, S->GreySigTotal, S->TT);
+  if (M->ndim == 2)
+    orc_gta_init_tt_rz(M, nA, S->nextC, S->omega, S->weight, S->start, S->finish, S->angDerivFac, S->quadTauW1, S->quadTauW2, S->Volume,
+                       S->Area, S->A_fp, S->A_ez, S->RadiusFP, S->RadiusEZ, S->GreySigTotal, S->TT);
+  else
+    orc_gta_init_tt(M, nA, S->omega, S->weight, S->Volume, S->A_fp, S->A_ez, S->GreySigTotal, S->TT);
   for (int c = 0; c < nc; c++) GreyCorrection[c] = 0.0;
   int nGreyIter = 1;
   orc_gta_grey_sweep(S, RB, R, 1);
@@ -454,4 +487,193 @@ void orc_add_grey_corrections(int ngr, int nc, const double *GreyCorrection, con
   for (int c = 1; c <= nc; c++)
     for (int g = 1; g <= ngr; g++)
       F2(PhiTotal, g, c, ngr) = F2(PhiTotal, g, c, ngr) + GreyCorrection[c - 1] * F2(Chi, g, c, ngr);
+}
+
+/* ------------------------------------------------------------------ */
+/* r-z grey sweeps                                                     */
+/* ------------------------------------------------------------------ */
+int orc_rz_angle_coefs(int NA, const double *omega, double *weight, unsigned char *start, unsigned char *finish, int *angleToLevel,
+                       double *alpha, double *tauc, double *angDerivFac, double *quadTauW1, double *quadTauW2);   /* umt_oracle.c */
+
+/* the GTA angle set in r-z: level-symmetric S2 (quadrz.F90:82-160 with norder = 2: one pair of xi-levels, one ordinate per
+   quadrant, dircos 0.577350269189625, weight 1), each level = starting direction, mu < 0, mu > 0, finishing direction */
+int orc_gta_quad_rz(double *omega /* (2,8) */, double *weight, unsigned char *start, unsigned char *finish, int *angleToLevel,
+                    double *angDerivFac, double *quadTauW1, double *quadTauW2) {
+  const double pi = 3.14159265358979323846, halfpi = 0.5 * pi;
+  const double xilev = 0.577350269189625, mu = 0.577350269189625, wgt = 1.0;
+  int m = 0;
+  for (int half = 0; half < 2; half++) {
+    const double sxi = half == 0 ? -xilev : xilev;
+    omega[2 * m] = -sqrt(1.0 - xilev * xilev); omega[2 * m + 1] = sxi; weight[m] = 0.0; m++;
+    omega[2 * m] = -mu; omega[2 * m + 1] = sxi; weight[m] = halfpi * wgt; m++;
+    omega[2 * m] = mu; omega[2 * m + 1] = sxi; weight[m] = halfpi * wgt; m++;
+    omega[2 * m] = sqrt(1.0 - xilev * xilev); omega[2 * m + 1] = sxi; weight[m] = 0.0; m++;
+  }
+  double alpha[8], tauc[8];
+  return orc_rz_angle_coefs(8, omega, weight, start, finish, angleToLevel, alpha, tauc, angDerivFac, quadTauW1, quadTauW2);
+}
+
+static double dot2(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1]; }
+
+/* SweepGreyUCBrz + SweepGreyUCBrzKernelNew for one (non-finishing) angle */
+void orc_gta_sweep_angle_rz(const orc_mesh *M, int nHyperPlanes, const int *zonesInPlane, const int *nextZ, const int *nextC,
+                            const double *omega, double quadwt, double fac, double quadTauW1, double quadTauW2, int StartingDirection,
+                            const double *Volume, const double *Area, const double *A_fp, const double *A_ez, const double *RadiusFP,
+                            const double *RadiusEZ, const double *GreySigTotal, const double *GreySigtInv, const double *TsaSource,
+                            double *tPsi, double *pInc, double *tPsiM, double *tInc, double *PsiBa, double *PhiInc) {
+  const int nc = M->ncornr, nb = M->nbelem;
+  for (int c = 0; c < nc; c++) { tPsi[c] = 0.0; pInc[c] = 0.0; }
+  for (int ib = 0; ib < nb; ib++) tPsi[nc + ib] = PsiBa[ib];
+  int ndoneZ = 0;
+  for (int hp = 1; hp <= nHyperPlanes; hp++) {
+    int nzones = zonesInPlane[hp - 1];
+    for (int ii = 1; ii <= nzones; ii++) {
+      int zone = abs(nextZ[ndoneZ + ii - 1]);
+      int nCorner = M->numCorner[zone - 1], c0 = M->cOffSet[zone - 1];
+      int nxBdy = 0, nxez[MAXC + 1] = {0}, ez_exit[3][MAXC + 1], bdy_exit[2][2 * MAXC + 1];
+      double denom[MAXC + 1], coefpsi[3][MAXC + 1], Sigt[MAXC + 1], Q[MAXC + 1], src[MAXC + 1];
+      for (int c = 1; c <= nCorner; c++) {
+        Q[c] = GreySigtInv[c0 + c - 1] * TsaSource[c0 + c - 1];
+        src[c] = Volume[c0 + c - 1] * TsaSource[c0 + c - 1] + fac * Area[c0 + c - 1] * tPsiM[c0 + c - 1];
+        Sigt[c] = GreySigTotal[c0 + c - 1];
+        denom[c] = Sigt[c] * Volume[c0 + c - 1] + fac * Area[c0 + c - 1];
+        pInc[c0 + c - 1] = fac * Area[c0 + c - 1] * tInc[c0 + c - 1];
+      }
+      for (int c = 1; c <= nCorner; c++) {
+        for (int cface = 1; cface <= 2; cface++) {
+          double afp = dot2(omega, &F3(A_fp, 1, cface, c0 + c, 2, 2));
+          double aez = dot2(omega, &F3(A_ez, 1, cface, c0 + c, 2, 2));
+          int cfp = F2(M->cFP, cface, c0 + c, 2);
+          if (afp < 0.0) {
+            double R_afp = F2(RadiusFP, cface, c0 + c, 2) * afp;
+            denom[c] = denom[c] - R_afp;
+            src[c] = src[c] - R_afp * tPsi[cfp - 1];
+            pInc[c0 + c - 1] = pInc[c0 + c - 1] - R_afp * tPsi[cfp - 1];
+          } else if (cfp > nc) {
+            nxBdy++; bdy_exit[0][nxBdy] = c; bdy_exit[1][nxBdy] = cfp - nc;
+          }
+          if (aez > 0.0) {
+            double R = F2(RadiusEZ, cface, c0 + c, 2);
+            int cez = F2(M->cEZ, cface, c0 + c, 2);
+            nxez[c]++; ez_exit[nxez[c]][c] = cez; coefpsi[nxez[c]][c] = R * aez;
+            denom[cez] = denom[cez] + R * aez;
+            double sez;
+            if (afp < 0.0) {
+              double sigA = Sigt[c] * Area[c0 + c - 1], sigA2 = sigA * sigA;
+              double gnum = aez * aez * (fouralpha * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+              double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+              sez = R * (gtau * sigA * (tPsi[cfp - 1] - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - Q[cez]));
+              src[c] = src[c] + sez;
+              src[cez] = src[cez] - sez;
+              pInc[c0 + c - 1] = pInc[c0 + c - 1] + R * gtau * sigA * tPsi[cfp - 1];
+              pInc[c0 + cez - 1] = pInc[c0 + cez - 1] - R * gtau * sigA * tPsi[cfp - 1];
+            } else {
+              sez = 0.5 * R * aez * (Q[c] - Q[cez]);
+              src[c] = src[c] + sez;
+              src[cez] = src[cez] - sez;
+            }
+          }
+        }
+      }
+      for (int i = 1; i <= nCorner; i++) {
+        int c = nextC[c0 + i - 1];
+        tPsi[c0 + c - 1] = src[c] / denom[c];
+        pInc[c0 + c - 1] = pInc[c0 + c - 1] / denom[c];
+        for (int cface = 1; cface <= nxez[c]; cface++) {
+          int cez = ez_exit[cface][c];
+          src[cez] = src[cez] + coefpsi[cface][c] * tPsi[c0 + c - 1];
+          pInc[c0 + cez - 1] = pInc[c0 + cez - 1] + coefpsi[cface][c] * pInc[c0 + c - 1];
+        }
+      }
+      for (int ib = 1; ib <= nxBdy; ib++) PsiBa[bdy_exit[1][ib] - 1] = tPsi[c0 + bdy_exit[0][ib] - 1];
+      for (int c = 1; c <= nCorner; c++) {
+        if (StartingDirection) tInc[c0 + c - 1] = pInc[c0 + c - 1];
+        else tInc[c0 + c - 1] = quadTauW1 * pInc[c0 + c - 1] - quadTauW2 * tInc[c0 + c - 1];
+      }
+    }
+    ndoneZ += nzones;
+  }
+  for (int c = 0; c < nc; c++) PhiInc[c] = PhiInc[c] + quadwt * pInc[c];
+  for (int c = 0; c < nc; c++) {
+    if (StartingDirection) tPsiM[c] = tPsi[c];
+    else tPsiM[c] = quadTauW1 * tPsi[c] - quadTauW2 * tPsiM[c];
+  }
+}
+
+/* InitGreySweepUCBrz for every zone: TT(c1, c0+c) = sum over the weighted angles of quadwt Pvv(c1,c), the starting direction's Pvv
+   carried through Tvv like PsiM */
+void orc_gta_init_tt_rz(const orc_mesh *M, int nAng, const int *nextC /* (nc,nAng) */, const double *omegas, const double *weights,
+                        const unsigned char *start, const unsigned char *finish, const double *angDerivFac, const double *quadTauW1,
+                        const double *quadTauW2, const double *Volume, const double *Area, const double *A_fp, const double *A_ez,
+                        const double *RadiusFP, const double *RadiusEZ, const double *GreySigTotal, double *TT) {
+  const int mC = M->maxCorner, nc = M->ncornr;
+  for (int zone = 1; zone <= M->nzones; zone++) {
+    int nCorner = M->numCorner[zone - 1], c0 = M->cOffSet[zone - 1];
+    double Tvv[MAXC + 1][MAXC + 1], Pvv[MAXC + 1][MAXC + 1], Sigt[MAXC + 1], denom[MAXC + 1], coefpsi[3][MAXC + 1]; /* [column][row] */
+    int nxez[MAXC + 1], ez_exit[3][MAXC + 1];
+    for (int i = 0; i <= MAXC; i++) for (int j = 0; j <= MAXC; j++) Tvv[i][j] = 0.0;
+    for (int c = 1; c <= nCorner; c++) {
+      for (int c1 = 1; c1 <= mC; c1++) F2(TT, c1, c0 + c, mC) = 0.0;
+      Sigt[c] = GreySigTotal[c0 + c - 1];
+    }
+    for (int a = 0; a < nAng; a++) {
+      if (finish[a]) continue;
+      const double *omega = omegas + 2 * a;
+      double quadwt = weights[a], fac = angDerivFac[a];
+      for (int i = 0; i <= MAXC; i++) { nxez[i] = 0; for (int j = 0; j <= MAXC; j++) Pvv[i][j] = 0.0; }
+      for (int c = 1; c <= nCorner; c++) {
+        Pvv[c][c] = Volume[c0 + c - 1];
+        denom[c] = Sigt[c] * Volume[c0 + c - 1] + fac * Area[c0 + c - 1];
+        for (int c1 = 1; c1 <= nCorner; c1++) Pvv[c1][c] = Pvv[c1][c] + fac * Area[c0 + c - 1] * Tvv[c1][c];
+      }
+      for (int c = 1; c <= nCorner; c++) {
+        for (int cface = 1; cface <= 2; cface++) {
+          double afp = dot2(omega, &F3(A_fp, 1, cface, c0 + c, 2, 2));
+          double aez = dot2(omega, &F3(A_ez, 1, cface, c0 + c, 2, 2));
+          if (afp < 0.0) denom[c] = denom[c] - F2(RadiusFP, cface, c0 + c, 2) * afp;
+          if (aez > 0.0) {
+            double R = F2(RadiusEZ, cface, c0 + c, 2);
+            int cez = F2(M->cEZ, cface, c0 + c, 2);
+            nxez[c]++; ez_exit[nxez[c]][c] = cez; coefpsi[nxez[c]][c] = R * aez;
+            denom[cez] = denom[cez] + R * aez;
+            double B1, B2;
+            if (afp < 0.0) {
+              double sigA = Sigt[c] * Area[c0 + c - 1], sigA2 = sigA * sigA;
+              double gnum = aez * aez * (fouralpha * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+              double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+              double B0 = 0.5 * aez * (1.0 - gtau) * R;
+              B1 = (B0 - R * gtau * sigA) / Sigt[c];
+              B2 = B0 / Sigt[cez];
+            } else {
+              B1 = 0.5 * R * aez / Sigt[c];
+              B2 = 0.5 * R * aez / Sigt[cez];
+            }
+            Pvv[c][c] = Pvv[c][c] + B1;
+            Pvv[cez][c] = Pvv[cez][c] - B2;
+            Pvv[c][cez] = Pvv[c][cez] - B1;
+            Pvv[cez][cez] = Pvv[cez][cez] + B2;
+          }
+        }
+      }
+      for (int i = 1; i <= nCorner; i++) {
+        int c = nextC[(size_t)nc * a + c0 + i - 1];
+        double dInv = 1.0 / denom[c];
+        for (int c1 = 1; c1 <= nCorner; c1++) Pvv[c1][c] = dInv * Pvv[c1][c];
+        for (int cface = 1; cface <= nxez[c]; cface++) {
+          int cez = ez_exit[cface][c];
+          double coef = coefpsi[cface][c];
+          for (int c1 = 1; c1 <= nCorner; c1++) Pvv[c1][cez] = Pvv[c1][cez] + coef * Pvv[c1][c];
+        }
+      }
+      if (start[a]) {
+        for (int c = 1; c <= nCorner; c++) for (int c1 = 1; c1 <= nCorner; c1++) Tvv[c1][c] = Pvv[c1][c];
+      } else {
+        for (int c = 1; c <= nCorner; c++)
+          for (int c1 = 1; c1 <= nCorner; c1++) {
+            F2(TT, c1, c0 + c, mC) = F2(TT, c1, c0 + c, mC) + quadwt * Pvv[c1][c];
+            Tvv[c1][c] = quadTauW1[a] * Pvv[c1][c] - quadTauW2[a] * Tvv[c1][c];
+          }
+      }
+    }
+  }
 }

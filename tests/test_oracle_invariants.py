@@ -313,3 +313,98 @@ def test_gta_transfer_matrix_is_the_sweep_response():
             tPsi, _ = P.sweep_angle(a, tsa, np.zeros(mesh.nbelem), np.zeros(nc))
             phi += w[a] * tPsi[:nc]
         assert np.abs(phi - TT[:, k]).max() <= 1e-13 * np.abs(TT).max()
+
+
+# ---------------------------------------------------------------------------
+# r-z grey transport acceleration (SweepGreyUCBrz KernelNew, InitSweepGreyUCBrz, level-symmetric S2 set)
+# ---------------------------------------------------------------------------
+def _gta_problem_rz(mesh, G=4, seed=7):
+    om = O.OMesh(mesh)
+    g = O.geometry(om)
+    q = O.gta_quad_rz()
+    sched = O.schedule(om, g, q["omega"], q["finish"])
+    rng = np.random.default_rng(seed)
+    nz, nc = mesh.nzones, mesh.ncornr
+    tau = PR.tau(1e-3)
+    Siga, Sigs, Eta = 5 * rng.random((nz, G)), 20 * rng.random((nz, G)), 0.5 * rng.random(nc)
+    Chi = rng.random((nc, G))
+    Chi /= Chi.sum(1, keepdims=True)
+    Phi = rng.random((nc, G))
+    op = O.gta_set_opacity(om, g, tau, Siga, Sigs, Eta, Chi)
+    gs = O.collision_rate(om, Eta, Siga, Sigs, Phi, np.zeros(nc), 0)
+    return om, g, q, sched, op, gs, Phi
+
+
+def test_gta_quadrature_rz():
+    """Level-symmetric S2 in r-z: two xi-levels (xi = -+1/sqrt 3) of start, mu = -1/sqrt 3, mu = +1/sqrt 3, finish, weights pi/2;
+    weighted-diamond coefficients from AngleCoef2D with the cell edges at phi = pi, pi/2, 0 (mu = -s, 0, s with s = sqrt(2/3))."""
+    q = O.gta_quad_rz()
+    mu, s = 1 / math.sqrt(3), math.sqrt(2.0 / 3.0)
+    assert q["start"].tolist() == [1, 0, 0, 0, 1, 0, 0, 0] and q["finish"][:8].tolist() == [0, 0, 0, 1, 0, 0, 0, 1]
+    assert abs(q["weight"].sum() / (2 * math.pi) - 1) <= 1e-15 and q["level"].tolist() == [1, 1, 1, 1, 2, 2, 2, 2]
+    assert np.abs(q["omega"][:4, 0] - [-s, -mu, mu, s]).max() <= 1e-15 and np.abs(np.abs(q["omega"][:, 1]) - mu).max() <= 1e-15
+    assert np.abs(q["weight"][[1, 2, 5, 6]] - math.pi / 2).max() <= 1e-15
+    tau1, tau2 = (s - mu) / s, mu / s
+    assert np.abs(q["quadTauW1"][[1, 2]] - [1 / tau1, 1 / tau2]).max() <= 1e-13
+    assert np.abs(q["quadTauW2"][[1, 2]] - [(1 - tau1) / tau1, (1 - tau2) / tau2]).max() <= 1e-13
+    # alpha_1 = w mu, alpha_2 = 0 (the level closes): angDerivFac = mu_m + alpha_m / (w tau_m)
+    assert np.abs(q["angDerivFac"][[1, 2]] - [-mu + mu / tau1, mu]).max() <= 1e-13
+    assert np.array_equal(q["angDerivFac"][4:], q["angDerivFac"][:4])
+
+
+@pytest.mark.parametrize("mk", [lambda: M.tiled_mesh((2, 2, 0)), lambda: M.box_mesh((4, 3))])
+def test_gta_rz_uniform_solution_preserved(mk):
+    """TsaSource = sigma * c in the volume and c on every incident boundary element: every swept angle returns tPsi = c,
+    including the angular-derivative chain through tPsiM (which must therefore carry c from the starting direction on)."""
+    mesh = mk()
+    om, g, q, sched, op, gs, Phi = _gta_problem_rz(mesh)
+    nc, nb = mesh.ncornr, mesh.nbelem
+    c = 0.7
+    P = O.GtaProblem(om, g, sched, q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q)
+    tsa = op["GreySigTotal"] * c
+    tPsiM, tInc, PhiInc = np.zeros(nc), np.zeros(nc), np.zeros(nc)
+    for a in range(8):
+        if q["finish"][a]:
+            continue
+        if q["start"][a]:
+            tPsiM[:] = 0
+            tInc[:] = 0
+        tPsi, pInc = P.sweep_angle_rz(a, tsa, np.full(nb, c), PhiInc, tPsiM, tInc)
+        assert np.abs(tPsi[:nc] - c).max() <= 1e-12
+
+
+def test_gta_rz_transfer_matrix_is_the_sweep_response():
+    """InitGreySweepUCBrz: for a zone-local unit source and no incident flux the angle-integrated corner fluxes of one r-z
+    GTASweep equal TT applied to the source (the starting direction feeding tPsiM exactly as Tvv feeds Pvv)."""
+    mesh = M.box_mesh((1, 1))
+    om, g, q, sched, op, gs, Phi = _gta_problem_rz(mesh)
+    P = O.GtaProblem(om, g, sched, q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q)
+    TT = P.init_tt().copy()
+    nc = mesh.ncornr
+    for k in range(nc):
+        tsa = np.zeros(nc)
+        tsa[k] = 1.0
+        phi, tPsiM, tInc = np.zeros(nc), np.zeros(nc), np.zeros(nc)
+        for a in range(8):
+            if q["finish"][a]:
+                continue
+            tPsi, _ = P.sweep_angle_rz(a, tsa, np.zeros(mesh.nbelem), np.zeros(nc), tPsiM, tInc)
+            phi += q["weight"][a] * tPsi[:nc]
+        assert np.abs(phi - TT[:, k]).max() <= 1e-13 * np.abs(TT).max()
+
+
+def test_gta_rz_solver_solves_the_grey_system():
+    mesh = M.tiled_mesh((2, 2, 0))
+    om, g, q, sched, op, gs, Phi = _gta_problem_rz(mesh)
+    nc, nb = mesh.ncornr, mesh.nbelem
+    P = O.GtaProblem(om, g, sched, q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q)
+    corr, n, err = P.solve(Phi, epsPoint=1e-10, maxIters=200)
+    assert 3 < n < 100 and err < 1e-10
+    Q = O.GtaProblem(om, g, sched, q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q)
+    Q.init_tt()
+    b, bB = np.zeros(nc), np.zeros((8, nb))
+    Q.grey_sweep(bB, b, True)
+    Q.GreySource[:] = 0
+    Mx, MB = corr.copy(), np.zeros((8, nb))
+    Q.grey_sweep(MB, Mx, False)
+    assert np.abs(b - (corr - Mx)).max() <= 1e-8 * np.abs(b).max()

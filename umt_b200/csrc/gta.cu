@@ -582,6 +582,8 @@ int need_gta(umt_ctx *ctx) {
   return UMT_OK;
 }
 
+double gta_wtiso(const umt_ctx *ctx) { return ctx->ndim == 3 ? 1.0 / (4.0 * PI) : 1.0 / (2.0 * PI); }   // Size_mod.F90:278-281
+
 void zone_params(umt_ctx *ctx, ZoneParams &Z, double *P) {
   GtaState &g = ctx->gta;
   Z.nz = ctx->nz; Z.nc = ctx->nc; Z.mC = ctx->maxCorner; Z.nAng = g.nAng;
@@ -589,7 +591,7 @@ void zone_params(umt_ctx *ctx, ZoneParams &Z, double *P) {
   Z.Volume = ctx->d_Volume; Z.Afp = ctx->d_Afp; Z.Aez = ctx->d_Aez; Z.omega = g.d_omega; Z.weight = g.d_weight;
   Z.sigTotal = g.d_sigTotal; Z.sigScat = g.d_sigScat; Z.greySource = g.d_greySource; Z.phiInc = g.d_phiInc;
   Z.TT = g.d_TT; Z.P = P;
-  Z.wtiso = 1.0 / (4.0 * PI);
+  Z.wtiso = gta_wtiso(ctx);
 }
 
 // GTASweep (GTA%ID = 1): d_P (nc) in; d_PsiB (nAng, nb) in/out; leaves PhiInc in g.d_phiInc
@@ -597,12 +599,20 @@ int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nb = ctx->nb, rows = nc + nb;
   TRY(umt_gta_exchange(ctx, d_PsiB));   // SendFlux / RecvFlux of every angle (GTASweep.F90:139-146): lagged one grey sweep
-  gta_tsa_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(d_P, g.d_sigScat, g.d_greySource, 1.0 / (4.0 * PI), g.d_tsaSource, nc);
+  gta_tsa_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(d_P, g.d_sigScat, g.d_greySource, gta_wtiso(ctx), g.d_tsaSource, nc);
   UMT_CUDA(ctx, cudaMemsetAsync(g.d_tpsi, 0, sizeof(double) * (size_t)rows * g.nAng, ctx->stream));
   if (nb > 0)
     UMT_CUDA(ctx, cudaMemcpy2DAsync(g.d_tpsi + nc, sizeof(double) * rows, d_PsiB, sizeof(double) * nb, sizeof(double) * nb, g.nAng,
                                     cudaMemcpyDeviceToDevice, ctx->stream));
   UMT_CUDA(ctx, cudaMemsetAsync(g.d_counters, 0, sizeof(int) * (1 + g.nCounters), ctx->stream));
+  if (ctx->ndim == 2) {
+    TRY(umt_gta_launch_sweep_rz(ctx));   // gta_rz.cu
+    gta_phiinc_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(g.d_pinc, g.d_weight, g.nAng, nc, g.d_phiInc);
+    if (nb > 0)
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(d_PsiB, sizeof(double) * nb, g.d_tpsi + nc, sizeof(double) * rows, sizeof(double) * nb, g.nAng,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    return UMT_OK;
+  }
   GtaSweepParams P;
   P.nc = nc; P.nb = nb; P.nz = ctx->nz; P.nItems = g.nItems;
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces; P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
@@ -651,7 +661,8 @@ void umt_gta_release(umt_ctx *ctx) {
   GtaState &g = ctx->gta;
   void *p[] = {g.d_omega, g.d_weight, g.d_nextZ, g.d_nextC, g.d_items, g.d_counters, g.d_sigTotal, g.d_sigtInv, g.d_sigScat, g.d_sigScatVol,
                g.d_greySource, g.d_tsaSource, g.d_phiInc, g.d_correction, g.d_chi, g.d_TT, g.d_tpsi, g.d_pinc, g.d_vec[0], g.d_vec[1], g.d_vec[2],
-               g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB};
+               g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB,
+               g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc};
   for (void *q : p) if (q) cudaFree(q);
   g = GtaState();
 }
@@ -662,13 +673,19 @@ void umt_gta_release(umt_ctx *ctx) {
 // GTA angle set (level-symmetric S2, rt/quadxyz.F90 + rtquad.F90:95-105), its sweep order, work items, device arrays
 extern "C" int umt_gta_setup(umt_ctx *ctx) {
   if (!ctx) return UMT_ERR_ARG;
-  if (ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: the GTA kernels are 3-D only so far");
+  if (ctx->ndim != 3 && ctx->ndim != 2) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: 2-D (r-z) or 3-D meshes");
   if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: host-only context");
   if (!ctx->have_conn || !ctx->have_geom || ctx->h_zoneOpp.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: needs full connectivity and geometry");
-  if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
+  if (ctx->ndim == 3 && (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
   if (!ctx->refl.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: reflecting boundaries are not supported by the GTA sweep yet");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
+  const int nd = ctx->ndim;
+  std::vector<WorkItem> items;
+  const int nz = ctx->nz, nc = ctx->nc, nb = ctx->nb;
+  if (nd == 2) {
+    TRY(umt_gta_setup_rz(ctx));
+  } else {
   g.nAng = 8;
   const double mu = 0.577350269189625;   // QuadratureData_mod.F90:711-713
   const int sx[8] = {1, -1, -1, 1, 1, -1, -1, 1}, sy[8] = {1, 1, -1, -1, 1, 1, -1, -1}, sz[8] = {1, 1, 1, 1, -1, -1, -1, -1};
@@ -682,11 +699,10 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   const double fac = 1.0 / ((1.0 / (4.0 * PI)) * sum);
   for (double &w : g.weight) w = fac * w;
   TRY(umt_host_build_order(ctx, g.omega.data(), g.nAng, g.nHyp, g.zonesInPlane, g.nextZ, g.nextC));
-  const int nz = ctx->nz, nc = ctx->nc, nb = ctx->nb;
+  }
   g.maxHyp = *std::max_element(g.nHyp.begin(), g.nHyp.end());
   std::vector<int> h_nextZ((size_t)g.nAng * nz);
   std::vector<unsigned char> h_nextC((size_t)g.nAng * nc);
-  std::vector<WorkItem> items;
   const int zpi = GTA_WARPS;   // one zone per warp of the sweep CTA
   std::vector<std::vector<int>> start(g.nAng), nIt(g.nAng);
   for (int a = 0; a < g.nAng; a++) {
@@ -695,7 +711,8 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
     start[a].assign(g.nHyp[a] + 1, 0); nIt[a].assign(g.nHyp[a], 0);
     for (int p = 0; p < g.nHyp[a]; p++) { start[a][p + 1] = start[a][p] + g.zonesInPlane[a][p]; nIt[a][p] = (g.zonesInPlane[a][p] + zpi - 1) / zpi; }
   }
-  for (int p = 0; p < g.maxHyp; p++)
+  if (nd == 2) TRY(umt_gta_finish_setup_rz(ctx, items));   // items chained along the xi-levels, r-z coefficient arrays
+  for (int p = 0; nd == 3 && p < g.maxHyp; p++)
     for (int a = 0; a < g.nAng; a++) {
       if (p >= g.nHyp[a]) continue;
       for (int k = 0; k < nIt[a][p]; k++) {
@@ -707,11 +724,11 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
       }
     }
   g.nItems = (int)items.size(); g.nCounters = g.nAng * g.maxHyp;
-  TRY(dalloc(ctx, &g.d_omega, 24)); TRY(dalloc(ctx, &g.d_weight, 8));
+  TRY(dalloc(ctx, &g.d_omega, (size_t)nd * g.nAng)); TRY(dalloc(ctx, &g.d_weight, g.nAng));
   TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));
   TRY(dalloc(ctx, &g.d_items, items.size())); TRY(dalloc(ctx, &g.d_counters, 1 + (size_t)g.nCounters));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_omega, g.omega.data(), sizeof(double) * 24, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_weight, g.weight.data(), sizeof(double) * 8, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_omega, g.omega.data(), sizeof(double) * nd * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_weight, g.weight.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_nextZ, h_nextZ.data(), sizeof(int) * h_nextZ.size(), cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_nextC, h_nextC.data(), h_nextC.size(), cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice));
@@ -845,10 +862,14 @@ extern "C" int umt_gta_init_tt(umt_ctx *ctx, double *TT /* (maxCorner, nc) or NU
   if (!ctx) return UMT_ERR_ARG;
   TRY(need_gta(ctx));
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZoneParams Z;
-  zone_params(ctx, Z, ctx->gta.d_P);
-  gta_init_tt_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z);
-  UMT_CUDA(ctx, cudaGetLastError());
+  if (ctx->ndim == 2) {
+    TRY(umt_gta_launch_init_tt_rz(ctx));
+  } else {
+    ZoneParams Z;
+    zone_params(ctx, Z, ctx->gta.d_P);
+    gta_init_tt_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->gta.tt_decomposed = false;
   if (TT) UMT_CUDA(ctx, cudaMemcpy(TT, ctx->gta.d_TT, sizeof(double) * (size_t)ctx->nc * ctx->maxCorner, cudaMemcpyDeviceToHost));

@@ -1,0 +1,324 @@
+// Grey transport acceleration in r-z geometry for sm_100a.
+//
+// Replaces snac/SweepGreyUCBrz.F90:12-133 + SweepGreyUCBrzKernelNew :137-330 (the 1-group UCB sweep of the "new" GTA
+// solver), the r-z branch of snac/GTASweep.F90:113-119,149-159 (tPsiM = tInc = 0, finishing directions skipped) and
+// snac/InitSweepGreyUCBrz.F90:10-235 (within-zone transfer matrices).  The angle set is the level-symmetric S2 set of
+// rt/quadrz.F90:82-160: two xi-levels of (starting direction, mu < 0, mu > 0, finishing direction).
+//
+// Device design: like the multigroup r-z sweep (sweeprz.cu) one persistent launch sweeps every non-finishing angle; work
+// items are (angle, hyperplane, chunk of zones) pulled through an atomic ticket and gated by the angle's previous plane and
+// by the previous angle of the xi-level (half-angle values tPsiM / tInc, carried per level).  With one group the
+// parallelism is zones-in-plane: one thread owns one zone.  tPsi (8, nc+nb) keeps PsiB(:, angle) in its tail rows as in
+// the 3-D grey sweep (gta.cu), pInc (8, nc) is summed in fixed angle order afterwards (deterministic PhiInc).
+#include <algorithm>
+#include <cmath>
+
+#include "umt_internal.h"
+
+namespace {
+
+constexpr int MAXC2 = 8;
+constexpr int GRZ_BLOCK = 64;   // zones per work item
+constexpr double FOURALPHA = 1.82;
+
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double dot2(const double *om, const double *A) { return __dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])); }
+
+struct GtaRZParams {
+  int nc, nb, nz, nItems;
+  const int *numCorner, *cOffSet, *cFP /* 0-based row; >= nc: boundary */, *cEZ;
+  const double *Volume, *Area, *Afp, *Aez, *RadiusFP, *RadiusEZ, *omega /* (nAng, 2) */;
+  const double *fac, *w1, *w2;
+  const unsigned char *start;
+  const int *level;
+  const int *nextZ;
+  const unsigned char *nextC;
+  const WorkItem *items;
+  int *counters;
+  const double *sigTotal, *sigtInv, *tsa;
+  double *tpsi, *pinc, *psim, *tinc;
+};
+
+// SweepGreyUCBrzKernelNew for one (zone, angle)
+template <int MC>
+__device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
+  const int nc = P.nc;
+  const double om[2] = {P.omega[2 * a], P.omega[2 * a + 1]};
+  double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
+  double *pincA = P.pinc + (size_t)a * nc;
+  double *psimL = P.psim + (size_t)P.level[a] * nc, *tincL = P.tinc + (size_t)P.level[a] * nc;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
+  const double fac = P.fac[a];
+  double Q[MC], src[MC], Sigt[MC], denom[MC], pinc[MC], coefpsi[MC][2];
+  int nxez[MC], ez_exit[MC][2];
+#pragma unroll
+  for (int c = 0; c < MC; c++) {
+    nxez[c] = 0;
+    if (c < nCorner) {
+      const int cc = c0 + c;
+      const double t = P.tsa[cc], area = P.Area[cc], vol = P.Volume[cc];
+      Q[c] = P.sigtInv[cc] * t;
+      src[c] = vol * t + fac * area * psimL[cc];
+      Sigt[c] = P.sigTotal[cc];
+      denom[c] = Sigt[c] * vol + fac * area;
+      pinc[c] = fac * area * tincL[cc];
+    }
+  }
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      const double afp = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
+      const double aez = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
+      double psifp = 0.0;
+      if (afp < 0.0) {
+        const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
+        psifp = __ldcg(&tpsi[P.cFP[cc * 2 + f]]);
+        denom[c] -= R_afp;
+        src[c] -= R_afp * psifp;
+        pinc[c] -= R_afp * psifp;
+      }
+      if (aez > 0.0) {
+        const double R = P.RadiusEZ[cc * 2 + f];
+        const int cez = P.cEZ[cc * 2 + f];
+        ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = R * aez; nxez[c]++;
+        denom[cez] += R * aez;
+        double sez;
+        if (afp < 0.0) {
+          const double sigA = Sigt[c] * P.Area[cc], sigA2 = sigA * sigA;
+          const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+          const double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+          sez = R * (gtau * sigA * (psifp - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - Q[cez]));
+          pinc[c] += R * gtau * sigA * psifp;
+          pinc[cez] -= R * gtau * sigA * psifp;
+        } else {
+          sez = 0.5 * R * aez * (Q[c] - Q[cez]);
+        }
+        src[c] += sez;
+        src[cez] -= sez;
+      }
+    }
+  }
+  for (int i = 0; i < nCorner; i++) {
+    const int c = nextC[c0 + i];
+    const double p = src[c] / denom[c], pi = pinc[c] / denom[c];
+    src[c] = p; pinc[c] = pi;   // src now holds the corner flux
+    for (int k = 0; k < nxez[c]; k++) {
+      const int cez = ez_exit[c][k];
+      src[cez] += coefpsi[c][k] * p;
+      pinc[cez] += coefpsi[c][k] * pi;
+    }
+  }
+  // corner fluxes, exiting boundary fluxes (:314-319), half-angle values for the next angle of the level (:120-130, :321-329)
+  const bool starting = P.start[a] != 0;
+  const double w1 = P.w1[a], w2 = P.w2[a];
+  for (int c = 0; c < nCorner; c++) {
+    const int cc = c0 + c;
+    tpsi[cc] = src[c];
+    pincA[cc] = pinc[c];
+    psimL[cc] = starting ? src[c] : w1 * src[c] - w2 * psimL[cc];
+    tincL[cc] = starting ? pinc[c] : w1 * pinc[c] - w2 * tincL[cc];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      const int row = P.cFP[cc * 2 + f];
+      if (row >= nc && !(dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2) < 0.0)) tpsi[row] = src[c];
+    }
+  }
+}
+
+template <int MC>
+__global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) {
+  __shared__ int s_item;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= P.nItems) break;
+    const WorkItem w = P.items[it];
+    const int zi = w.zbeg + threadIdx.x;
+    int zone0 = 0;
+    if (zi < w.zend) zone0 = P.nextZ[(size_t)w.angle * P.nz + zi];
+    if (threadIdx.x == blockDim.x - 1) {
+      if (w.wait_idx >= 0)
+        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
+      if (w.pad0 >= 0)   // the previous angle of this xi-level (tPsiM / tInc chain)
+        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
+    }
+    __syncthreads();
+    if (zi < w.zend) gta_zone_rz<MC>(P, w.angle, zone0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+    }
+  }
+}
+
+struct TTRZParams {
+  int nz, nc, mC, nAng;
+  const int *numCorner, *cOffSet, *cEZ;
+  const unsigned char *nextC, *start, *finish;
+  const double *Volume, *Area, *Afp, *Aez, *RadiusFP, *RadiusEZ, *omega, *weight, *fac, *w1, *w2, *sigTotal;
+  double *TT;
+};
+
+// InitGreySweepUCBrz: TT(:, corners of zone) = sum over the weighted angles of w Pvv, the starting direction's response
+// carried along the xi-level through Tvv
+template <int MC>
+__global__ void __launch_bounds__(64) gta_init_tt_rz_kernel(TTRZParams Z) {
+  const int zone = blockIdx.x * blockDim.x + threadIdx.x;
+  if (zone >= Z.nz) return;
+  const int nCorner = Z.numCorner[zone], c0 = Z.cOffSet[zone], mC = Z.mC;
+  double T[MC][MC], Tvv[MC][MC], Pvv[MC][MC];   // [column c1][row c]
+  double Sigt[MC], denom[MC], coefpsi[MC][2];
+  int nxez[MC], ez_exit[MC][2];
+  for (int i = 0; i < MC; i++) for (int j = 0; j < MC; j++) { T[i][j] = 0.0; Tvv[i][j] = 0.0; }
+  for (int c = 0; c < nCorner; c++) Sigt[c] = Z.sigTotal[c0 + c];
+  for (int a = 0; a < Z.nAng; a++) {
+    if (Z.finish[a]) continue;
+    const double om[2] = {Z.omega[2 * a], Z.omega[2 * a + 1]};
+    const double quadwt = Z.weight[a], fac = Z.fac[a];
+    for (int i = 0; i < MC; i++) { nxez[i] = 0; for (int j = 0; j < MC; j++) Pvv[i][j] = 0.0; }
+    for (int c = 0; c < nCorner; c++) {
+      const double vol = Z.Volume[c0 + c], area = Z.Area[c0 + c];
+      Pvv[c][c] = vol;
+      denom[c] = Sigt[c] * vol + fac * area;
+      for (int c1 = 0; c1 < nCorner; c1++) Pvv[c1][c] = Pvv[c1][c] + fac * area * Tvv[c1][c];
+    }
+    for (int c = 0; c < nCorner; c++) {
+      const int cc = c0 + c;
+      for (int f = 0; f < 2; f++) {
+        const double afp = dot2(om, Z.Afp + ((size_t)cc * 2 + f) * 2);
+        const double aez = dot2(om, Z.Aez + ((size_t)cc * 2 + f) * 2);
+        if (afp < 0.0) denom[c] -= Z.RadiusFP[cc * 2 + f] * afp;
+        if (aez > 0.0) {
+          const double R = Z.RadiusEZ[cc * 2 + f];
+          const int cez = Z.cEZ[cc * 2 + f];
+          ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = R * aez; nxez[c]++;
+          denom[cez] += R * aez;
+          double B1, B2;
+          if (afp < 0.0) {
+            const double sigA = Sigt[c] * Z.Area[cc], sigA2 = sigA * sigA;
+            const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+            const double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+            const double B0 = 0.5 * aez * (1.0 - gtau) * R;
+            B1 = (B0 - R * gtau * sigA) / Sigt[c];
+            B2 = B0 / Sigt[cez];
+          } else {
+            B1 = 0.5 * R * aez / Sigt[c];
+            B2 = 0.5 * R * aez / Sigt[cez];
+          }
+          Pvv[c][c] += B1; Pvv[cez][c] -= B2; Pvv[c][cez] -= B1; Pvv[cez][cez] += B2;
+        }
+      }
+    }
+    for (int i = 0; i < nCorner; i++) {
+      const int c = Z.nextC[(size_t)a * Z.nc + c0 + i];
+      const double dInv = 1.0 / denom[c];
+      for (int c1 = 0; c1 < nCorner; c1++) Pvv[c1][c] = dInv * Pvv[c1][c];
+      for (int k = 0; k < nxez[c]; k++) {
+        const int cez = ez_exit[c][k];
+        const double coef = coefpsi[c][k];
+        for (int c1 = 0; c1 < nCorner; c1++) Pvv[c1][cez] += coef * Pvv[c1][c];
+      }
+    }
+    if (Z.start[a]) {
+      for (int c = 0; c < nCorner; c++) for (int c1 = 0; c1 < nCorner; c1++) Tvv[c1][c] = Pvv[c1][c];
+    } else {
+      const double w1 = Z.w1[a], w2 = Z.w2[a];
+      for (int c = 0; c < nCorner; c++)
+        for (int c1 = 0; c1 < nCorner; c1++) {
+          T[c1][c] = T[c1][c] + quadwt * Pvv[c1][c];
+          Tvv[c1][c] = w1 * Pvv[c1][c] - w2 * Tvv[c1][c];
+        }
+    }
+  }
+  for (int c = 0; c < nCorner; c++)
+    for (int c1 = 0; c1 < mC; c1++) Z.TT[(size_t)(c0 + c) * mC + c1] = c1 < nCorner ? T[c1][c] : 0.0;
+}
+
+template <class T>
+int dalloc2(umt_ctx *ctx, T **p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  UMT_CUDA(ctx, cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
+  UMT_CUDA(ctx, cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(n, 1)));
+  return UMT_OK;
+}
+
+}  // namespace
+
+// angle set, sweep order and work items of the r-z grey sweeps; fills the parts of GtaState that umt_gta_setup (gta.cu)
+// turns into device arrays (omega, weight, nextZ, nextC, items) and uploads the r-z specific ones
+int umt_gta_setup_rz(umt_ctx *ctx) {
+  GtaState &g = ctx->gta;
+  if (ctx->maxCorner > MAXC2 || ctx->maxcf != 2) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: r-z needs maxCorner <= 8 and maxcf == 2");
+  if (!ctx->d_Area || !ctx->d_RadiusFP || !ctx->d_RadiusEZ) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: r-z geometry (Area, RadiusFP, RadiusEZ) not set");
+  if (umt_host_gta_quadrature_rz(g.omega, g.weight, g.start, g.finish, g.angDerivFac, g.tauW1, g.tauW2))
+    UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: r-z GTA quadrature failed");
+  g.nAng = (int)g.weight.size();
+  TRY(umt_host_build_order(ctx, g.omega.data(), g.nAng, g.nHyp, g.zonesInPlane, g.nextZ, g.nextC));
+  for (int a = 0; a < g.nAng; a++)
+    if (g.finish[a]) { g.nHyp[a] = 0; g.zonesInPlane[a].clear(); }   // finishing directions are not swept (GTASweep.F90:149)
+  return UMT_OK;
+}
+
+// items + r-z device arrays; called by umt_gta_setup after the common arrays exist
+int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items) {
+  GtaState &g = ctx->gta;
+  TRY(umt_build_items_rz_set(ctx->nz, g.nAng, g.nHyp, g.zonesInPlane, g.nextZ, g.start, GRZ_BLOCK, items, g.level, g.nLevels, g.maxHyp));
+  TRY(dalloc2(ctx, &g.d_start, g.nAng)); TRY(dalloc2(ctx, &g.d_finish, g.nAng)); TRY(dalloc2(ctx, &g.d_level, g.nAng));
+  TRY(dalloc2(ctx, &g.d_fac, g.nAng)); TRY(dalloc2(ctx, &g.d_w1, g.nAng)); TRY(dalloc2(ctx, &g.d_w2, g.nAng));
+  TRY(dalloc2(ctx, &g.d_psim, (size_t)g.nLevels * ctx->nc)); TRY(dalloc2(ctx, &g.d_tinc, (size_t)g.nLevels * ctx->nc));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_start, g.start.data(), g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_finish, g.finish.data(), g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_level, g.level.data(), sizeof(int) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_fac, g.angDerivFac.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_w1, g.tauW1.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_w2, g.tauW2.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  return UMT_OK;
+}
+
+int umt_gta_launch_sweep_rz(umt_ctx *ctx) {
+  GtaState &g = ctx->gta;
+  const int nc = ctx->nc;
+  // GTASweep.F90:113-119: tPsiM = tInc = 0; pInc of the finishing directions stays 0
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_psim, 0, sizeof(double) * (size_t)g.nLevels * nc, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_tinc, 0, sizeof(double) * (size_t)g.nLevels * nc, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(g.d_pinc, 0, sizeof(double) * (size_t)g.nAng * nc, ctx->stream));
+  GtaRZParams P;
+  P.nc = nc; P.nb = ctx->nb; P.nz = ctx->nz; P.nItems = g.nItems;
+  P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
+  P.Volume = ctx->d_Volume; P.Area = ctx->d_Area; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.RadiusFP = ctx->d_RadiusFP; P.RadiusEZ = ctx->d_RadiusEZ;
+  P.omega = g.d_omega; P.fac = g.d_fac; P.w1 = g.d_w1; P.w2 = g.d_w2; P.start = g.d_start; P.level = g.d_level;
+  P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
+  P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc; P.psim = g.d_psim; P.tinc = g.d_tinc;
+  void (*kern)(GtaRZParams) = ctx->maxCorner <= 4 ? gta_sweep_rz_kernel<4> : gta_sweep_rz_kernel<MAXC2>;
+  int occ = 0;
+  UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GRZ_BLOCK, 0));
+  const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), g.nItems));
+  kern<<<grid, GRZ_BLOCK, 0, ctx->stream>>>(P);
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}
+
+int umt_gta_launch_init_tt_rz(umt_ctx *ctx) {
+  GtaState &g = ctx->gta;
+  TTRZParams Z;
+  Z.nz = ctx->nz; Z.nc = ctx->nc; Z.mC = ctx->maxCorner; Z.nAng = g.nAng;
+  Z.numCorner = ctx->d_numCorner; Z.cOffSet = ctx->d_cOffSet; Z.cEZ = ctx->d_cEZ;
+  Z.nextC = g.d_nextC; Z.start = g.d_start; Z.finish = g.d_finish;
+  Z.Volume = ctx->d_Volume; Z.Area = ctx->d_Area; Z.Afp = ctx->d_Afp; Z.Aez = ctx->d_Aez; Z.RadiusFP = ctx->d_RadiusFP; Z.RadiusEZ = ctx->d_RadiusEZ;
+  Z.omega = g.d_omega; Z.weight = g.d_weight; Z.fac = g.d_fac; Z.w1 = g.d_w1; Z.w2 = g.d_w2; Z.sigTotal = g.d_sigTotal; Z.TT = g.d_TT;
+  void (*kern)(TTRZParams) = ctx->maxCorner <= 4 ? gta_init_tt_rz_kernel<4> : gta_init_tt_rz_kernel<MAXC2>;
+  kern<<<(ctx->nz + 63) / 64, 64, 0, ctx->stream>>>(Z);
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
+}

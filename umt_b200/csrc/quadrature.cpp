@@ -14,6 +14,10 @@ struct Rule { const double *x, *w; int n; };
 Rule row(const double *x, const double *w, int N) { return {x + N * (N - 1) / 2, w + N * (N - 1) / 2, N}; }
 }  // namespace
 
+int umt_host_finish_quadrature(int ndim, std::vector<double> &omega, std::vector<double> &weight, std::vector<unsigned char> &start,
+                               std::vector<unsigned char> &finish, std::vector<double> &angDerivFac, std::vector<double> &w1,
+                               std::vector<double> &w2);
+
 int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polaraxis, std::vector<double> &omega,
                                 std::vector<double> &weight, std::vector<unsigned char> &start,
                                 std::vector<unsigned char> &finish, std::vector<double> &angDerivFac,
@@ -58,6 +62,31 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
       }
     }
   }
+  return umt_host_finish_quadrature(ndim, omega, weight, start, finish, angDerivFac, w1, w2);
+}
+
+// the GTA angle set in r-z: level-symmetric S2 (rt/quadrz.F90:82-160 with norder = 2): per xi-level (xi = -+1/sqrt 3) a starting
+// direction, mu = -1/sqrt 3, mu = +1/sqrt 3 (weight pi/2 each) and a finishing direction
+int umt_host_gta_quadrature_rz(std::vector<double> &omega, std::vector<double> &weight, std::vector<unsigned char> &start,
+                               std::vector<unsigned char> &finish, std::vector<double> &angDerivFac, std::vector<double> &w1,
+                               std::vector<double> &w2) {
+  const double xilev = 0.577350269189625, mu = 0.577350269189625;   // QuadratureData_mod.F90:711-713
+  omega.clear(); weight.clear();
+  for (int half = 0; half < 2; half++) {
+    const double sxi = half == 0 ? -xilev : xilev;
+    auto push = [&](double m, double w) { omega.push_back(m); omega.push_back(sxi); weight.push_back(w); };
+    push(-std::sqrt(1.0 - xilev * xilev), 0.0);
+    push(-mu, 0.5 * kPi);
+    push(mu, 0.5 * kPi);
+    push(std::sqrt(1.0 - xilev * xilev), 0.0);
+  }
+  return umt_host_finish_quadrature(2, omega, weight, start, finish, angDerivFac, w1, w2);
+}
+
+// normalisation, starting/finishing flags (rtquad.F90:95-127) and, in r-z, the weighted-diamond coefficients of every xi-level
+int umt_host_finish_quadrature(int ndim, std::vector<double> &omega, std::vector<double> &weight, std::vector<unsigned char> &start,
+                               std::vector<unsigned char> &finish, std::vector<double> &angDerivFac, std::vector<double> &w1,
+                               std::vector<double> &w2) {
   const int NA = (int)weight.size();
   // sum of weights * wtiso = 1 (rtquad.F90:95-105; wtiso = 1/4pi in xyz, 1/2pi in rz, Size_mod.F90:278-281)
   const double wtiso = ndim == 3 ? 1.0 / (4.0 * kPi) : 1.0 / (2.0 * kPi);

@@ -230,9 +230,20 @@ __global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
 
 // Work items of the RZ sweep in a topological order of both dependencies (host side, once per schedule).
 int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
-  const int NA = ctx->NA, nz = ctx->nz;
+  int maxHyp = 0;
+  return umt_build_items_rz_set(ctx->nz, ctx->NA, ctx->nHyp, ctx->zonesInPlane, ctx->nextZ, ctx->h_start, zpi, items, ctx->h_level, ctx->nLevels, maxHyp);
+}
+
+// the same for any r-z angle set (the Sn set above, the GTA set in gta_rz.cu); angles with nHyp == 0 (finishing directions) get no items
+int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHypV, const std::vector<std::vector<int>> &zonesInPlaneV,
+                           const std::vector<std::vector<int>> &nextZV, const std::vector<unsigned char> &startV, int zpi,
+                           std::vector<WorkItem> &items, std::vector<int> &levelOut, int &nLevelsOut, int &maxHypOut) {
+  struct { const std::vector<int> &nHyp; const std::vector<std::vector<int>> &zonesInPlane, &nextZ; const std::vector<unsigned char> &h_start;
+           std::vector<int> h_level; int nLevels; } cx{nHypV, zonesInPlaneV, nextZV, startV, {}, 0};
+  auto *ctx = &cx;
   int maxHyp = 0;
   for (int a = 0; a < NA; a++) maxHyp = std::max(maxHyp, ctx->nHyp[a]);
+  maxHypOut = maxHyp;
   // xi-levels: a level starts at a starting direction; finishing directions are not swept
   std::vector<int> level(NA, 0), prev(NA, -1);
   int lev = -1, last = -1;
@@ -293,6 +304,8 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
       items.push_back(w);
     }
   }
+  levelOut = ctx->h_level;
+  nLevelsOut = ctx->nLevels;
   return UMT_OK;
 }
 

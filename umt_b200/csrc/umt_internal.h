@@ -89,6 +89,15 @@ struct GtaState {
   double *d_radEnergy = nullptr, *d_pzOld = nullptr, *d_volZone = nullptr;   // (nz)
   double *d_red = nullptr;             // reduction scratch
   double *d_P = nullptr, *d_PB = nullptr;   // staging for the host-facing sweep calls
+  // r-z: xi-levels chained through the half-angle values tPsiM / tInc (SweepGreyUCBrz.F90)
+  std::vector<unsigned char> start, finish;
+  std::vector<double> angDerivFac, tauW1, tauW2;
+  std::vector<int> level;
+  int nLevels = 0;
+  unsigned char *d_start = nullptr;
+  int *d_level = nullptr;
+  double *d_fac = nullptr, *d_w1 = nullptr, *d_w2 = nullptr, *d_psim = nullptr, *d_tinc = nullptr;   // psim/tinc: (nLevels, nc)
+  unsigned char *d_finish = nullptr;
 };
 
 struct umt_ctx {
@@ -198,6 +207,16 @@ int umt_build_plan3d(umt_ctx *ctx);
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx);
 int umt_launch_sweeprz(umt_ctx *ctx, int savePsi);
 int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zonesPerItem);
+int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHyp, const std::vector<std::vector<int>> &zonesInPlane,
+                           const std::vector<std::vector<int>> &nextZ, const std::vector<unsigned char> &start, int zonesPerItem,
+                           std::vector<WorkItem> &items, std::vector<int> &level, int &nLevels, int &maxHyp);
+int umt_host_gta_quadrature_rz(std::vector<double> &omega, std::vector<double> &weight, std::vector<unsigned char> &start,
+                               std::vector<unsigned char> &finish, std::vector<double> &angDerivFac, std::vector<double> &w1,
+                               std::vector<double> &w2);
+int umt_gta_setup_rz(umt_ctx *ctx);          // gta_rz.cu
+int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items);
+int umt_gta_launch_sweep_rz(umt_ctx *ctx);
+int umt_gta_launch_init_tt_rz(umt_ctx *ctx);
 int umt_host_build_schedule(umt_ctx *ctx);
 int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polaraxis,
                                 std::vector<double> &omega, std::vector<double> &weight,

@@ -247,7 +247,7 @@ class SweepContext:
         self._ck(self.lib.umt_gta_setup(self.h), "umt_gta_setup")
 
     def gta_quadrature(self):
-        om, w = np.zeros((8, 3)), np.zeros(8)
+        om, w = np.zeros((8, self.ndim)), np.zeros(8)
         self._ck(self.lib.umt_gta_get_quadrature(self.h, _dp(om), _dp(w)), "umt_gta_get_quadrature")
         return om, w
 
