@@ -45,6 +45,37 @@ def _rank_main():
         assert T.mixed_err(ctx.download_psib(), p.PsiB, 1e-12) <= 1.0
     print(f"rank {rank}: NCCL psib exchange parity ok, worst phi rel err {worst:.2e}", flush=True)
     ctx.close()
+    # grey transport acceleration on the decomposed mesh: grey psib exchange + allreduce of the inner products over NCCL
+    from oracle import oracle as O
+    from umt_b200 import problem as PR
+    from tests.test_gta_multidomain import _domain, _oracle_problem
+    G = 4
+    doms = [_domain(M.tiled_mesh((2, 2, 1), rank=r, size=world), G, 40 + r) for r in range(world)]
+    d = doms[rank]
+    mesh, g = d["mesh"], d["g"]
+    ctx = teton.SweepContext.from_mesh(mesh, G, local)
+    ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], A_bdy=g["A_bdy"])
+    ctx.build_product_quadrature(1, 1, 1)
+    ctx.upload_state(np.tile(d["Phi"] / (4 * np.pi), (8, 1, 1)), None, np.full((mesh.nzones, G), d["tau"]), np.zeros((mesh.ncornr, G)), d["tau"])
+    ctx.init_phi_total()
+    for b in T.shared_boundaries(mesh):
+        ctx.add_shared_boundary(b.neighbor, b.first_elem, b.n_elem)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(teton.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.set_comm(rank, world, idt.cpu().numpy().tobytes())
+    ctx.gta_setup()
+    ctx.gta_compute_opacity(d["Siga"], d["Sigs"], d["Eta"], d["Chi"].copy())
+    ctx.collision_rate(d["Eta"], d["Siga"], d["Sigs"], 0)
+    lists = T.oracle_gta_exchange_lists([x["mesh"] for x in doms], [x["g"] for x in doms], doms[0]["omega"])
+    corr, n, err = T.oracle_gta_multi_solve([x["mesh"] for x in doms], [_oracle_problem(x) for x in doms], lists, [x["Phi"] for x in doms],
+                                            [x["g"] for x in doms])
+    corr_d, n_d, err_d = ctx.gta_solve()
+    scale = max(np.abs(c).max() for c in corr)
+    assert n_d == n and n > 3, (n_d, n)
+    assert np.abs(corr_d - corr[rank]).max() <= 1e-8 * scale
+    print(f"rank {rank}: NCCL GTA solve ok, {n_d} grey sweeps, err {np.abs(corr_d - corr[rank]).max() / scale:.2e}", flush=True)
+    ctx.close()
     dist.destroy_process_group()
 
 
@@ -56,7 +87,7 @@ def test_two_ranks_over_nccl():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.abspath(__file__)], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("parity ok") == 2
+    assert r.stdout.count("parity ok") == 2 and r.stdout.count("NCCL GTA solve ok") == 2
 
 
 if __name__ == "__main__":
