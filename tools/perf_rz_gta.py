@@ -29,9 +29,10 @@ if what == "rz":
           "RZ d=%d G=%d zones=%d angles=%d planes/angle~%d sweep_ms %.3f phi_ms %.3f  unknowns/s (driver count) %.3e  B_alg(58+128/G) -> %.0f GB/s"
           % (d, G, mesh.nzones, NA, max(nh), best, ts[-1]["phi_ms"], unknowns / best * 1e3, swept * (58 + 128.0 / G) / best * 1e3 / 1e9), flush=True)
 else:
-    d = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    rz = what == "gtarz"
+    d = int(sys.argv[2]) if len(sys.argv) > 2 else (40 if rz else 20)
     G = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-    mesh = M.tiled_mesh((d, d, d))
+    mesh = M.tiled_mesh((d, d, 0) if rz else (d, d, d))
     ctx = teton.SweepContext.from_mesh(mesh, G)
     ctx.compute_geometry(mesh.px)
     ctx.build_product_quadrature(1, 1, 1)
@@ -39,7 +40,7 @@ else:
     rng = np.random.default_rng(7)
     tau = PR.tau()
     ctx.upload_state(None, None, np.full((nz, G), tau), np.zeros((nc, G)), tau)
-    ctx.init_teton(np.full(nz, PR.TR0), PR.group_bounds(G), PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
+    ctx.init_teton(np.full(nz, PR.TR0), PR.group_bounds(G), PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(2 if rz else 3), 0.0)
     ctx.init_phi_total()
     t0 = time.time(); ctx.gta_setup(); t_setup = time.time() - t0
     Siga, Sigs, Eta = 5 * rng.random((nz, G)), 20 * rng.random((nz, G)), 0.5 * rng.random(nc)
@@ -48,5 +49,5 @@ else:
     ctx.collision_rate(Eta, Siga, Sigs, 0)
     t0 = time.time(); corr, n, err = ctx.gta_solve(); t_solve = time.time() - t0
     nsweeps = n  # one grey sweep per unit of nGreyIter (1 + 2 per BiCGSTAB iteration)
-    print("GTA d=%d zones=%d corners=%d: setup %.2f s; solve %.1f ms, nGreyIter %d (= grey sweeps), %.3f ms per grey sweep, %.3e corner-angle solves/s, err %.2e"
+    print(("GTA r-z" if rz else "GTA") + " d=%d zones=%d corners=%d: setup %.2f s; solve %.1f ms, nGreyIter %d (= grey sweeps), %.3f ms per grey sweep, %.3e corner-angle solves/s, err %.2e"
           % (d, nz, nc, t_setup, t_solve * 1e3, n, t_solve * 1e3 / nsweeps, nsweeps * nc * 8 / t_solve, err), flush=True)

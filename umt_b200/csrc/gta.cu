@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(GTA_WARPS * 32) gta_sweep_kernel(GtaSweepParam
   __shared__ int s_item;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (;;) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);   // taken only when free to work on it: a ticket held ahead of time blocks a ready item behind a waiting one
     __syncthreads();
     const int it = s_item;
     if (it >= P.nItems) break;
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(GTA_WARPS * 32) gta_sweep_kernel(GtaSweepParam
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
     }
   }
 }

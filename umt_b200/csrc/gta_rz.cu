@@ -138,7 +138,7 @@ template <int MC>
 __global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) {
   __shared__ int s_item;
   for (;;) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);   // taken only when free to work on it: a ticket held ahead of time blocks a ready item behind a waiting one
     __syncthreads();
     const int it = s_item;
     if (it >= P.nItems) break;
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) 
     if (zi < w.zend) gta_zone_rz<MC>(P, w.angle, zone0);
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
     }
   }
 }

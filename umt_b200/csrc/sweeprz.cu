@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
   __shared__ int s_item;
   const int G = P.G;
   for (;;) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);   // taken only when free to work on it: a ticket held ahead of time blocks a ready item behind a waiting one
     __syncthreads();
     const int it = s_item;
     if (it >= P.nItems) break;
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
         zone_solve_rz<MC>(P, w.angle, g2, Z);
       }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(&P.counters[1 + w.signal_idx], 1);
+    if (threadIdx.x == 0) {   // publish the CTA's rows (acq_rel is enough: the writes were observed through the barrier) and signal
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
     }
   }
 }

@@ -68,7 +68,11 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
   {
     size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);   // 64 MB of the 126 MB: more slows the streaming kernels
     if (const char *ev = getenv("UMT_L2_PERSIST_MB")) want = std::min(want, (size_t)std::max(0, atoi(ev)) << 20);
-    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    if (ndim != 3) want = 0;   // only the 3-D plan kernel uses evict_last; the r-z kernels lose 7 % to a smaller normal L2
+    if (want > 0) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+      else { ctx->l2_persist = true; ctx->l2_persist_bytes = want; }
+    }
     if (getenv("UMT_VERBOSE")) fprintf(stderr, "umt: persisting L2 max %d MB, set-aside %zu MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
   }
   *out = ctx;
@@ -702,6 +706,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   int iter = 0;
   const bool multi = !ctx->shared.empty();
+  if (ctx->l2_persist && ctx->ndim == 3 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_bytes) != cudaSuccess) cudaGetLastError();
   if (multi) TRY(umt_exchange_tally(ctx, fluxTol));   // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74); packs the exiting rows
   for (;;) {
     iter++;
@@ -736,6 +741,12 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
     cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ms_exch += t;
     if (savePsi) break;                              // SetSweep.F90:185-187
     if (nNotConv == 0 || iter >= maxFluxIters) break;
+  }
+  // the sweep's evict_last Psi1 lines have served their purpose: hand the set-aside L2 back to the streaming kernels that follow
+  // (phi reduction, GTA); the stream is idle here (event synchronised above)
+  if (ctx->l2_persist && ctx->ndim == 3) {
+    if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
   }
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   TRY(launch_phi(ctx, ctx->d_psi1));

@@ -107,6 +107,8 @@ struct umt_ctx {
   double tau = 0.0;
   std::string err;
   int sm_count = 0;
+  bool l2_persist = false;             // the 3-D sweep runs with an L2 set-aside for its evict_last Psi1 lines
+  size_t l2_persist_bytes = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
 
