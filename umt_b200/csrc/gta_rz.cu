@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "umt_internal.h"
+#include "device_util.h"
 
 namespace {
 
@@ -45,7 +46,8 @@ struct GtaRZParams {
   double *tpsi, *pinc, *psim, *tinc;
 };
 
-// SweepGreyUCBrzKernelNew for one (zone, angle)
+// SweepGreyUCBrzKernelNew for one (zone, angle); loops fully unrolled and dynamic corner indices through select chains
+// (device_util.h) so that the zone stays in registers
 template <int MC>
 __device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
   const int nc = P.nc;
@@ -57,79 +59,99 @@ __device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
   const double fac = P.fac[a];
-  double Q[MC], src[MC], Sigt[MC], denom[MC], pinc[MC], coefpsi[MC][2];
-  int nxez[MC], ez_exit[MC][2];
+  double Q[MC], src[MC], Sigt[MC], denom[MC], pinc[MC], area[MC], pmOld[MC], tiOld[MC], coef[MC][2], aezv[MC][2];
+  int cezv[MC][2], rowv[MC][2];
+  unsigned exitMask = 0u;
 #pragma unroll
   for (int c = 0; c < MC; c++) {
-    nxez[c] = 0;
+    Q[c] = 0.0; src[c] = 0.0; Sigt[c] = 1.0; denom[c] = 1.0; pinc[c] = 0.0; area[c] = 0.0; pmOld[c] = 0.0; tiOld[c] = 0.0;
     if (c < nCorner) {
       const int cc = c0 + c;
-      const double t = P.tsa[cc], area = P.Area[cc], vol = P.Volume[cc];
+      const double t = P.tsa[cc], vol = P.Volume[cc];
+      area[c] = P.Area[cc];
+      pmOld[c] = psimL[cc]; tiOld[c] = tincL[cc];
       Q[c] = P.sigtInv[cc] * t;
-      src[c] = vol * t + fac * area * psimL[cc];
+      src[c] = vol * t + fac * area[c] * pmOld[c];
       Sigt[c] = P.sigTotal[cc];
-      denom[c] = Sigt[c] * vol + fac * area;
-      pinc[c] = fac * area * tincL[cc];
+      denom[c] = Sigt[c] * vol + fac * area[c];
+      pinc[c] = fac * area[c] * tiOld[c];
     }
   }
-  for (int c = 0; c < nCorner; c++) {
-    const int cc = c0 + c;
 #pragma unroll
-    for (int f = 0; f < 2; f++) {
-      const double afp = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
-      const double aez = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
-      double psifp = 0.0;
-      if (afp < 0.0) {
-        const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
-        psifp = __ldcg(&tpsi[P.cFP[cc * 2 + f]]);
-        denom[c] -= R_afp;
-        src[c] -= R_afp * psifp;
-        pinc[c] -= R_afp * psifp;
-      }
-      if (aez > 0.0) {
-        const double R = P.RadiusEZ[cc * 2 + f];
-        const int cez = P.cEZ[cc * 2 + f];
-        ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = R * aez; nxez[c]++;
-        denom[cez] += R * aez;
-        double sez;
+  for (int c = 0; c < MC; c++) {
+#pragma unroll
+    for (int f = 0; f < 2; f++) { coef[c][f] = 0.0; aezv[c][f] = 0.0; cezv[c][f] = 0; rowv[c][f] = 0; }
+    if (c < nCorner) {
+      const int cc = c0 + c;
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double afp = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
+        const double aez = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
+        const int row = P.cFP[cc * 2 + f];
+        rowv[c][f] = row;
+        double psifp = 0.0;
         if (afp < 0.0) {
-          const double sigA = Sigt[c] * P.Area[cc], sigA2 = sigA * sigA;
-          const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
-          const double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
-          sez = R * (gtau * sigA * (psifp - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - Q[cez]));
-          pinc[c] += R * gtau * sigA * psifp;
-          pinc[cez] -= R * gtau * sigA * psifp;
-        } else {
-          sez = 0.5 * R * aez * (Q[c] - Q[cez]);
+          const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
+          psifp = __ldcg(&tpsi[row]);
+          denom[c] -= R_afp;
+          src[c] -= R_afp * psifp;
+          pinc[c] -= R_afp * psifp;
+        } else if (row >= nc) exitMask |= 1u << (2 * c + f);
+        if (aez > 0.0) {
+          const double R = P.RadiusEZ[cc * 2 + f];
+          const int cez = P.cEZ[cc * 2 + f];
+          aezv[c][f] = aez; cezv[c][f] = cez; coef[c][f] = R * aez;
+          addto<MC>(denom, cez, R * aez);
+          const double qcez = pick<MC>(Q, cez);
+          double sez;
+          if (afp < 0.0) {
+            const double sigA = Sigt[c] * area[c], sigA2 = sigA * sigA;
+            const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+            const double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+            sez = R * (gtau * sigA * (psifp - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - qcez));
+            const double gi = R * gtau * sigA * psifp;
+            pinc[c] += gi;
+            addto<MC>(pinc, cez, -gi);
+          } else {
+            sez = 0.5 * R * aez * (Q[c] - qcez);
+          }
+          src[c] += sez;
+          addto<MC>(src, cez, -sez);
         }
-        src[c] += sez;
-        src[cez] -= sez;
       }
     }
   }
-  for (int i = 0; i < nCorner; i++) {
-    const int c = nextC[c0 + i];
-    const double p = src[c] / denom[c], pi = pinc[c] / denom[c];
-    src[c] = p; pinc[c] = pi;   // src now holds the corner flux
-    for (int k = 0; k < nxez[c]; k++) {
-      const int cez = ez_exit[c][k];
-      src[cez] += coefpsi[c][k] * p;
-      pinc[cez] += coefpsi[c][k] * pi;
+#pragma unroll
+  for (int i = 0; i < MC; i++) {
+    if (i < nCorner) {
+      const int c = nextC[c0 + i];
+      const double d = pick<MC>(denom, c);
+      const double p = pick<MC>(src, c) / d, pi = pick<MC>(pinc, c) / d;
+      put<MC>(src, c, p); put<MC>(pinc, c, pi);   // src now holds the corner flux
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        double cf = coef[0][f], az = aezv[0][f];
+        int cez = cezv[0][f];
+#pragma unroll
+        for (int k = 1; k < MC; k++) { cf = c == k ? coef[k][f] : cf; az = c == k ? aezv[k][f] : az; cez = c == k ? cezv[k][f] : cez; }
+        if (az > 0.0) { addto<MC>(src, cez, cf * p); addto<MC>(pinc, cez, cf * pi); }
+      }
     }
   }
   // corner fluxes, exiting boundary fluxes (:314-319), half-angle values for the next angle of the level (:120-130, :321-329)
   const bool starting = P.start[a] != 0;
   const double w1 = P.w1[a], w2 = P.w2[a];
-  for (int c = 0; c < nCorner; c++) {
-    const int cc = c0 + c;
-    tpsi[cc] = src[c];
-    pincA[cc] = pinc[c];
-    psimL[cc] = starting ? src[c] : w1 * src[c] - w2 * psimL[cc];
-    tincL[cc] = starting ? pinc[c] : w1 * pinc[c] - w2 * tincL[cc];
 #pragma unroll
-    for (int f = 0; f < 2; f++) {
-      const int row = P.cFP[cc * 2 + f];
-      if (row >= nc && !(dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2) < 0.0)) tpsi[row] = src[c];
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      const int cc = c0 + c;
+      tpsi[cc] = src[c];
+      pincA[cc] = pinc[c];
+      psimL[cc] = starting ? src[c] : w1 * src[c] - w2 * pmOld[c];
+      tincL[cc] = starting ? pinc[c] : w1 * pinc[c] - w2 * tiOld[c];
+#pragma unroll
+      for (int f = 0; f < 2; f++)
+        if (exitMask & (1u << (2 * c + f))) tpsi[rowv[c][f]] = src[c];
     }
   }
 }

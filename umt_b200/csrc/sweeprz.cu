@@ -18,8 +18,10 @@
 // Psi/PsiB <- PsiM are written by the thread that owns the corner.
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 
 #include "umt_internal.h"
+#include "device_util.h"
 
 namespace {
 
@@ -42,6 +44,11 @@ struct SweepRZParams {
   int *counters;
   const double *psi, *stotal, *sigt;
   double *psi1, *psim;
+  // chain kernel: one CTA per (xi-level, block of gb groups)
+  int gb, nGroupBlocks, maxAngLevel, hypStride;
+  const int *levelAngles;   // (nLevels, maxAngLevel) swept angles of each level in order, -1 padded
+  const int *planeOff;      // (NA, hypStride) first zone of each plane in nextZ(:,a); planeOff[a][nHyp[a]] = nz
+  const int *nHyp;          // (NA)
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -50,13 +57,18 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
   return v;
 }
 
+// Dynamic corner indices (cEZ, nextC) would put the per-thread zone arrays in local memory, and with a few hundred threads per SM
+// those 700-byte frames fall out of L1: every "array" access then costs an L2 round trip inside a dependent chain.  All loops
+// over corners and faces are therefore fully unrolled and the few dynamic accesses go through select chains, which keeps the
+// whole zone in registers.
 // Everything of one (zone, group) solve that does not depend on other work items: loaded and computed while the CTA's
 // dependencies are still being resolved, so that after the wait only the upstream fluxes and PsiM remain to be read.
 template <int MC>
 struct ZoneStatic {
-  double Q[MC], srcInit[MC], sumArea[MC], volSig[MC], areaFac[MC];
-  double afp[MC][2], aez[MC][2], Rafp[MC][2], Raez[MC][2];
+  double Q[MC], srcInit[MC], sumArea[MC], volSig[MC], areaFac[MC], area[MC];
+  double aez[MC][2], Rafp[MC][2], Raez[MC][2], Rez[MC][2];
   int row[MC][2], cez[MC][2];
+  unsigned inMask, exitMask;   // bit 2c+f: omega.A_fp < 0 (incident) / omega.A_fp > 0 on a boundary face (exiting)
   int nCorner, c0;
   double sig;
 };
@@ -71,9 +83,10 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
   const double sig = P.sigt[(size_t)zone * G + g];
   const double fac = P.angDerivFac[a];
-  Z.nCorner = nCorner; Z.c0 = c0; Z.sig = sig;
+  Z.nCorner = nCorner; Z.c0 = c0; Z.sig = sig; Z.inMask = 0u; Z.exitMask = 0u;
 #pragma unroll
   for (int c = 0; c < MC; c++) {
+    Z.Q[c] = 0.0; Z.srcInit[c] = 0.0; Z.sumArea[c] = 1.0; Z.volSig[c] = 0.0; Z.areaFac[c] = 0.0; Z.area[c] = 0.0;
     if (c < nCorner) {
       const size_t r = (size_t)(c0 + c) * G + g;
       const double source = P.stotal[r] + P.tau * psiA[r];
@@ -83,10 +96,13 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
       Z.sumArea[c] = fac * area;
       Z.volSig[c] = sig * vol;
       Z.areaFac[c] = area * fac;
+      Z.area[c] = area;
     }
   }
 #pragma unroll
   for (int c = 0; c < MC; c++) {
+#pragma unroll
+    for (int f = 0; f < 2; f++) { Z.aez[c][f] = 0.0; Z.Rafp[c][f] = 0.0; Z.Raez[c][f] = 0.0; Z.Rez[c][f] = 0.0; Z.row[c][f] = 0; Z.cez[c][f] = 0; }
     if (c < nCorner) {
       const int cc = c0 + c;
 #pragma unroll
@@ -95,21 +111,28 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
         const double *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
         const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
         const double aez = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
-        Z.afp[c][f] = afp; Z.aez[c][f] = aez;
-        Z.row[c][f] = P.cFP[cc * 2 + f];
+        const int row = P.cFP[cc * 2 + f];
+        Z.aez[c][f] = aez;
+        Z.row[c][f] = row;
         Z.cez[c][f] = P.cEZ[cc * 2 + f];
-        Z.Rafp[c][f] = 0.0; Z.Raez[c][f] = 0.0;
         if (afp < 0.0) {
+          Z.inMask |= 1u << (2 * c + f);
           Z.Rafp[c][f] = P.RadiusFP[cc * 2 + f] * afp;
           Z.sumArea[c] -= Z.Rafp[c][f];
-        }
+        } else if (afp > 0.0 && row >= nc) Z.exitMask |= 1u << (2 * c + f);
         if (aez > 0.0) {
-          Z.Raez[c][f] = P.RadiusEZ[cc * 2 + f] * aez;
-          Z.sumArea[Z.cez[c][f]] += Z.Raez[c][f];
+          Z.Rez[c][f] = P.RadiusEZ[cc * 2 + f];
+          Z.Raez[c][f] = Z.Rez[c][f] * aez;
         }
       }
     }
   }
+  // the EZ face of corner c adds to the denominator of the corner behind it (second pass: sumArea of every corner is initialised)
+#pragma unroll
+  for (int c = 0; c < MC; c++)
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+      if (c < nCorner && Z.aez[c][f] > 0.0) addto<MC>(Z.sumArea, Z.cez[c][f], Z.Raez[c][f]);
 }
 
 // SweepUCBrz.F90:103-243 for one (zone, group), second half: upstream fluxes, closure, corner solves, PsiM, exits.
@@ -126,62 +149,81 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
   double src[MC], psifp[MC][2], pm[MC];
 #pragma unroll
   for (int c = 0; c < MC; c++) {
+    src[c] = Z.srcInit[c];
+    pm[c] = 0.0;
+    psifp[c][0] = 0.0; psifp[c][1] = 0.0;
     if (c < nCorner) {
-      src[c] = Z.srcInit[c];
       pm[c] = psimL[(size_t)(c0 + c) * G + g];
 #pragma unroll
-      for (int f = 0; f < 2; f++) psifp[c][f] = Z.afp[c][f] < 0.0 ? __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]) : 0.0;
+      for (int f = 0; f < 2; f++)
+        if (Z.inMask & (1u << (2 * c + f))) psifp[c][f] = __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]);
     }
   }
-  for (int c = 0; c < nCorner; c++) {
-    const double area = P.Area[c0 + c];
 #pragma unroll
-    for (int f = 0; f < 2; f++) {
-      const double afp = Z.afp[c][f], aez = Z.aez[c][f];
-      if (afp < 0.0) src[c] -= Z.Rafp[c][f] * psifp[c][f];
-      if (aez > 0.0) {
-        const int cez = Z.cez[c][f];
-        double sez;
-        if (afp < 0.0) {
-          const double R = P.RadiusEZ[(c0 + c) * 2 + f];
-          const double sigA = sig * area, sigA2 = sigA * sigA;
-          const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
-          const double gden = area * (4.0 * sigA * sigA2 + aez * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
-          sez = R * (area * gnum * (sig * psifp[c][f] - Z.Q[c]) + 0.5 * aez * gden * (Z.Q[c] - Z.Q[cez])) / (gnum + gden * sig);
-        } else {
-          sez = 0.5 * Z.Raez[c][f] * (Z.Q[c] - Z.Q[cez]) / sig;
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      const double area = Z.area[c];
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const bool inc = (Z.inMask >> (2 * c + f)) & 1u;
+        const double aez = Z.aez[c][f];
+        if (inc) src[c] -= Z.Rafp[c][f] * psifp[c][f];
+        if (aez > 0.0) {
+          const int cez = Z.cez[c][f];
+          const double qcez = pick<MC>(Z.Q, cez);
+          double sez;
+          if (inc) {
+            const double R = Z.Rez[c][f];
+            const double sigA = sig * area, sigA2 = sigA * sigA;
+            const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
+            const double gden = area * (4.0 * sigA * sigA2 + aez * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
+            sez = R * (area * gnum * (sig * psifp[c][f] - Z.Q[c]) + 0.5 * aez * gden * (Z.Q[c] - qcez)) / (gnum + gden * sig);
+          } else {
+            sez = 0.5 * Z.Raez[c][f] * (Z.Q[c] - qcez) / sig;
+          }
+          src[c] += sez;
+          addto<MC>(src, cez, -sez);
         }
-        src[c] += sez;
-        src[cez] -= sez;
       }
     }
   }
-  for (int i = 0; i < nCorner; i++) {
-    const int c = nextC[c0 + i];
-    const double p = (src[c] + Z.areaFac[c] * pm[c]) / (Z.sumArea[c] + Z.volSig[c]);
-    src[c] = p;   // src now holds the corner flux
 #pragma unroll
-    for (int f = 0; f < 2; f++)
-      if (Z.aez[c][f] > 0.0) src[Z.cez[c][f]] += Z.Raez[c][f] * p;
+  for (int i = 0; i < MC; i++) {
+    if (i < nCorner) {
+      const int c = nextC[c0 + i];
+      const double p = (pick<MC>(src, c) + pick<MC>(Z.areaFac, c) * pick<MC>(pm, c)) / (pick<MC>(Z.sumArea, c) + pick<MC>(Z.volSig, c));
+      put<MC>(src, c, p);   // src now holds the corner flux
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        double raez = Z.Raez[0][f], aez = Z.aez[0][f];
+        int cez = Z.cez[0][f];
+#pragma unroll
+        for (int k = 1; k < MC; k++) { raez = c == k ? Z.Raez[k][f] : raez; aez = c == k ? Z.aez[k][f] : aez; cez = c == k ? Z.cez[k][f] : cez; }
+        if (aez > 0.0) addto<MC>(src, cez, raez * p);
+      }
+    }
   }
   // half-angle intensity for the next angle of the level; exiting boundary fluxes; finishing direction
   const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
   double *psi1N = psi1A + slab;   // slab of angle a+1 (only touched when it is a finishing direction)
   const double w1 = P.tauW1[a], w2 = P.tauW2[a];
-  for (int c = 0; c < nCorner; c++) {
-    const int cc = c0 + c;
-    const size_t r = (size_t)cc * G + g;
-    const double p = src[c];
-    const double pmn = starting ? p : w1 * p - w2 * pm[c];
-    psimL[r] = pmn;
-    psi1A[r] = p;
-    if (fin) psi1N[r] = pmn;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
 #pragma unroll
-    for (int f = 0; f < 2; f++) {
-      const int row = Z.row[c][f];
-      if (row >= nc && Z.afp[c][f] > 0.0) {
-        psi1A[(size_t)row * G + g] = p;             // PsiB(:,b,Angle)   <- Psi1(:,c)
-        if (fin) psi1N[(size_t)row * G + g] = pmn;  // PsiB(:,b,Angle+1) <- PsiM(:,c)
+  for (int c = 0; c < MC; c++) {
+    if (c < nCorner) {
+      const int cc = c0 + c;
+      const size_t r = (size_t)cc * G + g;
+      const double p = src[c];
+      const double pmn = starting ? p : w1 * p - w2 * pm[c];
+      psimL[r] = pmn;
+      psi1A[r] = p;
+      if (fin) psi1N[r] = pmn;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        if (Z.exitMask & (1u << (2 * c + f))) {
+          const int row = Z.row[c][f];
+          psi1A[(size_t)row * G + g] = p;             // PsiB(:,b,Angle)   <- Psi1(:,c)
+          if (fin) psi1N[(size_t)row * G + g] = pmn;  // PsiB(:,b,Angle+1) <- PsiM(:,c)
+        }
       }
     }
   }
@@ -226,12 +268,79 @@ __global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
   }
 }
 
+// Chain kernel.  In r-z the groups are independent of each other and the xi-levels are independent of each other, while
+// within (level, group) everything is one dependency chain: the planes of an angle in order, the angles of the level in order
+// (PsiM).  One CTA therefore owns one (xi-level, block of gb groups) and walks that chain by itself: every thread takes
+// (zone, group) pairs of the current plane, a __syncthreads() separates planes -- no tickets, no global counters, no device-
+// scope fences, no polling.  A plane step costs the latency of one zone solve instead of the ~10 us of a global
+// signal/poll round trip, which is what bounded sweeprz_kernel (planes of ~80 zones x 2400 dependent steps per level).
+// The static half of the next pair is computed before the barrier (it does not depend on the previous plane).
+template <int MC>
+__global__ void __launch_bounds__(256) sweeprz_chain_kernel(SweepRZParams P) {
+  const int lev = blockIdx.x / P.nGroupBlocks, g0 = (blockIdx.x - lev * P.nGroupBlocks) * P.gb;
+  const int gb = min(P.gb, P.G - g0);
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int k = 0; k < P.maxAngLevel; k++) {
+    const int a = P.levelAngles[lev * P.maxAngLevel + k];
+    if (a < 0) break;
+    const int *nextZ = P.nextZ + (size_t)a * P.nz;
+    const int *off = P.planeOff + (size_t)a * P.hypStride;
+    const int nh = P.nHyp[a];
+    for (int p = 0; p < nh; p++) {
+      const int zbeg = off[p], npairs = (off[p + 1] - zbeg) * gb;
+      int idx = tid;
+      ZoneStatic<MC> Z;
+      int g = 0;
+      if (idx < npairs) { const int zi = idx / gb; g = g0 + idx - zi * gb; zone_static_rz<MC>(P, a, nextZ[zbeg + zi], g, Z); }
+      __syncthreads();   // the previous plane (and the previous angle of the level) is complete and visible to the CTA
+      while (idx < npairs) {
+        zone_solve_rz<MC>(P, a, g, Z);
+        idx += T;
+        if (idx < npairs) { const int zi = idx / gb; g = g0 + idx - zi * gb; zone_static_rz<MC>(P, a, nextZ[zbeg + zi], g, Z); }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // Work items of the RZ sweep in a topological order of both dependencies (host side, once per schedule).
 int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
   int maxHyp = 0;
-  return umt_build_items_rz_set(ctx->nz, ctx->NA, ctx->nHyp, ctx->zonesInPlane, ctx->nextZ, ctx->h_start, zpi, items, ctx->h_level, ctx->nLevels, maxHyp);
+  int r = umt_build_items_rz_set(ctx->nz, ctx->NA, ctx->nHyp, ctx->zonesInPlane, ctx->nextZ, ctx->h_start, zpi, items, ctx->h_level, ctx->nLevels, maxHyp);
+  if (r || ctx->device < 0) return r;
+  // tables of the chain kernel: swept angles of every level in order, plane offsets, and its geometry: gb groups per CTA so
+  // that a (corner, group block) access is at least one 32-byte sector, as many threads as the largest plane has pairs
+  const int NA = ctx->NA, nL = ctx->nLevels;
+  int maxAng = 1, maxPlane = 1;
+  std::vector<int> cnt(nL, 0);
+  for (int a = 0; a < NA; a++) if (ctx->nHyp[a] > 0) maxAng = std::max(maxAng, ++cnt[ctx->h_level[a]]);
+  std::vector<int> la((size_t)nL * maxAng, -1), po((size_t)NA * (maxHyp + 1), 0), nh(NA, 0);
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (int a = 0; a < NA; a++) {
+    nh[a] = ctx->nHyp[a];
+    if (nh[a] == 0) continue;
+    la[(size_t)ctx->h_level[a] * maxAng + cnt[ctx->h_level[a]]++] = a;
+    int o = 0;
+    for (int p = 0; p < nh[a]; p++) { po[(size_t)a * (maxHyp + 1) + p] = o; o += ctx->zonesInPlane[a][p]; maxPlane = std::max(maxPlane, ctx->zonesInPlane[a][p]); }
+    po[(size_t)a * (maxHyp + 1) + nh[a]] = o;
+  }
+  int gb = std::min(ctx->G, 4);
+  if (const char *e = getenv("UMT_RZ_GROUP_BLOCK")) gb = std::max(1, std::min(ctx->G, atoi(e)));
+  ctx->rz_gb = gb;
+  ctx->rz_maxAngLevel = maxAng;
+  ctx->rz_threads = std::max(32, std::min(256, (maxPlane * gb + 31) / 32 * 32));
+  ctx->rz_chain = false;   // measured at configs[1]: item kernel 16.7 ms, chain kernel 33.7 ms (a pair solve is ~12 us of dependent latency either way; the item kernel also pipelines the angles of a level)
+  if (const char *e = getenv("UMT_RZ_KERNEL")) ctx->rz_chain = std::string(e) == "chain";
+  auto up = [&](int **d, const std::vector<int> &h) -> int {
+    if (*d) { cudaFree(*d); *d = nullptr; }
+    UMT_CUDA(ctx, cudaMalloc((void **)d, sizeof(int) * std::max<size_t>(h.size(), 1)));
+    UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+    return UMT_OK;
+  };
+  if ((r = up(&ctx->d_rzLevelAngles, la))) return r;
+  if ((r = up(&ctx->d_rzPlaneOff, po))) return r;
+  return up(&ctx->d_rzNHyp, nh);
 }
 
 // the same for any r-z angle set (the Sn set above, the GTA set in gta_rz.cu); angles with nHyp == 0 (finishing directions) get no items
@@ -326,6 +435,15 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   // Set%PsiM = 0 at the start of every flux pass (SetSweep.F90:94-96)
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * (size_t)ctx->nLevels * ctx->nc * ctx->G, ctx->stream));
+  if (ctx->rz_chain) {
+    P.gb = ctx->rz_gb; P.nGroupBlocks = (ctx->G + ctx->rz_gb - 1) / ctx->rz_gb; P.maxAngLevel = ctx->rz_maxAngLevel; P.hypStride = ctx->maxHyp + 1;
+    P.levelAngles = ctx->d_rzLevelAngles; P.planeOff = ctx->d_rzPlaneOff; P.nHyp = ctx->d_rzNHyp;
+    void (*ck)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_chain_kernel<4> : sweeprz_chain_kernel<MAXC2>;
+    ck<<<ctx->nLevels * P.nGroupBlocks, ctx->rz_threads, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches += 1;
+    return UMT_OK;
+  }
   void (*kern)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_kernel<4> : sweeprz_kernel<MAXC2>;
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RZ_BLOCK, 0));

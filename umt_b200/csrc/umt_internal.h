@@ -135,6 +135,10 @@ struct umt_ctx {
   int *d_level = nullptr;
   std::vector<int> h_level;
   int nLevels = 0;
+  // r-z chain kernel (sweeprz.cu): one CTA per (xi-level, group block)
+  bool rz_chain = false;
+  int rz_gb = 4, rz_maxAngLevel = 0, rz_threads = 256;
+  int *d_rzLevelAngles = nullptr, *d_rzPlaneOff = nullptr, *d_rzNHyp = nullptr;
   // device: schedule
   int *d_nextZ = nullptr;              // (NA, nz) signed 1-based
   unsigned char *d_nextC = nullptr;    // (NA, nc) 0-based local corner
