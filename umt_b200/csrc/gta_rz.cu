@@ -12,6 +12,8 @@
 // the 3-D grey sweep (gta.cu), pInc (8, nc) is summed in fixed angle order afterwards (deterministic PhiInc).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "umt_internal.h"
 #include "device_util.h"
@@ -77,30 +79,47 @@ __device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
       pinc[c] = fac * area[c] * tiOld[c];
     }
   }
+  // every load of the face loop up front and unconditional (rows of outgoing faces are read and ignored): inside the sign tests
+  // they would be issued one dependent round trip after the other
+  double afpv[MC][2], Rfp[MC][2], Rez[MC][2], psiup[MC][2];
+#pragma unroll
+  for (int c = 0; c < MC; c++)
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      coef[c][f] = 0.0; aezv[c][f] = 0.0; cezv[c][f] = 0; rowv[c][f] = 0; afpv[c][f] = 0.0; Rfp[c][f] = 0.0; Rez[c][f] = 0.0;
+      if (c < nCorner) {
+        const int cc = c0 + c;
+        afpv[c][f] = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
+        aezv[c][f] = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
+        rowv[c][f] = P.cFP[cc * 2 + f];
+        cezv[c][f] = P.cEZ[cc * 2 + f];
+        Rfp[c][f] = P.RadiusFP[cc * 2 + f];
+        Rez[c][f] = P.RadiusEZ[cc * 2 + f];
+      }
+    }
+#pragma unroll
+  for (int c = 0; c < MC; c++)
+#pragma unroll
+    for (int f = 0; f < 2; f++) psiup[c][f] = c < nCorner ? __ldcg(&tpsi[rowv[c][f]]) : 0.0;
 #pragma unroll
   for (int c = 0; c < MC; c++) {
-#pragma unroll
-    for (int f = 0; f < 2; f++) { coef[c][f] = 0.0; aezv[c][f] = 0.0; cezv[c][f] = 0; rowv[c][f] = 0; }
     if (c < nCorner) {
-      const int cc = c0 + c;
 #pragma unroll
       for (int f = 0; f < 2; f++) {
-        const double afp = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
-        const double aez = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
-        const int row = P.cFP[cc * 2 + f];
-        rowv[c][f] = row;
+        const double afp = afpv[c][f], aez = aezv[c][f];
+        const int row = rowv[c][f];
         double psifp = 0.0;
         if (afp < 0.0) {
-          const double R_afp = P.RadiusFP[cc * 2 + f] * afp;
-          psifp = __ldcg(&tpsi[row]);
+          const double R_afp = Rfp[c][f] * afp;
+          psifp = psiup[c][f];
           denom[c] -= R_afp;
           src[c] -= R_afp * psifp;
           pinc[c] -= R_afp * psifp;
         } else if (row >= nc) exitMask |= 1u << (2 * c + f);
         if (aez > 0.0) {
-          const double R = P.RadiusEZ[cc * 2 + f];
-          const int cez = P.cEZ[cc * 2 + f];
-          aezv[c][f] = aez; cezv[c][f] = cez; coef[c][f] = R * aez;
+          const double R = Rez[c][f];
+          const int cez = cezv[c][f];
+          coef[c][f] = R * aez;
           addto<MC>(denom, cez, R * aez);
           const double qcez = pick<MC>(Q, cez);
           double sez;
@@ -180,6 +199,31 @@ __global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) 
     if (threadIdx.x == 0) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
+    }
+  }
+}
+
+// Chain variant: with one group the only independent chains are the xi-levels, so one CTA per level walks its angles and
+// planes by itself, a __syncthreads() between planes instead of a global signal/poll round trip (see sweeprz_chain_kernel).
+template <int MC>
+__global__ void __launch_bounds__(256) gta_sweep_rz_chain_kernel(GtaRZParams P, const int *levelAngles, int maxAngLevel, const int *planeOff,
+                                                                  int hypStride, const int *nHyp) {
+  const int lev = blockIdx.x;
+  for (int k = 0; k < maxAngLevel; k++) {
+    const int a = levelAngles[lev * maxAngLevel + k];
+    if (a < 0) break;
+    const int *nextZ = P.nextZ + (size_t)a * P.nz;
+    const int *off = planeOff + (size_t)a * hypStride;
+    const int nh = nHyp[a];
+    for (int p = 0; p < nh; p++) {
+      const int zbeg = off[p], n = off[p + 1] - zbeg;
+      int zone0 = 0;
+      if ((int)threadIdx.x < n) zone0 = nextZ[zbeg + threadIdx.x];
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (i != (int)threadIdx.x) zone0 = nextZ[zbeg + i];
+        gta_zone_rz<MC>(P, a, zone0);
+      }
     }
   }
 }
@@ -305,6 +349,28 @@ int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items) {
   UMT_CUDA(ctx, cudaMemcpy(g.d_fac, g.angDerivFac.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_w1, g.tauW1.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_w2, g.tauW2.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  // tables of the chain kernel
+  int maxAng = 1, maxPlane = 1;
+  std::vector<int> cnt(g.nLevels, 0);
+  for (int a = 0; a < g.nAng; a++) if (g.nHyp[a] > 0) maxAng = std::max(maxAng, ++cnt[g.level[a]]);
+  std::vector<int> la((size_t)g.nLevels * maxAng, -1), po((size_t)g.nAng * (g.maxHyp + 1), 0), nh(g.nAng, 0);
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (int a = 0; a < g.nAng; a++) {
+    nh[a] = g.nHyp[a];
+    if (nh[a] == 0) continue;
+    la[(size_t)g.level[a] * maxAng + cnt[g.level[a]]++] = a;
+    int o = 0;
+    for (int p = 0; p < nh[a]; p++) { po[(size_t)a * (g.maxHyp + 1) + p] = o; o += g.zonesInPlane[a][p]; maxPlane = std::max(maxPlane, g.zonesInPlane[a][p]); }
+    po[(size_t)a * (g.maxHyp + 1) + nh[a]] = o;
+  }
+  g.rz_maxAngLevel = maxAng;
+  g.rz_threads = std::max(32, std::min(256, (maxPlane + 31) / 32 * 32));
+  g.rz_chain = true;
+  if (const char *e = getenv("UMT_GTA_RZ_KERNEL")) g.rz_chain = std::string(e) != "items";
+  TRY(dalloc2(ctx, &g.d_levelAngles, la.size())); TRY(dalloc2(ctx, &g.d_planeOff, po.size())); TRY(dalloc2(ctx, &g.d_nHyp, nh.size()));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_levelAngles, la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_planeOff, po.data(), sizeof(int) * po.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, cudaMemcpy(g.d_nHyp, nh.data(), sizeof(int) * nh.size(), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 
@@ -322,6 +388,12 @@ int umt_gta_launch_sweep_rz(umt_ctx *ctx) {
   P.omega = g.d_omega; P.fac = g.d_fac; P.w1 = g.d_w1; P.w2 = g.d_w2; P.start = g.d_start; P.level = g.d_level;
   P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
   P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc; P.psim = g.d_psim; P.tinc = g.d_tinc;
+  if (g.rz_chain) {
+    auto ck = ctx->maxCorner <= 4 ? gta_sweep_rz_chain_kernel<4> : gta_sweep_rz_chain_kernel<MAXC2>;
+    ck<<<g.nLevels, g.rz_threads, 0, ctx->stream>>>(P, g.d_levelAngles, g.rz_maxAngLevel, g.d_planeOff, g.maxHyp + 1, g.d_nHyp);
+    UMT_CUDA(ctx, cudaGetLastError());
+    return UMT_OK;
+  }
   void (*kern)(GtaRZParams) = ctx->maxCorner <= 4 ? gta_sweep_rz_kernel<4> : gta_sweep_rz_kernel<MAXC2>;
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GRZ_BLOCK, 0));

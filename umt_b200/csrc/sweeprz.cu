@@ -115,14 +115,15 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
         Z.aez[c][f] = aez;
         Z.row[c][f] = row;
         Z.cez[c][f] = P.cEZ[cc * 2 + f];
+        const double rfp = P.RadiusFP[cc * 2 + f], rez = P.RadiusEZ[cc * 2 + f];   // unconditional: not one round trip per sign test
         if (afp < 0.0) {
           Z.inMask |= 1u << (2 * c + f);
-          Z.Rafp[c][f] = P.RadiusFP[cc * 2 + f] * afp;
+          Z.Rafp[c][f] = rfp * afp;
           Z.sumArea[c] -= Z.Rafp[c][f];
         } else if (afp > 0.0 && row >= nc) Z.exitMask |= 1u << (2 * c + f);
         if (aez > 0.0) {
-          Z.Rez[c][f] = P.RadiusEZ[cc * 2 + f];
-          Z.Raez[c][f] = Z.Rez[c][f] * aez;
+          Z.Rez[c][f] = rez;
+          Z.Raez[c][f] = rez * aez;
         }
       }
     }

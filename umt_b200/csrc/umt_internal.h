@@ -98,6 +98,9 @@ struct GtaState {
   int *d_level = nullptr;
   double *d_fac = nullptr, *d_w1 = nullptr, *d_w2 = nullptr, *d_psim = nullptr, *d_tinc = nullptr;   // psim/tinc: (nLevels, nc)
   unsigned char *d_finish = nullptr;
+  bool rz_chain = false;               // one CTA per xi-level (gta_sweep_rz_chain_kernel)
+  int rz_maxAngLevel = 0, rz_threads = 64;
+  int *d_levelAngles = nullptr, *d_planeOff = nullptr, *d_nHyp = nullptr;
 };
 
 struct umt_ctx {
