@@ -528,3 +528,165 @@ def oracle_gta_multi_solve(meshes, Ps, lists, Phis, geoms, epsPoint=1e-6, maxIte
             raise RuntimeError("oracle_gta_multi_solve: not converging")
         rrOld = rr
     return corr, n, err
+
+
+# ---------------------------------------------------------------------------
+# SweepScheduler (rt/SweepScheduler.F90:32-313) and the per-step exchange of SetSweep.F90:113-170, lock step on every rank
+# ---------------------------------------------------------------------------
+def oracle_net_flux(problems, lists):
+    """setNetFlux.F90:61-141: NetFlux[r][k, a] = my exit current of angle a through shared boundary k minus the neighbour's."""
+    NA = problems[0].NA
+    ex = []
+    for r, p in enumerate(problems):
+        per_b = []
+        for k, b in enumerate(shared_boundaries(p.mesh)):
+            e = np.zeros(NA)
+            for a in range(NA):
+                el = lists[r][k][a][0]
+                dot = p.geom["A_bdy"][el - 1] @ p.omega[a]
+                e[a] = p.weight[a] * float((dot * p.PsiB[a, el - 1].sum(axis=1)).sum())
+            per_b.append(e)
+        ex.append(per_b)
+    out = []
+    for r, p in enumerate(problems):
+        nf = []
+        for k, b in enumerate(shared_boundaries(p.mesh)):
+            kq = [i for i, x in enumerate(shared_boundaries(problems[b.neighbor].mesh)) if x.neighbor == r][0]
+            nf.append(ex[r][k] - ex[b.neighbor][kq])
+        out.append(np.array(nf).reshape(len(nf), NA))
+    return out
+
+
+def oracle_sweep_scheduler(problems, nCommSets, netflux, mrefs=None):
+    """Every rank's CSet%AngleOrder (comm sets concatenated, 0-based angles) and RecvOrder[k] per shared boundary.
+    netflux[r] is (nShared_r, NA); mrefs[r][n][a] the mirror angle of a on reflecting boundary n (-1: not incident)."""
+    N, NA = len(problems), problems[0].NA
+    bps = NA // nCommSets
+    depend = [netflux[r].sum(axis=0) if len(netflux[r]) else np.zeros(NA) for r in range(N)]
+    depend = [d.copy() for d in depend]
+    nRefl = [np.zeros(NA, int) for _ in range(N)]
+    depAngle = []
+    for r in range(N):
+        mr = mrefs[r] if mrefs is not None else []
+        da = -np.ones((max(len(mr), 1), NA), int)
+        for n, m in enumerate(mr):
+            for a in range(NA):
+                if m[a] >= 0:
+                    da[n, m[a]] = a
+                    nRefl[r][a] += 1
+        depAngle.append(da)
+    notDone = [np.ones(NA, bool) for _ in range(N)]
+    order = [np.zeros(NA, int) for _ in range(N)]
+    nbrs = [shared_boundaries(p.mesh) for p in problems]
+    recv = [[np.zeros(NA, int) for _ in nbrs[r]] for r in range(N)]
+    for i in range(bps):
+        new = []
+        for r in range(N):
+            nb = []
+            for c in range(nCommSets):
+                bins = [b for b in range(c * bps, (c + 1) * bps) if notDone[r][b]]
+                imin = min(bins, key=lambda b: (nRefl[r][b], b))
+                if nRefl[r][imin] != 0:
+                    nRefl[r][imin] = 0
+                ready = [b for b in bins if nRefl[r][b] == 0]
+                best = ready[0]
+                for b in ready[1:]:
+                    if depend[r][b] > depend[r][best]:
+                        best = b
+                nb.append(best)
+            new.append(nb)
+        for r in range(N):
+            for c in range(nCommSets):
+                b = new[r][c]
+                order[r][c * bps + i] = b
+                for n in range(depAngle[r].shape[0]):
+                    aRef = depAngle[r][n, b]
+                    if aRef >= 0 and notDone[r][aRef]:
+                        nRefl[r][aRef] -= 1
+                notDone[r][b] = False
+        for r in range(N):
+            for k, sb in enumerate(nbrs[r]):
+                for c in range(nCommSets):
+                    b = new[sb.neighbor][c]
+                    recv[r][k][c * bps + i] = b
+                    if notDone[r][b]:
+                        depend[r][b] -= netflux[r][k, b]
+    return order, recv
+
+
+def oracle_multi_sweep_ordered(problems, lists, nCommSets, order, savePsi, maxFluxIters=1, fluxTol=1e-6):
+    """SetSweep.F90 with comm sets of several angles (3-D, no mesh cycles): at step i every comm set of every rank first sends
+    the neighbours the rows of the angles *they* sweep at step i (as they are now), then receives, then sweeps its own."""
+    N, NA = len(problems), problems[0].NA
+    bps = NA // nCommSets
+    nbrs = [shared_boundaries(p.mesh) for p in problems]
+
+    def exit_currents():
+        res = []
+        for r, p in enumerate(problems):
+            per_b = []
+            for k, b in enumerate(nbrs[r]):
+                ex = np.zeros(NA)
+                for a in range(NA):
+                    el = lists[r][k][a][0]
+                    dot = p.geom["A_bdy"][el - 1] @ p.omega[a]
+                    ex[a] = p.weight[a] * float((dot * p.PsiB[a, el - 1].sum(axis=1)).sum())
+                per_b.append(ex)
+            res.append(per_b)
+        return res
+
+    def incident(ex):
+        inc = []
+        for r, p in enumerate(problems):
+            v = np.zeros(NA)
+            for b in nbrs[r]:
+                kq = [i for i, x in enumerate(nbrs[b.neighbor]) if x.neighbor == r][0]
+                v += ex[b.neighbor][kq]
+            inc.append(v)
+        return inc
+
+    inc = incident(exit_currents())
+    it = 0
+    while True:
+        it += 1
+        PhiSets = [np.zeros((NA, p.mesh.ncornr, p.G)) for p in problems]
+        Psi1 = [np.zeros((p.mesh.ncornr + p.mesh.nbelem, p.G)) for p in problems]
+        for i in range(bps):
+            snap = [p.PsiB.copy() for p in problems]
+            for r, p in enumerate(problems):
+                for k, b in enumerate(nbrs[r]):
+                    kq = [j for j, x in enumerate(nbrs[b.neighbor]) if x.neighbor == r][0]
+                    for c in range(nCommSets):
+                        a = order[r][c * bps + i]
+                        rcv, snd = lists[r][k][a][1], lists[b.neighbor][kq][a][0]
+                        assert len(rcv) == len(snd)
+                        p.PsiB[a, rcv - 1] = snap[b.neighbor][a, snd - 1]
+            for r, p in enumerate(problems):
+                assert p.sched["totalCycles"] == 0
+                for c in range(nCommSets):
+                    a = order[r][c * bps + i]
+                    O.sweep_xyz(p.om, p.geom, p.sched, a, p.omega, p.weight, p.tau, p.STotal, p.Sigt, p.Psi[a], Psi1[r], p.PsiB[a], PhiSets[r][a], savePsi)
+        phis = []
+        for r, p in enumerate(problems):
+            Phi = np.zeros((p.mesh.ncornr, p.G))
+            for a in range(NA):
+                Phi = Phi + PhiSets[r][a]
+            phis.append(Phi)
+        inc_old, inc = inc, incident(exit_currents())
+        if savePsi:
+            break
+        notconv = 0
+        for r in range(N):   # testFluxConv.F90:55-105 per comm set
+            for c in range(nCommSets):
+                bins = range(c * bps, (c + 1) * bps)
+                total = sum(inc[r][b] for b in bins)
+                conv = True
+                for b in bins:
+                    rel = 0.0
+                    if total != 0.0 and inc[r][b] / total > 0.001:
+                        rel = abs(inc[r][b] - inc_old[r][b]) / inc[r][b]
+                    conv = conv and rel <= fluxTol
+                notconv += not conv
+        if notconv == 0 or it >= maxFluxIters:
+            break
+    return phis, it, inc

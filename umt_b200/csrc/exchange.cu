@@ -228,23 +228,30 @@ __global__ void __launch_bounds__(256) unpack_kernel(double *__restrict__ psi1, 
   psi1[dstRow[r] * G + (i - r * G)] = recvbuf[i];
 }
 
-// setIncidentFlux.F90:128-146 + testFluxConv.F90:55-105 with one bin per comm set.
+// setIncidentFlux.F90:128-146 + testFluxConv.F90:55-105.  Comm sets hold binsPerSet consecutive bins (1 by default: the bin's
+// weight in its set's total incident flux is then 1); a comm set has converged when every bin that carries more than 0.1 % of the
+// set's incident flux changed by no more than tol; nNotConv counts the comm sets that have not.
 // incRecv: (nShared, NA) exit currents received from the neighbours.
-__global__ void flux_conv_kernel(const double *incRecv, int nShared, int NA, const int *binOfAngle, int nBins, double *incFlux,
+__global__ void flux_conv_kernel(const double *incRecv, int nShared, int NA, const int *binOfAngle, int nBins, int binsPerSet, double *incFlux,
                                  double *incFluxOld, double tol, double floorFlux, int *nNotConv) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (int b = 0; b < nBins; b++) { incFluxOld[b] = incFlux[b]; incFlux[b] = 0.0; }
   for (int s = 0; s < nShared; s++)
     for (int a = 0; a < NA; a++) incFlux[binOfAngle[a]] += incRecv[(size_t)s * NA + a];
   int notConv = 0;
-  for (int b = 0; b < nBins; b++) {
-    const double total = incFlux[b];   // one bin per comm set: totalIncFlux is the bin itself
-    double rel = 0.0;
-    if (!(fabs(total) < floorFlux) && total != 0.0) {
-      const double weight = incFlux[b] / total;
-      if (weight > 0.001) rel = fabs(incFlux[b] - incFluxOld[b]) / incFlux[b];
+  for (int b0 = 0; b0 < nBins; b0 += binsPerSet) {
+    double total = 0.0;
+    for (int b = b0; b < b0 + binsPerSet; b++) total += incFlux[b];
+    bool conv = true;
+    for (int b = b0; b < b0 + binsPerSet; b++) {
+      double rel = 0.0;
+      if (!(fabs(total) < floorFlux) && total != 0.0) {
+        const double weight = incFlux[b] / total;
+        if (weight > 0.001) rel = fabs(incFlux[b] - incFluxOld[b]) / incFlux[b];
+      }
+      if (!(rel <= tol)) conv = false;
     }
-    if (!(rel <= tol)) notConv++;
+    if (!conv) notConv++;
   }
   *nNotConv = notConv;
 }
@@ -296,9 +303,9 @@ int need_abdy(umt_ctx *ctx) {
 void umt_exchange_release(umt_ctx *ctx) {
   for (auto &s : ctx->shared) {
     void *p[] = {s.d_send_row, s.d_recv_row, s.d_send_coef, s.d_chunks, s.d_partial, s.d_nChunksOfAngle, s.d_sendbuf, s.d_recvbuf,
-                 s.d_gsend, s.d_grecv, s.d_gsendbuf, s.d_grecvbuf};
+                 s.d_gsend, s.d_grecv, s.d_gsendbuf, s.d_grecvbuf, s.d_stage_send, s.d_stage_recv};
     for (void *q : p) if (q) cudaFree(q);
-    s.d_gsend = s.d_grecv = nullptr; s.d_gsendbuf = s.d_grecvbuf = nullptr;
+    s.d_gsend = s.d_grecv = nullptr; s.d_gsendbuf = s.d_grecvbuf = nullptr; s.d_stage_send = s.d_stage_recv = nullptr;
     s.d_send_row = s.d_recv_row = nullptr; s.d_send_coef = nullptr; s.d_chunks = nullptr; s.d_partial = nullptr;
     s.d_nChunksOfAngle = nullptr; s.d_sendbuf = s.d_recvbuf = nullptr;
   }
@@ -593,7 +600,8 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   UMT_CUDA(ctx, cudaGetLastError());
   r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
   if (r) return r;
-  flux_conv_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, ctx->d_incFlux,
+  const int binsPerSet = (ctx->ndim == 3 && ctx->nCommSets > 0) ? ctx->NA / ctx->nCommSets : 1;
+  flux_conv_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, binsPerSet, ctx->d_incFlux,
                                               ctx->d_incFluxOld, tol, ctx->fluxFloor, ctx->d_nNotConv);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches++;
@@ -748,4 +756,204 @@ int umt_gta_exchange(umt_ctx *ctx, double *d_PsiB) {
 int umt_allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) {
   if (ctx->nRanks <= 1 || !ctx->transport) return UMT_OK;
   return ctx->transport->allreduce_f64(ctx, d_vals, n, op);
+}
+
+// ---------------------------------------------------------------------------
+// SweepScheduler (rt/SweepScheduler.F90:32-313) + setNetFlux (rt/setNetFlux.F90:9-143) and the per-step exchange of
+// snac/SetSweep.F90:113-170 for comm sets that hold several angle bins
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restrict__ psi1, const long long *__restrict__ row, double *__restrict__ out,
+                                                          long long n, int G) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = i / G;
+  out[i] = __ldcg(&psi1[row[r] * G + (i - r * G)]);
+}
+}  // namespace
+
+// nCommSets consecutive groups of angle bins (3-D: bins are angles); 0 restores the finest decomposition
+extern "C" int umt_set_comm_sets(umt_ctx *ctx, int nCommSets) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm_sets: quadrature not set");
+  if (nCommSets < 0 || (nCommSets > 0 && ctx->NA % nCommSets != 0)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_comm_sets: %d sets do not divide %d angles", nCommSets, ctx->NA);
+  if (nCommSets > 0 && nCommSets < ctx->NA && ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm_sets: comm sets of several bins are 3-D only (r-z: one xi-level per comm set)");
+  ctx->nCommSets = nCommSets == ctx->NA ? 0 : nCommSets;
+  ctx->have_comm_order = false;
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+// The order in which every comm set sweeps its bins and the order in which the neighbours sweep theirs.  Collective.
+// netFlux (nShared, NA) = exiting minus incident current per shared boundary and angle; NULL: tallied from the PsiB on the
+// device (setNetFlux).  Dependency weight of a bin = sum over the shared boundaries of its net flux, minus what neighbours
+// have already swept; bins whose mirror images (reflecting boundaries) are still to come wait; largest weight first.
+extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
+  if (!ctx) return UMT_ERR_ARG;
+  if (ctx->nCommSets <= 0) { ctx->have_comm_order = false; return UMT_OK; }   // one bin per comm set: identity
+  if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: host-only context");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int NA = ctx->NA, nC = ctx->nCommSets, bps = NA / nC;
+  const size_t nS = ctx->shared.size();
+  if (nS > 0) { int r = ready(ctx); if (r) return r; }
+  int r = umt_reflect_stages(ctx);   // mirror angles
+  if (r) return r;
+  std::vector<double> w(std::max<size_t>(nS, 1) * NA, 1.0);
+  if (nS > 0) {
+    if (netFlux) std::copy(netFlux, netFlux + nS * NA, w.begin());
+    else {
+      if (!ctx->d_psi1) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: no state on the device to tally the net flux from");
+      r = umt_exchange_tally(ctx, 0.0);
+      if (r) return r;
+      std::vector<double> ex(nS * NA), in(nS * NA);
+      UMT_CUDA(ctx, cudaMemcpyAsync(ex.data(), ctx->d_exitFlux, sizeof(double) * nS * NA, cudaMemcpyDeviceToHost, ctx->stream));
+      UMT_CUDA(ctx, cudaMemcpyAsync(in.data(), ctx->d_incRecv, sizeof(double) * nS * NA, cudaMemcpyDeviceToHost, ctx->stream));
+      UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (size_t i = 0; i < nS * NA; i++) w[i] = ex[i] - in[i];
+    }
+  }
+  ctx->netFlux.assign(w.begin(), w.begin() + nS * NA);
+  std::vector<double> depend(NA, 0.0);
+  for (int a = 0; a < NA; a++)
+    for (size_t k = 0; k < nS; k++) depend[a] += w[k * NA + a];
+  const int nR = (int)ctx->refl.size();
+  std::vector<int> nRefl(NA, 0), depAngle((size_t)std::max(nR, 1) * NA, -1);
+  for (int n = 0; n < nR; n++)
+    for (int a = 0; a < NA; a++) {
+      const int m = ctx->refl[n].mref[a];
+      if (m >= 0) { depAngle[(size_t)n * NA + m] = a; nRefl[a]++; }
+    }
+  std::vector<unsigned char> notDone(NA, 1);
+  ctx->angleOrder.assign(NA, 0);
+  ctx->recvOrder.assign(nS, std::vector<int>(NA, 0));
+  int *d_s = nullptr, *d_r = nullptr;
+  UMT_CUDA(ctx, cudaMalloc((void **)&d_s, sizeof(int) * nC));
+  UMT_CUDA(ctx, cudaMalloc((void **)&d_r, sizeof(int) * nC * std::max<size_t>(nS, 1)));
+  std::vector<int> newbin(nC), binRecv(nC * std::max<size_t>(nS, 1));
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS, sizeof(int) * nC), rb(nS, sizeof(int) * nC);
+  int rc = UMT_OK;
+  for (int i = 0; i < bps && !rc; i++) {
+    for (int c = 0; c < nC; c++) {
+      const int b0 = c * bps, b1 = b0 + bps;
+      int imin = -1;
+      for (int b = b0; b < b1; b++) if (notDone[b] && (imin < 0 || nRefl[b] < nRefl[imin])) imin = b;   // minloc(nRefl, notDone)
+      if (nRefl[imin] != 0) nRefl[imin] = 0;
+      int best = -1;
+      for (int b = b0; b < b1; b++) if (notDone[b] && nRefl[b] == 0 && (best < 0 || depend[b] > depend[best])) best = b;   // maxloc(depend, Ready)
+      newbin[c] = best;
+    }
+    if (nS > 0) {   // every neighbour learns my bins of this step, I learn theirs
+      if (cudaMemcpyAsync(d_s, newbin.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = UMT_ERR_CUDA; break; }
+      for (size_t k = 0; k < nS; k++) { sp[k] = d_s; rp[k] = d_r + k * nC; }
+      rc = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+      if (rc) break;
+      if (cudaMemcpyAsync(binRecv.data(), d_r, sizeof(int) * nC * nS, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = UMT_ERR_CUDA; break; }
+    }
+    for (int c = 0; c < nC; c++) {
+      const int nb_ = newbin[c];
+      ctx->angleOrder[c * bps + i] = nb_;
+      for (int n = 0; n < nR; n++) {
+        const int aRef = depAngle[(size_t)n * NA + nb_];
+        if (aRef >= 0 && notDone[aRef]) nRefl[aRef]--;
+      }
+      notDone[nb_] = 0;
+    }
+    for (size_t k = 0; k < nS; k++)
+      for (int c = 0; c < nC; c++) {
+        const int b = binRecv[k * nC + c];
+        if (b < c * bps || b >= (c + 1) * bps) { ctx->err = "umt_sweep_scheduler: neighbour sent a bin outside the comm set"; rc = UMT_ERR_STATE; break; }
+        ctx->recvOrder[k][c * bps + i] = b;
+        if (notDone[b]) depend[b] -= w[k * NA + b];
+      }
+  }
+  cudaFree(d_s); cudaFree(d_r);
+  if (rc) { if (rc == UMT_ERR_CUDA) ctx->err = "umt_sweep_scheduler: CUDA copy failed"; return rc; }
+  ctx->commStageOf.assign(NA, 0);
+  for (int c = 0; c < nC; c++)
+    for (int i = 0; i < bps; i++) ctx->commStageOf[ctx->angleOrder[c * bps + i]] = i;
+  ctx->have_comm_order = true;
+  ctx->sched_dirty = true;
+  return nS > 0 ? umt_exchange_build_stages(ctx) : UMT_OK;
+}
+
+// CSet%NetFlux(shared, bin) the last umt_sweep_scheduler call worked with
+extern "C" int umt_get_net_flux(umt_ctx *ctx, double *netFlux /* (nShared, NA) */) {
+  if (!ctx || !netFlux) return UMT_ERR_ARG;
+  if (ctx->netFlux.size() != ctx->shared.size() * (size_t)ctx->NA) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_get_net_flux: no scheduler run yet");
+  std::copy(ctx->netFlux.begin(), ctx->netFlux.end(), netFlux);
+  return UMT_OK;
+}
+
+// CSet%AngleOrder of every comm set (concatenated, 1-based angles) and CSet%RecvOrder(:, shared) likewise
+extern "C" int umt_get_angle_order(umt_ctx *ctx, int *angleOrder /* (NA) */, int *recvOrder /* (nShared, NA) or NULL */) {
+  if (!ctx || !angleOrder) return UMT_ERR_ARG;
+  const int NA = ctx->NA;
+  if (!ctx->have_comm_order) {   // identity
+    for (int a = 0; a < NA; a++) angleOrder[a] = a + 1;
+    if (recvOrder) for (size_t k = 0; k < ctx->shared.size(); k++) for (int a = 0; a < NA; a++) recvOrder[k * NA + a] = a + 1;
+    return UMT_OK;
+  }
+  for (int a = 0; a < NA; a++) angleOrder[a] = ctx->angleOrder[a] + 1;
+  if (recvOrder) for (size_t k = 0; k < ctx->shared.size(); k++) for (int a = 0; a < NA; a++) recvOrder[k * NA + a] = ctx->recvOrder[k][a] + 1;
+  return UMT_OK;
+}
+
+// rows each neighbour needs from me at every step (the angles it sweeps then: RecvOrder) and rows I receive (AngleOrder)
+int umt_exchange_build_stages(umt_ctx *ctx) {
+  const int NA = ctx->NA, nC = ctx->nCommSets, bps = NA / nC;
+  for (size_t k = 0; k < ctx->shared.size(); k++) {
+    SharedBdy &s = ctx->shared[k];
+    if ((int)s.send_b.size() != NA) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_exchange_build_stages: exchange lists not built");
+    std::vector<long long> snd, rcv;
+    s.stage_send_off.assign(bps + 1, 0); s.stage_recv_off.assign(bps + 1, 0);
+    for (int i = 0; i < bps; i++) {
+      for (int c = 0; c < nC; c++) {
+        const int as = ctx->recvOrder[k][c * bps + i], ar = ctx->angleOrder[c * bps + i];
+        for (int b : s.send_b[as]) snd.push_back((long long)as * ctx->rows_total() + ctx->nc + b);
+        for (int b : s.recv_b[ar]) rcv.push_back((long long)ar * ctx->rows_total() + ctx->nc + b);
+      }
+      s.stage_send_off[i + 1] = snd.size(); s.stage_recv_off[i + 1] = rcv.size();
+    }
+    if (snd.size() != s.send_rows || rcv.size() != s.recv_rows) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_exchange_build_stages: row count mismatch");
+    int r;
+    if ((r = upload(ctx, &s.d_stage_send, snd))) return r;
+    if ((r = upload(ctx, &s.d_stage_recv, rcv))) return r;
+  }
+  return UMT_OK;
+}
+
+// SendFlux / TestSend / RecvFlux of sweep step `step` for every comm set (SetSweep.F90:126-132): what the neighbours sweep at
+// this step gets my *current* exiting rows (fresh where I swept that angle at an earlier step of this pass)
+int umt_exchange_stage(umt_ctx *ctx, int step) {
+  const int G = ctx->G;
+  const size_t nS = ctx->shared.size();
+  std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    if (!s.d_stage_send) UMT_FAIL(ctx, UMT_ERR_STATE, "staged exchange not built (umt_sweep_scheduler)");
+    const size_t o = s.stage_send_off[step];
+    const long long n = (long long)(s.stage_send_off[step + 1] - o) * G;
+    if (n > 0) {
+      gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_stage_send + o, s.d_sendbuf + o * G, n, G);
+      ctx->last_launches++;
+    }
+    sp[k] = s.d_sendbuf + o * G; sb[k] = sizeof(double) * (size_t)n;
+    const size_t ro = s.stage_recv_off[step];
+    rp[k] = s.d_recvbuf + ro * G; rb[k] = sizeof(double) * (s.stage_recv_off[step + 1] - ro) * G;
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  int r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  if (r) return r;
+  for (size_t k = 0; k < nS; k++) {
+    SharedBdy &s = ctx->shared[k];
+    const size_t ro = s.stage_recv_off[step];
+    const long long n = (long long)(s.stage_recv_off[step + 1] - ro) * G;
+    if (n > 0) {
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_stage_recv + ro, s.d_recvbuf + ro * G, n, G);
+      ctx->last_launches++;
+    }
+  }
+  UMT_CUDA(ctx, cudaGetLastError());
+  return UMT_OK;
 }

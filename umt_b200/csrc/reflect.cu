@@ -85,7 +85,14 @@ int umt_reflect_stages(umt_ctx *ctx) {
   ctx->stageOf.assign(NA, 0);
   ctx->nStages = 1;
   ctx->reflOpBegin.assign(2, 0);
-  if (ctx->refl.empty()) return UMT_OK;
+  if (ctx->refl.empty()) {
+    if (ctx->have_comm_order) {
+      ctx->stageOf = ctx->commStageOf;
+      ctx->nStages = 1 + *std::max_element(ctx->stageOf.begin(), ctx->stageOf.end());
+      ctx->reflOpBegin.assign(ctx->nStages + 1, 0);
+    }
+    return UMT_OK;
+  }
   if (!ctx->have_geom || !ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "reflecting boundaries need geometry and quadrature");
   // boundary-element area vectors = A_fp of the corner face they sit on
   std::vector<double> Abdy((size_t)nd * std::max(ctx->nb, 1), 0.0);
@@ -145,6 +152,7 @@ int umt_reflect_stages(umt_ctx *ctx) {
       }
     }
   }
+  if (ctx->have_comm_order) ctx->stageOf = ctx->commStageOf;   // SweepScheduler's order already honours the mirror dependencies
   ctx->nStages = 1 + *std::max_element(ctx->stageOf.begin(), ctx->stageOf.end());
   if (ctx->device < 0) return UMT_OK;
   std::vector<int4> ops;

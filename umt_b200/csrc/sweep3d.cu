@@ -1129,7 +1129,10 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
     const int begin = ctx->stageItemBegin[s], end = ctx->stageItemBegin[s + 1];
     if (end == begin) continue;
     if (s > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
-    int r = umt_launch_reflect(ctx, s);   // snreflect for the incident angles of this stage
+    int r = UMT_OK;
+    if (ctx->have_comm_order && !ctx->shared.empty()) r = umt_exchange_stage(ctx, s);   // SendFlux / RecvFlux of this sweep step
+    if (r) return r;
+    r = umt_launch_reflect(ctx, s);   // snreflect for the incident angles of this stage
     if (r) return r;
     P.items = ctx->d_items + begin;
     P.nItems = end - begin;

@@ -711,7 +711,8 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   for (;;) {
     iter++;
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (multi) TRY(umt_exchange_begin_pass(ctx));   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
+    if (multi && !ctx->have_comm_order) TRY(umt_exchange_begin_pass(ctx));   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
+    // (comm sets of several bins exchange step by step inside umt_launch_sweep3d)
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (ctx->totalCycles > 0) {                     // initFromCycleList
       const size_t n = (size_t)ctx->totalCycles * ctx->G;

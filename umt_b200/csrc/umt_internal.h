@@ -57,6 +57,9 @@ struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   std::vector<int> send_off, recv_off;                     // per-angle offsets (NA+1)
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
   size_t send_rows = 0, recv_rows = 0;
+  // staged exchange (comm sets with several bins): rows to send / receive at each step, grouped by step
+  long long *d_stage_send = nullptr, *d_stage_recv = nullptr;
+  std::vector<size_t> stage_send_off, stage_recv_off;   // (nSteps + 1) row offsets
   // grey (GTA) exchange: positions in the (8, nbelem) PsiB array of the exiting / incident elements, all angles concatenated
   int *d_gsend = nullptr, *d_grecv = nullptr;
   double *d_gsendbuf = nullptr, *d_grecvbuf = nullptr;
@@ -171,6 +174,14 @@ struct umt_ctx {
   std::vector<ReflBdy> refl;
   std::vector<int> stageOf, stageItemBegin;
   int nStages = 1;
+  // SweepScheduler (rt/SweepScheduler.F90): comm sets of several angle bins swept in AngleOrder, all comm sets concurrently.
+  // nCommSets == 0: the finest decomposition (one bin per comm set, scheduler = identity, exchange lagged a whole pass).
+  int nCommSets = 0;
+  bool have_comm_order = false;
+  std::vector<int> angleOrder;                   // (NA) per comm set concatenated: 0-based angle swept at each step
+  std::vector<std::vector<int>> recvOrder;       // [shared][NA] the neighbour's AngleOrder (0-based), same layout
+  std::vector<int> commStageOf;                  // (NA) step at which angle a is swept
+  std::vector<double> netFlux;                   // (nShared, NA) CSet%NetFlux of the last scheduler run
   int4 *d_reflOps = nullptr;           // (minc, mref, first, n) grouped by stage
   std::vector<int> reflOpBegin;        // per-stage offsets into d_reflOps
 
@@ -241,6 +252,8 @@ int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vect
 int umt_exchange_tally(umt_ctx *ctx, double tol);
 int umt_exchange_begin_pass(umt_ctx *ctx);
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);
+int umt_exchange_stage(umt_ctx *ctx, int step);               // SendFlux / RecvFlux of one sweep step (staged comm sets)
+int umt_exchange_build_stages(umt_ctx *ctx);
 int umt_gta_build_exchange(umt_ctx *ctx);                    // collective: GTA ListSend / ListRecv (findexit.F90 on the GTA angle set)
 int umt_gta_exchange(umt_ctx *ctx, double *d_PsiB);          // SendFlux / RecvFlux of GTASweep.F90:139-146 for all 8 angles
 int umt_allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op /* 0 sum, 1 max */);   // MPIAllReduce over the domains

@@ -345,6 +345,25 @@ class SweepContext:
         self._ck(self.lib.umt_get_exchange_lists(self.h, int(sharedIndex), int(angle), _ip(ls), _ip(lr)), "umt_get_exchange_lists")
         return ls[:ns[angle - 1]], lr[:nr[angle - 1]]
 
+    def set_comm_sets(self, nCommSets):
+        self._ck(self.lib.umt_set_comm_sets(self.h, int(nCommSets)), "umt_set_comm_sets")
+
+    def sweep_scheduler(self, netFlux=None):
+        """SweepScheduler for every comm set (collective); netFlux (nShared, NA) or None to tally it from the device PsiB"""
+        nf = None if netFlux is None else _dp(_f64(netFlux))
+        self._ck(self.lib.umt_sweep_scheduler(self.h, nf), "umt_sweep_scheduler")
+
+    def net_flux(self, nShared):
+        nf = np.zeros((nShared, self.NA))
+        self._ck(self.lib.umt_get_net_flux(self.h, _dp(nf)), "umt_get_net_flux")
+        return nf
+
+    def angle_order(self, nShared=0):
+        ao = np.zeros(self.NA, np.int32)
+        ro = np.zeros((max(nShared, 1), self.NA), np.int32)
+        self._ck(self.lib.umt_get_angle_order(self.h, _ip(ao), _ip(ro) if nShared else None), "umt_get_angle_order")
+        return ao, ro[:nShared]
+
     def incident_flux(self, nBins=None):
         n = nBins if nBins is not None else self.NA
         a, b = np.zeros(n), np.zeros(n)
