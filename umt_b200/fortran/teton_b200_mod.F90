@@ -126,6 +126,55 @@ module teton_b200_mod
          integer(C_SIGNED_CHAR) :: id128(128)
       end function
 
+!     SweepScheduler / setNetFlux for comm sets of several angle bins (rt/SweepScheduler.F90): optional, the default is one
+!     comm set per angle set.  Called once per cycle where control/initializeSets.F90:515-523 calls SweepScheduler.
+      integer(C_INT) function umt_set_comm_sets(ctx, nCommSets) bind(C, name="umt_set_comm_sets")
+         import :: C_INT, C_PTR
+         type(C_PTR),    value :: ctx
+         integer(C_INT), value :: nCommSets
+      end function
+
+      integer(C_INT) function umt_sweep_scheduler(ctx, netFlux) bind(C, name="umt_sweep_scheduler")
+         import :: C_INT, C_PTR
+         type(C_PTR), value :: ctx
+         type(C_PTR), value :: netFlux      ! C_NULL_PTR: tallied from the PsiB on the device
+      end function
+
+!     Grey transport acceleration (rt/GTASolver.F90 and friends): replaces the body of GTASolver + addGreyCorrections.
+      integer(C_INT) function umt_gta_setup(ctx) bind(C, name="umt_gta_setup")
+         import :: C_INT, C_PTR
+         type(C_PTR), value :: ctx
+      end function
+
+      integer(C_INT) function umt_gta_compute_opacity(ctx, Siga, Sigs, Eta, Chi) bind(C, name="umt_gta_compute_opacity")
+         import :: C_INT, C_PTR, C_DOUBLE
+         type(C_PTR), value :: ctx
+         real(C_DOUBLE)     :: Siga(*), Sigs(*), Eta(*), Chi(*)   ! Mat%Siga, Mat%Sigs (ngr,nzones), Mat%Eta (ncornr), GTA%Chi (ngr,ncornr)
+      end function
+
+      integer(C_INT) function umt_collision_rate(ctx, Eta, Siga, Sigs, residualFlag, GreySource) bind(C, name="umt_collision_rate")
+         import :: C_INT, C_PTR, C_DOUBLE
+         type(C_PTR),    value :: ctx
+         real(C_DOUBLE)        :: Eta(*), Siga(*), Sigs(*)
+         integer(C_INT), value :: residualFlag
+         type(C_PTR),    value :: GreySource                       ! C_NULL_PTR: stays on the device
+      end function
+
+      integer(C_INT) function umt_gta_solve(ctx, epsPoint, maxIters, epsGrey, enforceHardMax, nGreyIter, maxRelErr) &
+                              bind(C, name="umt_gta_solve")
+         import :: C_INT, C_PTR, C_DOUBLE
+         type(C_PTR),    value :: ctx
+         real(C_DOUBLE), value :: epsPoint, epsGrey
+         integer(C_INT), value :: maxIters, enforceHardMax
+         integer(C_INT)        :: nGreyIter
+         real(C_DOUBLE)        :: maxRelErr
+      end function
+
+      integer(C_INT) function umt_add_grey_corrections(ctx) bind(C, name="umt_add_grey_corrections")
+         import :: C_INT, C_PTR
+         type(C_PTR), value :: ctx
+      end function
+
    end interface
 
 contains
