@@ -246,7 +246,7 @@ class _Gta(C.Structure):
                 ("GreySigTotal", c_dp), ("GreySigtInv", c_dp), ("GreySigScat", c_dp), ("GreySigScatVol", c_dp),
                 ("GreySource", c_dp), ("TT", c_dp), ("wtiso", C.c_double),
                 ("Area", c_dp), ("RadiusFP", c_dp), ("RadiusEZ", c_dp), ("angDerivFac", c_dp), ("quadTauW1", c_dp), ("quadTauW2", c_dp),
-                ("start", c_bp), ("finish", c_bp)]
+                ("start", c_bp), ("finish", c_bp), ("nStagesR", C.c_int), ("nReflOps", C.c_int), ("angleStage", c_ip), ("reflOps", c_ip)]
 
 
 def gta_quad_xyz():
@@ -284,8 +284,9 @@ def collision_rate(om: OMesh, Eta, Siga, Sigs, PhiTotal, GreySource, residualFla
 class GtaProblem:
     """Keeps every array the C struct points at alive."""
 
-    def __init__(self, om: OMesh, geom, sched, omega, weight, opac, GreySource, wtiso, q=None):
-        """q: the r-z angle-set dict of gta_quad_rz() (2-D meshes)"""
+    def __init__(self, om: OMesh, geom, sched, omega, weight, opac, GreySource, wtiso, q=None, reflect=None):
+        """q: the r-z angle-set dict of gta_quad_rz() (2-D meshes); reflect = (angleStage (nAng), ops (n, 5) int32 rows of
+        (stage, minc, mref, first element, count), all 0-based) for reflecting boundaries (3-D)"""
         self.om, self.geom, self.sched, self.q = om, geom, sched, q
         self.omega = np.ascontiguousarray(omega)
         self.weight = np.ascontiguousarray(weight)
@@ -305,6 +306,11 @@ class GtaProblem:
             s.Area, s.RadiusFP, s.RadiusEZ = _dp(geom["Area"]), _dp(geom["RadiusFP"]), _dp(geom["RadiusEZ"])
             s.angDerivFac, s.quadTauW1, s.quadTauW2 = _dp(q["angDerivFac"]), _dp(q["quadTauW1"]), _dp(q["quadTauW2"])
             s.start, s.finish = _bp(q["start"]), _bp(q["finish"])
+        if reflect is not None and len(reflect[1]):
+            self._stage = np.ascontiguousarray(reflect[0], np.int32)
+            self._ops = np.ascontiguousarray(reflect[1], np.int32)
+            s.nStagesR, s.nReflOps = int(self._stage.max()) + 1, len(self._ops)
+            s.angleStage, s.reflOps = _ip(self._stage), _ip(self._ops)
         self.s = s
 
     def init_tt(self):

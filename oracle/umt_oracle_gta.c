@@ -289,6 +289,11 @@ typedef struct {
   /* r-z only (M->ndim == 2): omega is (2,nAng), A_fp/A_ez are (2,2,nc) */
   const double *Area, *RadiusFP, *RadiusEZ, *angDerivFac, *quadTauW1, *quadTauW2;
   const unsigned char *start, *finish;
+  /* reflecting boundaries (3-D): GTASweep.F90:151 calls snreflect before each angle; angles are taken stage by stage (mirror images
+     first), the copies PsiB(first..first+n-1, minc) <- PsiB(.., mref) of a stage made before its sweeps */
+  int nStagesR, nReflOps;
+  const int *angleStage;   /* (nAng) */
+  const int *reflOps;      /* (nReflOps, 5): stage, minc, mref (0-based angles), first (0-based element), n */
 } orc_gta;
 
 void orc_gta_sweep_angle_rz(const orc_mesh *M, int nHyperPlanes, const int *zonesInPlane, const int *nextZ, const int *nextC,
@@ -368,11 +373,28 @@ void orc_gta_grey_sweep(const orc_gta *S, double *PsiB, double *P, int withSourc
                              S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, tPsiM, tInc, PsiB + (size_t)nb * a, PhiInc);
     }
     free(tPsiM); free(tInc);
-  } else
-  for (int a = 0; a < S->nAng; a++)
-    orc_gta_sweep_angle(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
-                        S->nextC + (size_t)nc * a, S->omega + 3 * a, S->weight[a], S->Volume, S->A_fp, S->A_ez,
-                        S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, PsiB + (size_t)nb * a, PhiInc);
+  } else {
+    /* PhiInc is summed in angle order whatever the sweep order (as gta_phiinc_kernel does): each angle's w pInc is kept */
+    const int nSt = S->nReflOps > 0 ? S->nStagesR : 1;
+    double *pAll = calloc((size_t)nc * S->nAng, sizeof(double)), *dummy = calloc(nc, sizeof(double));
+    for (int st = 0; st < nSt; st++) {
+      for (int o = 0; o < S->nReflOps; o++) {
+        const int *op = S->reflOps + 5 * o;
+        if (op[0] != st) continue;
+        for (int i = 0; i < op[4]; i++) PsiB[(size_t)nb * op[1] + op[3] + i] = PsiB[(size_t)nb * op[2] + op[3] + i];
+      }
+      for (int a = 0; a < S->nAng; a++) {
+        if (S->nReflOps > 0 && S->angleStage[a] != st) continue;
+        orc_gta_sweep_angle(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
+                            S->nextC + (size_t)nc * a, S->omega + 3 * a, S->weight[a], S->Volume, S->A_fp, S->A_ez,
+                            S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, PsiB + (size_t)nb * a, dummy);
+        memcpy(pAll + (size_t)nc * a, pInc, sizeof(double) * nc);
+      }
+    }
+    for (int a = 0; a < S->nAng; a++)
+      for (int c = 0; c < nc; c++) PhiInc[c] = PhiInc[c] + S->weight[a] * pAll[(size_t)nc * a + c];
+    free(pAll); free(dummy);
+  }
   for (int zone = 1; zone <= nz; zone++) scalar_intensity(S, zone, PhiInc, P, withSource);
   free(TsaSource); free(PhiInc); free(tPsi); free(pInc);
 }

@@ -157,3 +157,87 @@ def test_source_build_extension(G):
     ctx.sweep(False)
     assert np.isfinite(ctx.download_phi()).all()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# reflecting boundaries in the grey sweeps (GTASweep.F90:151 snreflect on the GTA angle set)
+# ---------------------------------------------------------------------------
+def _gta_reflect(mesh, g, omega):
+    """mirror angles of the S2 set on every reflecting boundary, sweep stages, and the copy ops (stage, minc, mref, first, n)"""
+    class _P:
+        pass
+    p = _P()
+    p.mesh, p.geom, p.omega, p.NA = mesh, g, omega, len(omega)
+    mrefs = T.oracle_reflected_angles(p)
+    stage = T.reflect_stages(mrefs, p.NA)
+    ops = [(stage[a], a, int(mr[a]), b.first_elem - 1, b.n_elem) for mr, b in zip(mrefs, T.reflecting_boundaries(mesh)) for a in range(p.NA) if mr[a] >= 0]
+    return np.array(stage, np.int32), np.array(ops, np.int32).reshape(-1, 5)
+
+
+def _setup_reflecting(mesh, G=4, seed=7):
+    s = _setup(mesh, G, seed)
+    # _setup called gta_setup before the reflecting boundaries were known: add them and set up again
+    for b in T.reflecting_boundaries(mesh):
+        s["ctx"].add_reflecting_boundary(b.first_elem, b.n_elem)
+    s["ctx"].gta_setup()
+    return s
+
+
+@pytest.mark.parametrize("sides", [(1,), (0, 2), (0, 2, 4), (0, 1)])
+def test_gta_reflecting_matches_oracle(sides):
+    s = _setup_reflecting(M.tiled_mesh((2, 2, 2), reflecting=sides))
+    ctx, om, g = s["ctx"], s["om"], s["g"]
+    nc, nb = s["mesh"].ncornr, s["mesh"].nbelem
+    refl = _gta_reflect(s["mesh"], g, s["omega"])
+    chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()
+    op = O.gta_set_opacity(om, g, s["tau"], s["Siga"], s["Sigs"], s["Eta"], chi_ref)
+    ctx.gta_compute_opacity(s["Siga"], s["Sigs"], s["Eta"], chi_dev)
+    gs = O.collision_rate(om, s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    ctx.collision_rate(s["Eta"], s["Siga"], s["Sigs"], 0)
+    P = O.GtaProblem(om, g, s["sched"], s["omega"], s["w"], op, gs, PR.wtiso(3), reflect=refl)
+    P.init_tt()
+    ctx.gta_init_tt()
+    rng = np.random.default_rng(11)
+    Pr, Br = rng.random(nc), rng.random((8, nb))
+    Pd, Bd = Pr.copy(), Br.copy()
+    P.grey_sweep(Br, Pr, True)
+    ctx.gta_grey_sweep(Pd, Bd, True)
+    assert T.mixed_err(Pd, Pr, 1e-11) <= 1.0 and T.mixed_err(Bd, Br, 1e-11) <= 1.0
+    # the solver on top (fresh transfer matrices)
+    P2 = O.GtaProblem(om, g, s["sched"], s["omega"], s["w"], op, gs, PR.wtiso(3), reflect=refl)
+    corr, n, err = P2.solve(s["Phi"])
+    corr_d, n_d, err_d = ctx.gta_solve()
+    assert n_d == n and n > 3
+    assert np.abs(corr_d - corr).max() <= 1e-8 * np.abs(corr).max()
+    ctx.close()
+
+
+def test_gta_mirror_plane_reproduces_symmetric_full_domain():
+    """uniform data on the box [0,1]^3 is symmetric about x = 1/2: the grey correction of the left half closed by a reflecting
+    x+ side equals the full-domain correction (solved tightly on both)."""
+    G = 2
+
+    def uniform(mesh):
+        s = _setup_reflecting(mesh, G) if T.reflecting_boundaries(mesh) else _setup(mesh, G)
+        s["Siga"][:] = 1.0; s["Sigs"][:] = 30.0; s["Eta"][:] = 0.2; s["Chi"][:] = 0.5
+        return s
+    full = uniform(M.box_mesh((8, 4, 4)))
+    op = O.gta_set_opacity(full["om"], full["g"], full["tau"], full["Siga"], full["Sigs"], full["Eta"], full["Chi"].copy())
+    phi1 = np.ones_like(full["Phi"])
+    gs = O.collision_rate(full["om"], full["Eta"], full["Siga"], full["Sigs"], phi1, np.zeros(full["mesh"].ncornr), 0)
+    corr_full, n, _ = O.GtaProblem(full["om"], full["g"], full["sched"], full["omega"], full["w"], op, gs, PR.wtiso(3)).solve(phi1, epsPoint=1e-11, maxIters=200)
+    full["ctx"].close()
+    half = uniform(M.box_mesh((4, 4, 4), lengths=(0.5, 1.0, 1.0), reflecting=(1,)))
+    ctx, hm = half["ctx"], half["mesh"]
+    ctx.upload_state(np.tile(np.ones((hm.ncornr, G)) / (4 * np.pi), (8, 1, 1)), None, np.full((hm.nzones, G), half["tau"]), np.zeros((hm.ncornr, G)), half["tau"])
+    ctx.init_phi_total()
+    ctx.gta_compute_opacity(half["Siga"], half["Sigs"], half["Eta"], half["Chi"].copy())
+    ctx.collision_rate(half["Eta"], half["Siga"], half["Sigs"], 0)
+    corr_half, n_h, _ = ctx.gta_solve(epsPoint=1e-11, maxIters=200)
+    fm = full["mesh"]
+    zc_f = np.repeat(np.add.reduceat(fm.px, fm.cOffSet) / 8.0, fm.numCorner, axis=0)
+    look = {tuple(np.round(np.r_[fm.px[c], zc_f[c]] * 1e8).astype(np.int64)): c for c in range(fm.ncornr)}
+    zc_h = np.repeat(np.add.reduceat(hm.px, hm.cOffSet) / 8.0, hm.numCorner, axis=0)
+    idx = np.array([look[tuple(np.round(np.r_[hm.px[c], zc_h[c]] * 1e8).astype(np.int64))] for c in range(hm.ncornr)])
+    assert np.abs(corr_half - corr_full[idx]).max() <= 1e-7 * np.abs(corr_full).max()
+    ctx.close()

@@ -283,6 +283,13 @@ __global__ void __launch_bounds__(GTA_WARPS * 32) gta_sweep_kernel(GtaSweepParam
   }
 }
 
+// snreflect for the grey sweeps: tPsi tail rows are PsiB(:, angle)
+__global__ void gta_reflect_kernel(double *tpsi, const int4 *ops, int rows, int nc) {
+  const int4 o = ops[blockIdx.y];   // x = Minc, y = Mref, z = first boundary element, w = count
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < o.w) tpsi[(size_t)o.x * rows + nc + o.z + i] = tpsi[(size_t)o.y * rows + nc + o.z + i];
+}
+
 // TsaSource = wtiso (GreySigScat P + GreySource)   (GTASweep.F90:84-89)
 __global__ void gta_tsa_kernel(const double *P, const double *sigScat, const double *greySource, double wtiso, double *tsa, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -621,9 +628,21 @@ int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc;
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gta_sweep_kernel, GTA_WARPS * 32, 0));
-  const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), g.nItems));
-  gta_sweep_kernel<<<grid, GTA_WARPS * 32, 0, ctx->stream>>>(P);
-  UMT_CUDA(ctx, cudaGetLastError());
+  for (int sR = 0; sR < g.nStagesR; sR++) {
+    const int ib = g.stageItemBegin[sR], ie = g.stageItemBegin[sR + 1];
+    const int ob = g.reflOpBegin[sR], oe = g.reflOpBegin[sR + 1];
+    if (oe > ob) {   // PsiB(b, Minc) <- PsiB(b, Mref) on the reflecting boundaries (snreflect.F90:60-76)
+      int maxN = 1;
+      for (const auto &R : ctx->refl) maxN = std::max(maxN, R.n);
+      gta_reflect_kernel<<<dim3((maxN + 255) / 256, oe - ob), 256, 0, ctx->stream>>>(g.d_tpsi, g.d_reflOps + ob, rows, nc);
+    }
+    if (ie == ib) continue;
+    if (sR > 0) UMT_CUDA(ctx, cudaMemsetAsync(g.d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
+    P.items = g.d_items + ib; P.nItems = ie - ib;
+    const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), P.nItems));
+    gta_sweep_kernel<<<grid, GTA_WARPS * 32, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
   gta_phiinc_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(g.d_pinc, g.d_weight, g.nAng, nc, g.d_phiInc);
   if (nb > 0)
     UMT_CUDA(ctx, cudaMemcpy2DAsync(d_PsiB, sizeof(double) * nb, g.d_tpsi + nc, sizeof(double) * rows, sizeof(double) * nb, g.nAng,
@@ -662,7 +681,7 @@ void umt_gta_release(umt_ctx *ctx) {
   void *p[] = {g.d_omega, g.d_weight, g.d_nextZ, g.d_nextC, g.d_items, g.d_counters, g.d_sigTotal, g.d_sigtInv, g.d_sigScat, g.d_sigScatVol,
                g.d_greySource, g.d_tsaSource, g.d_phiInc, g.d_correction, g.d_chi, g.d_TT, g.d_tpsi, g.d_pinc, g.d_vec[0], g.d_vec[1], g.d_vec[2],
                g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB,
-               g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc, g.d_levelAngles, g.d_planeOff, g.d_nHyp};
+               g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc, g.d_levelAngles, g.d_planeOff, g.d_nHyp, g.d_reflOps};
   for (void *q : p) if (q) cudaFree(q);
   g = GtaState();
 }
@@ -677,7 +696,7 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: host-only context");
   if (!ctx->have_conn || !ctx->have_geom || ctx->h_zoneOpp.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: needs full connectivity and geometry");
   if (ctx->ndim == 3 && (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
-  if (!ctx->refl.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: reflecting boundaries are not supported by the GTA sweep yet");
+  if (!ctx->refl.empty() && ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: reflecting boundaries are not supported by the r-z GTA sweep yet");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   const int nd = ctx->ndim;
@@ -712,8 +731,17 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
     for (int p = 0; p < g.nHyp[a]; p++) { start[a][p + 1] = start[a][p] + g.zonesInPlane[a][p]; nIt[a][p] = (g.zonesInPlane[a][p] + zpi - 1) / zpi; }
   }
   if (nd == 2) TRY(umt_gta_finish_setup_rz(ctx, items));   // items chained along the xi-levels, r-z coefficient arrays
-  for (int p = 0; nd == 3 && p < g.maxHyp; p++)
+  // reflecting boundaries (GTASweep.F90:151 snreflect): angles in stages, mirror images first, one launch per stage
+  g.nStagesR = 1; g.stageOf.assign(g.nAng, 0);
+  if (nd == 3) {
+    TRY(umt_reflect_analyze(ctx, g.omega.data(), g.nAng, g.mref, g.stageOf));
+    g.nStagesR = 1 + *std::max_element(g.stageOf.begin(), g.stageOf.end());
+  }
+  g.stageItemBegin.assign(g.nStagesR + 1, 0);
+  for (int sR = 0; nd == 3 && sR < g.nStagesR; sR++) {
+  for (int p = 0; p < g.maxHyp; p++)
     for (int a = 0; a < g.nAng; a++) {
+      if (g.stageOf[a] != sR) continue;
       if (p >= g.nHyp[a]) continue;
       for (int k = 0; k < nIt[a][p]; k++) {
         WorkItem w;
@@ -723,6 +751,21 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
         items.push_back(w);
       }
     }
+    g.stageItemBegin[sR + 1] = (int)items.size();
+  }
+  if (nd == 2) g.stageItemBegin[1] = (int)items.size();
+  {
+    std::vector<int4> ops;
+    g.reflOpBegin.assign(g.nStagesR + 1, 0);
+    for (int sR = 0; sR < g.nStagesR; sR++) {
+      for (size_t k = 0; k < g.mref.size(); k++)
+        for (int a = 0; a < g.nAng; a++)
+          if (g.stageOf[a] == sR && g.mref[k][a] >= 0) ops.push_back(make_int4(a, g.mref[k][a], ctx->refl[k].first, ctx->refl[k].n));
+      g.reflOpBegin[sR + 1] = (int)ops.size();
+    }
+    TRY(dalloc(ctx, &g.d_reflOps, ops.size()));
+    if (!ops.empty()) UMT_CUDA(ctx, cudaMemcpy(g.d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
+  }
   g.nItems = (int)items.size(); g.nCounters = g.nAng * g.maxHyp;
   TRY(dalloc(ctx, &g.d_omega, (size_t)nd * g.nAng)); TRY(dalloc(ctx, &g.d_weight, g.nAng));
   TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));

@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(256) snreflect_kernel(double *psi1, const int4
 }
 
 // reflectAxis.F90:74-123: the boundary normal has exactly one non-zero component; the mirror angle flips it
-int mirror_angle(const umt_ctx *ctx, int inc, const double *Area, std::string &why) {
-  const int nd = ctx->ndim, NA = ctx->NA;
+int mirror_angle(const umt_ctx *ctx, const double *omegas, int NA, int inc, const double *Area, std::string &why) {
+  const int nd = ctx->ndim;
   const double fuz = 1.0e-6, tol = 1.0e-10;
   double mag = 0.0;
   for (int d = 0; d < nd; d++) mag += Area[d] * Area[d];
@@ -36,10 +36,10 @@ int mirror_angle(const umt_ctx *ctx, int inc, const double *Area, std::string &w
     else nmax = d;
   }
   if (nzero != nd - 1) { why = "only axis-aligned reflecting planes are supported"; return -2; }
-  const double *oi = &ctx->h_omega[(size_t)inc * nd];
+  const double *oi = &omegas[(size_t)inc * nd];
   int mref = -1;
   for (int ia = 0; ia < NA; ia++) {
-    const double *o = &ctx->h_omega[(size_t)ia * nd];
+    const double *o = &omegas[(size_t)ia * nd];
     if (std::fabs(o[nmax] + oi[nmax]) >= fuz) continue;
     bool same = true;
     for (int d = 0; d < nd; d++)
@@ -77,6 +77,60 @@ extern "C" int umt_get_reflect_stages(umt_ctx *ctx, int *stageOf) {
   int r = umt_reflect_stages(ctx);
   if (r) return r;
   std::copy(ctx->stageOf.begin(), ctx->stageOf.end(), stageOf);
+  return UMT_OK;
+}
+
+// mirror angles (per reflecting boundary) and sweep stages of an arbitrary ordinate set: the Sn set below, the GTA set in gta.cu
+int umt_reflect_analyze(umt_ctx *ctx, const double *omegas, int NA, std::vector<std::vector<int>> &mrefOut, std::vector<int> &stageOut) {
+  const int nd = ctx->ndim;
+  mrefOut.assign(ctx->refl.size(), std::vector<int>(NA, -1));
+  stageOut.assign(NA, 0);
+  if (ctx->refl.empty()) return UMT_OK;
+  if (!ctx->have_geom) UMT_FAIL(ctx, UMT_ERR_STATE, "reflecting boundaries need geometry");
+  std::vector<double> Abdy((size_t)nd * std::max(ctx->nb, 1), 0.0);
+  for (int c = 0; c < ctx->nc; c++)
+    for (int f = 0; f < ctx->h_nCFaces[c]; f++) {
+      const int v = ctx->h_cFP[(size_t)c * ctx->maxcf + f];
+      if (v > ctx->nc)
+        for (int d = 0; d < nd; d++) Abdy[(size_t)(v - ctx->nc - 1) * nd + d] = ctx->h_Afp[((size_t)c * ctx->maxcf + f) * nd + d];
+    }
+  const double eps = 1.0e-15;
+  for (size_t k = 0; k < ctx->refl.size(); k++) {
+    const double *A0 = &Abdy[(size_t)ctx->refl[k].first * nd];
+    for (int a = 0; a < NA; a++) {
+      double dot = 0.0;
+      for (int d = 0; d < nd; d++) dot += omegas[(size_t)a * nd + d] * A0[d];
+      if (dot < -eps) {
+        std::string why;
+        const int m = mirror_angle(ctx, omegas, NA, a, A0, why);
+        if (m < 0) UMT_FAIL(ctx, UMT_ERR_ARG, "reflecting boundary %zu, angle %d: %s", k, a + 1, why.c_str());
+        mrefOut[k][a] = m;
+      }
+    }
+  }
+  std::vector<int> state(NA, 0);
+  std::vector<std::vector<int>> deps(NA);
+  for (const auto &mr : mrefOut)
+    for (int a = 0; a < NA; a++) if (mr[a] >= 0) deps[a].push_back(mr[a]);
+  struct Frame { int a; size_t i; };
+  for (int root = 0; root < NA; root++) {
+    if (state[root]) continue;
+    std::vector<Frame> st{{root, 0}};
+    state[root] = 1;
+    while (!st.empty()) {
+      Frame &f = st.back();
+      if (f.i < deps[f.a].size()) {
+        const int m = deps[f.a][f.i++];
+        if (state[m] == 0) { state[m] = 1; st.push_back({m, 0}); }
+        else if (state[m] == 2) stageOut[f.a] = std::max(stageOut[f.a], stageOut[m] + 1);
+      } else {
+        state[f.a] = 2;
+        const int done = f.a;
+        st.pop_back();
+        if (!st.empty()) stageOut[st.back().a] = std::max(stageOut[st.back().a], stageOut[done] + 1);
+      }
+    }
+  }
   return UMT_OK;
 }
 
@@ -121,7 +175,7 @@ int umt_reflect_stages(umt_ctx *ctx) {
       for (int d = 0; d < nd; d++) dot += ctx->h_omega[(size_t)a * nd + d] * A0[d];
       if (dot < -eps) {
         std::string why;
-        const int m = mirror_angle(ctx, a, A0, why);
+        const int m = mirror_angle(ctx, ctx->h_omega.data(), NA, a, A0, why);
         if (m < 0) UMT_FAIL(ctx, UMT_ERR_ARG, "reflecting boundary %zu, angle %d: %s", k, a + 1, why.c_str());
         R.mref[a] = m;
       }

@@ -92,6 +92,11 @@ struct GtaState {
   double *d_radEnergy = nullptr, *d_pzOld = nullptr, *d_volZone = nullptr;   // (nz)
   double *d_red = nullptr;             // reduction scratch
   double *d_P = nullptr, *d_PB = nullptr;   // staging for the host-facing sweep calls
+  // reflecting boundaries (3-D): the angles are swept in stages, mirror images first; the PsiB copies of snreflect before each stage
+  int nStagesR = 1;
+  std::vector<int> stageOf, stageItemBegin, reflOpBegin;
+  std::vector<std::vector<int>> mref;
+  int4 *d_reflOps = nullptr;           // (minc, mref, first, n) grouped by stage
   // r-z: xi-levels chained through the half-angle values tPsiM / tInc (SweepGreyUCBrz.F90)
   std::vector<unsigned char> start, finish;
   std::vector<double> angDerivFac, tauW1, tauW2;
@@ -245,6 +250,7 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
 int umt_device_geometry(umt_ctx *ctx, const double *d_px);
 void umt_exchange_release(umt_ctx *ctx);
 int umt_reflect_stages(umt_ctx *ctx);
+int umt_reflect_analyze(umt_ctx *ctx, const double *omegas, int NA, std::vector<std::vector<int>> &mref, std::vector<int> &stageOf);
 int umt_launch_reflect(umt_ctx *ctx, int stage);
 void umt_gta_release(umt_ctx *ctx);
 int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vector<int> &nHyp, std::vector<std::vector<int>> &zonesInPlane,
