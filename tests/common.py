@@ -323,7 +323,7 @@ def oracle_reflected_angles(p):
             if p.omega[a] @ A < -1e-15:
                 for ia in range(p.NA):   # reflectAxis.F90:101-113, last match wins
                     if abs(p.omega[ia, nmax] + p.omega[a, nmax]) < 1e-6 and all(
-                            abs(p.omega[ia, d] - p.omega[a, d]) < 1e-6 for d in range(3) if d != nmax):
+                            abs(p.omega[ia, d] - p.omega[a, d]) < 1e-6 for d in range(p.omega.shape[1]) if d != nmax):
                         mref[a] = ia
                 assert mref[a] >= 0
         out.append(mref)
@@ -690,3 +690,66 @@ def oracle_multi_sweep_ordered(problems, lists, nCommSets, order, savePsi, maxFl
         if notconv == 0 or it >= maxFluxIters:
             break
     return phis, it, inc
+
+
+def rz_reflect_stages(p, mrefs):
+    """r-z stages as csrc/reflect.cu assigns them: xi-levels ordered by the mirror dependencies between levels (same DFS, back edges
+    lagged), every angle of a level its own step."""
+    lev = np.asarray(p.q["level"]) - 1
+    nL = int(lev.max()) + 1
+    ldeps = [[] for _ in range(nL)]
+    for m in mrefs:
+        for a in range(p.NA):
+            if m[a] >= 0 and lev[m[a]] != lev[a]:
+                ldeps[lev[a]].append(int(lev[m[a]]))
+    lstage, state = [0] * nL, [0] * nL
+    for root in range(nL):
+        if state[root]:
+            continue
+        st = [[root, 0]]
+        state[root] = 1
+        while st:
+            a, i = st[-1]
+            if i < len(ldeps[a]):
+                st[-1][1] += 1
+                m = ldeps[a][i]
+                if state[m] == 0:
+                    state[m] = 1
+                    st.append([m, 0])
+                elif state[m] == 2:
+                    lstage[a] = max(lstage[a], lstage[m] + 1)
+            else:
+                state[a] = 2
+                st.pop()
+                if st:
+                    lstage[st[-1][0]] = max(lstage[st[-1][0]], lstage[a] + 1)
+    cnt = [0] * nL
+    pos = []
+    for a in range(p.NA):
+        pos.append(cnt[lev[a]])
+        cnt[lev[a]] += 1
+    maxPos = max(cnt)
+    return [lstage[lev[a]] * maxPos + pos[a] for a in range(p.NA)]
+
+
+def oracle_sweep_rz_reflecting(p, savePsi):
+    """SetSweep angle loop in r-z with snreflect right before every swept angle (SetSweep.F90:139-143); levels advance together
+    in the stage order of rz_reflect_stages, PsiM kept per xi-level."""
+    m = p.mesh
+    mrefs = oracle_reflected_angles(p)
+    stage = rz_reflect_stages(p, mrefs)
+    refl = reflecting_boundaries(m)
+    lev = np.asarray(p.q["level"]) - 1
+    Phi = np.zeros((m.ncornr, p.G))
+    PsiM = {int(l): np.zeros((m.ncornr, p.G)) for l in set(lev.tolist())}
+    Psi1 = np.zeros((m.ncornr + m.nbelem, p.G))
+    for s in range(max(stage) + 1):
+        for a in [a for a in range(p.NA) if stage[a] == s]:
+            if p.q["finish"][a]:
+                continue
+            for k, b in enumerate(refl):
+                if mrefs[k][a] >= 0:
+                    sl = slice(b.first_elem - 1, b.first_elem - 1 + b.n_elem)
+                    p.PsiB[a, sl] = p.PsiB[mrefs[k][a], sl]
+            O.sweep_rz(p.om, p.geom, p.sched, a, p.q, p.tau, p.STotal, p.Sigt, p.Psi, Psi1, PsiM[int(lev[a])], p.PsiB, Phi, p.bdy[a], savePsi)
+    return Phi, stage, mrefs

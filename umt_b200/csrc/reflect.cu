@@ -207,6 +207,42 @@ int umt_reflect_stages(umt_ctx *ctx) {
     }
   }
   if (ctx->have_comm_order) ctx->stageOf = ctx->commStageOf;   // SweepScheduler's order already honours the mirror dependencies
+  if (nd == 2) {
+    // r-z: the angles of a xi-level are a chain (PsiM), so stages are assigned per level from the mirror dependencies *between*
+    // levels (z-normal planes: the partner level), and inside a level every angle gets its own step: snreflect then runs right
+    // before each angle exactly as in the reference (a mirror image earlier in the level is fresh, a later one lagged one pass).
+    // Finishing directions are not swept and get no copy (SetSweep.F90:141-143).
+    const int nL = std::max(ctx->nLevels, 1);
+    std::vector<std::vector<int>> ldeps(nL);
+    for (const auto &R : ctx->refl)
+      for (int a = 0; a < NA; a++)
+        if (R.mref[a] >= 0 && ctx->h_level[R.mref[a]] != ctx->h_level[a]) ldeps[ctx->h_level[a]].push_back(ctx->h_level[R.mref[a]]);
+    std::vector<int> lstage(nL, 0), lstate(nL, 0);
+    for (int root = 0; root < nL; root++) {
+      if (lstate[root]) continue;
+      std::vector<Frame> st{{root, 0}};
+      lstate[root] = 1;
+      while (!st.empty()) {
+        Frame &f = st.back();
+        if (f.i < ldeps[f.a].size()) {
+          const int m = ldeps[f.a][f.i++];
+          if (lstate[m] == 0) { lstate[m] = 1; st.push_back({m, 0}); }
+          else if (lstate[m] == 2) lstage[f.a] = std::max(lstage[f.a], lstage[m] + 1);
+        } else {
+          lstate[f.a] = 2;
+          const int done = f.a;
+          st.pop_back();
+          if (!st.empty()) lstage[st.back().a] = std::max(lstage[st.back().a], lstage[done] + 1);
+        }
+      }
+    }
+    int maxPos = 1;
+    std::vector<int> pos(NA, 0), cnt(nL, 0);
+    for (int a = 0; a < NA; a++) { pos[a] = cnt[ctx->h_level[a]]++; maxPos = std::max(maxPos, cnt[ctx->h_level[a]]); }
+    for (int a = 0; a < NA; a++) ctx->stageOf[a] = lstage[ctx->h_level[a]] * maxPos + pos[a];
+    for (auto &R : ctx->refl)
+      for (int a = 0; a < NA; a++) if (ctx->h_finish[a]) R.mref[a] = -1;
+  }
   ctx->nStages = 1 + *std::max_element(ctx->stageOf.begin(), ctx->stageOf.end());
   if (ctx->device < 0) return UMT_OK;
   std::vector<int4> ops;

@@ -309,7 +309,16 @@ __global__ void __launch_bounds__(256) sweeprz_chain_kernel(SweepRZParams P) {
 int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
   int maxHyp = 0;
   int r = umt_build_items_rz_set(ctx->nz, ctx->NA, ctx->nHyp, ctx->zonesInPlane, ctx->nextZ, ctx->h_start, zpi, items, ctx->h_level, ctx->nLevels, maxHyp);
-  if (r || ctx->device < 0) return r;
+  if (r) return r;
+  if (ctx->nStages > 1) {   // reflecting boundaries: one launch per stage, items of a stage contiguous (their relative order kept)
+    std::stable_sort(items.begin(), items.end(), [&](const WorkItem &x, const WorkItem &y) { return ctx->stageOf[x.angle] < ctx->stageOf[y.angle]; });
+    size_t i = 0;
+    for (int st = 0; st < ctx->nStages; st++) {
+      while (i < items.size() && ctx->stageOf[items[i].angle] <= st) i++;
+      ctx->stageItemBegin[st + 1] = (int)i;
+    }
+  }
+  if (ctx->device < 0) return r;
   // tables of the chain kernel: swept angles of every level in order, plane offsets, and its geometry: gb groups per CTA so
   // that a (corner, group block) access is at least one 32-byte sector, as many threads as the largest plane has pairs
   const int NA = ctx->NA, nL = ctx->nLevels;
@@ -436,7 +445,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   // Set%PsiM = 0 at the start of every flux pass (SetSweep.F90:94-96)
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * (size_t)ctx->nLevels * ctx->nc * ctx->G, ctx->stream));
-  if (ctx->rz_chain) {
+  if (ctx->rz_chain && ctx->nStages <= 1) {
     P.gb = ctx->rz_gb; P.nGroupBlocks = (ctx->G + ctx->rz_gb - 1) / ctx->rz_gb; P.maxAngLevel = ctx->rz_maxAngLevel; P.hypStride = ctx->maxHyp + 1;
     P.levelAngles = ctx->d_rzLevelAngles; P.planeOff = ctx->d_rzPlaneOff; P.nHyp = ctx->d_rzNHyp;
     void (*ck)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_chain_kernel<4> : sweeprz_chain_kernel<MAXC2>;
@@ -449,9 +458,24 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RZ_BLOCK, 0));
   if (occ < 1) occ = 1;
-  const int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
-  kern<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P);
-  UMT_CUDA(ctx, cudaGetLastError());
-  ctx->last_launches += 1;
+  if (ctx->nStages <= 1) {
+    const int grid = std::max(1, std::min(ctx->sm_count * occ, ctx->nItems));
+    kern<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches += 1;
+    return UMT_OK;
+  }
+  for (int st = 0; st < ctx->nStages; st++) {   // reflecting boundaries: snreflect, then the angles of this stage
+    const int begin = ctx->stageItemBegin[st], end = ctx->stageItemBegin[st + 1];
+    int r = umt_launch_reflect(ctx, st);
+    if (r) return r;
+    if (end == begin) continue;
+    if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
+    P.items = ctx->d_items + begin; P.nItems = end - begin;
+    const int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
+    kern<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches += 1;
+  }
   return UMT_OK;
 }

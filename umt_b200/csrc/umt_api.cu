@@ -366,8 +366,7 @@ static int finalize_schedule(umt_ctx *ctx) {
   TRY(umt_reflect_stages(ctx));
   ctx->stageItemBegin.assign(ctx->nStages + 1, 0);
   if (ctx->ndim == 2) {
-    if (ctx->nStages > 1) UMT_FAIL(ctx, UMT_ERR_STATE, "reflecting boundaries are not supported by the RZ sweep yet");
-    TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering
+    TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering; grouped by reflection stage
   } else {
     for (int s = 0; s < ctx->nStages; s++) {
       std::vector<int> ang;
