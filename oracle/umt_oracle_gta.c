@@ -363,16 +363,35 @@ void orc_gta_grey_sweep(const orc_gta *S, double *PsiB, double *P, int withSourc
   double *tPsi = malloc(sizeof(double) * (nc + nb)), *pInc = malloc(sizeof(double) * nc);
   for (int c = 0; c < nc; c++) TsaSource[c] = S->wtiso * (S->GreySigScat[c] * P[c] + S->GreySource[c]);
   if (M->ndim == 2) {
-    /* GTASweep.F90:113-119: tPsiM = tInc = 0, then every non-finishing angle in turn (:149-159) */
-    double *tPsiM = calloc(nc, sizeof(double)), *tInc = calloc(nc, sizeof(double));
-    for (int a = 0; a < S->nAng; a++) {
-      if (S->finish[a]) continue;
-      orc_gta_sweep_angle_rz(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
-                             S->nextC + (size_t)nc * a, S->omega + 2 * a, S->weight[a], S->angDerivFac[a], S->quadTauW1[a],
-                             S->quadTauW2[a], S->start[a], S->Volume, S->Area, S->A_fp, S->A_ez, S->RadiusFP, S->RadiusEZ,
-                             S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, tPsiM, tInc, PsiB + (size_t)nb * a, PhiInc);
+    /* GTASweep.F90:113-119: tPsiM = tInc = 0, then every non-finishing angle in turn (:149-159), snreflect before each (:151).
+       With reflecting boundaries the angles are taken in stage order (levels advance together), so the half-angle arrays are
+       kept per xi-level; PhiInc is summed in angle order afterwards */
+    int nLev = 0;
+    int levelOf[64];
+    for (int a = 0; a < S->nAng; a++) { if (S->start[a]) nLev++; levelOf[a] = nLev - 1; }
+    double *tPsiM = calloc((size_t)nc * nLev, sizeof(double)), *tInc = calloc((size_t)nc * nLev, sizeof(double));
+    double *pAll = calloc((size_t)nc * S->nAng, sizeof(double)), *dummy = calloc(nc, sizeof(double));
+    const int nSt = S->nReflOps > 0 ? S->nStagesR : 1;
+    for (int st = 0; st < nSt; st++) {
+      for (int a = 0; a < S->nAng; a++) {
+        if (S->finish[a]) continue;
+        if (S->nReflOps > 0 && S->angleStage[a] != st) continue;
+        for (int o = 0; o < S->nReflOps; o++) {
+          const int *op = S->reflOps + 5 * o;
+          if (op[0] != st || op[1] != a) continue;
+          for (int i = 0; i < op[4]; i++) PsiB[(size_t)nb * op[1] + op[3] + i] = PsiB[(size_t)nb * op[2] + op[3] + i];
+        }
+        orc_gta_sweep_angle_rz(M, S->nHyperPlanes[a], S->zonesInPlane + (size_t)nz * a, S->nextZ + (size_t)nz * a,
+                               S->nextC + (size_t)nc * a, S->omega + 2 * a, S->weight[a], S->angDerivFac[a], S->quadTauW1[a],
+                               S->quadTauW2[a], S->start[a], S->Volume, S->Area, S->A_fp, S->A_ez, S->RadiusFP, S->RadiusEZ,
+                               S->GreySigTotal, S->GreySigtInv, TsaSource, tPsi, pInc, tPsiM + (size_t)nc * levelOf[a],
+                               tInc + (size_t)nc * levelOf[a], PsiB + (size_t)nb * a, dummy);
+        memcpy(pAll + (size_t)nc * a, pInc, sizeof(double) * nc);
+      }
     }
-    free(tPsiM); free(tInc);
+    for (int a = 0; a < S->nAng; a++)
+      for (int c = 0; c < nc; c++) PhiInc[c] = PhiInc[c] + S->weight[a] * pAll[(size_t)nc * a + c];
+    free(tPsiM); free(tInc); free(pAll); free(dummy);
   } else {
     /* PhiInc is summed in angle order whatever the sweep order (as gta_phiinc_kernel does): each angle's w pInc is kept */
     const int nSt = S->nReflOps > 0 ? S->nStagesR : 1;

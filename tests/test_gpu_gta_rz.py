@@ -111,3 +111,50 @@ def test_gta_rz_solver_matches_oracle(name, mk):
     ctx.add_grey_corrections()
     assert np.abs(ctx.download_phi() - phi_ref).max() <= 1e-8 * np.abs(phi_ref).max()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# reflecting boundaries in the r-z grey sweeps
+# ---------------------------------------------------------------------------
+def _reflect_info(mesh, g, q):
+    class _P:
+        pass
+    p = _P()
+    p.mesh, p.geom, p.omega, p.NA, p.q = mesh, g, q["omega"], 8, q
+    mrefs = T.oracle_reflected_angles(p)
+    stage = T.rz_reflect_stages(p, mrefs)
+    ops = [(stage[a], a, int(mr[a]), b.first_elem - 1, b.n_elem) for mr, b in zip(mrefs, T.reflecting_boundaries(mesh))
+           for a in range(8) if mr[a] >= 0 and not q["finish"][a]]
+    return np.array(stage, np.int32), np.array(ops, np.int32).reshape(-1, 5)
+
+
+@pytest.mark.parametrize("sides", [(2,), (3,), (2, 3), (1,), (1, 3)])
+def test_gta_rz_reflecting_matches_oracle(sides):
+    mesh = M.tiled_mesh((2, 2, 0), reflecting=sides)
+    s = _setup(mesh)
+    ctx, om, g, q = s["ctx"], s["om"], s["g"], s["q"]
+    for b in T.reflecting_boundaries(mesh):
+        ctx.add_reflecting_boundary(b.first_elem, b.n_elem)
+    ctx.gta_setup()
+    nc, nb = mesh.ncornr, mesh.nbelem
+    refl = _reflect_info(mesh, g, q)
+    chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()
+    op = O.gta_set_opacity(om, g, s["tau"], s["Siga"], s["Sigs"], s["Eta"], chi_ref)
+    ctx.gta_compute_opacity(s["Siga"], s["Sigs"], s["Eta"], chi_dev)
+    gs = O.collision_rate(om, s["Eta"], s["Siga"], s["Sigs"], s["Phi"], np.zeros(nc), 0)
+    ctx.collision_rate(s["Eta"], s["Siga"], s["Sigs"], 0)
+    P = O.GtaProblem(om, g, s["sched"], q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q, reflect=refl)
+    P.init_tt()
+    ctx.gta_init_tt()
+    rng = np.random.default_rng(11)
+    Pr, Br = rng.random(nc), rng.random((8, nb))
+    Pd, Bd = Pr.copy(), Br.copy()
+    P.grey_sweep(Br, Pr, True)
+    ctx.gta_grey_sweep(Pd, Bd, True)
+    assert T.mixed_err(Pd, Pr, 1e-11) <= 1.0 and T.mixed_err(Bd, Br, 1e-11) <= 1.0
+    P2 = O.GtaProblem(om, g, s["sched"], q["omega"], q["weight"], op, gs, PR.wtiso(2), q=q, reflect=refl)
+    corr, n, err = P2.solve(s["Phi"])
+    corr_d, n_d, err_d = ctx.gta_solve()
+    assert n_d == n and n > 3
+    assert np.abs(corr_d - corr).max() <= 1e-8 * np.abs(corr).max()
+    ctx.close()

@@ -696,7 +696,6 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: host-only context");
   if (!ctx->have_conn || !ctx->have_geom || ctx->h_zoneOpp.empty()) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: needs full connectivity and geometry");
   if (ctx->ndim == 3 && (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_gta_setup: maxCorner <= 8, maxcf == 3");
-  if (!ctx->refl.empty() && ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_setup: reflecting boundaries are not supported by the r-z GTA sweep yet");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   const int nd = ctx->ndim;
@@ -733,9 +732,27 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   if (nd == 2) TRY(umt_gta_finish_setup_rz(ctx, items));   // items chained along the xi-levels, r-z coefficient arrays
   // reflecting boundaries (GTASweep.F90:151 snreflect): angles in stages, mirror images first, one launch per stage
   g.nStagesR = 1; g.stageOf.assign(g.nAng, 0);
-  if (nd == 3) {
-    TRY(umt_reflect_analyze(ctx, g.omega.data(), g.nAng, g.mref, g.stageOf));
-    g.nStagesR = 1 + *std::max_element(g.stageOf.begin(), g.stageOf.end());
+  TRY(umt_reflect_analyze(ctx, g.omega.data(), g.nAng, g.mref, g.stageOf));
+  if (nd == 2 && !ctx->refl.empty()) {
+    // r-z: levels ordered by the mirror dependencies between levels, every angle of a level its own step (as reflect.cu does for
+    // the multigroup sweep); finishing directions are not swept and get no copy
+    const int nL = std::max(g.nLevels, 1);
+    std::vector<std::vector<int>> ldeps(nL);
+    for (const auto &mr : g.mref)
+      for (int a = 0; a < g.nAng; a++)
+        if (mr[a] >= 0 && g.level[mr[a]] != g.level[a]) ldeps[g.level[a]].push_back(g.level[mr[a]]);
+    std::vector<int> lstage;
+    umt_level_stages(nL, ldeps, lstage);
+    int maxPos = 1;
+    std::vector<int> pos(g.nAng, 0), cnt(nL, 0);
+    for (int a = 0; a < g.nAng; a++) { pos[a] = cnt[g.level[a]]++; maxPos = std::max(maxPos, cnt[g.level[a]]); }
+    for (int a = 0; a < g.nAng; a++) g.stageOf[a] = lstage[g.level[a]] * maxPos + pos[a];
+    for (auto &mr : g.mref) for (int a = 0; a < g.nAng; a++) if (g.finish[a]) mr[a] = -1;
+  }
+  g.nStagesR = 1 + *std::max_element(g.stageOf.begin(), g.stageOf.end());
+  if (nd == 2 && g.nStagesR > 1) {   // items of a stage contiguous, their relative order kept
+    std::stable_sort(items.begin(), items.end(), [&](const WorkItem &x, const WorkItem &y) { return g.stageOf[x.angle] < g.stageOf[y.angle]; });
+    g.rz_chain = false;              // the chain kernel owns whole levels; stages cut across them
   }
   g.stageItemBegin.assign(g.nStagesR + 1, 0);
   for (int sR = 0; nd == 3 && sR < g.nStagesR; sR++) {
@@ -753,7 +770,13 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
     }
     g.stageItemBegin[sR + 1] = (int)items.size();
   }
-  if (nd == 2) g.stageItemBegin[1] = (int)items.size();
+  if (nd == 2) {
+    size_t i = 0;
+    for (int sR = 0; sR < g.nStagesR; sR++) {
+      while (i < items.size() && g.stageOf[items[i].angle] <= sR) i++;
+      g.stageItemBegin[sR + 1] = (int)i;
+    }
+  }
   {
     std::vector<int4> ops;
     g.reflOpBegin.assign(g.nStagesR + 1, 0);

@@ -228,6 +228,12 @@ __global__ void __launch_bounds__(256) gta_sweep_rz_chain_kernel(GtaRZParams P, 
   }
 }
 
+__global__ void gta_reflect_rows_kernel(double *tpsi, const int4 *ops, int rows, int nc) {
+  const int4 o = ops[blockIdx.y];   // x = Minc, y = Mref, z = first boundary element, w = count
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < o.w) tpsi[(size_t)o.x * rows + nc + o.z + i] = tpsi[(size_t)o.y * rows + nc + o.z + i];
+}
+
 struct TTRZParams {
   int nz, nc, mC, nAng;
   const int *numCorner, *cOffSet, *cEZ;
@@ -397,9 +403,21 @@ int umt_gta_launch_sweep_rz(umt_ctx *ctx) {
   void (*kern)(GtaRZParams) = ctx->maxCorner <= 4 ? gta_sweep_rz_kernel<4> : gta_sweep_rz_kernel<MAXC2>;
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GRZ_BLOCK, 0));
-  const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), g.nItems));
-  kern<<<grid, GRZ_BLOCK, 0, ctx->stream>>>(P);
-  UMT_CUDA(ctx, cudaGetLastError());
+  for (int sR = 0; sR < g.nStagesR; sR++) {   // one stage unless the domain has reflecting boundaries
+    const int ib = g.stageItemBegin[sR], ie = g.stageItemBegin[sR + 1];
+    const int ob = g.reflOpBegin[sR], oe = g.reflOpBegin[sR + 1];
+    if (oe > ob) {   // snreflect: PsiB(b, Minc) <- PsiB(b, Mref), the tail rows of tPsi
+      int maxN = 1;
+      for (const auto &R : ctx->refl) maxN = std::max(maxN, R.n);
+      gta_reflect_rows_kernel<<<dim3((maxN + 255) / 256, oe - ob), 256, 0, ctx->stream>>>(g.d_tpsi, g.d_reflOps + ob, nc + ctx->nb, nc);
+    }
+    if (ie == ib) continue;
+    if (sR > 0) UMT_CUDA(ctx, cudaMemsetAsync(g.d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
+    P.items = g.d_items + ib; P.nItems = ie - ib;
+    const int grid = std::max(1, std::min(ctx->sm_count * std::max(occ, 1), P.nItems));
+    kern<<<grid, GRZ_BLOCK, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
   return UMT_OK;
 }
 

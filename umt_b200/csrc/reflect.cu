@@ -134,6 +134,31 @@ int umt_reflect_analyze(umt_ctx *ctx, const double *omegas, int NA, std::vector<
   return UMT_OK;
 }
 
+// stage of every node of a dependency graph = longest chain of dependencies below it; an edge that would close a cycle is lagged
+void umt_level_stages(int nL, const std::vector<std::vector<int>> &ldeps, std::vector<int> &lstage) {
+  struct Frame { int a; size_t i; };
+  lstage.assign(nL, 0);
+  std::vector<int> lstate(nL, 0);
+  for (int root = 0; root < nL; root++) {
+    if (lstate[root]) continue;
+    std::vector<Frame> st{{root, 0}};
+    lstate[root] = 1;
+    while (!st.empty()) {
+      Frame &f = st.back();
+      if (f.i < ldeps[f.a].size()) {
+        const int m = ldeps[f.a][f.i++];
+        if (lstate[m] == 0) { lstate[m] = 1; st.push_back({m, 0}); }
+        else if (lstate[m] == 2) lstage[f.a] = std::max(lstage[f.a], lstage[m] + 1);
+      } else {
+        lstate[f.a] = 2;
+        const int done = f.a;
+        st.pop_back();
+        if (!st.empty()) lstage[st.back().a] = std::max(lstage[st.back().a], lstage[done] + 1);
+      }
+    }
+  }
+}
+
 int umt_reflect_stages(umt_ctx *ctx) {
   const int NA = ctx->NA, nd = ctx->ndim;
   ctx->stageOf.assign(NA, 0);
@@ -217,25 +242,8 @@ int umt_reflect_stages(umt_ctx *ctx) {
     for (const auto &R : ctx->refl)
       for (int a = 0; a < NA; a++)
         if (R.mref[a] >= 0 && ctx->h_level[R.mref[a]] != ctx->h_level[a]) ldeps[ctx->h_level[a]].push_back(ctx->h_level[R.mref[a]]);
-    std::vector<int> lstage(nL, 0), lstate(nL, 0);
-    for (int root = 0; root < nL; root++) {
-      if (lstate[root]) continue;
-      std::vector<Frame> st{{root, 0}};
-      lstate[root] = 1;
-      while (!st.empty()) {
-        Frame &f = st.back();
-        if (f.i < ldeps[f.a].size()) {
-          const int m = ldeps[f.a][f.i++];
-          if (lstate[m] == 0) { lstate[m] = 1; st.push_back({m, 0}); }
-          else if (lstate[m] == 2) lstage[f.a] = std::max(lstage[f.a], lstage[m] + 1);
-        } else {
-          lstate[f.a] = 2;
-          const int done = f.a;
-          st.pop_back();
-          if (!st.empty()) lstage[st.back().a] = std::max(lstage[st.back().a], lstage[done] + 1);
-        }
-      }
-    }
+    std::vector<int> lstage;
+    umt_level_stages(nL, ldeps, lstage);
     int maxPos = 1;
     std::vector<int> pos(NA, 0), cnt(nL, 0);
     for (int a = 0; a < NA; a++) { pos[a] = cnt[ctx->h_level[a]]++; maxPos = std::max(maxPos, cnt[ctx->h_level[a]]); }

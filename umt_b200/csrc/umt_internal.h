@@ -250,6 +250,7 @@ int umt_host_product_quadrature(int ndim, int npolar, int nazimuthal, int polara
 int umt_device_geometry(umt_ctx *ctx, const double *d_px);
 void umt_exchange_release(umt_ctx *ctx);
 int umt_reflect_stages(umt_ctx *ctx);
+void umt_level_stages(int nL, const std::vector<std::vector<int>> &ldeps, std::vector<int> &lstage);
 int umt_reflect_analyze(umt_ctx *ctx, const double *omegas, int NA, std::vector<std::vector<int>> &mref, std::vector<int> &stageOf);
 int umt_launch_reflect(umt_ctx *ctx, int stage);
 void umt_gta_release(umt_ctx *ctx);
