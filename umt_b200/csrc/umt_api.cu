@@ -66,7 +66,9 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
   // L2 set-aside for evict_last lines: the sweep stores Psi1 rows with an evict_last hint so that the downstream zones find
   // them in L2; without a persisting carve-out the hint has nothing to hold on to.  UMT_L2_PERSIST_MB overrides (0 = off).
   {
-    size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);   // 64 MB of the 126 MB: more slows the streaming kernels
+    // 64 MB of the 126 MB: more slows the streaming kernels.  Set once: toggling the limit around every sweep gave the phi kernel
+    // its 0.4 ms back but made bench.py hang under ncu (cudaDeviceSetLimit between profiled kernels)
+    size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)64 << 20);
     if (const char *ev = getenv("UMT_L2_PERSIST_MB")) want = std::min(want, (size_t)std::max(0, atoi(ev)) << 20);
     if (ndim != 3) want = 0;   // only the 3-D plan kernel uses evict_last; the r-z kernels lose 7 % to a smaller normal L2
     if (want > 0) {
@@ -705,7 +707,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   int iter = 0;
   const bool multi = !ctx->shared.empty();
-  if (ctx->l2_persist && ctx->ndim == 3 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_bytes) != cudaSuccess) cudaGetLastError();
+
   if (multi) TRY(umt_exchange_tally(ctx, fluxTol));   // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74); packs the exiting rows
   for (;;) {
     iter++;
@@ -742,12 +744,7 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
     if (savePsi) break;                              // SetSweep.F90:185-187
     if (nNotConv == 0 || iter >= maxFluxIters) break;
   }
-  // the sweep's evict_last Psi1 lines have served their purpose: hand the set-aside L2 back to the streaming kernels that follow
-  // (phi reduction, GTA); the stream is idle here (event synchronised above)
-  if (ctx->l2_persist && ctx->ndim == 3) {
-    if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
-  }
+
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   TRY(launch_phi(ctx, ctx->d_psi1));
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
