@@ -61,16 +61,21 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 // those 700-byte frames fall out of L1: every "array" access then costs an L2 round trip inside a dependent chain.  All loops
 // over corners and faces are therefore fully unrolled and the few dynamic accesses go through select chains, which keeps the
 // whole zone in registers.
-// Everything of one (zone, group) solve that does not depend on other work items: loaded and computed while the CTA's
-// dependencies are still being resolved, so that after the wait only the upstream fluxes and PsiM remain to be read.
+// Everything of one (zone, group) solve that does not depend on other work items, computed while the CTA's dependencies are still
+// being resolved.  The corner-balance closure is linear in the upstream fluxes u = Psi1(row) and in PsiM, so the static half goes
+// all the way to that linear form -- including every division -- and the half on the dependency chain is a handful of FMAs:
+//   src(c)  = srcS(c) + sum_f k1(c,f) u(c,f)            (k1 = -R_fp afp + A1: incident face, and its share of the EZ closure)
+//   src(cez(c,f)) += k2(c,f) u(c,f)                     (k2 = -A1)
+//   psi(c_i) = (src(c_i) + areaFac_i PsiM(c_i)) inv_i,  src(dz_i[f]) += rz_i[f] psi(c_i)    for the corners c_i in nextC order
+// with sez(c,f) = A1 u + A0 (SweepUCBrz.F90:170-205; A0 is folded into srcS).  Same arithmetic as the reference up to the order in
+// which the terms of src are added and the reciprocal of the denominator.
 template <int MC>
 struct ZoneStatic {
-  double Q[MC], srcInit[MC], sumArea[MC], volSig[MC], areaFac[MC], area[MC];
-  double aez[MC][2], Rafp[MC][2], Raez[MC][2], Rez[MC][2];
-  int row[MC][2], cez[MC][2];
+  double srcS[MC], k1[MC][2], k2[MC][2];
+  double areaFac[MC], inv[MC], rz[MC][2];   // areaFac: by corner; inv, rz: by solve step
+  int row[MC][2], cez[MC][2], dz[MC][2], ci[MC];
   unsigned inMask, exitMask;   // bit 2c+f: omega.A_fp < 0 (incident) / omega.A_fp > 0 on a boundary face (exiting)
   int nCorner, c0;
-  double sig;
 };
 
 template <int MC>
@@ -79,129 +84,140 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
   const double om0 = P.omega[2 * a], om1 = P.omega[2 * a + 1];
   const size_t slab = (size_t)(nc + P.nb) * G;
   const double *psiA = P.psi + (size_t)a * slab;
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
   const double sig = P.sigt[(size_t)zone * G + g];
   const double fac = P.angDerivFac[a];
-  Z.nCorner = nCorner; Z.c0 = c0; Z.sig = sig; Z.inMask = 0u; Z.exitMask = 0u;
+  Z.nCorner = nCorner; Z.c0 = c0; Z.inMask = 0u; Z.exitMask = 0u;
+  double Q[MC], sumArea[MC], volSig[MC], area[MC], aez[MC][2], Raez[MC][2];
 #pragma unroll
   for (int c = 0; c < MC; c++) {
-    Z.Q[c] = 0.0; Z.srcInit[c] = 0.0; Z.sumArea[c] = 1.0; Z.volSig[c] = 0.0; Z.areaFac[c] = 0.0; Z.area[c] = 0.0;
+    Q[c] = 0.0; Z.srcS[c] = 0.0; sumArea[c] = 1.0; volSig[c] = 0.0; Z.areaFac[c] = 0.0; area[c] = 0.0; Z.ci[c] = c;
     if (c < nCorner) {
       const size_t r = (size_t)(c0 + c) * G + g;
       const double source = P.stotal[r] + P.tau * psiA[r];
-      const double area = P.Area[c0 + c], vol = P.Volume[c0 + c];
-      Z.Q[c] = source;
-      Z.srcInit[c] = vol * source;
-      Z.sumArea[c] = fac * area;
-      Z.volSig[c] = sig * vol;
-      Z.areaFac[c] = area * fac;
-      Z.area[c] = area;
+      const double ar = P.Area[c0 + c], vol = P.Volume[c0 + c];
+      Q[c] = source;
+      Z.srcS[c] = vol * source;
+      sumArea[c] = fac * ar;
+      volSig[c] = sig * vol;
+      Z.areaFac[c] = ar * fac;
+      area[c] = ar;
+      Z.ci[c] = nextC[c0 + c];
     }
   }
+  double afpv[MC][2], rfp[MC][2], rez[MC][2];
 #pragma unroll
-  for (int c = 0; c < MC; c++) {
+  for (int c = 0; c < MC; c++)
 #pragma unroll
-    for (int f = 0; f < 2; f++) { Z.aez[c][f] = 0.0; Z.Rafp[c][f] = 0.0; Z.Raez[c][f] = 0.0; Z.Rez[c][f] = 0.0; Z.row[c][f] = 0; Z.cez[c][f] = 0; }
-    if (c < nCorner) {
-      const int cc = c0 + c;
-#pragma unroll
-      for (int f = 0; f < 2; f++) {
+    for (int f = 0; f < 2; f++) {
+      aez[c][f] = 0.0; afpv[c][f] = 0.0; rfp[c][f] = 0.0; rez[c][f] = 0.0; Raez[c][f] = 0.0;
+      Z.k1[c][f] = 0.0; Z.k2[c][f] = 0.0; Z.row[c][f] = 0; Z.cez[c][f] = 0;
+      if (c < nCorner) {
+        const int cc = c0 + c;
         const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2;
         const double *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
-        const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
-        const double aez = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
-        const int row = P.cFP[cc * 2 + f];
-        Z.aez[c][f] = aez;
-        Z.row[c][f] = row;
+        afpv[c][f] = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
+        aez[c][f] = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
+        Z.row[c][f] = P.cFP[cc * 2 + f];
         Z.cez[c][f] = P.cEZ[cc * 2 + f];
-        const double rfp = P.RadiusFP[cc * 2 + f], rez = P.RadiusEZ[cc * 2 + f];   // unconditional: not one round trip per sign test
-        if (afp < 0.0) {
-          Z.inMask |= 1u << (2 * c + f);
-          Z.Rafp[c][f] = rfp * afp;
-          Z.sumArea[c] -= Z.Rafp[c][f];
-        } else if (afp > 0.0 && row >= nc) Z.exitMask |= 1u << (2 * c + f);
-        if (aez > 0.0) {
-          Z.Rez[c][f] = rez;
-          Z.Raez[c][f] = rez * aez;
-        }
+        rfp[c][f] = P.RadiusFP[cc * 2 + f];
+        rez[c][f] = P.RadiusEZ[cc * 2 + f];
       }
     }
-  }
-  // the EZ face of corner c adds to the denominator of the corner behind it (second pass: sumArea of every corner is initialised)
 #pragma unroll
   for (int c = 0; c < MC; c++)
 #pragma unroll
     for (int f = 0; f < 2; f++)
-      if (c < nCorner && Z.aez[c][f] > 0.0) addto<MC>(Z.sumArea, Z.cez[c][f], Z.Raez[c][f]);
+      if (c < nCorner) {
+        const double afp = afpv[c][f], az = aez[c][f];
+        const bool inc = afp < 0.0;
+        if (inc) {
+          Z.inMask |= 1u << (2 * c + f);
+          const double Rafp = rfp[c][f] * afp;
+          Z.k1[c][f] = -Rafp;
+          sumArea[c] -= Rafp;
+        } else if (afp > 0.0 && Z.row[c][f] >= nc) Z.exitMask |= 1u << (2 * c + f);
+        if (az > 0.0) {
+          const int cez = Z.cez[c][f];
+          const double R = rez[c][f], qcez = pick<MC>(Q, cez);
+          Raez[c][f] = R * az;
+          addto<MC>(sumArea, cez, Raez[c][f]);
+          double A0;
+          if (inc) {
+            const double ar = area[c];
+            const double sigA = sig * ar, sigA2 = sigA * sigA;
+            const double gnum = az * az * (FOURALPHA * sigA2 + az * (4.0 * sigA + 3.0 * az));
+            const double gden = ar * (4.0 * sigA * sigA2 + az * (6.0 * sigA2 + 2.0 * az * (2.0 * sigA + az)));
+            const double rd = R / (gnum + gden * sig);
+            const double A1 = rd * (ar * gnum * sig);
+            A0 = rd * (0.5 * az * gden * (Q[c] - qcez) - ar * gnum * Q[c]);
+            Z.k1[c][f] += A1;
+            Z.k2[c][f] = -A1;
+          } else {
+            A0 = 0.5 * Raez[c][f] * (Q[c] - qcez) / sig;
+          }
+          Z.srcS[c] += A0;
+          addto<MC>(Z.srcS, cez, -A0);
+        }
+      }
+  // the corner solves in nextC order: everything but the fluxes themselves
+#pragma unroll
+  for (int i = 0; i < MC; i++) {
+    Z.inv[i] = 1.0; Z.rz[i][0] = 0.0; Z.rz[i][1] = 0.0; Z.dz[i][0] = 0; Z.dz[i][1] = 0;
+    if (i < nCorner) {
+      const int c = Z.ci[i];
+      Z.inv[i] = 1.0 / (pick<MC>(sumArea, c) + pick<MC>(volSig, c));
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        double r = Raez[0][f];
+        int d = Z.cez[0][f];
+#pragma unroll
+        for (int k = 1; k < MC; k++) { r = c == k ? Raez[k][f] : r; d = c == k ? Z.cez[k][f] : d; }
+        Z.rz[i][f] = r;   // 0 unless the EZ face is outgoing
+        Z.dz[i][f] = d;
+      }
+    }
+  }
 }
 
-// SweepUCBrz.F90:103-243 for one (zone, group), second half: upstream fluxes, closure, corner solves, PsiM, exits.
-// Accumulation order into src is the reference's (corner-major, face-minor).
+// The half of the solve on the dependency chain: upstream fluxes and PsiM in, corner fluxes, PsiM, exiting fluxes out.
 template <int MC>
 __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int g, const ZoneStatic<MC> &Z) {
   const int G = P.G, nc = P.nc;
   const size_t slab = (size_t)(nc + P.nb) * G;
   double *psi1A = P.psi1 + (size_t)a * slab;
   double *psimL = P.psim + (size_t)P.level[a] * nc * G;
-  const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int nCorner = Z.nCorner, c0 = Z.c0;
-  const double sig = Z.sig;
-  double src[MC], psifp[MC][2], pm[MC];
+  double src[MC], u[MC][2], pm[MC];
 #pragma unroll
   for (int c = 0; c < MC; c++) {
-    src[c] = Z.srcInit[c];
+    src[c] = Z.srcS[c];
     pm[c] = 0.0;
-    psifp[c][0] = 0.0; psifp[c][1] = 0.0;
+    u[c][0] = 0.0; u[c][1] = 0.0;
     if (c < nCorner) {
       pm[c] = psimL[(size_t)(c0 + c) * G + g];
 #pragma unroll
       for (int f = 0; f < 2; f++)
-        if (Z.inMask & (1u << (2 * c + f))) psifp[c][f] = __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]);
+        if (Z.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]);
     }
   }
 #pragma unroll
-  for (int c = 0; c < MC; c++) {
-    if (c < nCorner) {
-      const double area = Z.area[c];
+  for (int c = 0; c < MC; c++)
 #pragma unroll
-      for (int f = 0; f < 2; f++) {
-        const bool inc = (Z.inMask >> (2 * c + f)) & 1u;
-        const double aez = Z.aez[c][f];
-        if (inc) src[c] -= Z.Rafp[c][f] * psifp[c][f];
-        if (aez > 0.0) {
-          const int cez = Z.cez[c][f];
-          const double qcez = pick<MC>(Z.Q, cez);
-          double sez;
-          if (inc) {
-            const double R = Z.Rez[c][f];
-            const double sigA = sig * area, sigA2 = sigA * sigA;
-            const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
-            const double gden = area * (4.0 * sigA * sigA2 + aez * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
-            sez = R * (area * gnum * (sig * psifp[c][f] - Z.Q[c]) + 0.5 * aez * gden * (Z.Q[c] - qcez)) / (gnum + gden * sig);
-          } else {
-            sez = 0.5 * Z.Raez[c][f] * (Z.Q[c] - qcez) / sig;
-          }
-          src[c] += sez;
-          addto<MC>(src, cez, -sez);
-        }
-      }
+    for (int f = 0; f < 2; f++) {
+      src[c] = fma(Z.k1[c][f], u[c][f], src[c]);
+      addto<MC>(src, Z.cez[c][f], Z.k2[c][f] * u[c][f]);
     }
-  }
 #pragma unroll
   for (int i = 0; i < MC; i++) {
     if (i < nCorner) {
-      const int c = nextC[c0 + i];
-      const double p = (pick<MC>(src, c) + pick<MC>(Z.areaFac, c) * pick<MC>(pm, c)) / (pick<MC>(Z.sumArea, c) + pick<MC>(Z.volSig, c));
+      const int c = Z.ci[i];
+      const double p = (pick<MC>(src, c) + pick<MC>(Z.areaFac, c) * pick<MC>(pm, c)) * Z.inv[i];
       put<MC>(src, c, p);   // src now holds the corner flux
-#pragma unroll
-      for (int f = 0; f < 2; f++) {
-        double raez = Z.Raez[0][f], aez = Z.aez[0][f];
-        int cez = Z.cez[0][f];
-#pragma unroll
-        for (int k = 1; k < MC; k++) { raez = c == k ? Z.Raez[k][f] : raez; aez = c == k ? Z.aez[k][f] : aez; cez = c == k ? Z.cez[k][f] : cez; }
-        if (aez > 0.0) addto<MC>(src, cez, raez * p);
-      }
+      addto<MC>(src, Z.dz[i][0], Z.rz[i][0] * p);
+      addto<MC>(src, Z.dz[i][1], Z.rz[i][1] * p);
     }
   }
   // half-angle intensity for the next angle of the level; exiting boundary fluxes; finishing direction
