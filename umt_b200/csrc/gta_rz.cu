@@ -48,51 +48,59 @@ struct GtaRZParams {
   double *tpsi, *pinc, *psim, *tinc;
 };
 
-// SweepGreyUCBrzKernelNew for one (zone, angle); loops fully unrolled and dynamic corner indices through select chains
-// (device_util.h) so that the zone stays in registers
+// SweepGreyUCBrzKernelNew for one (zone, angle), split like the multigroup r-z solve (sweeprz.cu): the static half (no dependence
+// on other zones of this sweep) reduces the closure to its linear form in the upstream fluxes u = tPsi(row) and in the half-angle
+// values, every division included; the half on the dependency chain is a few FMAs per face:
+//   src(c)  = srcS(c) + fa(c) tPsiM(c) + sum_f k1(c,f) u(c,f),   src(cez) += k2(c,f) u(c,f)
+//   pInc(c) =           fa(c) tInc(c)  + sum_f k1(c,f) u(c,f),   pInc(cez) += k2(c,f) u(c,f)
+//   psi(c_i) = src(c_i) inv_i, pinc(c_i) = pInc(c_i) inv_i, pushed into dz_i[f] with rz_i[f]     (corners c_i in nextC order)
+// k1 = -R_fp afp + R gtau sigA, k2 = -R gtau sigA (SweepGreyUCBrz.F90:262-297).  Loops are fully unrolled and dynamic corner
+// indices go through select chains (device_util.h), so the zone stays in registers.
 template <int MC>
-__device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
+struct GtaZoneRZ {
+  double srcS[MC], fa[MC], k1[MC][2], k2[MC][2], inv[MC], rz[MC][2];
+  int row[MC][2], cez[MC][2], dz[MC][2], ci[MC];
+  unsigned inMask, exitMask;
+  int nCorner, c0;
+};
+
+template <int MC>
+__device__ __forceinline__ void gta_static_rz(const GtaRZParams &P, int a, int zone0, GtaZoneRZ<MC> &Z) {
   const int nc = P.nc;
   const double om[2] = {P.omega[2 * a], P.omega[2 * a + 1]};
-  double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
-  double *pincA = P.pinc + (size_t)a * nc;
-  double *psimL = P.psim + (size_t)P.level[a] * nc, *tincL = P.tinc + (size_t)P.level[a] * nc;
   const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
   const double fac = P.fac[a];
-  double Q[MC], src[MC], Sigt[MC], denom[MC], pinc[MC], area[MC], pmOld[MC], tiOld[MC], coef[MC][2], aezv[MC][2];
-  int cezv[MC][2], rowv[MC][2];
-  unsigned exitMask = 0u;
+  Z.nCorner = nCorner; Z.c0 = c0; Z.inMask = 0u; Z.exitMask = 0u;
+  double Q[MC], Sigt[MC], denom[MC], area[MC], coef[MC][2], afpv[MC][2], aezv[MC][2], Rfp[MC][2], Rez[MC][2];
 #pragma unroll
   for (int c = 0; c < MC; c++) {
-    Q[c] = 0.0; src[c] = 0.0; Sigt[c] = 1.0; denom[c] = 1.0; pinc[c] = 0.0; area[c] = 0.0; pmOld[c] = 0.0; tiOld[c] = 0.0;
+    Q[c] = 0.0; Z.srcS[c] = 0.0; Sigt[c] = 1.0; denom[c] = 1.0; area[c] = 0.0; Z.fa[c] = 0.0; Z.ci[c] = c;
     if (c < nCorner) {
       const int cc = c0 + c;
       const double t = P.tsa[cc], vol = P.Volume[cc];
       area[c] = P.Area[cc];
-      pmOld[c] = psimL[cc]; tiOld[c] = tincL[cc];
       Q[c] = P.sigtInv[cc] * t;
-      src[c] = vol * t + fac * area[c] * pmOld[c];
+      Z.srcS[c] = vol * t;
       Sigt[c] = P.sigTotal[cc];
+      Z.fa[c] = fac * area[c];
       denom[c] = Sigt[c] * vol + fac * area[c];
-      pinc[c] = fac * area[c] * tiOld[c];
+      Z.ci[c] = nextC[cc];
     }
   }
-  // every load of the face loop up front and unconditional (rows of outgoing faces are read and ignored): inside the sign tests
-  // they would be issued one dependent round trip after the other
-  double afpv[MC][2], Rfp[MC][2], Rez[MC][2], psiup[MC][2];
 #pragma unroll
   for (int c = 0; c < MC; c++)
 #pragma unroll
     for (int f = 0; f < 2; f++) {
-      coef[c][f] = 0.0; aezv[c][f] = 0.0; cezv[c][f] = 0; rowv[c][f] = 0; afpv[c][f] = 0.0; Rfp[c][f] = 0.0; Rez[c][f] = 0.0;
+      coef[c][f] = 0.0; aezv[c][f] = 0.0; afpv[c][f] = 0.0; Rfp[c][f] = 0.0; Rez[c][f] = 0.0;
+      Z.k1[c][f] = 0.0; Z.k2[c][f] = 0.0; Z.cez[c][f] = 0; Z.row[c][f] = 0;
       if (c < nCorner) {
         const int cc = c0 + c;
         afpv[c][f] = dot2(om, P.Afp + ((size_t)cc * 2 + f) * 2);
         aezv[c][f] = dot2(om, P.Aez + ((size_t)cc * 2 + f) * 2);
-        rowv[c][f] = P.cFP[cc * 2 + f];
-        cezv[c][f] = P.cEZ[cc * 2 + f];
+        Z.row[c][f] = P.cFP[cc * 2 + f];
+        Z.cez[c][f] = P.cEZ[cc * 2 + f];
         Rfp[c][f] = P.RadiusFP[cc * 2 + f];
         Rez[c][f] = P.RadiusEZ[cc * 2 + f];
       }
@@ -100,64 +108,96 @@ __device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
 #pragma unroll
   for (int c = 0; c < MC; c++)
 #pragma unroll
-    for (int f = 0; f < 2; f++) psiup[c][f] = c < nCorner ? __ldcg(&tpsi[rowv[c][f]]) : 0.0;
-#pragma unroll
-  for (int c = 0; c < MC; c++) {
-    if (c < nCorner) {
-#pragma unroll
-      for (int f = 0; f < 2; f++) {
+    for (int f = 0; f < 2; f++)
+      if (c < nCorner) {
         const double afp = afpv[c][f], aez = aezv[c][f];
-        const int row = rowv[c][f];
-        double psifp = 0.0;
-        if (afp < 0.0) {
+        const bool inc = afp < 0.0;
+        if (inc) {
           const double R_afp = Rfp[c][f] * afp;
-          psifp = psiup[c][f];
+          Z.inMask |= 1u << (2 * c + f);
+          Z.k1[c][f] = -R_afp;
           denom[c] -= R_afp;
-          src[c] -= R_afp * psifp;
-          pinc[c] -= R_afp * psifp;
-        } else if (row >= nc) exitMask |= 1u << (2 * c + f);
+        } else if (Z.row[c][f] >= nc) Z.exitMask |= 1u << (2 * c + f);
         if (aez > 0.0) {
           const double R = Rez[c][f];
-          const int cez = cezv[c][f];
+          const int cez = Z.cez[c][f];
           coef[c][f] = R * aez;
           addto<MC>(denom, cez, R * aez);
           const double qcez = pick<MC>(Q, cez);
-          double sez;
-          if (afp < 0.0) {
+          double B0;
+          if (inc) {
             const double sigA = Sigt[c] * area[c], sigA2 = sigA * sigA;
             const double gnum = aez * aez * (FOURALPHA * sigA2 + aez * (4.0 * sigA + 3.0 * aez));
             const double gtau = gnum / (gnum + 4.0 * sigA2 * sigA2 + aez * sigA * (6.0 * sigA2 + 2.0 * aez * (2.0 * sigA + aez)));
-            sez = R * (gtau * sigA * (psifp - Q[c]) + 0.5 * aez * (1.0 - gtau) * (Q[c] - qcez));
-            const double gi = R * gtau * sigA * psifp;
-            pinc[c] += gi;
-            addto<MC>(pinc, cez, -gi);
+            const double B1 = R * gtau * sigA;
+            B0 = R * (0.5 * aez * (1.0 - gtau) * (Q[c] - qcez) - gtau * sigA * Q[c]);
+            Z.k1[c][f] += B1;
+            Z.k2[c][f] = -B1;
           } else {
-            sez = 0.5 * R * aez * (Q[c] - qcez);
+            B0 = 0.5 * R * aez * (Q[c] - qcez);
           }
-          src[c] += sez;
-          addto<MC>(src, cez, -sez);
+          Z.srcS[c] += B0;
+          addto<MC>(Z.srcS, cez, -B0);
         }
+      }
+#pragma unroll
+  for (int i = 0; i < MC; i++) {
+    Z.inv[i] = 1.0; Z.rz[i][0] = 0.0; Z.rz[i][1] = 0.0; Z.dz[i][0] = 0; Z.dz[i][1] = 0;
+    if (i < nCorner) {
+      const int c = Z.ci[i];
+      Z.inv[i] = 1.0 / pick<MC>(denom, c);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        double r = coef[0][f];
+        int d = Z.cez[0][f];
+#pragma unroll
+        for (int k = 1; k < MC; k++) { r = c == k ? coef[k][f] : r; d = c == k ? Z.cez[k][f] : d; }
+        Z.rz[i][f] = r;
+        Z.dz[i][f] = d;
       }
     }
   }
+}
+
+template <int MC>
+__device__ __forceinline__ void gta_solve_rz(const GtaRZParams &P, int a, const GtaZoneRZ<MC> &Z) {
+  const int nc = P.nc;
+  double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
+  double *pincA = P.pinc + (size_t)a * nc;
+  double *psimL = P.psim + (size_t)P.level[a] * nc, *tincL = P.tinc + (size_t)P.level[a] * nc;
+  const int nCorner = Z.nCorner, c0 = Z.c0;
+  double src[MC], pinc[MC], pmOld[MC], tiOld[MC], u[MC][2];
+#pragma unroll
+  for (int c = 0; c < MC; c++) {
+    pmOld[c] = 0.0; tiOld[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
+    if (c < nCorner) {
+      pmOld[c] = psimL[c0 + c]; tiOld[c] = tincL[c0 + c];
+#pragma unroll
+      for (int f = 0; f < 2; f++)
+        if (Z.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&tpsi[Z.row[c][f]]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MC; c++) { src[c] = fma(Z.fa[c], pmOld[c], Z.srcS[c]); pinc[c] = Z.fa[c] * tiOld[c]; }
+#pragma unroll
+  for (int c = 0; c < MC; c++)
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      const double t1 = Z.k1[c][f] * u[c][f], t2 = Z.k2[c][f] * u[c][f];
+      src[c] += t1; pinc[c] += t1;
+      addto<MC>(src, Z.cez[c][f], t2);
+      addto<MC>(pinc, Z.cez[c][f], t2);
+    }
 #pragma unroll
   for (int i = 0; i < MC; i++) {
     if (i < nCorner) {
-      const int c = nextC[c0 + i];
-      const double d = pick<MC>(denom, c);
-      const double p = pick<MC>(src, c) / d, pi = pick<MC>(pinc, c) / d;
+      const int c = Z.ci[i];
+      const double p = pick<MC>(src, c) * Z.inv[i], pi = pick<MC>(pinc, c) * Z.inv[i];
       put<MC>(src, c, p); put<MC>(pinc, c, pi);   // src now holds the corner flux
 #pragma unroll
-      for (int f = 0; f < 2; f++) {
-        double cf = coef[0][f], az = aezv[0][f];
-        int cez = cezv[0][f];
-#pragma unroll
-        for (int k = 1; k < MC; k++) { cf = c == k ? coef[k][f] : cf; az = c == k ? aezv[k][f] : az; cez = c == k ? cezv[k][f] : cez; }
-        if (az > 0.0) { addto<MC>(src, cez, cf * p); addto<MC>(pinc, cez, cf * pi); }
-      }
+      for (int f = 0; f < 2; f++) { addto<MC>(src, Z.dz[i][f], Z.rz[i][f] * p); addto<MC>(pinc, Z.dz[i][f], Z.rz[i][f] * pi); }
     }
   }
-  // corner fluxes, exiting boundary fluxes (:314-319), half-angle values for the next angle of the level (:120-130, :321-329)
   const bool starting = P.start[a] != 0;
   const double w1 = P.w1[a], w2 = P.w2[a];
 #pragma unroll
@@ -170,7 +210,7 @@ __device__ void gta_zone_rz(const GtaRZParams &P, int a, int zone0) {
       tincL[cc] = starting ? pinc[c] : w1 * pinc[c] - w2 * tiOld[c];
 #pragma unroll
       for (int f = 0; f < 2; f++)
-        if (exitMask & (1u << (2 * c + f))) tpsi[rowv[c][f]] = src[c];
+        if (Z.exitMask & (1u << (2 * c + f))) tpsi[Z.row[c][f]] = src[c];
     }
   }
 }
@@ -185,8 +225,8 @@ __global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) 
     if (it >= P.nItems) break;
     const WorkItem w = P.items[it];
     const int zi = w.zbeg + threadIdx.x;
-    int zone0 = 0;
-    if (zi < w.zend) zone0 = P.nextZ[(size_t)w.angle * P.nz + zi];
+    GtaZoneRZ<MC> Z;
+    if (zi < w.zend) gta_static_rz<MC>(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + zi], Z);
     if (threadIdx.x == blockDim.x - 1) {
       if (w.wait_idx >= 0)
         while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
@@ -194,7 +234,7 @@ __global__ void __launch_bounds__(GRZ_BLOCK) gta_sweep_rz_kernel(GtaRZParams P) 
         while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
     }
     __syncthreads();
-    if (zi < w.zend) gta_zone_rz<MC>(P, w.angle, zone0);
+    if (zi < w.zend) gta_solve_rz<MC>(P, w.angle, Z);
     __syncthreads();
     if (threadIdx.x == 0) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -217,12 +257,12 @@ __global__ void __launch_bounds__(256) gta_sweep_rz_chain_kernel(GtaRZParams P, 
     const int nh = nHyp[a];
     for (int p = 0; p < nh; p++) {
       const int zbeg = off[p], n = off[p + 1] - zbeg;
-      int zone0 = 0;
-      if ((int)threadIdx.x < n) zone0 = nextZ[zbeg + threadIdx.x];
+      GtaZoneRZ<MC> Z;
+      if ((int)threadIdx.x < n) gta_static_rz<MC>(P, a, nextZ[zbeg + threadIdx.x], Z);   // off the chain: before the barrier
       __syncthreads();
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (i != (int)threadIdx.x) zone0 = nextZ[zbeg + i];
-        gta_zone_rz<MC>(P, a, zone0);
+        if (i != (int)threadIdx.x) gta_static_rz<MC>(P, a, nextZ[zbeg + i], Z);
+        gta_solve_rz<MC>(P, a, Z);
       }
     }
   }
@@ -371,8 +411,8 @@ int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items) {
   }
   g.rz_maxAngLevel = maxAng;
   g.rz_threads = std::max(32, std::min(256, (maxPlane + 31) / 32 * 32));
-  g.rz_chain = true;
-  if (const char *e = getenv("UMT_GTA_RZ_KERNEL")) g.rz_chain = std::string(e) != "items";
+  g.rz_chain = false;   // measured at 38 k zones: item kernel 6.0 ms per grey sweep (static half overlaps the dependency wait), chain kernel 12.4 ms
+  if (const char *e = getenv("UMT_GTA_RZ_KERNEL")) g.rz_chain = std::string(e) == "chain";
   TRY(dalloc2(ctx, &g.d_levelAngles, la.size())); TRY(dalloc2(ctx, &g.d_planeOff, po.size())); TRY(dalloc2(ctx, &g.d_nHyp, nh.size()));
   UMT_CUDA(ctx, cudaMemcpy(g.d_levelAngles, la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice));
   UMT_CUDA(ctx, cudaMemcpy(g.d_planeOff, po.data(), sizeof(int) * po.size(), cudaMemcpyHostToDevice));
