@@ -8,7 +8,7 @@ SMI=$!
 timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 kill $SMI
 tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu "$@" > gpurun_out/${TAG}_launches.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu "$@" > gpurun_out/${TAG}_launches.log 2>&1
 grep -v "^==" gpurun_out/${TAG}_launches.csv | tail -30
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep3d -s 1 -c 1 -o gpurun_out/${TAG}_sweep3d -f python bench.py --dims 6 --steps 1 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_full.log
