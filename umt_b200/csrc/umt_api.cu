@@ -336,7 +336,18 @@ static int finalize_schedule(umt_ctx *ctx) {
   // the last few planes of every active angle stay L2-resident for their downstream zones.
   int K = NA;
   double stagger = 0.5;
-  if (ctx->use_plan) K = 4;   // measured at -d 20 G=128: K=4 41.2 ms, K=8 42.5 ms, K=2 52 ms (too few ready items per level)
+  if (ctx->use_plan) {
+    // measured at -d 20 G=128 (planes of ~750 zones): K=4 41.2 ms, K=8 42.5 ms, K=2 52 ms (too few ready items per level).
+    // Small meshes have small planes: keep about 2400 items (4x the engines of the GPU) per level, two batches being active
+    // at any time, so that the plane-to-plane latency of one angle hides behind the others.
+    double avgPlane = 0.0;
+    int nSwept = 0;
+    for (int a = 0; a < NA; a++) if (ctx->nHyp[a] > 0) { avgPlane += (double)nz / ctx->nHyp[a]; nSwept++; }
+    avgPlane = nSwept ? avgPlane / nSwept : 1.0;
+    K = 4;
+    while (K < NA && 2.0 * K * avgPlane / zpi < 2400.0) K *= 2;
+    K = std::min(K, NA);
+  }
   if (const char *e = getenv("UMT_ANGLE_BATCH")) K = std::max(1, atoi(e));
   if (const char *e = getenv("UMT_BATCH_STAGGER")) stagger = std::max(0.0, atof(e));
   const int delta = std::max(1, (int)(stagger * maxHyp));
