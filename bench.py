@@ -259,13 +259,11 @@ def main():
     h2d = h_sigt.numel() * 8 + h_stotal.numel() * 8
     d2h = h_phi.numel() * 8
     for _ in range(1):
-        ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau); ctx.sweep(False, args.flux_iters); ctx.download_phi(h_phi.numpy())
+        ctx.control_sweep(h_sigt.numpy(), h_stotal.numpy(), tau, h_phi.numpy(), False, args.flux_iters)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau)
-        ctx.sweep(False, args.flux_iters)
-        ctx.download_phi(h_phi.numpy())
+        ctx.control_sweep(h_sigt.numpy(), h_stotal.numpy(), tau, h_phi.numpy(), False, args.flux_iters)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     if rank == 0:
@@ -283,7 +281,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": total_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "what": "umt_upload_state(Sigt,STotal) from pinned host + umt_sweep + umt_download_phi to pinned host"},
+                    "ms_per_step": e2e_ms, "what": "umt_control_sweep: Sigt, STotal from pinned host -> whole ControlSweep -> PhiTotal to pinned host (phi reduction and its D2H overlapped)"},
             "gpu_launches": launches,
             "flux_passes_per_step": iters / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

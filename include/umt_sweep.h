@@ -124,6 +124,11 @@ int umt_init_radiation_field(umt_ctx *ctx);
 int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone);
 /* Device time of the kernels of the last umt_sweep, in ms: [0] sweep kernel(s),
    [1] psi->phi reduction, [2] exchange (pack/NCCL/unpack), [3] whole call. */
+/* One rt/ControlSweep.F90 call with the host arrays the Fortran caller owns: GSet%Sigt (ngr,nzones) and GSet%STotal
+   (ngr,ncornr) in (NULL: keep what is on the device), Rad%PhiTotal (ngr,ncornr) out; = umt_upload_state + umt_sweep +
+   umt_download_phi with the phi reduction and its device-to-host copy overlapped.  Pinned host buffers recommended. */
+int umt_control_sweep(umt_ctx *ctx, const double *Sigt, const double *STotal, double tau, int savePsi, int maxFluxIters,
+                      double fluxTol, int *itersDone, double *PhiTotal);
 int umt_last_sweep_times(umt_ctx *ctx, double *ms4);
 int umt_last_sweep_launches(umt_ctx *ctx, int *nLaunches);
 int umt_synchronize(umt_ctx *ctx);

@@ -80,3 +80,23 @@ def test_device_geometry_matches_oracle():
             scale = np.abs(ref[k]).max()
             assert np.abs(g[k] - ref[k]).max() <= 1e-13 * scale, k
         ctx.close()
+
+
+def test_control_sweep_with_host_buffers_equals_upload_sweep_download():
+    """umt_control_sweep (one ControlSweep with the caller's host arrays, chunked phi reduction overlapped with its download)
+    gives bit for bit what umt_upload_state + umt_sweep + umt_download_phi give."""
+    m = M.tiled_mesh((5, 5, 5))   # large enough for the chunked path (nc * G >= 2^22)
+    p = T.make_problem_3d(m, 1, 1, 192)
+    ctx = T.gpu_context_3d(p)
+    ctx.sweep(savePsi=False)
+    phi_a = ctx.download_phi()
+    ctx2 = T.gpu_context_3d(p)
+    phi_b = np.zeros_like(phi_a)
+    it = ctx2.control_sweep(p.Sigt, p.STotal, p.tau, phi_b)
+    assert it == 1 and np.array_equal(phi_a, phi_b)
+    phi_c = np.full_like(phi_a, -1.0)
+    ctx2.control_sweep(None, 2.0 * p.STotal, p.tau, phi_c)       # new source from the host, Sigt kept
+    ctx.upload_state(None, None, None, 2.0 * p.STotal, p.tau)
+    ctx.sweep(savePsi=False)
+    assert np.array_equal(ctx.download_phi(), phi_c)
+    ctx.close(); ctx2.close()

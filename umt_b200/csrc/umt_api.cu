@@ -635,6 +635,15 @@ __global__ void exit_copy_kernel(const double *psi, double *psi1, const int *eb,
   psi1[((size_t)ea[m] * rows + nc + eb[m]) * G + g] = psi[((size_t)ea[m] * rows + ec[m]) * G + g];
 }
 
+static int launch_phi_range(umt_ctx *ctx, const double *field, size_t off, size_t n) {   // corners*groups [off, off+n), off even
+  const size_t threads = (n + 1) / 2;
+  const int grid = (int)((threads + 255) / 256);
+  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field + off, ctx->d_weight, nullptr, ctx->d_phi + off, n, ctx->NA, (size_t)ctx->rows * ctx->G);
+  UMT_CUDA(ctx, cudaGetLastError());
+  ctx->last_launches += 1;
+  return UMT_OK;
+}
+
 static int launch_phi(umt_ctx *ctx, const double *field) {
   const size_t n = (size_t)ctx->nc * ctx->G;
   const size_t threads = (n + 1) / 2;
@@ -705,7 +714,29 @@ extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
 // the controller: rt/ControlSweep.F90 -> snac/SetSweep.F90 -> getPhiTotal
 // ---------------------------------------------------------------------------
 
+static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone, double *hostPhi);
+
 extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone) {
+  return sweep_impl(ctx, savePsi, maxFluxIters, fluxTol, itersDone, nullptr);
+}
+
+// One ControlSweep with host buffers (what the Fortran caller exchanges per call): GSet%Sigt (ngr,nzones) and GSet%STotal
+// (ngr,ncornr) in, Rad%PhiTotal (ngr,ncornr) out.  The phi reduction runs in chunks of corners and each chunk goes home on a
+// second stream as soon as it is reduced, so the device-to-host copy overlaps the reduction.  Host buffers should be pinned.
+extern "C" int umt_control_sweep(umt_ctx *ctx, const double *Sigt, const double *STotal, double tau, int savePsi, int maxFluxIters,
+                                 double fluxTol, int *itersDone, double *PhiTotal) {
+  if (!ctx || !PhiTotal) return UMT_ERR_ARG;
+  if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  NEED_DEVICE(ctx, "umt_control_sweep");
+  TRY(ensure_state(ctx));
+  const size_t G = ctx->G;
+  if (Sigt) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt, sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, ctx->stream));
+  if (STotal) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal, sizeof(double) * G * ctx->nc, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tau = tau;
+  return sweep_impl(ctx, savePsi, maxFluxIters, fluxTol, itersDone, PhiTotal);
+}
+
+static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *itersDone, double *hostPhi) {
   if (!ctx) return UMT_ERR_ARG;
   if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   NEED_DEVICE(ctx, "umt_sweep");
@@ -757,9 +788,25 @@ extern "C" int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double flu
   }
 
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-  TRY(launch_phi(ctx, ctx->d_psi1));
+  if (!hostPhi) {
+    TRY(launch_phi(ctx, ctx->d_psi1));
+  } else {
+    const size_t n = (size_t)ctx->nc * ctx->G;
+    const int nChunks = n >= (size_t)1 << 22 ? 8 : 1;
+    const size_t per = ((n + nChunks - 1) / nChunks + 1) / 2 * 2;   // even: the kernel works on pairs
+    for (int k = 0; k < nChunks; k++) {
+      const size_t o = (size_t)k * per;
+      if (o >= n) break;
+      const size_t m = std::min(per, n - o);
+      TRY(launch_phi_range(ctx, ctx->d_psi1, o, m));
+      UMT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+      UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev[7], 0));
+      UMT_CUDA(ctx, cudaMemcpyAsync(hostPhi + o, ctx->d_phi + o, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream2));
+    }
+  }
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
   UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+  if (hostPhi) UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
   cudaEventElapsedTime(&ms_phi, ctx->ev[5], ctx->ev[6]);
   cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
   if (savePsi) {

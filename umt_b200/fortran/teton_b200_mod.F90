@@ -101,6 +101,17 @@ module teton_b200_mod
          integer(C_INT)        :: itersDone
       end function
 
+!     one whole ControlSweep with the caller's host arrays (upload, SetSweep, getPhiTotal, download overlapped)
+      integer(C_INT) function umt_control_sweep(ctx, Sigt, STotal, tau, savePsi, maxFluxIters, fluxTol, itersDone, PhiTotal) &
+                              bind(C, name="umt_control_sweep")
+         import :: C_INT, C_PTR, C_DOUBLE
+         type(C_PTR),    value :: ctx
+         real(C_DOUBLE)        :: Sigt(*), STotal(*), PhiTotal(*)
+         real(C_DOUBLE), value :: tau, fluxTol
+         integer(C_INT), value :: savePsi, maxFluxIters
+         integer(C_INT)        :: itersDone
+      end function
+
       integer(C_INT) function umt_download_phi(ctx, PhiTotal) bind(C, name="umt_download_phi")
          import :: C_INT, C_PTR, C_DOUBLE
          type(C_PTR), value :: ctx

@@ -213,6 +213,15 @@ class SweepContext:
         self._ck(self.lib.umt_sweep(self.h, int(bool(savePsi)), int(maxFluxIters), C.c_double(fluxTol), C.byref(it)), "umt_sweep")
         return it.value
 
+    def control_sweep(self, Sigt, STotal, tau, PhiTotal, savePsi=False, maxFluxIters=1, fluxTol=1e-6):
+        """ControlSweep with host buffers: Sigt (nz, G), STotal (nc, G) in (None keeps the device copy), PhiTotal (nc, G) out (filled in place)"""
+        it = C.c_int(0)
+        assert PhiTotal.dtype == np.float64 and PhiTotal.flags.c_contiguous and PhiTotal.shape == (self.nc, self.G)
+        self._ck(self.lib.umt_control_sweep(self.h, None if Sigt is None else _dp(_f64(Sigt)), None if STotal is None else _dp(_f64(STotal)),
+                                            C.c_double(tau), int(bool(savePsi)), int(maxFluxIters), C.c_double(fluxTol), C.byref(it), _dp(PhiTotal)),
+                 "umt_control_sweep")
+        return it.value
+
     def last_times(self):
         t = np.zeros(4)
         self._ck(self.lib.umt_last_sweep_times(self.h, _dp(t)), "umt_last_sweep_times")
