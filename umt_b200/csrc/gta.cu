@@ -152,7 +152,7 @@ __device__ void gta_solve_zone(const GtaSweepParams &P, int a, int zone0) {
 // and at most 8 corners; other zones take gta_solve_zone on lane 0.
 struct GtaZoneStatic {   // everything that does not depend on other work items (loaded before the dependency wait)
   double afp, aez, vol, sigv, q, tsaVol;
-  int cez, row, zone0, nCorner, c0;
+  int cez, row, zone0, nCorner, c0, myNext;
   bool fast;
 };
 
@@ -164,8 +164,9 @@ __device__ __forceinline__ void gta_zone_static(const GtaSweepParams &P, int a, 
   Z.zone0 = zone0; Z.nCorner = nCorner; Z.c0 = c0;
   const bool threeFaces = lane >= nCorner || P.nCFaces[c0 + lane] == 3;
   Z.fast = nCorner <= MAXC && __all_sync(0xffffffffu, threeFaces);
-  Z.afp = 0.0; Z.aez = 0.0; Z.vol = 0.0; Z.sigv = 0.0; Z.q = 0.0; Z.tsaVol = 0.0; Z.cez = c < MAXC ? c : 0; Z.row = 0;
+  Z.afp = 0.0; Z.aez = 0.0; Z.vol = 0.0; Z.sigv = 0.0; Z.q = 0.0; Z.tsaVol = 0.0; Z.cez = c < MAXC ? c : 0; Z.row = 0; Z.myNext = 0;
   if (!Z.fast) return;
+  if (lane < nCorner) Z.myNext = P.nextC[(size_t)a * P.nc + c0 + lane];   // the corner order does not depend on other zones: off the chain
   if (c < nCorner) {
     const int cc = c0 + c;
     const double t = P.tsa[cc];
@@ -193,7 +194,7 @@ __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int
   const double afp = Z.afp, aez = Z.aez, sigv = Z.sigv, q = Z.q;
   const int cez = Z.cez;
   const double psifp = (valid && afp < 0.0) ? __ldcg(&tpsi[Z.row]) : 0.0;
-  int myNext = lane < nCorner ? P.nextC[(size_t)a * nc + c0 + lane] : 0;
+  const int myNext = Z.myNext;
   // the FP face "opposite" EZ face f is face (f+1) mod 3 of the same corner (SweepGreyUCBxyz.F90:263-270)
   const int lop = (lane & ~3) | (f == 2 ? 0 : f + 1);
   const double afpo = __shfl_sync(FULL, afp, lop), psio = __shfl_sync(FULL, psifp, lop);
@@ -255,7 +256,10 @@ __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int
 
 constexpr int GTA_WARPS = 8;   // warps per CTA = zones per work item
 
-__global__ void __launch_bounds__(GTA_WARPS * 32) gta_sweep_kernel(GtaSweepParams P) {
+#ifndef GTA_MINB
+#define GTA_MINB 4   // CTAs per SM the grey sweep is compiled for (register cap 65536 / (256 GTA_MINB))
+#endif
+__global__ void __launch_bounds__(GTA_WARPS * 32, GTA_MINB) gta_sweep_kernel(GtaSweepParams P) {
   __shared__ int s_item;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (;;) {
