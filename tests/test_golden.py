@@ -92,3 +92,51 @@ def test_gpu_reproduces_golden_cycle():
         assert np.allclose([ed["EnergyRadiation"], ed["TrMax"], ed["PowerEscape"]], row[:3], rtol=1e-10, atol=0)
     assert T.relerr(ctx.download_phi(), g["phi"]) <= 1e-12
     ctx.close()
+
+
+def test_oracle_reproduces_golden_gta_and_scheduler():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(G_DIR), "..", "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = _load("gta_solve_G4_seed7.npz")
+    c3, n3, e3 = mg.gta_solve(M.tiled_mesh((1, 1, 2)))
+    c2, n2, e2 = mg.gta_solve(M.tiled_mesh((2, 2, 0)))
+    assert n3 == int(g["iters_xyz"]) and n2 == int(g["iters_rz"])
+    assert np.abs(c3 - g["corr_xyz_tiled112"]).max() <= 1e-9 * np.abs(c3).max()      # Krylov: compiler-dependent rounding is amplified
+    assert np.abs(c2 - g["corr_rz_tiled22"]).max() <= 1e-9 * np.abs(c2).max()
+    q = O.gta_quad_rz()
+    assert np.array_equal(q["angDerivFac"], g["rz_angDerivFac"]) and np.array_equal(q["quadTauW1"], g["rz_tauW1"])
+    s = _load("scheduler_2domains_4sets_seed9.npz")
+    problems = [T.make_problem_3d(M.tiled_mesh((2, 2, 1), rank=r, size=2), 1, 2, 2, seed=200 + r) for r in range(2)]
+    rng = np.random.default_rng(9)
+    nf = [rng.standard_normal((len(T.shared_boundaries(p.mesh)), problems[0].NA)) for p in problems]
+    order, recv = T.oracle_sweep_scheduler(problems, 4, nf)
+    assert np.array_equal(np.array(order), s["order"]) and np.array_equal(np.array([r[0] for r in recv]), s["recv"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_gta():
+    import importlib.util
+    from umt_b200.teton import SweepContext
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(G_DIR), "..", "tools", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = _load("gta_solve_G4_seed7.npz")
+    for mesh, key, itk in ((M.tiled_mesh((1, 1, 2)), "corr_xyz_tiled112", "iters_xyz"), (M.tiled_mesh((2, 2, 0)), "corr_rz_tiled22", "iters_rz")):
+        G = 4
+        Siga, Sigs, Eta, Chi, Phi = mg.gta_inputs(mesh, G, 7)
+        ctx = SweepContext.from_mesh(mesh, G)
+        ctx.compute_geometry(mesh.px)
+        ctx.build_product_quadrature(1, 1, 1)
+        NA = len(O.quad_rz(1, 1)["weight"]) if mesh.ndim == 2 else 8
+        tau = PR.tau(1e-3)
+        ctx.upload_state(np.tile(Phi / (4 * np.pi if mesh.ndim == 3 else 2 * np.pi), (NA, 1, 1)), None, np.full((mesh.nzones, G), tau), np.zeros((mesh.ncornr, G)), tau)
+        ctx.init_phi_total()
+        ctx.gta_setup()
+        ctx.gta_compute_opacity(Siga, Sigs, Eta, Chi.copy())
+        ctx.collision_rate(Eta, Siga, Sigs, 0)
+        corr, n, err = ctx.gta_solve()
+        assert n == int(g[itk])
+        assert np.abs(corr - g[key]).max() <= 1e-8 * np.abs(g[key]).max()
+        ctx.close()

@@ -57,8 +57,51 @@ def case_cycle():
     np.savez_compressed(os.path.join(OUT, "cycle_tiled111_P2A2_G2.npz"), edits=np.array(rows), phi=r["phi"])
 
 
+def gta_inputs(mesh, G, seed):
+    rng = np.random.default_rng(seed)
+    nz, nc = mesh.nzones, mesh.ncornr
+    Siga, Sigs, Eta = 5 * rng.random((nz, G)), 20 * rng.random((nz, G)), 0.5 * rng.random(nc)
+    Chi = rng.random((nc, G))
+    Chi /= Chi.sum(1, keepdims=True)
+    Phi = rng.random((nc, G))
+    return Siga, Sigs, Eta, Chi, Phi
+
+
+def gta_solve(mesh, G=4, seed=7):
+    om = O.OMesh(mesh)
+    g = O.geometry(om)
+    rz = mesh.ndim == 2
+    q = O.gta_quad_rz() if rz else None
+    omega, w = (q["omega"], q["weight"]) if rz else O.gta_quad_xyz()
+    sched = O.schedule(om, g, omega, q["finish"] if rz else None)
+    Siga, Sigs, Eta, Chi, Phi = gta_inputs(mesh, G, seed)
+    op = O.gta_set_opacity(om, g, PR.tau(1e-3), Siga, Sigs, Eta, Chi)
+    gs = O.collision_rate(om, Eta, Siga, Sigs, Phi, np.zeros(mesh.ncornr), 0)
+    P = O.GtaProblem(om, g, sched, omega, w, op, gs, PR.wtiso(mesh.ndim), q=q)
+    corr, n, err = P.solve(Phi)
+    return corr, n, err
+
+
+def case_gta():
+    c3, n3, e3 = gta_solve(M.tiled_mesh((1, 1, 2)))
+    c2, n2, e2 = gta_solve(M.tiled_mesh((2, 2, 0)))
+    q = O.gta_quad_rz()
+    np.savez_compressed(os.path.join(OUT, "gta_solve_G4_seed7.npz"), corr_xyz_tiled112=c3, iters_xyz=n3, err_xyz=e3, corr_rz_tiled22=c2, iters_rz=n2,
+                        err_rz=e2, rz_angDerivFac=q["angDerivFac"], rz_tauW1=q["quadTauW1"])
+
+
+def case_scheduler():
+    N, nCommSets = 2, 4
+    problems = [T.make_problem_3d(M.tiled_mesh((2, 2, 1), rank=r, size=N), 1, 2, 2, seed=200 + r) for r in range(N)]
+    NA = problems[0].NA
+    rng = np.random.default_rng(9)
+    nf = [rng.standard_normal((len(T.shared_boundaries(p.mesh)), NA)) for p in problems]
+    order, recv = T.oracle_sweep_scheduler(problems, nCommSets, nf)
+    np.savez_compressed(os.path.join(OUT, "scheduler_2domains_4sets_seed9.npz"), order=np.array(order), recv=np.array([r[0] for r in recv]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for f in (case_xyz, case_rz, case_quadrature, case_cycle):
+    for f in (case_xyz, case_rz, case_quadrature, case_cycle, case_gta, case_scheduler):
         f()
     print(sorted(os.listdir(OUT)), sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)), "bytes")
