@@ -370,32 +370,27 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
 }
 
 // the same for any r-z angle set (the Sn set above, the GTA set in gta_rz.cu); angles with nHyp == 0 (finishing directions) get no items
-int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHypV, const std::vector<std::vector<int>> &zonesInPlaneV,
-                           const std::vector<std::vector<int>> &nextZV, const std::vector<unsigned char> &startV, int zpi,
+int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHyp, const std::vector<std::vector<int>> &zonesInPlane,
+                           const std::vector<std::vector<int>> &nextZ, const std::vector<unsigned char> &start, int zpi,
                            std::vector<WorkItem> &items, std::vector<int> &levelOut, int &nLevelsOut, int &maxHypOut) {
-  struct { const std::vector<int> &nHyp; const std::vector<std::vector<int>> &zonesInPlane, &nextZ; const std::vector<unsigned char> &h_start;
-           std::vector<int> h_level; int nLevels; } cx{nHypV, zonesInPlaneV, nextZV, startV, {}, 0};
-  auto *ctx = &cx;
   int maxHyp = 0;
-  for (int a = 0; a < NA; a++) maxHyp = std::max(maxHyp, ctx->nHyp[a]);
+  for (int a = 0; a < NA; a++) maxHyp = std::max(maxHyp, nHyp[a]);
   maxHypOut = maxHyp;
   // xi-levels: a level starts at a starting direction; finishing directions are not swept
   std::vector<int> level(NA, 0), prev(NA, -1);
   int lev = -1, last = -1;
   for (int a = 0; a < NA; a++) {
-    if (ctx->h_start[a] || lev < 0) { lev++; last = -1; }
+    if (start[a] || lev < 0) { lev++; last = -1; }
     level[a] = lev;
-    if (ctx->nHyp[a] == 0) continue;
+    if (nHyp[a] == 0) continue;
     prev[a] = last;
     last = a;
   }
-  ctx->h_level = level;
-  ctx->nLevels = lev + 1;
   std::vector<std::vector<int>> planeOf(NA), nItemsPlane(NA), planeStart(NA), tdone(NA), dep2(NA);
   struct Key { int t, a, p; };
   std::vector<Key> keys;
   for (int a = 0; a < NA; a++) {
-    const int nh = ctx->nHyp[a];
+    const int nh = nHyp[a];
     if (nh == 0) continue;
     planeOf[a].assign(nz, 0);
     planeStart[a].assign(nh + 1, 0);
@@ -403,17 +398,17 @@ int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHypV, const 
     tdone[a].assign(nh, 0);
     dep2[a].assign(nh, -1);
     for (int p = 0; p < nh; p++) {
-      const int n = ctx->zonesInPlane[a][p];
+      const int n = zonesInPlane[a][p];
       planeStart[a][p + 1] = planeStart[a][p] + n;
       nItemsPlane[a][p] = (n + zpi - 1) / zpi;
-      for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) planeOf[a][std::abs(ctx->nextZ[a][i]) - 1] = p;
+      for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) planeOf[a][std::abs(nextZ[a][i]) - 1] = p;
     }
     const int pa = prev[a];
     for (int p = 0; p < nh; p++) {
       int t = p > 0 ? tdone[a][p - 1] : 0;
       if (pa >= 0) {
         int q = 0;
-        for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) q = std::max(q, planeOf[pa][std::abs(ctx->nextZ[a][i]) - 1]);
+        for (int i = planeStart[a][p]; i < planeStart[a][p + 1]; i++) q = std::max(q, planeOf[pa][std::abs(nextZ[a][i]) - 1]);
         dep2[a][p] = q;
         t = std::max(t, tdone[pa][q]);
       }
@@ -425,7 +420,7 @@ int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHypV, const 
   items.clear();
   for (const Key &k : keys) {
     const int a = k.a, p = k.p;
-    const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
+    const int n = zonesInPlane[a][p], z0 = planeStart[a][p];
     for (int j = 0; j < nItemsPlane[a][p]; j++) {
       WorkItem w;
       w.angle = a;
@@ -439,8 +434,8 @@ int umt_build_items_rz_set(int nz, int NA, const std::vector<int> &nHypV, const 
       items.push_back(w);
     }
   }
-  levelOut = ctx->h_level;
-  nLevelsOut = ctx->nLevels;
+  levelOut = level;
+  nLevelsOut = lev + 1;
   return UMT_OK;
 }
 
