@@ -133,6 +133,35 @@ def cpu_sweep_rate(G, npolar, nazim, sample_dims, steps=1, warmup=0):
     return unknowns / dt, cores, dt, f"3-D tiled mesh -d {sample_dims[0]},{sample_dims[1]},{sample_dims[2]} -G {G} P{npolar} A{nazim} ({unknowns:.3e} unknowns per sweep), same problem data, one full SetSweep+getPhiTotal, oracle built {'-O3 -march=native -fopenmp' if fast else '-O2 -fopenmp -ffp-contract=off'}"
 
 
+def reference_cuda_rate(G, npolar, nazim, sample_dims):
+    """The reference's own GPU offload of this path -- `gpu_sweepucbxyz` (T/gpu/GPU_SweepUCBxyz.cu, compiled unmodified for sm_100a
+    by oracle/Makefile), called angle by angle with host arrays exactly as SetSweep_CUDA.F90 does (it uploads and downloads
+    everything on every call) -- timed on a bounded sample of the workload.  A reported baseline next to cpu_baseline."""
+    from oracle import oracle as O
+    from tests import common as T
+    if not O.ref_cuda_available():
+        return None
+    m = M.tiled_mesh(sample_dims)
+    p = T.make_problem_3d(m, npolar, nazim, G, driver_like=True)
+    nc, nb = m.ncornr, m.nbelem
+    Psi1 = np.zeros((nc + nb, G)); Phi = np.zeros((nc, G))
+
+    def one_pass():
+        Phi[:] = 0.0
+        for a in range(p.NA):
+            O.ref_cuda_sweep_xyz(p.om, p.geom, p.sched, a, p.omega, p.weight, p.tau, p.STotal, p.Sigt, p.Psi[a], Psi1, p.PsiB[a],
+                                 Phi, p.cyclePsi, False, stream_id=0)
+    one_pass()   # allocates the shim's static buffers, warms up
+    t0 = time.perf_counter()
+    one_pass()
+    dt = time.perf_counter() - t0
+    unknowns = nc * p.NA * G
+    return {"value": unknowns / dt, "unit": "unknowns/s", "kind": "reference (its CUDA sweep, unmodified, sm_100a build)",
+            "ms_per_sweep": dt * 1e3,
+            "sample": f"3-D tiled mesh -d {sample_dims[0]},{sample_dims[1]},{sample_dims[2]} -G {G} P{npolar} A{nazim} ({unknowns:.3e} unknowns), "
+                      f"{p.NA} gpu_sweepucbxyz calls with host arrays (one stream), wall clock"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -298,6 +327,18 @@ def main():
             cd = args.cpu_dims or 10
             v, cores, dt, sample = cpu_sweep_rate(G, args.polar, args.azimuthal, (cd, cd, cd), steps=3, warmup=0)
             line["cpu_baseline"] = {"value": v, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample + f", 3 sweeps of {dt:.1f} s"}
+            ctx.close()
+            try:   # in a child process: the reference shim exit()s on any CUDA error and prints its allocations to stdout
+                import subprocess
+                out = subprocess.run([sys.executable, "-c", "import json, bench; print('REFCUDA ' + json.dumps(bench.reference_cuda_rate("
+                                      f"{G}, {args.polar}, {args.azimuthal}, ({cd}, {cd}, {cd}))))"],
+                                     cwd=ROOT, capture_output=True, text=True, timeout=600)
+                got = [l for l in out.stdout.splitlines() if l.startswith("REFCUDA ")]
+                rc = json.loads(got[-1][8:]) if got else {"unavailable": f"child exited {out.returncode}: {out.stderr[-200:]}"}
+                if rc:
+                    line["reference_cuda"] = rc
+            except Exception as e:   # a reported extra, never allowed to cost the bench line
+                line["reference_cuda"] = {"unavailable": repr(e)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

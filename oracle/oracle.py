@@ -367,3 +367,54 @@ def add_grey_corrections(GreyCorrection, Chi, PhiTotal):
     nc, ngr = PhiTotal.shape
     lib().orc_add_grey_corrections(ngr, nc, _dp(GreyCorrection), _dp(Chi), _dp(PhiTotal))
     return PhiTotal
+
+
+# ---------------------------------------------------------------------------
+# The reference's own CUDA sweep (gpu/GPU_SweepUCBxyz.cu, compiled unmodified into _ref/libgpu_sweepucbxyz_ref.so by the
+# Makefile).  Needs a GPU, so only the -m gpu tests and bench.py's reference_cuda leg call it.
+_REFCUDA = None
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libgpu_sweepucbxyz_ref.so"))
+
+
+def ref_cuda_lib():
+    global _REFCUDA
+    if _REFCUDA is None:
+        _REFCUDA = C.CDLL(os.path.join(_HERE, "_ref", "libgpu_sweepucbxyz_ref.so"))
+        _REFCUDA.gpu_sweepucbxyz.restype = None
+        _REFCUDA.gpu_streamsynchronize.restype = None
+    return _REFCUDA
+
+
+def ref_cuda_sweep_xyz(om, geom, sched, a, omega, weight, tau, STotal, Sigt, PsiA, Psi1, PsiBA, Phi, cyclePsi, savePsi,
+                       stream_id=0, sync=True):
+    """One call of the reference's `gpu_sweepucbxyz` (GPU_SweepUCBxyz.cu:532-572, argument order of the Fortran interface
+    SweepUCBxyzToGPU.F90:30-91) for angle index a (0-based): every argument by reference, host arrays in Teton's layout.
+    Like the Fortran caller (SetSweep_CUDA.F90) the whole cycleList/cyclePsi are passed with this angle's offset and count;
+    the shim runs initFromCycleList, Q = STotal + tau*Psi, the sweep, Phi += quadwt*Psi1 and updateCycleList on the device
+    and copies PsiB, Phi, Psi1, cyclePsi (and Psi when savePsi) back.  No reflecting boundaries (nBdyElem = 0).
+    The static device buffers of a stream id are sized by its first call: use a new stream_id (< 80) for a new problem size."""
+    m = om.m
+    G = STotal.shape[-1]
+    assert m.ndim == 3 and m.maxcf == 3, "the reference kernel indexes omega.A with ndim where maxcf is meant (:327, :360)"
+    assert G % 4 == 0, "GROUPS_IN_BLOCK = 4 and no group bound check in the reference kernel (:207)"
+    assert (m.ncornr * G) % 2 == 0
+    for arr in (STotal, Sigt, PsiA, Psi1, PsiBA, Phi, cyclePsi):
+        assert arr.flags["C_CONTIGUOUS"] and arr.dtype == np.float64
+    i = lambda v: C.byref(C.c_int(int(v)))
+    d = lambda v: C.byref(C.c_double(float(v)))
+    nhp = int(sched["nHyperPlanes"][a])
+    om_a = np.ascontiguousarray(omega[a], dtype=np.float64)
+    keep = om.keep
+    L = ref_cuda_lib()
+    L.gpu_sweepucbxyz(
+        i(a + 1), i(nhp), _ip(sched["zonesInPlane"][a]), _ip(sched["nextZ"][a]), _ip(sched["nextC"][a]),
+        _dp(STotal), d(tau), _dp(PsiA), i(G), _dp(geom["Volume"]), _dp(Sigt), _ip(keep["nCFaces"]),
+        i(m.ndim), i(m.maxcf), i(m.ncornr), _dp(geom["A_fp"]), _dp(om_a), _ip(keep["cFP"]), _dp(Psi1), i(m.nbelem),
+        _dp(geom["A_ez"]), _ip(keep["cEZ"]), i(omega.shape[0]), d(weight[a]), _dp(Phi), _dp(PsiBA), i(m.maxCorner),
+        i(0), i(stream_id), i(1), i(1 if savePsi else 0), i(sched["numCycles"][a]), i(sched["cycleOffSet"][a]),
+        _dp(cyclePsi), _ip(sched["cycleList"]), i(0), i(0), _dp(PsiBA), i(0), _ip(keep["numCorner"]), _ip(keep["cOffSet"]))
+    if sync:
+        L.gpu_streamsynchronize(i(stream_id))
