@@ -389,13 +389,14 @@ def ref_cuda_lib():
 
 
 def ref_cuda_sweep_xyz(om, geom, sched, a, omega, weight, tau, STotal, Sigt, PsiA, Psi1, PsiBA, Phi, cyclePsi, savePsi,
-                       stream_id=0, sync=True):
+                       stream_id=0, sync=True, lib=None):
     """One call of the reference's `gpu_sweepucbxyz` (GPU_SweepUCBxyz.cu:532-572, argument order of the Fortran interface
     SweepUCBxyzToGPU.F90:30-91) for angle index a (0-based): every argument by reference, host arrays in Teton's layout.
     Like the Fortran caller (SetSweep_CUDA.F90) the whole cycleList/cyclePsi are passed with this angle's offset and count;
     the shim runs initFromCycleList, Q = STotal + tau*Psi, the sweep, Phi += quadwt*Psi1 and updateCycleList on the device
     and copies PsiB, Phi, Psi1, cyclePsi (and Psi when savePsi) back.  No reflecting boundaries (nBdyElem = 0).
-    The static device buffers of a stream id are sized by its first call: use a new stream_id (< 80) for a new problem size."""
+    The static device buffers of a stream id are sized by its first call: use a new stream_id (< 80) for a new problem size.
+    `lib`: another library exporting the same three symbols (the product's back-compat seam, include/teton_gpu_compat.h)."""
     m = om.m
     G = STotal.shape[-1]
     assert m.ndim == 3 and m.maxcf == 3, "the reference kernel indexes omega.A with ndim where maxcf is meant (:327, :360)"
@@ -408,7 +409,9 @@ def ref_cuda_sweep_xyz(om, geom, sched, a, omega, weight, tau, STotal, Sigt, Psi
     nhp = int(sched["nHyperPlanes"][a])
     om_a = np.ascontiguousarray(omega[a], dtype=np.float64)
     keep = om.keep
-    L = ref_cuda_lib()
+    L = lib if lib is not None else ref_cuda_lib()
+    L.gpu_sweepucbxyz.restype = None
+    L.gpu_streamsynchronize.restype = None
     L.gpu_sweepucbxyz(
         i(a + 1), i(nhp), _ip(sched["zonesInPlane"][a]), _ip(sched["nextZ"][a]), _ip(sched["nextC"][a]),
         _dp(STotal), d(tau), _dp(PsiA), i(G), _dp(geom["Volume"]), _dp(Sigt), _ip(keep["nCFaces"]),

@@ -32,9 +32,9 @@ def _need_ref():
                                     "/root/reference and nvcc exist (build() does); the file travels with the snapshot")
 
 
-def _reference_pass(p, savePsi, sid):
-    """One flux pass angle by angle through the reference's CUDA shim; mutates p.Psi (if savePsi), p.PsiB, p.cyclePsi the way
-    SetSweep_CUDA.F90 does and returns (PhiTotal, Psi1 of every angle)."""
+def _reference_pass(p, savePsi, sid, lib=None):
+    """One flux pass angle by angle through the reference's CUDA shim (or `lib`'s symbol of the same name); mutates p.Psi
+    (if savePsi), p.PsiB, p.cyclePsi the way SetSweep_CUDA.F90 does and returns (PhiTotal, Psi1 of every angle)."""
     m = p.mesh
     nc, nb, G = m.ncornr, m.nbelem, p.G
     phi_total = np.zeros((nc, G))
@@ -43,7 +43,7 @@ def _reference_pass(p, savePsi, sid):
         Psi1 = np.zeros((nc + nb, G))
         Phi = np.zeros((nc, G))
         O.ref_cuda_sweep_xyz(p.om, p.geom, p.sched, a, p.omega, p.weight, p.tau, p.STotal, p.Sigt, p.Psi[a], Psi1, p.PsiB[a],
-                             Phi, p.cyclePsi, savePsi, stream_id=sid)
+                             Phi, p.cyclePsi, savePsi, stream_id=sid, lib=lib)
         phi_total += Phi
         psi1_all[a] = Psi1[:nc]
     return phi_total, psi1_all
@@ -144,3 +144,82 @@ def test_strongly_warped_mesh_direct_solve_branch():
     previous content of Psi1: compared angle by angle with identical Psi1 input (oracle against reference only)"""
     p = _three_way(M.box_mesh((7, 6, 5), warp=0.9, seed=2), 2, 2, 4, passes=(False, True), library=False)
     assert (p.sched["nextZ"] < 0).sum() > 0
+
+
+# ---------------------------------------------------------------------------
+# the product's back-compat seam: libumtsweep.so exports gpu_sweepucbxyz with the reference's signature
+# (include/teton_gpu_compat.h), so the same caller drives both libraries
+# ---------------------------------------------------------------------------
+def _compat_vs_reference(mesh, P, A, G, passes, driver_like=False):
+    _need_ref()
+    from umt_b200 import teton
+    lib = teton.load_library()
+    p_ref = T.make_problem_3d(mesh, P, A, G, driver_like=driver_like)
+    if p_ref.sched["totalCycles"] > 0:
+        _seed_cycles(p_ref)
+    p_lib = _clone_state(p_ref)
+    sid_ref, sid_lib = _stream_id(), _stream_id()
+    for save in passes:
+        phi_ref, psi1_ref = _reference_pass(p_ref, save, sid_ref)
+        phi_lib, psi1_lib = _reference_pass(p_lib, save, sid_lib, lib=lib)
+        assert T.relerr(phi_lib, phi_ref) <= TOL
+        assert T.mixed_err(psi1_lib, psi1_ref, TOL) <= 1.0
+        assert T.mixed_err(p_lib.PsiB, p_ref.PsiB, TOL) <= 1.0
+        assert T.mixed_err(p_lib.cyclePsi, p_ref.cyclePsi, TOL) <= 1.0
+        assert T.mixed_err(p_lib.Psi, p_ref.Psi, TOL) <= 1.0
+    return p_ref
+
+
+def test_compat_symbol_tiled_mesh():
+    _compat_vs_reference(M.tiled_mesh((2, 2, 2)), 2, 2, 16, passes=(False, True))
+
+
+def test_compat_symbol_driver_problem():
+    _compat_vs_reference(M.tiled_mesh((2, 2, 3)), 2, 2, 4, passes=(False, False, True), driver_like=True)
+
+
+def test_compat_symbol_cycle_list_and_direct_solve_zones():
+    p = _compat_vs_reference(M.box_mesh((4, 4, 4), warp=0.35, seed=3), 2, 2, 4, passes=(False, True))
+    assert p.sched["totalCycles"] > 0
+    p = _compat_vs_reference(M.box_mesh((7, 6, 5), warp=0.9, seed=2), 2, 2, 4, passes=(False, True))
+    assert (p.sched["nextZ"] < 0).sum() > 0
+
+
+def test_compat_symbol_reflecting_boundary_rows():
+    """the one-reflecting-boundary arguments (b0, nBdyElem, PsiBMref): both shims overwrite the incident rows
+    [b0, b0+nBdyElem) of PsiB with the mirror angle's rows before the sweep (GPU_SweepUCBxyz.cu:796-807)"""
+    _need_ref()
+    import ctypes as C
+    from umt_b200 import teton
+    m = M.box_mesh((3, 3, 3))
+    p = T.make_problem_3d(m, 1, 1, 8)
+    nc, nb, G = m.ncornr, m.nbelem, p.G
+    # first boundary of the mesh (b0 = 0): for b0 > 0 the reference offsets its copy by b0 doubles instead of b0 rows
+    # (`d_PsiB + *b0`, `PsiBMref + *b0`, :802-803), which this library does not imitate
+    b0, n = 0, m.boundaries[0].n_elem
+    out = []
+    for lib in (None, teton.load_library()):
+        L = lib if lib is not None else O.ref_cuda_lib()
+        a, mref = 0, p.NA - 1
+        Psi1 = np.zeros((nc + nb, G)); Phi = np.zeros((nc, G))
+        PsiB = p.PsiB[a].copy(); PsiBM = p.PsiB[mref].copy(); Psi = p.Psi[a].copy(); cyc = p.cyclePsi.copy()
+        i = lambda v: C.byref(C.c_int(int(v)))
+        d = lambda v: C.byref(C.c_double(float(v)))
+        s, k = p.sched, p.om.keep
+        om_a = np.ascontiguousarray(p.omega[a])
+        sid = _stream_id()
+        L.gpu_sweepucbxyz.restype = None
+        L.gpu_sweepucbxyz(
+            i(a + 1), i(s["nHyperPlanes"][a]), O._ip(s["zonesInPlane"][a]), O._ip(s["nextZ"][a]), O._ip(s["nextC"][a]),
+            O._dp(p.STotal), d(p.tau), O._dp(Psi), i(G), O._dp(p.geom["Volume"]), O._dp(p.Sigt), O._ip(k["nCFaces"]),
+            i(3), i(3), i(nc), O._dp(p.geom["A_fp"]), O._dp(om_a), O._ip(k["cFP"]), O._dp(Psi1), i(nb),
+            O._dp(p.geom["A_ez"]), O._ip(k["cEZ"]), i(p.NA), d(p.weight[a]), O._dp(Phi), O._dp(PsiB), i(m.maxCorner),
+            i(0), i(sid), i(1), i(0), i(0), i(0), O._dp(cyc), O._ip(s["cycleList"]), i(b0), i(n), O._dp(PsiBM), i(mref + 1),
+            O._ip(k["numCorner"]), O._ip(k["cOffSet"]))
+        L.gpu_streamsynchronize.restype = None
+        L.gpu_streamsynchronize(i(sid))
+        out.append((Psi1[:nc].copy(), PsiB, Phi))
+    (psi1_r, psib_r, phi_r), (psi1_l, psib_l, phi_l) = out
+    assert T.relerr(phi_l, phi_r) <= TOL
+    assert T.mixed_err(psi1_l, psi1_r, TOL) <= 1.0
+    assert T.mixed_err(psib_l, psib_r, TOL) <= 1.0
