@@ -8,12 +8,19 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product never does.
  *
- * PARITY STATUS: "parity unpinned" against a real reference run — the reference
- * ships no golden vectors, known-answer tests or fixtures for this path
- *  and cannot be compiled here.  The restatement is
- * pinned by (a) following the cited Fortran line by line, (b) the analytic
- * invariants of SURVEY.md section 4 (tests/test_oracle_invariants.py) and (c) the
- * committed fixtures in tests/golden/ that freeze its own output.
+ * PARITY STATUS.  Pinned to real reference code: orc_sweep_xyz (SweepUCBxyz, source term,
+ * Phi accumulation, exiting PsiB, cycle lists, the direct-solve branch of zones with an
+ * intra-zone cycle) is checked on the GPU box against the reference's OWN implementation of
+ * the same routine, gpu/GPU_SweepUCBxyz.cu, compiled unmodified by oracle/Makefile into
+ * oracle/_ref/libgpu_sweepucbxyz_ref.so (tests/test_gpu_reference_cuda.py, 1e-12); the
+ * Planck-group integrals are checked against misc/NormalizedBlackBody.cc compiled the same
+ * way (oracle/_ref/libnbb_ref.so).  "parity unpinned" for everything else (quadrature,
+ * geometry, snnext schedules, the r-z sweep, exchange, GTA): the Fortran reference cannot be
+ * compiled here and ships no golden vectors, known-answer tests or fixtures for this path
+ * (SURVEY.md section 4, section 8c); those parts are pinned by (a) following the cited
+ * Fortran line by line, (b) the analytic invariants of SURVEY.md section 4
+ * (tests/test_oracle_invariants.py) and (c) the committed fixtures in tests/golden/ that
+ * freeze the restatement's own output.
  *
  * Conventions: every integer id stored in an array is 1-based exactly as
  * Teton's Fortran holds it; arrays are the Fortran column-major memory image
