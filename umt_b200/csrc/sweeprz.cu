@@ -29,6 +29,9 @@ constexpr int MAXC2 = 8;   // corners per zone (quads: 4; general polygons up to
 constexpr int RZ_BLOCK = 64;   // threads per CTA = (zone, group) pairs per work item: small items keep the per-plane latency low
                                // (measured on the 40x40-tile r-z mesh, G = 64: 64 pairs 24.5 ms, 128 pairs 36 ms)
 constexpr double FOURALPHA = 1.82;   // SweepUCBrz.F90:88
+#ifndef RZ_MIN_CTAS
+#define RZ_MIN_CTAS 1
+#endif
 
 struct SweepRZParams {
   int nc, nb, nz, G, NA, nItems;
@@ -49,7 +52,24 @@ struct SweepRZParams {
   const int *levelAngles;   // (nLevels, maxAngLevel) swept angles of each level in order, -1 padded
   const int *planeOff;      // (NA, hypStride) first zone of each plane in nextZ(:,a); planeOff[a][nHyp[a]] = nz
   const int *nHyp;          // (NA)
+  // dataflow kernel
+  double *psimA;            // (NA, nc, G) PsiM as written by angle a
+  const int *prevAngle;     // (NA) previous swept angle of the level, -1: none (starting direction)
 };
+
+// Dataflow variant: a quiet NaN with a payload no arithmetic produces marks "not computed yet".  The corner rows of Psi1 and the
+// per-angle PsiM slabs are filled with it before the launch; a consumer polls the values it needs until they are real, so the
+// data are their own completion flags: no counters, no fences (every 8-byte value is validated by itself), no barriers.
+constexpr unsigned long long RZ_SENTINEL = 0xFFFFDEADFFFFDEADull;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
@@ -183,24 +203,55 @@ __device__ __forceinline__ void zone_static_rz(const SweepRZParams &P, int a, in
 }
 
 // The half of the solve on the dependency chain: upstream fluxes and PsiM in, corner fluxes, PsiM, exiting fluxes out.
-template <int MC>
+template <int MC, bool FLOW = false>
 __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int g, const ZoneStatic<MC> &Z) {
   const int G = P.G, nc = P.nc;
   const size_t slab = (size_t)(nc + P.nb) * G;
   double *psi1A = P.psi1 + (size_t)a * slab;
-  double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+  double *psimL = FLOW ? P.psimA + (size_t)a * nc * G : P.psim + (size_t)P.level[a] * nc * G;
   const int nCorner = Z.nCorner, c0 = Z.c0;
   double src[MC], u[MC][2], pm[MC];
+  if (FLOW) {
+    // poll the upstream fluxes (rows >= nc are boundary values: inputs, never marked) and the previous angle's PsiM
+    const int pa = P.prevAngle[a];
+    const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc * G;
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int c = 0; c < MC; c++) {
+        pm[c] = 0.0;
+        u[c][0] = 0.0; u[c][1] = 0.0;
+        if (c < nCorner) {
+          if (pa >= 0) {
+            const unsigned long long v = ld_relaxed_u64(&psimP[(size_t)(c0 + c) * G + g]);
+            ok = ok && v != RZ_SENTINEL;
+            pm[c] = __longlong_as_double((long long)v);
+          }
+#pragma unroll
+          for (int f = 0; f < 2; f++)
+            if (Z.inMask & (1u << (2 * c + f))) {
+              const unsigned long long v = ld_relaxed_u64(&psi1A[(size_t)Z.row[c][f] * G + g]);
+              ok = ok && v != RZ_SENTINEL;
+              u[c][f] = __longlong_as_double((long long)v);
+            }
+        }
+      }
+      if (!ok) __nanosleep(40);
+    } while (!ok);
+  }
 #pragma unroll
   for (int c = 0; c < MC; c++) {
     src[c] = Z.srcS[c];
-    pm[c] = 0.0;
-    u[c][0] = 0.0; u[c][1] = 0.0;
-    if (c < nCorner) {
-      pm[c] = psimL[(size_t)(c0 + c) * G + g];
+    if (!FLOW) {
+      pm[c] = 0.0;
+      u[c][0] = 0.0; u[c][1] = 0.0;
+      if (c < nCorner) {
+        pm[c] = psimL[(size_t)(c0 + c) * G + g];
 #pragma unroll
-      for (int f = 0; f < 2; f++)
-        if (Z.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]);
+        for (int f = 0; f < 2; f++)
+          if (Z.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)Z.row[c][f] * G + g]);
+      }
     }
   }
 #pragma unroll
@@ -231,8 +282,8 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
       const size_t r = (size_t)cc * G + g;
       const double p = src[c];
       const double pmn = starting ? p : w1 * p - w2 * pm[c];
-      psimL[r] = pmn;
-      psi1A[r] = p;
+      if (FLOW) { st_relaxed_f64(&psimL[r], pmn); st_relaxed_f64(&psi1A[r], p); }
+      else { psimL[r] = pmn; psi1A[r] = p; }
       if (fin) psi1N[r] = pmn;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
 #pragma unroll
       for (int f = 0; f < 2; f++) {
@@ -248,7 +299,7 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
 
 // One (zone, group) pair per thread (items hold at most blockDim pairs): the static half runs before the dependency wait.
 template <int MC>
-__global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
+__global__ void __launch_bounds__(RZ_BLOCK, RZ_MIN_CTAS) sweeprz_kernel(SweepRZParams P) {
   __shared__ int s_item;
   const int G = P.G;
   for (;;) {
@@ -283,6 +334,243 @@ __global__ void __launch_bounds__(RZ_BLOCK) sweeprz_kernel(SweepRZParams P) {
       asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Record kernel (quads, G <= 64).  Everything of a zone solve that does not depend on the group -- omega.A products, radii, the
+// group-independent part of sumArea, connectivity, the solve order -- is the same for the G threads of a zone and for every
+// sweep until the mesh or the schedule changes.  rz_rec_build_kernel computes it once per (angle, zone) into a 384-byte record
+// in sweep order; the sweep's CTA copies the records of its item into shared memory and its threads keep only the
+// group-dependent values in registers (Q, the closure coefficients A1, the reciprocals), indexing the rest in shared memory
+// with the dynamic corner numbers directly.  Against sweeprz_kernel: a third of the instructions, two dependent levels of global
+// loads fewer ahead of the solve, and few enough registers for twice the resident warps (the sweep is bound by the latency of
+// the pair solves times the resident warps, not by the plane-to-plane chain: 4x the zones take 3.9x the time).
+struct alignas(16) RZRec {
+  double vol[4], area[4], areaFac[4], sumArea[4];   // by corner; sumArea: angDerivFac*Area - sum R.afp (incident) + sum R.aez (incoming EZ)
+  double k1b[4][2], az[4][2], rez[4][2];            // -R_fp afp of incident faces (else 0); omega.A_ez where > 0 (else 0); RadiusEZ
+  int row[4][2];                                    // Psi1 row behind the FP face (>= nc: boundary element)
+  int c0, zone, nCorner;
+  unsigned inMask, exitMask;
+  unsigned char cez[4][2], ci[4];                   // corner across the EZ face; corners in solve order (nextC)
+};
+static_assert(sizeof(RZRec) == 384, "RZRec layout");
+#ifndef RZ_REC_MIN_CTAS
+#define RZ_REC_MIN_CTAS 10
+#endif
+
+__global__ void rz_rec_build_kernel(SweepRZParams P, RZRec *recs) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)P.NA * P.nz) return;
+  const int a = (int)(idx / P.nz);
+  if (P.nHyp[a] == 0) return;
+  const int zone0 = P.nextZ[idx], zone = (zone0 < 0 ? -zone0 : zone0) - 1;
+  const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone], nc = P.nc;
+  const double om0 = P.omega[2 * a], om1 = P.omega[2 * a + 1], fac = P.angDerivFac[a];
+  const unsigned char *nextC = P.nextC + (size_t)a * nc;
+  RZRec R;
+  R.c0 = c0; R.zone = zone; R.nCorner = nCorner; R.inMask = 0u; R.exitMask = 0u;
+  for (int c = 0; c < 4; c++) {
+    R.vol[c] = 0.0; R.area[c] = 0.0; R.areaFac[c] = 0.0; R.sumArea[c] = 1.0; R.ci[c] = (unsigned char)c;
+    for (int f = 0; f < 2; f++) { R.k1b[c][f] = 0.0; R.az[c][f] = 0.0; R.rez[c][f] = 0.0; R.row[c][f] = 0; R.cez[c][f] = 0; }
+    if (c < nCorner) {
+      const double ar = P.Area[c0 + c];
+      R.vol[c] = P.Volume[c0 + c]; R.area[c] = ar; R.areaFac[c] = ar * fac; R.sumArea[c] = fac * ar; R.ci[c] = nextC[c0 + c];
+    }
+  }
+  for (int c = 0; c < nCorner; c++)
+    for (int f = 0; f < 2; f++) {
+      const int cc = c0 + c;
+      const double *Af = P.Afp + ((size_t)cc * 2 + f) * 2, *Ae = P.Aez + ((size_t)cc * 2 + f) * 2;
+      const double afp = __dadd_rn(__dmul_rn(om0, Af[0]), __dmul_rn(om1, Af[1]));
+      const double az = __dadd_rn(__dmul_rn(om0, Ae[0]), __dmul_rn(om1, Ae[1]));
+      const int row = P.cFP[cc * 2 + f], cez = P.cEZ[cc * 2 + f];
+      R.row[c][f] = row; R.cez[c][f] = (unsigned char)cez; R.rez[c][f] = P.RadiusEZ[cc * 2 + f];
+      if (afp < 0.0) {
+        const double Rafp = __dmul_rn(P.RadiusFP[cc * 2 + f], afp);
+        R.inMask |= 1u << (2 * c + f);
+        R.k1b[c][f] = -Rafp;
+        R.sumArea[c] = __dadd_rn(R.sumArea[c], -Rafp);
+      } else if (afp > 0.0 && row >= nc) R.exitMask |= 1u << (2 * c + f);
+      if (az > 0.0) {
+        R.az[c][f] = az;
+        R.sumArea[cez] = __dadd_rn(R.sumArea[cez], __dmul_rn(R.rez[c][f], az));
+      }
+    }
+  recs[idx] = R;
+}
+
+__global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(SweepRZParams P, const RZRec *recs) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  RZRec *s_rec = reinterpret_cast<RZRec *>(s_raw);
+  __shared__ int s_item;
+  const int G = P.G, nc = P.nc;
+  const size_t slab = (size_t)(nc + P.nb) * G;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= P.nItems) break;
+    const WorkItem w = P.items[it];
+    const int a = w.angle, nrec = w.zend - w.zbeg, npairs = nrec * G;
+    {   // the item's records are contiguous: 24 16-byte words each
+      const uint4 *src4 = reinterpret_cast<const uint4 *>(recs + (size_t)a * P.nz + w.zbeg);
+      uint4 *dst4 = reinterpret_cast<uint4 *>(s_rec);
+      for (int k = threadIdx.x; k < nrec * 24; k += blockDim.x) dst4[k] = __ldg(src4 + k);
+    }
+    __syncthreads();
+    const int zi = threadIdx.x / G, g = threadIdx.x - zi * G;
+    const bool active = (int)threadIdx.x < npairs;
+    const RZRec &R = s_rec[active ? zi : 0];
+    const int nCorner = R.nCorner, c0 = R.c0;
+    const double *psiA = P.psi + (size_t)a * slab;
+    double *psi1A = P.psi1 + (size_t)a * slab;
+    double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+    double srcS[4], A1[4][2], inv[4];
+    if (active) {   // group-dependent static half
+      const double sig = P.sigt[(size_t)R.zone * G + g], sigInv = 1.0 / sig;
+      double Q[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        Q[c] = 0.0;
+        if (c < nCorner) { const size_t r = (size_t)(c0 + c) * G + g; Q[c] = P.stotal[r] + P.tau * psiA[r]; }
+        srcS[c] = R.vol[c] * Q[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          A1[c][f] = 0.0;
+          const double az = R.az[c][f];
+          if (az > 0.0) {
+            const int cez = R.cez[c][f];
+            const double Rr = R.rez[c][f], dq = Q[c] - pick<4>(Q, cez);
+            double A0;
+            if (R.inMask & (1u << (2 * c + f))) {
+              const double ar = R.area[c];
+              const double sigA = sig * ar, sigA2 = sigA * sigA;
+              const double gnum = az * az * (FOURALPHA * sigA2 + az * (4.0 * sigA + 3.0 * az));
+              const double gden = ar * (4.0 * sigA * sigA2 + az * (6.0 * sigA2 + 2.0 * az * (2.0 * sigA + az)));
+              const double rd = Rr / (gnum + gden * sig);
+              A1[c][f] = rd * (ar * gnum * sig);
+              A0 = rd * (0.5 * az * gden * dq - ar * gnum * Q[c]);
+            } else {
+              A0 = 0.5 * (Rr * az) * dq * sigInv;
+            }
+            srcS[c] += A0;
+            addto<4>(srcS, cez, -A0);
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int c = R.ci[i];
+        inv[i] = 1.0 / (R.sumArea[c] + sig * R.vol[c]);
+      }
+    }
+    if (threadIdx.x == blockDim.x - 1) {
+      if (w.wait_idx >= 0)
+        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
+      if (w.pad0 >= 0)
+        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
+    }
+    __syncthreads();
+    if (active) {   // the half on the dependency chain
+      double src[4], pm[4], u[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        src[c] = srcS[c]; pm[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
+        if (c < nCorner) {
+          pm[c] = psimL[(size_t)(c0 + c) * G + g];
+#pragma unroll
+          for (int f = 0; f < 2; f++)
+            if (R.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)R.row[c][f] * G + g]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          src[c] = fma(R.k1b[c][f] + A1[c][f], u[c][f], src[c]);
+          addto<4>(src, R.cez[c][f], -A1[c][f] * u[c][f]);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (i < nCorner) {
+          const int c = R.ci[i];
+          const double p = (pick<4>(src, c) + R.areaFac[c] * pick<4>(pm, c)) * inv[i];
+          put<4>(src, c, p);
+          addto<4>(src, R.cez[c][0], (R.rez[c][0] * R.az[c][0]) * p);
+          addto<4>(src, R.cez[c][1], (R.rez[c][1] * R.az[c][1]) * p);
+        }
+      }
+      const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
+      double *psi1N = psi1A + slab;
+      const double w1 = P.tauW1[a], w2 = P.tauW2[a];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        if (c < nCorner) {
+          const size_t r = (size_t)(c0 + c) * G + g;
+          const double p = src[c];
+          const double pmn = starting ? p : w1 * p - w2 * pm[c];
+          psimL[r] = pmn;
+          psi1A[r] = p;
+          if (fin) psi1N[r] = pmn;
+#pragma unroll
+          for (int f = 0; f < 2; f++) {
+            if (R.exitMask & (1u << (2 * c + f))) {
+              const int row = R.row[c][f];
+              psi1A[(size_t)row * G + g] = p;
+              if (fin) psi1N[(size_t)row * G + g] = pmn;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
+    }
+  }
+}
+
+// Dataflow kernel.  The same work items in the same topological order, but nothing waits for a whole plane: every warp takes
+// 32 (zone, group) pairs of an item, runs the static half, then each lane polls exactly the values its pair needs -- the Psi1 rows
+// behind its incident faces and the previous angle's PsiM of its corners -- until they are no longer marked (RZ_SENTINEL), solves
+// and stores.  A dependent hop costs one L2 store -> load round trip instead of store -> fence -> counter -> poll -> load, and a
+// plane's slowest item no longer holds up the whole next plane.  Producers always hold earlier tickets than their consumers and
+// a warp takes a ticket only when it is free, so every polled value is being computed by a resident warp: no deadlock.
+// Not used with cycle lists / direct-solve zones (a consumer must see the OLD value there, which needs the plane order) nor
+// with reflecting boundaries (staged launches).
+template <int MC>
+__global__ void __launch_bounds__(RZ_BLOCK, RZ_MIN_CTAS) sweeprz_flow_kernel(SweepRZParams P, int warpsPerItem) {
+  const int G = P.G, lane = threadIdx.x & 31;
+  const int nUnits = P.nItems * warpsPerItem;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&P.counters[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nUnits) break;
+    const int it = t / warpsPerItem, sub = t - it * warpsPerItem;
+    const WorkItem w = P.items[it];
+    const int npairs = (w.zend - w.zbeg) * G;
+    const int idx = sub * 32 + lane;
+    if (idx < npairs) {
+      const int zi = idx / G, g = idx - zi * G;
+      ZoneStatic<MC> Z;
+      zone_static_rz<MC>(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + w.zbeg + zi], g, Z);
+      zone_solve_rz<MC, true>(P, w.angle, g, Z);
+    }
+    __syncwarp();
+  }
+}
+
+// marks the corner rows of Psi1 and the PsiM slab of every swept angle as "not computed yet"
+__global__ void sweeprz_mark_kernel(double *psi1, double *psimA, const int *nHyp, size_t slab, size_t ncG) {
+  const int a = blockIdx.y;
+  if (nHyp[a] == 0) return;
+  ulonglong2 *p1 = reinterpret_cast<ulonglong2 *>(psi1 + (size_t)a * slab), *p2 = reinterpret_cast<ulonglong2 *>(psimA + (size_t)a * ncG);
+  const ulonglong2 v = make_ulonglong2(RZ_SENTINEL, RZ_SENTINEL);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncG / 2; i += (size_t)gridDim.x * blockDim.x) { p1[i] = v; p2[i] = v; }
 }
 
 // Chain kernel.  In r-z the groups are independent of each other and the xi-levels are independent of each other, while
@@ -364,6 +652,25 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
     UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
     return UMT_OK;
   };
+  // dataflow kernel: previous swept angle of each level; usable without cycle lists, direct-solve zones and reflecting boundaries,
+  // with G even (16-byte marks) and items of at most RZ_BLOCK pairs
+  std::vector<int> prevA(NA, -1);
+  {
+    std::vector<int> lastOf(nL, -1);
+    for (int a = 0; a < NA; a++) { if (nh[a] == 0) continue; prevA[a] = lastOf[ctx->h_level[a]]; lastOf[ctx->h_level[a]] = a; }
+  }
+  bool plain = ctx->nStages <= 1 && ctx->G % 2 == 0 && ctx->G <= RZ_BLOCK && ((size_t)(ctx->nc + ctx->nb) * ctx->G) % 2 == 0;
+  for (int a = 0; a < NA && plain; a++) {
+    if (ctx->numCycles[a] > 0) plain = false;
+    for (int z : ctx->nextZ[a]) if (z < 0) { plain = false; break; }
+  }
+  ctx->rz_flow = false;
+  if (const char *e = getenv("UMT_RZ_KERNEL")) ctx->rz_flow = plain && std::string(e) == "flow";
+  // record kernel: quads, every item's pairs fit one CTA
+  ctx->rz_rec = ctx->maxCorner <= 4 && ctx->G <= RZ_BLOCK && ctx->zones_per_item * ctx->G <= RZ_BLOCK;
+  if (const char *e = getenv("UMT_RZ_KERNEL")) if (std::string(e) != "rec") ctx->rz_rec = false;
+  ctx->rz_recs_valid = false;
+  if ((r = up(&ctx->d_rzPrev, prevA))) return r;
   if ((r = up(&ctx->d_rzLevelAngles, la))) return r;
   if ((r = up(&ctx->d_rzPlaneOff, po))) return r;
   return up(&ctx->d_rzNHyp, nh);
@@ -463,6 +770,57 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
     ck<<<ctx->nLevels * P.nGroupBlocks, ctx->rz_threads, 0, ctx->stream>>>(P);
     UMT_CUDA(ctx, cudaGetLastError());
     ctx->last_launches += 1;
+    return UMT_OK;
+  }
+  if (ctx->rz_flow && ctx->nStages <= 1) {
+    const size_t ncG = (size_t)ctx->nc * ctx->G, slab = (size_t)(ctx->nc + ctx->nb) * ctx->G;
+    if (!ctx->d_rzPsimA) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_rzPsimA, sizeof(double) * ncG * ctx->NA));
+    P.psimA = ctx->d_rzPsimA; P.prevAngle = ctx->d_rzPrev;
+    sweeprz_mark_kernel<<<dim3(ctx->sm_count * 2, ctx->NA), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_rzPsimA, ctx->d_rzNHyp, slab, ncG);
+    UMT_CUDA(ctx, cudaGetLastError());
+    void (*fk)(SweepRZParams, int) = ctx->maxCorner <= 4 ? sweeprz_flow_kernel<4> : sweeprz_flow_kernel<MAXC2>;
+    int occ = 0;
+    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fk, RZ_BLOCK, 0));
+    if (occ < 1) occ = 1;
+    const int wpi = (std::min(RZ_BLOCK, ctx->zones_per_item * ctx->G) + 31) / 32;
+    const int grid = std::max(1, std::min(ctx->sm_count * occ, (ctx->nItems * wpi + RZ_BLOCK / 32 - 1) / (RZ_BLOCK / 32)));
+    fk<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P, wpi);
+    UMT_CUDA(ctx, cudaGetLastError());
+    ctx->last_launches += 2;
+    return UMT_OK;
+  }
+  if (ctx->rz_rec) {
+    P.nHyp = ctx->d_rzNHyp;
+    RZRec *recs = static_cast<RZRec *>(ctx->d_rzRecs);
+    if (!ctx->rz_recs_valid) {
+      const size_t n = (size_t)ctx->NA * ctx->nz;
+      if (ctx->d_rzRecs) { cudaFree(ctx->d_rzRecs); ctx->d_rzRecs = nullptr; }
+      UMT_CUDA(ctx, cudaMalloc(&ctx->d_rzRecs, sizeof(RZRec) * n));
+      recs = static_cast<RZRec *>(ctx->d_rzRecs);
+      rz_rec_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(P, recs);
+      UMT_CUDA(ctx, cudaGetLastError());
+      ctx->rz_recs_valid = true;
+    }
+    const size_t smem = sizeof(RZRec) * (size_t)ctx->zones_per_item;
+    int occ = 0;
+    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweeprz_rec_kernel, RZ_BLOCK, smem));
+    if (occ < 1) occ = 1;
+    const int nSt = std::max(1, ctx->nStages);
+    for (int st = 0; st < nSt; st++) {   // reflecting boundaries: snreflect, then the angles of this stage (one stage otherwise)
+      int begin = 0, end = ctx->nItems;
+      if (ctx->nStages > 1) {
+        begin = ctx->stageItemBegin[st]; end = ctx->stageItemBegin[st + 1];
+        int r = umt_launch_reflect(ctx, st);
+        if (r) return r;
+        if (end == begin) continue;
+        if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
+      }
+      P.items = ctx->d_items + begin; P.nItems = end - begin;
+      const int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
+      sweeprz_rec_kernel<<<grid, RZ_BLOCK, smem, ctx->stream>>>(P, recs);
+      UMT_CUDA(ctx, cudaGetLastError());
+      ctx->last_launches += 1;
+    }
     return UMT_OK;
   }
   void (*kern)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_kernel<4> : sweeprz_kernel<MAXC2>;

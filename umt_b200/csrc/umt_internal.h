@@ -150,6 +150,13 @@ struct umt_ctx {
   bool rz_chain = false;
   int rz_gb = 4, rz_maxAngLevel = 0, rz_threads = 256;
   int *d_rzLevelAngles = nullptr, *d_rzPlaneOff = nullptr, *d_rzNHyp = nullptr;
+  // r-z record kernel (sweeprz.cu): group-independent half of the zone solve precomputed per (angle, zone), 384 B each
+  void *d_rzRecs = nullptr;            // (NA, nz) RZRec in sweep order
+  bool rz_rec = false, rz_recs_valid = false;
+  // r-z dataflow kernel (sweeprz.cu): no counters, the angular fluxes themselves are the completion flags
+  bool rz_flow = false;
+  int *d_rzPrev = nullptr;             // (NA) previous swept angle of the xi-level, -1 for the first
+  double *d_rzPsimA = nullptr;         // (NA, nc, G) half-angle intensity written by each angle (read by the next one of its level)
   // device: schedule
   int *d_nextZ = nullptr;              // (NA, nz) signed 1-based
   unsigned char *d_nextC = nullptr;    // (NA, nc) 0-based local corner
