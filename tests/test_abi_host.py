@@ -169,3 +169,33 @@ def test_planck_groups_match_reference_build():
         ours = teton.planck_groups(Tr, b)
         ref = O.planck_groups_ref(Tr, b)
         assert np.abs(ours - ref).max() <= 1e-14 * ref.max()
+
+
+# ---------------------------------------------------------------------------
+# the reference's own C seam (include/teton_gpu_compat.h)
+# ---------------------------------------------------------------------------
+_GPU_SWEEP_ARGS = ("Angle nHyperPlanes nZonesInPlane nextZ nextC STotal tau Psi Groups Volume Sigt nCFacesArray ndim maxcf ncorner "
+                   "A_fp omega cFP Psi1 nbelem A_ez cEZ NumAngles quadwt Phi PsiB maxCorner mem0solve1 streamIdPtr totalStreams savePsi "
+                   "numCycles cycleOffSet cyclePsi cycleList b0 nBdyElem PsiBMref Mref Geom_numCorner Geom_cOffSet").split()
+
+
+def _prototype_args(src, name):
+    m = re.search(r"void\s+" + name + r"\s*\((.*?)\)\s*[;{]", re.sub(r"/\*.*?\*/|//[^\n]*", "", src, flags=re.S), flags=re.S)
+    assert m, name
+    return [(a.split()[0], a.replace("*", " ").split()[-1]) for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+
+
+def test_compat_header_has_the_reference_signature():
+    """gpu_sweepucbxyz: 41 by-reference arguments in the order of the Fortran interface block
+    (gpu/SweepUCBxyzToGPU.F90:43-91); compared with the reference source itself when the tree is present."""
+    hdr = open(os.path.join(ROOT, "include", "teton_gpu_compat.h")).read()
+    args = _prototype_args(hdr, "gpu_sweepucbxyz")
+    assert [n for _, n in args] == _GPU_SWEEP_ARGS and len(args) == 41
+    ref = "/root/reference/src/teton/gpu/GPU_SweepUCBxyz.cu"
+    if os.path.exists(ref):
+        rargs = _prototype_args(open(ref).read(), "gpu_sweepucbxyz")
+        assert rargs == args, "types/names differ from the reference's definition"
+        assert _prototype_args(open(ref).read(), "gpu_streamsynchronize") == _prototype_args(hdr, "gpu_streamsynchronize")
+    lib = teton.load_library()
+    for n in ("gpu_sweepucbxyz", "gpu_streamsynchronize", "gpu_devicesynchronize"):
+        assert hasattr(lib, n)

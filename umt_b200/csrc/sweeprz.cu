@@ -358,7 +358,17 @@ static_assert(sizeof(RZRec) == 384, "RZRec layout");
 #define RZ_REC_MIN_CTAS 10
 #endif
 
-__global__ void rz_rec_build_kernel(SweepRZParams P, RZRec *recs) {
+// Canonical quad labelling.  The corners of a quad swept in a generic direction are solved source -> its two neighbours ->
+// sink, and the two neighbours never exchange flux (they are opposite corners).  Relabelling the corners by that position
+// (p0 = first corner of nextC, p1 = p0+1, p2 = p0+3, p3 = p0+2 in the zone's cyclic numbering) and ordering the two face
+// slots of a corner as (toward local+1, toward local+3) makes the corner across every EZ face and the solve order compile-time
+// constants (RZ_NB below), so the register arrays of the solve need no select chains at all (a third of the instructions of
+// the labelled-by-corner version).  Any topological order gives the reference's corner fluxes; only the order in which the two
+// pushes into the sink are added differs from nextC's.  Zones that do not fit (triangles, flows like 0>1>3>2) are counted and
+// the whole mesh then takes the by-corner records.
+__device__ __host__ constexpr int rz_nb(int p, int f) { return f == 0 ? (p == 0 ? 1 : p == 1 ? 3 : p == 2 ? 0 : 2) : (p == 0 ? 2 : p == 1 ? 0 : p == 2 ? 3 : 1); }
+
+__global__ void rz_rec_build_kernel(SweepRZParams P, RZRec *recs, int canonMode, int *nonCanon) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)P.NA * P.nz) return;
   const int a = (int)(idx / P.nz);
@@ -396,9 +406,35 @@ __global__ void rz_rec_build_kernel(SweepRZParams P, RZRec *recs) {
         R.sumArea[cez] = __dadd_rn(R.sumArea[cez], __dmul_rn(R.rez[c][f], az));
       }
     }
+  if (canonMode) {
+    const int L0 = R.ci[0];
+    const int L[4] = {L0, (L0 + 1) & 3, (L0 + 3) & 3, (L0 + 2) & 3};
+    bool ok = nCorner == 4 && R.ci[3] == L[3] && ((R.ci[1] == L[1] && R.ci[2] == L[2]) || (R.ci[1] == L[2] && R.ci[2] == L[1]));
+    RZRec C;
+    C.c0 = c0; C.zone = zone; C.nCorner = nCorner; C.inMask = 0u; C.exitMask = 0u;
+    for (int p = 0; p < 4; p++) {
+      const int c = L[p];
+      C.vol[p] = R.vol[c]; C.area[p] = R.area[c]; C.areaFac[p] = R.areaFac[c]; C.sumArea[p] = R.sumArea[c]; C.ci[p] = (unsigned char)c;
+      for (int f = 0; f < 2; f++) {
+        const int target = L[rz_nb(p, f)];
+        const int fl = R.cez[c][0] == target ? 0 : (R.cez[c][1] == target ? 1 : -1);
+        if (fl < 0 || R.cez[c][0] == R.cez[c][1]) { ok = false; C.k1b[p][f] = 0.0; C.az[p][f] = 0.0; C.rez[p][f] = 0.0; C.row[p][f] = 0; C.cez[p][f] = 0; continue; }
+        C.k1b[p][f] = R.k1b[c][fl]; C.az[p][f] = R.az[c][fl]; C.rez[p][f] = R.rez[c][fl]; C.row[p][f] = R.row[c][fl];
+        C.cez[p][f] = (unsigned char)rz_nb(p, f);
+        if (R.inMask & (1u << (2 * c + fl))) C.inMask |= 1u << (2 * p + f);
+        if (R.exitMask & (1u << (2 * c + fl))) C.exitMask |= 1u << (2 * p + f);
+      }
+    }
+    if (!ok) atomicAdd(nonCanon, 1);
+    recs[idx] = C;
+    return;
+  }
   recs[idx] = R;
 }
 
+// FLOW: the dataflow scheme of sweeprz_flow_kernel (below) on top of the records.  CANON: records labelled by solve position
+// (see rz_rec_build_kernel): array index = position, R.ci[p] = local corner of position p (for the row addresses only).
+template <bool FLOW, bool CANON>
 __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(SweepRZParams P, const RZRec *recs) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   RZRec *s_rec = reinterpret_cast<RZRec *>(s_raw);
@@ -421,10 +457,11 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
     const int zi = threadIdx.x / G, g = threadIdx.x - zi * G;
     const bool active = (int)threadIdx.x < npairs;
     const RZRec &R = s_rec[active ? zi : 0];
+#define LC(c) (CANON ? (int)R.ci[c] : (c))
     const int nCorner = R.nCorner, c0 = R.c0;
     const double *psiA = P.psi + (size_t)a * slab;
     double *psi1A = P.psi1 + (size_t)a * slab;
-    double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+    double *psimL = FLOW ? P.psimA + (size_t)a * nc * G : P.psim + (size_t)P.level[a] * nc * G;
     double srcS[4], A1[4][2], inv[4];
     if (active) {   // group-dependent static half
       const double sig = P.sigt[(size_t)R.zone * G + g], sigInv = 1.0 / sig;
@@ -432,7 +469,7 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         Q[c] = 0.0;
-        if (c < nCorner) { const size_t r = (size_t)(c0 + c) * G + g; Q[c] = P.stotal[r] + P.tau * psiA[r]; }
+        if (c < nCorner) { const size_t r = (size_t)(c0 + LC(c)) * G + g; Q[c] = P.stotal[r] + P.tau * psiA[r]; }
         srcS[c] = R.vol[c] * Q[c];
       }
 #pragma unroll
@@ -442,7 +479,7 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
           A1[c][f] = 0.0;
           const double az = R.az[c][f];
           if (az > 0.0) {
-            const int cez = R.cez[c][f];
+            const int cez = CANON ? rz_nb(c, f) : (int)R.cez[c][f];
             const double Rr = R.rez[c][f], dq = Q[c] - pick<4>(Q, cez);
             double A0;
             if (R.inMask & (1u << (2 * c + f))) {
@@ -462,27 +499,73 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         }
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int c = R.ci[i];
+        const int c = CANON ? i : (int)R.ci[i];
         inv[i] = 1.0 / (R.sumArea[c] + sig * R.vol[c]);
       }
     }
-    if (threadIdx.x == blockDim.x - 1) {
-      if (w.wait_idx >= 0)
-        while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
-      if (w.pad0 >= 0)
-        while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
+    if (!FLOW) {
+      if (threadIdx.x == blockDim.x - 1) {
+        if (w.wait_idx >= 0)
+          while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
+        if (w.pad0 >= 0)
+          while (ld_acquire(&P.counters[1 + w.pad0]) < w.pad1) __nanosleep(20);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (active) {   // the half on the dependency chain
       double src[4], pm[4], u[4][2];
+      if (FLOW) {   // every lane polls the values its pair needs until they are no longer marked
+        const int pa = P.prevAngle[a];
+        const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc * G;
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              if (c < nCorner) {
+                if (pa >= 0) ok = ok && ld_relaxed_u64(&psimP[(size_t)(c0 + LC(c)) * G + g]) != RZ_SENTINEL;
+#pragma unroll
+                for (int f = 0; f < 2; f++)
+                  if (R.inMask & (1u << (2 * c + f))) ok = ok && ld_relaxed_u64(&psi1A[(size_t)R.row[c][f] * G + g]) != RZ_SENTINEL;
+              }
+            if (!ok) __nanosleep(100);
+          } while (!ok);
+        }
+        __syncwarp();
+        do {
+          ok = true;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            pm[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
+            if (c < nCorner) {
+              if (pa >= 0) {
+                const unsigned long long v = ld_relaxed_u64(&psimP[(size_t)(c0 + LC(c)) * G + g]);
+                ok = ok && v != RZ_SENTINEL;
+                pm[c] = __longlong_as_double((long long)v);
+              }
+#pragma unroll
+              for (int f = 0; f < 2; f++)
+                if (R.inMask & (1u << (2 * c + f))) {
+                  const unsigned long long v = ld_relaxed_u64(&psi1A[(size_t)R.row[c][f] * G + g]);
+                  ok = ok && v != RZ_SENTINEL;
+                  u[c][f] = __longlong_as_double((long long)v);
+                }
+            }
+          }
+          if (!ok) __nanosleep(40);
+        } while (!ok);
+      }
 #pragma unroll
       for (int c = 0; c < 4; c++) {
-        src[c] = srcS[c]; pm[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
-        if (c < nCorner) {
-          pm[c] = psimL[(size_t)(c0 + c) * G + g];
+        src[c] = srcS[c];
+        if (!FLOW) {
+          pm[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
+          if (c < nCorner) {
+            pm[c] = psimL[(size_t)(c0 + LC(c)) * G + g];
 #pragma unroll
-          for (int f = 0; f < 2; f++)
-            if (R.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)R.row[c][f] * G + g]);
+            for (int f = 0; f < 2; f++)
+              if (R.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)R.row[c][f] * G + g]);
+          }
         }
       }
 #pragma unroll
@@ -490,16 +573,16 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
 #pragma unroll
         for (int f = 0; f < 2; f++) {
           src[c] = fma(R.k1b[c][f] + A1[c][f], u[c][f], src[c]);
-          addto<4>(src, R.cez[c][f], -A1[c][f] * u[c][f]);
+          addto<4>(src, CANON ? rz_nb(c, f) : (int)R.cez[c][f], -A1[c][f] * u[c][f]);
         }
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         if (i < nCorner) {
-          const int c = R.ci[i];
+          const int c = CANON ? i : (int)R.ci[i];
           const double p = (pick<4>(src, c) + R.areaFac[c] * pick<4>(pm, c)) * inv[i];
           put<4>(src, c, p);
-          addto<4>(src, R.cez[c][0], (R.rez[c][0] * R.az[c][0]) * p);
-          addto<4>(src, R.cez[c][1], (R.rez[c][1] * R.az[c][1]) * p);
+          addto<4>(src, CANON ? rz_nb(c, 0) : (int)R.cez[c][0], (R.rez[c][0] * R.az[c][0]) * p);
+          addto<4>(src, CANON ? rz_nb(c, 1) : (int)R.cez[c][1], (R.rez[c][1] * R.az[c][1]) * p);
         }
       }
       const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
@@ -508,11 +591,11 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         if (c < nCorner) {
-          const size_t r = (size_t)(c0 + c) * G + g;
+          const size_t r = (size_t)(c0 + LC(c)) * G + g;
           const double p = src[c];
           const double pmn = starting ? p : w1 * p - w2 * pm[c];
-          psimL[r] = pmn;
-          psi1A[r] = p;
+          if (FLOW) { st_relaxed_f64(&psimL[r], pmn); st_relaxed_f64(&psi1A[r], p); }
+          else { psimL[r] = pmn; psi1A[r] = p; }
           if (fin) psi1N[r] = pmn;
 #pragma unroll
           for (int f = 0; f < 2; f++) {
@@ -525,12 +608,15 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         }
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
+    if (!FLOW) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
+      }
     }
   }
+#undef LC
 }
 
 // Dataflow kernel.  The same work items in the same topological order, but nothing waits for a whole plane: every warp takes
@@ -665,10 +751,10 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
     for (int z : ctx->nextZ[a]) if (z < 0) { plain = false; break; }
   }
   ctx->rz_flow = false;
-  if (const char *e = getenv("UMT_RZ_KERNEL")) ctx->rz_flow = plain && std::string(e) == "flow";
+  if (const char *e = getenv("UMT_RZ_KERNEL")) ctx->rz_flow = plain && (std::string(e) == "flow" || std::string(e) == "recflow");
   // record kernel: quads, every item's pairs fit one CTA
   ctx->rz_rec = ctx->maxCorner <= 4 && ctx->G <= RZ_BLOCK && ctx->zones_per_item * ctx->G <= RZ_BLOCK;
-  if (const char *e = getenv("UMT_RZ_KERNEL")) if (std::string(e) != "rec") ctx->rz_rec = false;
+  if (const char *e = getenv("UMT_RZ_KERNEL")) if (std::string(e) != "rec" && std::string(e) != "recflow") ctx->rz_rec = false;
   ctx->rz_recs_valid = false;
   if ((r = up(&ctx->d_rzPrev, prevA))) return r;
   if ((r = up(&ctx->d_rzLevelAngles, la))) return r;
@@ -772,7 +858,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
     ctx->last_launches += 1;
     return UMT_OK;
   }
-  if (ctx->rz_flow && ctx->nStages <= 1) {
+  if (ctx->rz_flow && !ctx->rz_rec && ctx->nStages <= 1) {
     const size_t ncG = (size_t)ctx->nc * ctx->G, slab = (size_t)(ctx->nc + ctx->nb) * ctx->G;
     if (!ctx->d_rzPsimA) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_rzPsimA, sizeof(double) * ncG * ctx->NA));
     P.psimA = ctx->d_rzPsimA; P.prevAngle = ctx->d_rzPrev;
@@ -797,13 +883,42 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       if (ctx->d_rzRecs) { cudaFree(ctx->d_rzRecs); ctx->d_rzRecs = nullptr; }
       UMT_CUDA(ctx, cudaMalloc(&ctx->d_rzRecs, sizeof(RZRec) * n));
       recs = static_cast<RZRec *>(ctx->d_rzRecs);
-      rz_rec_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(P, recs);
-      UMT_CUDA(ctx, cudaGetLastError());
+      // canonical labelling first; if any zone does not fit, the by-corner records for the whole mesh
+      int *d_bad = nullptr, h_bad = 0;
+      UMT_CUDA(ctx, cudaMalloc((void **)&d_bad, sizeof(int)));
+      UMT_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+      bool canon = true;
+      if (const char *e = getenv("UMT_RZ_CANON")) canon = atoi(e) != 0;
+      if (canon) {
+        rz_rec_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(P, recs, 1, d_bad);
+        UMT_CUDA(ctx, cudaGetLastError());
+        UMT_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        canon = h_bad == 0;
+      }
+      if (!canon) {
+        rz_rec_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(P, recs, 0, d_bad);
+        UMT_CUDA(ctx, cudaGetLastError());
+        UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      }
+      cudaFree(d_bad);
+      ctx->rz_canon = canon;
       ctx->rz_recs_valid = true;
     }
     const size_t smem = sizeof(RZRec) * (size_t)ctx->zones_per_item;
+    const bool flow = ctx->rz_flow && ctx->nStages <= 1;
+    void (*rk)(SweepRZParams, const RZRec *) = flow ? (ctx->rz_canon ? sweeprz_rec_kernel<true, true> : sweeprz_rec_kernel<true, false>)
+                                                    : (ctx->rz_canon ? sweeprz_rec_kernel<false, true> : sweeprz_rec_kernel<false, false>);
+    if (flow) {
+      const size_t ncG = (size_t)ctx->nc * ctx->G, slabE = (size_t)(ctx->nc + ctx->nb) * ctx->G;
+      if (!ctx->d_rzPsimA) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_rzPsimA, sizeof(double) * ncG * ctx->NA));
+      P.psimA = ctx->d_rzPsimA; P.prevAngle = ctx->d_rzPrev;
+      sweeprz_mark_kernel<<<dim3(ctx->sm_count * 2, ctx->NA), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_rzPsimA, ctx->d_rzNHyp, slabE, ncG);
+      UMT_CUDA(ctx, cudaGetLastError());
+      ctx->last_launches += 1;
+    }
     int occ = 0;
-    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweeprz_rec_kernel, RZ_BLOCK, smem));
+    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk, RZ_BLOCK, smem));
     if (occ < 1) occ = 1;
     const int nSt = std::max(1, ctx->nStages);
     for (int st = 0; st < nSt; st++) {   // reflecting boundaries: snreflect, then the angles of this stage (one stage otherwise)
@@ -817,7 +932,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       }
       P.items = ctx->d_items + begin; P.nItems = end - begin;
       const int grid = std::max(1, std::min(ctx->sm_count * occ, P.nItems));
-      sweeprz_rec_kernel<<<grid, RZ_BLOCK, smem, ctx->stream>>>(P, recs);
+      rk<<<grid, RZ_BLOCK, smem, ctx->stream>>>(P, recs);
       UMT_CUDA(ctx, cudaGetLastError());
       ctx->last_launches += 1;
     }
