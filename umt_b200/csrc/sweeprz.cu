@@ -519,20 +519,6 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc * G;
         bool ok;
         do {
-            ok = true;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-              if (c < nCorner) {
-                if (pa >= 0) ok = ok && ld_relaxed_u64(&psimP[(size_t)(c0 + LC(c)) * G + g]) != RZ_SENTINEL;
-#pragma unroll
-                for (int f = 0; f < 2; f++)
-                  if (R.inMask & (1u << (2 * c + f))) ok = ok && ld_relaxed_u64(&psi1A[(size_t)R.row[c][f] * G + g]) != RZ_SENTINEL;
-              }
-            if (!ok) __nanosleep(100);
-          } while (!ok);
-        }
-        __syncwarp();
-        do {
           ok = true;
 #pragma unroll
           for (int c = 0; c < 4; c++) {
