@@ -441,11 +441,22 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
   __shared__ int s_item;
   const int G = P.G, nc = P.nc;
   const size_t slab = (size_t)(nc + P.nb) * G;
+#ifdef RZ_TICKET_AHEAD   // A/B: the next ticket is taken while the current item is worked on (hides the atomic's round trip)
+  __shared__ int s_next[2];
+  if (threadIdx.x == 0) s_next[0] = atomicAdd(&P.counters[0], 1);
+  __syncthreads();
+  int it = s_next[0], buf = 0;
+  for (;;) {
+    if (it >= P.nItems) break;
+    int nxt = 0;
+    if (threadIdx.x == 0) nxt = atomicAdd(&P.counters[0], 1);
+#else
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(&P.counters[0], 1);
     __syncthreads();
     const int it = s_item;
     if (it >= P.nItems) break;
+#endif
     const WorkItem w = P.items[it];
     const int a = w.angle, nrec = w.zend - w.zbeg, npairs = nrec * G;
     {   // the item's records are contiguous: 24 16-byte words each
@@ -594,6 +605,9 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         }
       }
     }
+#ifdef RZ_TICKET_AHEAD
+    if (threadIdx.x == 0) s_next[buf ^ 1] = nxt;
+#endif
     if (!FLOW) {
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -601,6 +615,10 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
       }
     }
+#ifdef RZ_TICKET_AHEAD
+    if (FLOW) __syncthreads();
+    it = s_next[buf ^ 1]; buf ^= 1;
+#endif
   }
 #undef LC
 }
