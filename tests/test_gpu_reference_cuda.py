@@ -127,6 +127,12 @@ def test_tiled_mesh_driver_problem_three_passes():
     _three_way(M.tiled_mesh((2, 2, 3)), 2, 2, 4, passes=(False, False, True), driver_like=True)
 
 
+def test_baseline_config0_size():
+    """BASELINE configs[0] at full size: tiled mesh -d 10,10,10 (24 000 zones, 192 000 corners), -P 2 -A 2 (32 angles), the driver's
+    problem data; G = 4 instead of 2 because the reference kernel handles groups in blocks of 4 without a bound check (:32, :207)"""
+    _three_way(M.tiled_mesh((10, 10, 10)), 2, 2, 4, passes=(False, True), driver_like=True)
+
+
 def test_box_mesh_more_angles_and_groups():
     _three_way(M.box_mesh((5, 4, 3)), 3, 2, 32)
 
