@@ -888,8 +888,9 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       UMT_CUDA(ctx, cudaMalloc(&ctx->d_rzRecs, sizeof(RZRec) * n));
       recs = static_cast<RZRec *>(ctx->d_rzRecs);
       // canonical labelling first; if any zone does not fit, the by-corner records for the whole mesh
-      int *d_bad = nullptr, h_bad = 0;
-      UMT_CUDA(ctx, cudaMalloc((void **)&d_bad, sizeof(int)));
+      int h_bad = 0;
+      if (!ctx->d_rzBad) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_rzBad, sizeof(int)));
+      int *d_bad = ctx->d_rzBad;
       UMT_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
       bool canon = true;
       if (const char *e = getenv("UMT_RZ_CANON")) canon = atoi(e) != 0;
@@ -905,7 +906,6 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
         UMT_CUDA(ctx, cudaGetLastError());
         UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       }
-      cudaFree(d_bad);
       ctx->rz_canon = canon;
       ctx->rz_recs_valid = true;
     }

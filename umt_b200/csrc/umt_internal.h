@@ -152,6 +152,7 @@ struct umt_ctx {
   int *d_rzLevelAngles = nullptr, *d_rzPlaneOff = nullptr, *d_rzNHyp = nullptr;
   // r-z record kernel (sweeprz.cu): group-independent half of the zone solve precomputed per (angle, zone), 384 B each
   void *d_rzRecs = nullptr;            // (NA, nz) RZRec in sweep order
+  int *d_rzBad = nullptr;              // number of zones that do not fit the canonical labelling
   bool rz_rec = false, rz_recs_valid = false, rz_canon = false;
   // r-z dataflow kernel (sweeprz.cu): no counters, the angular fluxes themselves are the completion flags
   bool rz_flow = false;
