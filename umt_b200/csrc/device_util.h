@@ -17,3 +17,14 @@ template <int MC> __device__ __forceinline__ void put(double (&a)[MC], int i, do
   for (int k = 0; k < MC; k++) a[k] = i == k ? v : a[k];
 }
 
+// Dataflow sweeps (sweeprz.cu, gta_rz.cu): a quiet NaN with a payload no arithmetic produces marks "not computed yet"; consumers poll
+// the values they need until they are real, so the data are their own completion flags (no counters, fences or barriers).
+constexpr unsigned long long UMT_SENTINEL = 0xFFFFDEADFFFFDEADull;
+__device__ __forceinline__ unsigned long long umt_ld_relaxed_u64(const double *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void umt_st_relaxed_f64(double *p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}

@@ -685,7 +685,8 @@ void umt_gta_release(umt_ctx *ctx) {
   void *p[] = {g.d_omega, g.d_weight, g.d_nextZ, g.d_nextC, g.d_items, g.d_counters, g.d_sigTotal, g.d_sigtInv, g.d_sigScat, g.d_sigScatVol,
                g.d_greySource, g.d_tsaSource, g.d_phiInc, g.d_correction, g.d_chi, g.d_TT, g.d_tpsi, g.d_pinc, g.d_vec[0], g.d_vec[1], g.d_vec[2],
                g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB,
-               g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc, g.d_levelAngles, g.d_planeOff, g.d_nHyp, g.d_reflOps};
+               g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc, g.d_levelAngles, g.d_planeOff, g.d_nHyp, g.d_reflOps,
+               g.d_prevAngle, g.d_psimA, g.d_tincA};
   for (void *q : p) if (q) cudaFree(q);
   g = GtaState();
 }

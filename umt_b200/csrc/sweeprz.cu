@@ -60,16 +60,7 @@ struct SweepRZParams {
 // Dataflow variant: a quiet NaN with a payload no arithmetic produces marks "not computed yet".  The corner rows of Psi1 and the
 // per-angle PsiM slabs are filled with it before the launch; a consumer polls the values it needs until they are real, so the
 // data are their own completion flags: no counters, no fences (every 8-byte value is validated by itself), no barriers.
-constexpr unsigned long long RZ_SENTINEL = 0xFFFFDEADFFFFDEADull;
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
-  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
+constexpr unsigned long long RZ_SENTINEL = UMT_SENTINEL;   // device_util.h
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
@@ -224,14 +215,14 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
         u[c][0] = 0.0; u[c][1] = 0.0;
         if (c < nCorner) {
           if (pa >= 0) {
-            const unsigned long long v = ld_relaxed_u64(&psimP[(size_t)(c0 + c) * G + g]);
+            const unsigned long long v = umt_ld_relaxed_u64(&psimP[(size_t)(c0 + c) * G + g]);
             ok = ok && v != RZ_SENTINEL;
             pm[c] = __longlong_as_double((long long)v);
           }
 #pragma unroll
           for (int f = 0; f < 2; f++)
             if (Z.inMask & (1u << (2 * c + f))) {
-              const unsigned long long v = ld_relaxed_u64(&psi1A[(size_t)Z.row[c][f] * G + g]);
+              const unsigned long long v = umt_ld_relaxed_u64(&psi1A[(size_t)Z.row[c][f] * G + g]);
               ok = ok && v != RZ_SENTINEL;
               u[c][f] = __longlong_as_double((long long)v);
             }
@@ -282,7 +273,7 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
       const size_t r = (size_t)cc * G + g;
       const double p = src[c];
       const double pmn = starting ? p : w1 * p - w2 * pm[c];
-      if (FLOW) { st_relaxed_f64(&psimL[r], pmn); st_relaxed_f64(&psi1A[r], p); }
+      if (FLOW) { umt_st_relaxed_f64(&psimL[r], pmn); umt_st_relaxed_f64(&psi1A[r], p); }
       else { psimL[r] = pmn; psi1A[r] = p; }
       if (fin) psi1N[r] = pmn;   // Psi(:,c,Angle+1) <- PsiM (becomes Psi when the buffers trade roles on savePsi)
 #pragma unroll
@@ -536,14 +527,14 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
             pm[c] = 0.0; u[c][0] = 0.0; u[c][1] = 0.0;
             if (c < nCorner) {
               if (pa >= 0) {
-                const unsigned long long v = ld_relaxed_u64(&psimP[(size_t)(c0 + LC(c)) * G + g]);
+                const unsigned long long v = umt_ld_relaxed_u64(&psimP[(size_t)(c0 + LC(c)) * G + g]);
                 ok = ok && v != RZ_SENTINEL;
                 pm[c] = __longlong_as_double((long long)v);
               }
 #pragma unroll
               for (int f = 0; f < 2; f++)
                 if (R.inMask & (1u << (2 * c + f))) {
-                  const unsigned long long v = ld_relaxed_u64(&psi1A[(size_t)R.row[c][f] * G + g]);
+                  const unsigned long long v = umt_ld_relaxed_u64(&psi1A[(size_t)R.row[c][f] * G + g]);
                   ok = ok && v != RZ_SENTINEL;
                   u[c][f] = __longlong_as_double((long long)v);
                 }
@@ -591,7 +582,7 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
           const size_t r = (size_t)(c0 + LC(c)) * G + g;
           const double p = src[c];
           const double pmn = starting ? p : w1 * p - w2 * pm[c];
-          if (FLOW) { st_relaxed_f64(&psimL[r], pmn); st_relaxed_f64(&psi1A[r], p); }
+          if (FLOW) { umt_st_relaxed_f64(&psimL[r], pmn); umt_st_relaxed_f64(&psi1A[r], p); }
           else { psimL[r] = pmn; psi1A[r] = p; }
           if (fin) psi1N[r] = pmn;
 #pragma unroll

@@ -107,6 +107,9 @@ struct GtaState {
   double *d_fac = nullptr, *d_w1 = nullptr, *d_w2 = nullptr, *d_psim = nullptr, *d_tinc = nullptr;   // psim/tinc: (nLevels, nc)
   unsigned char *d_finish = nullptr;
   bool rz_chain = false;               // one CTA per xi-level (gta_sweep_rz_chain_kernel)
+  bool rz_flow = false;                // dataflow kernel (gta_sweep_rz_flow_kernel): values as their own completion flags
+  int *d_prevAngle = nullptr;          // (nAng) previous swept angle of the xi-level, -1: none
+  double *d_psimA = nullptr, *d_tincA = nullptr;   // (nAng, nc) half-angle values as written by each angle
   int rz_maxAngLevel = 0, rz_threads = 64;
   int *d_levelAngles = nullptr, *d_planeOff = nullptr, *d_nHyp = nullptr;
 };
