@@ -408,3 +408,38 @@ def test_gta_rz_solver_solves_the_grey_system():
     Mx, MB = corr.copy(), np.zeros((8, nb))
     Q.grey_sweep(MB, Mx, False)
     assert np.abs(b - (corr - Mx)).max() <= 1e-8 * np.abs(b).max()
+
+
+# ---------------------------------------------------------------------------
+# premise of the r-z record kernel's canonical quad labelling (csrc/sweeprz.cu, rz_rec_build_kernel)
+# ---------------------------------------------------------------------------
+def _canonical_fraction_rz(mesh, npolar=2, nazimuthal=2):
+    """fraction of (angle, zone) pairs whose corner order from snnext is source -> its two neighbours (in either order) -> the
+    opposite corner, with the EZ faces of every corner leading to the cyclic neighbours local+1 and local+3"""
+    p = T.make_problem_rz(mesh, npolar, nazimuthal, 2)
+    cez = np.asarray(mesh.cEZ).reshape(mesh.ncornr, 2) - 1
+    good = total = 0
+    for a in range(p.NA):
+        if p.sched["nHyperPlanes"][a] == 0:
+            continue
+        nextC = p.sched["nextC"][a] - 1
+        for z in range(mesh.nzones):
+            total += 1
+            if mesh.numCorner[z] != 4:
+                continue
+            c0 = mesh.cOffSet[z]
+            ci = nextC[c0:c0 + 4]
+            L0 = ci[0]
+            L = [L0, (L0 + 1) & 3, (L0 + 3) & 3, (L0 + 2) & 3]
+            ok = ci[3] == L[3] and {int(ci[1]), int(ci[2])} == {L[1], L[2]}
+            for c in range(4):
+                ok = ok and {int(cez[c0 + c, 0]), int(cez[c0 + c, 1])} == {(c + 1) & 3, (c + 3) & 3}
+            good += bool(ok)
+    return good / max(total, 1)
+
+
+def test_rz_tiled_mesh_zones_fit_the_canonical_quad_labelling():
+    """every zone of the tiled r-z mesh, for every swept ordinate of the product set, is solved source -> neighbours -> sink:
+    the record kernel's compile-time neighbour table applies to the whole mesh (a mesh where it does not takes the by-corner records)"""
+    for dims in ((3, 3, 0), (2, 5, 0)):
+        assert _canonical_fraction_rz(M.tiled_mesh(dims)) == 1.0
