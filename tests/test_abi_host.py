@@ -199,3 +199,21 @@ def test_compat_header_has_the_reference_signature():
     lib = teton.load_library()
     for n in ("gpu_sweepucbxyz", "gpu_streamsynchronize", "gpu_devicesynchronize"):
         assert hasattr(lib, n)
+
+
+def test_quadrature_tables_match_the_reference_data_module(tmp_path):
+    """umt_b200/csrc/quad_tables.inc (used by the library and the oracle alike) is the numeric content of the reference's
+    mods/QuadratureData_mod.F90:1144-4528: regenerated here from the reference tree and compared value by value (skipped where
+    the tree is absent, e.g. on the GPU box)."""
+    ref = "/root/reference/src/teton/mods/QuadratureData_mod.F90"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree absent")
+    import subprocess
+    import sys
+    out = tmp_path / "quad_tables.inc"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "extract_quadrature_tables.py"), ref, str(out)],
+                          stdout=subprocess.DEVNULL)
+    num = re.compile(r"[-+]?\d+\.\d+e[-+]\d+")
+    a = [float(x) for x in num.findall(open(out).read())]
+    b = [float(x) for x in num.findall(open(os.path.join(ROOT, "umt_b200", "csrc", "quad_tables.inc")).read())]
+    assert len(a) == len(b) == 6 * 528 and a == b
