@@ -217,3 +217,19 @@ def test_quadrature_tables_match_the_reference_data_module(tmp_path):
     a = [float(x) for x in num.findall(open(out).read())]
     b = [float(x) for x in num.findall(open(os.path.join(ROOT, "umt_b200", "csrc", "quad_tables.inc")).read())]
     assert len(a) == len(b) == 6 * 528 and a == b
+
+
+def test_problem_constants_match_the_reference_sources():
+    """umt_b200/problem.py restates the driver's problem; its constants are read back from the reference sources when present."""
+    base = "/root/reference/src/teton"
+    if not os.path.exists(base):
+        pytest.skip("reference tree absent")
+    from umt_b200 import problem as PR
+    rc = open(os.path.join(base, "mods", "radconstant_mod.F90")).read()
+    assert float(re.search(r"speed_light\s*=\s*([0-9.]+)_adqt", rc).group(1)) == PR.SPEED_LIGHT
+    assert float(re.search(r"rad_constant\s*=\s*([0-9.]+)_adqt", rc).group(1)) == PR.RAD_CONSTANT
+    drv = open(os.path.join(base, "driver", "test_driver.cc")).read()
+    for key, val in (("thermo_density", PR.RHO), ("electron_specific_heat", PR.CV), ("radiation_temperature", PR.TR0),
+                     ("electron_temperature", PR.TE0)):
+        m = re.search(r'material_field_vals\[1\]\["%s"\]\s*=\s*([0-9.eE+-]+);' % key, drv)
+        assert m and float(m.group(1)) == val, key
