@@ -233,3 +233,23 @@ def test_problem_constants_match_the_reference_sources():
                      ("electron_temperature", PR.TE0)):
         m = re.search(r'material_field_vals\[1\]\["%s"\]\s*=\s*([0-9.eE+-]+);' % key, drv)
         assert m and float(m.group(1)) == val, key
+
+
+def test_unstructured_box_base_mesh_matches_the_reference_generator():
+    """BASELINE configs[3]: the 12-vertex / 6-hex-per-layer base mesh of umt_b200/mesh.py (_UB_XY6, _UB_QUADS) is the one
+    driver/makeUnstructuredBox.cc:39-110 builds (its AddVertex / AddHex calls are read back here; the MFEM refinement on top
+    of it stays a stand-in)."""
+    src_path = "/root/reference/src/teton/driver/makeUnstructuredBox.cc"
+    if not os.path.exists(src_path):
+        pytest.skip("reference tree absent")
+    from umt_b200 import mesh as MM
+    src = open(src_path).read()
+    verts = re.findall(r"mesh\.AddVertex\(([^;]*?),\s*([^;]*?),\s*i \* width / 3\.0\);", src)
+    assert len(verts) == 12
+    xy = np.array([[eval(x, {"width": 1.0}), eval(y, {"width": 1.0})] for x, y in verts])
+    assert np.allclose(xy, MM._UB_XY6 / 6.0, rtol=0, atol=1e-15)
+    letters = {k: i for i, k in enumerate("abcdefghijkl")}
+    hexes = re.findall(r"mesh\.AddHex\((\w) \+ B, (\w) \+ B, (\w) \+ B, (\w) \+ B,", src)
+    assert len(hexes) == 12 and hexes[:6] == hexes[6:]       # two identical layers
+    assert [[letters[c] for c in h] for h in hexes[:6]] == MM._UB_QUADS.tolist()
+    assert MM._UB_LAYERS == 2
