@@ -46,8 +46,6 @@ def _rank_main():
     print(f"rank {rank}: NCCL psib exchange parity ok, worst phi rel err {worst:.2e}", flush=True)
     ctx.close()
     # grey transport acceleration on the decomposed mesh: grey psib exchange + allreduce of the inner products over NCCL
-    from oracle import oracle as O
-    from umt_b200 import problem as PR
     from tests.test_gta_multidomain import _domain, _oracle_problem
     G = 4
     doms = [_domain(M.tiled_mesh((2, 2, 1), rank=r, size=world), G, 40 + r) for r in range(world)]

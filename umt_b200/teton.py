@@ -9,8 +9,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
-
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
