@@ -40,7 +40,8 @@ def use_fast_build() -> bool:
     it).  Returns False (and keeps the strict build) if it cannot be built.  Must be called before the first lib()."""
     global _LIB
     try:
-        subprocess.check_call(["make", "-C", _HERE, "fast"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        # -B: always rebuilt on the machine that runs it (-march=native: a binary shipped from another host may not run here)
+        subprocess.check_call(["make", "-B", "-C", _HERE, "fast"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         _LIB = None
         os.environ["UMT_ORACLE_LIB"] = os.path.join(_HERE, "_ref", "libumt_oracle_fast.so")
         return True
