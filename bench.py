@@ -162,20 +162,59 @@ def reference_cuda_rate(G, npolar, nazim, sample_dims):
                       f"{p.NA} gpu_sweepucbxyz calls with host arrays (one stream), wall clock"}
 
 
+def reference_sample_dims(args):
+    """Tiles per side of the bounded CPU sample: the full -d 20 problem needs 50 GB of host memory per domain for Psi alone."""
+    if args.cpu_dims:
+        return args.cpu_dims
+    return 10 if args.gpus == 1 else (8 if args.gpus <= 4 else 6)
+
+
 def run_reference(args):
+    """The CPU path on the host cores of this box: N = --gpus mesh domains (what `mpirun -n N` of the reference runs), swept
+    concurrently, the host cores split evenly over the domains (OpenMP over angle sets inside each, SetSweep.F90:113-116).
+    Under torchrun rank 0 alone does this (with every core of the box, whatever OMP_NUM_THREADS the launcher exported)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    d = args.cpu_dims or 8
-    val, cores, dt, sample = cpu_sweep_rate(args.groups, args.polar, args.azimuthal, (d, d, d), steps=args.steps, warmup=min(args.warmup, 1))
+    from oracle import oracle as O
+    from tests import common as T
+    N = max(args.gpus, 1)
+    d = reference_sample_dims(args)
+    G = args.groups
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_domain = max(1, cores // N)
+    fast = O.use_fast_build()
+    problems = [T.make_problem_3d(M.tiled_mesh((d, d, d), rank=r, size=N), args.polar, args.azimuthal, G, driver_like=True) for r in range(N)]
+    unknowns = sum(p.mesh.ncornr * p.NA * G for p in problems)
+
+    def one_step():
+        th = [threading.Thread(target=T.oracle_sweep_3d, args=(p, False, per_domain)) for p in problems]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    for _ in range(min(args.warmup, 1)):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        one_step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = unknowns / dt
+    sample = (f"{N} domain(s) of a 3-D tiled mesh -d {d},{d},{d} -G {G} P{args.polar} A{args.azimuthal} ({unknowns:.3e} unknowns per step, "
+              f"the bench workload's problem data at a reduced domain size: the -d {args.dims} domain needs {24 * args.dims ** 3 * 8 * 8 * args.polar * args.azimuthal * G * 8 / 1e9:.0f} GB of host memory for Psi), "
+              f"domains swept concurrently with {per_domain} OpenMP thread(s) each, one full SetSweep+getPhiTotal per domain and step, no psib exchange "
+              f"(lagged exchange cost not charged to the CPU arm), oracle built {'-O3 -march=native -fopenmp' if fast else '-O2 -fopenmp -ffp-contract=off'}")
+    cfg = workload_config(args)
+    cfg["reference_sample"] = sample
+    cfg["reference_sample_dims"] = [d, d, d]
     line = {
         "impl": "reference", "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": val, "unit": "unknowns/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "unknowns/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "unknowns/s", "cores": min(cores, per_domain * N), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "unknowns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference (Fortran+MPI+Conduit) cannot be built in this image; this is the CPU restatement of SweepUCBxyz/SetSweep (oracle/), OpenMP over angle sets like SetSweep.F90:113-116",
+        "note": "the reference (Fortran+MPI+Conduit) cannot be built in this image; this is the CPU restatement of SweepUCBxyz/SetSweep (oracle/), OpenMP over angle sets like SetSweep.F90:113-116; throughput is size-normalised (unknowns/s), the sample size is stated in config.reference_sample",
     }
     print(json.dumps(line), flush=True)
 
@@ -186,6 +225,76 @@ def workload_config(args):
             "zones_per_domain": 24 * d * d * d, "groups": args.groups, "angles": 8 * args.polar * args.azimuthal,
             "l2_policy": "inputs (Psi 2x50 GB, STotal, Phi) are far larger than the 126 MB L2; no flush needed",
             "parallelism": f"spatial domains x{args.gpus}, psib exchange lagged one flux pass"}
+
+
+# ---------------------------------------------------------------------------
+def _parity_domain(teton, r, N, device, G=8):
+    """One small mesh domain (2 x 2 x 2 tiles of the N-domain tiled mesh) with seeded random state, built by the library alone."""
+    mesh = M.tiled_mesh((2, 2, 2), rank=r, size=N)
+    ctx = teton.SweepContext.from_mesh(mesh, G, device=device)
+    ctx.compute_geometry(mesh.px)
+    NA = ctx.build_product_quadrature(1, 2, 1)
+    for b in mesh.boundaries:
+        if b.bc_type == M.BC_SHARED:
+            ctx.add_shared_boundary(b.neighbor, b.first_elem, b.n_elem)
+    ctx.build_schedule()
+    rng = np.random.default_rng(4242 + r)
+    nz, nc, nb = mesh.nzones, mesh.ncornr, mesh.nbelem
+    tau = 3.0
+    ctx.upload_state(0.5 + rng.random((NA, nc, G)), 0.5 + rng.random((NA, nb, G)), tau + 20.0 * rng.random((nz, G)), rng.random((nc, G)), tau)
+    return ctx
+
+
+def nccl_parity_check(teton, torch, dist, rank, world, local):
+    """Correctness of the multi-GPU path, checked on every rank before anything is timed: a small decomposed problem swept over the
+    real NCCL communicator (psib rows by ncclSend/ncclRecv, convergence by ncclAllReduce) must give the PhiTotal / PsiB / Psi that the
+    same library computes with all `world` domains inside one process (in-process transport, which tests/test_gpu_exchange.py pins to
+    the lock-step oracle at 2, 4 and 8 domains).  Returns the worst relative difference over ranks (expected 0: same kernels, same data)."""
+    ctx = _parity_domain(teton, rank, world, local)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(teton.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.set_comm(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    ctx.build_exchange()
+    local_ctxs = [_parity_domain(teton, r, world, local) for r in range(world)]
+    teton.connect_local(local_ctxs)
+
+    def group(fn):
+        out, err = [None] * world, [None] * world
+
+        def work(r):
+            try:
+                out[r] = fn(local_ctxs[r])
+            except BaseException as e:   # noqa: BLE001
+                err[r] = e
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+    group(lambda c: c.build_exchange())
+    worst = 0.0
+    for save, iters in ((False, 3), (True, 1)):
+        it = ctx.sweep(save, iters, 1e-6)
+        its = group(lambda c: c.sweep(save, iters, 1e-6))
+        assert its[rank] == it, f"rank {rank}: {it} flux passes over NCCL, {its[rank]} in process"
+        ref = local_ctxs[rank]
+        for a, b in ((ctx.download_phi(), ref.download_phi()), (ctx.download_psib(), ref.download_psib()), (ctx.download_psi(), ref.download_psi())):
+            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))))
+    ctx.close()
+    for c in local_ctxs:
+        c.close()
+    t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t.item())
+    if not worst <= 1e-13:
+        raise SystemExit(f"NCCL parity check failed: worst relative difference {worst:.3e} between the NCCL and the in-process run")
+    return worst
 
 
 # ---------------------------------------------------------------------------
@@ -201,6 +310,7 @@ def main():
     ap.add_argument("--azimuthal", type=int, default=2)
     ap.add_argument("--cpu-dims", type=int, default=0, help="tiles per side of the bounded CPU sample (default: 10 for the cpu_baseline leg, 8 per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing NCCL parity check (N > 1)")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -218,6 +328,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = {"checked": True, "what": "2x2x2-tile domains, 16 angles, 8 groups: Phi/PsiB/Psi over NCCL == in-process transport on every rank (3 flux passes + savePsi sweep)",
+                  "max_rel_diff": nccl_parity_check(teton, torch, dist, rank, world, local), "domains": world}
 
     def barrier():
         if world > 1:
@@ -312,6 +426,7 @@ def main():
             "e2e": {"value": total_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "what": "umt_control_sweep: Sigt, STotal from pinned host -> whole ControlSweep -> PhiTotal to pinned host (phi reduction and its D2H overlapped)"},
             "gpu_launches": launches,
+            "parity_checked": bool(parity), "parity": parity,
             "flux_passes_per_step": iters / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tpu * unknowns / 1e9) if tpu else None, "traffic_unit": "GB per launch",

@@ -117,6 +117,21 @@ int umt_init_teton(umt_ctx *ctx, const double *Trz, const double *groupBounds, d
 int umt_set_boundary_sources(umt_ctx *ctx);   /* control/setBoundarySources.F90:42 without source profiles: PsiB = 0 */
 int umt_init_phi_total(umt_ctx *ctx, const double *volRatio);
 int umt_init_radiation_field(umt_ctx *ctx);
+/* initCyclePsi alone (control/constructDynMemory.F90:56-109): Set%cyclePsi(:,m) <- Psi(:,c,angle) for the corners on the cycle
+   lists.  A caller that uploads Psi and installs new schedules every cycle (umt_b200/fortran/SetSweep_B200.F90) calls it after the
+   upload, as the reference's initializeRadiationField does.  (The library also re-seeds by itself when a cycle list changes.) */
+int umt_init_cycle_psi(umt_ctx *ctx);
+
+/* ---- device memory of the angular flux -------------------------------------- */
+/* The reference holds Set%Psi once plus a one-angle scratch Set%Psi1 (mods/SetData_mod.F90:157,164).  So does this library on 3-D
+   meshes without cycle lists, direct-solve zones, reflecting boundaries or staged comm sets ("single-psi" layout): a savePsi sweep
+   writes Psi in place, the other sweeps keep Psi1 in a ring of angle batches whose PhiTotal contribution is tallied, in fixed angle
+   order, as the batches retire.  umt_set_psi1_ring chooses the ring size in angle batches (0 = as many as the free device memory
+   holds; a ring that holds every batch needs no in-sweep tally).  Every other problem keeps a full second buffer.
+   umt_get_psi_layout: info6 = {1 if single-psi, Psi1 slabs allocated, angles per batch, ring size in batches, batches,
+   angles tallied inside the sweep kernel}; bytes = device memory of Psi plus the Psi1 workspace. */
+int umt_set_psi1_ring(umt_ctx *ctx, int nBatches);
+int umt_get_psi_layout(umt_ctx *ctx, int *info6, double *bytes);
 
 /* ---- the hot path: rt/ControlSweep.F90:15-81 = SetSweep + getPhiTotal ---- */
 /* maxFluxIters / fluxTol: incidentFlux iteration control (SetSweep.F90:81-207,

@@ -32,3 +32,17 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_reference_arm_under_torchrun_uses_every_core_and_states_its_sample():
+    """torchrun exports OMP_NUM_THREADS=1; rank 0's CPU arm must still use the box's cores, split over the N domains, and say
+    which bounded sample it timed."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                          "--cpu-dims", "2", "--groups", "4"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    ncores = len(os.sched_getaffinity(0))
+    assert d["n_gpus"] == 2
+    assert d["cpu_baseline"]["cores"] == max(1, ncores // 2) * 2
+    assert d["config"]["reference_sample_dims"] == [2, 2, 2] and "-d 2,2,2" in d["config"]["reference_sample"]

@@ -15,6 +15,8 @@ struct Slot {
   int nz = 0, nc = 0, nb = 0, G = 0, maxcf = 0, maxCorner = 0;
   std::vector<double> phi;
 };
+// The reference's seam has no context argument (its own shim keeps static device buffers per stream id, GPU_SweepUCBxyz.cu:650-758),
+// so this table is the one piece of process-wide state in the library; the context API (include/umt_sweep.h) has none.
 Slot g_slot[kMaxStreams];
 std::mutex g_mu;                           // the reference's caller holds an omp critical around the call (SweepUCBxyzToGPU.F90:193)
 
@@ -46,6 +48,7 @@ extern "C" void gpu_sweepucbxyz(int *Angle, int *nHyperPlanes, int *nZonesInPlan
     int dev = 0;
     MUST_CUDA(nullptr, cudaGetDevice(&dev));
     MUST(nullptr, umt_ctx_create(dev, *ndim, nz, nc, nb, *maxcf, *maxCorner, G, &s.ctx));
+    s.ctx->force_legacy = true;   // the caller owns Psi1 and PsiB and sees them after every call: keep them in one full workspace
     s.nz = nz; s.nc = nc; s.nb = nb; s.G = G; s.maxcf = *maxcf; s.maxCorner = *maxCorner;
     s.phi.assign((size_t)G * nc, 0.0);
   }

@@ -548,7 +548,7 @@ extern "C" int umt_build_exchange(umt_ctx *ctx) {
     if (s.d_sendbuf) cudaFree(s.d_sendbuf);
     if (s.d_recvbuf) cudaFree(s.d_recvbuf);
     UMT_CUDA(ctx, cudaMalloc((void **)&s.d_partial, sizeof(double) * (size_t)NA * maxChunks));
-    UMT_CUDA(ctx, cudaMemset(s.d_partial, 0, sizeof(double) * (size_t)NA * maxChunks));
+    UMT_CUDA(ctx, cudaMemsetAsync(s.d_partial, 0, sizeof(double) * (size_t)NA * maxChunks, ctx->stream));
     UMT_CUDA(ctx, cudaMalloc((void **)&s.d_sendbuf, sizeof(double) * std::max<size_t>(s.send_rows * G, 1)));
     UMT_CUDA(ctx, cudaMalloc((void **)&s.d_recvbuf, sizeof(double) * std::max<size_t>(s.recv_rows * G, 1)));
   }
@@ -563,7 +563,7 @@ extern "C" int umt_build_exchange(umt_ctx *ctx) {
   for (int i = 0; i < 4; i++) {
     if (*arrs[i]) cudaFree(*arrs[i]);
     UMT_CUDA(ctx, cudaMalloc(arrs[i], sizeof(double) * std::max<size_t>(sizes[i], 1)));
-    UMT_CUDA(ctx, cudaMemset(*arrs[i], 0, sizeof(double) * std::max<size_t>(sizes[i], 1)));
+    UMT_CUDA(ctx, cudaMemsetAsync(*arrs[i], 0, sizeof(double) * std::max<size_t>(sizes[i], 1), ctx->stream));
   }
   if (!ctx->d_nNotConv) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_nNotConv, sizeof(int)));
   ctx->exch_dirty = false;
@@ -590,7 +590,7 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   for (size_t k = 0; k < nS; k++) {
     SharedBdy &s = ctx->shared[k];
     if (s.nChunks > 0) {
-      pack_tally_kernel<<<s.nChunks, 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
+      pack_tally_kernel<<<s.nChunks, 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
       ctx->last_launches++;
     }
     tally_finish_kernel<<<(NA + 127) / 128, 128, 0, ctx->stream>>>(s.d_partial, s.d_nChunksOfAngle, s.maxChunks, ctx->d_exitFlux + k * NA, NA);
@@ -626,7 +626,7 @@ int umt_exchange_begin_pass(umt_ctx *ctx) {
     SharedBdy &s = ctx->shared[k];
     const long long n = (long long)s.recv_rows * G;
     if (n > 0) {
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_recv_row, s.d_recvbuf, n, G);
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_recv_row, s.d_recvbuf, n, G);
       ctx->last_launches++;
     }
   }
@@ -802,7 +802,7 @@ extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
   if (nS > 0) {
     if (netFlux) std::copy(netFlux, netFlux + nS * NA, w.begin());
     else {
-      if (!ctx->d_psi1) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: no state on the device to tally the net flux from");
+      if (!ctx->d_psi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: no state on the device to tally the net flux from");
       r = umt_exchange_tally(ctx, 0.0);
       if (r) return r;
       std::vector<double> ex(nS * NA), in(nS * NA);
@@ -866,6 +866,7 @@ extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
         ctx->recvOrder[k][c * bps + i] = b;
         if (notDone[b]) depend[b] -= w[k * NA + b];
       }
+    // (a failure leaves the step loop through its !rc condition; the neighbours fail on their next exchange with this rank)
   }
   cudaFree(d_s); cudaFree(d_r);
   if (rc) { if (rc == UMT_ERR_CUDA) ctx->err = "umt_sweep_scheduler: CUDA copy failed"; return rc; }
@@ -935,7 +936,7 @@ int umt_exchange_stage(umt_ctx *ctx, int step) {
     const size_t o = s.stage_send_off[step];
     const long long n = (long long)(s.stage_send_off[step + 1] - o) * G;
     if (n > 0) {
-      gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_stage_send + o, s.d_sendbuf + o * G, n, G);
+      gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_stage_send + o, s.d_sendbuf + o * G, n, G);
       ctx->last_launches++;
     }
     sp[k] = s.d_sendbuf + o * G; sb[k] = sizeof(double) * (size_t)n;
@@ -950,7 +951,7 @@ int umt_exchange_stage(umt_ctx *ctx, int step) {
     const size_t ro = s.stage_recv_off[step];
     const long long n = (long long)(s.stage_recv_off[step + 1] - ro) * G;
     if (n > 0) {
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, s.d_stage_recv + ro, s.d_recvbuf + ro * G, n, G);
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_stage_recv + ro, s.d_recvbuf + ro * G, n, G);
       ctx->last_launches++;
     }
   }

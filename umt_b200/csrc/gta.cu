@@ -581,7 +581,7 @@ template <class T>
 int dalloc(umt_ctx *ctx, T **p, size_t n, bool zero = true) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   UMT_CUDA(ctx, cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
-  if (zero) UMT_CUDA(ctx, cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(n, 1)));
+  if (zero) UMT_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(T) * std::max<size_t>(n, 1), ctx->stream));
   return UMT_OK;
 }
 
@@ -956,11 +956,11 @@ extern "C" int umt_gta_sweep(umt_ctx *ctx, const double *P, const double *GreySo
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nb = ctx->nb;
   if (GreySource) UMT_CUDA(ctx, cudaMemcpy(g.d_greySource, GreySource, sizeof(double) * nc, cudaMemcpyHostToDevice));
-  if (!withSource) UMT_CUDA(ctx, cudaMemset(g.d_greySource, 0, sizeof(double) * nc));
+  if (!withSource) UMT_CUDA(ctx, cudaMemsetAsync(g.d_greySource, 0, sizeof(double) * nc, ctx->stream));
   UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
   if (nb > 0) {
     if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
-    else UMT_CUDA(ctx, cudaMemset(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng));
+    else UMT_CUDA(ctx, cudaMemsetAsync(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng, ctx->stream));
   }
   TRY(gta_device_sweep(ctx, g.d_P, g.d_PB));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -979,7 +979,7 @@ extern "C" int umt_gta_grey_sweep(umt_ctx *ctx, double *P, double *PsiB_gta, int
   UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
   if (nb > 0) {
     if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
-    else UMT_CUDA(ctx, cudaMemset(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng));
+    else UMT_CUDA(ctx, cudaMemsetAsync(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng, ctx->stream));
   }
   TRY(gta_grey_sweep(ctx, g.d_P, g.d_PB, withSource));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

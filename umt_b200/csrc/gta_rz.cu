@@ -434,7 +434,7 @@ template <class T>
 int dalloc2(umt_ctx *ctx, T **p, size_t n) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   UMT_CUDA(ctx, cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
-  UMT_CUDA(ctx, cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(n, 1)));
+  UMT_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(T) * std::max<size_t>(n, 1), ctx->stream));
   return UMT_OK;
 }
 

@@ -274,7 +274,7 @@ int umt_launch_reflect(umt_ctx *ctx, int stage) {
   int maxN = 1;
   for (const auto &R : ctx->refl) maxN = std::max(maxN, R.n);
   const unsigned gx = (unsigned)std::min<size_t>(((size_t)maxN * ctx->G + 255) / 256, 1024);
-  snreflect_kernel<<<dim3(gx, end - begin), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_reflOps + begin, end - begin, ctx->rows, ctx->nc, ctx->G);
+  snreflect_kernel<<<dim3(gx, end - begin), 256, 0, ctx->stream>>>(ctx->psib_buf(), ctx->d_reflOps + begin, end - begin, ctx->rows, ctx->nc, ctx->G);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches += 1;
   return UMT_OK;

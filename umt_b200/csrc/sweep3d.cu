@@ -46,10 +46,20 @@ struct Sweep3DParams {
   const WorkItem *items;
   int *counters;
   const double *psi, *stotal, *sigt;
-  double *psi1;
+  double *upBase;          // Psi1 workspace: slab pad1 of an item holds the corner rows its angle writes (legacy: d_psi1, slab = angle;
+                           // in place: d_psi, slab = angle; ring: the ring, slab = slot)
+  double *bBase;           // buffer whose slab tails are Set%PsiB (legacy: d_psi1, single-psi layout: d_psi); slab = angle
+  int ncG;                 // nc * G: row offsets at or beyond it address boundary elements
+  const double *weight;    // quadrature weights and PhiTotal for the phi-tally items (ring mode)
+  double *phi;
   const ZoneRec *recs;
   const int2 *zinfo;       // (NA, nz) in sweep order: first corner row, zone | numCorner << 28
 };
+
+__device__ __forceinline__ double dot3_seq(const double *om, const double *A) {
+  // DOT_PRODUCT order, no contraction: the signs decide incoming/outgoing exactly as on the host
+  return __dadd_rn(__dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])), __dmul_rn(om[2], A[2]));
+}
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
   int v;
@@ -60,13 +70,15 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 // ---------------------------------------------------------------------------
 // generic zone solve: SweepUCBxyz.F90:103-306 for one (zone, group)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a, int zone0, int g) {
+__device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a, int upIdx, int zone0, int g) {
   const int G = P.G, nc = P.nc;
-  const double om0 = P.omega[3 * a], om1 = P.omega[3 * a + 1], om2 = P.omega[3 * a + 2];
+  // omega . A without FMA contraction: the schedule (host snneed, plan_build_kernel) decided incident / exiting from the same
+  // uncontracted sums, and a face classified differently here would read a row the schedule does not order
+  const double om[3] = {P.omega[3 * a], P.omega[3 * a + 1], P.omega[3 * a + 2]};
   const size_t slab = (size_t)(nc + P.nb) * G;   // Psi, Psi1 are (G, nc+nb, NA): boundary rows follow the corner rows
   const double *psiA = P.psi + (size_t)a * slab;
-  double *psi1A = P.psi1 + (size_t)a * slab;
-  double *psibA = psi1A + (size_t)nc * G;
+  double *psi1A = P.upBase + (size_t)upIdx * slab;
+  double *psibA = P.bBase + (size_t)a * slab + (size_t)nc * G;
   const unsigned char *nextC = P.nextC + (size_t)a * nc;
   const int zone = (zone0 < 0 ? -zone0 : zone0) - 1;
   const int nCorner = P.numCorner[zone], c0 = P.cOffSet[zone];
@@ -90,7 +102,7 @@ __device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a
     double sa = 0.0;
     for (int f = 0; f < nCF; f++) {
       const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
-      afp[f] = om0 * A[0] + om1 * A[1] + om2 * A[2];
+      afp[f] = dot3_seq(om, A);
       psifp[f] = 0.0;
       if (afp[f] > 0.0) {
         sa += afp[f];
@@ -102,7 +114,7 @@ __device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a
     }
     for (int f = 0; f < nCF; f++) {
       const double *A = P.Aez + ((size_t)cc * MAXCF + f) * 3;
-      const double aez = om0 * A[0] + om1 * A[1] + om2 * A[2];
+      const double aez = dot3_seq(om, A);
       const int cez = P.cEZ[cc * MAXCF + f];
       if (cez > c) {
         if (aez > 0.0) { ez_exit[c][nxez[c]] = cez; coefpsi[c][nxez[c]] = aez; nxez[c]++; }
@@ -161,14 +173,14 @@ __device__ __forceinline__ void solve_zone_generic(const Sweep3DParams &P, int a
       const int row = P.cFP[cc * MAXCF + f];
       if (row >= nc) {
         const double *A = P.Afp + ((size_t)cc * MAXCF + f) * 3;
-        const double afp = om0 * A[0] + om1 * A[1] + om2 * A[2];
+        const double afp = dot3_seq(om, A);
         if (afp > 0.0) psibA[(size_t)(row - nc) * G + g] = src[c];
       }
     }
   }
 }
 
-__device__ __noinline__ void solve_zone_slow(const Sweep3DParams &P, int a, int zone0, int g) { solve_zone_generic(P, a, zone0, g); }
+__device__ __noinline__ void solve_zone_slow(const Sweep3DParams &P, int a, int upIdx, int zone0, int g) { solve_zone_generic(P, a, upIdx, zone0, g); }
 
 __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
   __shared__ int s_item;
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(128) sweep3d_generic_kernel(Sweep3DParams P) {
     const int npairs = (w.zend - w.zbeg) * G;
     for (int idx = threadIdx.x; idx < npairs; idx += blockDim.x) {
       const int zi = idx / G, g = idx - zi * G;
-      solve_zone_generic(P, w.angle, nextZ[w.zbeg + zi], g);
+      solve_zone_generic(P, w.angle, w.pad1, nextZ[w.zbeg + zi], g);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -210,11 +222,6 @@ struct PlanBuildParams {
   int *nSlow;     // [0] zones on the slow path, [1] zones on the canonical (register-resident) path
   int canon;      // try the canonical order
 };
-
-__device__ __forceinline__ double dot3_seq(const double *om, const double *A) {
-  // DOT_PRODUCT order, no contraction: the signs decide incoming/outgoing exactly as on the host
-  return __dadd_rn(__dadd_rn(__dmul_rn(om[0], A[0]), __dmul_rn(om[1], A[1])), __dmul_rn(om[2], A[2]));
-}
 
 // The in-zone corner graph of a hexahedron swept in a generic direction is the cube DAG: one source corner,
 // its three neighbours, their three pairwise common neighbours, one sink.  "Canonical" solve order numbers
@@ -478,7 +485,7 @@ constexpr int PLAN_ZMAX = 8;     // zones per item at most
 #define PLAN_NCW_DEF 4
 #endif
 constexpr int PLAN_NCW = PLAN_NCW_DEF;      // consumer warps per CTA
-constexpr int PLAN_CTL_BYTES = 768;         // barriers + per-stage metadata ahead of the stages
+constexpr int PLAN_CTL_BYTES = 896;         // barriers + per-stage metadata ahead of the stages
 constexpr int PLAN_LANES = PLAN_NCW * 32;
 
 // How the consumer warps of a CTA are grouped for a given group count (host side, once per context).
@@ -515,7 +522,9 @@ static PlanGeom plan_geom(int G, int NH) {
   return g;
 }
 
-struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, pad0, pad1, pad2; };
+// n: zones of the item; -1: sentinel (the engine is done); -2: phi-tally item (angle = first angle of the batch, upIdx = packed
+// slot / count / first flag, c0..c1 = its 16-byte columns of PhiTotal)
+struct StageMeta { int angle, n, signal_idx, wait_idx, wait_count, upIdx, c0, c1; };
 
 // Shared memory: barriers and per-stage metadata in the first PLAN_CTL_BYTES, then the stages.  One stage = one
 // work item: the TMA landing area of its Psi^n / STotal / Sigt rows, [zone][corner][G] (a zone's corner
@@ -527,6 +536,7 @@ struct PlanCtl {
   unsigned long long full[PLAN_MAX_STAGES], empty[PLAN_MAX_STAGES];
   StageMeta meta[PLAN_MAX_STAGES];
   int sigRing[PLAN_RING];        // signal_idx of the CTA's item k at k % PLAN_RING
+  int sig2Ring[PLAN_RING];       // its second counter (-1: none)
   volatile int issuedCount;      // real items issued so far (loader -> signaller)
   volatile int doneFlag;         // loader finished: issuedCount is final
   volatile int nSignaled;        // items whose completion is published (signaller -> loader)
@@ -552,7 +562,7 @@ __device__ __forceinline__ void sts_v2(unsigned addr, const V2 &v) {
 // contiguous run of 16-byte words, and the NH independent dependency chains interleave in the FP64 pipe.
 template <int NH>
 __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const ZoneEdge *__restrict__ &E, const int p, const int NC,
-                                            const V2 (&pfC)[3][NH], V2 (&pfN)[3][NH], const double *__restrict__ up, double *__restrict__ upw,
+                                            const V2 (&pfC)[3][NH], V2 (&pfN)[3][NH], double *__restrict__ upg, double *__restrict__ pbg, const int ncG,
                                             const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const V2 (&rsig)[NH], const unsigned flags,
                                             const unsigned hs, const int hg) {
   const int nout = R->nOut[p];
@@ -561,7 +571,8 @@ __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const
 #pragma unroll
     for (int k = 0; k < 3; k++)
       if (k < nn) {
-        const double *src = up + R->inOff[p + 1][k];
+        const int o = R->inOff[p + 1][k];
+        const double *src = (o >= ncG ? pbg : upg) + o;
 #pragma unroll
         for (int h = 0; h < NH; h++) pfN[k][h] = ld_l2(src + h * hg);
       }
@@ -628,7 +639,7 @@ __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const
   for (int h = 0; h < NH; h++) {
     psi[h].x = s[h].x * rcp_fast(sa + sv[h].x);
     psi[h].y = s[h].y * rcp_fast(sa + sv[h].y);
-    st_keep(upw + R->crow[p] + h * hg, psi[h]);
+    st_keep(upg + R->crow[p] + h * hg, psi[h]);
   }
 #pragma unroll
   for (int k = 0; k < 3; k++)
@@ -649,15 +660,15 @@ __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const
     for (int f = 0; f < 3; f++)
       if (em & (1u << f)) {
 #pragma unroll
-        for (int h = 0; h < NH; h++) st_keep(upw + R->exitOff[p][f] + h * hg, psi[h]);
+        for (int h = 0; h < NH; h++) st_keep(pbg + R->exitOff[p][f] + h * hg, psi[h]);
       }
   }
   E += nout;
 }
 
 template <int NH>
-__device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ psi1Ag,
-                                                const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const unsigned hs, const int hg) {
+__device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ upg, double *__restrict__ pbg,
+                                                const int ncG, const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const unsigned hs, const int hg) {
   const unsigned flags = R->flags;
   const int NC = (int)(flags & 15u);
   // Q = STotal + tau Psi^n, src = V Q (SweepUCBxyz.F90:119-126), in place over the landed rows
@@ -691,14 +702,16 @@ __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec 
 #pragma unroll
     for (int k = 0; k < 3; k++)
       if (k < n0) {
+        const int o = R->inOff[0][k];
+        const double *src = (o >= ncG ? pbg : upg) + o;
 #pragma unroll
-        for (int h = 0; h < NH; h++) pfA[k][h] = ld_l2(psi1Ag + R->inOff[0][k] + h * hg);
+        for (int h = 0; h < NH; h++) pfA[k][h] = ld_l2(src + h * hg);
       }
   }
 #pragma unroll 1
   for (int p = 0; p < NC; p += 2) {
-    plan_corner<NH>(R, E, p, NC, pfA, pfB, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags, hs, hg);
-    if (p + 1 < NC) plan_corner<NH>(R, E, p + 1, NC, pfB, pfA, psi1Ag, psi1Ag, qs, ss, sig, rsig, flags, hs, hg);
+    plan_corner<NH>(R, E, p, NC, pfA, pfB, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
+    if (p + 1 < NC) plan_corner<NH>(R, E, p + 1, NC, pfB, pfA, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
   }
 }
 
@@ -720,8 +733,8 @@ __device__ __forceinline__ V2 ldcg_v2(const double *p) {
 // An edge whose opposite FP face is not incident uses the same closure with N = 0, which is algebraically the
 // reference's sez = aez (Q - Q_cez) / (2 sigma) (SweepUCBxyz.F90:254-256).
 template <int NH>
-__device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ psi1Ag,
-                                                 const unsigned char *__restrict__ colPsi, const unsigned char *__restrict__ colSt,
+__device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ upg, double *__restrict__ pbg,
+                                                 const int ncG, const unsigned char *__restrict__ colPsi, const unsigned char *__restrict__ colSt,
                                                  const V2 (&sig)[NH], const unsigned hs, const int hg) {
   V2 Q[MAXC][NH], S[MAXC][NH];
   V2 pf[MAXC][3][NH];   // only the slots k < cn_nout(p) exist
@@ -731,7 +744,8 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
     const int nin = R->nIn[p];
 #pragma unroll
     for (int k = 0; k < cn_nout(p); k++) {
-      const double *src = psi1Ag + R->inOff[p][k];
+      const int o = R->inOff[p][k];
+      const double *src = (o >= ncG ? pbg : upg) + o;
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         pf[p][k][h].x = 0.0; pf[p][k][h].y = 0.0;
@@ -758,7 +772,8 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
 #pragma unroll
       for (int pp = 4; pp < 7; pp++) {
         const int nin = R->nIn[pp];
-        const double *src = psi1Ag + R->inOff[pp][0];
+        const int o = R->inOff[pp][0];
+        const double *src = (o >= ncG ? pbg : upg) + o;
 #pragma unroll
         for (int h = 0; h < NH; h++) {
           pf[pp][0][h].x = 0.0; pf[pp][0][h].y = 0.0;
@@ -783,7 +798,8 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
       for (int k = cn_nout(p); k < 3; k++)
         if (k < (int)R->nIn[p]) {
           const double af = R->inAfp[p][k];
-          const double *src = psi1Ag + R->inOff[p][k];
+          const int o = R->inOff[p][k];
+          const double *src = (o >= ncG ? pbg : upg) + o;
 #pragma unroll
           for (int h = 0; h < NH; h++) {
             const V2 v = ldcg_v2(src + h * hg);
@@ -825,7 +841,7 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
     for (int h = 0; h < NH; h++) {
       psi[h].x = s[h].x * rcp_fast(sa + sv[h].x);
       psi[h].y = s[h].y * rcp_fast(sa + sv[h].y);
-      st_keep_free(psi1Ag + R->crow[p] + h * hg, psi[h]);
+      st_keep_free(upg + R->crow[p] + h * hg, psi[h]);
     }
 #pragma unroll
     for (int k = 0; k < cn_nout(p); k++) {
@@ -843,9 +859,41 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
       for (int f = 0; f < 3; f++)
         if (em & (1u << f)) {
 #pragma unroll
-          for (int h = 0; h < NH; h++) st_keep_free(psi1Ag + R->exitOff[p][f] + h * hg, psi[h]);
+          for (int h = 0; h < NH; h++) st_keep_free(pbg + R->exitOff[p][f] + h * hg, psi[h]);
         }
     }
+  }
+}
+
+// Phi-tally item (ring mode): PhiTotal(columns c0..c1) (+)= sum over the nA angles of a retiring batch of w_a Psi1_a, the angles in
+// ascending order on top of the running sum, so that PhiTotal ends up bit-identical to the fixed-order sum over all angles
+// (control/getPhiTotal_OMPOL.F90:134-160 + SweepUCBxyz.F90:270).  The batch's Psi1 slabs sit in consecutive ring slots.  Everything is
+// read and written through L2 (ld.cg / st.cg): other SMs wrote these rows, and ring slots are reused.
+__device__ __noinline__ void phi_tally_item(const Sweep3DParams &P, const int a0, const int packed, const int c0, const int c1, const int elane,
+                                            const int nLanes) {
+  const int slot0 = packed & 0xffff, nA = (packed >> 16) & 0xff;
+  const bool first = (packed >> 30) & 1;
+  const size_t slab = (size_t)(P.nc + P.nb) * P.G;
+  const double *src = P.upBase + (size_t)slot0 * slab;
+  for (int c = c0 + elane; c < c1; c += 2 * nLanes) {
+    const int cB = c + nLanes;
+    const bool hasB = cB < c1;
+    double2 sA = make_double2(0.0, 0.0), sB = make_double2(0.0, 0.0);
+    if (!first) {
+      sA = __ldcg(reinterpret_cast<const double2 *>(P.phi) + c);
+      if (hasB) sB = __ldcg(reinterpret_cast<const double2 *>(P.phi) + cB);
+    }
+#pragma unroll 4
+    for (int i = 0; i < nA; i++) {
+      const double wa = P.weight[a0 + i];
+      const double2 vA = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)i * slab) + c);
+      double2 vB = make_double2(0.0, 0.0);
+      if (hasB) vB = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)i * slab) + cB);
+      sA.x = sA.x + wa * vA.x; sA.y = sA.y + wa * vA.y;
+      sB.x = sB.x + wa * vB.x; sB.y = sB.y + wa * vB.y;
+    }
+    __stcg(reinterpret_cast<double2 *>(P.phi) + c, sA);
+    if (hasB) __stcg(reinterpret_cast<double2 *>(P.phi) + cB, sB);
   }
 }
 
@@ -894,7 +942,7 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     int2 qZ = make_int2(0, 0), nZ = make_int2(0, 0);   // info of zone l % zpi of that item
     int qCount = 0, qPos = 0, nCount = 0, nPhase = 0, nT = 0;
     bool exhausted = false;                   // no tickets left beyond the next batch
-    qW.angle = qW.zbeg = qW.zend = qW.wait_idx = qW.wait_count = qW.signal_idx = 0; nW = qW;
+    qW.angle = qW.zbeg = qW.zend = qW.wait_idx = qW.wait_count = qW.signal_idx = qW.pad0 = qW.pad1 = 0; nW = qW;
     auto fetch_step = [&]() {                 // one dependent step of fetching the next batch
       if (nPhase == 0) {
         if (lane == 0) nT = atomicAdd(&P.counters[0], QB);
@@ -905,7 +953,7 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
         if (myItem < nCount) nW = P.items[nT + myItem];
         nPhase = 2;
       } else if (nPhase == 2) {
-        if (myItem < nCount && myZone < nW.zend - nW.zbeg) nZ = P.zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
+        if (myItem < nCount && nW.angle >= 0 && myZone < nW.zend - nW.zbeg) nZ = P.zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
         nPhase = 3;
       }
     };
@@ -945,23 +993,30 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
             w.angle = __shfl_sync(0xffffffffu, qW.angle, srcLane); w.zbeg = __shfl_sync(0xffffffffu, qW.zbeg, srcLane);
             w.zend = __shfl_sync(0xffffffffu, qW.zend, srcLane); w.wait_idx = __shfl_sync(0xffffffffu, qW.wait_idx, srcLane);
             w.wait_count = __shfl_sync(0xffffffffu, qW.wait_count, srcLane); w.signal_idx = __shfl_sync(0xffffffffu, qW.signal_idx, srcLane);
+            w.pad0 = __shfl_sync(0xffffffffu, qW.pad0, srcLane); w.pad1 = __shfl_sync(0xffffffffu, qW.pad1, srcLane);
             int2 zi;
             zi.x = __shfl_sync(0xffffffffu, qZ.x, (srcLane + lane) & 31); zi.y = __shfl_sync(0xffffffffu, qZ.y, (srcLane + lane) & 31);
             qPos++;
-            const int n = w.zend - w.zbeg;
-            const size_t first = (size_t)w.angle * P.nz + w.zbeg;
+            const bool tally = w.angle < 0;      // phi-tally item: nothing to land, the engine streams straight from global memory
+            const int n = tally ? 0 : w.zend - w.zbeg;
+            const size_t first = tally ? 0 : (size_t)w.angle * P.nz + w.zbeg;
             unsigned bytes = 0;
             if (lane < n) bytes = rowBytes * (2u * ((unsigned)zi.y >> 28) + 1u);
             bytes = __reduce_add_sync(0xffffffffu, bytes) + (unsigned)(n * sizeof(ZoneRec));
             unsigned char *st = stages + (size_t)sFill * P.stageBytes;
             if (lane == 0) {
-              S.meta[sFill].angle = w.angle; S.meta[sFill].n = n;
+              S.meta[sFill].angle = tally ? -1 - w.angle : w.angle; S.meta[sFill].n = tally ? -2 : n;
               S.meta[sFill].wait_idx = w.wait_idx; S.meta[sFill].wait_count = w.wait_count;
+              S.meta[sFill].upIdx = w.pad1; S.meta[sFill].c0 = w.zbeg; S.meta[sFill].c1 = w.zend;
               S.sigRing[nIssued & (PLAN_RING - 1)] = w.signal_idx;
+              S.sig2Ring[nIssued & (PLAN_RING - 1)] = w.pad0;
               __threadfence_block();
               S.issuedCount = nIssued + 1;
-              mbar_arrive_expect_tx(&S.full[sFill], bytes);
-              tma_load_1d_hint(st + P.offRecs, P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[sFill], L2_EVICT_FIRST);
+              if (tally) mbar_arrive(&S.full[sFill]);
+              else {
+                mbar_arrive_expect_tx(&S.full[sFill], bytes);
+                tma_load_1d_hint(st + P.offRecs, P.recs + first, (unsigned)(n * sizeof(ZoneRec)), &S.full[sFill], L2_EVICT_FIRST);
+              }
             }
             __syncwarp();
             if (lane < n) {
@@ -1010,8 +1065,11 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
         if (++s2 == NS) { s2 = 0; p2 ^= 1u; }
       }
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      for (int j = 0; j < m; j++)
+      for (int j = 0; j < m; j++) {
         asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + S.sigRing[(k + j) & (PLAN_RING - 1)]]) : "memory");
+        const int s2i = S.sig2Ring[(k + j) & (PLAN_RING - 1)];
+        if (s2i >= 0) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + s2i]) : "memory");
+      }
       k += m; sg = s2; par = p2;
       S.nSignaled = k;
     }
@@ -1029,23 +1087,26 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     const int s = k % NS;
     mbar_wait(&S.full[s], (k / NS) & 1);
     const StageMeta m = S.meta[s];
-    if (m.n < 0) break;
-    if (zi < m.n) {
+    if (m.n == -1) break;
+    if (m.n == -2) {
+      phi_tally_item(P, m.angle, m.upIdx, m.c0, m.c1, elane, 32 * wpe);
+    } else if (zi < m.n) {
       unsigned char *st = stages + (size_t)s * P.stageBytes;
       const ZoneRec *R = reinterpret_cast<const ZoneRec *>(st + P.offRecs) + zi;
-      double *psi1Ag = P.psi1 + (size_t)m.angle * slab + 2 * li;
+      double *upg = P.upBase + (size_t)m.upIdx * slab + 2 * li;   // corner rows of this angle's Psi1
+      double *pbg = P.bBase + (size_t)m.angle * slab + 2 * li;    // boundary-element rows (Set%PsiB(:,:,angle))
       if (R->flags & ZREC_SLOW) {
         for (int h = 0; h < NH; h++) {
-          solve_zone_slow(P, m.angle, R->zone0, 2 * (li + h * LZ));
-          solve_zone_slow(P, m.angle, R->zone0, 2 * (li + h * LZ) + 1);
+          solve_zone_slow(P, m.angle, m.upIdx, R->zone0, 2 * (li + h * LZ));
+          solve_zone_slow(P, m.angle, m.upIdx, R->zone0, 2 * (li + h * LZ) + 1);
         }
       } else {
         const unsigned col = (unsigned)(zi * MAXC * Gv + li) * 16u;
         V2 sig[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) sig[h] = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li + h * LZ) * 16);
-        if (R->flags & ZREC_CANON) solve_zone_canon<NH>(tau, R, psi1Ag, st + col, st + P.offSt + col, sig, hs, hg);
-        else solve_zone_plan<NH>(tau, R, psi1Ag, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
+        if (R->flags & ZREC_CANON) solve_zone_canon<NH>(tau, R, upg, pbg, P.ncG, st + col, st + P.offSt + col, sig, hs, hg);
+        else solve_zone_plan<NH>(tau, R, upg, pbg, P.ncG, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
       }
     }
     __syncwarp();
@@ -1063,7 +1124,9 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
   P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
-  P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1;
+  P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt;
+  P.upBase = ctx->d_psi1; P.bBase = ctx->psib_buf(); P.ncG = ctx->nc * ctx->G;
+  P.weight = ctx->d_weight; P.phi = ctx->d_phi;
   P.recs = ctx->d_recs; P.zinfo = ctx->d_zinfo;
 }
 
@@ -1083,7 +1146,7 @@ int umt_build_plan3d(umt_ctx *ctx) {
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_recs, n * sizeof(ZoneRec)));
   int *d_nslow = nullptr;
   UMT_CUDA(ctx, cudaMalloc((void **)&d_nslow, 2 * sizeof(int)));
-  UMT_CUDA(ctx, cudaMemset(d_nslow, 0, 2 * sizeof(int)));
+  UMT_CUDA(ctx, cudaMemsetAsync(d_nslow, 0, 2 * sizeof(int), ctx->stream));
   PlanBuildParams B;
   B.nc = ctx->nc; B.nb = ctx->nb; B.nz = ctx->nz; B.NA = ctx->NA; B.G = ctx->G;
   B.numCorner = ctx->d_numCorner; B.cOffSet = ctx->d_cOffSet; B.nCFaces = ctx->d_nCFaces; B.cFP = ctx->d_cFP; B.cEZ = ctx->d_cEZ;
@@ -1116,7 +1179,7 @@ static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
   return UMT_OK;
 }
 
-int umt_launch_sweep3d(umt_ctx *ctx) {
+int umt_launch_sweep3d(umt_ctx *ctx, int savePsi) {
   if (ctx->maxCorner > MAXC || ctx->maxcf != MAXCF)
     UMT_FAIL(ctx, UMT_ERR_ARG, "3-D sweep supports maxCorner <= %d and maxcf == %d (got %d, %d)", MAXC, MAXCF,
              ctx->maxCorner, ctx->maxcf);
@@ -1124,16 +1187,31 @@ int umt_launch_sweep3d(umt_ctx *ctx) {
   fill_params(ctx, P);
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   if (ctx->use_plan && !ctx->d_recs) UMT_FAIL(ctx, UMT_ERR_STATE, "sweep plan not built");
+  if (!ctx->d_psi1) UMT_FAIL(ctx, UMT_ERR_STATE, "Psi1 workspace not allocated");
+  if (ctx->single_psi) {
+    // single-psi layout (one stage, plan kernel): Set%PsiB is the tail of every Psi slab; a savePsi sweep writes Psi in place,
+    // the other sweeps write the Psi1 ring and tally the batches that have to leave it
+    P.bBase = ctx->d_psi;
+    P.upBase = savePsi ? ctx->d_psi : ctx->d_psi1;
+    if (!savePsi && ctx->nTallied > 0) {
+      P.items = ctx->d_itemsRing;
+      P.nItems = ctx->nItemsRing;
+      int r = launch_plan(ctx, P);
+      if (r) return r;
+      ctx->last_launches += 1;
+      return UMT_OK;
+    }
+  }
   // one launch per reflection stage (a single stage unless the domain has reflecting boundaries)
   for (int s = 0; s < ctx->nStages; s++) {
     const int begin = ctx->stageItemBegin[s], end = ctx->stageItemBegin[s + 1];
-    if (end == begin) continue;
     if (s > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist
     int r = UMT_OK;
     if (ctx->have_comm_order && !ctx->shared.empty()) r = umt_exchange_stage(ctx, s);   // SendFlux / RecvFlux of this sweep step
     if (r) return r;
     r = umt_launch_reflect(ctx, s);   // snreflect for the incident angles of this stage
     if (r) return r;
+    if (end == begin) continue;       // nothing to sweep at this step here; the neighbours' send/recv above were still matched
     P.items = ctx->d_items + begin;
     P.nItems = end - begin;
     if (ctx->use_plan) {

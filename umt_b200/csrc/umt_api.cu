@@ -8,7 +8,8 @@
 
 #include "umt_internal.h"
 
-static std::string g_create_error;
+// error text of a failed umt_ctx_create on this thread (there is no context to hold it yet)
+static thread_local std::string g_create_error;
 
 extern "C" const char *umt_version(void) { return "umt_b200 0.1.0 (sm_100a)"; }
 
@@ -72,8 +73,10 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
     if (const char *ev = getenv("UMT_L2_PERSIST_MB")) want = std::min(want, (size_t)std::max(0, atoi(ev)) << 20);
     if (ndim != 3) want = 0;   // only the 3-D plan kernel uses evict_last; the r-z kernels lose 7 % to a smaller normal L2
     if (want > 0) {
+      size_t before = 0;
+      if (cudaDeviceGetLimit(&before, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); before = 0; }
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
-      else { ctx->l2_persist = true; ctx->l2_persist_bytes = want; }
+      else { ctx->l2_persist = true; ctx->l2_persist_bytes = want; ctx->l2_persist_before = before; }
     }
     if (getenv("UMT_VERBOSE")) fprintf(stderr, "umt: persisting L2 max %d MB, set-aside %zu MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20, want >> 20, prop.l2CacheSize >> 20);
   }
@@ -91,10 +94,12 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
                   ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo, ctx->d_angDerivFac, ctx->d_tauW1, ctx->d_tauW2,
                   ctx->d_start, ctx->d_finishNext, ctx->d_level, ctx->d_reflOps, ctx->d_rzLevelAngles, ctx->d_rzPlaneOff, ctx->d_rzNHyp,
-                  ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad};
+                  ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad, ctx->d_itemsRing, ctx->d_tailSlot, ctx->d_tailW};
   for (void *p : ptrs) if (p) cudaFree(p);
   umt_exchange_release(ctx);
   umt_gta_release(ctx);
+  // hand the device-wide L2 set-aside back (the last 3-D context to go restores what it found)
+  if (ctx->l2_persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_before) != cudaSuccess) cudaGetLastError();
   for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -297,6 +302,9 @@ extern "C" int umt_get_schedule(umt_ctx *ctx, int angle, int *zonesInPlane, int 
   return UMT_OK;
 }
 
+static int ensure_layout(umt_ctx *ctx);
+static int seed_cycle_psi(umt_ctx *ctx);
+
 // Translate the per-angle hyperplane lists into the device work-item list.
 static int finalize_schedule(umt_ctx *ctx) {
   if (!ctx->sched_dirty) return UMT_OK;
@@ -328,6 +336,18 @@ static int finalize_schedule(umt_ctx *ctx) {
   if (const char *e = getenv("UMT_PLAN_NH")) ctx->plan_nh = (atoi(e) == 2 && ctx->G % 4 == 0) ? 2 : 1;
   ctx->plan_ncw = 4;
   if (const char *e = getenv("UMT_PLAN_WARPS")) ctx->plan_ncw = atoi(e) == 8 ? 8 : 4;
+  TRY(dev_alloc_copy(ctx, &ctx->d_nextZ, h_nextZ.data(), h_nextZ.size()));
+  TRY(dev_alloc_copy(ctx, &ctx->d_nextC, h_nextC.data(), h_nextC.size()));
+  if (ctx->use_plan && ctx->device >= 0) {   // the plan records first: the Psi1 ring below is sized by what is left of the HBM
+    std::vector<int2> zinfo((size_t)NA * nz);
+    for (int a = 0; a < NA; a++)
+      for (int i = 0; i < nz; i++) {
+        const int z = std::abs(h_nextZ[(size_t)a * nz + i]) - 1;
+        zinfo[(size_t)a * nz + i] = make_int2(ctx->h_cOffSet[z], z | (ctx->h_numCorner[z] << 28));
+      }
+    TRY(dev_alloc_copy(ctx, &ctx->d_zinfo, zinfo.data(), zinfo.size()));
+    TRY(umt_build_plan3d(ctx));
+  }
   int pairsRZ = 64;   // one (zone, group) pair per thread of the 64-thread RZ CTA (sweeprz.cu RZ_BLOCK)
   if (const char *e = getenv("UMT_PAIRS_PER_ITEM")) pairsRZ = std::max(1, std::min(64, atoi(e)));
   const int zpi = ctx->ndim == 3 ? umt_sweep3d_zones_per_item(ctx) : std::max(1, pairsRZ / ctx->G);
@@ -379,9 +399,48 @@ static int finalize_schedule(umt_ctx *ctx) {
   // image.  Angles are therefore swept in stages (umt_reflect_stages); all angles of a stage are independent.
   TRY(umt_reflect_stages(ctx));
   ctx->stageItemBegin.assign(ctx->nStages + 1, 0);
+  // Psi storage layout (umt_internal.h): one Psi + a ring for Psi1 whenever the sweep never needs an angle's previous Psi1 and all
+  // angles go in one launch; otherwise the two-buffer layout.
+  {
+    bool single = ctx->ndim == 3 && ctx->use_plan && ctx->device >= 0 && !ctx->force_legacy && ctx->nStages == 1 && !ctx->have_comm_order;
+    for (int a = 0; a < NA && single; a++) single = ctx->nHyp[a] > 0 && ctx->numCycles[a] == 0 && ctx->nBad[a] == 0;
+    if (const char *e = getenv("UMT_PSI_LAYOUT")) if (!strcmp(e, "legacy")) single = false;
+    ctx->single_psi_wanted = single;
+    ctx->ringBatchesAuto = 0;
+    if (single) {
+      // as many angle batches as the free HBM holds next to what is already allocated (the current workspace counts as free)
+      size_t freeB = 0, totalB = 0;
+      UMT_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
+      const size_t slabB = sizeof(double) * (size_t)(nc + ctx->nb) * ctx->G;
+      freeB += (size_t)ctx->psi1Slots * slabB;
+      const size_t reserve = ((size_t)2 << 30) + totalB / 50;
+      const size_t slots = freeB > reserve ? (freeB - reserve) / slabB : 0;
+      ctx->ringBatchesAuto = (int)std::min<size_t>((size_t)(NA + K - 1) / K, slots / (size_t)K);
+      if (const char *e = getenv("UMT_RING_BATCHES")) ctx->ringBatchesAuto = std::max(1, atoi(e));
+    }
+  }
+  auto make_item = [&](int a, int p, int k, int upIdx) {
+    const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
+    WorkItem w;
+    w.angle = a;
+    w.zbeg = z0 + k * zpi;
+    w.zend = std::min(z0 + n, w.zbeg + zpi);
+    w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
+    w.wait_count = p > 0 ? planeSignals[a][p - 1] : 0;
+    w.signal_idx = a * maxHyp + p;
+    w.pad0 = -1;
+    w.pad1 = upIdx;
+    return w;
+  };
+  std::vector<WorkItem> ringItems;
+  ctx->angleBatch = K; ctx->nBatches = 0; ctx->ringBatches = 0; ctx->nTallied = 0;
+  ctx->slotOfAngle.assign(NA, 0);
+  for (int a = 0; a < NA; a++) ctx->slotOfAngle[a] = a;
+  int nExtraCounters = 0;
   if (ctx->ndim == 2) {
     TRY(umt_build_items_rz(ctx, items, zpi));   // PsiM chain within a xi-level: own ordering; grouped by reflection stage
   } else {
+    // every angle's Psi1 in its own slab (legacy layout, and the in-place savePsi sweep of the single-psi layout)
     for (int s = 0; s < ctx->nStages; s++) {
       std::vector<int> ang;
       for (int a2 = 0; a2 < NA; a2++) if (ctx->stageOf[a2] == s) ang.push_back(a2);
@@ -393,39 +452,96 @@ static int finalize_schedule(umt_ctx *ctx) {
           const int a = ang[ia];
           const int p = lev - (ia / K) * delta;
           if (p < 0 || p >= ctx->nHyp[a]) continue;
-          const int n = ctx->zonesInPlane[a][p], z0 = planeStart[a][p];
-          for (int k = 0; k < nItemsPlane[a][p]; k++) {
-            WorkItem w;
-            w.angle = a;
-            w.zbeg = z0 + k * zpi;
-            w.zend = std::min(z0 + n, w.zbeg + zpi);
-            w.wait_idx = p > 0 ? a * maxHyp + p - 1 : -1;
-            w.wait_count = p > 0 ? planeSignals[a][p - 1] : 0;
-            w.signal_idx = a * maxHyp + p;
-            w.pad0 = w.pad1 = 0;
-            items.push_back(w);
-          }
+          for (int k = 0; k < nItemsPlane[a][p]; k++) items.push_back(make_item(a, p, k, a));
         }
       ctx->stageItemBegin[s + 1] = (int)items.size();
+    }
+    // Single-psi layout, non-final sweeps: Psi1 lives in a ring of ringBatches * K slabs.  Batch b (angles bK .. bK+K-1) writes the
+    // slots (b mod ringBatches) K + i; once its last plane is done its Psi1 is tallied into PhiTotal by phi-tally items spread over
+    // the following levels, and batch b + ringBatches may then reuse the slots.  Counters past the plane counters: gate[b] (bumped
+    // by every sweep item of batch b and by every tally item of batch b-1: a tally item of batch b waits for all of them, which
+    // also keeps the tallies in batch order) and done[b] (bumped by the tally items of batch b: plane 0 of batch b + ringBatches
+    // waits for it).  Every dependency of an item sits earlier in the ticket order, so the launch cannot deadlock.
+    if (ctx->single_psi_wanted) {
+      const int nB = (NA + K - 1) / K;
+      int Rb = ctx->ringBatchesWanted > 0 ? ctx->ringBatchesWanted : ctx->ringBatchesAuto;
+      Rb = std::max(1, std::min(Rb, nB));
+      if (Rb < nB && Rb < 2) Rb = std::min(2, nB);       // a retiring batch and a running one at the very least
+      ctx->nBatches = nB; ctx->ringBatches = Rb;
+      const int tallyB = nB - Rb;                          // batches 0 .. tallyB-1 are tallied by the sweep kernel itself
+      ctx->nTallied = std::min(NA, tallyB * K);
+      for (int a = 0; a < NA; a++) ctx->slotOfAngle[a] = ((a / K) % Rb) * K + a % K;
+      if (tallyB > 0) {
+        const int columns = (int)(((size_t)nc * ctx->G) / 2);   // use_plan: G even
+        int CH = 2048;
+        if (const char *e = getenv("UMT_PHI_CHUNK")) CH = std::max(64, atoi(e));
+        const int nPhi = (columns + CH - 1) / CH;
+        const int spread = std::max(1, delta / 2);
+        const int gateBase = NA * maxHyp, doneBase = gateBase + nB;
+        nExtraCounters = 2 * nB;
+        std::vector<int> start(nB), tend(nB, 0), nItemsBatch(nB, 0);
+        for (int b = 0; b < nB; b++) {
+          for (int a = b * K; a < std::min(NA, (b + 1) * K); a++)
+            for (int p = 0; p < ctx->nHyp[a]; p++) nItemsBatch[b] += nItemsPlane[a][p];
+          start[b] = b * delta;
+          if (b > 0) start[b] = std::max(start[b], start[b - 1]);
+          if (b >= Rb) start[b] = std::max(start[b], tend[b - Rb] + spread);       // its slots' previous tenant is fully tallied
+          tend[b] = start[b] + maxHyp;                                            // first level of batch b's tally items
+          if (b > 0) tend[b] = std::max(tend[b], tend[b - 1] + spread);
+        }
+        int nLevels = 0;
+        for (int b = 0; b < nB; b++) nLevels = std::max(nLevels, std::max(start[b] + maxHyp, b < tallyB ? tend[b] + spread : 0));
+        std::vector<WorkItem> lvSweep, lvPhi;
+        for (int lev = 0; lev < nLevels; lev++) {
+          lvSweep.clear(); lvPhi.clear();
+          for (int a = 0; a < NA; a++) {
+            const int b = a / K, p = lev - start[b];
+            if (p < 0 || p >= ctx->nHyp[a]) continue;
+            for (int k = 0; k < nItemsPlane[a][p]; k++) {
+              WorkItem w = make_item(a, p, k, ctx->slotOfAngle[a]);
+              if (p == 0 && b >= Rb && b - Rb < tallyB) { w.wait_idx = doneBase + b - Rb; w.wait_count = nPhi; }
+              if (b < tallyB) w.pad0 = gateBase + b;
+              lvSweep.push_back(w);
+            }
+          }
+          for (int b = 0; b < tallyB; b++) {
+            const int l = lev - tend[b];
+            if (l < 0 || l >= spread) continue;
+            const int j0 = (int)((long long)nPhi * l / spread), j1 = (int)((long long)nPhi * (l + 1) / spread);
+            const int nAb = std::min(NA, (b + 1) * K) - b * K;
+            for (int j = j0; j < j1; j++) {
+              WorkItem w;
+              w.angle = -1 - b * K;
+              w.zbeg = j * CH; w.zend = std::min(columns, (j + 1) * CH);
+              w.wait_idx = gateBase + b; w.wait_count = nItemsBatch[b] + (b > 0 ? nPhi : 0);
+              w.signal_idx = doneBase + b;
+              w.pad0 = b + 1 < tallyB ? gateBase + b + 1 : -1;
+              w.pad1 = ctx->slotOfAngle[b * K] | (nAb << 16) | ((b == 0 ? 1 : 0) << 30);
+              lvPhi.push_back(w);
+            }
+          }
+          // tally items evenly among the level's sweep items (both are independent of each other within a level)
+          size_t is = 0, ip = 0;
+          const size_t ns = lvSweep.size(), np = lvPhi.size();
+          while (is < ns || ip < np) {
+            if (ip < np && (is >= ns || ip * (ns + 1) <= is * np)) ringItems.push_back(lvPhi[ip++]);
+            else ringItems.push_back(lvSweep[is++]);
+          }
+        }
+      } else {
+        ringItems = items;   // the whole quadrature fits the ring: same order, no in-kernel tally (slot = angle)
+      }
     }
   }
   if (ctx->ndim == 2) ctx->stageItemBegin[ctx->nStages] = (int)items.size();
   ctx->nItems = (int)items.size();
-  ctx->nCounters = NA * maxHyp;
-  TRY(dev_alloc_copy(ctx, &ctx->d_nextZ, h_nextZ.data(), h_nextZ.size()));
-  TRY(dev_alloc_copy(ctx, &ctx->d_nextC, h_nextC.data(), h_nextC.size()));
+  ctx->nItemsRing = (int)ringItems.size();
+  ctx->nCounters = NA * maxHyp + nExtraCounters;
+  if (ctx->single_psi_wanted && ctx->nTallied > 0) TRY(dev_alloc_copy(ctx, &ctx->d_itemsRing, ringItems.data(), ringItems.size()));
+  else if (ctx->d_itemsRing) { cudaFree(ctx->d_itemsRing); ctx->d_itemsRing = nullptr; ctx->nItemsRing = 0; }
   TRY(dev_alloc_copy(ctx, &ctx->d_items, items.data(), items.size()));
   TRY(dev_alloc_copy<int>(ctx, &ctx->d_counters, nullptr, 1 + (size_t)ctx->nCounters));
-  if (ctx->use_plan && ctx->device >= 0) {
-    std::vector<int2> zinfo((size_t)NA * nz);
-    for (int a = 0; a < NA; a++)
-      for (int i = 0; i < nz; i++) {
-        const int z = std::abs(h_nextZ[(size_t)a * nz + i]) - 1;
-        zinfo[(size_t)a * nz + i] = make_int2(ctx->h_cOffSet[z], z | (ctx->h_numCorner[z] << 28));
-      }
-    TRY(dev_alloc_copy(ctx, &ctx->d_zinfo, zinfo.data(), zinfo.size()));
-    TRY(umt_build_plan3d(ctx));
-  }
+  if (ctx->device >= 0 && ctx->d_psi) TRY(ensure_layout(ctx));
   // cycle lists (control/constructDynMemory.F90:56-213)
   std::vector<int> cl, ca;
   int off = 0;
@@ -437,13 +553,18 @@ static int finalize_schedule(umt_ctx *ctx) {
     }
     off += ctx->numCycles[a];
   }
-  const bool cyclesChanged = off != ctx->totalCycles || !ctx->d_cyclePsi;
+  // Set%cyclePsi belongs to the list it was filled for: when the list changes (another corner set, not merely another length) the
+  // old values are some other corners' fluxes.  Re-seed it from Psi the way initCyclePsi does (constructDynMemory.F90:56-109);
+  // the caller's umt_init_radiation_field / umt_init_cycle_psi after the upload of Psi does the same explicitly.
+  const bool cyclesChanged = !ctx->d_cyclePsi || cl != ctx->h_cycleFlat || ca != ctx->h_cycleAngleFlat;
   ctx->totalCycles = off;
+  ctx->h_cycleFlat = cl; ctx->h_cycleAngleFlat = ca;
   TRY(dev_alloc_copy(ctx, &ctx->d_cycleList, cl.data(), cl.size()));
   TRY(dev_alloc_copy(ctx, &ctx->d_cycleAngle, ca.data(), ca.size()));
-  if (cyclesChanged) {
+  if (cyclesChanged && ctx->device >= 0) {
     TRY(dev_alloc_copy<double>(ctx, &ctx->d_cyclePsi, nullptr, (size_t)std::max(off, 1) * ctx->G));
-    UMT_CUDA(ctx, cudaMemset(ctx->d_cyclePsi, 0, sizeof(double) * (size_t)std::max(off, 1) * ctx->G));
+    UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_cyclePsi, 0, sizeof(double) * (size_t)std::max(off, 1) * ctx->G, ctx->stream));
+    if (off > 0 && ctx->d_psi) TRY(seed_cycle_psi(ctx));
   }
   // exit lists (AngleSet BdyExit, rt/findexit.F90:296-349)
   std::vector<int> eb, ec, ea;
@@ -473,26 +594,25 @@ static int ensure_state(umt_ctx *ctx) {
   NEED_DEVICE(ctx, "device state");
   if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "set the quadrature before uploading state");
   if (ctx->d_psi) return UMT_OK;
-  // Psi and Psi1 are both (G, ncornr+nbelem, NA): like Set%Psi1 in the reference (SetData_mod.F90:164)
-  // the boundary-element rows follow the corner rows, so a cFP value addresses either kind of
-  // upstream row directly; Set%PsiB(:,:,a) *is* the tail of the buffer currently playing Psi1.
+  // Psi slabs are (G, ncornr+nbelem) per angle: like Set%Psi1 in the reference (SetData_mod.F90:164) the boundary-element rows
+  // follow the corner rows, so a cFP value addresses either kind of upstream row.  The Psi1 workspace (full or a ring) is
+  // allocated once the schedule says which layout applies (ensure_layout); until then Set%PsiB lives in the tails of d_psi.
   const size_t G = ctx->G, nc = ctx->nc, NA = ctx->NA;
   ctx->rows = ctx->nc + ctx->nb;
   ctx->psi_elems = G * ctx->rows * NA;
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi, sizeof(double) * ctx->psi_elems));
-  UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psi1, sizeof(double) * ctx->psi_elems));
+  ctx->psib_in_psi = true; ctx->psi1Slots = 0;
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_stotal, sizeof(double) * G * nc));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_sigt, sizeof(double) * G * ctx->nz));
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_phi, sizeof(double) * G * nc));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_psi, 0, sizeof(double) * ctx->psi_elems));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_psi1, 0, sizeof(double) * ctx->psi_elems));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_stotal, 0, sizeof(double) * G * nc));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_sigt, 0, sizeof(double) * G * ctx->nz));
-  UMT_CUDA(ctx, cudaMemset(ctx->d_phi, 0, sizeof(double) * G * nc));
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psi, 0, sizeof(double) * ctx->psi_elems, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_stotal, 0, sizeof(double) * G * nc, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_sigt, 0, sizeof(double) * G * ctx->nz, ctx->stream));
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_phi, 0, sizeof(double) * G * nc, ctx->stream));
   if (ctx->ndim == 2) {
     const size_t nl = (size_t)std::max(ctx->nLevels, 1);   // Set%PsiM(G,nc), one per xi-level (levels sweep concurrently)
     UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_psim, sizeof(double) * G * nc * nl));
-    UMT_CUDA(ctx, cudaMemset(ctx->d_psim, 0, sizeof(double) * G * nc * nl));
+    UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * G * nc * nl, ctx->stream));
   }
   return UMT_OK;
 }
@@ -504,7 +624,7 @@ extern "C" int umt_upload_state(umt_ctx *ctx, const double *Psi, const double *P
   TRY(ensure_state(ctx));
   const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb, NA = ctx->NA, pitch = G * ctx->rows * 8;
   if (Psi) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi, pitch, Psi, G * nc * 8, G * nc * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
-  if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + G * nc, pitch, PsiB, G * nb * 8, G * nb * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
+  if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->psib_buf() + G * nc, pitch, PsiB, G * nb * 8, G * nb * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
   if (Sigt) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt, sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, ctx->stream));
   if (STotal) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal, sizeof(double) * G * nc, cudaMemcpyHostToDevice, ctx->stream));
   ctx->tau = tau;
@@ -527,7 +647,7 @@ static int set_copy(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles,
       else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
     }
     if (PsiB && nb) {
-      double *d = ctx->d_psi1 + ((size_t)(angle0 + a) * ctx->rows + nc) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
+      double *d = ctx->psib_buf() + ((size_t)(angle0 + a) * ctx->rows + nc) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
       if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
       else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
     }
@@ -559,7 +679,7 @@ extern "C" int umt_download_psi(umt_ctx *ctx, double *Psi) {
 }
 extern "C" int umt_download_psib(umt_ctx *ctx, double *PsiB) {
   if (!ctx) return UMT_ERR_ARG;
-  return download(ctx, PsiB, ctx->d_psi1, (size_t)ctx->G * ctx->nc, (size_t)ctx->G * ctx->nb, ctx->NA, (size_t)ctx->G * ctx->rows);
+  return download(ctx, PsiB, ctx->psib_buf(), (size_t)ctx->G * ctx->nc, (size_t)ctx->G * ctx->nb, ctx->NA, (size_t)ctx->G * ctx->rows);
 }
 extern "C" int umt_download_phi(umt_ctx *ctx, double *Phi) {
   if (!ctx) return UMT_ERR_ARG;
@@ -636,27 +756,139 @@ __global__ void exit_copy_kernel(const double *psi, double *psi1, const int *eb,
   psi1[((size_t)ea[m] * rows + nc + eb[m]) * G + g] = psi[((size_t)ea[m] * rows + ec[m]) * G + g];
 }
 
-static int launch_phi_range(umt_ctx *ctx, const double *field, size_t off, size_t n) {   // corners*groups [off, off+n), off even
-  const size_t threads = (n + 1) / 2;
+// The same tally over an explicit list of Psi1 slabs (ring slots of the angles the sweep kernel has not tallied itself), on top of
+// what PhiTotal already holds when `accumulate` is set: the angles come in ascending order, so the running sum is the same
+// sequence of operations as the fixed-order sum over all angles.
+__global__ void __launch_bounds__(256) phi_slots_kernel(const double *__restrict__ ws, const int *__restrict__ slot, const double *__restrict__ w,
+                                                        int nA, double *__restrict__ phi, size_t n, size_t stride, int accumulate) {
+  const size_t i2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i2 >= n) return;   // n and stride are even on this path (G even)
+  double2 s = make_double2(0.0, 0.0);
+  if (accumulate) s = *reinterpret_cast<const double2 *>(phi + i2);
+#pragma unroll 4
+  for (int a = 0; a < nA; a++) {
+    const double2 v = __ldcs(reinterpret_cast<const double2 *>(ws + (size_t)slot[a] * stride + i2));
+    const double wa = w[a];
+    s.x = s.x + wa * v.x;
+    s.y = s.y + wa * v.y;
+  }
+  *reinterpret_cast<double2 *>(phi + i2) = s;
+}
+
+// psi -> phi after the sweep(s) for the corners*groups range [off, off+n) (off even), whatever the layout:
+//   legacy: all angles from the Psi1 workspace; single-psi, savePsi sweep: all angles from Psi (written in place);
+//   single-psi, other sweeps: the angles still in the ring, on top of what the sweep kernel tallied.
+static int launch_phi_range(umt_ctx *ctx, int savePsi, size_t off, size_t n) {
+  const size_t threads = (n + 1) / 2, stride = (size_t)ctx->rows * ctx->G;
   const int grid = (int)((threads + 255) / 256);
-  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field + off, ctx->d_weight, nullptr, ctx->d_phi + off, n, ctx->NA, (size_t)ctx->rows * ctx->G);
+  if (!ctx->single_psi || savePsi) {
+    const double *field = ctx->single_psi ? ctx->d_psi : ctx->d_psi1;
+    phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field + off, ctx->d_weight, nullptr, ctx->d_phi + off, n, ctx->NA, stride);
+  } else {
+    const int nTail = ctx->NA - ctx->nTallied;
+    phi_slots_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_psi1 + off, ctx->d_tailSlot, ctx->d_tailW, nTail, ctx->d_phi + off, n, stride,
+                                                    ctx->nTallied > 0 ? 1 : 0);
+  }
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches += 1;
   return UMT_OK;
 }
 
-static int launch_phi(umt_ctx *ctx, const double *field) {
+static int launch_phi(umt_ctx *ctx, const double *field) {   // all angles of a full (NA, rows, G) field
   const size_t n = (size_t)ctx->nc * ctx->G;
   const size_t threads = (n + 1) / 2;
   const int grid = (int)((threads + 255) / 256);
-  unsigned char *d_skip = nullptr;
-  if (ctx->ndim == 2) {
-    // starting / finishing directions carry zero weight (rt/rtquad.F90:107-127) and are not tallied
-    // (SweepUCBrz.F90:233-239); weight==0 makes the product exact, no skip array needed.
-  }
-  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field, ctx->d_weight, d_skip, ctx->d_phi, n, ctx->NA, (size_t)ctx->rows * ctx->G);
+  // starting / finishing directions carry zero weight (rt/rtquad.F90:107-127) and are not tallied
+  // (SweepUCBrz.F90:233-239); weight==0 makes the product exact, no skip array needed.
+  phi_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(field, ctx->d_weight, nullptr, ctx->d_phi, n, ctx->NA, (size_t)ctx->rows * ctx->G);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches += 1;
+  return UMT_OK;
+}
+
+// (Re)allocate the Psi1 workspace for the layout the schedule allows and move Set%PsiB to where that layout keeps it.
+static int ensure_layout(umt_ctx *ctx) {
+  const bool single = ctx->single_psi_wanted;
+  const int slots = single ? std::min(ctx->NA, ctx->ringBatches * ctx->angleBatch) : ctx->NA;
+  if (single) {   // what the post-sweep tally still has to add (follows the item list just built)
+    std::vector<int> ts;
+    std::vector<double> tw;
+    for (int a = ctx->nTallied; a < ctx->NA; a++) { ts.push_back(ctx->slotOfAngle[a]); tw.push_back(ctx->h_weight[a]); }
+    TRY(dev_alloc_copy(ctx, &ctx->d_tailSlot, ts.data(), ts.size()));
+    TRY(dev_alloc_copy(ctx, &ctx->d_tailW, tw.data(), tw.size()));
+  }
+  if (ctx->d_psi1 && ctx->single_psi == single && ctx->psi1Slots == slots) return UMT_OK;
+  const size_t G = ctx->G, slab = G * ctx->rows, pitch = slab * 8, off = G * ctx->nc, tailB = G * ctx->nb * 8;
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_psi1) {
+    if (!ctx->psib_in_psi && ctx->nb > 0)     // legacy -> anything: PsiB goes home to the tails of d_psi first
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi + off, pitch, ctx->d_psi1 + off, pitch, tailB, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->psib_in_psi = true;
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaFree(ctx->d_psi1));
+    ctx->d_psi1 = nullptr; ctx->psi1Slots = 0;
+  }
+  if (slots < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "not enough free device memory for a Psi1 ring of even one angle batch");
+  cudaError_t e = cudaMalloc((void **)&ctx->d_psi1, sizeof(double) * slab * slots);
+  if (e != cudaSuccess) {
+    ctx->d_psi1 = nullptr;
+    UMT_FAIL(ctx, UMT_ERR_CUDA, "Psi1 workspace of %d slabs (%.1f GB): %s", slots, (double)(slab * slots * 8) / 1e9, cudaGetErrorString(e));
+  }
+  UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psi1, 0, sizeof(double) * slab * slots, ctx->stream));
+  ctx->psi1Slots = slots; ctx->single_psi = single;
+  if (!single) {
+    if (ctx->nb > 0) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + off, pitch, ctx->d_psi + off, pitch, tailB, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->psib_in_psi = false;
+  }
+  if (getenv("UMT_VERBOSE"))
+    fprintf(stderr, "umt: psi layout %s, Psi1 workspace %d slabs (%.2f GB), angle batch %d, ring %d of %d batches, %d angles tallied in the sweep kernel\n",
+            single ? "single" : "legacy", slots, (double)(slab * slots * 8) / 1e9, ctx->angleBatch, ctx->ringBatches, ctx->nBatches, ctx->nTallied);
+  return UMT_OK;
+}
+
+// initCyclePsi (constructDynMemory.F90:56-109): cyclePsi(:,m) <- Psi(:,c,angle) for the corners on the cycle lists
+static int seed_cycle_psi(umt_ctx *ctx) {
+  if (ctx->totalCycles > 0) {
+    const size_t n = (size_t)ctx->totalCycles * ctx->G;
+    cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_cyclePsi, ctx->d_cycleList,
+                                                                       ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 0);
+    UMT_CUDA(ctx, cudaGetLastError());
+  }
+  return UMT_OK;
+}
+
+extern "C" int umt_init_cycle_psi(umt_ctx *ctx) {
+  if (!ctx) return UMT_ERR_ARG;
+  NEED_DEVICE(ctx, "umt_init_cycle_psi");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  TRY(ensure_state(ctx));
+  TRY(finalize_schedule(ctx));
+  TRY(seed_cycle_psi(ctx));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return UMT_OK;
+}
+
+// Angle batches the Psi1 ring of the single-psi layout should hold (0: as many as the free device memory allows, which is also
+// the fastest; >= the number of batches: every angle keeps its own slab and nothing is tallied inside the sweep kernel).
+extern "C" int umt_set_psi1_ring(umt_ctx *ctx, int nBatches) {
+  if (!ctx || nBatches < 0) return UMT_ERR_ARG;
+  ctx->ringBatchesWanted = nBatches;
+  ctx->sched_dirty = true;
+  return UMT_OK;
+}
+
+// layout in force after the last schedule finalisation: info[0] 1 = single-psi, [1] Psi1 slabs allocated, [2] angle batch K,
+// [3] ring size in batches, [4] batches, [5] angles tallied by the sweep kernel; bytes = device memory of Psi + Psi1 workspace
+extern "C" int umt_get_psi_layout(umt_ctx *ctx, int *info6, double *bytes) {
+  if (!ctx) return UMT_ERR_ARG;
+  NEED_DEVICE(ctx, "umt_get_psi_layout");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->d_psi) TRY(finalize_schedule(ctx));
+  if (info6) {
+    info6[0] = ctx->single_psi ? 1 : 0; info6[1] = ctx->psi1Slots; info6[2] = ctx->angleBatch;
+    info6[3] = ctx->ringBatches; info6[4] = ctx->nBatches; info6[5] = ctx->nTallied;
+  }
+  if (bytes) *bytes = 8.0 * (double)ctx->G * ctx->rows * ((double)ctx->NA + ctx->psi1Slots);
   return UMT_OK;
 }
 
@@ -684,7 +916,7 @@ extern "C" int umt_set_boundary_sources(umt_ctx *ctx) {
   TRY(ensure_state(ctx));
   if (ctx->nb > 0) {
     const size_t G = ctx->G;
-    UMT_CUDA(ctx, cudaMemset2DAsync(ctx->d_psi1 + G * ctx->nc, G * ctx->rows * 8, 0, G * ctx->nb * 8, ctx->NA, ctx->stream));
+    UMT_CUDA(ctx, cudaMemset2DAsync(ctx->psib_buf() + G * ctx->nc, G * ctx->rows * 8, 0, G * ctx->nb * 8, ctx->NA, ctx->stream));
     UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return UMT_OK;
@@ -697,16 +929,11 @@ extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
   TRY(finalize_schedule(ctx));
   if (ctx->nExit > 0) {
     const size_t n = (size_t)ctx->nExit * ctx->G;
-    exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_psi1, ctx->d_exitB, ctx->d_exitC,
+    exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->psib_buf(), ctx->d_exitB, ctx->d_exitC,
                                                                       ctx->d_exitA, ctx->nExit, ctx->nc, ctx->rows, ctx->G);
     UMT_CUDA(ctx, cudaGetLastError());
   }
-  if (ctx->totalCycles > 0) {
-    const size_t n = (size_t)ctx->totalCycles * ctx->G;
-    cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->d_cyclePsi, ctx->d_cycleList,
-                                                                       ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 0);
-    UMT_CUDA(ctx, cudaGetLastError());
-  }
+  TRY(seed_cycle_psi(ctx));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return UMT_OK;
 }
@@ -758,13 +985,13 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
     if (multi && !ctx->have_comm_order) TRY(umt_exchange_begin_pass(ctx));   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
     // (comm sets of several bins exchange step by step inside umt_launch_sweep3d)
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    if (ctx->totalCycles > 0) {                     // initFromCycleList
+    if (ctx->totalCycles > 0) {                     // initFromCycleList (meshes with cycle lists keep the legacy layout)
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
       cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
                                                                          ctx->d_cycleAngle, ctx->totalCycles, ctx->rows, ctx->G, 1);
       ctx->last_launches++;
     }
-    if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx));
+    if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx, savePsi));
     else TRY(umt_launch_sweeprz(ctx, savePsi));
     if (ctx->totalCycles > 0) {                     // updateCycleList
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
@@ -790,7 +1017,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
 
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   if (!hostPhi) {
-    TRY(launch_phi(ctx, ctx->d_psi1));
+    TRY(launch_phi_range(ctx, savePsi, 0, (size_t)ctx->nc * ctx->G));
   } else {
     const size_t n = (size_t)ctx->nc * ctx->G;
     const int nChunks = n >= (size_t)1 << 22 ? 8 : 1;
@@ -799,7 +1026,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
       const size_t o = (size_t)k * per;
       if (o >= n) break;
       const size_t m = std::min(per, n - o);
-      TRY(launch_phi_range(ctx, ctx->d_psi1, o, m));
+      TRY(launch_phi_range(ctx, savePsi, o, m));
       UMT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
       UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev[7], 0));
       UMT_CUDA(ctx, cudaMemcpyAsync(hostPhi + o, ctx->d_phi + o, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream2));
@@ -810,15 +1037,18 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   if (hostPhi) UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
   cudaEventElapsedTime(&ms_phi, ctx->ev[5], ctx->ev[6]);
   cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
-  if (savePsi) {
-    // Psi(:,:,Angle) <- Psi1 for every angle without a copy: the buffers trade roles, and the
-    // boundary rows (PsiB) move over to the buffer that plays Psi1 from now on
+  if (savePsi && !ctx->single_psi) {
+    // legacy layout: Psi(:,:,Angle) <- Psi1 for every angle without a copy: the buffers trade roles, and the
+    // boundary rows (PsiB) move over to the buffer that plays Psi1 from now on.  (Single-psi layout: the sweep wrote Psi in place.)
     std::swap(ctx->d_psi, ctx->d_psi1);
-    if (ctx->nb > 0) {
-      const size_t G = ctx->G, pitch = G * ctx->rows * 8, off = G * ctx->nc;
+    const size_t G = ctx->G, pitch = G * ctx->rows * 8, off = G * ctx->nc;
+    bool anyBad = false;
+    for (int a = 0; a < ctx->NA; a++) anyBad = anyBad || ctx->nBad[a] > 0;
+    if (anyBad)   // Set%Psi1 persists across the savePsi sweep in the reference: its direct-solve zones (SweepUCBxyz.F90:283-298) iterate on it
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1, pitch, ctx->d_psi, pitch, G * ctx->nc * 8, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->nb > 0)
       UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + off, pitch, ctx->d_psi + off, pitch, G * ctx->nb * 8, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
-      UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->last_ms[0] = ms_sweep; ctx->last_ms[1] = ms_phi; ctx->last_ms[2] = ms_exch; ctx->last_ms[3] = ms_all;
   if (itersDone) *itersDone = iter;

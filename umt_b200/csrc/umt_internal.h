@@ -9,12 +9,15 @@
 #include "../../include/umt_sweep.h"
 
 struct WorkItem {       // one chunk of one hyperplane of one angle
-  int angle;            // 0-based angle
-  int zbeg, zend;       // range in nextZ(:,angle)
+  int angle;            // 0-based angle; phi-tally items of the 3-D plan kernel: -1 - (first angle of the batch)
+  int zbeg, zend;       // range in nextZ(:,angle); phi-tally items: range of 16-byte columns of PhiTotal
   int wait_idx;         // counter to wait on (-1: none)
   int wait_count;       // value it must reach
   int signal_idx;       // counter to bump when done
-  int pad0, pad1;
+  int pad0, pad1;       // r-z / grey kernels: second dependency (counter, value), pad0 < 0: none.
+                        // 3-D plan kernel: pad0 = second counter to bump (-1: none; the batch's gate counter in ring mode),
+                        // pad1 = slab of the Psi1 workspace the item's angle writes (ring slot; legacy / in place: the angle);
+                        // phi-tally items: pad1 = first slot | angles in the batch << 16 | first tally of the sweep << 30
 };
 
 // Plan record of one (zone, angle) for the 3-D plan kernel (sweep3d.cu): the zone's corners
@@ -122,7 +125,7 @@ struct umt_ctx {
   std::string err;
   int sm_count = 0;
   bool l2_persist = false;             // the 3-D sweep runs with an L2 set-aside for its evict_last Psi1 lines
-  size_t l2_persist_bytes = 0;
+  size_t l2_persist_bytes = 0, l2_persist_before = 0;   // before: the device limit found at creation, restored at destroy
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
 
@@ -166,7 +169,9 @@ struct umt_ctx {
   unsigned char *d_nextC = nullptr;    // (NA, nc) 0-based local corner
   WorkItem *d_items = nullptr;
   int nItems = 0, nCounters = 0, maxHyp = 0;
-  int *d_counters = nullptr;           // [0]=ticket, [1..] per (angle,plane)
+  WorkItem *d_itemsRing = nullptr;     // single-psi layout, non-final sweeps: items with ring slots and the in-kernel phi-tally items
+  int nItemsRing = 0;
+  int *d_counters = nullptr;           // [0]=ticket, [1..] per (angle,plane), then per batch: gate, tally done (ring mode)
   ZoneRec *d_recs = nullptr;           // (NA, nz) plan records in sweep order
   int2 *d_zinfo = nullptr;             // (NA, nz) first corner row, zone | numCorner << 28 (what the TMA producer needs)
   bool use_plan = false;
@@ -178,9 +183,28 @@ struct umt_ctx {
   int *d_exitB = nullptr, *d_exitC = nullptr, *d_exitA = nullptr; int nExit = 0;  // flattened bdyList over angles
   std::vector<int> exitOff;            // per-angle offsets into d_exit*
   // device: state
-  // d_psi, d_psi1: (NA, rows = nc+nb, G); the nb tail rows of d_psi1 are Set%PsiB
+  // d_psi: (NA, rows = nc+nb, G) = Set%Psi (corner rows; the nb tail rows of each slab are padding or Set%PsiB, see below).
+  // d_psi1: (psi1Slots, rows, G) workspace for Set%Psi1.  Two layouts (umt_api.cu ensure_layout):
+  //   legacy  psi1Slots = NA, the tails of d_psi1 are Set%PsiB, a savePsi sweep ends with the two buffers trading roles.  Every
+  //           r-z problem, and 3-D problems with cycle lists, direct-solve zones, reflecting boundaries or staged comm sets.
+  //   single  the tails of d_psi are Set%PsiB; a savePsi sweep writes Psi in place (a zone reads its own Psi^n rows before it
+  //           writes them and only ever reads new upstream rows, SweepUCBxyz.F90:119-126,149-158,314-318); the other sweeps
+  //           keep Psi1 in a ring of psi1Slots <= NA slabs whose angle batches are tallied into PhiTotal as they retire.
   double *d_psi = nullptr, *d_psi1 = nullptr, *d_stotal = nullptr, *d_sigt = nullptr, *d_phi = nullptr;
   int rows = 0;
+  bool single_psi = false;             // layout in force (valid once d_psi1 exists)
+  bool psib_in_psi = true;             // Set%PsiB = tails of d_psi (true until a legacy workspace exists)
+  bool force_legacy = false;           // compat.cu pokes Psi1 / PsiB directly
+  int psi1Slots = 0;                   // slabs allocated in d_psi1
+  bool single_psi_wanted = false;      // what the schedule allows (finalize_schedule)
+  int ringBatchesAuto = 0;             // ring size the free HBM allows, in batches
+  std::vector<int> h_cycleFlat, h_cycleAngleFlat;   // the cycle list Set%cyclePsi on the device belongs to
+  int ringBatchesWanted = 0;           // umt_set_psi1_ring: angle batches the ring should hold (0 = as memory allows)
+  int angleBatch = 0, ringBatches = 0, nBatches = 0;   // K, ring size in batches (>= nBatches: no in-kernel tally), batches
+  std::vector<int> slotOfAngle;        // (NA) ring slot of each angle's Psi1 in a non-final sweep
+  int nTallied = 0;                    // angles [0, nTallied) are tallied into PhiTotal by the sweep kernel itself
+  int *d_tailSlot = nullptr; double *d_tailW = nullptr;   // slots / weights of the angles the post-sweep tally still has to add
+  double *psib_buf() const { return psib_in_psi ? d_psi : d_psi1; }   // buffer whose slab tails are Set%PsiB
   double *d_psim = nullptr;            // RZ half-angle intensity (G,nc) per xi-level
   size_t psi_elems = 0;
 
@@ -238,7 +262,7 @@ struct umt_ctx {
   } while (0)
 
 // kernels / host pieces implemented in other translation units
-int umt_launch_sweep3d(umt_ctx *ctx);
+int umt_launch_sweep3d(umt_ctx *ctx, int savePsi);
 int umt_build_plan3d(umt_ctx *ctx);
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx);
 int umt_launch_sweeprz(umt_ctx *ctx, int savePsi);

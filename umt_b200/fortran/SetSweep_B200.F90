@@ -80,6 +80,10 @@ subroutine SetSweep_B200(savePsi)
          rc = umt_upload_set(b200_ctx, Set%g0, Set%Groups, Set%angle0, Set%NumAngles, c_loc(Set%Psi), c_loc(Set%PsiB))
          call b200_check(rc, "umt_upload_set")
       enddo
+      ! Set%cyclePsi <- Psi on the cycle-list corners, as initializeRadiationField does every cycle
+      ! (control/constructDynMemory.F90:56-109); the schedules installed above define the lists
+      rc = umt_init_cycle_psi(b200_ctx)
+      call b200_check(rc, "umt_init_cycle_psi")
       b200_static_uploaded = .TRUE.     ! finalizeSets resets it at the end of the cycle
    endif
 

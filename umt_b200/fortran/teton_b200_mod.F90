@@ -86,6 +86,17 @@ module teton_b200_mod
          type(C_PTR),    value :: Psi, PsiB
       end function
 
+      integer(C_INT) function umt_init_cycle_psi(ctx) bind(C, name="umt_init_cycle_psi")
+         import :: C_INT, C_PTR
+         type(C_PTR),    value :: ctx
+      end function
+
+      integer(C_INT) function umt_set_psi1_ring(ctx, nBatches) bind(C, name="umt_set_psi1_ring")
+         import :: C_INT, C_PTR
+         type(C_PTR),    value :: ctx
+         integer(C_INT), value :: nBatches     ! angle batches the Psi1 ring holds (0: as the free device memory allows)
+      end function
+
       integer(C_INT) function umt_download_set(ctx, g0, Groups, angle0, NumAngles, Psi, PsiB) bind(C, name="umt_download_set")
          import :: C_INT, C_PTR
          type(C_PTR),    value :: ctx

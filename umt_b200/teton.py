@@ -205,6 +205,19 @@ class SweepContext:
     def init_radiation_field(self):
         self._ck(self.lib.umt_init_radiation_field(self.h), "umt_init_radiation_field")
 
+    def init_cycle_psi(self):
+        self._ck(self.lib.umt_init_cycle_psi(self.h), "umt_init_cycle_psi")
+
+    def set_psi1_ring(self, nBatches):
+        self._ck(self.lib.umt_set_psi1_ring(self.h, int(nBatches)), "umt_set_psi1_ring")
+
+    def psi_layout(self):
+        info = np.zeros(6, np.int32)
+        b = C.c_double(0.0)
+        self._ck(self.lib.umt_get_psi_layout(self.h, _ip(info), C.byref(b)), "umt_get_psi_layout")
+        return dict(single=bool(info[0]), psi1_slabs=int(info[1]), angle_batch=int(info[2]), ring_batches=int(info[3]),
+                    batches=int(info[4]), angles_tallied_in_sweep=int(info[5]), bytes=b.value)
+
     # -- hot path ------------------------------------------------------------
     def sweep(self, savePsi=False, maxFluxIters=1, fluxTol=1e-6):
         it = C.c_int(0)
