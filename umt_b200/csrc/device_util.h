@@ -28,3 +28,42 @@ __device__ __forceinline__ unsigned long long umt_ld_relaxed_u64(const double *p
 __device__ __forceinline__ void umt_st_relaxed_f64(double *p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+
+// mbarrier / 1-D TMA (cp.async.bulk) helpers for the pipelined r-z sweep (sweeprz.cu); sweep3d.cu keeps its own copies
+__device__ __forceinline__ unsigned umt_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void umt_mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(umt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void umt_mbar_arrive(unsigned long long *bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(umt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umt_mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(umt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umt_mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "WAIT_%=:\n"
+      "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "  @p bra DONE_%=;\n"
+      "  bra WAIT_%=;\n"
+      "DONE_%=: }\n" ::"r"(umt_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool umt_mbar_test(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "  mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "  selp.u32 %0, 1, 0, p; }\n" : "=r"(ok) : "r"(umt_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+constexpr unsigned long long UMT_L2_EVICT_FIRST = 0x12F0000000000000ull;   // the encoding CUTLASS names TMA::CacheHintSm90::EVICT_FIRST
+__device__ __forceinline__ void umt_tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(umt_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(umt_smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int umt_ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}

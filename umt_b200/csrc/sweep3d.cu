@@ -35,6 +35,12 @@ constexpr int MAXC = 8;    // corners per zone handled by these kernels
 constexpr int MAXCF = 3;   // corner faces
 constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 
+// address of the Psi1 row at element offset o of an angle's slab: corner rows in the Psi1 workspace (upg), boundary-element rows
+// (o >= ncG) in the buffer whose tails are Set%PsiB (pbg).
+// TWO is a template parameter of the zone solves: false where both are the same buffer (legacy layout, in-place savePsi sweep).
+#define PLAN_ROW(o) ((TWO && (o) >= ncG ? pbg : upg) + (o))
+#define PLAN_BROW(o) ((TWO ? pbg : upg) + (o))
+
 struct Sweep3DParams {
   int nc, nb, nz, G, NA, nItems;
   int wpe, nEngines, nStages, stageBytes, offSt, offSigt, offRecs, zpi;   // PlanGeom
@@ -560,7 +566,7 @@ __device__ __forceinline__ void sts_v2(unsigned addr, const V2 &v) {
 // downstream corner of an edge is only known from the record.  A lane owns NH columns (2 NH groups) that lie
 // LZ columns apart (hs bytes in shared memory, hg doubles in global memory): every access of a warp stays a
 // contiguous run of 16-byte words, and the NH independent dependency chains interleave in the FP64 pipe.
-template <int NH>
+template <int NH, bool TWO>
 __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const ZoneEdge *__restrict__ &E, const int p, const int NC,
                                             const V2 (&pfC)[3][NH], V2 (&pfN)[3][NH], double *__restrict__ upg, double *__restrict__ pbg, const int ncG,
                                             const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const V2 (&rsig)[NH], const unsigned flags,
@@ -572,7 +578,7 @@ __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const
     for (int k = 0; k < 3; k++)
       if (k < nn) {
         const int o = R->inOff[p + 1][k];
-        const double *src = (o >= ncG ? pbg : upg) + o;
+        const double *src = PLAN_ROW(o);
 #pragma unroll
         for (int h = 0; h < NH; h++) pfN[k][h] = ld_l2(src + h * hg);
       }
@@ -660,13 +666,13 @@ __device__ __forceinline__ void plan_corner(const ZoneRec *__restrict__ R, const
     for (int f = 0; f < 3; f++)
       if (em & (1u << f)) {
 #pragma unroll
-        for (int h = 0; h < NH; h++) st_keep(pbg + R->exitOff[p][f] + h * hg, psi[h]);
+        for (int h = 0; h < NH; h++) st_keep(PLAN_BROW(R->exitOff[p][f]) + h * hg, psi[h]);
       }
   }
   E += nout;
 }
 
-template <int NH>
+template <int NH, bool TWO>
 __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ upg, double *__restrict__ pbg,
                                                 const int ncG, const unsigned qs, const unsigned ss, const V2 (&sig)[NH], const unsigned hs, const int hg) {
   const unsigned flags = R->flags;
@@ -703,15 +709,15 @@ __device__ __forceinline__ void solve_zone_plan(const double tau, const ZoneRec 
     for (int k = 0; k < 3; k++)
       if (k < n0) {
         const int o = R->inOff[0][k];
-        const double *src = (o >= ncG ? pbg : upg) + o;
+        const double *src = PLAN_ROW(o);
 #pragma unroll
         for (int h = 0; h < NH; h++) pfA[k][h] = ld_l2(src + h * hg);
       }
   }
 #pragma unroll 1
   for (int p = 0; p < NC; p += 2) {
-    plan_corner<NH>(R, E, p, NC, pfA, pfB, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
-    if (p + 1 < NC) plan_corner<NH>(R, E, p + 1, NC, pfB, pfA, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
+    plan_corner<NH, TWO>(R, E, p, NC, pfA, pfB, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
+    if (p + 1 < NC) plan_corner<NH, TWO>(R, E, p + 1, NC, pfB, pfA, upg, pbg, ncG, qs, ss, sig, rsig, flags, hs, hg);
   }
 }
 
@@ -732,7 +738,7 @@ __device__ __forceinline__ V2 ldcg_v2(const double *p) {
 // and shared memory is only read: the landed Psi^n / STotal columns once each, plus the record fields.
 // An edge whose opposite FP face is not incident uses the same closure with N = 0, which is algebraically the
 // reference's sez = aez (Q - Q_cez) / (2 sigma) (SweepUCBxyz.F90:254-256).
-template <int NH>
+template <int NH, bool TWO>
 __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec *__restrict__ R, double *__restrict__ upg, double *__restrict__ pbg,
                                                  const int ncG, const unsigned char *__restrict__ colPsi, const unsigned char *__restrict__ colSt,
                                                  const V2 (&sig)[NH], const unsigned hs, const int hg) {
@@ -745,7 +751,7 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
 #pragma unroll
     for (int k = 0; k < cn_nout(p); k++) {
       const int o = R->inOff[p][k];
-      const double *src = (o >= ncG ? pbg : upg) + o;
+      const double *src = PLAN_ROW(o);
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         pf[p][k][h].x = 0.0; pf[p][k][h].y = 0.0;
@@ -773,7 +779,7 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
       for (int pp = 4; pp < 7; pp++) {
         const int nin = R->nIn[pp];
         const int o = R->inOff[pp][0];
-        const double *src = (o >= ncG ? pbg : upg) + o;
+        const double *src = PLAN_ROW(o);
 #pragma unroll
         for (int h = 0; h < NH; h++) {
           pf[pp][0][h].x = 0.0; pf[pp][0][h].y = 0.0;
@@ -799,7 +805,7 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
         if (k < (int)R->nIn[p]) {
           const double af = R->inAfp[p][k];
           const int o = R->inOff[p][k];
-          const double *src = (o >= ncG ? pbg : upg) + o;
+          const double *src = PLAN_ROW(o);
 #pragma unroll
           for (int h = 0; h < NH; h++) {
             const V2 v = ldcg_v2(src + h * hg);
@@ -859,7 +865,7 @@ __device__ __forceinline__ void solve_zone_canon(const double tau, const ZoneRec
       for (int f = 0; f < 3; f++)
         if (em & (1u << f)) {
 #pragma unroll
-          for (int h = 0; h < NH; h++) st_keep_free(pbg + R->exitOff[p][f] + h * hg, psi[h]);
+          for (int h = 0; h < NH; h++) st_keep_free(PLAN_BROW(R->exitOff[p][f]) + h * hg, psi[h]);
         }
     }
   }
@@ -874,26 +880,32 @@ __device__ __noinline__ void phi_tally_item(const Sweep3DParams &P, const int a0
   const int slot0 = packed & 0xffff, nA = (packed >> 16) & 0xff;
   const bool first = (packed >> 30) & 1;
   const size_t slab = (size_t)(P.nc + P.nb) * P.G;
-  const double *src = P.upBase + (size_t)slot0 * slab;
-  for (int c = c0 + elane; c < c1; c += 2 * nLanes) {
-    const int cB = c + nLanes;
-    const bool hasB = cB < c1;
-    double2 sA = make_double2(0.0, 0.0), sB = make_double2(0.0, 0.0);
-    if (!first) {
-      sA = __ldcg(reinterpret_cast<const double2 *>(P.phi) + c);
-      if (hasB) sB = __ldcg(reinterpret_cast<const double2 *>(P.phi) + cB);
+  const double2 *src = reinterpret_cast<const double2 *>(P.upBase + (size_t)slot0 * slab);
+  const size_t slab2 = slab / 2;
+  double2 *phi = reinterpret_cast<double2 *>(P.phi);
+  constexpr int U = 4;   // columns per lane in flight: U (nA + 1) independent 16-byte loads hide the DRAM latency of this streaming item
+  for (int c = c0 + elane; c < c1; c += U * nLanes) {
+    double2 s[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      s[u] = make_double2(0.0, 0.0);
+      if (!first && c + u * nLanes < c1) s[u] = __ldcg(phi + c + u * nLanes);
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int i = 0; i < nA; i++) {
       const double wa = P.weight[a0 + i];
-      const double2 vA = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)i * slab) + c);
-      double2 vB = make_double2(0.0, 0.0);
-      if (hasB) vB = __ldcg(reinterpret_cast<const double2 *>(src + (size_t)i * slab) + cB);
-      sA.x = sA.x + wa * vA.x; sA.y = sA.y + wa * vA.y;
-      sB.x = sB.x + wa * vB.x; sB.y = sB.y + wa * vB.y;
+      double2 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        v[u] = make_double2(0.0, 0.0);
+        if (c + u * nLanes < c1) v[u] = __ldcg(src + (size_t)i * slab2 + c + u * nLanes);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) { s[u].x = s[u].x + wa * v[u].x; s[u].y = s[u].y + wa * v[u].y; }
     }
-    __stcg(reinterpret_cast<double2 *>(P.phi) + c, sA);
-    if (hasB) __stcg(reinterpret_cast<double2 *>(P.phi) + cB, sB);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (c + u * nLanes < c1) __stcg(phi + c + u * nLanes, s[u]);
   }
 }
 
@@ -902,8 +914,11 @@ __device__ __noinline__ void phi_tally_item(const Sweep3DParams &P, const int a0
 #else
 #define PLAN_BOUNDS(NH) __launch_bounds__(PLAN_LANES + 64, (NH == 1 ? PLAN_MINB : PLAN_MINB2))
 #endif
-template <int NH>
+// MODE 0: Psi1 rows and boundary-element rows in one buffer, slab = angle (legacy layout; in-place savePsi sweep of the single-psi layout)
+//      1: ring slots for the Psi1 rows, boundary-element rows in the Psi buffer, phi-tally items (single-psi layout, other sweeps)
+template <int NH, int MODE>
 __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
+  constexpr bool TWO = MODE == 1, RING = MODE == 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw);
   unsigned char *stages = smem_raw + PLAN_CTL_BYTES;
@@ -953,7 +968,7 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
         if (myItem < nCount) nW = P.items[nT + myItem];
         nPhase = 2;
       } else if (nPhase == 2) {
-        if (myItem < nCount && nW.angle >= 0 && myZone < nW.zend - nW.zbeg) nZ = P.zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
+        if (myItem < nCount && (!RING || nW.angle >= 0) && myZone < nW.zend - nW.zbeg) nZ = P.zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
         nPhase = 3;
       }
     };
@@ -993,11 +1008,12 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
             w.angle = __shfl_sync(0xffffffffu, qW.angle, srcLane); w.zbeg = __shfl_sync(0xffffffffu, qW.zbeg, srcLane);
             w.zend = __shfl_sync(0xffffffffu, qW.zend, srcLane); w.wait_idx = __shfl_sync(0xffffffffu, qW.wait_idx, srcLane);
             w.wait_count = __shfl_sync(0xffffffffu, qW.wait_count, srcLane); w.signal_idx = __shfl_sync(0xffffffffu, qW.signal_idx, srcLane);
-            w.pad0 = __shfl_sync(0xffffffffu, qW.pad0, srcLane); w.pad1 = __shfl_sync(0xffffffffu, qW.pad1, srcLane);
+            w.pad0 = -1; w.pad1 = w.angle;
+            if (RING) { w.pad0 = __shfl_sync(0xffffffffu, qW.pad0, srcLane); w.pad1 = __shfl_sync(0xffffffffu, qW.pad1, srcLane); }
             int2 zi;
             zi.x = __shfl_sync(0xffffffffu, qZ.x, (srcLane + lane) & 31); zi.y = __shfl_sync(0xffffffffu, qZ.y, (srcLane + lane) & 31);
             qPos++;
-            const bool tally = w.angle < 0;      // phi-tally item: nothing to land, the engine streams straight from global memory
+            const bool tally = RING && w.angle < 0;   // phi-tally item: nothing to land, the engine streams straight from global memory
             const int n = tally ? 0 : w.zend - w.zbeg;
             const size_t first = tally ? 0 : (size_t)w.angle * P.nz + w.zbeg;
             unsigned bytes = 0;
@@ -1007,9 +1023,8 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
             if (lane == 0) {
               S.meta[sFill].angle = tally ? -1 - w.angle : w.angle; S.meta[sFill].n = tally ? -2 : n;
               S.meta[sFill].wait_idx = w.wait_idx; S.meta[sFill].wait_count = w.wait_count;
-              S.meta[sFill].upIdx = w.pad1; S.meta[sFill].c0 = w.zbeg; S.meta[sFill].c1 = w.zend;
+              if (RING) { S.meta[sFill].upIdx = w.pad1; S.meta[sFill].c0 = w.zbeg; S.meta[sFill].c1 = w.zend; S.sig2Ring[nIssued & (PLAN_RING - 1)] = w.pad0; }
               S.sigRing[nIssued & (PLAN_RING - 1)] = w.signal_idx;
-              S.sig2Ring[nIssued & (PLAN_RING - 1)] = w.pad0;
               __threadfence_block();
               S.issuedCount = nIssued + 1;
               if (tally) mbar_arrive(&S.full[sFill]);
@@ -1067,8 +1082,8 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       for (int j = 0; j < m; j++) {
         asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + S.sigRing[(k + j) & (PLAN_RING - 1)]]) : "memory");
-        const int s2i = S.sig2Ring[(k + j) & (PLAN_RING - 1)];
-        if (s2i >= 0) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + s2i]) : "memory");
+        const int s2i = RING ? S.sig2Ring[(k + j) & (PLAN_RING - 1)] : -1;
+        if (RING && s2i >= 0) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + s2i]) : "memory");
       }
       k += m; sg = s2; par = p2;
       S.nSignaled = k;
@@ -1088,25 +1103,26 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     mbar_wait(&S.full[s], (k / NS) & 1);
     const StageMeta m = S.meta[s];
     if (m.n == -1) break;
-    if (m.n == -2) {
+    if (RING && m.n == -2) {
       phi_tally_item(P, m.angle, m.upIdx, m.c0, m.c1, elane, 32 * wpe);
     } else if (zi < m.n) {
       unsigned char *st = stages + (size_t)s * P.stageBytes;
       const ZoneRec *R = reinterpret_cast<const ZoneRec *>(st + P.offRecs) + zi;
-      double *upg = P.upBase + (size_t)m.upIdx * slab + 2 * li;   // corner rows of this angle's Psi1
-      double *pbg = P.bBase + (size_t)m.angle * slab + 2 * li;    // boundary-element rows (Set%PsiB(:,:,angle))
+      const int upIdx = RING ? m.upIdx : m.angle;
+      double *upg = P.upBase + (size_t)upIdx * slab + 2 * li;                      // corner rows of this angle's Psi1
+      double *pbg = TWO ? P.bBase + (size_t)m.angle * slab + 2 * li : upg;         // boundary-element rows (Set%PsiB(:,:,angle))
       if (R->flags & ZREC_SLOW) {
         for (int h = 0; h < NH; h++) {
-          solve_zone_slow(P, m.angle, m.upIdx, R->zone0, 2 * (li + h * LZ));
-          solve_zone_slow(P, m.angle, m.upIdx, R->zone0, 2 * (li + h * LZ) + 1);
+          solve_zone_slow(P, m.angle, upIdx, R->zone0, 2 * (li + h * LZ));
+          solve_zone_slow(P, m.angle, upIdx, R->zone0, 2 * (li + h * LZ) + 1);
         }
       } else {
         const unsigned col = (unsigned)(zi * MAXC * Gv + li) * 16u;
         V2 sig[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) sig[h] = *reinterpret_cast<const V2 *>(st + P.offSigt + (size_t)(zi * Gv + li + h * LZ) * 16);
-        if (R->flags & ZREC_CANON) solve_zone_canon<NH>(tau, R, upg, pbg, P.ncG, st + col, st + P.offSt + col, sig, hs, hg);
-        else solve_zone_plan<NH>(tau, R, upg, pbg, P.ncG, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
+        if (R->flags & ZREC_CANON) solve_zone_canon<NH, TWO>(tau, R, upg, pbg, P.ncG, st + col, st + P.offSt + col, sig, hs, hg);
+        else solve_zone_plan<NH, TWO>(tau, R, upg, pbg, P.ncG, smem_u32(st) + col, smem_u32(st + P.offSt) + col, sig, hs, hg);
       }
     }
     __syncwarp();
@@ -1164,10 +1180,12 @@ int umt_build_plan3d(umt_ctx *ctx) {
   return UMT_OK;
 }
 
-static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P) {
+static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P, int mode) {
   const int threads = PLAN_LANES + 64;   // consumers + loader warp + signaller warp
   const size_t smem = plan_geom(ctx->G, ctx->plan_nh).smemBytes;
-  void (*kern)(Sweep3DParams) = ctx->plan_nh == 2 ? sweep3d_plan_kernel<2> : sweep3d_plan_kernel<1>;
+  void (*kern)(Sweep3DParams);
+  if (ctx->plan_nh == 2) kern = mode == 1 ? sweep3d_plan_kernel<2, 1> : sweep3d_plan_kernel<2, 0>;
+  else kern = mode == 1 ? sweep3d_plan_kernel<1, 1> : sweep3d_plan_kernel<1, 0>;
   UMT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -1196,12 +1214,14 @@ int umt_launch_sweep3d(umt_ctx *ctx, int savePsi) {
     if (!savePsi && ctx->nTallied > 0) {
       P.items = ctx->d_itemsRing;
       P.nItems = ctx->nItemsRing;
-      int r = launch_plan(ctx, P);
+      int r = launch_plan(ctx, P, 1);
       if (r) return r;
       ctx->last_launches += 1;
       return UMT_OK;
     }
   }
+  if (P.upBase != P.bBase) UMT_FAIL(ctx, UMT_ERR_STATE, "single-psi layout without a ring item list");
+  const int mode = 0;
   // one launch per reflection stage (a single stage unless the domain has reflecting boundaries)
   for (int s = 0; s < ctx->nStages; s++) {
     const int begin = ctx->stageItemBegin[s], end = ctx->stageItemBegin[s + 1];
@@ -1215,7 +1235,7 @@ int umt_launch_sweep3d(umt_ctx *ctx, int savePsi) {
     P.items = ctx->d_items + begin;
     P.nItems = end - begin;
     if (ctx->use_plan) {
-      r = launch_plan(ctx, P);
+      r = launch_plan(ctx, P, mode);
       if (r) return r;
     } else {
       int occ = 0;

@@ -614,6 +614,294 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
 #undef LC
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Pipelined record kernel (UMT_RZ_KERNEL=pipe; quads with canonical records, G <= 64, G even; NOT the default, see the launcher): the serial per-item chain of
+// sweeprz_rec_kernel (ticket -> item -> records -> inputs from DRAM -> divisions -> poll -> barrier -> upstream loads -> solve ->
+// stores -> fence -> signal, one CTA doing all of it for one item at a time) split over three roles, as in the 3-D plan kernel:
+//   * a loader warp takes tickets ahead (QB at a time, descriptors and zone info fetched by its lanes in parallel), lands every
+//     item's records and its Psi^n / STotal / Sigt rows in one of the CTA's shared-memory stages with cp.async.bulk (1-D TMA,
+//     mbarrier complete_tx) and resolves BOTH dependencies of the item -- the previous hyperplane of its angle and the plane of
+//     the previous angle of its xi-level that covers its zones (PsiM chain, SweepUCBrz.F90:212-240) -- with ld.acquire, then
+//     makes the second arrival on the stage's `full` barrier;
+//   * engines of two warps (one thread per (zone, group) pair of an item) wait on `full`, compute the group-dependent static
+//     half from shared memory, read PsiM and the upstream Psi1 rows through L2, solve, store, and arrive on `empty`: they never
+//     poll global memory and there is no __syncthreads() per item;
+//   * a signaller warp turns `empty` arrivals into fence.acq_rel.gpu + red on the plane counters.
+#ifndef RZP_NE
+#define RZP_NE 2                 // engines per CTA
+#endif
+#ifndef RZP_MIN_CTAS
+#define RZP_MIN_CTAS 3
+#endif
+constexpr int RZP_WPE = 2;                         // warps per engine: 64 (zone, group) pairs per item at most
+constexpr int RZP_THREADS = RZP_NE * RZP_WPE * 32 + 64;
+constexpr int RZP_MAX_STAGES = 12, RZP_RING = 32, RZP_CTL_BYTES = 768, RZP_ZMAX = 8;
+struct RZPMeta { int angle, n, signal_idx, wait_idx, wait_count, wait2_idx, wait2_count, pad; };
+struct RZPCtl {
+  unsigned long long full[RZP_MAX_STAGES], empty[RZP_MAX_STAGES];
+  RZPMeta meta[RZP_MAX_STAGES];
+  int sigRing[RZP_RING];
+  volatile int issuedCount, doneFlag, nSignaled;
+  int pad;
+};
+static_assert(sizeof(RZPCtl) <= RZP_CTL_BYTES, "RZPCtl must fit the control block");
+struct RZPGeom { int nStages, stageBytes, offSt, offSigt, offRecs, zpi; };
+
+__global__ void __launch_bounds__(RZP_THREADS, RZP_MIN_CTAS) sweeprz_pipe_kernel(SweepRZParams P, const RZRec *__restrict__ recs,
+                                                                                 const int2 *__restrict__ zinfo, RZPGeom Gm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  RZPCtl &S = *reinterpret_cast<RZPCtl *>(smem_raw);
+  unsigned char *stages = smem_raw + RZP_CTL_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = P.G, nc = P.nc, NS = Gm.nStages;
+  const size_t slab = (size_t)(nc + P.nb) * G;
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) { umt_mbar_init(&S.full[s], 2); umt_mbar_init(&S.empty[s], RZP_WPE); }
+    S.issuedCount = 0; S.doneFlag = 0; S.nSignaled = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == RZP_NE * RZP_WPE) {
+    // ---------------- loader warp (same scheme as sweep3d_plan_kernel's) ----------------
+    int nIssued = 0, nReleased = 0, sentinels = -1;
+    int kFill = 0, sFill = 0, sRel = 0, lastOk = -1, lastOk2 = -1;
+    unsigned parPrev = 1;
+    const unsigned rowBytes = (unsigned)G * 8u;
+    const int zpi = Gm.zpi, QB = min(8, 32 / zpi);
+    const int myItem = lane / zpi, myZone = lane - myItem * zpi;
+    WorkItem qW, nW;
+    int2 qZ = make_int2(0, 0), nZ = make_int2(0, 0);
+    int qCount = 0, qPos = 0, nCount = 0, nPhase = 0, nT = 0;
+    bool exhausted = false;
+    qW.angle = qW.zbeg = qW.zend = qW.wait_idx = qW.wait_count = qW.signal_idx = qW.pad0 = qW.pad1 = 0; nW = qW;
+    auto fetch_step = [&]() {
+      if (nPhase == 0) {
+        if (lane == 0) nT = atomicAdd(&P.counters[0], QB);
+        nPhase = 1;
+      } else if (nPhase == 1) {
+        nT = __shfl_sync(0xffffffffu, nT, 0);
+        nCount = max(0, min(QB, P.nItems - nT));
+        if (myItem < nCount) nW = P.items[nT + myItem];
+        nPhase = 2;
+      } else if (nPhase == 2) {
+        if (myItem < nCount && myZone < nW.zend - nW.zbeg) nZ = zinfo[(size_t)nW.angle * P.nz + nW.zbeg + myZone];
+        nPhase = 3;
+      }
+    };
+    for (;;) {
+      bool progressed = false;
+      if (qPos == qCount && !exhausted) {
+        while (nPhase < 3) fetch_step();
+        qW = nW; qZ = nZ; qCount = nCount; qPos = 0; nPhase = 0;
+        if (qCount < QB) exhausted = true;
+      }
+      if (!exhausted && nPhase < 3) fetch_step();
+      if (nReleased < nIssued) {
+        int ok = 1;
+        if (lane == 0) {
+          const RZPMeta &m = S.meta[sRel];
+          ok = m.wait_idx < 0 || m.wait_idx == lastOk || umt_ld_acquire(&P.counters[1 + m.wait_idx]) >= m.wait_count;
+          if (ok) {
+            lastOk = m.wait_idx;
+            ok = m.wait2_idx < 0 || m.wait2_idx == lastOk2 || umt_ld_acquire(&P.counters[1 + m.wait2_idx]) >= m.wait2_count;
+            if (ok) { lastOk2 = m.wait2_idx; umt_mbar_arrive(&S.full[sRel]); }
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          nReleased++; progressed = true;
+          if (++sRel == NS) sRel = 0;
+        }
+      }
+      if (sentinels < 0 && exhausted && qPos == qCount) sentinels = RZP_NE;
+      if (sentinels != 0) {
+        int free_ = 1;
+        if (lane == 0) free_ = (kFill < NS || umt_mbar_test(&S.empty[sFill], parPrev)) && (sentinels > 0 || nIssued - S.nSignaled < RZP_RING);
+        free_ = __shfl_sync(0xffffffffu, free_, 0);
+        if (free_) {
+          if (sentinels > 0) {
+            if (lane == 0) { S.meta[sFill].n = -1; umt_mbar_arrive(&S.full[sFill]); umt_mbar_arrive(&S.full[sFill]); }
+            sentinels--;
+          } else {
+            const int srcLane = qPos * zpi;
+            WorkItem w;
+            w.angle = __shfl_sync(0xffffffffu, qW.angle, srcLane); w.zbeg = __shfl_sync(0xffffffffu, qW.zbeg, srcLane);
+            w.zend = __shfl_sync(0xffffffffu, qW.zend, srcLane); w.wait_idx = __shfl_sync(0xffffffffu, qW.wait_idx, srcLane);
+            w.wait_count = __shfl_sync(0xffffffffu, qW.wait_count, srcLane); w.signal_idx = __shfl_sync(0xffffffffu, qW.signal_idx, srcLane);
+            w.pad0 = __shfl_sync(0xffffffffu, qW.pad0, srcLane); w.pad1 = __shfl_sync(0xffffffffu, qW.pad1, srcLane);
+            int2 zi;
+            zi.x = __shfl_sync(0xffffffffu, qZ.x, (srcLane + lane) & 31); zi.y = __shfl_sync(0xffffffffu, qZ.y, (srcLane + lane) & 31);
+            qPos++;
+            const int n = w.zend - w.zbeg;
+            const size_t first = (size_t)w.angle * P.nz + w.zbeg;
+            const unsigned bytes = (unsigned)n * (9u * rowBytes + (unsigned)sizeof(RZRec));   // per zone: 4 Psi rows, 4 STotal rows, 1 Sigt row, 1 record
+            unsigned char *st = stages + (size_t)sFill * Gm.stageBytes;
+            if (lane == 0) {
+              RZPMeta &m = S.meta[sFill];
+              m.angle = w.angle; m.n = n; m.wait_idx = w.wait_idx; m.wait_count = w.wait_count; m.wait2_idx = w.pad0; m.wait2_count = w.pad1;
+              S.sigRing[nIssued & (RZP_RING - 1)] = w.signal_idx;
+              __threadfence_block();
+              S.issuedCount = nIssued + 1;
+              umt_mbar_arrive_expect_tx(&S.full[sFill], bytes);
+              umt_tma_load_1d(st + Gm.offRecs, recs + first, (unsigned)(n * sizeof(RZRec)), &S.full[sFill], UMT_L2_EVICT_FIRST);
+            }
+            __syncwarp();
+            if (lane < n) {   // zi.x = first corner of the zone, zi.y = zone
+              umt_tma_load_1d(st + (size_t)lane * 4 * rowBytes, P.psi + (size_t)w.angle * slab + (size_t)zi.x * G, 4u * rowBytes, &S.full[sFill], UMT_L2_EVICT_FIRST);
+              umt_tma_load_1d(st + Gm.offSt + (size_t)lane * 4 * rowBytes, P.stotal + (size_t)zi.x * G, 4u * rowBytes, &S.full[sFill], UMT_L2_EVICT_FIRST);
+              umt_tma_load_1d(st + Gm.offSigt + (size_t)lane * rowBytes, P.sigt + (size_t)zi.y * G, rowBytes, &S.full[sFill], UMT_L2_EVICT_FIRST);
+            }
+            nIssued++;
+          }
+          progressed = true;
+          kFill++;
+          if (++sFill == NS) { sFill = 0; parPrev ^= 1u; }
+        }
+      }
+      if (sentinels == 0 && nReleased == nIssued) break;
+      if (!progressed) __nanosleep(32);
+    }
+    if (lane == 0) { __threadfence_block(); S.doneFlag = 1; }
+    return;
+  }
+
+  if (warp == RZP_NE * RZP_WPE + 1) {
+    // ---------------- signaller warp ----------------
+    if (lane != 0) return;
+    int k = 0, sg = 0;
+    unsigned par = 0;
+    for (;;) {
+      const int done = S.doneFlag;
+      __threadfence_block();
+      const int issued = S.issuedCount;
+      if (k >= issued) {
+        if (done) break;
+        __nanosleep(64);
+        continue;
+      }
+      umt_mbar_wait(&S.empty[sg], par);
+      int m = 1, s2 = sg + 1;
+      unsigned p2 = par;
+      if (s2 == NS) { s2 = 0; p2 ^= 1u; }
+      while (k + m < issued && umt_mbar_test(&S.empty[s2], p2)) {
+        m++;
+        if (++s2 == NS) { s2 = 0; p2 ^= 1u; }
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      for (int j = 0; j < m; j++)
+        asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + S.sigRing[(k + j) & (RZP_RING - 1)]]) : "memory");
+      k += m; sg = s2; par = p2;
+      S.nSignaled = k;
+    }
+    return;
+  }
+
+  // ---------------- engines: two warps, one thread per (zone, group) pair of the item ----------------
+  const int eng = warp / RZP_WPE, elane = (warp - eng * RZP_WPE) * 32 + lane;
+  const int zi = elane / G, g = elane - zi * G;
+  const double tau = P.tau;
+  for (int k = eng;; k += RZP_NE) {
+    const int s = k % NS;
+    umt_mbar_wait(&S.full[s], (k / NS) & 1);
+    const RZPMeta m = S.meta[s];
+    if (m.n < 0) break;
+    if (zi < m.n) {
+      const unsigned char *st = stages + (size_t)s * Gm.stageBytes;
+      const RZRec &R = reinterpret_cast<const RZRec *>(st + Gm.offRecs)[zi];
+      const double *sPsi = reinterpret_cast<const double *>(st) + (size_t)zi * 4 * G + g;
+      const double *sSt = reinterpret_cast<const double *>(st + Gm.offSt) + (size_t)zi * 4 * G + g;
+      const int a = m.angle, c0 = R.c0;
+      double *psi1A = P.psi1 + (size_t)a * slab;
+      double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+      // upstream fluxes and the previous angle's PsiM go in flight first (the item's dependencies are complete)
+      double pm[4], u[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        pm[c] = __ldcg(&psimL[(size_t)(c0 + (int)R.ci[c]) * G + g]);
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          u[c][f] = 0.0;
+          if (R.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)R.row[c][f] * G + g]);
+        }
+      }
+      // group-dependent static half from the landed rows (corners by solve position: R.ci[p] = local corner of position p)
+      const double sig = reinterpret_cast<const double *>(st + Gm.offSigt)[zi * G + g], sigInv = 1.0 / sig;
+      double Q[4], src[4], A1[4][2], inv[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int lc = (int)R.ci[c] * G;
+        Q[c] = sSt[lc] + tau * sPsi[lc];
+        src[c] = R.vol[c] * Q[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          A1[c][f] = 0.0;
+          const double az = R.az[c][f];
+          if (az > 0.0) {
+            const int cez = rz_nb(c, f);
+            const double Rr = R.rez[c][f], dq = Q[c] - Q[cez];
+            double A0;
+            if (R.inMask & (1u << (2 * c + f))) {
+              const double ar = R.area[c];
+              const double sigA = sig * ar, sigA2 = sigA * sigA;
+              const double gnum = az * az * (FOURALPHA * sigA2 + az * (4.0 * sigA + 3.0 * az));
+              const double gden = ar * (4.0 * sigA * sigA2 + az * (6.0 * sigA2 + 2.0 * az * (2.0 * sigA + az)));
+              const double rd = Rr / (gnum + gden * sig);
+              A1[c][f] = rd * (ar * gnum * sig);
+              A0 = rd * (0.5 * az * gden * dq - ar * gnum * Q[c]);
+            } else {
+              A0 = 0.5 * (Rr * az) * dq * sigInv;
+            }
+            src[c] += A0;
+            src[cez] -= A0;
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < 4; i++) inv[i] = 1.0 / (R.sumArea[i] + sig * R.vol[i]);
+      // the half on the dependency chain
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          src[c] = fma(R.k1b[c][f] + A1[c][f], u[c][f], src[c]);
+          src[rz_nb(c, f)] += -A1[c][f] * u[c][f];
+        }
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double p = (src[c] + R.areaFac[c] * pm[c]) * inv[c];
+        src[c] = p;
+        src[rz_nb(c, 0)] += (R.rez[c][0] * R.az[c][0]) * p;
+        src[rz_nb(c, 1)] += (R.rez[c][1] * R.az[c][1]) * p;
+      }
+      const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
+      double *psi1N = psi1A + slab;
+      const double w1 = P.tauW1[a], w2 = P.tauW2[a];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const size_t r = (size_t)(c0 + (int)R.ci[c]) * G + g;
+        const double p = src[c];
+        const double pmn = starting ? p : w1 * p - w2 * pm[c];
+        psimL[r] = pmn; psi1A[r] = p;
+        if (fin) psi1N[r] = pmn;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+          if (R.exitMask & (1u << (2 * c + f))) {
+            const int row = R.row[c][f];
+            psi1A[(size_t)row * G + g] = p;
+            if (fin) psi1N[(size_t)row * G + g] = pmn;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) umt_mbar_arrive(&S.empty[s]);
+  }
+}
+
 // Dataflow kernel.  The same work items in the same topological order, but nothing waits for a whole plane: every warp takes
 // 32 (zone, group) pairs of an item, runs the static half, then each lane polls exactly the values its pair needs -- the Psi1 rows
 // behind its incident faces and the previous angle's PsiM of its corners -- until they are no longer marked (RZ_SENTINEL), solves
@@ -899,9 +1187,62 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       }
       ctx->rz_canon = canon;
       ctx->rz_recs_valid = true;
+      // what the loader warp of the pipelined kernel needs per (angle, zone in sweep order): first corner row, zone
+      std::vector<int2> zinfo(n, make_int2(0, 0));
+      for (int a = 0; a < ctx->NA; a++) {
+        if (ctx->nHyp[a] == 0) continue;
+        for (int i = 0; i < ctx->nz; i++) {
+          const int z = std::abs(ctx->nextZ[a][i]) - 1;
+          zinfo[(size_t)a * ctx->nz + i] = make_int2(ctx->h_cOffSet[z], z);
+        }
+      }
+      if (ctx->d_zinfo) { cudaFree(ctx->d_zinfo); ctx->d_zinfo = nullptr; }
+      UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_zinfo, sizeof(int2) * n));
+      UMT_CUDA(ctx, cudaMemcpy(ctx->d_zinfo, zinfo.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
+    }
+    const bool flow = ctx->rz_flow && ctx->nStages <= 1;
+    bool pipe = ctx->rz_canon && !flow && ctx->G % 2 == 0 && ctx->zones_per_item <= RZP_ZMAX && ctx->zones_per_item * ctx->G <= 64;
+    // measured at configs[1] size (40x40 tiles, G = 64): 12-17 ms against the record kernel's 5.2 ms.  The r-z sweep has 4 xi-levels of 5
+    // chained angles and ~80-zone planes: about a thousand items are ready at any time, so items a CTA holds ahead of their turn
+    // (tickets in batches, in-order release within the CTA) keep engines idle behind a waiting item while ready items sit in another
+    // CTA's queue; the record kernel takes a ticket only when its CTA is free.  Kept for experiments: UMT_RZ_KERNEL=pipe.
+    if (const char *e = getenv("UMT_RZ_KERNEL")) { if (std::string(e) != "pipe") pipe = false; } else pipe = false;
+    if (pipe) {
+      RZPGeom gm;
+      const int zpi = ctx->zones_per_item, G = ctx->G;
+      gm.zpi = zpi;
+      gm.offSt = zpi * 4 * G * 8;
+      gm.offSigt = 2 * gm.offSt;
+      gm.offRecs = gm.offSigt + zpi * G * 8;
+      gm.stageBytes = (gm.offRecs + zpi * (int)sizeof(RZRec) + 127) / 128 * 128;
+      const int budget = (227 * 1024) / RZP_MIN_CTAS - 1024 - RZP_CTL_BYTES;
+      gm.nStages = std::min(RZP_MAX_STAGES, std::max(RZP_NE + 1, std::min(RZP_NE + 4, budget / gm.stageBytes)));
+      if (const char *e = getenv("UMT_RZ_STAGES")) gm.nStages = std::max(RZP_NE + 1, std::min(RZP_MAX_STAGES, atoi(e)));
+      const size_t smemP = RZP_CTL_BYTES + (size_t)gm.nStages * gm.stageBytes;
+      UMT_CUDA(ctx, cudaFuncSetAttribute(sweeprz_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+      int occP = 0;
+      UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occP, sweeprz_pipe_kernel, RZP_THREADS, smemP));
+      if (occP < 1) UMT_FAIL(ctx, UMT_ERR_CUDA, "sweeprz_pipe_kernel does not fit on an SM");
+      if (const char *e = getenv("UMT_RZ_CTAS_PER_SM")) occP = std::max(1, std::min(occP, atoi(e)));
+      const int nSt = std::max(1, ctx->nStages);
+      for (int st = 0; st < nSt; st++) {   // reflecting boundaries: snreflect, then the angles of this stage (one stage otherwise)
+        int begin = 0, end = ctx->nItems;
+        if (ctx->nStages > 1) {
+          begin = ctx->stageItemBegin[st]; end = ctx->stageItemBegin[st + 1];
+          int r = umt_launch_reflect(ctx, st);
+          if (r) return r;
+          if (end == begin) continue;
+          if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
+        }
+        P.items = ctx->d_items + begin; P.nItems = end - begin;
+        const int grid = std::max(1, std::min(ctx->sm_count * occP, (P.nItems + 7) / 8));
+        sweeprz_pipe_kernel<<<grid, RZP_THREADS, smemP, ctx->stream>>>(P, recs, ctx->d_zinfo, gm);
+        UMT_CUDA(ctx, cudaGetLastError());
+        ctx->last_launches += 1;
+      }
+      return UMT_OK;
     }
     const size_t smem = sizeof(RZRec) * (size_t)ctx->zones_per_item;
-    const bool flow = ctx->rz_flow && ctx->nStages <= 1;
     void (*rk)(SweepRZParams, const RZRec *) = flow ? (ctx->rz_canon ? sweeprz_rec_kernel<true, true> : sweeprz_rec_kernel<true, false>)
                                                     : (ctx->rz_canon ? sweeprz_rec_kernel<false, true> : sweeprz_rec_kernel<false, false>);
     if (flow) {
