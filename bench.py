@@ -221,10 +221,34 @@ def run_reference(args):
 
 def workload_config(args):
     d = args.dims
-    return {"workload": f"BASELINE configs[4] per-domain: Blueprint 3D tiled mesh -B local -d {d},{d},{d} -G {args.groups} -P {args.polar} -A {args.azimuthal}, one domain per GPU, vacuum BCs, mini-app opacities (Sigt = 1/(c dt), STotal = 0), non-final sweep (savePsi = false)",
+    which = "BASELINE configs[4] per-domain" if (args.polar, args.azimuthal) == (2, 2) else "BASELINE configs[2] (-P 4 -A 4) at the largest domain that fits one B200" if (args.polar, args.azimuthal) == (4, 4) else "3-D tiled mesh"
+    return {"workload": f"{which}: Blueprint 3D tiled mesh -B local -d {d},{d},{d} -G {args.groups} -P {args.polar} -A {args.azimuthal}, one domain per GPU, vacuum BCs, mini-app opacities (Sigt = 1/(c dt), STotal = 0), non-final sweep (savePsi = false)",
             "zones_per_domain": 24 * d * d * d, "groups": args.groups, "angles": 8 * args.polar * args.azimuthal,
-            "l2_policy": "inputs (Psi 2x50 GB, STotal, Phi) are far larger than the 126 MB L2; no flush needed",
-            "parallelism": f"spatial domains x{args.gpus}, psib exchange lagged one flux pass"}
+            "l2_policy": "inputs (Psi, the Psi1 workspace, STotal, Phi: tens of GB) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"spatial domains x{args.gpus}, psib exchange lagged one flux pass (the transfer for the next pass overlaps the phi tally)"}
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """One rank per GPU: run this process on the cores of the GPU's NUMA node (its staging buffers come from umt_host_alloc, which
+    binds their pages to the same node).  Returns the node, or None when the platform gives no NUMA information."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------
@@ -309,6 +333,7 @@ def main():
     ap.add_argument("--polar", type=int, default=2)
     ap.add_argument("--azimuthal", type=int, default=2)
     ap.add_argument("--cpu-dims", type=int, default=0, help="tiles per side of the bounded CPU sample (default: 10 for the cpu_baseline leg, 8 per step for --impl reference)")
+    ap.add_argument("--ring", type=int, default=-1, help="Psi1 ring size in angle batches (umt_set_psi1_ring; default: as the free HBM allows)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing NCCL parity check (N > 1)")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
@@ -326,6 +351,7 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     parity = None
@@ -352,17 +378,25 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(teton.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         ctx.set_comm(rank, world, bytes(idt.cpu().numpy().tobytes()))
-    ctx.build_schedule()
+    t0 = time.perf_counter()
+    ctx.build_schedule()                      # rtorder/snnext/findexit for every angle on the host threads (the reference redoes it every cycle)
+    sched_ms = (time.perf_counter() - t0) * 1e3
     nz, nc = mesh.nzones, mesh.ncornr
     tau = PR.tau()
-    # pinned host buffers of what the Fortran caller hands over / gets back per ControlSweep
-    h_sigt = torch.full((nz, G), tau, dtype=torch.float64).pin_memory()
-    h_stotal = torch.zeros((nc, G), dtype=torch.float64).pin_memory()
-    h_phi = torch.empty((nc, G), dtype=torch.float64).pin_memory()
-    ctx.upload_state(None, None, h_sigt.numpy(), h_stotal.numpy(), tau)
+    # page-locked host buffers (on the GPU's NUMA node) of what the Fortran caller hands over / gets back per ControlSweep
+    h_sigt = ctx.host_array((nz, G)); h_sigt[:] = tau
+    h_stotal = ctx.host_array((nc, G)); h_stotal[:] = 0.0
+    h_phi = ctx.host_array((nc, G))
+    if args.ring >= 0:
+        ctx.set_psi1_ring(args.ring)
+    ctx.upload_state(None, None, h_sigt, h_stotal, tau)
     ctx.init_teton(np.full(nz, PR.TR0), PR.group_bounds(G), PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
     ctx.init_phi_total()
-    ctx.init_radiation_field()
+    t0 = time.perf_counter()
+    ctx.init_radiation_field()                # first use of the schedule: plan records, work items, Psi1 workspace
+    finalize_ms = (time.perf_counter() - t0) * 1e3
+    layout = ctx.psi_layout()
+    mem_free, mem_total = torch.cuda.mem_get_info()
     unknowns = nc * NA * G
     total_unknowns = unknowns * world
 
@@ -399,14 +433,14 @@ def main():
     value = total_unknowns / (step_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -----------------------------
-    h2d = h_sigt.numel() * 8 + h_stotal.numel() * 8
-    d2h = h_phi.numel() * 8
+    h2d = h_sigt.size * 8 + h_stotal.size * 8
+    d2h = h_phi.size * 8
     for _ in range(1):
-        ctx.control_sweep(h_sigt.numpy(), h_stotal.numpy(), tau, h_phi.numpy(), False, args.flux_iters)
+        ctx.control_sweep(h_sigt, h_stotal, tau, h_phi, False, args.flux_iters)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.control_sweep(h_sigt.numpy(), h_stotal.numpy(), tau, h_phi.numpy(), False, args.flux_iters)
+        ctx.control_sweep(h_sigt, h_stotal, tau, h_phi, False, args.flux_iters)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     if rank == 0:
@@ -434,7 +468,12 @@ def main():
                          "kernel": "sweep3d (persistent, all angles)", "bytes_per_unknown": balg, "kernel_ms": sweep_kernel_ms,
                          "peak_source": peak_src,
                          "whole_sweep_41B_model": {"bytes_per_unknown": algorithmic_bytes_per_unknown(G), "achieved": model41, "frac": model41 / peak}},
-            "kernel_ms": {"sweep": sweep_ms / args.steps, "phi": phi_ms / args.steps, "exchange": exch_ms / args.steps},
+            "kernel_ms": {"sweep": sweep_ms / args.steps, "phi": phi_ms / args.steps, "exchange": exch_ms / args.steps,
+                          "note": "exchange = unpack before the sweep + (tally, currents, transfer of the next pass's rows) on a second stream under the phi tally"},
+            "psi_layout": dict(layout, device_memory_used_GB=(mem_total - mem_free) / 1e9),
+            "setup_ms": {"build_schedule_host": sched_ms, "first_use_plan_records_items_workspace": finalize_ms,
+                         "note": "once per mesh/quadrature (the reference rebuilds its schedules every cycle, control/initializeSets.F90:95-105); not in the timed region"},
+            "host_buffers": {"numa_node": numa, "kind": "umt_host_alloc (page-locked, bound to the GPU's NUMA node)"},
             "device_ms_per_step": device_step_ms,
             "clocks": sampler.summary(),
         }

@@ -22,6 +22,8 @@
 #ifndef UMT_SWEEP_H
 #define UMT_SWEEP_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -40,6 +42,12 @@ int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int nbelem,
 int umt_ctx_destroy(umt_ctx *ctx);
 const char *umt_last_error(const umt_ctx *ctx); /* ctx may be NULL: last create error */
 const char *umt_version(void);
+
+/* Page-locked host staging memory on the NUMA node of the context's GPU, for the arrays that cross PCIe every sweep (GSet%Sigt,
+   GSet%STotal, Rad%PhiTotal: rt/ControlSweep.F90 hands them over per call).  *numaNode (may be NULL) returns the node the pages were
+   bound to, -1 if the platform gave no NUMA information (plain page-locked memory then).  Free with umt_host_free. */
+int umt_host_alloc(umt_ctx *ctx, size_t bytes, void **ptr, int *numaNode);
+int umt_host_free(umt_ctx *ctx, void *ptr);
 
 /* ---- mesh connectivity: mods/Geometry_mod.F90:19-78, aux/setTetonZone.F90 ---- */
 /* numCorner(nz), cOffSet(nz), nCFacesArray(nc), cFP(maxcf,nc), cEZ(maxcf,nc).

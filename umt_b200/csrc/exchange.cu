@@ -76,6 +76,10 @@ std::mutex g_nccl_mutex;
     if (_r != ncclSuccess) UMT_FAIL(ctx, UMT_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(_r));          \
   } while (0)
 
+// stream the exchange work of a context currently goes to: its main stream, or the second stream while umt_sweep overlaps the
+// post-sweep exchange with the phi tally
+static inline cudaStream_t xstream(const umt_ctx *ctx) { return ctx->xstream ? ctx->xstream : ctx->stream; }
+
 struct NcclTransport : UmtTransport {
   ncclComm_t comm = nullptr;
   ~NcclTransport() override { if (comm) g_nccl.CommDestroy(comm); }
@@ -84,18 +88,18 @@ struct NcclTransport : UmtTransport {
     UMT_NCCL(ctx, g_nccl.GroupStart());
     for (size_t s = 0; s < ctx->shared.size(); s++) {
       const int peer = ctx->shared[s].neighbor;
-      if (sb[s]) UMT_NCCL(ctx, g_nccl.Send(sp[s], sb[s], ncclInt8, peer, comm, ctx->stream));
-      if (rb[s]) UMT_NCCL(ctx, g_nccl.Recv(rp[s], rb[s], ncclInt8, peer, comm, ctx->stream));
+      if (sb[s]) UMT_NCCL(ctx, g_nccl.Send(sp[s], sb[s], ncclInt8, peer, comm, xstream(ctx)));
+      if (rb[s]) UMT_NCCL(ctx, g_nccl.Recv(rp[s], rb[s], ncclInt8, peer, comm, xstream(ctx)));
     }
     UMT_NCCL(ctx, g_nccl.GroupEnd());
     return UMT_OK;
   }
   int allreduce_max(umt_ctx *ctx, int *d_value) override {
-    UMT_NCCL(ctx, g_nccl.AllReduce(d_value, d_value, 1, ncclInt32, ncclMax, comm, ctx->stream));
+    UMT_NCCL(ctx, g_nccl.AllReduce(d_value, d_value, 1, ncclInt32, ncclMax, comm, xstream(ctx)));
     return UMT_OK;
   }
   int allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) override {
-    UMT_NCCL(ctx, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, op ? ncclMax : ncclSum, comm, ctx->stream));
+    UMT_NCCL(ctx, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, op ? ncclMax : ncclSum, comm, xstream(ctx)));
     return UMT_OK;
   }
 };
@@ -130,7 +134,7 @@ struct LocalTransport : UmtTransport {
   int exchange(umt_ctx *ctx, const std::vector<const void *> &sp, const std::vector<size_t> &sb, const std::vector<void *> &rp,
                const std::vector<size_t> &rb) override {
     recvPtrNow = rp; recvBytesNow = rb;
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // my send buffers are packed, my receive buffers are free
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));   // my send buffers are packed, my receive buffers are free
     grp->barrier();
     for (size_t s = 0; s < ctx->shared.size(); s++) {
       umt_ctx *peer = grp->members[ctx->shared[s].neighbor];
@@ -140,30 +144,30 @@ struct LocalTransport : UmtTransport {
         if (peer->shared[k].neighbor == ctx->myRank) t = (int)k;
       if (t < 0 || pt->recvBytesNow[t] != sb[s])
         UMT_FAIL(ctx, UMT_ERR_STATE, "local exchange: rank %d and rank %d disagree on the message size of their shared boundary", ctx->myRank, ctx->shared[s].neighbor);
-      if (sb[s]) UMT_CUDA(ctx, cudaMemcpyAsync(pt->recvPtrNow[t], sp[s], sb[s], cudaMemcpyDefault, ctx->stream));
+      if (sb[s]) UMT_CUDA(ctx, cudaMemcpyAsync(pt->recvPtrNow[t], sp[s], sb[s], cudaMemcpyDefault, xstream(ctx)));
     }
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
     grp->barrier();
     return UMT_OK;
   }
   int allreduce_max(umt_ctx *ctx, int *d_value) override {
     int v = 0;
-    UMT_CUDA(ctx, cudaMemcpyAsync(&v, d_value, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaMemcpyAsync(&v, d_value, sizeof(int), cudaMemcpyDeviceToHost, xstream(ctx)));
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
     { std::lock_guard<std::mutex> lk(grp->m); grp->redux = std::max(grp->redux, v); }
     grp->barrier();
     { std::lock_guard<std::mutex> lk(grp->m); v = grp->redux; }
     grp->barrier();
     if (ctx->myRank == 0) { std::lock_guard<std::mutex> lk(grp->m); grp->redux = 0; }
     grp->barrier();
-    UMT_CUDA(ctx, cudaMemcpyAsync(d_value, &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaMemcpyAsync(d_value, &v, sizeof(int), cudaMemcpyHostToDevice, xstream(ctx)));
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
     return UMT_OK;
   }
   int allreduce_f64(umt_ctx *ctx, double *d_vals, int n, int op) override {
     std::vector<double> v(n);
-    UMT_CUDA(ctx, cudaMemcpyAsync(v.data(), d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaMemcpyAsync(v.data(), d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, xstream(ctx)));
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
     {
       std::lock_guard<std::mutex> lk(grp->m);
       if (grp->fbuf.size() < (size_t)grp->n * n) grp->fbuf.resize((size_t)grp->n * n);
@@ -177,8 +181,8 @@ struct LocalTransport : UmtTransport {
       v[i] = a;
     }
     grp->barrier();   // nobody overwrites the buffer while another rank still reads it
-    UMT_CUDA(ctx, cudaMemcpyAsync(d_vals, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UMT_CUDA(ctx, cudaMemcpyAsync(d_vals, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, xstream(ctx)));
+    UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
     return UMT_OK;
   }
 };
@@ -590,10 +594,10 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   for (size_t k = 0; k < nS; k++) {
     SharedBdy &s = ctx->shared[k];
     if (s.nChunks > 0) {
-      pack_tally_kernel<<<s.nChunks, 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
+      pack_tally_kernel<<<s.nChunks, 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
       ctx->last_launches++;
     }
-    tally_finish_kernel<<<(NA + 127) / 128, 128, 0, ctx->stream>>>(s.d_partial, s.d_nChunksOfAngle, s.maxChunks, ctx->d_exitFlux + k * NA, NA);
+    tally_finish_kernel<<<(NA + 127) / 128, 128, 0, xstream(ctx)>>>(s.d_partial, s.d_nChunksOfAngle, s.maxChunks, ctx->d_exitFlux + k * NA, NA);
     ctx->last_launches++;
     sp[k] = ctx->d_exitFlux + k * NA; rp[k] = ctx->d_incRecv + k * NA; sb[k] = rb[k] = sizeof(double) * NA;
   }
@@ -601,15 +605,17 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
   if (r) return r;
   const int binsPerSet = (ctx->ndim == 3 && ctx->nCommSets > 0) ? ctx->NA / ctx->nCommSets : 1;
-  flux_conv_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, binsPerSet, ctx->d_incFlux,
+  flux_conv_kernel<<<1, 32, 0, xstream(ctx)>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, binsPerSet, ctx->d_incFlux,
                                               ctx->d_incFluxOld, tol, ctx->fluxFloor, ctx->d_nNotConv);
   UMT_CUDA(ctx, cudaGetLastError());
   ctx->last_launches++;
   return UMT_OK;
 }
 
-// SendFlux / RecvFlux for every angle: what the neighbours packed after their previous sweep lands in my incident rows
-int umt_exchange_begin_pass(umt_ctx *ctx) {
+// SendFlux / RecvFlux for every angle, first half: the rows every domain packed after its last sweep travel to the neighbours'
+// receive buffers (collective).  umt_sweep issues this right after the post-sweep tally, on the second stream, so that the
+// transfer of the NEXT pass's incident rows overlaps the phi tally of this one (the exchange is lagged one pass anyway).
+int umt_exchange_rows(umt_ctx *ctx) {
   int r = ready(ctx);
   if (r) return r;
   const int G = ctx->G;
@@ -620,13 +626,18 @@ int umt_exchange_begin_pass(umt_ctx *ctx) {
     sp[k] = s.d_sendbuf; rp[k] = s.d_recvbuf;
     sb[k] = sizeof(double) * s.send_rows * G; rb[k] = sizeof(double) * s.recv_rows * G;
   }
-  r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
-  if (r) return r;
+  return ctx->transport->exchange(ctx, sp, sb, rp, rb);
+}
+
+// second half: the received rows land in my incident PsiB rows (RecvFlux.F90:68-78)
+int umt_exchange_unpack(umt_ctx *ctx) {
+  const int G = ctx->G;
+  const size_t nS = ctx->shared.size();
   for (size_t k = 0; k < nS; k++) {
     SharedBdy &s = ctx->shared[k];
     const long long n = (long long)s.recv_rows * G;
     if (n > 0) {
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->psib_buf(), s.d_recv_row, s.d_recvbuf, n, G);
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_recv_row, s.d_recvbuf, n, G);
       ctx->last_launches++;
     }
   }
@@ -638,8 +649,8 @@ int umt_exchange_begin_pass(umt_ctx *ctx) {
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv) {
   int r = ctx->transport->allreduce_max(ctx, ctx->d_nNotConv);
   if (r) return r;
-  UMT_CUDA(ctx, cudaMemcpyAsync(nNotConv, ctx->d_nNotConv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  UMT_CUDA(ctx, cudaMemcpyAsync(nNotConv, ctx->d_nNotConv, sizeof(int), cudaMemcpyDeviceToHost, xstream(ctx)));
+  UMT_CUDA(ctx, cudaStreamSynchronize(xstream(ctx)));
   return UMT_OK;
 }
 

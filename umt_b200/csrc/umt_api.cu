@@ -5,6 +5,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "umt_internal.h"
 
@@ -57,7 +60,9 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking);
   for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evx[i]);
   if (e != cudaSuccess) {
     g_create_error = std::string("umt_ctx_create: ") + cudaGetErrorString(e);
     delete ctx;
@@ -96,14 +101,85 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_start, ctx->d_finishNext, ctx->d_level, ctx->d_reflOps, ctx->d_rzLevelAngles, ctx->d_rzPlaneOff, ctx->d_rzNHyp,
                   ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad, ctx->d_itemsRing, ctx->d_tailSlot, ctx->d_tailW};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (auto &b : ctx->host_blocks) { cudaHostUnregister(b.first); munmap(b.first, b.second); }   // umt_host_alloc blocks never freed
+  ctx->host_blocks.clear();
   umt_exchange_release(ctx);
   umt_gta_release(ctx);
   // hand the device-wide L2 set-aside back (the last 3-D context to go restores what it found)
   if (ctx->l2_persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_before) != cudaSuccess) cudaGetLastError();
   for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 3; i++) if (ctx->evx[i]) cudaEventDestroy(ctx->evx[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   delete ctx;
+  return UMT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host staging buffers next to the GPU
+// ---------------------------------------------------------------------------
+// Page-locked host memory whose pages sit on the NUMA node of the context's GPU (the node of its PCIe root, from sysfs), for the
+// arrays a caller hands to umt_control_sweep / umt_upload_* / umt_download_* every sweep.  With one rank per GPU on a two-socket
+// box, buffers pinned wherever the rank happened to run cross the socket interconnect on every copy (measured in round 1: 8 ranks
+// moved 3.3 GB per step each at 15 GB/s instead of 55).  The pages are placed by first touch under a preferred-node memory policy
+// and then registered with CUDA; without NUMA information this is a plain page-locked allocation.
+
+namespace {
+int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+}  // namespace
+
+extern "C" int umt_host_alloc(umt_ctx *ctx, size_t bytes, void **ptr, int *numaNode) {
+  if (!ctx || !ptr || bytes == 0) return UMT_ERR_ARG;
+  NEED_DEVICE(ctx, "umt_host_alloc");
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  *ptr = nullptr;
+  const long page = sysconf(_SC_PAGESIZE);
+  const size_t len = (bytes + page - 1) / page * page;
+  void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_host_alloc: mmap of %zu bytes failed", len);
+  const int node = gpu_numa_node(ctx->device);
+  bool bound = false;
+#ifdef SYS_mbind
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, mask, 8 * sizeof(mask), 0) == 0;
+  }
+#endif
+  for (size_t o = 0; o < len; o += page) static_cast<volatile char *>(p)[o] = 0;   // first touch: the pages exist where the policy says
+  cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    munmap(p, len);
+    UMT_FAIL(ctx, UMT_ERR_CUDA, "umt_host_alloc: cudaHostRegister of %zu bytes: %s", len, cudaGetErrorString(e));
+  }
+  ctx->host_blocks[p] = len;
+  if (numaNode) *numaNode = bound ? node : -1;
+  *ptr = p;
+  return UMT_OK;
+}
+
+extern "C" int umt_host_free(umt_ctx *ctx, void *ptr) {
+  if (!ptr) return UMT_OK;
+  if (!ctx) return UMT_ERR_ARG;
+  auto it = ctx->host_blocks.find(ptr);
+  if (it == ctx->host_blocks.end()) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_host_free: not a block of this context's umt_host_alloc");
+  const size_t len = it->second;
+  ctx->host_blocks.erase(it);
+  cudaHostUnregister(ptr);
+  munmap(ptr, len);
   return UMT_OK;
 }
 
@@ -626,6 +702,7 @@ extern "C" int umt_upload_state(umt_ctx *ctx, const double *Psi, const double *P
   TRY(ensure_state(ctx));
   const size_t G = ctx->G, nc = ctx->nc, nb = ctx->nb, NA = ctx->NA, pitch = G * ctx->rows * 8;
   if (Psi) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi, pitch, Psi, G * nc * 8, G * nc * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
+  if (PsiB && nb) ctx->pack_valid = ctx->recv_valid = false;
   if (PsiB && nb) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->psib_buf() + G * nc, pitch, PsiB, G * nb * 8, G * nb * 8, NA, cudaMemcpyHostToDevice, ctx->stream));
   if (Sigt) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt, sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, ctx->stream));
   if (STotal) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal, sizeof(double) * G * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -648,6 +725,7 @@ static int set_copy(umt_ctx *ctx, int g0, int Groups, int angle0, int NumAngles,
       if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
       else UMT_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)Groups * 8, d, G * 8, (size_t)Groups * 8, nc, kind, ctx->stream));
     }
+    if (PsiB && nb && up) ctx->pack_valid = ctx->recv_valid = false;
     if (PsiB && nb) {
       double *d = ctx->psib_buf() + ((size_t)(angle0 + a) * ctx->rows + nc) * G + g0, *h = PsiB + (size_t)a * nb * Groups;
       if (up) UMT_CUDA(ctx, cudaMemcpy2DAsync(d, G * 8, h, (size_t)Groups * 8, (size_t)Groups * 8, nb, kind, ctx->stream));
@@ -916,6 +994,7 @@ extern "C" int umt_set_boundary_sources(umt_ctx *ctx) {
   if (!ctx) return UMT_ERR_ARG;
   if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   TRY(ensure_state(ctx));
+  ctx->pack_valid = ctx->recv_valid = false;
   if (ctx->nb > 0) {
     const size_t G = ctx->G;
     UMT_CUDA(ctx, cudaMemset2DAsync(ctx->psib_buf() + G * ctx->nc, G * ctx->rows * 8, 0, G * ctx->nb * 8, ctx->NA, ctx->stream));
@@ -929,6 +1008,7 @@ extern "C" int umt_init_radiation_field(umt_ctx *ctx) {
   if (ctx->device >= 0) UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   TRY(ensure_state(ctx));
   TRY(finalize_schedule(ctx));
+  ctx->pack_valid = ctx->recv_valid = false;
   if (ctx->nExit > 0) {
     const size_t n = (size_t)ctx->nExit * ctx->G;
     exit_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi, ctx->psib_buf(), ctx->d_exitB, ctx->d_exitC,
@@ -980,12 +1060,19 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   int iter = 0;
   const bool multi = !ctx->shared.empty();
 
-  if (multi) TRY(umt_exchange_tally(ctx, fluxTol));   // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74); packs the exiting rows
+  const bool staged = multi && ctx->have_comm_order;   // comm sets of several bins exchange step by step inside umt_launch_sweep3d
+  bool overlapped = false;
+  // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74): packs the exiting rows and tallies the exit currents -- unless the
+  // tally that followed the previous sweep still describes the PsiB on the device
+  if (multi && !ctx->pack_valid) { TRY(umt_exchange_tally(ctx, fluxTol)); ctx->pack_valid = true; ctx->recv_valid = false; }
   for (;;) {
     iter++;
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (multi && !ctx->have_comm_order) TRY(umt_exchange_begin_pass(ctx));   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
-    // (comm sets of several bins exchange step by step inside umt_launch_sweep3d)
+    if (multi && !staged) {   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
+      if (!ctx->recv_valid) TRY(umt_exchange_rows(ctx));
+      TRY(umt_exchange_unpack(ctx));
+      ctx->recv_valid = false;
+    }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (ctx->totalCycles > 0) {                     // initFromCycleList (meshes with cycle lists keep the legacy layout)
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
@@ -1003,19 +1090,50 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
     }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     int nNotConv = 0;
-    if (multi) {                                     // setIncidentFlux + testFluxConv + Allreduce(max nNotConv)
+    const bool last = savePsi || iter >= maxFluxIters;   // SetSweep.F90:185-187: no further pass whatever the fluxes say
+    if (multi && last) {
+      // setIncidentFlux + testFluxConv of the last pass, and already the transfer of the rows the NEXT pass will start from (the
+      // exchange is lagged one pass), on a stream of their own: they run under the phi tally below.  nNotConv is not needed.
+      UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev[3], 0));
+      UMT_CUDA(ctx, cudaEventRecord(ctx->evx[0], ctx->stream3));
+      ctx->xstream = ctx->stream3;
+      int r = umt_exchange_tally(ctx, fluxTol);
+      if (!r && !staged) { r = umt_exchange_rows(ctx); ctx->recv_valid = !r; }
+      ctx->xstream = nullptr;
+      if (r) return r;
+      ctx->pack_valid = true;
+      UMT_CUDA(ctx, cudaEventRecord(ctx->evx[1], ctx->stream3));
+      overlapped = true;
+    } else if (multi) {                               // setIncidentFlux + testFluxConv + Allreduce(max nNotConv)
       TRY(umt_exchange_tally(ctx, fluxTol));
+      ctx->pack_valid = true;
       TRY(umt_exchange_test_convergence(ctx, &nNotConv));
     }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    if (!last || !multi) UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    if (last) break;
     float t;
     cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]); ms_exch += t;
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_sweep += t;
     cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ms_exch += t;
-    if (savePsi) break;                              // SetSweep.F90:185-187
-    if (nNotConv == 0 || iter >= maxFluxIters) break;
+    if (nNotConv == 0) {   // converged early: the next pass's rows can travel under the phi tally as well
+      if (multi && !staged) {
+        UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev[4], 0));
+        UMT_CUDA(ctx, cudaEventRecord(ctx->evx[0], ctx->stream3));
+        ctx->xstream = ctx->stream3;
+        const int r = umt_exchange_rows(ctx);
+        ctx->xstream = nullptr;
+        if (r) return r;
+        ctx->recv_valid = true;
+        UMT_CUDA(ctx, cudaEventRecord(ctx->evx[1], ctx->stream3));
+        overlapped = true;
+      }
+      iter = -iter;   // marks "left the loop with the pass already accounted for"
+      break;
+    }
   }
+  const bool timedInLoop = iter < 0;
+  if (iter < 0) iter = -iter;
 
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   if (!hostPhi) {
@@ -1034,9 +1152,16 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
       UMT_CUDA(ctx, cudaMemcpyAsync(hostPhi + o, ctx->d_phi + o, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream2));
     }
   }
+  if (overlapped) UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evx[1], 0));   // the call ends when the exchange has, too
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
   UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
   if (hostPhi) UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+  if (!timedInLoop) {   // the last pass (its events were not read inside the loop)
+    float t;
+    cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]); ms_exch += t;
+    cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_sweep += t;
+  }
+  if (overlapped) { float t; cudaEventElapsedTime(&t, ctx->evx[0], ctx->evx[1]); ms_exch += t; }
   cudaEventElapsedTime(&ms_phi, ctx->ev[5], ctx->ev[6]);
   cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
   if (savePsi && !ctx->single_psi) {

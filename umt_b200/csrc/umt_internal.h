@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -126,8 +127,12 @@ struct umt_ctx {
   int sm_count = 0;
   bool l2_persist = false;             // the 3-D sweep runs with an L2 set-aside for its evict_last Psi1 lines
   size_t l2_persist_bytes = 0, l2_persist_before = 0;   // before: the device limit found at creation, restored at destroy
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; phi chunks -> host; overlapped exchange
+  cudaStream_t xstream = nullptr;      // where exchange work goes right now (nullptr: the main stream), see exchange.cu
+  cudaEvent_t ev[8] = {}, evx[3] = {};
+  // lagged exchange state: the send buffers hold the exiting rows of the current PsiB / the receive buffers already hold what
+  // the neighbours packed after their last sweep (the transfer was overlapped with the phi tally of that sweep)
+  bool pack_valid = false, recv_valid = false;
 
   // host copies (for schedule builder, exit lists, tallies)
   std::vector<int> h_numCorner, h_cOffSet, h_nCFaces, h_cFP, h_cEZ, h_zoneFaces, h_zoneOpp, h_faceOpp, h_CToFace, h_BdyToC;
@@ -239,6 +244,7 @@ struct umt_ctx {
   int rows_total() const { return nc + nb; }
 
   GtaState gta;
+  std::map<void *, size_t> host_blocks;   // umt_host_alloc: live blocks and their mapped length
 
   // stats
   double last_ms[4] = {0, 0, 0, 0};
@@ -292,7 +298,8 @@ void umt_gta_release(umt_ctx *ctx);
 int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vector<int> &nHyp, std::vector<std::vector<int>> &zonesInPlane,
                          std::vector<std::vector<int>> &nextZ, std::vector<std::vector<int>> &nextC);
 int umt_exchange_tally(umt_ctx *ctx, double tol);
-int umt_exchange_begin_pass(umt_ctx *ctx);
+int umt_exchange_rows(umt_ctx *ctx);      // collective: packed exiting rows -> the neighbours' receive buffers
+int umt_exchange_unpack(umt_ctx *ctx);    // receive buffers -> incident PsiB rows
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);
 int umt_exchange_stage(umt_ctx *ctx, int step);               // SendFlux / RecvFlux of one sweep step (staged comm sets)
 int umt_exchange_build_stages(umt_ctx *ctx);

@@ -80,6 +80,9 @@ class SweepContext:
 
     def close(self):
         if self.h:
+            for ptr in getattr(self, "_host_blocks", []):
+                self.lib.umt_host_free(self.h, ptr)
+            self._host_blocks = []
             self.lib.umt_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -217,6 +220,18 @@ class SweepContext:
         self._ck(self.lib.umt_get_psi_layout(self.h, _ip(info), C.byref(b)), "umt_get_psi_layout")
         return dict(single=bool(info[0]), psi1_slabs=int(info[1]), angle_batch=int(info[2]), ring_batches=int(info[3]),
                     batches=int(info[4]), angles_tallied_in_sweep=int(info[5]), bytes=b.value)
+
+    def host_array(self, shape):
+        """float64 array in page-locked host memory on the NUMA node of this context's GPU (umt_host_alloc); freed with the context"""
+        n = int(np.prod(shape))
+        ptr, node = C.c_void_p(), C.c_int(-1)
+        self._ck(self.lib.umt_host_alloc(self.h, C.c_size_t(max(n, 1) * 8), C.byref(ptr), C.byref(node)), "umt_host_alloc")
+        if not hasattr(self, "_host_blocks"):
+            self._host_blocks = []
+        self._host_blocks.append(ptr)
+        self.host_numa_node = node.value
+        buf = (C.c_double * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
 
     # -- hot path ------------------------------------------------------------
     def sweep(self, savePsi=False, maxFluxIters=1, fluxTol=1e-6):
