@@ -213,8 +213,8 @@ int umt_set_flux_floor(umt_ctx *ctx, double floorFlux);
 
 /* ---- end-of-cycle edits on the device-resident fields: aux/rtedit.F90:142-232, control/BoundaryEdit.F90, setEnergyDensity.F90 ---- */
 /* out5 = {EnergyRadiation, TrMax, PowerEscape, PowerIncident (0 without source boundaries), sum_zones sum_c V_c sum_g PhiTotal};
-   optional (NULL to skip): Mat%trz(nzones), RadEdit%RadPowerEscape(ngr), Rad%RadEnergyDensity(nzones, ngr).  3-D only so far for the
-   boundary edit.  Escape currents use Set%Psi at the boundary corners as the reference does (call after the savePsi sweep). */
+   optional (NULL to skip): Mat%trz(nzones), RadEdit%RadPowerEscape(ngr), Rad%RadEnergyDensity(nzones, ngr).  3-D and r-z (the r-z
+   boundary edit carries geometryFactor = 2 pi and the radius of the boundary element, control/BoundaryEdit.F90:123).  Escape currents use Set%Psi at the boundary corners as the reference does (call after the savePsi sweep). */
 int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConstant, double tr4floor, double *out5, double *trz,
                     double *RadPowerEscape, double *RadEnergyDensity);
 

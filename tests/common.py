@@ -411,6 +411,35 @@ def oracle_cycle_3d(p, dt, tr4floor):
                 EnergyRadBOC=e_boc, EnergyCheck=dt * (0.0 - float(esc.sum())) - d_erad, phi=phi)
 
 
+def oracle_cycle_rz(p, dt, tr4floor):
+    """The same time step in r-z: geometryFactor = 2 pi (Size_mod.F90:275), Volume is volume / 2 pi (volumeUCBrz.F90:127-135),
+    the boundary edit carries the radius of the boundary element (BoundaryEdit.F90:123) and only weighted angles are tallied."""
+    m = p.mesh
+    V = p.geom["Volume"]
+    gf = 2.0 * np.pi
+    p.PsiB[:] = 0.0
+    phi0 = np.einsum("a,acg->cg", p.weight, p.Psi)
+    for a in range(p.NA):
+        for b, c in p.bdy[a]:
+            p.PsiB[a, b - 1] = p.Psi[a, c - 1]
+    e_boc = gf * float((V[:, None] * phi0).sum()) / SPEED_LIGHT
+    for _ in range(2):
+        oracle_sweep_rz(p, False)
+    phi = oracle_sweep_rz(p, True)
+    erad_z = np.add.reduceat((V[:, None] * phi).sum(1), m.cOffSet)
+    e_rad = gf * float(erad_z.sum()) / SPEED_LIGHT
+    trz = np.sqrt(np.sqrt(np.maximum(erad_z / (p.geom["VolumeZone"] * RAD_CONSTANT * SPEED_LIGHT), tr4floor)))
+    esc = np.zeros(p.G)
+    for a in range(p.NA):
+        if not p.weight[a] > 0.0:
+            continue
+        for b, c in p.bdy[a]:
+            esc += p.weight[a] * gf * p.geom["RadiusB"][b - 1] * float(p.geom["A_bdy"][b - 1] @ p.omega[a]) * p.Psi[a, c - 1]
+    d_erad = e_rad - e_boc
+    return dict(EnergyRadiation=e_rad, TrMax=float(trz.max()), PowerEscape=float(esc.sum()), RadPowerEscape=esc, trz=trz,
+                EnergyRadBOC=e_boc, EnergyCheck=dt * (0.0 - float(esc.sum())) - d_erad, phi=phi)
+
+
 # ---------------------------------------------------------------------------
 # multi-domain GTA (GTASweep.F90:66-76,139-146 exchange + GTASolver.F90 with its MPIAllReduce calls), lock step on every rank
 # ---------------------------------------------------------------------------

@@ -44,3 +44,28 @@ def test_cycles_match_oracle(mk, P, A, G):
     d_ref = np.add.reduceat(V[:, None] * ref["phi"], mesh.cOffSet, axis=0) / p.geom["VolumeZone"][:, None] / PR.SPEED_LIGHT
     assert T.relerr(dens["RadEnergyDensity"], d_ref) <= 1e-12
     ctx.close()
+
+
+def test_rz_cycles_match_oracle():
+    """The r-z mini-app time step (BASELINE configs[1]'s geometry): boundary edit with the 2 pi r factor (BoundaryEdit.F90:123),
+    energies with geometryFactor = 2 pi, three cycles to 1e-10."""
+    G = 4
+    mesh = M.tiled_mesh((3, 3, 0))
+    p = T.make_problem_rz(mesh, 2, 2, G, driver_like=True)
+    p.tau = PR.tau()
+    p.Sigt[:] = p.tau
+    B = planck_groups(PR.TR0, PR.group_bounds(G), 1.0, PR.SPEED_LIGHT * PR.RAD_CONSTANT)
+    p.Psi[:] = PR.wtiso(2) * B
+    ctx = T.gpu_context_rz(p, own_schedule=True)
+    cyc = MiniAppCycle(ctx, mesh, G)
+    assert T.relerr(ctx.download_psi(), p.Psi) <= 1e-13
+    for _ in range(3):
+        ref = T.oracle_cycle_rz(p, PR.DT, PR.TFLOOR ** 4)
+        ed = cyc.step()
+        for k in ("EnergyRadiation", "TrMax", "PowerEscape", "EnergyRadBOC"):
+            assert abs(ed[k] - ref[k]) <= 1e-10 * abs(ref[k]), k
+        assert T.relerr(ed["RadPowerEscape"], ref["RadPowerEscape"]) <= 1e-10
+        assert T.relerr(ctx.download_phi(), ref["phi"]) <= 1e-12
+        assert abs(ed["EnergyCheck"] / ed["EnergyRadiation"]) <= 1e-9
+        assert abs(ref["EnergyCheck"] / ref["EnergyRadiation"]) <= 1e-9
+    ctx.close()

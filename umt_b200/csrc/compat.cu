@@ -66,19 +66,19 @@ extern "C" void gpu_sweepucbxyz(int *Angle, int *nHyperPlanes, int *nZonesInPlan
   MUST(ctx, umt_upload_state(ctx, Psi, PsiB, Sigt, STotal, *tau));
   MUST(ctx, umt_finalize_schedule(ctx));
   // previous Psi1 (read by the "direct solve" zones, :479-496) and this angle's cyclePsi rows (initFromCycleList, :858)
-  MUST_CUDA(ctx, cudaMemcpy(ctx->d_psi1, Psi1, sizeof(double) * G * (size_t)nc, cudaMemcpyHostToDevice));
+  MUST_CUDA(ctx, umt_memcpy(ctx, ctx->d_psi1, Psi1, sizeof(double) * G * (size_t)nc, cudaMemcpyHostToDevice));
   if (*numCycles > 0)
-    MUST_CUDA(ctx, cudaMemcpy(ctx->d_cyclePsi, cyclePsi + (size_t)G * *cycleOffSet, sizeof(double) * G * (size_t)*numCycles,
+    MUST_CUDA(ctx, umt_memcpy(ctx, ctx->d_cyclePsi, cyclePsi + (size_t)G * *cycleOffSet, sizeof(double) * G * (size_t)*numCycles,
                               cudaMemcpyHostToDevice));
   int iters = 0;
   MUST(ctx, umt_sweep(ctx, 0, 1, 0.0, &iters));
   // results back into the caller's arrays (:966-993)
-  MUST_CUDA(ctx, cudaMemcpy(Psi1, ctx->d_psi1, sizeof(double) * G * (size_t)nc, cudaMemcpyDeviceToHost));
-  if (nb > 0) MUST_CUDA(ctx, cudaMemcpy(PsiB, ctx->d_psi1 + (size_t)G * nc, sizeof(double) * G * (size_t)nb, cudaMemcpyDeviceToHost));
+  MUST_CUDA(ctx, umt_memcpy(ctx, Psi1, ctx->d_psi1, sizeof(double) * G * (size_t)nc, cudaMemcpyDeviceToHost));
+  if (nb > 0) MUST_CUDA(ctx, umt_memcpy(ctx, PsiB, ctx->d_psi1 + (size_t)G * nc, sizeof(double) * G * (size_t)nb, cudaMemcpyDeviceToHost));
   MUST(ctx, umt_download_phi(ctx, s.phi.data()));                 // quadwt * Psi1 of this angle
   for (size_t i = 0, n = (size_t)G * nc; i < n; i++) Phi[i] += s.phi[i];   // Set%Phi += quadwt*Psi1 (:465)
   if (*numCycles > 0)
-    MUST_CUDA(ctx, cudaMemcpy(cyclePsi + (size_t)G * *cycleOffSet, ctx->d_cyclePsi, sizeof(double) * G * (size_t)*numCycles,
+    MUST_CUDA(ctx, umt_memcpy(ctx, cyclePsi + (size_t)G * *cycleOffSet, ctx->d_cyclePsi, sizeof(double) * G * (size_t)*numCycles,
                               cudaMemcpyDeviceToHost));
   if (*savePsi == 1) std::memcpy(Psi, Psi1, sizeof(double) * G * (size_t)nc);   // (:974-978)
 }

@@ -29,6 +29,16 @@ __device__ __forceinline__ void umt_st_relaxed_f64(double *p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// Watchdog of the dataflow polling loops: a value that never turns real (a caller's array that carries the mark's bit pattern, an
+// uninitialised row) must end in an error, not in a hung GPU.  Every 256 polls a thread looks at the launch's abort flag; a thread
+// that has polled `limit` times raises it.  Pollers then leave their loops with whatever they hold (the sweep's result is discarded:
+// the host sees the flag and returns UMT_ERR_STATE).
+__device__ __forceinline__ bool umt_spin_expired(unsigned &polls, int *abortFlag, unsigned limit) {
+  if ((++polls & 255u) != 0u) return false;
+  if (polls >= limit) atomicExch(abortFlag, 1);
+  return *reinterpret_cast<volatile int *>(abortFlag) != 0;
+}
+
 // mbarrier / 1-D TMA (cp.async.bulk) helpers for the pipelined r-z sweep (sweeprz.cu); sweep3d.cu keeps its own copies
 __device__ __forceinline__ unsigned umt_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void umt_mbar_init(unsigned long long *bar, int count) {

@@ -3,7 +3,8 @@
 //                                     trz(zone) = (max(ERad / (VolumeZone a c), tr4floor))^(1/4), TrMax
 //   control/initializeZones.F90:25-50 Rad%radEnergy(zone), EnergyRadBOC (same sum at the start of the cycle)
 //   control/BoundaryEdit.F90:55-150   RadPowerEscape(g) = sum over vacuum boundary elements and weighted angles with
-//                                     omega.A_bdy > 0 of w (omega.A_bdy) Psi(g, BdyToC(b), angle)   (no mesh motion: lambdaD = 1)
+//                                     omega.A_bdy > 0 of w (omega.A_bdy) Psi(g, BdyToC(b), angle)   (no mesh motion: lambdaD = 1);
+//                                     r-z (:123): times geometryFactor = 2 pi and the radius of the boundary element
 //   control/setEnergyDensity.F90      RadEnergyDensity(zone,g) = sum_c (V_c / VolumeZone) PhiTotal(g,c) / c
 // Sums are two-stage and ordered (deterministic).
 #include <algorithm>
@@ -116,7 +117,7 @@ extern "C" int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConsta
     sum_max_finish_kernel<<<1, 32, 0, ctx->stream>>>(d_part, NB, d_out);
     e = cudaMemcpyAsync(h2, d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess && trz) e = cudaMemcpy(trz, d_trz, sizeof(double) * nz, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && trz) e = umt_memcpy(ctx, trz, d_trz, sizeof(double) * nz, cudaMemcpyDeviceToHost);
   }
   // escape through vacuum boundary elements (neither shared nor reflecting), weighted angles only
   double escape = 0.0;
@@ -146,7 +147,15 @@ extern "C" int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConsta
         double dot = 0.0;
         for (int d = 0; d < nd; d++) dot += ctx->h_omega[(size_t)a * nd + d] * ctx->h_Abdy[(size_t)b * nd + d];
         double factor = ctx->h_weight[a] * geometryFactor;
-        if (nd == 2) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_cycle_edits: the RZ boundary edit (BdyT%%Radius factor) is not implemented yet");
+        if (nd == 2) {
+          // BoundaryEdit.F90:123: factor = weight * geometryFactor * BdyT%Radius(b), and Radius(b) is the RadiusFP of the corner face
+          // the boundary element sits on (volumeUCBrz.F90:102-113 and geometryUCBrz.F90:84-85 are the same expressions)
+          if (ctx->h_RadiusFP.size() != 2 * (size_t)ctx->nc) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_cycle_edits: r-z boundary edit needs RadiusFP (umt_set_geometry / umt_compute_geometry)");
+          int f = -1;
+          for (int k = 0; k < ctx->h_nCFaces[c]; k++) if (ctx->h_cFP[(size_t)c * ctx->maxcf + k] == ctx->nc + b + 1) f = k;
+          if (f < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_cycle_edits: boundary element %d is not a face of corner %d", b + 1, c + 1);
+          factor *= ctx->h_RadiusFP[(size_t)c * 2 + f];
+        }
         ec.push_back(c); ea.push_back(a); coef.push_back(factor * dot);
       }
     }
@@ -159,9 +168,9 @@ extern "C" int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConsta
       if (e == cudaSuccess) e = cudaMalloc((void **)&d_coef, sizeof(double) * nE);
       if (e == cudaSuccess) e = cudaMalloc((void **)&d_p, sizeof(double) * (size_t)nChunks * G);
       if (e == cudaSuccess) {
-        cudaMemcpy(d_ec, ec.data(), sizeof(int) * nE, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_ea, ea.data(), sizeof(int) * nE, cudaMemcpyHostToDevice);
-        cudaMemcpy(d_coef, coef.data(), sizeof(double) * nE, cudaMemcpyHostToDevice);
+        umt_memcpy(ctx, d_ec, ec.data(), sizeof(int) * nE, cudaMemcpyHostToDevice);
+        umt_memcpy(ctx, d_ea, ea.data(), sizeof(int) * nE, cudaMemcpyHostToDevice);
+        umt_memcpy(ctx, d_coef, coef.data(), sizeof(double) * nE, cudaMemcpyHostToDevice);
         escape_partial_kernel<<<nChunks, 128, 0, ctx->stream>>>(ctx->d_psi, d_ec, d_ea, d_coef, nE, perChunk, ctx->rows, G, d_p);
         escape_finish_kernel<<<(G + 127) / 128, 128, 0, ctx->stream>>>(d_p, nChunks, G, d_out + 2);
         e = cudaMemcpyAsync(hEsc.data(), d_out + 2, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream);
@@ -178,7 +187,7 @@ extern "C" int umt_cycle_edits(umt_ctx *ctx, double speedLight, double radConsta
       const size_t n = (size_t)nz * G;
       energy_density_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(nz, G, ctx->d_numCorner, ctx->d_cOffSet, ctx->d_Volume, ctx->d_phi, geometryFactor / speedLight, d_dens);
       e = cudaStreamSynchronize(ctx->stream);
-      if (e == cudaSuccess) e = cudaMemcpy(RadEnergyDensity, d_dens, sizeof(double) * n, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = umt_memcpy(ctx, RadEnergyDensity, d_dens, sizeof(double) * n, cudaMemcpyDeviceToHost);
     }
     cudaFree(d_dens);
   }

@@ -264,7 +264,7 @@ template <class T>
 int upload(umt_ctx *ctx, T **d, const std::vector<T> &h) {
   if (*d) { cudaFree(*d); *d = nullptr; }
   UMT_CUDA(ctx, cudaMalloc((void **)d, sizeof(T) * std::max<size_t>(h.size(), 1)));
-  if (!h.empty()) UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  if (!h.empty()) UMT_CUDA(ctx, umt_memcpy(ctx, *d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 
@@ -442,7 +442,7 @@ static int exchange_incident_tests(umt_ctx *ctx) {
     std::vector<signed char> mine(n);
     rc = umt_get_incident_test(ctx, (int)k, mine.data());
     if (!rc && (cudaMalloc((void **)&dS[k], n) != cudaSuccess || cudaMalloc((void **)&dR[k], n) != cudaSuccess)) { ctx->err = "cudaMalloc (incident test)"; rc = UMT_ERR_CUDA; }
-    if (!rc) cudaMemcpy(dS[k], mine.data(), n, cudaMemcpyHostToDevice);
+    if (!rc) umt_memcpy(ctx, dS[k], mine.data(), n, cudaMemcpyHostToDevice);
     sp[k] = dS[k]; rp[k] = dR[k]; sb[k] = rb[k] = n;
   }
   if (!rc) rc = ctx->transport->exchange(ctx, sp, sb, rp, rb);
@@ -451,7 +451,7 @@ static int exchange_incident_tests(umt_ctx *ctx) {
     if (!rc) {
       SharedBdy &s = ctx->shared[k];
       s.incTestR.resize((size_t)s.n * ctx->NA);
-      cudaMemcpy(s.incTestR.data(), dR[k], s.incTestR.size(), cudaMemcpyDeviceToHost);
+      umt_memcpy(ctx, s.incTestR.data(), dR[k], s.incTestR.size(), cudaMemcpyDeviceToHost);
     }
     if (dS[k]) cudaFree(dS[k]);
     if (dR[k]) cudaFree(dR[k]);
@@ -659,8 +659,8 @@ extern "C" int umt_get_incident_flux(umt_ctx *ctx, double *incFlux, double *incF
   if (!ctx->d_incFlux) UMT_FAIL(ctx, UMT_ERR_STATE, "no exchange state");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (incFlux) UMT_CUDA(ctx, cudaMemcpy(incFlux, ctx->d_incFlux, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
-  if (incFluxOld) UMT_CUDA(ctx, cudaMemcpy(incFluxOld, ctx->d_incFluxOld, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
+  if (incFlux) UMT_CUDA(ctx, umt_memcpy(ctx, incFlux, ctx->d_incFlux, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
+  if (incFluxOld) UMT_CUDA(ctx, umt_memcpy(ctx, incFluxOld, ctx->d_incFluxOld, sizeof(double) * ctx->nBins, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 
@@ -711,13 +711,13 @@ int umt_gta_build_exchange(umt_ctx *ctx) {
           mine[k][(size_t)a * s.n + b] = dot < 0.0 ? -1 : (dot > 0.0 ? 1 : 0);
         }
     if (cudaMalloc((void **)&dS[k], n) != cudaSuccess || cudaMalloc((void **)&dR[k], n) != cudaSuccess) { ctx->err = "cudaMalloc (GTA incident test)"; rc = UMT_ERR_CUDA; }
-    if (!rc) cudaMemcpy(dS[k], mine[k].data(), n, cudaMemcpyHostToDevice);
+    if (!rc) umt_memcpy(ctx, dS[k], mine[k].data(), n, cudaMemcpyHostToDevice);
     sp[k] = dS[k]; rp[k] = dR[k]; sb[k] = rb[k] = n;
   }
   if (!rc) rc = ctx->transport->exchange(ctx, sp, sb, rp, rb);
   if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "GTA incident test exchange failed"; rc = UMT_ERR_CUDA; }
   for (size_t k = 0; k < nS; k++) {
-    if (!rc) { theirs[k].resize(mine[k].size()); cudaMemcpy(theirs[k].data(), dR[k], theirs[k].size(), cudaMemcpyDeviceToHost); }
+    if (!rc) { theirs[k].resize(mine[k].size()); umt_memcpy(ctx, theirs[k].data(), dR[k], theirs[k].size(), cudaMemcpyDeviceToHost); }
     if (dS[k]) cudaFree(dS[k]);
     if (dR[k]) cudaFree(dR[k]);
   }

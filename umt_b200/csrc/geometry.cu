@@ -176,7 +176,7 @@ __global__ void geometry_rz_kernel(GeomParams P) {
 template <class T>
 int up(umt_ctx *ctx, T **d, const std::vector<T> &h) {
   UMT_CUDA(ctx, cudaMalloc((void **)d, sizeof(T) * std::max<size_t>(h.size(), 1)));
-  UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, *d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 }  // namespace
@@ -222,14 +222,14 @@ extern "C" int umt_compute_geometry(umt_ctx *ctx, const double *px) {
   }
   if (!rc) {   // host mirrors for the schedule builder
     ctx->h_Volume.resize(nc); ctx->h_Afp.resize((size_t)nd * mcf * nc); ctx->h_Aez.resize((size_t)nd * mcf * nc);
-    cudaMemcpy(ctx->h_Volume.data(), ctx->d_Volume, sizeof(double) * nc, cudaMemcpyDeviceToHost);
-    cudaMemcpy(ctx->h_Afp.data(), ctx->d_Afp, sizeof(double) * ctx->h_Afp.size(), cudaMemcpyDeviceToHost);
-    cudaMemcpy(ctx->h_Aez.data(), ctx->d_Aez, sizeof(double) * ctx->h_Aez.size(), cudaMemcpyDeviceToHost);
+    umt_memcpy(ctx, ctx->h_Volume.data(), ctx->d_Volume, sizeof(double) * nc, cudaMemcpyDeviceToHost);
+    umt_memcpy(ctx, ctx->h_Afp.data(), ctx->d_Afp, sizeof(double) * ctx->h_Afp.size(), cudaMemcpyDeviceToHost);
+    umt_memcpy(ctx, ctx->h_Aez.data(), ctx->d_Aez, sizeof(double) * ctx->h_Aez.size(), cudaMemcpyDeviceToHost);
     if (nd == 2) {
       ctx->h_Area.resize(nc); ctx->h_RadiusFP.resize(2 * (size_t)nc); ctx->h_RadiusEZ.resize(2 * (size_t)nc);
-      cudaMemcpy(ctx->h_Area.data(), ctx->d_Area, sizeof(double) * nc, cudaMemcpyDeviceToHost);
-      cudaMemcpy(ctx->h_RadiusFP.data(), ctx->d_RadiusFP, sizeof(double) * 2 * nc, cudaMemcpyDeviceToHost);
-      cudaMemcpy(ctx->h_RadiusEZ.data(), ctx->d_RadiusEZ, sizeof(double) * 2 * nc, cudaMemcpyDeviceToHost);
+      umt_memcpy(ctx, ctx->h_Area.data(), ctx->d_Area, sizeof(double) * nc, cudaMemcpyDeviceToHost);
+      umt_memcpy(ctx, ctx->h_RadiusFP.data(), ctx->d_RadiusFP, sizeof(double) * 2 * nc, cudaMemcpyDeviceToHost);
+      umt_memcpy(ctx, ctx->h_RadiusEZ.data(), ctx->d_RadiusEZ, sizeof(double) * 2 * nc, cudaMemcpyDeviceToHost);
     }
     ctx->have_geom = true; ctx->have_abdy = false; ctx->sched_dirty = true;
   }

@@ -792,17 +792,17 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
       g.reflOpBegin[sR + 1] = (int)ops.size();
     }
     TRY(dalloc(ctx, &g.d_reflOps, ops.size()));
-    if (!ops.empty()) UMT_CUDA(ctx, cudaMemcpy(g.d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
+    if (!ops.empty()) UMT_CUDA(ctx, umt_memcpy(ctx, g.d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
   }
   g.nItems = (int)items.size(); g.nCounters = g.nAng * g.maxHyp;
   TRY(dalloc(ctx, &g.d_omega, (size_t)nd * g.nAng)); TRY(dalloc(ctx, &g.d_weight, g.nAng));
   TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));
   TRY(dalloc(ctx, &g.d_items, items.size())); TRY(dalloc(ctx, &g.d_counters, 1 + (size_t)g.nCounters));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_omega, g.omega.data(), sizeof(double) * nd * g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_weight, g.weight.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_nextZ, h_nextZ.data(), sizeof(int) * h_nextZ.size(), cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_nextC, h_nextC.data(), h_nextC.size(), cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_omega, g.omega.data(), sizeof(double) * nd * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_weight, g.weight.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_nextZ, h_nextZ.data(), sizeof(int) * h_nextZ.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_nextC, h_nextC.data(), h_nextC.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice));
   double **percorner[] = {&g.d_sigTotal, &g.d_sigtInv, &g.d_sigScat, &g.d_sigScatVol, &g.d_greySource, &g.d_tsaSource, &g.d_phiInc, &g.d_correction,
                           &g.d_vec[0], &g.d_vec[1], &g.d_vec[2], &g.d_vec[3], &g.d_P};
   for (double **p : percorner) TRY(dalloc(ctx, p, nc));
@@ -835,10 +835,10 @@ extern "C" int umt_gta_set_opacity(umt_ctx *ctx, const double *GreySigTotal, con
   const int nc = ctx->nc;
   std::vector<double> inv(nc);
   for (int c = 0; c < nc; c++) inv[c] = 1.0 / GreySigTotal[c];
-  UMT_CUDA(ctx, cudaMemcpy(g.d_sigTotal, GreySigTotal, sizeof(double) * nc, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_sigScat, GreySigScat, sizeof(double) * nc, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_sigScatVol, GreySigScatVol, sizeof(double) * nc, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_sigtInv, inv.data(), sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_sigTotal, GreySigTotal, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_sigScat, GreySigScat, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_sigScatVol, GreySigScatVol, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_sigtInv, inv.data(), sizeof(double) * nc, cudaMemcpyHostToDevice));
   g.have_opacity = true;
   return UMT_OK;
 }
@@ -848,7 +848,7 @@ static int upload_c2z(umt_ctx *ctx, int **d_c2z) {
   for (int z = 0; z < ctx->nz; z++)
     for (int c = 0; c < ctx->h_numCorner[z]; c++) c2z[ctx->h_cOffSet[z] + c] = z;
   UMT_CUDA(ctx, cudaMalloc((void **)d_c2z, sizeof(int) * ctx->nc));
-  UMT_CUDA(ctx, cudaMemcpy(*d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, *d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 
@@ -866,14 +866,14 @@ extern "C" int umt_gta_compute_opacity(umt_ctx *ctx, const double *Siga, const d
   if (!rc) rc = dalloc(ctx, &d_s, (size_t)nz * G, false);
   if (!rc) rc = dalloc(ctx, &d_e, nc, false);
   if (!rc) {
-    cudaMemcpy(d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
-    cudaMemcpy(g.d_chi, Chi, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, g.d_chi, Chi, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
     gta_opacity_kernel<<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, G, ctx->tau, d_c2z, d_a, d_s, d_e, ctx->d_Volume, g.d_chi, g.d_sigTotal,
                                                              g.d_sigScat, g.d_sigScatVol, g.d_sigtInv);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(Chi, g.d_chi, sizeof(double) * (size_t)nc * G, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = umt_memcpy(ctx, Chi, g.d_chi, sizeof(double) * (size_t)nc * G, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { ctx->err = std::string("umt_gta_compute_opacity: ") + cudaGetErrorString(e); rc = UMT_ERR_CUDA; }
   }
   cudaFree(d_a); cudaFree(d_s); cudaFree(d_e); cudaFree(d_c2z);
@@ -887,10 +887,10 @@ extern "C" int umt_gta_get_opacity(umt_ctx *ctx, double *GreySigTotal, double *G
   GtaState &g = ctx->gta;
   const size_t n = sizeof(double) * ctx->nc;
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (GreySigTotal) UMT_CUDA(ctx, cudaMemcpy(GreySigTotal, g.d_sigTotal, n, cudaMemcpyDeviceToHost));
-  if (GreySigScat) UMT_CUDA(ctx, cudaMemcpy(GreySigScat, g.d_sigScat, n, cudaMemcpyDeviceToHost));
-  if (GreySigScatVol) UMT_CUDA(ctx, cudaMemcpy(GreySigScatVol, g.d_sigScatVol, n, cudaMemcpyDeviceToHost));
-  if (GreySigtInv) UMT_CUDA(ctx, cudaMemcpy(GreySigtInv, g.d_sigtInv, n, cudaMemcpyDeviceToHost));
+  if (GreySigTotal) UMT_CUDA(ctx, umt_memcpy(ctx, GreySigTotal, g.d_sigTotal, n, cudaMemcpyDeviceToHost));
+  if (GreySigScat) UMT_CUDA(ctx, umt_memcpy(ctx, GreySigScat, g.d_sigScat, n, cudaMemcpyDeviceToHost));
+  if (GreySigScatVol) UMT_CUDA(ctx, umt_memcpy(ctx, GreySigScatVol, g.d_sigScatVol, n, cudaMemcpyDeviceToHost));
+  if (GreySigtInv) UMT_CUDA(ctx, umt_memcpy(ctx, GreySigtInv, g.d_sigtInv, n, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 
@@ -909,12 +909,12 @@ extern "C" int umt_collision_rate(umt_ctx *ctx, const double *Eta, const double 
   if (!rc) rc = dalloc(ctx, &d_s, (size_t)nz * G, false);
   if (!rc) rc = dalloc(ctx, &d_e, nc, false);
   if (!rc) {
-    cudaMemcpy(d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_a, Siga, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_s, Sigs, sizeof(double) * nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
     collision_rate_kernel<<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, G, d_c2z, d_e, d_a, d_s, ctx->d_phi, g.d_greySource, residualFlag);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess && GreySource) e = cudaMemcpy(GreySource, g.d_greySource, sizeof(double) * nc, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && GreySource) e = umt_memcpy(ctx, GreySource, g.d_greySource, sizeof(double) * nc, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { ctx->err = std::string("umt_collision_rate: ") + cudaGetErrorString(e); rc = UMT_ERR_CUDA; }
   }
   cudaFree(d_a); cudaFree(d_s); cudaFree(d_e); cudaFree(d_c2z);
@@ -925,7 +925,7 @@ extern "C" int umt_gta_set_source(umt_ctx *ctx, const double *GreySource) {
   if (!ctx || !GreySource) return UMT_ERR_ARG;
   if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  UMT_CUDA(ctx, cudaMemcpy(ctx->gta.d_greySource, GreySource, sizeof(double) * ctx->nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, ctx->gta.d_greySource, GreySource, sizeof(double) * ctx->nc, cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 
@@ -943,7 +943,7 @@ extern "C" int umt_gta_init_tt(umt_ctx *ctx, double *TT /* (maxCorner, nc) or NU
   }
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->gta.tt_decomposed = false;
-  if (TT) UMT_CUDA(ctx, cudaMemcpy(TT, ctx->gta.d_TT, sizeof(double) * (size_t)ctx->nc * ctx->maxCorner, cudaMemcpyDeviceToHost));
+  if (TT) UMT_CUDA(ctx, umt_memcpy(ctx, TT, ctx->gta.d_TT, sizeof(double) * (size_t)ctx->nc * ctx->maxCorner, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 
@@ -955,17 +955,18 @@ extern "C" int umt_gta_sweep(umt_ctx *ctx, const double *P, const double *GreySo
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nb = ctx->nb;
-  if (GreySource) UMT_CUDA(ctx, cudaMemcpy(g.d_greySource, GreySource, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  if (GreySource) UMT_CUDA(ctx, umt_memcpy(ctx, g.d_greySource, GreySource, sizeof(double) * nc, cudaMemcpyHostToDevice));
   if (!withSource) UMT_CUDA(ctx, cudaMemsetAsync(g.d_greySource, 0, sizeof(double) * nc, ctx->stream));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
   if (nb > 0) {
-    if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
+    if (PsiB_gta) UMT_CUDA(ctx, umt_memcpy(ctx, g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
     else UMT_CUDA(ctx, cudaMemsetAsync(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng, ctx->stream));
   }
   TRY(gta_device_sweep(ctx, g.d_P, g.d_PB));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (PhiInc) UMT_CUDA(ctx, cudaMemcpy(PhiInc, g.d_phiInc, sizeof(double) * nc, cudaMemcpyDeviceToHost));
-  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, cudaMemcpy(PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
+  TRY(umt_check_abort(ctx, "umt_gta_sweep"));
+  if (PhiInc) UMT_CUDA(ctx, umt_memcpy(ctx, PhiInc, g.d_phiInc, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, umt_memcpy(ctx, PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 
@@ -976,15 +977,16 @@ extern "C" int umt_gta_grey_sweep(umt_ctx *ctx, double *P, double *PsiB_gta, int
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
   GtaState &g = ctx->gta;
   const int nc = ctx->nc, nb = ctx->nb;
-  UMT_CUDA(ctx, cudaMemcpy(g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_P, P, sizeof(double) * nc, cudaMemcpyHostToDevice));
   if (nb > 0) {
-    if (PsiB_gta) UMT_CUDA(ctx, cudaMemcpy(g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
+    if (PsiB_gta) UMT_CUDA(ctx, umt_memcpy(ctx, g.d_PB, PsiB_gta, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyHostToDevice));
     else UMT_CUDA(ctx, cudaMemsetAsync(g.d_PB, 0, sizeof(double) * (size_t)nb * g.nAng, ctx->stream));
   }
   TRY(gta_grey_sweep(ctx, g.d_P, g.d_PB, withSource));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  UMT_CUDA(ctx, cudaMemcpy(P, g.d_P, sizeof(double) * nc, cudaMemcpyDeviceToHost));
-  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, cudaMemcpy(PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
+  TRY(umt_check_abort(ctx, "umt_gta_grey_sweep"));
+  UMT_CUDA(ctx, umt_memcpy(ctx, P, g.d_P, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+  if (PsiB_gta && nb > 0) UMT_CUDA(ctx, umt_memcpy(ctx, PsiB_gta, g.d_PB, sizeof(double) * (size_t)nb * g.nAng, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 
@@ -1060,6 +1062,7 @@ extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double
     double e3[3];
     UMT_CUDA(ctx, cudaMemcpyAsync(e3, g.d_red + 3 * RED_BLOCKS, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
     UMT_CUDA(ctx, cudaStreamSynchronize(st));
+    TRY(umt_check_abort(ctx, "umt_gta_solve"));
     if (std::isinf(e3[2])) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_gta_solve: grey solver encountered a NaN (iteration %d)", nGreyIter);
     const double relErrL2 = e3[1] != 0.0 ? std::sqrt(std::fabs(e3[0] / e3[1])) : 0.0;
     maxRelErrGrey = std::max(e3[2], relErrL2);
@@ -1075,6 +1078,7 @@ extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double
     rrOld = rr;
   }
   UMT_CUDA(ctx, cudaStreamSynchronize(st));
+  TRY(umt_check_abort(ctx, "umt_gta_solve"));
   if (nGreyIterOut) *nGreyIterOut = nGreyIter;
   if (maxRelErrOut) *maxRelErrOut = maxRelErrGrey;
   return UMT_OK;
@@ -1084,7 +1088,7 @@ extern "C" int umt_gta_get_correction(umt_ctx *ctx, double *GreyCorrection) {
   if (!ctx || !GreyCorrection) return UMT_ERR_ARG;
   if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  UMT_CUDA(ctx, cudaMemcpy(GreyCorrection, ctx->gta.d_correction, sizeof(double) * ctx->nc, cudaMemcpyDeviceToHost));
+  UMT_CUDA(ctx, umt_memcpy(ctx, GreyCorrection, ctx->gta.d_correction, sizeof(double) * ctx->nc, cudaMemcpyDeviceToHost));
   return UMT_OK;
 }
 

@@ -46,6 +46,8 @@ struct GtaRZParams {
   int *counters;
   const double *sigTotal, *sigtInv, *tsa;
   double *tpsi, *pinc, *psim, *tinc;
+  int *abortFlag;      // watchdog of the dataflow polling loop (device_util.h)
+  unsigned spinLimit;
   // dataflow kernel
   double *psimA, *tincA;    // (nAng, nc) tPsiM / tInc as written by angle a
   const int *prevAngle;     // (nAng) previous swept angle of the level, -1: none
@@ -178,6 +180,7 @@ __device__ __forceinline__ void gta_solve_rz(const GtaRZParams &P, int a, const 
     const int pa = P.prevAngle[a];
     const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc, *tincP = P.tincA + (size_t)(pa < 0 ? 0 : pa) * nc;
     bool ok;
+    unsigned polls = 0;
     do {
       ok = true;
 #pragma unroll
@@ -198,7 +201,7 @@ __device__ __forceinline__ void gta_solve_rz(const GtaRZParams &P, int a, const 
             }
         }
       }
-      if (!ok) __nanosleep(40);
+      if (!ok) { __nanosleep(40); if (umt_spin_expired(polls, P.abortFlag, P.spinLimit)) break; }
     } while (!ok);
   } else {
 #pragma unroll
@@ -462,12 +465,12 @@ int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items) {
   TRY(dalloc2(ctx, &g.d_start, g.nAng)); TRY(dalloc2(ctx, &g.d_finish, g.nAng)); TRY(dalloc2(ctx, &g.d_level, g.nAng));
   TRY(dalloc2(ctx, &g.d_fac, g.nAng)); TRY(dalloc2(ctx, &g.d_w1, g.nAng)); TRY(dalloc2(ctx, &g.d_w2, g.nAng));
   TRY(dalloc2(ctx, &g.d_psim, (size_t)g.nLevels * ctx->nc)); TRY(dalloc2(ctx, &g.d_tinc, (size_t)g.nLevels * ctx->nc));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_start, g.start.data(), g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_finish, g.finish.data(), g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_level, g.level.data(), sizeof(int) * g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_fac, g.angDerivFac.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_w1, g.tauW1.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_w2, g.tauW2.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_start, g.start.data(), g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_finish, g.finish.data(), g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_level, g.level.data(), sizeof(int) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_fac, g.angDerivFac.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_w1, g.tauW1.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_w2, g.tauW2.data(), sizeof(double) * g.nAng, cudaMemcpyHostToDevice));
   // tables of the chain kernel
   int maxAng = 1, maxPlane = 1;
   std::vector<int> cnt(g.nLevels, 0);
@@ -497,13 +500,13 @@ int umt_gta_finish_setup_rz(umt_ctx *ctx, std::vector<WorkItem> &items) {
     g.rz_flow = plain;   // measured at 38 k zones: 4.48 ms per grey sweep against 6.00 ms with the item kernel (UMT_GTA_RZ_KERNEL=item)
     if (const char *e = getenv("UMT_GTA_RZ_KERNEL")) g.rz_flow = plain && std::string(e) == "flow";
     TRY(dalloc2(ctx, &g.d_prevAngle, prevA.size()));
-    UMT_CUDA(ctx, cudaMemcpy(g.d_prevAngle, prevA.data(), sizeof(int) * prevA.size(), cudaMemcpyHostToDevice));
+    UMT_CUDA(ctx, umt_memcpy(ctx, g.d_prevAngle, prevA.data(), sizeof(int) * prevA.size(), cudaMemcpyHostToDevice));
     TRY(dalloc2(ctx, &g.d_psimA, (size_t)g.nAng * ctx->nc)); TRY(dalloc2(ctx, &g.d_tincA, (size_t)g.nAng * ctx->nc));
   }
   TRY(dalloc2(ctx, &g.d_levelAngles, la.size())); TRY(dalloc2(ctx, &g.d_planeOff, po.size())); TRY(dalloc2(ctx, &g.d_nHyp, nh.size()));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_levelAngles, la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_planeOff, po.data(), sizeof(int) * po.size(), cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(g.d_nHyp, nh.data(), sizeof(int) * nh.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_levelAngles, la.data(), sizeof(int) * la.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_planeOff, po.data(), sizeof(int) * po.size(), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, g.d_nHyp, nh.data(), sizeof(int) * nh.size(), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 
@@ -528,6 +531,7 @@ int umt_gta_launch_sweep_rz(umt_ctx *ctx) {
     return UMT_OK;
   }
   if (g.rz_flow && g.nStagesR <= 1) {
+    P.abortFlag = ctx->d_abort; P.spinLimit = ctx->spinLimit;
     P.psimA = g.d_psimA; P.tincA = g.d_tincA; P.prevAngle = g.d_prevAngle; P.nHyp = g.d_nHyp;
     gta_rz_mark_kernel<<<dim3(std::max(1, std::min(ctx->sm_count, (nc + 255) / 256)), g.nAng), 256, 0, ctx->stream>>>(g.d_tpsi, g.d_psimA, g.d_tincA, g.d_nHyp, nc, nc + ctx->nb);
     UMT_CUDA(ctx, cudaGetLastError());
@@ -539,6 +543,7 @@ int umt_gta_launch_sweep_rz(umt_ctx *ctx) {
     const int grid = std::max(1, std::min(ctx->sm_count * std::max(occF, 1), (g.nItems * wpi + wpi - 1) / wpi));
     fk<<<grid, GRZ_BLOCK, 0, ctx->stream>>>(P, wpi);
     UMT_CUDA(ctx, cudaGetLastError());
+    UMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));   // checked after the next sync
     return UMT_OK;
   }
   void (*kern)(GtaRZParams) = ctx->maxCorner <= 4 ? gta_sweep_rz_kernel<4> : gta_sweep_rz_kernel<MAXC2>;

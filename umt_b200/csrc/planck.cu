@@ -72,9 +72,9 @@ extern "C" int umt_init_teton(umt_ctx *ctx, const double *Trz, const double *gro
   UMT_CUDA(ctx, cudaMalloc((void **)&d_c2z, sizeof(int) * ctx->nc));
   UMT_CUDA(ctx, cudaMalloc((void **)&d_tr, sizeof(double) * ctx->nz));
   UMT_CUDA(ctx, cudaMalloc((void **)&d_b, sizeof(double) * (ctx->G + 1)));
-  UMT_CUDA(ctx, cudaMemcpy(d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(d_tr, Trz, sizeof(double) * ctx->nz, cudaMemcpyHostToDevice));
-  UMT_CUDA(ctx, cudaMemcpy(d_b, groupBounds, sizeof(double) * (ctx->G + 1), cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, d_c2z, c2z.data(), sizeof(int) * ctx->nc, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, d_tr, Trz, sizeof(double) * ctx->nz, cudaMemcpyHostToDevice));
+  UMT_CUDA(ctx, umt_memcpy(ctx, d_b, groupBounds, sizeof(double) * (ctx->G + 1), cudaMemcpyHostToDevice));
   init_psi_kernel<<<ctx->nc, 128, sizeof(double) * ctx->G, ctx->stream>>>(ctx->d_psi, d_tr, d_c2z, d_b, ctx->G, ctx->rows, ctx->NA, 1.0,
                                                                            speedLight * radConstant, wtiso, efloor);
   cudaError_t e = cudaGetLastError();

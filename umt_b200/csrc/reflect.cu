@@ -263,7 +263,7 @@ int umt_reflect_stages(umt_ctx *ctx) {
   }
   if (ctx->d_reflOps) { cudaFree(ctx->d_reflOps); ctx->d_reflOps = nullptr; }
   UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_reflOps, sizeof(int4) * std::max<size_t>(ops.size(), 1)));
-  if (!ops.empty()) UMT_CUDA(ctx, cudaMemcpy(ctx->d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
+  if (!ops.empty()) UMT_CUDA(ctx, umt_memcpy(ctx, ctx->d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 

@@ -54,18 +54,18 @@ extern "C" int umt_build_source(umt_ctx *ctx, const double *Siga, const double *
   if (e == cudaSuccess) e = cudaMalloc((void **)&d_chi, sizeof(double) * (size_t)nc * G);
   if (e == cudaSuccess && EmissionRate) e = cudaMalloc((void **)&d_em, sizeof(double) * (size_t)nc * G);
   if (e == cudaSuccess) {
-    cudaMemcpy(d_c2z, c2z.data(), sizeof(int) * nc, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_a, Siga, sizeof(double) * (size_t)nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_s, Sigs, sizeof(double) * (size_t)nz * G, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_chi, Chi, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
-    if (EmissionRate) cudaMemcpy(d_em, EmissionRate, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_c2z, c2z.data(), sizeof(int) * nc, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_a, Siga, sizeof(double) * (size_t)nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_s, Sigs, sizeof(double) * (size_t)nz * G, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_e, Eta, sizeof(double) * nc, cudaMemcpyHostToDevice);
+    umt_memcpy(ctx, d_chi, Chi, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
+    if (EmissionRate) umt_memcpy(ctx, d_em, EmissionRate, sizeof(double) * (size_t)nc * G, cudaMemcpyHostToDevice);
     const double wtiso = ctx->ndim == 3 ? 1.0 / (4.0 * 3.14159265358979323846) : 1.0 / (2.0 * 3.14159265358979323846);
     const unsigned blocks = (unsigned)(((size_t)nc * 32 + 255) / 256);
     source_build_kernel<<<blocks, 256, 0, ctx->stream>>>(nc, G, d_c2z, d_a, d_s, d_e, d_chi, d_em, ctx->d_phi, wtiso, ctx->d_stotal);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess && STotalOut) e = cudaMemcpy(STotalOut, ctx->d_stotal, sizeof(double) * (size_t)nc * G, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && STotalOut) e = umt_memcpy(ctx, STotalOut, ctx->d_stotal, sizeof(double) * (size_t)nc * G, cudaMemcpyDeviceToHost);
   }
   cudaFree(d_c2z); cudaFree(d_a); cudaFree(d_s); cudaFree(d_e); cudaFree(d_chi); cudaFree(d_em);
   if (e != cudaSuccess) UMT_FAIL(ctx, UMT_ERR_CUDA, "umt_build_source: %s", cudaGetErrorString(e));

@@ -55,6 +55,8 @@ struct SweepRZParams {
   // dataflow kernel
   double *psimA;            // (NA, nc, G) PsiM as written by angle a
   const int *prevAngle;     // (NA) previous swept angle of the level, -1: none (starting direction)
+  int *abortFlag;           // watchdog of the polling loops (device_util.h)
+  unsigned spinLimit;
 };
 
 // Dataflow variant: a quiet NaN with a payload no arithmetic produces marks "not computed yet".  The corner rows of Psi1 and the
@@ -207,6 +209,7 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
     const int pa = P.prevAngle[a];
     const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc * G;
     bool ok;
+    unsigned polls = 0;
     do {
       ok = true;
 #pragma unroll
@@ -228,7 +231,7 @@ __device__ __forceinline__ void zone_solve_rz(const SweepRZParams &P, int a, int
             }
         }
       }
-      if (!ok) __nanosleep(40);
+      if (!ok) { __nanosleep(40); if (umt_spin_expired(polls, P.abortFlag, P.spinLimit)) break; }
     } while (!ok);
   }
 #pragma unroll
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
         const int pa = P.prevAngle[a];
         const double *psimP = P.psimA + (size_t)(pa < 0 ? 0 : pa) * nc * G;
         bool ok;
+        unsigned polls = 0;
         do {
           ok = true;
 #pragma unroll
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(RZ_BLOCK, RZ_REC_MIN_CTAS) sweeprz_rec_kernel(
                 }
             }
           }
-          if (!ok) __nanosleep(40);
+          if (!ok) { __nanosleep(40); if (umt_spin_expired(polls, P.abortFlag, P.spinLimit)) break; }
         } while (!ok);
       }
 #pragma unroll
@@ -1018,7 +1022,7 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
   auto up = [&](int **d, const std::vector<int> &h) -> int {
     if (*d) { cudaFree(*d); *d = nullptr; }
     UMT_CUDA(ctx, cudaMalloc((void **)d, sizeof(int) * std::max<size_t>(h.size(), 1)));
-    UMT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+    UMT_CUDA(ctx, umt_memcpy(ctx, *d, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
     return UMT_OK;
   };
   // dataflow kernel: previous swept angle of each level; usable without cycle lists, direct-solve zones and reflecting boundaries,
@@ -1129,6 +1133,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   P.start = ctx->d_start; P.finishNext = ctx->d_finishNext; P.level = ctx->d_level;
   P.nextZ = ctx->d_nextZ; P.nextC = ctx->d_nextC; P.items = ctx->d_items; P.counters = ctx->d_counters;
   P.psi = ctx->d_psi; P.stotal = ctx->d_stotal; P.sigt = ctx->d_sigt; P.psi1 = ctx->d_psi1; P.psim = ctx->d_psim;
+  P.abortFlag = ctx->d_abort; P.spinLimit = ctx->spinLimit;
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int) * (1 + ctx->nCounters), ctx->stream));
   // Set%PsiM = 0 at the start of every flux pass (SetSweep.F90:94-96)
   UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_psim, 0, sizeof(double) * (size_t)ctx->nLevels * ctx->nc * ctx->G, ctx->stream));
@@ -1155,6 +1160,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
     const int grid = std::max(1, std::min(ctx->sm_count * occ, (ctx->nItems * wpi + RZ_BLOCK / 32 - 1) / (RZ_BLOCK / 32)));
     fk<<<grid, RZ_BLOCK, 0, ctx->stream>>>(P, wpi);
     UMT_CUDA(ctx, cudaGetLastError());
+    UMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));   // checked after the next sync
     ctx->last_launches += 2;
     return UMT_OK;
   }
@@ -1198,7 +1204,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       }
       if (ctx->d_zinfo) { cudaFree(ctx->d_zinfo); ctx->d_zinfo = nullptr; }
       UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_zinfo, sizeof(int2) * n));
-      UMT_CUDA(ctx, cudaMemcpy(ctx->d_zinfo, zinfo.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
+      UMT_CUDA(ctx, umt_memcpy(ctx, ctx->d_zinfo, zinfo.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
     }
     const bool flow = ctx->rz_flow && ctx->nStages <= 1;
     bool pipe = ctx->rz_canon && !flow && ctx->G % 2 == 0 && ctx->zones_per_item <= RZP_ZMAX && ctx->zones_per_item * ctx->G <= 64;
@@ -1272,6 +1278,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       UMT_CUDA(ctx, cudaGetLastError());
       ctx->last_launches += 1;
     }
+    if (flow) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return UMT_OK;
   }
   void (*kern)(SweepRZParams) = ctx->maxCorner <= 4 ? sweeprz_kernel<4> : sweeprz_kernel<MAXC2>;

@@ -26,7 +26,7 @@ static int dev_alloc_copy(umt_ctx *ctx, T **dptr, const T *h, size_t n) {
   if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
   if (n == 0) n = 1;
   UMT_CUDA(ctx, cudaMalloc((void **)dptr, n * sizeof(T)));
-  if (h) UMT_CUDA(ctx, cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  if (h) UMT_CUDA(ctx, umt_memcpy(ctx, *dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
   return UMT_OK;
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
@@ -69,6 +69,14 @@ extern "C" int umt_ctx_create(int device, int ndim, int nzones, int ncornr, int 
     return UMT_ERR_CUDA;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc((void **)&ctx->d_abort, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_abort, 0, sizeof(int)) != cudaSuccess ||
+      cudaHostAlloc((void **)&ctx->h_abort, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    g_create_error = "umt_ctx_create: watchdog flag allocation failed";
+    delete ctx;
+    return UMT_ERR_CUDA;
+  }
+  *ctx->h_abort = 0;
+  if (const char *ev = getenv("UMT_SPIN_LIMIT")) ctx->spinLimit = (unsigned)std::max(256, atoi(ev));
   // L2 set-aside for evict_last lines: the sweep stores Psi1 rows with an evict_last hint so that the downstream zones find
   // them in L2; without a persisting carve-out the hint has nothing to hold on to.  UMT_L2_PERSIST_MB overrides (0 = off).
   {
@@ -101,6 +109,8 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_start, ctx->d_finishNext, ctx->d_level, ctx->d_reflOps, ctx->d_rzLevelAngles, ctx->d_rzPlaneOff, ctx->d_rzNHyp,
                   ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad, ctx->d_itemsRing, ctx->d_tailSlot, ctx->d_tailW};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (ctx->d_abort) cudaFree(ctx->d_abort);
+  if (ctx->h_abort) cudaFreeHost(ctx->h_abort);
   for (auto &b : ctx->host_blocks) { cudaHostUnregister(b.first); munmap(b.first, b.second); }   // umt_host_alloc blocks never freed
   ctx->host_blocks.clear();
   umt_exchange_release(ctx);
@@ -665,6 +675,15 @@ static int finalize_schedule(umt_ctx *ctx) {
 
 int umt_finalize_schedule(umt_ctx *ctx) { return finalize_schedule(ctx); }
 
+// A dataflow kernel (values as their own completion flags) whose polling budget ran out raised the abort flag; its result is garbage.
+int umt_check_abort(umt_ctx *ctx, const char *what) {
+  if (!ctx->h_abort || *ctx->h_abort == 0) return UMT_OK;
+  *ctx->h_abort = 0;
+  cudaMemsetAsync(ctx->d_abort, 0, sizeof(int), ctx->stream);
+  UMT_FAIL(ctx, UMT_ERR_STATE, "%s: a dataflow sweep gave up waiting for a value that never became real (an input carrying the "
+           "'not computed yet' bit pattern 0xFFFFDEADFFFFDEAD, or a broken schedule); the result of this call is undefined", what);
+}
+
 // ---------------------------------------------------------------------------
 // state
 // ---------------------------------------------------------------------------
@@ -1179,7 +1198,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   }
   ctx->last_ms[0] = ms_sweep; ctx->last_ms[1] = ms_phi; ctx->last_ms[2] = ms_exch; ctx->last_ms[3] = ms_all;
   if (itersDone) *itersDone = iter;
-  return UMT_OK;
+  return umt_check_abort(ctx, "umt_sweep");
 }
 
 extern "C" int umt_last_sweep_times(umt_ctx *ctx, double *ms4) {

@@ -244,6 +244,9 @@ struct umt_ctx {
   int rows_total() const { return nc + nb; }
 
   GtaState gta;
+  // watchdog of the dataflow kernels: device flag, its page-locked host copy (fetched after every dataflow launch), poll budget
+  int *d_abort = nullptr, *h_abort = nullptr;
+  unsigned spinLimit = 1u << 21;       // polls of ~1 us each before a thread gives up (UMT_SPIN_LIMIT)
   std::map<void *, size_t> host_blocks;   // umt_host_alloc: live blocks and their mapped length
 
   // stats
@@ -267,7 +270,17 @@ struct umt_ctx {
                cudaGetErrorString(_e));                                                \
   } while (0)
 
+// Blocking copy ordered with the context's stream.  (cudaMemcpy runs on the legacy default stream, which the context's non-blocking
+// streams do not synchronise with: a pageable host-to-device copy may still be in flight when it returns, and a device-to-host copy
+// does not wait for kernels queued on the context's stream.)
+static inline cudaError_t umt_memcpy(const umt_ctx *ctx, void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(ctx->stream);
+}
+
 // kernels / host pieces implemented in other translation units
+int umt_check_abort(umt_ctx *ctx, const char *what);   // after a sync: UMT_ERR_STATE if a dataflow kernel gave up waiting
 int umt_launch_sweep3d(umt_ctx *ctx, int savePsi);
 int umt_build_plan3d(umt_ctx *ctx);
 int umt_sweep3d_zones_per_item(const umt_ctx *ctx);

@@ -51,3 +51,44 @@ class MiniAppCycle:
         ed["sweeps"], ed["flux_passes"] = sweeps, passes
         self.history.append(ed)
         return ed
+
+
+class FullPhysicsStep:
+    """The linear solve of a temperature iteration with grey acceleration switched on (rt/LinearSolver.F90:55-121, what the mini-app
+    build compiles out), every per-corner field staying on the device:
+
+      getCollisionRate(residualFlag = 0)            GTA%GreySource = sum_g (Eta siga + sigs) PhiTotal
+      ControlSweep(savePsi)                         the multigroup sweep + PhiTotal
+      getCollisionRate(residualFlag = 1)            GreySource = new collision rate - old one (the residual the grey solve corrects)
+      GTASolver + addGreyCorrections                BiCGSTAB on the grey transport operator; PhiTotal += correction * Chi
+
+    followed, between iterations, by the rebuild of the isotropic source GSet%STotal from the corrected PhiTotal (umt_build_source:
+    the mini-app reference never fills STotal, so that formula is this library's documented extension; parity unpinned).  Opacities
+    are the caller's: Mat%Siga, Mat%Sigs (nzones, ngr), Mat%Eta (ncornr), GTA%Chi (ncornr, ngr), emission (ncornr, ngr)."""
+
+    def __init__(self, ctx, mesh, ngr, Siga, Sigs, Eta, Chi, EmissionRate, dt=PR.DT, flux_iters=2, flux_tol=1e-6):
+        self.ctx, self.mesh, self.G = ctx, mesh, ngr
+        self.Siga, self.Sigs, self.Eta, self.Emis = Siga, Sigs, Eta, EmissionRate
+        self.Chi = np.ascontiguousarray(Chi, dtype=np.float64).copy()
+        self.tau = PR.tau(dt)
+        self.flux_iters, self.flux_tol = flux_iters, flux_tol
+        # setTotalOpacity.F90:52: Sigt = siga + sigs + tau; then GTA setup (angle set, sweep order, setGTAOpacityNEW, transfer matrices)
+        ctx.upload_state(None, None, Siga + Sigs + self.tau, None, self.tau)
+        ctx.gta_setup()
+        self.opacity = ctx.gta_compute_opacity(Siga, Sigs, Eta, self.Chi)   # Chi comes back rescaled, as setGTAOpacityNEW leaves it
+        self.history = []
+
+    def rebuild_source(self):
+        """GSet%STotal from the PhiTotal on the device (stays there; returned for inspection)"""
+        return self.ctx.build_source(self.Siga, self.Sigs, self.Eta, self.Chi, self.Emis)
+
+    def linear_solver(self, savePsi=False):
+        ctx = self.ctx
+        ctx.collision_rate(self.Eta, self.Siga, self.Sigs, 0)
+        passes = ctx.sweep(savePsi, self.flux_iters, self.flux_tol)
+        ctx.collision_rate(self.Eta, self.Siga, self.Sigs, 1)
+        corr, n, err = ctx.gta_solve()
+        ctx.add_grey_corrections()
+        rec = dict(flux_passes=passes, grey_sweeps=n, grey_error=err, correction_max=float(np.abs(corr).max()))
+        self.history.append(rec)
+        return rec
