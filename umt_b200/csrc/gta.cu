@@ -22,7 +22,10 @@
 #include <cmath>
 #include <cstring>
 
+#include <string>
+
 #include "umt_internal.h"
+#include "device_util.h"
 
 namespace {
 
@@ -51,6 +54,8 @@ struct GtaSweepParams {
   int *counters;
   const double *sigTotal, *sigtInv, *tsa;
   double *tpsi, *pinc;
+  int *abortFlag;         // dataflow kernel: watchdog of the polling loop (device_util.h)
+  unsigned spinLimit;
 };
 
 // SweepGreyUCBxyzKernelNew for one (zone, angle)
@@ -183,6 +188,10 @@ __device__ __forceinline__ void gta_zone_static(const GtaSweepParams &P, int a, 
   }
 }
 
+// FLOW (dataflow kernel): the corner rows of tPsi were marked "not computed yet" before the launch; every face lane polls the value
+// behind its incident face until it is real (the data are their own completion flags), and the corner fluxes are stored with
+// relaxed device-scope stores -- no counters, no fences, no barriers, and a zone starts as soon as ITS upstream zones are done.
+template <bool FLOW>
 __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int a, int lane, const GtaZoneStatic &Z) {
   const unsigned FULL = 0xffffffffu;
   const int nc = P.nc;
@@ -193,7 +202,23 @@ __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int
   const bool valid = c < nCorner && f < 3;
   const double afp = Z.afp, aez = Z.aez, sigv = Z.sigv, q = Z.q;
   const int cez = Z.cez;
-  const double psifp = (valid && afp < 0.0) ? __ldcg(&tpsi[Z.row]) : 0.0;
+  double psifp = 0.0;
+  if (FLOW) {
+    const bool need = valid && afp < 0.0 && Z.row < nc;      // boundary elements (rows >= nc) are inputs, never marked
+    if (valid && afp < 0.0 && Z.row >= nc) psifp = __ldcg(&tpsi[Z.row]);
+    unsigned polls = 0;
+    for (;;) {
+      unsigned long long v = 0ull;
+      if (need) v = umt_ld_relaxed_u64(&tpsi[Z.row]);
+      const bool ok = !need || v != UMT_SENTINEL;
+      if (need) psifp = __longlong_as_double((long long)v);
+      if (__all_sync(FULL, ok)) break;
+      __nanosleep(40);
+      if (__any_sync(FULL, umt_spin_expired(polls, P.abortFlag, P.spinLimit))) break;
+    }
+  } else {
+    psifp = (valid && afp < 0.0) ? __ldcg(&tpsi[Z.row]) : 0.0;
+  }
   const int myNext = Z.myNext;
   // the FP face "opposite" EZ face f is face (f+1) mod 3 of the same corner (SweepGreyUCBxyz.F90:263-270)
   const int lop = (lane & ~3) | (f == 2 ? 0 : f + 1);
@@ -250,7 +275,10 @@ __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int
       if (ak > 0.0 && c == tk && c != cs) { src += ak * psi; pinc += ak * pin; }
     }
   }
-  if (c < nCorner && f == 0) { tpsi[c0 + c] = src; pincA[c0 + c] = pinc; }
+  if (c < nCorner && f == 0) {
+    pincA[c0 + c] = pinc;
+    if (FLOW) umt_st_relaxed_f64(&tpsi[c0 + c], src); else tpsi[c0 + c] = src;
+  }
   if (valid && Z.row >= nc && afp > 0.0) tpsi[Z.row] = src;   // PsiB(b, Angle) <- tPsi
 }
 
@@ -276,7 +304,7 @@ __global__ void __launch_bounds__(GTA_WARPS * 32, GTA_MINB) gta_sweep_kernel(Gta
       while (ld_acquire(&P.counters[1 + w.wait_idx]) < w.wait_count) __nanosleep(20);
     __syncthreads();
     if (active) {
-      if (Z.fast) gta_zone_solve_warp(P, w.angle, lane, Z);
+      if (Z.fast) gta_zone_solve_warp<false>(P, w.angle, lane, Z);
       else if (lane == 0) gta_solve_zone(P, w.angle, Z.zone0);
     }
     __syncthreads();
@@ -285,6 +313,37 @@ __global__ void __launch_bounds__(GTA_WARPS * 32, GTA_MINB) gta_sweep_kernel(Gta
       asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(&P.counters[1 + w.signal_idx]) : "memory");
     }
   }
+}
+
+// Dataflow variant (meshes whose zones all take the warp solve, no reflecting boundaries, no direct-solve zones): every warp takes
+// ONE zone of the item list through its own ticket, in the list's topological order, so the zones a warp polls for are held by
+// warps with earlier tickets: no deadlock.  A plane-to-plane hop is one L2 store -> load round trip instead of
+// store -> fence -> counter -> poll -> barrier -> load.
+__global__ void __launch_bounds__(GTA_WARPS * 32, GTA_MINB) gta_sweep_flow_kernel(GtaSweepParams P) {
+  const int lane = threadIdx.x & 31;
+  const int nUnits = P.nItems * GTA_WARPS;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&P.counters[0], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nUnits) break;
+    const int it = t / GTA_WARPS, sub = t - it * GTA_WARPS;
+    const WorkItem w = P.items[it];
+    const int zi = w.zbeg + sub;
+    if (zi < w.zend) {
+      GtaZoneStatic Z;
+      gta_zone_static(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + zi], lane, Z);
+      gta_zone_solve_warp<true>(P, w.angle, lane, Z);   // the host only launches this kernel when every zone is "fast"
+    }
+    __syncwarp();
+  }
+}
+
+// marks the corner rows of tPsi of every angle as "not computed yet"
+__global__ void gta_mark_kernel(double *tpsi, int nc, int rows) {
+  const double mark = __longlong_as_double((long long)UMT_SENTINEL);
+  double *t = tpsi + (size_t)blockIdx.y * rows;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) t[i] = mark;
 }
 
 // snreflect for the grey sweeps: tPsi tail rows are PsiB(:, angle)
@@ -630,6 +689,21 @@ int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = g.d_omega;
   P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
   P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc;
+  if (g.flow3d && g.nStagesR <= 1) {
+    P.abortFlag = ctx->d_abort; P.spinLimit = ctx->spinLimit;
+    gta_mark_kernel<<<dim3(std::max(1, std::min(2 * ctx->sm_count, (nc + 255) / 256)), g.nAng), 256, 0, ctx->stream>>>(g.d_tpsi, nc, rows);
+    int occF = 0;
+    UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, gta_sweep_flow_kernel, GTA_WARPS * 32, 0));
+    const int gridF = std::max(1, std::min(ctx->sm_count * std::max(occF, 1), g.nItems));
+    gta_sweep_flow_kernel<<<gridF, GTA_WARPS * 32, 0, ctx->stream>>>(P);
+    UMT_CUDA(ctx, cudaGetLastError());
+    UMT_CUDA(ctx, cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));   // checked after the next sync
+    gta_phiinc_kernel<<<nblk(nc), 256, 0, ctx->stream>>>(g.d_pinc, g.d_weight, g.nAng, nc, g.d_phiInc);
+    if (nb > 0)
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(d_PsiB, sizeof(double) * nb, g.d_tpsi + nc, sizeof(double) * rows, sizeof(double) * nb, g.nAng,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    return UMT_OK;
+  }
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gta_sweep_kernel, GTA_WARPS * 32, 0));
   for (int sR = 0; sR < g.nStagesR; sR++) {
@@ -795,6 +869,13 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
     if (!ops.empty()) UMT_CUDA(ctx, umt_memcpy(ctx, g.d_reflOps, ops.data(), sizeof(int4) * ops.size(), cudaMemcpyHostToDevice));
   }
   g.nItems = (int)items.size(); g.nCounters = g.nAng * g.maxHyp;
+  // 3-D dataflow kernel (gta_sweep_flow_kernel): every zone must take the warp solve (<= 8 corners of three faces each, no
+  // intra-zone cycle) and the angles must go in one launch (no reflecting boundaries).  UMT_GTA_KERNEL=item keeps the counters.
+  g.flow3d = nd == 3 && g.nStagesR <= 1 && ctx->maxCorner <= MAXC;
+  for (int c = 0; c < nc && g.flow3d; c++) g.flow3d = ctx->h_nCFaces[c] == 3;
+  for (int a = 0; a < g.nAng && g.flow3d; a++)
+    for (int z : g.nextZ[a]) if (z < 0) { g.flow3d = false; break; }
+  if (const char *e = getenv("UMT_GTA_KERNEL")) if (std::string(e) == "item") g.flow3d = false;
   TRY(dalloc(ctx, &g.d_omega, (size_t)nd * g.nAng)); TRY(dalloc(ctx, &g.d_weight, g.nAng));
   TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));
   TRY(dalloc(ctx, &g.d_items, items.size())); TRY(dalloc(ctx, &g.d_counters, 1 + (size_t)g.nCounters));

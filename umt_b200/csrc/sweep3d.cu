@@ -44,6 +44,8 @@ constexpr double FOURALPHA = 1.82;   // SweepUCBxyz.F90:80
 struct Sweep3DParams {
   int nc, nb, nz, G, NA, nItems;
   int wpe, nEngines, nStages, stageBytes, offSt, offSigt, offRecs, zpi;   // PlanGeom
+  int nStagesWG;           // stages per half of the warp-group build
+  int qbMax;               // tickets a loader takes at a time (at most)
   double tau;
   const int *numCorner, *cOffSet, *nCFaces, *cFP /* 0-based row; >= nc: boundary */, *cEZ /* 0-based */;
   const double *Volume, *Afp, *Aez, *omega;
@@ -912,29 +914,49 @@ __device__ __noinline__ void phi_tally_item(const Sweep3DParams &P, const int a0
 #ifdef PLAN_MAXNREG   // explicit register cap instead of the CTAs-per-SM hint (A/B builds)
 #define PLAN_BOUNDS(NH) __maxnreg__(PLAN_MAXNREG)
 #else
-#define PLAN_BOUNDS(NH) __launch_bounds__(PLAN_LANES + 64, (NH == 1 ? PLAN_MINB : PLAN_MINB2))
+#define PLAN_BOUNDS(NH) __launch_bounds__(WG ? PLAN_WG_THREADS : PLAN_LANES + 64, WG ? 1 : (NH == 1 ? PLAN_MINB : PLAN_MINB2))
 #endif
 // MODE 0: Psi1 rows and boundary-element rows in one buffer, slab = angle (legacy layout; in-place savePsi sweep of the single-psi layout)
 //      1: ring slots for the Psi1 rows, boundary-element rows in the Psi buffer, phi-tally items (single-psi layout, other sweeps)
-template <int NH, int MODE>
+// WG: the warp-group build (one CTA of 16 warps per SM).  Warps 0-11 are consumers (three warp groups), warps 12-15 the loader and
+// signaller warps of two independent halves (half h: consumer warps 6h .. 6h+5, its own control block and stages).  After the role
+// split the consumer warp groups raise their register budget with setmaxnreg and the producer group lowers its own, so the SM runs
+// 12 consumer warps at the register count that the 2 x 6-warp CTAs of the plain build give to 8: half as many again to hide the
+// latency of the upstream rows behind.
+#ifndef PLAN_WG_CONS
+#define PLAN_WG_CONS 152
+#endif
+#ifndef PLAN_WG_PROD
+#define PLAN_WG_PROD 40
+#endif
+constexpr int PLAN_WG_THREADS = 512, PLAN_WG_NCW = 6, PLAN_WG_CONS_REGS = PLAN_WG_CONS, PLAN_WG_PROD_REGS = PLAN_WG_PROD;
+static_assert(12 * 32 * PLAN_WG_CONS + 4 * 32 * PLAN_WG_PROD <= 65536, "register file of one SM");
+template <int NH, int MODE, bool WG>
 __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
   constexpr bool TWO = MODE == 1, RING = MODE == 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw);
-  unsigned char *stages = smem_raw + PLAN_CTL_BYTES;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int rwarp = tid >> 5;                       // warp of the CTA
+  // role index within the (virtual) CTA: 0 .. NCW-1 consumers, NCW loader, NCW+1 signaller
+  const int half = WG ? (rwarp < 2 * PLAN_WG_NCW ? rwarp / PLAN_WG_NCW : (rwarp - 2 * PLAN_WG_NCW) >> 1) : 0;
+  const int warp = WG ? (rwarp < 2 * PLAN_WG_NCW ? rwarp - half * PLAN_WG_NCW : PLAN_WG_NCW + ((rwarp - 2 * PLAN_WG_NCW) & 1)) : rwarp;
+  constexpr int NCW = WG ? PLAN_WG_NCW : PLAN_NCW;
   const int G = P.G, Gv = G >> 1;   // lanes per zone
-  const int NS = P.nStages, NE = P.nEngines, wpe = P.wpe;
+  const int wpe = P.wpe;
+  const int NS = WG ? P.nStagesWG : P.nStages, NE = WG ? PLAN_WG_NCW / wpe : P.nEngines;
+  PlanCtl &S = *reinterpret_cast<PlanCtl *>(smem_raw + (WG ? half * PLAN_CTL_BYTES : 0));
+  unsigned char *stages = smem_raw + (WG ? 2 * PLAN_CTL_BYTES + (size_t)half * NS * P.stageBytes : PLAN_CTL_BYTES);
   const size_t slab = (size_t)(P.nc + P.nb) * G;
-  if (tid == 0) {
+  if (lane == 0 && (WG ? (rwarp == 0 || rwarp == PLAN_WG_NCW) : tid == 0)) {   // one thread per control block
     for (int s = 0; s < NS; s++) { mbar_init(&S.full[s], 2); mbar_init(&S.empty[s], wpe); }
     S.issuedCount = 0; S.doneFlag = 0; S.nSignaled = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-
-  if (warp == PLAN_NCW) {
+  if (warp >= NCW) {   // producer roles (WG: the whole fourth warp group)
+  if (WG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PLAN_WG_PROD_REGS));
+  if (warp == NCW) {
     // ---------------- loader warp ----------------
     // Per CTA-local sequence number k (stage k % NS, engine k % NE):
     //   issue(k):   next queued item -> TMA of its records and Psi^n/STotal/Sigt rows (needs item k-NS finished by its engine);
@@ -951,7 +973,7 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     int sRel = 0;                             // stage of the next release
     int lastOk = -1;                          // wait_idx last seen complete
     const unsigned rowBytes = (unsigned)G * 8u;
-    const int zpi = P.zpi, QB = min(8, 32 / zpi);
+    const int zpi = P.zpi, QB = min(P.qbMax, 32 / zpi);
     const int myItem = lane / zpi, myZone = lane - myItem * zpi;
     WorkItem qW, nW;                          // lane l: descriptor of item l / zpi of the current / next batch
     int2 qZ = make_int2(0, 0), nZ = make_int2(0, 0);   // info of zone l % zpi of that item
@@ -1055,7 +1077,7 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     return;
   }
 
-  if (warp == PLAN_NCW + 1) {
+  {
     // ---------------- signaller warp ----------------
     // signal(k): item k's engine has arrived on empty[k % NS] -> make its Psi1 rows visible device-wide (one fence for
     // every item found complete) and bump the completion counter of each item's plane.
@@ -1090,6 +1112,8 @@ __global__ void PLAN_BOUNDS(NH) sweep3d_plan_kernel(Sweep3DParams P) {
     }
     return;
   }
+  }
+  if (WG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PLAN_WG_CONS_REGS));
 
   // ---------------- consumer warps: engines of wpe warps, each on its own stages ----------------
   const int eng = warp / wpe, elane = (warp - eng * wpe) * 32 + lane;   // my engine, my lane in it
@@ -1136,6 +1160,8 @@ void fill_params(umt_ctx *ctx, Sweep3DParams &P) {
   const PlanGeom pg = plan_geom(ctx->G, ctx->plan_nh);
   P.wpe = pg.wpe; P.nEngines = pg.nEngines; P.nStages = pg.nStages; P.stageBytes = pg.stageBytes;
   P.offSt = pg.offSt; P.offSigt = pg.offSigt; P.offRecs = pg.offRecs; P.zpi = pg.zpi;
+  P.nStagesWG = 0; P.qbMax = 4;   // tickets per batch: 8 held items too far ahead of their turn (40.5 -> 38.6 ms)
+  if (const char *e = getenv("UMT_PLAN_QB")) P.qbMax = std::max(1, std::min(8, atoi(e)));
   P.numCorner = ctx->d_numCorner; P.cOffSet = ctx->d_cOffSet; P.nCFaces = ctx->d_nCFaces;
   P.cFP = ctx->d_cFP; P.cEZ = ctx->d_cEZ;
   P.Volume = ctx->d_Volume; P.Afp = ctx->d_Afp; P.Aez = ctx->d_Aez; P.omega = ctx->d_omega;
@@ -1184,8 +1210,26 @@ static int launch_plan(umt_ctx *ctx, const Sweep3DParams &P, int mode) {
   const int threads = PLAN_LANES + 64;   // consumers + loader warp + signaller warp
   const size_t smem = plan_geom(ctx->G, ctx->plan_nh).smemBytes;
   void (*kern)(Sweep3DParams);
-  if (ctx->plan_nh == 2) kern = mode == 1 ? sweep3d_plan_kernel<2, 1> : sweep3d_plan_kernel<2, 0>;
-  else kern = mode == 1 ? sweep3d_plan_kernel<1, 1> : sweep3d_plan_kernel<1, 0>;
+  if (ctx->plan_nh == 2) kern = mode == 1 ? sweep3d_plan_kernel<2, 1, false> : sweep3d_plan_kernel<2, 0, false>;
+  else kern = mode == 1 ? sweep3d_plan_kernel<1, 1, false> : sweep3d_plan_kernel<1, 0, false>;
+  // warp-group build: two-warp engines only (G = 128 with two groups per lane), UMT_PLAN_WG=0 switches it off
+  // (measured at -d 20 -G 128: 37.4 ms against 38.6 ms for the plain build, both with 4 tickets per batch; 40.5 ms with 8)
+  bool wg = ctx->plan_nh == 1 && P.wpe == 2 && PLAN_NCW == 4;
+  if (const char *e = getenv("UMT_PLAN_WG")) wg = wg && atoi(e) != 0;
+  if (wg) {
+    Sweep3DParams Q = P;
+    const int perHalf = ((227 * 1024 - 2 * PLAN_CTL_BYTES) / 2) / P.stageBytes;
+    // engines + 2 landing stages per half (more hold tickets ahead of their turn: 6 stages 46 ms, 5 stages 37.4, 4 stages 37.8)
+    Q.nStagesWG = std::max(PLAN_WG_NCW / P.wpe + 1, std::min(PLAN_WG_NCW / P.wpe + 2, std::min(PLAN_MAX_STAGES, perHalf)));
+    if (const char *e = getenv("UMT_PLAN_STAGES")) Q.nStagesWG = std::max(PLAN_WG_NCW / P.wpe + 1, std::min(std::min(PLAN_MAX_STAGES, perHalf), atoi(e)));
+    const size_t smemWG = 2 * PLAN_CTL_BYTES + 2 * (size_t)Q.nStagesWG * P.stageBytes;
+    void (*kw)(Sweep3DParams) = mode == 1 ? sweep3d_plan_kernel<1, 1, true> : sweep3d_plan_kernel<1, 0, true>;
+    UMT_CUDA(ctx, cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemWG));
+    const int gridWG = std::max(1, std::min(ctx->sm_count, (P.nItems + 15) / 16));
+    kw<<<gridWG, PLAN_WG_THREADS, smemWG, ctx->stream>>>(Q);
+    UMT_CUDA(ctx, cudaGetLastError());
+    return UMT_OK;
+  }
   UMT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
