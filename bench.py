@@ -87,9 +87,10 @@ class ClockSampler(threading.Thread):
 
 
 def profiled_traffic_per_unknown():
-    """dram__bytes_read.sum + dram__bytes_write.sum of sweep3d_plan_kernel divided by the unknowns of that launch, from the
-    committed ncu capture of this very workload (profiles/r01b_sweep3d_d20_G128_ncu_summary.txt: -d 20,20,20 -G 128, 6.29e9 unknowns per launch)."""
-    p = os.path.join(ROOT, "profiles", "r01b_sweep3d_d20_G128_ncu_summary.txt")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the 3-D sweep kernel divided by the unknowns of that launch, from the committed
+    ncu capture of this very workload and kernel build (profiles/r02_sweep3d_d20_G128_ncu_summary.txt: `ncu --set full` of
+    `python bench.py --steps 1 --warmup 1`, i.e. -d 20,20,20 -G 128 P2 A2, 6.29e9 unknowns per launch; tools/gpu_evidence.sh)."""
+    p = os.path.join(ROOT, "profiles", "r02_sweep3d_d20_G128_ncu_summary.txt")
     try:
         rd = wr = None
         for line in open(p):
@@ -465,7 +466,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tpu * unknowns / 1e9) if tpu else None, "traffic_unit": "GB per launch",
                          "traffic_source": (f"ncu dram read+write {tpu:.1f} B/unknown measured at -d 20,20,20 -G 128 P2 A2 ({tsrc}), scaled by this launch's unknowns" if tpu else None),
-                         "kernel": "sweep3d (persistent, all angles)", "bytes_per_unknown": balg, "kernel_ms": sweep_kernel_ms,
+                         "kernel": "sweep3d_plan_kernel (persistent, all angles; warp-group build: 12 consumer warps per SM)", "bytes_per_unknown": balg, "kernel_ms": sweep_kernel_ms,
                          "peak_source": peak_src,
                          "whole_sweep_41B_model": {"bytes_per_unknown": algorithmic_bytes_per_unknown(G), "achieved": model41, "frac": model41 / peak}},
             "kernel_ms": {"sweep": sweep_ms / args.steps, "phi": phi_ms / args.steps, "exchange": exch_ms / args.steps,
@@ -473,7 +474,7 @@ def main():
             "psi_layout": dict(layout, device_memory_used_GB=(mem_total - mem_free) / 1e9),
             "setup_ms": {"build_schedule_host": sched_ms, "first_use_plan_records_items_workspace": finalize_ms,
                          "note": "once per mesh/quadrature (the reference rebuilds its schedules every cycle, control/initializeSets.F90:95-105); not in the timed region"},
-            "host_buffers": {"numa_node": numa, "kind": "umt_host_alloc (page-locked, bound to the GPU's NUMA node)"},
+            "host_buffers": {"rank_bound_to_numa_node": numa, "pages_bound_to_numa_node": getattr(ctx, "host_numa_node", None), "kind": "umt_host_alloc (page-locked, bound to the GPU's NUMA node)"},
             "device_ms_per_step": device_step_ms,
             "clocks": sampler.summary(),
         }

@@ -56,6 +56,7 @@ struct GtaSweepParams {
   double *tpsi, *pinc;
   int *abortFlag;         // dataflow kernel: watchdog of the polling loop (device_util.h)
   unsigned spinLimit;
+  const unsigned *pollMask;   // dataflow kernel: (nAng, nz in sweep order) bit 3c+f: the zone behind FP face f of corner c sits in an earlier plane
 };
 
 // SweepGreyUCBxyzKernelNew for one (zone, angle)
@@ -192,7 +193,7 @@ __device__ __forceinline__ void gta_zone_static(const GtaSweepParams &P, int a, 
 // behind its incident face until it is real (the data are their own completion flags), and the corner fluxes are stored with
 // relaxed device-scope stores -- no counters, no fences, no barriers, and a zone starts as soon as ITS upstream zones are done.
 template <bool FLOW>
-__device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int a, int lane, const GtaZoneStatic &Z) {
+__device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int a, int lane, const GtaZoneStatic &Z, unsigned pollMask = 0u) {
   const unsigned FULL = 0xffffffffu;
   const int nc = P.nc;
   double *tpsi = P.tpsi + (size_t)a * (nc + P.nb);
@@ -204,8 +205,15 @@ __device__ __forceinline__ void gta_zone_solve_warp(const GtaSweepParams &P, int
   const int cez = Z.cez;
   double psifp = 0.0;
   if (FLOW) {
-    const bool need = valid && afp < 0.0 && Z.row < nc;      // boundary elements (rows >= nc) are inputs, never marked
-    if (valid && afp < 0.0 && Z.row >= nc) psifp = __ldcg(&tpsi[Z.row]);
+    // Only faces whose upstream zone the schedule puts in an earlier plane are waited for.  An incident face the schedule does not
+    // order (omega.A = 0 up to rounding: the sign is noise and so is the weight of its flux) takes what is there, 0 if nothing yet --
+    // what the counter kernel and the reference read from a zeroed tPsi.
+    const bool inc = valid && afp < 0.0;
+    const bool need = inc && Z.row < nc && ((pollMask >> (3 * c + f)) & 1u);
+    if (inc && !need) {
+      const unsigned long long v = umt_ld_relaxed_u64(&tpsi[Z.row]);
+      psifp = v == UMT_SENTINEL ? 0.0 : __longlong_as_double((long long)v);
+    }
     unsigned polls = 0;
     for (;;) {
       unsigned long long v = 0ull;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(GTA_WARPS * 32, GTA_MINB) gta_sweep_flow_kerne
     if (zi < w.zend) {
       GtaZoneStatic Z;
       gta_zone_static(P, w.angle, P.nextZ[(size_t)w.angle * P.nz + zi], lane, Z);
-      gta_zone_solve_warp<true>(P, w.angle, lane, Z);   // the host only launches this kernel when every zone is "fast"
+      gta_zone_solve_warp<true>(P, w.angle, lane, Z, P.pollMask[(size_t)w.angle * P.nz + zi]);   // every zone is "fast" (host check)
     }
     __syncwarp();
   }
@@ -690,7 +698,7 @@ int gta_device_sweep(umt_ctx *ctx, const double *d_P, double *d_PsiB) {
   P.nextZ = g.d_nextZ; P.nextC = g.d_nextC; P.items = g.d_items; P.counters = g.d_counters;
   P.sigTotal = g.d_sigTotal; P.sigtInv = g.d_sigtInv; P.tsa = g.d_tsaSource; P.tpsi = g.d_tpsi; P.pinc = g.d_pinc;
   if (g.flow3d && g.nStagesR <= 1) {
-    P.abortFlag = ctx->d_abort; P.spinLimit = ctx->spinLimit;
+    P.abortFlag = ctx->d_abort; P.spinLimit = ctx->spinLimit; P.pollMask = g.d_pollMask;
     gta_mark_kernel<<<dim3(std::max(1, std::min(2 * ctx->sm_count, (nc + 255) / 256)), g.nAng), 256, 0, ctx->stream>>>(g.d_tpsi, nc, rows);
     int occF = 0;
     UMT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occF, gta_sweep_flow_kernel, GTA_WARPS * 32, 0));
@@ -760,7 +768,7 @@ void umt_gta_release(umt_ctx *ctx) {
                g.d_greySource, g.d_tsaSource, g.d_phiInc, g.d_correction, g.d_chi, g.d_TT, g.d_tpsi, g.d_pinc, g.d_vec[0], g.d_vec[1], g.d_vec[2],
                g.d_vec[3], g.d_vecB[0], g.d_vecB[1], g.d_vecB[2], g.d_vecB[3], g.d_radEnergy, g.d_pzOld, g.d_volZone, g.d_red, g.d_P, g.d_PB,
                g.d_start, g.d_finish, g.d_level, g.d_fac, g.d_w1, g.d_w2, g.d_psim, g.d_tinc, g.d_levelAngles, g.d_planeOff, g.d_nHyp, g.d_reflOps,
-               g.d_prevAngle, g.d_psimA, g.d_tincA};
+               g.d_prevAngle, g.d_psimA, g.d_tincA, g.d_pollMask};
   for (void *q : p) if (q) cudaFree(q);
   g = GtaState();
 }
@@ -876,6 +884,26 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   for (int a = 0; a < g.nAng && g.flow3d; a++)
     for (int z : g.nextZ[a]) if (z < 0) { g.flow3d = false; break; }
   if (const char *e = getenv("UMT_GTA_KERNEL")) if (std::string(e) == "item") g.flow3d = false;
+  if (g.flow3d) {
+    std::vector<int> zoneOf(nc), planeOf(nz);
+    for (int z = 0; z < nz; z++) for (int c = 0; c < ctx->h_numCorner[z]; c++) zoneOf[ctx->h_cOffSet[z] + c] = z;
+    std::vector<unsigned> mask((size_t)g.nAng * nz, 0u);
+    for (int a = 0; a < g.nAng; a++) {
+      for (int p = 0; p < g.nHyp[a]; p++) for (int i = start[a][p]; i < start[a][p + 1]; i++) planeOf[std::abs(g.nextZ[a][i]) - 1] = p;
+      for (int i = 0; i < nz; i++) {
+        const int z = std::abs(g.nextZ[a][i]) - 1, c0 = ctx->h_cOffSet[z];
+        unsigned m = 0u;
+        for (int c = 0; c < ctx->h_numCorner[z]; c++)
+          for (int f = 0; f < 3; f++) {
+            const int row = ctx->h_cFP[(size_t)(c0 + c) * 3 + f] - 1;
+            if (row < nc && planeOf[zoneOf[row]] < planeOf[z]) m |= 1u << (3 * c + f);
+          }
+        mask[(size_t)a * nz + i] = m;
+      }
+    }
+    TRY(dalloc(ctx, &g.d_pollMask, mask.size()));
+    UMT_CUDA(ctx, umt_memcpy(ctx, g.d_pollMask, mask.data(), sizeof(unsigned) * mask.size(), cudaMemcpyHostToDevice));
+  }
   TRY(dalloc(ctx, &g.d_omega, (size_t)nd * g.nAng)); TRY(dalloc(ctx, &g.d_weight, g.nAng));
   TRY(dalloc(ctx, &g.d_nextZ, h_nextZ.size())); TRY(dalloc(ctx, &g.d_nextC, h_nextC.size()));
   TRY(dalloc(ctx, &g.d_items, items.size())); TRY(dalloc(ctx, &g.d_counters, 1 + (size_t)g.nCounters));
