@@ -451,7 +451,9 @@ def main():
         peak, peak_src = measured_peak()
         balg = sweep_kernel_bytes_per_unknown(G)
         achieved = unknowns * balg / (sweep_kernel_ms * 1e-3) / 1e9
-        tpu, tsrc = profiled_traffic_per_unknown()
+        # the committed capture is of the default workload in the two-buffer layout; any other run reports no traffic figure
+        same = (d, G, args.polar, args.azimuthal) == (20, 128, 2, 2) and not layout["single"]
+        tpu, tsrc = profiled_traffic_per_unknown() if same else (None, None)
         model41 = unknowns * algorithmic_bytes_per_unknown(G) / ((sweep_ms + phi_ms) / max(iters, 1) * 1e-3) / 1e9
         line = {
             "metric": "Sn sweep unknowns/sec (corner x angle x group)", "value": value, "unit": "unknowns/s",

@@ -499,7 +499,7 @@ static int finalize_schedule(umt_ctx *ctx) {
       UMT_CUDA(ctx, cudaMemGetInfo(&freeB, &totalB));
       const size_t slabB = sizeof(double) * (size_t)(nc + ctx->nb) * ctx->G;
       freeB += (size_t)ctx->psi1Slots * slabB;
-      const size_t reserve = ((size_t)2 << 30) + totalB / 50;
+      const size_t reserve = std::max((size_t)4 << 30, totalB / 10);   // left to the caller and to this library's smaller arrays
       const size_t slots = freeB > reserve ? (freeB - reserve) / slabB : 0;
       ctx->ringBatchesAuto = (int)std::min<size_t>((size_t)(NA + K - 1) / K, slots / (size_t)K);
       if (const char *e = getenv("UMT_RING_BATCHES")) ctx->ringBatchesAuto = std::max(1, atoi(e));
