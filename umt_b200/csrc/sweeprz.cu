@@ -906,6 +906,213 @@ __global__ void __launch_bounds__(RZP_THREADS, RZP_MIN_CTAS) sweeprz_pipe_kernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Level-chain kernel (quads with canonical records, one stage).  The r-z sweep is bound by its dependency chain, not by throughput:
+// 4P xi-levels whose (A + 1) swept angles are chained through PsiM, each angle a chain of hyperplanes, and every hop of the item
+// kernels costs store -> fence -> counter -> poll -> load.  Here ONE CTA owns one (xi-level, block of gb groups) -- the groups are
+// independent -- and walks that chain by itself, one step (a hyperplane, or a chunk of a large one) per __syncthreads(): no
+// tickets, counters, fences or polls anywhere.  The CTA is split into two groups of threads, one thread per (zone, group) pair
+// of a step in each:
+//   * the CHAIN group does only what depends on the previous steps: PsiM and upstream Psi1 rows through L2, a handful of FMAs per
+//     face (the closure in its linear form), the corner fluxes, the stores;
+//   * the STATIC group runs one step ahead: it copies the step's records into shared memory (two steps ahead), turns the landed
+//     Psi^n / STotal / Sigt values (loaded one step ahead into registers) into the group-dependent coefficients (every division of
+//     the zone solve) and leaves them in shared memory for the chain group.
+// The hop is then the dependent half alone.  Rows written by a step are read by later steps of the same CTA through L2 (ld.cg);
+// __syncthreads() orders them.
+struct RZRecS {   // RZRec as it sits in shared memory at the padded stride: same members, 8-byte alignment only
+  double vol[4], area[4], areaFac[4], sumArea[4];
+  double k1b[4][2], az[4][2], rez[4][2];
+  int row[4][2];
+  int c0, zone, nCorner;
+  unsigned inMask, exitMask;
+  unsigned char cez[4][2], ci[4];
+};
+static_assert(sizeof(RZRecS) == sizeof(RZRec), "RZRecS mirrors RZRec");
+struct RZStep { int angle, zbeg, n, pad; };          // zones [zbeg, zbeg + n) of nextZ(:, angle): one plane or a chunk of it
+constexpr int RZL_REC_STRIDE = 392;                  // 384-byte record + 8: consecutive zones fall into different shared-memory banks
+constexpr int RZL_NSTAT = 16;                        // per pair: src[4], A1[4][2], inv[4]
+struct RZLParams {
+  const RZRec *recs;
+  const int2 *zinfo;                                 // (NA, nz) in sweep order: first corner row, zone
+  const RZStep *steps;                               // (nLevels, maxSteps)
+  const int *nSteps;                                 // (nLevels)
+  int maxSteps, gb, nGB, ZCH, CT;                    // groups per CTA, group blocks, zones per step at most, threads per group
+};
+
+constexpr int RZL_MAX_CT = 320;                      // threads per group at most (640 per CTA: 102 registers each)
+__global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZParams P, RZLParams L) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  const int G = P.G, nc = P.nc, CT = L.CT, PCH = L.ZCH * L.gb;
+  const size_t slab = (size_t)(nc + P.nb) * G;
+  const int lev = blockIdx.x / L.nGB, g0 = (blockIdx.x - lev * L.nGB) * L.gb, gbA = min(L.gb, G - g0);
+  const int tid = threadIdx.x;
+  const bool chain = tid < CT;
+  const int t = chain ? tid : tid - CT;
+  unsigned char *recBuf = lsm;                                                   // 3 x ZCH x RZL_REC_STRIDE
+  double *statBuf = reinterpret_cast<double *>(lsm + (size_t)3 * L.ZCH * RZL_REC_STRIDE);   // 2 x RZL_NSTAT x PCH
+  const RZStep *steps = L.steps + (size_t)lev * L.maxSteps;
+  const int nS = L.nSteps[lev];
+  const double tau = P.tau;
+  const int zi = t / gbA, g = g0 + (t - zi * gbA);     // my pair of every step (if the step has that many)
+
+  auto copy_records = [&](int s) {                     // static group: records of step s -> recBuf[s % 3], padded stride
+    if (s >= nS) return;
+    const RZStep st = steps[s];
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(L.recs + (size_t)st.angle * P.nz + st.zbeg);
+    unsigned char *dst = recBuf + (size_t)(s % 3) * L.ZCH * RZL_REC_STRIDE;
+    for (int k = t; k < st.n * 24; k += CT) {
+      const int z = k / 24, w = k - z * 24;
+      const uint4 v = __ldg(src4 + k);   // two 8-byte stores: the padded stride is 8 mod 16
+      *reinterpret_cast<uint2 *>(dst + (size_t)z * RZL_REC_STRIDE + w * 16) = make_uint2(v.x, v.y);
+      *reinterpret_cast<uint2 *>(dst + (size_t)z * RZL_REC_STRIDE + w * 16 + 8) = make_uint2(v.z, v.w);
+    }
+  };
+  // inputs of my pair of a step, loaded one step ahead (static group): Psi^n and STotal of the 4 corners (local order), Sigt
+  double inPsi[4], inSt[4], inSig = 1.0;
+  int2 zNext = make_int2(0, 0);                        // zone info of my pair two steps ahead
+  auto load_zinfo = [&](int s) {
+    if (s < nS) { const RZStep st = steps[s]; if (zi < st.n) zNext = L.zinfo[(size_t)st.angle * P.nz + st.zbeg + zi]; }
+  };
+  auto load_inputs = [&](int s) {                      // uses zNext (= zone info of step s)
+    if (s >= nS) return;
+    const RZStep st = steps[s];
+    if (zi >= st.n) return;
+    const double *psiA = P.psi + (size_t)st.angle * slab + (size_t)zNext.x * G + g;
+    const double *stA = P.stotal + (size_t)zNext.x * G + g;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { inPsi[c] = __ldcs(psiA + (size_t)c * G); inSt[c] = __ldcs(stA + (size_t)c * G); }
+    inSig = __ldg(P.sigt + (size_t)zNext.y * G + g);
+  };
+  auto static_half = [&](int s) {                      // coefficients of my pair of step s -> statBuf[s % 2]
+    const RZStep st = steps[s];
+    if (zi >= st.n) return;
+    const RZRecS &R = *reinterpret_cast<const RZRecS *>(recBuf + ((size_t)(s % 3) * L.ZCH + zi) * RZL_REC_STRIDE);
+    double *out = statBuf + (size_t)(s % 2) * RZL_NSTAT * PCH + t;
+    const double sig = inSig, sigInv = 1.0 / sig;
+    double Q[4], src[4], A1[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {   // records are labelled by solve position: R.ci[p] = local corner of position p
+      const int lc = R.ci[c];
+      double a = inPsi[0], b = inSt[0];
+#pragma unroll
+      for (int k = 1; k < 4; k++) { a = lc == k ? inPsi[k] : a; b = lc == k ? inSt[k] : b; }
+      Q[c] = b + tau * a;
+      src[c] = R.vol[c] * Q[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        A1[c][f] = 0.0;
+        const double az = R.az[c][f];
+        if (az > 0.0) {
+          const int cez = rz_nb(c, f);
+          const double Rr = R.rez[c][f], dq = Q[c] - Q[cez];
+          double A0;
+          if (R.inMask & (1u << (2 * c + f))) {
+            const double ar = R.area[c];
+            const double sigA = sig * ar, sigA2 = sigA * sigA;
+            const double gnum = az * az * (FOURALPHA * sigA2 + az * (4.0 * sigA + 3.0 * az));
+            const double gden = ar * (4.0 * sigA * sigA2 + az * (6.0 * sigA2 + 2.0 * az * (2.0 * sigA + az)));
+            const double rd = Rr / (gnum + gden * sig);
+            A1[c][f] = rd * (ar * gnum * sig);
+            A0 = rd * (0.5 * az * gden * dq - ar * gnum * Q[c]);
+          } else {
+            A0 = 0.5 * (Rr * az) * dq * sigInv;
+          }
+          src[c] += A0;
+          src[cez] -= A0;
+        }
+      }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      out[(size_t)c * PCH] = src[c];
+      out[(size_t)(4 + 2 * c) * PCH] = A1[c][0];
+      out[(size_t)(5 + 2 * c) * PCH] = A1[c][1];
+      out[(size_t)(12 + c) * PCH] = 1.0 / (R.sumArea[c] + sig * R.vol[c]);
+    }
+  };
+  auto chain_half = [&](int s) {
+    const RZStep st = steps[s];
+    if (zi >= st.n) return;
+    const int a = st.angle;
+    const RZRecS &R = *reinterpret_cast<const RZRecS *>(recBuf + ((size_t)(s % 3) * L.ZCH + zi) * RZL_REC_STRIDE);
+    const double *in = statBuf + (size_t)(s % 2) * RZL_NSTAT * PCH + t;
+    double *psi1A = P.psi1 + (size_t)a * slab;
+    double *psimL = P.psim + (size_t)P.level[a] * nc * G;
+    const int c0 = R.c0;
+    double pm[4], u[4][2], src[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      pm[c] = __ldcg(&psimL[(size_t)(c0 + (int)R.ci[c]) * G + g]);
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        u[c][f] = 0.0;
+        if (R.inMask & (1u << (2 * c + f))) u[c][f] = __ldcg(&psi1A[(size_t)R.row[c][f] * G + g]);
+      }
+      src[c] = in[(size_t)c * PCH];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        const double a1 = in[(size_t)(4 + 2 * c + f) * PCH];
+        src[c] = fma(R.k1b[c][f] + a1, u[c][f], src[c]);
+        src[rz_nb(c, f)] += -a1 * u[c][f];
+      }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double p = (src[c] + R.areaFac[c] * pm[c]) * in[(size_t)(12 + c) * PCH];
+      src[c] = p;
+      src[rz_nb(c, 0)] += (R.rez[c][0] * R.az[c][0]) * p;
+      src[rz_nb(c, 1)] += (R.rez[c][1] * R.az[c][1]) * p;
+    }
+    const bool starting = P.start[a] != 0, fin = P.finishNext[a] != 0;
+    double *psi1N = psi1A + slab;
+    const double w1 = P.tauW1[a], w2 = P.tauW2[a];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const size_t r = (size_t)(c0 + (int)R.ci[c]) * G + g;
+      const double p = src[c];
+      const double pmn = starting ? p : w1 * p - w2 * pm[c];
+      __stcg(&psimL[r], pmn); __stcg(&psi1A[r], p);
+      if (fin) psi1N[r] = pmn;
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        if (R.exitMask & (1u << (2 * c + f))) {
+          const int row = R.row[c][f];
+          psi1A[(size_t)row * G + g] = p;
+          if (fin) psi1N[(size_t)row * G + g] = pmn;
+        }
+      }
+    }
+  };
+
+  // prologue: the static group brings steps 0 and 1 into flight, then step 0 is fully prepared before the chain group starts
+  const bool mine = zi < L.ZCH;
+  if (!chain) {
+    copy_records(0); copy_records(1);
+    if (mine) { load_zinfo(0); load_inputs(0); }
+  }
+  __syncthreads();
+  if (!chain && mine) { static_half(0); load_zinfo(1); load_inputs(1); load_zinfo(2); }
+  __syncthreads();
+  for (int s = 0; s < nS; s++) {
+    if (chain) {
+      if (mine) chain_half(s);
+    } else {
+      copy_records(s + 2);
+      if (mine && s + 1 < nS) {
+        static_half(s + 1);          // consumes the inputs loaded for step s + 1
+        load_inputs(s + 2);          // zNext holds the zone info of step s + 2
+        load_zinfo(s + 3);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Dataflow kernel.  The same work items in the same topological order, but nothing waits for a whole plane: every warp takes
 // 32 (zone, group) pairs of an item, runs the static half, then each lane polls exactly the values its pair needs -- the Psi1 rows
 // behind its incident faces and the previous angle's PsiM of its corners -- until they are no longer marked (RZ_SENTINEL), solves
@@ -1193,6 +1400,7 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       }
       ctx->rz_canon = canon;
       ctx->rz_recs_valid = true;
+      ctx->rz_lc_zch = 0;   // the level-chain kernel's step table belongs to the old schedule
       // what the loader warp of the pipelined kernel needs per (angle, zone in sweep order): first corner row, zone
       std::vector<int2> zinfo(n, make_int2(0, 0));
       for (int a = 0; a < ctx->NA; a++) {
@@ -1207,6 +1415,52 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       UMT_CUDA(ctx, umt_memcpy(ctx, ctx->d_zinfo, zinfo.data(), sizeof(int2) * n, cudaMemcpyHostToDevice));
     }
     const bool flow = ctx->rz_flow && ctx->nStages <= 1;
+    bool lc = ctx->rz_canon && !flow && ctx->nStages <= 1;
+    if (const char *e = getenv("UMT_RZ_KERNEL")) { if (std::string(e) != "lc") lc = false; } else lc = false;
+    if (lc) {
+      // steps of every xi-level: its swept angles in order, their planes in order, large planes cut into chunks of ZCH zones
+      int gb = 2;
+      if (const char *e = getenv("UMT_RZ_LC_GB")) gb = std::max(1, std::min(8, atoi(e)));
+      gb = std::min(gb, ctx->G);
+      int maxPlane = 1;
+      for (int a = 0; a < ctx->NA; a++) for (int p = 0; p < ctx->nHyp[a]; p++) maxPlane = std::max(maxPlane, ctx->zonesInPlane[a][p]);
+      int ZCH = std::min(maxPlane, std::min(RZL_MAX_CT / gb, (int)(220000 / (3 * RZL_REC_STRIDE + 2 * RZL_NSTAT * 8 * gb))));
+      if (const char *e = getenv("UMT_RZ_LC_ZONES")) ZCH = std::max(1, std::min(ZCH, atoi(e)));
+      if (!ctx->d_rzSteps || ctx->rz_lc_zch != ZCH) {
+        const int nL = ctx->nLevels;
+        std::vector<std::vector<RZStep>> per(nL);
+        for (int a = 0; a < ctx->NA; a++) {
+          if (ctx->nHyp[a] == 0) continue;
+          int z0 = 0;
+          for (int p = 0; p < ctx->nHyp[a]; p++) {
+            const int n = ctx->zonesInPlane[a][p];
+            for (int o = 0; o < n; o += ZCH) per[ctx->h_level[a]].push_back(RZStep{a, z0 + o, std::min(ZCH, n - o), 0});
+            z0 += n;
+          }
+        }
+        size_t maxSteps = 1;
+        for (auto &v : per) maxSteps = std::max(maxSteps, v.size());
+        std::vector<RZStep> flat((size_t)nL * maxSteps, RZStep{0, 0, 0, 0});
+        std::vector<int> ns(nL, 0);
+        for (int l = 0; l < nL; l++) { ns[l] = (int)per[l].size(); std::copy(per[l].begin(), per[l].end(), flat.begin() + (size_t)l * maxSteps); }
+        if (ctx->d_rzSteps) { cudaFree(ctx->d_rzSteps); ctx->d_rzSteps = nullptr; }
+        if (ctx->d_rzNSteps) { cudaFree(ctx->d_rzNSteps); ctx->d_rzNSteps = nullptr; }
+        UMT_CUDA(ctx, cudaMalloc(&ctx->d_rzSteps, sizeof(RZStep) * flat.size()));
+        UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_rzNSteps, sizeof(int) * nL));
+        UMT_CUDA(ctx, umt_memcpy(ctx, ctx->d_rzSteps, flat.data(), sizeof(RZStep) * flat.size(), cudaMemcpyHostToDevice));
+        UMT_CUDA(ctx, umt_memcpy(ctx, ctx->d_rzNSteps, ns.data(), sizeof(int) * nL, cudaMemcpyHostToDevice));
+        ctx->rz_lc_zch = ZCH; ctx->rz_lc_maxSteps = (int)maxSteps;
+      }
+      RZLParams L;
+      L.recs = recs; L.zinfo = ctx->d_zinfo; L.steps = static_cast<const RZStep *>(ctx->d_rzSteps); L.nSteps = ctx->d_rzNSteps;
+      L.maxSteps = ctx->rz_lc_maxSteps; L.gb = gb; L.nGB = (ctx->G + gb - 1) / gb; L.ZCH = ZCH; L.CT = (ZCH * gb + 31) / 32 * 32;
+      const size_t smemL = (size_t)3 * ZCH * RZL_REC_STRIDE + (size_t)2 * RZL_NSTAT * 8 * ZCH * gb;
+      UMT_CUDA(ctx, cudaFuncSetAttribute(sweeprz_lc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemL));
+      sweeprz_lc_kernel<<<ctx->nLevels * L.nGB, 2 * L.CT, smemL, ctx->stream>>>(P, L);
+      UMT_CUDA(ctx, cudaGetLastError());
+      ctx->last_launches += 1;
+      return UMT_OK;
+    }
     bool pipe = ctx->rz_canon && !flow && ctx->G % 2 == 0 && ctx->zones_per_item <= RZP_ZMAX && ctx->zones_per_item * ctx->G <= 64;
     // measured at configs[1] size (40x40 tiles, G = 64): 12-17 ms against the record kernel's 5.2 ms.  The r-z sweep has 4 xi-levels of 5
     // chained angles and ~80-zone planes: about a thousand items are ready at any time, so items a CTA holds ahead of their turn

@@ -107,7 +107,7 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
                   ctx->d_exitB, ctx->d_exitC, ctx->d_exitA, ctx->d_psi, ctx->d_psi1, ctx->d_stotal,
                   ctx->d_sigt, ctx->d_phi, ctx->d_psim, ctx->d_recs, ctx->d_zinfo, ctx->d_angDerivFac, ctx->d_tauW1, ctx->d_tauW2,
                   ctx->d_start, ctx->d_finishNext, ctx->d_level, ctx->d_reflOps, ctx->d_rzLevelAngles, ctx->d_rzPlaneOff, ctx->d_rzNHyp,
-                  ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad, ctx->d_itemsRing, ctx->d_tailSlot, ctx->d_tailW};
+                  ctx->d_rzPrev, ctx->d_rzPsimA, ctx->d_rzRecs, ctx->d_rzBad, ctx->d_rzSteps, ctx->d_rzNSteps, ctx->d_itemsRing, ctx->d_tailSlot, ctx->d_tailW};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->d_abort) cudaFree(ctx->d_abort);
   if (ctx->h_abort) cudaFreeHost(ctx->h_abort);

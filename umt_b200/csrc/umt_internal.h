@@ -167,6 +167,8 @@ struct umt_ctx {
   void *d_rzRecs = nullptr;            // (NA, nz) RZRec in sweep order
   int *d_rzBad = nullptr;              // number of zones that do not fit the canonical labelling
   bool rz_rec = false, rz_recs_valid = false, rz_canon = false;
+  // r-z level-chain kernel (sweeprz.cu): steps (plane chunks) of every xi-level
+  void *d_rzSteps = nullptr; int *d_rzNSteps = nullptr; int rz_lc_zch = 0, rz_lc_maxSteps = 0;
   // r-z dataflow kernel (sweeprz.cu): no counters, the angular fluxes themselves are the completion flags
   bool rz_flow = false;
   int *d_rzPrev = nullptr;             // (NA) previous swept angle of the xi-level, -1 for the first
