@@ -195,14 +195,16 @@ int umt_get_exchange_counts(umt_ctx *ctx, int sharedIndex, int *nSend /* (NA) */
 int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, int *listSend, int *listRecv);
 /* CSet%IncFlux / IncFluxOld per comm set after the last umt_sweep (rt/setIncidentFlux.F90:128-146):
    one bin per angle in 3-D, per xi-level in 2-D. */
-/* rt/SweepScheduler.F90 + rt/setNetFlux.F90.  By default every angle (3-D) / xi-level (r-z) is its own comm set: all are
-   swept concurrently, the exchange is lagged one flux pass and the scheduler is the identity.  umt_set_comm_sets groups the
-   angles into nCommSets consecutive comm sets of NA/nCommSets bins (the reference's nSets < maxAngleSets,
+/* rt/SweepScheduler.F90 + rt/setNetFlux.F90.  The scheduler orders angle BINS: angles in 3-D, xi-levels in r-z (SweepScheduler.F90:110-117).
+   By default every bin is its own comm set: all are swept concurrently, the exchange is lagged one flux pass and the scheduler is the
+   identity.  umt_set_comm_sets groups the bins into nCommSets consecutive comm sets (the reference's nSets < maxAngleSets,
    aux/ConstructPhaseSpaceSets.F90:247-296); umt_sweep_scheduler (collective over the domains, once per cycle like
    control/initializeSets.F90:515-523) then fixes CSet%AngleOrder / RecvOrder from the net flux on the shared boundaries
-   (netFlux (nShared, NA) = exiting - incident current; NULL: tallied from the PsiB on the device) and the mirror dependencies,
-   and umt_sweep runs the comm sets' steps one after the other with SendFlux/RecvFlux per step (snac/SetSweep.F90:113-170),
-   so a neighbour that sweeps an angle later in the pass receives this pass's flux.  3-D only. */
+   (netFlux: rows of NA doubles per shared boundary, entry b = exiting - incident current of bin b -- the first nLevels entries of a row in
+   r-z; NULL: tallied from the PsiB on the device) and the mirror dependencies, and umt_sweep runs the comm sets' steps one after the other
+   with SendFlux/RecvFlux per step (snac/SetSweep.F90:113-170), so a neighbour that sweeps a bin later in the pass receives this pass's
+   flux.  umt_get_angle_order returns the angles (a level's angles in level order in r-z).  r-z comm sets of several levels are not
+   combined with reflecting boundaries. */
 int umt_set_comm_sets(umt_ctx *ctx, int nCommSets);
 int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux);
 int umt_get_net_flux(umt_ctx *ctx, double *netFlux /* (nShared, NA): CSet%NetFlux of the last umt_sweep_scheduler */);

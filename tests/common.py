@@ -586,10 +586,11 @@ def oracle_net_flux(problems, lists):
     return out
 
 
-def oracle_sweep_scheduler(problems, nCommSets, netflux, mrefs=None):
+def oracle_sweep_scheduler(problems, nCommSets, netflux, mrefs=None, nBins=None):
     """Every rank's CSet%AngleOrder (comm sets concatenated, 0-based angles) and RecvOrder[k] per shared boundary.
-    netflux[r] is (nShared_r, NA); mrefs[r][n][a] the mirror angle of a on reflecting boundary n (-1: not incident)."""
-    N, NA = len(problems), problems[0].NA
+    netflux[r] is (nShared_r, NA); mrefs[r][n][a] the mirror angle of a on reflecting boundary n (-1: not incident).
+    nBins: schedule that many angle bins instead of the angles themselves (r-z: the xi-levels; no reflecting boundaries then)."""
+    N, NA = len(problems), (nBins if nBins is not None else problems[0].NA)
     bps = NA // nCommSets
     depend = [netflux[r].sum(axis=0) if len(netflux[r]) else np.zeros(NA) for r in range(N)]
     depend = [d.copy() for d in depend]
@@ -782,3 +783,96 @@ def oracle_sweep_rz_reflecting(p, savePsi):
                     p.PsiB[a, sl] = p.PsiB[mrefs[k][a], sl]
             O.sweep_rz(p.om, p.geom, p.sched, a, p.q, p.tau, p.STotal, p.Sigt, p.Psi, Psi1, PsiM[int(lev[a])], p.PsiB, Phi, p.bdy[a], savePsi)
     return Phi, stage, mrefs
+
+
+# ---------------------------------------------------------------------------
+# r-z: the scheduler's angle bins are the xi-levels (SweepScheduler.F90:110-117)
+# ---------------------------------------------------------------------------
+def rz_bins(p):
+    lev = np.asarray(p.q["level"]) - 1
+    nBins = int(lev.max()) + 1
+    return lev, [np.flatnonzero(lev == b) for b in range(nBins)]
+
+
+def oracle_net_flux_bins(problems, lists):
+    """setNetFlux per shared boundary and xi-level: the per-angle net flux summed over the angles of each bin"""
+    lev, angles = rz_bins(problems[0])
+    per_angle = oracle_net_flux(problems, lists)
+    return [np.stack([nf[:, a].sum(axis=1) for a in angles], axis=1) if len(nf) else np.zeros((0, len(angles))) for nf in per_angle]
+
+
+def oracle_multi_sweep_ordered_rz(problems, lists, nCommSets, binOrder, savePsi, maxFluxIters=1, fluxTol=1e-6):
+    """SetSweep.F90 in r-z with comm sets of several xi-levels: at step i every comm set of every rank first sends the neighbours the
+    rows of the levels *they* sweep at step i (as they are now), receives its own, then sweeps the angles of its level in order."""
+    N, NA = len(problems), problems[0].NA
+    lev, angles = rz_bins(problems[0])
+    nBins = len(angles)
+    bps = nBins // nCommSets
+    nbrs = [shared_boundaries(p.mesh) for p in problems]
+
+    def exit_currents():
+        res = []
+        for r, p in enumerate(problems):
+            per_b = []
+            for k, b in enumerate(nbrs[r]):
+                ex = np.zeros(NA)
+                for a in range(NA):
+                    el = lists[r][k][a][0]
+                    dot = p.geom["A_bdy"][el - 1] @ p.omega[a]
+                    ex[a] = p.weight[a] * float((dot * p.PsiB[a, el - 1].sum(axis=1)).sum())
+                per_b.append(ex)
+            res.append(per_b)
+        return res
+
+    def incident(ex):
+        inc = []
+        for r, p in enumerate(problems):
+            v = np.zeros(nBins)
+            for b in nbrs[r]:
+                kq = [i for i, x in enumerate(nbrs[b.neighbor]) if x.neighbor == r][0]
+                np.add.at(v, lev, ex[b.neighbor][kq])
+            inc.append(v)
+        return inc
+
+    inc = incident(exit_currents())
+    it = 0
+    while True:
+        it += 1
+        Phi = [np.zeros((p.mesh.ncornr, p.G)) for p in problems]
+        PsiM = [{b: np.zeros((p.mesh.ncornr, p.G)) for b in range(nBins)} for p in problems]
+        Psi1 = [np.zeros((p.mesh.ncornr + p.mesh.nbelem, p.G)) for p in problems]
+        for i in range(bps):
+            snap = [p.PsiB.copy() for p in problems]
+            for r, p in enumerate(problems):
+                for k, b in enumerate(nbrs[r]):
+                    kq = [j for j, x in enumerate(nbrs[b.neighbor]) if x.neighbor == r][0]
+                    for c in range(nCommSets):
+                        for a in angles[binOrder[r][c * bps + i]]:
+                            rcv, snd = lists[r][k][a][1], lists[b.neighbor][kq][a][0]
+                            assert len(rcv) == len(snd)
+                            p.PsiB[a, rcv - 1] = snap[b.neighbor][a, snd - 1]
+            for r, p in enumerate(problems):
+                for c in range(nCommSets):
+                    bn = binOrder[r][c * bps + i]
+                    for a in angles[bn]:
+                        if p.q["finish"][a]:
+                            continue
+                        O.sweep_rz(p.om, p.geom, p.sched, a, p.q, p.tau, p.STotal, p.Sigt, p.Psi, Psi1[r], PsiM[r][bn], p.PsiB, Phi[r], p.bdy[a], savePsi)
+        inc_old, inc = inc, incident(exit_currents())
+        if savePsi:
+            break
+        notconv = 0
+        for r in range(N):   # testFluxConv.F90:55-105 per comm set
+            for c in range(nCommSets):
+                bins = range(c * bps, (c + 1) * bps)
+                total = sum(inc[r][b] for b in bins)
+                conv = True
+                for b in bins:
+                    rel = 0.0
+                    if total != 0.0 and inc[r][b] / total > 0.001:
+                        rel = abs(inc[r][b] - inc_old[r][b]) / inc[r][b]
+                    conv = conv and rel <= fluxTol
+                notconv += not conv
+        if notconv == 0 or it >= maxFluxIters:
+            break
+    return Phi, it, inc

@@ -77,3 +77,20 @@ __device__ __forceinline__ int umt_ld_acquire(const int *p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+// 1/x for normal x > 0: MUFU.RCP64H seed + two Newton steps, ~1 ulp (as in sweep3d.cu); keeps IEEE division off latency-bound paths
+__device__ __forceinline__ double umt_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in the background
+__device__ __forceinline__ void umt_cp_async8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(umt_smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void umt_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void umt_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

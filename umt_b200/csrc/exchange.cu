@@ -604,7 +604,7 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   UMT_CUDA(ctx, cudaGetLastError());
   r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
   if (r) return r;
-  const int binsPerSet = (ctx->ndim == 3 && ctx->nCommSets > 0) ? ctx->NA / ctx->nCommSets : 1;
+  const int binsPerSet = ctx->nCommSets > 0 ? ctx->nBins / ctx->nCommSets : 1;
   flux_conv_kernel<<<1, 32, 0, xstream(ctx)>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, binsPerSet, ctx->d_incFlux,
                                               ctx->d_incFluxOld, tol, ctx->fluxFloor, ctx->d_nNotConv);
   UMT_CUDA(ctx, cudaGetLastError());
@@ -783,13 +783,26 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const double *__restri
 }
 }  // namespace
 
-// nCommSets consecutive groups of angle bins (3-D: bins are angles); 0 restores the finest decomposition
+// Angle bins of the scheduler (rt/SweepScheduler.F90:110-117: "an angle-bin is a xi-level in 2d and an angle in 3D"): bin of every
+// angle and the angles of every bin in sweep order.
+static void angle_bins(const umt_ctx *ctx, int &nBins, std::vector<int> &binOf, std::vector<std::vector<int>> &anglesOf) {
+  const int NA = ctx->NA;
+  binOf.assign(NA, 0);
+  if (ctx->ndim == 3) { nBins = NA; for (int a = 0; a < NA; a++) binOf[a] = a; }
+  else { nBins = std::max(ctx->nLevels, 1); for (int a = 0; a < NA; a++) binOf[a] = ctx->h_level[a]; }
+  anglesOf.assign(nBins, {});
+  for (int a = 0; a < NA; a++) anglesOf[binOf[a]].push_back(a);
+}
+
+// nCommSets consecutive groups of angle bins (3-D: bins are angles, r-z: xi-levels); 0 restores the finest decomposition
 extern "C" int umt_set_comm_sets(umt_ctx *ctx, int nCommSets) {
   if (!ctx) return UMT_ERR_ARG;
   if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm_sets: quadrature not set");
-  if (nCommSets < 0 || (nCommSets > 0 && ctx->NA % nCommSets != 0)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_comm_sets: %d sets do not divide %d angles", nCommSets, ctx->NA);
-  if (nCommSets > 0 && nCommSets < ctx->NA && ctx->ndim != 3) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm_sets: comm sets of several bins are 3-D only (r-z: one xi-level per comm set)");
-  ctx->nCommSets = nCommSets == ctx->NA ? 0 : nCommSets;
+  const int nBinsAll = ctx->ndim == 3 ? ctx->NA : std::max(ctx->nLevels, 1);
+  if (nCommSets < 0 || (nCommSets > 0 && nBinsAll % nCommSets != 0)) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_set_comm_sets: %d sets do not divide %d angle bins", nCommSets, nBinsAll);
+  if (nCommSets > 0 && nCommSets < nBinsAll && ctx->ndim != 3 && !ctx->refl.empty())
+    UMT_FAIL(ctx, UMT_ERR_STATE, "umt_set_comm_sets: r-z comm sets of several xi-levels are not supported together with reflecting boundaries");
+  ctx->nCommSets = nCommSets == nBinsAll ? 0 : nCommSets;
   ctx->have_comm_order = false;
   ctx->sched_dirty = true;
   return UMT_OK;
@@ -804,11 +817,17 @@ extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
   if (ctx->nCommSets <= 0) { ctx->have_comm_order = false; return UMT_OK; }   // one bin per comm set: identity
   if (ctx->device < 0) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: host-only context");
   UMT_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int NA = ctx->NA, nC = ctx->nCommSets, bps = NA / nC;
+  const int NA = ctx->NA, nC = ctx->nCommSets;
+  int nBins = 0;
+  std::vector<int> binOf;
+  std::vector<std::vector<int>> anglesOf;
+  angle_bins(ctx, nBins, binOf, anglesOf);
+  const int bps = nBins / nC;           // bins per comm set
   const size_t nS = ctx->shared.size();
   if (nS > 0) { int r = ready(ctx); if (r) return r; }
   int r = umt_reflect_stages(ctx);   // mirror angles
   if (r) return r;
+  // weightComm(shared, bin): rows of NA entries, the first nBins used (3-D: nBins == NA)
   std::vector<double> w(std::max<size_t>(nS, 1) * NA, 1.0);
   if (nS > 0) {
     if (netFlux) std::copy(netFlux, netFlux + nS * NA, w.begin());
@@ -816,27 +835,30 @@ extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
       if (!ctx->d_psi) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_sweep_scheduler: no state on the device to tally the net flux from");
       r = umt_exchange_tally(ctx, 0.0);
       if (r) return r;
+      ctx->pack_valid = true; ctx->recv_valid = false;
       std::vector<double> ex(nS * NA), in(nS * NA);
       UMT_CUDA(ctx, cudaMemcpyAsync(ex.data(), ctx->d_exitFlux, sizeof(double) * nS * NA, cudaMemcpyDeviceToHost, ctx->stream));
       UMT_CUDA(ctx, cudaMemcpyAsync(in.data(), ctx->d_incRecv, sizeof(double) * nS * NA, cudaMemcpyDeviceToHost, ctx->stream));
       UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      for (size_t i = 0; i < nS * NA; i++) w[i] = ex[i] - in[i];
+      std::fill(w.begin(), w.end(), 0.0);
+      for (size_t k = 0; k < nS; k++)   // setNetFlux.F90:61-141: exit minus incident current per shared boundary and bin
+        for (int a = 0; a < NA; a++) w[k * NA + binOf[a]] += ex[k * NA + a] - in[k * NA + a];
     }
   }
   ctx->netFlux.assign(w.begin(), w.begin() + nS * NA);
-  std::vector<double> depend(NA, 0.0);
-  for (int a = 0; a < NA; a++)
-    for (size_t k = 0; k < nS; k++) depend[a] += w[k * NA + a];
+  std::vector<double> depend(nBins, 0.0);
+  for (int b = 0; b < nBins; b++)
+    for (size_t k = 0; k < nS; k++) depend[b] += w[k * NA + b];
   const int nR = (int)ctx->refl.size();
-  std::vector<int> nRefl(NA, 0), depAngle((size_t)std::max(nR, 1) * NA, -1);
+  std::vector<int> nRefl(nBins, 0), depAngle((size_t)std::max(nR, 1) * NA, -1);
   for (int n = 0; n < nR; n++)
     for (int a = 0; a < NA; a++) {
       const int m = ctx->refl[n].mref[a];
-      if (m >= 0) { depAngle[(size_t)n * NA + m] = a; nRefl[a]++; }
+      if (m >= 0) { depAngle[(size_t)n * NA + m] = a; nRefl[binOf[a]]++; }
     }
-  std::vector<unsigned char> notDone(NA, 1);
-  ctx->angleOrder.assign(NA, 0);
-  ctx->recvOrder.assign(nS, std::vector<int>(NA, 0));
+  std::vector<unsigned char> notDone(nBins, 1);
+  std::vector<int> binOrder(nBins, 0);                                // per comm set concatenated: bin swept at each step
+  std::vector<std::vector<int>> binRecvOrder(nS, std::vector<int>(nBins, 0));
   int *d_s = nullptr, *d_r = nullptr;
   UMT_CUDA(ctx, cudaMalloc((void **)&d_s, sizeof(int) * nC));
   UMT_CUDA(ctx, cudaMalloc((void **)&d_r, sizeof(int) * nC * std::max<size_t>(nS, 1)));
@@ -863,27 +885,35 @@ extern "C" int umt_sweep_scheduler(umt_ctx *ctx, const double *netFlux) {
     }
     for (int c = 0; c < nC; c++) {
       const int nb_ = newbin[c];
-      ctx->angleOrder[c * bps + i] = nb_;
-      for (int n = 0; n < nR; n++) {
-        const int aRef = depAngle[(size_t)n * NA + nb_];
-        if (aRef >= 0 && notDone[aRef]) nRefl[aRef]--;
-      }
+      binOrder[c * bps + i] = nb_;
+      for (int n = 0; n < nR; n++)
+        for (int a : anglesOf[nb_]) {
+          const int aRef = depAngle[(size_t)n * NA + a];
+          if (aRef >= 0 && notDone[binOf[aRef]]) nRefl[binOf[aRef]]--;
+        }
       notDone[nb_] = 0;
     }
     for (size_t k = 0; k < nS; k++)
       for (int c = 0; c < nC; c++) {
         const int b = binRecv[k * nC + c];
         if (b < c * bps || b >= (c + 1) * bps) { ctx->err = "umt_sweep_scheduler: neighbour sent a bin outside the comm set"; rc = UMT_ERR_STATE; break; }
-        ctx->recvOrder[k][c * bps + i] = b;
+        binRecvOrder[k][c * bps + i] = b;
         if (notDone[b]) depend[b] -= w[k * NA + b];
       }
     // (a failure leaves the step loop through its !rc condition; the neighbours fail on their next exchange with this rank)
   }
   cudaFree(d_s); cudaFree(d_r);
   if (rc) { if (rc == UMT_ERR_CUDA) ctx->err = "umt_sweep_scheduler: CUDA copy failed"; return rc; }
+  // CSet%AngleOrder / RecvOrder: the angles of the chosen bins in bin order (SweepScheduler.F90:269-300), and the step of every angle
+  ctx->angleOrder.clear();
+  ctx->recvOrder.assign(nS, {});
   ctx->commStageOf.assign(NA, 0);
+  ctx->binOrder = binOrder; ctx->binRecvOrder = binRecvOrder; ctx->nSchedBins = nBins; ctx->binsPerSet = bps;
   for (int c = 0; c < nC; c++)
-    for (int i = 0; i < bps; i++) ctx->commStageOf[ctx->angleOrder[c * bps + i]] = i;
+    for (int i = 0; i < bps; i++) {
+      for (int a : anglesOf[binOrder[c * bps + i]]) { ctx->angleOrder.push_back(a); ctx->commStageOf[a] = i; }
+      for (size_t k = 0; k < nS; k++) for (int a : anglesOf[binRecvOrder[k][c * bps + i]]) ctx->recvOrder[k].push_back(a);
+    }
   ctx->have_comm_order = true;
   ctx->sched_dirty = true;
   return nS > 0 ? umt_exchange_build_stages(ctx) : UMT_OK;
@@ -913,17 +943,22 @@ extern "C" int umt_get_angle_order(umt_ctx *ctx, int *angleOrder /* (NA) */, int
 
 // rows each neighbour needs from me at every step (the angles it sweeps then: RecvOrder) and rows I receive (AngleOrder)
 int umt_exchange_build_stages(umt_ctx *ctx) {
-  const int NA = ctx->NA, nC = ctx->nCommSets, bps = NA / nC;
+  const int NA = ctx->NA, nC = ctx->nCommSets, bps = ctx->binsPerSet;
+  int nBins = 0;
+  std::vector<int> binOf;
+  std::vector<std::vector<int>> anglesOf;
+  angle_bins(ctx, nBins, binOf, anglesOf);
   for (size_t k = 0; k < ctx->shared.size(); k++) {
     SharedBdy &s = ctx->shared[k];
     if ((int)s.send_b.size() != NA) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_exchange_build_stages: exchange lists not built");
     std::vector<long long> snd, rcv;
     s.stage_send_off.assign(bps + 1, 0); s.stage_recv_off.assign(bps + 1, 0);
     for (int i = 0; i < bps; i++) {
-      for (int c = 0; c < nC; c++) {
-        const int as = ctx->recvOrder[k][c * bps + i], ar = ctx->angleOrder[c * bps + i];
-        for (int b : s.send_b[as]) snd.push_back((long long)as * ctx->rows_total() + ctx->nc + b);
-        for (int b : s.recv_b[ar]) rcv.push_back((long long)ar * ctx->rows_total() + ctx->nc + b);
+      for (int c = 0; c < nC; c++) {   // the neighbour gets the angles of the bin IT sweeps at this step, I receive those of mine
+        for (int as : anglesOf[ctx->binRecvOrder[k][c * bps + i]])
+          for (int b : s.send_b[as]) snd.push_back((long long)as * ctx->rows_total() + ctx->nc + b);
+        for (int ar : anglesOf[ctx->binOrder[c * bps + i]])
+          for (int b : s.recv_b[ar]) rcv.push_back((long long)ar * ctx->rows_total() + ctx->nc + b);
       }
       s.stage_send_off[i + 1] = snd.size(); s.stage_recv_off[i + 1] = rcv.size();
     }

@@ -959,14 +959,13 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
   auto copy_records = [&](int s) {                     // static group: records of step s -> recBuf[s % 3], padded stride
     if (s >= nS) return;
     const RZStep st = steps[s];
-    const uint4 *src4 = reinterpret_cast<const uint4 *>(L.recs + (size_t)st.angle * P.nz + st.zbeg);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(L.recs + (size_t)st.angle * P.nz + st.zbeg);
     unsigned char *dst = recBuf + (size_t)(s % 3) * L.ZCH * RZL_REC_STRIDE;
-    for (int k = t; k < st.n * 24; k += CT) {
-      const int z = k / 24, w = k - z * 24;
-      const uint4 v = __ldg(src4 + k);   // two 8-byte stores: the padded stride is 8 mod 16
-      *reinterpret_cast<uint2 *>(dst + (size_t)z * RZL_REC_STRIDE + w * 16) = make_uint2(v.x, v.y);
-      *reinterpret_cast<uint2 *>(dst + (size_t)z * RZL_REC_STRIDE + w * 16 + 8) = make_uint2(v.z, v.w);
+    for (int k = t; k < st.n * 48; k += CT) {   // 8-byte asynchronous copies (the padded stride is 8 mod 16): nobody waits for them here
+      const int z = k / 48, w = k - z * 48;
+      umt_cp_async8(dst + (size_t)z * RZL_REC_STRIDE + w * 8, src + (size_t)k * 8);
     }
+    umt_cp_async_commit();
   };
   // inputs of my pair of a step, loaded one step ahead (static group): Psi^n and STotal of the 4 corners (local order), Sigt
   double inPsi[4], inSt[4], inSig = 1.0;
@@ -989,7 +988,7 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
     if (zi >= st.n) return;
     const RZRecS &R = *reinterpret_cast<const RZRecS *>(recBuf + ((size_t)(s % 3) * L.ZCH + zi) * RZL_REC_STRIDE);
     double *out = statBuf + (size_t)(s % 2) * RZL_NSTAT * PCH + t;
-    const double sig = inSig, sigInv = 1.0 / sig;
+    const double sig = inSig, sigInv = umt_rcp(sig);
     double Q[4], src[4], A1[4][2];
 #pragma unroll
     for (int c = 0; c < 4; c++) {   // records are labelled by solve position: R.ci[p] = local corner of position p
@@ -1015,7 +1014,7 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
             const double sigA = sig * ar, sigA2 = sigA * sigA;
             const double gnum = az * az * (FOURALPHA * sigA2 + az * (4.0 * sigA + 3.0 * az));
             const double gden = ar * (4.0 * sigA * sigA2 + az * (6.0 * sigA2 + 2.0 * az * (2.0 * sigA + az)));
-            const double rd = Rr / (gnum + gden * sig);
+            const double rd = Rr * umt_rcp(gnum + gden * sig);
             A1[c][f] = rd * (ar * gnum * sig);
             A0 = rd * (0.5 * az * gden * dq - ar * gnum * Q[c]);
           } else {
@@ -1030,7 +1029,7 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
       out[(size_t)c * PCH] = src[c];
       out[(size_t)(4 + 2 * c) * PCH] = A1[c][0];
       out[(size_t)(5 + 2 * c) * PCH] = A1[c][1];
-      out[(size_t)(12 + c) * PCH] = 1.0 / (R.sumArea[c] + sig * R.vol[c]);
+      out[(size_t)(12 + c) * PCH] = umt_rcp(R.sumArea[c] + sig * R.vol[c]);
     }
   };
   auto chain_half = [&](int s) {
@@ -1094,6 +1093,7 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
   if (!chain) {
     copy_records(0); copy_records(1);
     if (mine) { load_zinfo(0); load_inputs(0); }
+    umt_cp_async_wait_all();
   }
   __syncthreads();
   if (!chain && mine) { static_half(0); load_zinfo(1); load_inputs(1); load_zinfo(2); }
@@ -1102,12 +1102,13 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
     if (chain) {
       if (mine) chain_half(s);
     } else {
-      copy_records(s + 2);
+      copy_records(s + 2);           // asynchronous: read for the first time one iteration from now
       if (mine && s + 1 < nS) {
         static_half(s + 1);          // consumes the inputs loaded for step s + 1
         load_inputs(s + 2);          // zNext holds the zone info of step s + 2
         load_zinfo(s + 3);
       }
+      umt_cp_async_wait_all();
     }
     __syncthreads();
   }
@@ -1248,7 +1249,10 @@ int umt_build_items_rz(umt_ctx *ctx, std::vector<WorkItem> &items, int zpi) {
   if (const char *e = getenv("UMT_RZ_KERNEL")) ctx->rz_flow = plain && (std::string(e) == "flow" || std::string(e) == "recflow");
   // record kernel: quads, every item's pairs fit one CTA
   ctx->rz_rec = ctx->maxCorner <= 4 && ctx->G <= RZ_BLOCK && ctx->zones_per_item * ctx->G <= RZ_BLOCK;
-  if (const char *e = getenv("UMT_RZ_KERNEL")) if (std::string(e) != "rec" && std::string(e) != "recflow") ctx->rz_rec = false;
+  if (const char *e = getenv("UMT_RZ_KERNEL")) {   // rec, recflow, pipe and lc all run from the records
+    const std::string k(e);
+    if (k != "rec" && k != "recflow" && k != "pipe" && k != "lc") ctx->rz_rec = false;
+  }
   ctx->rz_recs_valid = false;
   if ((r = up(&ctx->d_rzPrev, prevA))) return r;
   if ((r = up(&ctx->d_rzLevelAngles, la))) return r;
@@ -1489,7 +1493,10 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
         int begin = 0, end = ctx->nItems;
         if (ctx->nStages > 1) {
           begin = ctx->stageItemBegin[st]; end = ctx->stageItemBegin[st + 1];
-          int r = umt_launch_reflect(ctx, st);
+          int r = UMT_OK;
+          if (ctx->have_comm_order && !ctx->shared.empty()) r = umt_exchange_stage(ctx, st);   // SendFlux / RecvFlux of this sweep step
+          if (r) return r;
+          r = umt_launch_reflect(ctx, st);
           if (r) return r;
           if (end == begin) continue;
           if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
@@ -1521,7 +1528,10 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
       int begin = 0, end = ctx->nItems;
       if (ctx->nStages > 1) {
         begin = ctx->stageItemBegin[st]; end = ctx->stageItemBegin[st + 1];
-        int r = umt_launch_reflect(ctx, st);
+        int r = UMT_OK;
+        if (ctx->have_comm_order && !ctx->shared.empty()) r = umt_exchange_stage(ctx, st);   // SendFlux / RecvFlux of this sweep step
+        if (r) return r;
+        r = umt_launch_reflect(ctx, st);
         if (r) return r;
         if (end == begin) continue;
         if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
@@ -1548,7 +1558,10 @@ int umt_launch_sweeprz(umt_ctx *ctx, int /*savePsi*/) {
   }
   for (int st = 0; st < ctx->nStages; st++) {   // reflecting boundaries: snreflect, then the angles of this stage
     const int begin = ctx->stageItemBegin[st], end = ctx->stageItemBegin[st + 1];
-    int r = umt_launch_reflect(ctx, st);
+    int r = UMT_OK;
+    if (ctx->have_comm_order && !ctx->shared.empty()) r = umt_exchange_stage(ctx, st);   // SendFlux / RecvFlux of this sweep step
+    if (r) return r;
+    r = umt_launch_reflect(ctx, st);
     if (r) return r;
     if (end == begin) continue;
     if (st > 0) UMT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));   // the ticket; plane counters persist

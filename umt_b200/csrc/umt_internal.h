@@ -230,6 +230,9 @@ struct umt_ctx {
   std::vector<int> angleOrder;                   // (NA) per comm set concatenated: 0-based angle swept at each step
   std::vector<std::vector<int>> recvOrder;       // [shared][NA] the neighbour's AngleOrder (0-based), same layout
   std::vector<int> commStageOf;                  // (NA) step at which angle a is swept
+  std::vector<int> binOrder;                     // (nSchedBins) per comm set concatenated: bin swept at each step (3-D: bin = angle, r-z: xi-level)
+  std::vector<std::vector<int>> binRecvOrder;    // [shared][nSchedBins] the neighbour's bin order
+  int nSchedBins = 0, binsPerSet = 1;
   std::vector<double> netFlux;                   // (nShared, NA) CSet%NetFlux of the last scheduler run
   int4 *d_reflOps = nullptr;           // (minc, mref, first, n) grouped by stage
   std::vector<int> reflOpBegin;        // per-stage offsets into d_reflOps
