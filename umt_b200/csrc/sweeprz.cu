@@ -940,7 +940,7 @@ struct RZLParams {
   int maxSteps, gb, nGB, ZCH, CT;                    // groups per CTA, group blocks, zones per step at most, threads per group
 };
 
-constexpr int RZL_MAX_CT = 320;                      // threads per group at most (640 per CTA: 102 registers each)
+constexpr int RZL_MAX_CT = 288;                      // threads per group at most (576 per CTA: 113 registers each)
 __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZParams P, RZLParams L) {
   extern __shared__ __align__(16) unsigned char lsm[];
   const int G = P.G, nc = P.nc, CT = L.CT, PCH = L.ZCH * L.gb;
@@ -968,22 +968,24 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
     umt_cp_async_commit();
   };
   // inputs of my pair of a step, loaded one step ahead (static group): Psi^n and STotal of the 4 corners (local order), Sigt
-  double inPsi[4], inSt[4], inSig = 1.0;
+  // (two register sets: the loads for step s + 2 are issued before the static half of step s + 1 consumes the other set, so they have
+  // a whole iteration to land)
+  double aPsi[4], aSt[4], aSig = 1.0, bPsi[4], bSt[4], bSig = 1.0;
   int2 zNext = make_int2(0, 0);                        // zone info of my pair two steps ahead
   auto load_zinfo = [&](int s) {
     if (s < nS) { const RZStep st = steps[s]; if (zi < st.n) zNext = L.zinfo[(size_t)st.angle * P.nz + st.zbeg + zi]; }
   };
-  auto load_inputs = [&](int s) {                      // uses zNext (= zone info of step s)
+  auto load_inputs = [&](int s, double (&dPsi)[4], double (&dSt)[4], double &dSig) {   // uses zNext (= zone info of step s)
     if (s >= nS) return;
     const RZStep st = steps[s];
     if (zi >= st.n) return;
     const double *psiA = P.psi + (size_t)st.angle * slab + (size_t)zNext.x * G + g;
     const double *stA = P.stotal + (size_t)zNext.x * G + g;
 #pragma unroll
-    for (int c = 0; c < 4; c++) { inPsi[c] = __ldcs(psiA + (size_t)c * G); inSt[c] = __ldcs(stA + (size_t)c * G); }
-    inSig = __ldg(P.sigt + (size_t)zNext.y * G + g);
+    for (int c = 0; c < 4; c++) { dPsi[c] = __ldcs(psiA + (size_t)c * G); dSt[c] = __ldcs(stA + (size_t)c * G); }
+    dSig = __ldg(P.sigt + (size_t)zNext.y * G + g);
   };
-  auto static_half = [&](int s) {                      // coefficients of my pair of step s -> statBuf[s % 2]
+  auto static_half = [&](int s, const double (&inPsi)[4], const double (&inSt)[4], const double inSig) {   // coefficients of my pair of step s -> statBuf[s % 2]
     const RZStep st = steps[s];
     if (zi >= st.n) return;
     const RZRecS &R = *reinterpret_cast<const RZRecS *>(recBuf + ((size_t)(s % 3) * L.ZCH + zi) * RZL_REC_STRIDE);
@@ -1088,30 +1090,38 @@ __global__ void __launch_bounds__(2 * RZL_MAX_CT, 1) sweeprz_lc_kernel(SweepRZPa
     }
   };
 
-  // prologue: the static group brings steps 0 and 1 into flight, then step 0 is fully prepared before the chain group starts
+  // prologue: the static group brings the records of steps 0 and 1 and the inputs of step 0 in, prepares step 0, and leaves the
+  // inputs of step 1 and the zone info of step 2 in flight
   const bool mine = zi < L.ZCH;
   if (!chain) {
     copy_records(0); copy_records(1);
-    if (mine) { load_zinfo(0); load_inputs(0); }
+    if (mine) { load_zinfo(0); load_inputs(0, aPsi, aSt, aSig); load_zinfo(1); }
     umt_cp_async_wait_all();
   }
   __syncthreads();
-  if (!chain && mine) { static_half(0); load_zinfo(1); load_inputs(1); load_zinfo(2); }
+  if (!chain && mine) { static_half(0, aPsi, aSt, aSig); load_inputs(1, aPsi, aSt, aSig); load_zinfo(2); }
   __syncthreads();
-  for (int s = 0; s < nS; s++) {
-    if (chain) {
-      if (mine) chain_half(s);
-    } else {
-      copy_records(s + 2);           // asynchronous: read for the first time one iteration from now
-      if (mine && s + 1 < nS) {
-        static_half(s + 1);          // consumes the inputs loaded for step s + 1
-        load_inputs(s + 2);          // zNext holds the zone info of step s + 2
-        load_zinfo(s + 3);
-      }
-      umt_cp_async_wait_all();
-    }
-    __syncthreads();
+  // one iteration: the chain group does step s; the static group completes the records of step s + 1 (issued an iteration ago),
+  // issues the records and the inputs of step s + 2 (into the set that is free) and prepares step s + 1 from the other set
+#define RZL_ITER(S, CUR_PSI, CUR_ST, CUR_SIG, NXT_PSI, NXT_ST, NXT_SIG)                              \
+  if (chain) {                                                                                       \
+    if (mine) chain_half(S);                                                                         \
+  } else {                                                                                           \
+    umt_cp_async_wait_all();                                                                         \
+    asm volatile("bar.sync 1, %0;" ::"r"(CT) : "memory");                                            \
+    copy_records((S) + 2);                                                                           \
+    if (mine) {                                                                                      \
+      load_inputs((S) + 2, NXT_PSI, NXT_ST, NXT_SIG);                                                \
+      load_zinfo((S) + 3);                                                                           \
+      if ((S) + 1 < nS) static_half((S) + 1, CUR_PSI, CUR_ST, CUR_SIG);                              \
+    }                                                                                                \
+  }                                                                                                  \
+  __syncthreads();
+  for (int s = 0; s < nS; s += 2) {
+    RZL_ITER(s, aPsi, aSt, aSig, bPsi, bSt, bSig)
+    if (s + 1 < nS) { RZL_ITER(s + 1, bPsi, bSt, bSig, aPsi, aSt, aSig) }
   }
+#undef RZL_ITER
 }
 
 // Dataflow kernel.  The same work items in the same topological order, but nothing waits for a whole plane: every warp takes
