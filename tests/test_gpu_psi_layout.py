@@ -140,3 +140,18 @@ def test_multi_domain_exchange_on_the_ring_layout():
                     assert T.mixed_err(ctx.download_psi(), p.Psi, TOL) <= 1.0
         for c in ctxs:
             c.close()
+
+
+def test_configs2_quadrature_P4_A4_on_the_ring_matches_oracle():
+    """BASELINE configs[2]'s quadrature (-P 4 -A 4: 128 angles) at a size the oracle finishes in seconds, psi stored once and Psi1 in
+    a ring of 3 of its 32 angle batches (what the -d 16 -G 128 bench run of that config does with 13 of 32)."""
+    mesh = M.tiled_mesh((3, 3, 3))
+    with _env(UMT_ANGLE_BATCH=4, UMT_PHI_CHUNK=256):
+        p = T.make_problem_3d(mesh, 4, 4, 8)
+        assert p.NA == 128
+        ctx = T.gpu_context_3d(p, own_schedule=True, own_geometry=True, own_quadrature=(4, 4, 1))
+        ctx.set_psi1_ring(3)
+        lay = ctx.psi_layout()
+        assert lay["single"] and lay["psi1_slabs"] == 12 and lay["angles_tallied_in_sweep"] == 116
+        _sweeps(p, ctx)
+        ctx.close()

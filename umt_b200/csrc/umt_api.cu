@@ -111,7 +111,10 @@ extern "C" int umt_ctx_destroy(umt_ctx *ctx) {
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->d_abort) cudaFree(ctx->d_abort);
   if (ctx->h_abort) cudaFreeHost(ctx->h_abort);
-  for (auto &b : ctx->host_blocks) { cudaHostUnregister(b.first); munmap(b.first, b.second); }   // umt_host_alloc blocks never freed
+  for (auto &b : ctx->host_blocks) {   // umt_host_alloc blocks never freed
+    if (b.second == 0) cudaFreeHost(b.first);
+    else { cudaHostUnregister(b.first); munmap(b.first, b.second); }
+  }
   ctx->host_blocks.clear();
   umt_exchange_release(ctx);
   umt_gta_release(ctx);
@@ -172,8 +175,15 @@ extern "C" int umt_host_alloc(umt_ctx *ctx, size_t bytes, void **ptr, int *numaN
   for (size_t o = 0; o < len; o += page) static_cast<volatile char *>(p)[o] = 0;   // first touch: the pages exist where the policy says
   cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
   if (e != cudaSuccess) {
+    // registering foreign pages is refused in some environments (under a profiler, in some containers): plain page-locked memory then
+    cudaGetLastError();
     munmap(p, len);
-    UMT_FAIL(ctx, UMT_ERR_CUDA, "umt_host_alloc: cudaHostRegister of %zu bytes: %s", len, cudaGetErrorString(e));
+    e = cudaHostAlloc(&p, len, cudaHostAllocPortable);
+    if (e != cudaSuccess) UMT_FAIL(ctx, UMT_ERR_CUDA, "umt_host_alloc: %zu page-locked bytes: %s", len, cudaGetErrorString(e));
+    ctx->host_blocks[p] = 0;   // length 0: a cudaHostAlloc block
+    if (numaNode) *numaNode = -1;
+    *ptr = p;
+    return UMT_OK;
   }
   ctx->host_blocks[p] = len;
   if (numaNode) *numaNode = bound ? node : -1;
@@ -188,6 +198,7 @@ extern "C" int umt_host_free(umt_ctx *ctx, void *ptr) {
   if (it == ctx->host_blocks.end()) UMT_FAIL(ctx, UMT_ERR_ARG, "umt_host_free: not a block of this context's umt_host_alloc");
   const size_t len = it->second;
   ctx->host_blocks.erase(it);
+  if (len == 0) { cudaFreeHost(ptr); return UMT_OK; }
   cudaHostUnregister(ptr);
   munmap(ptr, len);
   return UMT_OK;
