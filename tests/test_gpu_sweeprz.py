@@ -66,3 +66,16 @@ def test_uniform_solution_preserved():
     assert np.abs(ctx.download_psi() / psi0 - 1).max() <= 1e-12
     assert np.abs(ctx.download_phi() / (2 * np.pi * psi0) - 1).max() <= 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("kernel", ["pipe", "lc", "recflow", "item"])
+def test_optional_rz_kernels_match_oracle(kernel):
+    """The r-z kernel variants kept as options (the TMA pipeline, the level-chain kernel, the dataflow
+    variant on the records, the plain item kernel) stay parity-checked."""
+    import os
+    os.environ["UMT_RZ_KERNEL"] = kernel
+    try:
+        _run_case(M.tiled_mesh((3, 3, 0)), 2, 2, 16)
+        _run_case(M.tiled_mesh((4, 2, 0)), 2, 2, 64, driver_like=True, sweeps=(False, True))
+    finally:
+        del os.environ["UMT_RZ_KERNEL"]
