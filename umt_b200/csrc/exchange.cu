@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) pack_tally_kernel(const double *__restric
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const int r = ch.rowBeg + (int)(i / G), g = (int)(i % G);
     const double v = __ldcg(&psi1[srcRow[r] * G + g]);
-    sendbuf[(size_t)r * G + g] = v;
+    sendbuf[(size_t)r * G + g] = v;   // the local send buffer, or the neighbour's receive buffer (put path: peer memory)
     acc += coef[r] * v;
   }
   __shared__ double red[256];
@@ -306,6 +306,9 @@ int need_abdy(umt_ctx *ctx) {
 
 void umt_exchange_release(umt_ctx *ctx) {
   for (auto &s : ctx->shared) {
+    if (s.peer_is_ipc) for (double *q : s.peer_recv) if (q) cudaIpcCloseMemHandle(q);
+    s.peer_recv[0] = s.peer_recv[1] = nullptr; s.peer_is_ipc = false;
+    if (s.d_recvbuf2) { cudaFree(s.d_recvbuf2); s.d_recvbuf2 = nullptr; }
     void *p[] = {s.d_send_row, s.d_recv_row, s.d_send_coef, s.d_chunks, s.d_partial, s.d_nChunksOfAngle, s.d_sendbuf, s.d_recvbuf,
                  s.d_gsend, s.d_grecv, s.d_gsendbuf, s.d_grecvbuf, s.d_stage_send, s.d_stage_recv};
     for (void *q : p) if (q) cudaFree(q);
@@ -313,6 +316,7 @@ void umt_exchange_release(umt_ctx *ctx) {
     s.d_send_row = s.d_recv_row = nullptr; s.d_send_coef = nullptr; s.d_chunks = nullptr; s.d_partial = nullptr;
     s.d_nChunksOfAngle = nullptr; s.d_sendbuf = s.d_recvbuf = nullptr;
   }
+  ctx->put_ready = false;
   void *p[] = {ctx->d_exitFlux, ctx->d_incRecv, ctx->d_incFlux, ctx->d_incFluxOld, ctx->d_binOfAngle, ctx->d_nNotConv};
   for (void *q : p) if (q) cudaFree(q);
   ctx->d_exitFlux = ctx->d_incRecv = ctx->d_incFlux = ctx->d_incFluxOld = nullptr; ctx->d_binOfAngle = nullptr; ctx->d_nNotConv = nullptr;
@@ -504,6 +508,82 @@ extern "C" int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, 
   return UMT_OK;
 }
 
+// Put path: peer pointers to the neighbours' receive buffers (CUDA IPC between ranks, plain pointers between the domains of one
+// process).  pack_tally_kernel then stores the exiting rows straight into the neighbour's buffer -- pack and transfer in one kernel, NVLink
+// stores when the neighbour sits on another GPU -- instead of packing a local send buffer that ncclSend/ncclRecv copy across; the
+// neighbour's rows and mine are in the same order (findexit.F90 matches the shared elements one by one).  Collective (the handles
+// travel through the communicator).  Any failure on any rank leaves put_ready false everywhere and the NCCL path in force;
+// UMT_EXCHANGE_PUT=0 switches it off.  (Storing the rows from inside the sweep kernel was measured and dropped: the extra code in the
+// zone solve cost 10 % of the sweep, 36.7 -> 40.4 ms at -d 20 -G 128, to save a 0.2 ms pack kernel.)
+static int setup_put(umt_ctx *ctx) {
+  ctx->put_ready = false;
+  const size_t nS = ctx->shared.size();
+  bool want = nS > 0 && ctx->transport != nullptr;
+  if (const char *e = getenv("UMT_EXCHANGE_PUT")) want = want && atoi(e) != 0;
+  // every rank must take the same decision: the handle exchange below is collective, and `want` only depends on things all ranks share
+  if (!want) return UMT_OK;
+  bool ok = true;
+  if (auto *lt = dynamic_cast<LocalTransport *>(ctx->transport)) {
+    lt->grp->barrier();   // every member has allocated its buffers
+    for (size_t k = 0; k < nS; k++) {
+      umt_ctx *peer = lt->grp->members[ctx->shared[k].neighbor];
+      int t = -1;
+      for (size_t j = 0; j < peer->shared.size(); j++) if (peer->shared[j].neighbor == ctx->myRank) t = (int)j;
+      if (t < 0 || peer->device != ctx->device) { ok = false; continue; }   // (in-process domains on different GPUs keep the copy path)
+      ctx->shared[k].peer_recv[0] = peer->shared[t].d_recvbuf; ctx->shared[k].peer_recv[1] = peer->shared[t].d_recvbuf2;
+      ctx->shared[k].peer_is_ipc = false;
+    }
+    lt->grp->barrier();
+  } else {
+    // CUDA IPC handles of my two receive buffers go to the neighbour that will write them
+    std::vector<cudaIpcMemHandle_t> mine(2 * nS), theirs(2 * nS);
+    unsigned char *dS = nullptr, *dR = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    if (cudaMalloc((void **)&dS, 2 * nS * hb) != cudaSuccess || cudaMalloc((void **)&dR, 2 * nS * hb) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    for (size_t k = 0; k < nS && ok; k++) {
+      if (cudaIpcGetMemHandle(&mine[2 * k], ctx->shared[k].d_recvbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine[2 * k + 1], ctx->shared[k].d_recvbuf2) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    }
+    if (!ok) std::memset(mine.data(), 0, mine.size() * hb);   // still take part in the collective below
+    if (dS && dR) {
+      umt_memcpy(ctx, dS, mine.data(), 2 * nS * hb, cudaMemcpyHostToDevice);
+      std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS, 2 * hb), rb(nS, 2 * hb);
+      for (size_t k = 0; k < nS; k++) { sp[k] = dS + 2 * k * hb; rp[k] = dR + 2 * k * hb; }
+      if (ctx->transport->exchange(ctx, sp, sb, rp, rb) != UMT_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
+      else umt_memcpy(ctx, theirs.data(), dR, 2 * nS * hb, cudaMemcpyDeviceToHost);
+    }
+    if (dS) cudaFree(dS);
+    if (dR) cudaFree(dR);
+    const cudaIpcMemHandle_t zero{};
+    for (size_t k = 0; k < nS && ok; k++)
+      for (int j = 0; j < 2; j++) {
+        void *q = nullptr;
+        if (!std::memcmp(&theirs[2 * k + j], &zero, hb) || cudaIpcOpenMemHandle(&q, theirs[2 * k + j], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        ctx->shared[k].peer_recv[j] = static_cast<double *>(q);
+        ctx->shared[k].peer_is_ipc = true;
+      }
+    // all ranks use the put path or none does (a rank that failed would otherwise wait for rows nobody sends)
+    int *d_ok = nullptr;
+    int h_ok = ok ? 0 : 1;
+    if (cudaMalloc((void **)&d_ok, sizeof(int)) == cudaSuccess) {
+      umt_memcpy(ctx, d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice);
+      if (ctx->transport->allreduce_max(ctx, d_ok) == UMT_OK) umt_memcpy(ctx, &h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+      else h_ok = 1;
+      cudaFree(d_ok);
+    } else h_ok = 1;
+    ok = h_ok == 0;
+  }
+  if (auto *lt = dynamic_cast<LocalTransport *>(ctx->transport)) {   // same all-or-none rule inside a process
+    { std::lock_guard<std::mutex> lk(lt->grp->m); if (!ok) lt->grp->redux = 1; }
+    lt->grp->barrier();
+    { std::lock_guard<std::mutex> lk(lt->grp->m); ok = lt->grp->redux == 0; }
+    lt->grp->barrier();
+    if (ctx->myRank == 0) { std::lock_guard<std::mutex> lk(lt->grp->m); lt->grp->redux = 0; }
+    lt->grp->barrier();
+  }
+  ctx->put_ready = ok;
+  return UMT_OK;
+}
+
 extern "C" int umt_build_exchange(umt_ctx *ctx) {
   if (!ctx) return UMT_ERR_ARG;
   if (!ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_build_exchange: quadrature not set");
@@ -555,6 +635,10 @@ extern "C" int umt_build_exchange(umt_ctx *ctx) {
     UMT_CUDA(ctx, cudaMemsetAsync(s.d_partial, 0, sizeof(double) * (size_t)NA * maxChunks, ctx->stream));
     UMT_CUDA(ctx, cudaMalloc((void **)&s.d_sendbuf, sizeof(double) * std::max<size_t>(s.send_rows * G, 1)));
     UMT_CUDA(ctx, cudaMalloc((void **)&s.d_recvbuf, sizeof(double) * std::max<size_t>(s.recv_rows * G, 1)));
+    if (s.peer_is_ipc) for (double *q : s.peer_recv) if (q) cudaIpcCloseMemHandle(q);
+    s.peer_recv[0] = s.peer_recv[1] = nullptr; s.peer_is_ipc = false;
+    if (s.d_recvbuf2) { cudaFree(s.d_recvbuf2); s.d_recvbuf2 = nullptr; }
+    UMT_CUDA(ctx, cudaMalloc((void **)&s.d_recvbuf2, sizeof(double) * std::max<size_t>(s.recv_rows * G, 1)));
   }
   const size_t nS = ctx->shared.size();
   // flux-convergence bins: one per comm set (3-D: angle, 2-D: xi-level)
@@ -571,7 +655,9 @@ extern "C" int umt_build_exchange(umt_ctx *ctx) {
   }
   if (!ctx->d_nNotConv) UMT_CUDA(ctx, cudaMalloc((void **)&ctx->d_nNotConv, sizeof(int)));
   ctx->exch_dirty = false;
-  return UMT_OK;
+  ctx->pack_valid = ctx->recv_valid = false;
+  ctx->passCount = 0;
+  return setup_put(ctx);
 }
 
 // ---------------------------------------------------------------------------
@@ -594,7 +680,9 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   for (size_t k = 0; k < nS; k++) {
     SharedBdy &s = ctx->shared[k];
     if (s.nChunks > 0) {
-      pack_tally_kernel<<<s.nChunks, 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_send_row, s.d_send_coef, s.d_chunks, s.d_sendbuf, s.d_partial, G);
+      // put path: the rows the neighbour's NEXT pass to be swept starts from go straight into the buffer it will unpack then
+      double *dst = ctx->put_now ? s.peer_recv[(ctx->passCount + 1) & 1] : s.d_sendbuf;
+      pack_tally_kernel<<<s.nChunks, 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_send_row, s.d_send_coef, s.d_chunks, dst, s.d_partial, G);
       ctx->last_launches++;
     }
     tally_finish_kernel<<<(NA + 127) / 128, 128, 0, xstream(ctx)>>>(s.d_partial, s.d_nChunksOfAngle, s.maxChunks, ctx->d_exitFlux + k * NA, NA);
@@ -612,6 +700,10 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
   return UMT_OK;
 }
 
+// The receive buffer that holds (or will hold) the rows the NEXT pass to be swept starts from: pass n (= passCount) reads buffer
+// (n + 1) & 1, and while it is swept the neighbours' put stores fill buffer n & 1 for pass n + 1.
+double *umt_recv_buffer(const umt_ctx *ctx, const SharedBdy &s) { return ((ctx->passCount + 1) & 1) ? s.d_recvbuf2 : s.d_recvbuf; }
+
 // SendFlux / RecvFlux for every angle, first half: the rows every domain packed after its last sweep travel to the neighbours'
 // receive buffers (collective).  umt_sweep issues this right after the post-sweep tally, on the second stream, so that the
 // transfer of the NEXT pass's incident rows overlaps the phi tally of this one (the exchange is lagged one pass anyway).
@@ -623,7 +715,7 @@ int umt_exchange_rows(umt_ctx *ctx) {
   std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS), rb(nS);
   for (size_t k = 0; k < nS; k++) {
     SharedBdy &s = ctx->shared[k];
-    sp[k] = s.d_sendbuf; rp[k] = s.d_recvbuf;
+    sp[k] = s.d_sendbuf; rp[k] = umt_recv_buffer(ctx, s);
     sb[k] = sizeof(double) * s.send_rows * G; rb[k] = sizeof(double) * s.recv_rows * G;
   }
   return ctx->transport->exchange(ctx, sp, sb, rp, rb);
@@ -637,7 +729,7 @@ int umt_exchange_unpack(umt_ctx *ctx) {
     SharedBdy &s = ctx->shared[k];
     const long long n = (long long)s.recv_rows * G;
     if (n > 0) {
-      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_recv_row, s.d_recvbuf, n, G);
+      unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, xstream(ctx)>>>(ctx->psib_buf(), s.d_recv_row, umt_recv_buffer(ctx, s), n, G);
       ctx->last_launches++;
     }
   }

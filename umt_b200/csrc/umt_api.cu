@@ -1099,9 +1099,18 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
 
   const bool staged = multi && ctx->have_comm_order;   // comm sets of several bins exchange step by step inside umt_launch_sweep3d
   bool overlapped = false;
+  // put path: the tally kernel stores the exiting rows straight into the neighbours' receive buffers (peer memory) and its trade of the
+  // exit currents tells every domain that its neighbours' rows have arrived: no send buffer, no ncclSend/ncclRecv of the rows
+  const bool put = multi && !staged && ctx->put_ready;
   // restoreCommOrder + setIncidentFlux (SetSweep.F90:68-74): packs the exiting rows and tallies the exit currents -- unless the
   // tally that followed the previous sweep still describes the PsiB on the device
-  if (multi && !ctx->pack_valid) { TRY(umt_exchange_tally(ctx, fluxTol)); ctx->pack_valid = true; ctx->recv_valid = false; }
+  if (multi && !ctx->pack_valid) {
+    ctx->put_now = put;
+    const int rt = umt_exchange_tally(ctx, fluxTol);
+    ctx->put_now = false;
+    if (rt) return rt;
+    ctx->pack_valid = true; ctx->recv_valid = put;
+  }
   for (;;) {
     iter++;
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1119,6 +1128,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
     }
     if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx, savePsi));
     else TRY(umt_launch_sweeprz(ctx, savePsi));
+    ctx->passCount++;   // from here on "the next pass" reads the other receive buffer
     if (ctx->totalCycles > 0) {                     // updateCycleList
       const size_t n = (size_t)ctx->totalCycles * ctx->G;
       cycle_copy_kernel<<<(int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList,
@@ -1134,16 +1144,25 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
       UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev[3], 0));
       UMT_CUDA(ctx, cudaEventRecord(ctx->evx[0], ctx->stream3));
       ctx->xstream = ctx->stream3;
-      int r = umt_exchange_tally(ctx, fluxTol);
-      if (!r && !staged) { r = umt_exchange_rows(ctx); ctx->recv_valid = !r; }
+      ctx->put_now = put;
+      int r = umt_exchange_tally(ctx, fluxTol);   // its trade of the exit currents is also what tells me the neighbours' puts are complete
+      ctx->put_now = false;
+      if (!r && !staged) {
+        if (!put) r = umt_exchange_rows(ctx);
+        ctx->recv_valid = !r;
+      }
       ctx->xstream = nullptr;
       if (r) return r;
       ctx->pack_valid = true;
       UMT_CUDA(ctx, cudaEventRecord(ctx->evx[1], ctx->stream3));
       overlapped = true;
     } else if (multi) {                               // setIncidentFlux + testFluxConv + Allreduce(max nNotConv)
-      TRY(umt_exchange_tally(ctx, fluxTol));
+      ctx->put_now = put;
+      const int rt = umt_exchange_tally(ctx, fluxTol);
+      ctx->put_now = false;
+      if (rt) return rt;
       ctx->pack_valid = true;
+      if (put) ctx->recv_valid = true;
       TRY(umt_exchange_test_convergence(ctx, &nNotConv));
     }
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -1154,7 +1173,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
     cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]); ms_sweep += t;
     cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]); ms_exch += t;
     if (nNotConv == 0) {   // converged early: the next pass's rows can travel under the phi tally as well
-      if (multi && !staged) {
+      if (multi && !staged && !put) {
         UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev[4], 0));
         UMT_CUDA(ctx, cudaEventRecord(ctx->evx[0], ctx->stream3));
         ctx->xstream = ctx->stream3;

@@ -60,6 +60,13 @@ struct SharedBdy {      // one neighbour (rt/findexit.F90:102-294)
   int nChunks = 0, maxChunks = 1;
   std::vector<int> send_off, recv_off;                     // per-angle offsets (NA+1)
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  // put path (exchange.cu): pack_tally_kernel stores the exiting rows straight into the neighbour's receive buffer over peer memory
+  // (NVLink stores when the neighbour is another GPU) instead of packing a send buffer for ncclSend/ncclRecv.  Two receive buffers
+  // alternate by pass (d_recvbuf = [0], d_recvbuf2 = [1]): a neighbour may already be writing the rows of its next pass while this
+  // domain still unpacks the previous ones.  peer_recv: the NEIGHBOUR's two buffers as seen from this process.
+  double *d_recvbuf2 = nullptr;
+  double *peer_recv[2] = {nullptr, nullptr};
+  bool peer_is_ipc = false;
   size_t send_rows = 0, recv_rows = 0;
   // staged exchange (comm sets with several bins): rows to send / receive at each step, grouped by step
   long long *d_stage_send = nullptr, *d_stage_recv = nullptr;
@@ -135,6 +142,9 @@ struct umt_ctx {
   // lagged exchange state: the send buffers hold the exiting rows of the current PsiB / the receive buffers already hold what
   // the neighbours packed after their last sweep (the transfer was overlapped with the phi tally of that sweep)
   bool pack_valid = false, recv_valid = false;
+  bool put_ready = false;              // peer pointers to every neighbour's receive buffers are open
+  bool put_now = false;                // umt_exchange_tally packs into the neighbours' buffers (set by the controller)
+  long long passCount = 0;             // passes swept since the exchange was built (parity of the receive buffers)
 
   // host copies (for schedule builder, exit lists, tallies)
   std::vector<int> h_numCorner, h_cOffSet, h_nCFaces, h_cFP, h_cEZ, h_zoneFaces, h_zoneOpp, h_faceOpp, h_CToFace, h_BdyToC;
@@ -319,6 +329,7 @@ int umt_host_build_order(umt_ctx *ctx, const double *omegas, int nAng, std::vect
                          std::vector<std::vector<int>> &nextZ, std::vector<std::vector<int>> &nextC);
 int umt_exchange_tally(umt_ctx *ctx, double tol);
 int umt_exchange_rows(umt_ctx *ctx);      // collective: packed exiting rows -> the neighbours' receive buffers
+double *umt_recv_buffer(const umt_ctx *ctx, const SharedBdy &s);
 int umt_exchange_unpack(umt_ctx *ctx);    // receive buffers -> incident PsiB rows
 int umt_exchange_test_convergence(umt_ctx *ctx, int *nNotConv);
 int umt_exchange_stage(umt_ctx *ctx, int step);               // SendFlux / RecvFlux of one sweep step (staged comm sets)
