@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _setup(mesh, G=4, seed=7, scat=20.0):
+def _setup(mesh, G=4, seed=7, scat=20.0, own_geometry=False):
     om = O.OMesh(mesh)
     g = O.geometry(om)
     omega, w = O.gta_quad_xyz()
@@ -30,7 +30,10 @@ def _setup(mesh, G=4, seed=7, scat=20.0):
     Chi /= Chi.sum(1, keepdims=True)
     Phi = rng.random((nc, G))
     ctx = SweepContext.from_mesh(mesh, G)
-    ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], A_bdy=g["A_bdy"])
+    if own_geometry:   # umt_compute_geometry (built without FMA contraction) must put every omega.A = 0 tie where the oracle's does
+        ctx.compute_geometry(mesh.px)
+    else:
+        ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], A_bdy=g["A_bdy"])
     ctx.build_product_quadrature(1, 1, 1)
     ctx.upload_state(np.tile(Phi / (4 * np.pi), (8, 1, 1)), None, np.full((nz, G), tau), np.zeros((nc, G)), tau)
     ctx.init_phi_total()          # PhiTotal on the device = sum_a w_a Psi = Phi
@@ -91,9 +94,10 @@ def test_gta_pieces_match_oracle(name, mk):
     ctx.close()
 
 
+@pytest.mark.parametrize("own_geometry", [False, True])
 @pytest.mark.parametrize("name,mk", MESHES[:2])
-def test_gta_solver_matches_oracle(name, mk):
-    s = _setup(mk())
+def test_gta_solver_matches_oracle(name, mk, own_geometry):
+    s = _setup(mk(), own_geometry=own_geometry)
     ctx, om, g = s["ctx"], s["om"], s["g"]
     nc = s["mesh"].ncornr
     chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()

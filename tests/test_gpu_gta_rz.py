@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _setup(mesh, G=4, seed=7, scat=20.0):
+def _setup(mesh, G=4, seed=7, scat=20.0, own_geometry=False):
     om = O.OMesh(mesh)
     g = O.geometry(om)
     q = O.gta_quad_rz()
@@ -29,7 +29,10 @@ def _setup(mesh, G=4, seed=7, scat=20.0):
     # a Sn context in r-z whose PhiTotal is Phi: 1 x 1 product set, Psi = Phi / 2 pi on every weighted ordinate
     qs = O.quad_rz(1, 1)
     ctx = SweepContext.from_mesh(mesh, G)
-    ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], g["Area"], g["RadiusFP"], g["RadiusEZ"], g["A_bdy"])
+    if own_geometry:
+        ctx.compute_geometry(mesh.px)
+    else:
+        ctx.set_geometry(g["Volume"], g["A_fp"], g["A_ez"], g["Area"], g["RadiusFP"], g["RadiusEZ"], g["A_bdy"])
     ctx.build_product_quadrature(1, 1, 1)
     ctx.upload_state(np.tile(s["Phi"] / (2 * np.pi), (len(qs["weight"]), 1, 1)), None, np.full((nz, G), tau), np.zeros((nc, G)), tau)
     ctx.init_phi_total()
@@ -91,9 +94,10 @@ def test_gta_rz_pieces_match_oracle(name, mk):
     ctx.close()
 
 
+@pytest.mark.parametrize("own_geometry", [False, True])
 @pytest.mark.parametrize("name,mk", MESHES)
-def test_gta_rz_solver_matches_oracle(name, mk):
-    s = _setup(mk())
+def test_gta_rz_solver_matches_oracle(name, mk, own_geometry):
+    s = _setup(mk(), own_geometry=own_geometry)
     ctx, om, g, q = s["ctx"], s["om"], s["g"], s["q"]
     nc = s["mesh"].ncornr
     chi_ref, chi_dev = s["Chi"].copy(), s["Chi"].copy()

@@ -79,6 +79,10 @@ def test_device_geometry_matches_oracle():
         for k in ("Volume", "A_fp", "A_ez", "A_bdy", "VolumeZone"):
             scale = np.abs(ref[k]).max()
             assert np.abs(g[k] - ref[k]).max() <= 1e-13 * scale, k
+        # geometry.cu is compiled without FMA contraction and evaluates the reference's expressions in the reference's order: the
+        # area vectors (whose sign against omega decides upstream/downstream, ties included) agree to the last bit
+        for k in ("A_fp", "A_ez", "A_bdy"):
+            assert np.array_equal(g[k], ref[k]), k
         ctx.close()
 
 

@@ -5,8 +5,9 @@
 !  Rad%PhiTotal filled, so ControlSweep must NOT call getPhiTotal       *
 !  after it (see INTEGRATION.md for the two-line change).               *
 !                                                                       *
-!  Per cycle (first call after initializeSets): connectivity, geometry, *
-!  quadrature, sweep schedules and Psi/PsiB go to the device once.      *
+!  Once per mesh (b200_mesh_uploaded; cleared by the host when it moves *
+!  the mesh): geometry, quadrature and sweep schedules go to the device.*
+!  Per cycle (first call after initializeSets): Psi/PsiB go up once.    *
 !  Per call: Sigt, STotal, tau up; PhiTotal down; on savePsi also       *
 !  Psi/PsiB down, because finalizeSets/rtedit read them on the host.    *
 !                                                                       *
@@ -68,13 +69,19 @@ subroutine SetSweep_B200(savePsi)
       ! rc = umt_set_comm(b200_ctx, Size%myRankInGroup, Size%nprocs, id128)
    endif
 
-!  Once per cycle: geometry, quadrature, schedules (initializeSets rebuilt them) and the angular flux
-   if (.not. b200_static_uploaded) then
+!  Once per mesh: geometry, quadrature, schedules.  initializeSets rebuilds the host copies every cycle
+!  (initializeSets.F90:85-105), identically while the mesh does not move; the context keeps what it built from them
+   if (.not. b200_mesh_uploaded) then
       rc = umt_set_geometry(b200_ctx, Geom%Volume, Geom%A_fp, Geom%A_ez, C_NULL_PTR, C_NULL_PTR, C_NULL_PTR, C_NULL_PTR)
       call b200_check(rc, "umt_set_geometry")
       ! no reflecting boundaries: set s holds angle s (decomposeAngleSets.F90:280-285); gather omega/weight
       ! of all sets into quadrature order and install them once
       call b200_install_quadrature_and_schedules()
+      b200_mesh_uploaded = .TRUE.
+   endif
+
+!  Once per cycle: the angular flux
+   if (.not. b200_static_uploaded) then
       do setID = 1, nSets
          Set => getSetData(Quad, setID)
          rc = umt_upload_set(b200_ctx, Set%g0, Set%Groups, Set%angle0, Set%NumAngles, c_loc(Set%Psi), c_loc(Set%PsiB))
