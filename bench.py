@@ -342,6 +342,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if os.environ.get("UMT_TRACE"):   # debugging aid: Python stacks of every thread on stderr if the run is still going after 60 s
+        import faulthandler
+        faulthandler.dump_traceback_later(60, repeat=False)
     import torch
     import torch.distributed as dist
     from umt_b200 import teton

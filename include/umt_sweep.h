@@ -174,9 +174,9 @@ int umt_add_shared_boundary(umt_ctx *ctx, int neighborRank, int firstBdyElem, in
    umt_nccl_unique_id).  NCCL is dlopen'ed; fails with UMT_ERR_NCCL if absent.  The psib
    rows then travel GPU-to-GPU with ncclSend/ncclRecv (replaces the persistent MPI
    requests of rt/initcomm.F90:88-101). */
-/* (The rows themselves then travel over peer memory where that is possible -- umt_build_exchange opens the neighbours' receive buffers
-   through CUDA IPC and the pack kernel stores into them directly over NVLink; NCCL carries the small per-pass messages and is the
-   fallback for the rows.) */
+/* (Between the domains of one process, and between ranks when UMT_EXCHANGE_PUT=1 is set, the rows travel over peer memory instead:
+   umt_build_exchange opens the neighbours' receive buffers (CUDA IPC between ranks) and the pack kernel stores into them directly,
+   over NVLink when the neighbour is another GPU; NCCL then only carries the small per-pass messages.) */
 int umt_nccl_unique_id(unsigned char *id128);
 int umt_set_comm(umt_ctx *ctx, int myRank, int nRanks, const unsigned char *id128);
 /* In-process alternative: the n contexts become ranks 0..n-1 of one group (several domains

@@ -78,12 +78,16 @@ def _rank_main():
 
 
 @pytest.mark.gpu
-def test_two_ranks_over_nccl():
+@pytest.mark.parametrize("put", ["0", "1"])
+def test_two_ranks_over_nccl(put):
+    """put = 0: the psib rows travel by ncclSend/ncclRecv (the default between ranks); put = 1: the pack kernel stores them into the
+    neighbour's receive buffer over CUDA IPC peer memory (opt-in, UMT_EXCHANGE_PUT=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, UMT_EXCHANGE_PUT=put)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", os.path.abspath(__file__)], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--master-port", "29517", os.path.abspath(__file__)], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("parity ok") == 2 and r.stdout.count("NCCL GTA solve ok") == 2
 

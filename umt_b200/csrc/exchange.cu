@@ -512,14 +512,19 @@ extern "C" int umt_get_exchange_lists(umt_ctx *ctx, int sharedIndex, int angle, 
 // process).  pack_tally_kernel then stores the exiting rows straight into the neighbour's buffer -- pack and transfer in one kernel, NVLink
 // stores when the neighbour sits on another GPU -- instead of packing a local send buffer that ncclSend/ncclRecv copy across; the
 // neighbour's rows and mine are in the same order (findexit.F90 matches the shared elements one by one).  Collective (the handles
-// travel through the communicator).  Any failure on any rank leaves put_ready false everywhere and the NCCL path in force;
-// UMT_EXCHANGE_PUT=0 switches it off.  (Storing the rows from inside the sweep kernel was measured and dropped: the extra code in the
+// travel through the communicator).  Any failure on any rank leaves put_ready false everywhere and the NCCL path in force.
+// Default inside a process; between ranks only with UMT_EXCHANGE_PUT=1 (verified at 2 ranks; a 4-rank run stalled in the bench's
+// host-buffer loop and was not resolved).  UMT_EXCHANGE_PUT=0 switches it off everywhere.  (Storing the rows from inside the sweep kernel was measured and dropped: the extra code in the
 // zone solve cost 10 % of the sweep, 36.7 -> 40.4 ms at -d 20 -G 128, to save a 0.2 ms pack kernel.)
 static int setup_put(umt_ctx *ctx) {
   ctx->put_ready = false;
   const size_t nS = ctx->shared.size();
   bool want = nS > 0 && ctx->transport != nullptr;
+  const bool local = dynamic_cast<LocalTransport *>(ctx->transport) != nullptr;
+  // between the domains of one process the put path is the default; between ranks (CUDA IPC) it is opt-in, UMT_EXCHANGE_PUT=1
   if (const char *e = getenv("UMT_EXCHANGE_PUT")) want = want && atoi(e) != 0;
+  else want = want && local;
+  UMT_TRACE(ctx, "setup_put: want %d local %d boundaries %zu", (int)want, (int)local, nS);
   // every rank must take the same decision: the handle exchange below is collective, and `want` only depends on things all ranks share
   if (!want) return UMT_OK;
   bool ok = true;
@@ -548,8 +553,10 @@ static int setup_put(umt_ctx *ctx) {
       umt_memcpy(ctx, dS, mine.data(), 2 * nS * hb, cudaMemcpyHostToDevice);
       std::vector<const void *> sp(nS); std::vector<void *> rp(nS); std::vector<size_t> sb(nS, 2 * hb), rb(nS, 2 * hb);
       for (size_t k = 0; k < nS; k++) { sp[k] = dS + 2 * k * hb; rp[k] = dR + 2 * k * hb; }
+      UMT_TRACE(ctx, "setup_put: trading %zu handles", 2 * nS);
       if (ctx->transport->exchange(ctx, sp, sb, rp, rb) != UMT_OK || cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
       else umt_memcpy(ctx, theirs.data(), dR, 2 * nS * hb, cudaMemcpyDeviceToHost);
+      UMT_TRACE(ctx, "setup_put: handles traded ok %d", (int)ok);
     }
     if (dS) cudaFree(dS);
     if (dR) cudaFree(dR);
@@ -561,6 +568,7 @@ static int setup_put(umt_ctx *ctx) {
         ctx->shared[k].peer_recv[j] = static_cast<double *>(q);
         ctx->shared[k].peer_is_ipc = true;
       }
+    UMT_TRACE(ctx, "setup_put: handles opened ok %d", (int)ok);
     // all ranks use the put path or none does (a rank that failed would otherwise wait for rows nobody sends)
     int *d_ok = nullptr;
     int h_ok = ok ? 0 : 1;
@@ -581,6 +589,7 @@ static int setup_put(umt_ctx *ctx) {
     lt->grp->barrier();
   }
   ctx->put_ready = ok;
+  UMT_TRACE(ctx, "setup_put: put_ready %d", (int)ok);
   return UMT_OK;
 }
 
@@ -690,7 +699,9 @@ int umt_exchange_tally(umt_ctx *ctx, double tol) {
     sp[k] = ctx->d_exitFlux + k * NA; rp[k] = ctx->d_incRecv + k * NA; sb[k] = rb[k] = sizeof(double) * NA;
   }
   UMT_CUDA(ctx, cudaGetLastError());
+  UMT_TRACE(ctx, "tally: packed (put %d, passCount %lld), trading currents with %zu neighbours", (int)ctx->put_now, ctx->passCount, nS);
   r = ctx->transport->exchange(ctx, sp, sb, rp, rb);
+  UMT_TRACE(ctx, "tally: trade enqueued rc %d", r);
   if (r) return r;
   const int binsPerSet = ctx->nCommSets > 0 ? ctx->nBins / ctx->nCommSets : 1;
   flux_conv_kernel<<<1, 32, 0, xstream(ctx)>>>(ctx->d_incRecv, (int)ctx->shared.size(), ctx->NA, ctx->d_binOfAngle, ctx->nBins, binsPerSet, ctx->d_incFlux,

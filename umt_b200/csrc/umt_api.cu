@@ -1113,6 +1113,7 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   }
   for (;;) {
     iter++;
+    UMT_TRACE(ctx, "sweep: pass %d (passCount %lld) put %d recv_valid %d pack_valid %d", iter, ctx->passCount, (int)put, (int)ctx->recv_valid, (int)ctx->pack_valid);
     UMT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (multi && !staged) {   // InitExchange/SendFlux/RecvFlux: lagged psib from the previous pass
       if (!ctx->recv_valid) TRY(umt_exchange_rows(ctx));
@@ -1210,7 +1211,9 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   }
   if (overlapped) UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evx[1], 0));   // the call ends when the exchange has, too
   UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+  UMT_TRACE(ctx, "sweep: %d passes enqueued, waiting for the device", iter);
   UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+  UMT_TRACE(ctx, "sweep: device done");
   if (hostPhi) UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
   if (!timedInLoop) {   // the last pass (its events were not read inside the loop)
     float t;

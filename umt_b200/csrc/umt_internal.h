@@ -287,6 +287,13 @@ struct umt_ctx {
                cudaGetErrorString(_e));                                                \
   } while (0)
 
+// UMT_TRACE=1 in the environment: progress lines of the collective parts (exchange set-up, flux passes) on stderr, one per rank
+#define UMT_TRACE(ctx, ...)                                                                                     \
+  do {                                                                                                          \
+    static const bool umt_trace_on_ = getenv("UMT_TRACE") && atoi(getenv("UMT_TRACE")) != 0;                    \
+    if (umt_trace_on_) { fprintf(stderr, "[umt rank %d] ", (ctx)->myRank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } \
+  } while (0)
+
 // Blocking copy ordered with the context's stream.  (cudaMemcpy runs on the legacy default stream, which the context's non-blocking
 // streams do not synchronise with: a pageable host-to-device copy may still be in flight when it returns, and a device-to-host copy
 // does not wait for kernels queued on the context's stream.)
