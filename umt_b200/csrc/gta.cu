@@ -462,6 +462,121 @@ __global__ void __launch_bounds__(64) gta_init_tt_kernel(ZoneParams Z) {
     for (int c = 0; c < mC; c++) Z.TT[(size_t)(c0 + c1) * mC + c] = c < nCorner ? T[c][c1] : 0.0;
 }
 
+// InitGreySweepUCBxyz for meshes of hexahedra (8 corners, 3 faces each) and the 8 S2 ordinates: the thread-per-zone kernel above keeps
+// 1.5 KB of dynamically indexed arrays per thread in local memory and took 5.7 ms at 192 k zones.  Here 64 threads work on one zone:
+// thread (angle a, row r) owns row r of Pvv in registers (the elimination acts on the rows independently, InitSweepGreyUCBxyz.F90's
+// loop over c1) and, as corner r, computes that corner's share of the set-up (denominator, closure coefficients B1/B2, exit
+// coefficients); the 8 lanes of an angle trade these by shuffles.  The angle sum runs in angle order through shared memory.
+constexpr int TTH_ZONES = 2;   // zones per CTA (128 threads)
+__global__ void __launch_bounds__(TTH_ZONES * 64) gta_init_tt_hex_kernel(ZoneParams Z) {
+  __shared__ double sm[TTH_ZONES][8][8][9];
+  const int zl = threadIdx.x >> 6, t = threadIdx.x & 63, a = t >> 3, r = t & 7;
+  const int zone = blockIdx.x * TTH_ZONES + zl;
+  const bool live = zone < Z.nz;
+  const int zq = live ? zone : Z.nz - 1;            // idle threads of the last CTA redo the last zone (shuffles stay convergent)
+  const int c0 = Z.cOffSet[zq], cc = c0 + r;
+  const int base = threadIdx.x & 24;                // first lane of my angle's group of 8 within the warp
+  const double om[3] = {Z.omega[3 * a], Z.omega[3 * a + 1], Z.omega[3 * a + 2]};
+  // ---- my corner's share of the set-up -------------------------------------------------------------------------------------
+  const double vol = Z.Volume[cc], sigt = Z.sigTotal[cc], sigv = vol * sigt;
+  double afp[3], aez[3], B1[3], B2[3], xcoef[3];
+  int cez[3];
+  double dn = sigv;
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    afp[f] = dot3(om, Z.Afp + ((size_t)cc * MAXCF + f) * 3);
+    if (afp[f] > 0.0) dn += afp[f];
+  }
+  unsigned mine = 0;                                // bits 4f..4f+2: cEZ of face f, bit 4f+3: Pvv closure terms present (aez > 0)
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    aez[f] = dot3(om, Z.Aez + ((size_t)cc * MAXCF + f) * 3);
+    cez[f] = Z.cEZ[cc * MAXCF + f];
+    B1[f] = B2[f] = 0.0;
+    if (aez[f] > 0.0) {
+      dn += aez[f];
+      const int ifp = (f + 1) % 3;
+      const double area_opp = afp[ifp] < 0.0 ? -afp[ifp] : 0.0;
+      const double sigtN = Z.sigTotal[c0 + cez[f]], ae = aez[f];
+      if (area_opp > 0.0) {
+        const double sigv2 = sigv * sigv;
+        const double gnum = ae * ae * (FOURALPHA * sigv2 + ae * (4.0 * sigv + 3.0 * ae));
+        const double gtau = gnum / (gnum + 4.0 * sigv2 * sigv2 + ae * sigv * (6.0 * sigv2 + 2.0 * ae * (2.0 * sigv + ae)));
+        const double B0 = 0.5 * ae * (1.0 - gtau);
+        B1[f] = (B0 - gtau * sigv) / sigt;
+        B2[f] = B0 / sigtN;
+      } else {
+        B1[f] = 0.5 * ae / sigt;
+        B2[f] = 0.5 * ae / sigtN;
+      }
+      mine |= 8u << (4 * f);
+    }
+    mine |= (unsigned)cez[f] << (4 * f);
+    // exit r -> cez through this face: the pair's lower corner decides (its A_ez, as the reference's loop over cez > c does)
+    if (cez[f] > r) xcoef[f] = aez[f] > 0.0 ? aez[f] : 0.0;
+    else {
+      const int nb = c0 + cez[f];
+      double alow = 0.0;
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+        if (Z.cEZ[nb * MAXCF + g] == r) alow = dot3(om, Z.Aez + ((size_t)nb * MAXCF + g) * 3);
+      xcoef[f] = alow < 0.0 ? -alow : 0.0;
+    }
+    if (xcoef[f] > 0.0) mine |= 0x1000u << f;       // bit 12+f: face f is an exit of this corner
+  }
+  // ---- row r of Pvv and the dependency counts (4 bits per corner, the same word in the 8 lanes of an angle) -----------------------
+  double row[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) row[c] = c == r ? vol : 0.0;
+  unsigned need = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const unsigned w = __shfl_sync(0xffffffffu, mine, base + c);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double b1 = __shfl_sync(0xffffffffu, B1[f], base + c), b2 = __shfl_sync(0xffffffffu, B2[f], base + c);
+      const int ce = (w >> (4 * f)) & 7;
+      if ((w >> (4 * f)) & 8u) {                    // Pvv(c,c) += B1, Pvv(cez,c) -= B2, Pvv(c,cez) -= B1, Pvv(cez,cez) += B2
+        if (r == c) { row[c] += b1; addto(row, ce, -b1); }
+        if (r == ce) { row[c] -= b2; addto(row, ce, b2); }
+      }
+      if ((w >> (12 + f)) & 1u) need += 1u << (4 * ce);
+    }
+  }
+  // ---- elimination in the order of the fewest unresolved upstream corners (first minimum, as minloc) -----------------------------
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    int c = 0;
+    unsigned best = need & 15u;
+#pragma unroll
+    for (int k = 1; k < 8; k++) { const unsigned v = (need >> (4 * k)) & 15u; if (v < best) { best = v; c = k; } }
+    const double dInv = 1.0 / __shfl_sync(0xffffffffu, dn, base + c);
+    const double v = dInv * pick(row, c);
+    put(row, c, v);
+    const unsigned w = __shfl_sync(0xffffffffu, mine, base + c);
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+      const double coef = __shfl_sync(0xffffffffu, xcoef[f], base + c);
+      if ((w >> (12 + f)) & 1u) {
+        const int ce = (w >> (4 * f)) & 7;
+        need -= 1u << (4 * ce);
+        addto(row, ce, coef * v);
+      }
+    }
+    need |= 15u << (4 * c);                         // done
+  }
+  // ---- TT(c, c0 + c1) = sum over the angles, in angle order, of w_a Pvv_a(c, c1) ------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < 8; c++) sm[zl][a][r][c] = row[c];
+  __syncthreads();
+  if (!live) return;
+  const int c1 = t >> 3, c = t & 7;                 // consecutive threads write consecutive TT entries
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s = s + Z.weight[k] * sm[zl][k][c][c1];
+  Z.TT[(size_t)(c0 + c1) * Z.mC + c] = s;
+}
+
 // ScalarIntensityDecompose + ScalarIntensitySolve for one zone
 __global__ void __launch_bounds__(64) gta_scalar_kernel(ZoneParams Z, int withSource) {
   const int zone = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,6 +624,48 @@ __global__ void __launch_bounds__(64) gta_scalar_kernel(ZoneParams Z, int withSo
   }
   for (int c = 0; c < n; c++) Z.P[c0 + c] = Phi[c];
 #undef TTF
+}
+
+// ScalarIntensitySolve alone (the LU factors are in place) for meshes of hexahedra: 8 lanes per zone, lane j holds column j of the
+// factors (TT(0..7, c0+j), one 64-byte row of the array) in registers.  Forward substitution by columns, back substitution with every
+// partial sum accumulated in ascending index order: the same sums in the same order as the one-thread version above.
+__global__ void __launch_bounds__(256) gta_scalar_solve_hex_kernel(ZoneParams Z) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  int zone = gt >> 3;
+  const int j = gt & 7, base = threadIdx.x & 24;
+  const bool live = zone < Z.nz;
+  if (!live) zone = Z.nz - 1;
+  const int c0 = Z.cOffSet[zone];
+  double col[8];   // col[i] = TT(i, c0 + j)
+  const double2 *src = reinterpret_cast<const double2 *>(Z.TT + (size_t)(c0 + j) * 8);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const double2 v = src[i]; col[2 * i] = v.x; col[2 * i + 1] = v.y; }
+  double phi = Z.phiInc[c0 + j];
+  // Phi(j) = Phi(j) + sum_{i<j} -TT(i,j) Phi(i)
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const double pi = __shfl_sync(0xffffffffu, j == i ? phi + t : 0.0, base + i);   // lane i's value is final once i terms are in
+    if (j == i) { phi = phi + t; t = 0.0; }
+    if (j > i) t = t - col[i] * pi;
+  }
+  if (j == 7) phi = phi + t;
+  // Phi(k) = (Phi(k) - sum_{i>k} Phi(i) TT(i,k)) / TT(k,k), k = 7 .. 0: TT(i,k) is element i of column k, lane k's col[i]
+  double diag = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) diag = j == i ? col[i] : diag;
+  if (j == 7) phi = phi / diag;
+#pragma unroll
+  for (int k = 6; k >= 0; k--) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = k + 1; i < 8; i++) {
+      const double pi = __shfl_sync(0xffffffffu, phi, base + i);
+      s = s + pi * col[i];
+    }
+    if (j == k) phi = (phi - s) / diag;
+  }
+  if (live) Z.P[c0 + j] = phi;
 }
 
 // setGTAOpacityNEW per corner; Chi (nc, G) rescaled in place
@@ -586,8 +743,14 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const double *x, const
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
-__global__ void sum_partials_kernel(const double *partial, int n, double *out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; i++) s += partial[i]; *out = s; }
+// (one CTA: the partials are fetched by all threads at once, then summed by one thread in index order -- deterministic, and not a
+// chain of dependent global loads)
+constexpr int RED_MAX = 1024;
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double *partial, int n, double *out) {
+  __shared__ double sh[RED_MAX];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = partial[i];
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < n; i++) s += sh[i]; *out = s; }
 }
 
 // zone corrections and the error norms of GTASolver.F90:331-375; partial[0..nb)=errL2, [nb..2nb)=phiL2, [2nb..3nb)=max rel err
@@ -616,11 +779,16 @@ __global__ void __launch_bounds__(256) zone_error_kernel(int nz, const int *numC
   }
   if (threadIdx.x == 0) { partial[blockIdx.x] = r0[0]; partial[gridDim.x + blockIdx.x] = r1[0]; partial[2 * gridDim.x + blockIdx.x] = r2[0]; }
 }
-__global__ void zone_error_finish_kernel(const double *partial, int nb, double *out3) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double e = 0.0, p = 0.0, m = 0.0;
-    for (int i = 0; i < nb; i++) { e += partial[i]; p += partial[nb + i]; m = fmax(m, partial[2 * nb + i]); }
-    out3[0] = e; out3[1] = p; out3[2] = m;
+__global__ void __launch_bounds__(256) zone_error_finish_kernel(const double *partial, int nb, double *out3) {
+  __shared__ double sh[3 * RED_MAX];
+  for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) sh[i] = partial[i];
+  __syncthreads();
+  if (threadIdx.x < 3) {   // one thread per quantity, each in index order
+    const double *q = sh + threadIdx.x * nb;
+    double v = 0.0;
+    if (threadIdx.x < 2) for (int i = 0; i < nb; i++) v += q[i];
+    else for (int i = 0; i < nb; i++) v = fmax(v, q[i]);
+    out3[threadIdx.x] = v;
   }
 }
 
@@ -653,6 +821,7 @@ int dalloc(umt_ctx *ctx, T **p, size_t n, bool zero = true) {
 }
 
 constexpr int RED_BLOCKS = 296;   // 2 per SM
+static_assert(RED_BLOCKS <= RED_MAX, "the finishing kernels stage the partials in shared memory");
 
 int need_gta(umt_ctx *ctx) {
   if (!ctx->gta.ready) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA not set up (umt_gta_setup)");
@@ -745,7 +914,8 @@ int gta_grey_sweep(umt_ctx *ctx, double *d_P, double *d_PsiB, int withSource) {
     if (ctx->gta.tt_decomposed) UMT_FAIL(ctx, UMT_ERR_STATE, "GTA transfer matrices already decomposed: call umt_gta_init_tt before another withSource sweep");
     ctx->gta.tt_decomposed = true;
   }
-  gta_scalar_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z, withSource);
+  if (!withSource && ctx->gta.hexTT) gta_scalar_solve_hex_kernel<<<nblk((size_t)ctx->nz * 8, 256), 256, 0, ctx->stream>>>(Z);
+  else gta_scalar_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z, withSource);
   UMT_CUDA(ctx, cudaGetLastError());
   return UMT_OK;
 }
@@ -753,7 +923,7 @@ int gta_grey_sweep(umt_ctx *ctx, double *d_P, double *d_PsiB, int withSource) {
 int device_dot(umt_ctx *ctx, const double *x, const double *y, double *result) {
   GtaState &g = ctx->gta;
   dot_partial_kernel<<<RED_BLOCKS, 256, 0, ctx->stream>>>(x, y, g.d_sigScatVol, ctx->nc, g.d_red);
-  sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
+  sum_partials_kernel<<<1, 256, 0, ctx->stream>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
   TRY(umt_allreduce_f64(ctx, g.d_red + 3 * RED_BLOCKS, 1, 0));   // MPIAllReduce(sum) of scat_prod / scat_prod1
   UMT_CUDA(ctx, cudaMemcpyAsync(result, g.d_red + 3 * RED_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -884,6 +1054,11 @@ extern "C" int umt_gta_setup(umt_ctx *ctx) {
   for (int a = 0; a < g.nAng && g.flow3d; a++)
     for (int z : g.nextZ[a]) if (z < 0) { g.flow3d = false; break; }
   if (const char *e = getenv("UMT_GTA_KERNEL")) if (std::string(e) == "item") g.flow3d = false;
+  // InitGreySweep with 64 threads per zone: hexahedra only (8 corners of 3 faces), the 8 S2 ordinates
+  g.hexTT = nd == 3 && g.nAng == 8 && ctx->maxCorner == 8;
+  for (int z = 0; z < ctx->nz && g.hexTT; z++) g.hexTT = ctx->h_numCorner[z] == 8;
+  for (int c = 0; c < nc && g.hexTT; c++) g.hexTT = ctx->h_nCFaces[c] == 3;
+  if (const char *e = getenv("UMT_GTA_TT")) if (std::string(e) == "zone") g.hexTT = false;
   if (g.flow3d) {
     std::vector<int> zoneOf(nc), planeOf(nz);
     for (int z = 0; z < nz; z++) for (int c = 0; c < ctx->h_numCorner[z]; c++) zoneOf[ctx->h_cOffSet[z] + c] = z;
@@ -1047,7 +1222,8 @@ extern "C" int umt_gta_init_tt(umt_ctx *ctx, double *TT /* (maxCorner, nc) or NU
   } else {
     ZoneParams Z;
     zone_params(ctx, Z, ctx->gta.d_P);
-    gta_init_tt_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z);
+    if (ctx->gta.hexTT) gta_init_tt_hex_kernel<<<(ctx->nz + TTH_ZONES - 1) / TTH_ZONES, TTH_ZONES * 64, 0, ctx->stream>>>(Z);
+    else gta_init_tt_kernel<<<nblk(ctx->nz, 64), 64, 0, ctx->stream>>>(Z);
     UMT_CUDA(ctx, cudaGetLastError());
   }
   UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1167,7 +1343,7 @@ extern "C" int umt_gta_solve(umt_ctx *ctx, double epsPoint, int maxIters, double
     if (nB) k_dir<<<nblk(nB), 256, 0, st>>>(DB, RB, beta, omegaCG, AB, nB);
     zone_error_kernel<<<RED_BLOCKS, 256, 0, st>>>(nz, ctx->d_numCorner, ctx->d_cOffSet, ctx->d_Volume, g.d_volZone, g.d_correction, g.d_radEnergy,
                                                   g.d_pzOld, g.d_red);
-    zone_error_finish_kernel<<<1, 32, 0, st>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
+    zone_error_finish_kernel<<<1, 256, 0, st>>>(g.d_red, RED_BLOCKS, g.d_red + 3 * RED_BLOCKS);
     double e3[3];
     UMT_CUDA(ctx, cudaMemcpyAsync(e3, g.d_red + 3 * RED_BLOCKS, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
     UMT_CUDA(ctx, cudaStreamSynchronize(st));

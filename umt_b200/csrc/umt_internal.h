@@ -117,6 +117,7 @@ struct GtaState {
   int *d_level = nullptr;
   double *d_fac = nullptr, *d_w1 = nullptr, *d_w2 = nullptr, *d_psim = nullptr, *d_tinc = nullptr;   // psim/tinc: (nLevels, nc)
   unsigned char *d_finish = nullptr;
+  bool hexTT = false;                  // InitGreySweep by gta_init_tt_hex_kernel (all zones hexahedra)
   bool flow3d = false;                 // 3-D dataflow kernel (gta_sweep_flow_kernel): values as their own completion flags
   unsigned *d_pollMask = nullptr;      // (nAng, nz) which incident faces of a zone the schedule orders (see gta.cu)
   bool rz_chain = false;               // one CTA per xi-level (gta_sweep_rz_chain_kernel)
