@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--azimuthal", type=int, default=2)
     ap.add_argument("--cpu-dims", type=int, default=0, help="tiles per side of the bounded CPU sample (default: 10 for the cpu_baseline leg, 8 per step for --impl reference)")
     ap.add_argument("--ring", type=int, default=-1, help="Psi1 ring size in angle batches (umt_set_psi1_ring; default: as the free HBM allows)")
+    ap.add_argument("--group-sets", type=int, default=2, help="group sets of the pipelined end-to-end call (umt_control_sweep_sets; 1: one set, umt_control_sweep only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing NCCL parity check (N > 1)")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
@@ -447,6 +448,45 @@ def main():
         ctx.control_sweep(h_sigt, h_stotal, tau, h_phi, False, args.flux_iters)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_what = "umt_control_sweep: Sigt, STotal from pinned host -> whole ControlSweep -> PhiTotal to pinned host (phi reduction and its D2H overlapped)"
+    e2e_one_set = None
+    host_node = getattr(ctx, "host_numa_node", None)
+    S = args.group_sets
+    if world == 1 and S > 1 and G % S == 0 and (G // S) % 2 == 0:
+        # The same domain and groups as `S` group sets, one context each (the reference's phase-space sets split the groups the same
+        # way), through umt_control_sweep_sets: upload of set k+1 and download of set k-1 run under the sweep of set k.
+        e2e_one_set = {"value": total_unknowns / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "what": e2e_what}
+        ctx.close()
+        Gs = G // S
+        bounds = PR.group_bounds(G)
+        sets, hs, ht, hp = [], [], [], []
+        for k in range(S):
+            c = teton.SweepContext.from_mesh(mesh, Gs, device=local)
+            c.compute_geometry(mesh.px)
+            c.build_product_quadrature(args.polar, args.azimuthal, 1)
+            c.build_schedule()
+            a = c.host_array((nz, Gs)); a[:] = tau
+            b = c.host_array((nc, Gs)); b[:] = 0.0
+            hs.append(a); ht.append(b); hp.append(c.host_array((nc, Gs)))
+            c.upload_state(None, None, a, b, tau)
+            c.init_teton(np.full(nz, PR.TR0), bounds[k * Gs:(k + 1) * Gs + 1], PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
+            c.init_phi_total()
+            c.init_radiation_field()
+            sets.append(c)
+        for _ in range(2):
+            teton.control_sweep_sets(sets, hs, ht, tau, hp, False, args.flux_iters)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            teton.control_sweep_sets(sets, hs, ht, tau, hp, False, args.flux_iters)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        set_ms = [c.last_times() for c in sets]
+        e2e_what = (f"umt_control_sweep_sets: the {G} groups as {S} group sets of {Gs} (one context each), Sigt/STotal of every set from pinned host -> "
+                    f"sweep -> PhiTotal to pinned host, sets pipelined (upload of set k+1 and download of set k-1 under the sweep of set k); "
+                    f"sweep kernels {', '.join('%.1f' % t['sweep_ms'] for t in set_ms)} ms")
+        for c in sets:
+            c.close()
     if rank == 0:
         sampler.stop()
 
@@ -464,7 +504,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": total_unknowns / (e2e_ms * 1e-3), "unit": "unknowns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "what": "umt_control_sweep: Sigt, STotal from pinned host -> whole ControlSweep -> PhiTotal to pinned host (phi reduction and its D2H overlapped)"},
+                    "ms_per_step": e2e_ms, "what": e2e_what, "one_group_set": e2e_one_set},
             "gpu_launches": launches,
             "parity_checked": bool(parity), "parity": parity,
             "flux_passes_per_step": iters / args.steps,
@@ -479,7 +519,7 @@ def main():
             "psi_layout": dict(layout, device_memory_used_GB=(mem_total - mem_free) / 1e9),
             "setup_ms": {"build_schedule_host": sched_ms, "first_use_plan_records_items_workspace": finalize_ms,
                          "note": "once per mesh/quadrature (the reference rebuilds its schedules every cycle, control/initializeSets.F90:95-105); not in the timed region"},
-            "host_buffers": {"rank_bound_to_numa_node": numa, "pages_bound_to_numa_node": getattr(ctx, "host_numa_node", None), "kind": "umt_host_alloc (page-locked, bound to the GPU's NUMA node)"},
+            "host_buffers": {"rank_bound_to_numa_node": numa, "pages_bound_to_numa_node": host_node, "kind": "umt_host_alloc (page-locked, bound to the GPU's NUMA node)"},
             "device_ms_per_step": device_step_ms,
             "clocks": sampler.summary(),
         }

@@ -152,6 +152,14 @@ int umt_sweep(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTol, int *
    umt_download_phi with the phi reduction and its device-to-host copy overlapped.  Pinned host buffers recommended. */
 int umt_control_sweep(umt_ctx *ctx, const double *Sigt, const double *STotal, double tau, int savePsi, int maxFluxIters,
                       double fluxTol, int *itersDone, double *PhiTotal);
+/* One ControlSweep over the n group sets of a domain, one context per group set (the reference's phase-space sets split the groups
+   the same way: every SetData has its g0 / Groups, mods/SetData_mod.F90:35-50, and GSet%Sigt / GSet%STotal are per group set,
+   mods/GroupSet_mod.F90).  Sigt[k] (Groups_k, nzones), STotal[k] (Groups_k, ncornr) in, PhiTotal[k] (Groups_k, ncornr) out, all host
+   arrays (page-locked recommended).  The sets are pipelined: the upload of set k+1 and the download of set k-1 run while set k is
+   swept, so host<->device traffic in both directions hides behind the sweeps.  Same results as n umt_control_sweep calls (groups do
+   not couple inside a sweep).  Contexts with shared boundaries are swept one after the other (each with its own exchange). */
+int umt_control_sweep_sets(umt_ctx *const *ctxs, int n, const double *const *Sigt, const double *const *STotal, double tau, int savePsi,
+                           int maxFluxIters, double fluxTol, int *itersDone, double *const *PhiTotal);
 int umt_last_sweep_times(umt_ctx *ctx, double *ms4);
 int umt_last_sweep_launches(umt_ctx *ctx, int *nLaunches);
 int umt_synchronize(umt_ctx *ctx);

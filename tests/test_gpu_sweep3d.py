@@ -104,3 +104,46 @@ def test_control_sweep_with_host_buffers_equals_upload_sweep_download():
     ctx.sweep(savePsi=False)
     assert np.array_equal(ctx.download_phi(), phi_c)
     ctx.close(); ctx2.close()
+
+
+def test_control_sweep_sets_pipelined_group_sets():
+    """umt_control_sweep_sets: the groups of a domain in three group sets (one context each, uneven sizes, the first large enough for
+    the chunked phi download), uploads / sweeps / downloads pipelined across the sets.  Must equal, bit for bit, the same contexts
+    swept one at a time, and the one-context sweep of all groups to rounding (groups do not couple, SweepUCBxyz.F90:119-281)."""
+    import copy
+    from umt_b200 import teton
+    m = M.tiled_mesh((5, 5, 5))
+    sizes = [192, 64, 128]
+    G = sum(sizes)
+    p = T.make_problem_3d(m, 1, 1, G)
+    full = T.gpu_context_3d(p)
+    bounds = np.cumsum([0] + sizes)
+
+    def subset(k):
+        q = copy.copy(p)
+        sl = slice(bounds[k], bounds[k + 1])
+        q.G = sizes[k]
+        q.Psi, q.PsiB = np.ascontiguousarray(p.Psi[:, :, sl]), np.ascontiguousarray(p.PsiB[:, :, sl])
+        q.Sigt, q.STotal = np.ascontiguousarray(p.Sigt[:, sl]), np.ascontiguousarray(p.STotal[:, sl])
+        return q
+    subs = [subset(k) for k in range(3)]
+    sets = [T.gpu_context_3d(q) for q in subs]
+    ones = [T.gpu_context_3d(q) for q in subs]
+    for save in (False, True, False):
+        scale = 2.0 if save else 1.0   # a new source from the host every call
+        full.upload_state(None, None, None, scale * p.STotal, p.tau)
+        full.sweep(savePsi=save)
+        phi_full = full.download_phi()
+        out = [np.full((m.ncornr, g), -1.0) for g in sizes]
+        it = teton.control_sweep_sets(sets, [q.Sigt for q in subs], [scale * q.STotal for q in subs], p.tau, out, savePsi=save)
+        assert it == 1
+        for k, (c, q) in enumerate(zip(ones, subs)):
+            ref = np.zeros((m.ncornr, sizes[k]))
+            c.control_sweep(q.Sigt, scale * q.STotal, p.tau, ref, savePsi=save)
+            assert np.array_equal(out[k], ref), (save, k)
+            assert T.relerr(out[k], phi_full[:, bounds[k]:bounds[k + 1]]) <= 1e-13, (save, k)
+    for k, c in enumerate(sets):
+        assert T.mixed_err(c.download_psi(), full.download_psi()[:, :, bounds[k]:bounds[k + 1]], 1e-13) <= 1.0
+        assert T.mixed_err(c.download_psib(), full.download_psib()[:, :, bounds[k]:bounds[k + 1]], 1e-13) <= 1.0
+    for c in sets + ones + [full]:
+        c.close()

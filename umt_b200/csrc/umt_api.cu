@@ -1246,6 +1246,114 @@ static int sweep_impl(umt_ctx *ctx, int savePsi, int maxFluxIters, double fluxTo
   return umt_check_abort(ctx, "umt_sweep");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Group sets of one domain, pipelined (umt_control_sweep_sets).  Single-domain contexts only: a pass is then upload -> sweep kernel
+// -> phi tally in chunks, each chunk followed by its download, with no host decision in between, so a whole set can be enqueued
+// without waiting for it.
+// ---------------------------------------------------------------------------------------------------------------------------
+static int sweep_enqueue_single(umt_ctx *ctx, int savePsi, double *hostPhi) {
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->last_launches = 0;
+  const size_t nCyc = (size_t)ctx->totalCycles * ctx->G;
+  if (ctx->totalCycles > 0) {                     // initFromCycleList
+    cycle_copy_kernel<<<(int)((nCyc + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList, ctx->d_cycleAngle,
+                                                                          ctx->totalCycles, ctx->rows, ctx->G, 1);
+    ctx->last_launches++;
+  }
+  if (ctx->ndim == 3) TRY(umt_launch_sweep3d(ctx, savePsi));
+  else TRY(umt_launch_sweeprz(ctx, savePsi));
+  ctx->passCount++;
+  if (ctx->totalCycles > 0) {                     // updateCycleList
+    cycle_copy_kernel<<<(int)((nCyc + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_psi1, ctx->d_cyclePsi, ctx->d_cycleList, ctx->d_cycleAngle,
+                                                                          ctx->totalCycles, ctx->rows, ctx->G, 0);
+    ctx->last_launches++;
+  }
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  const size_t n = (size_t)ctx->nc * ctx->G;
+  const int nChunks = n >= (size_t)1 << 22 ? 8 : 1;
+  const size_t per = ((n + nChunks - 1) / nChunks + 1) / 2 * 2;
+  for (int k = 0; k < nChunks; k++) {
+    const size_t o = (size_t)k * per;
+    if (o >= n) break;
+    const size_t m = std::min(per, n - o);
+    TRY(launch_phi_range(ctx, savePsi, o, m));
+    UMT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+    UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev[7], 0));
+    UMT_CUDA(ctx, cudaMemcpyAsync(hostPhi + o, ctx->d_phi + o, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream2));
+  }
+  UMT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));   // the set's kernels are done: the next set's sweep may take the SMs
+  return UMT_OK;
+}
+
+static int sweep_finish_single(umt_ctx *ctx, int savePsi) {
+  UMT_CUDA(ctx, cudaSetDevice(ctx->device));
+  UMT_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+  UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+  float ms_sweep = 0.f, ms_phi = 0.f, ms_all = 0.f;
+  cudaEventElapsedTime(&ms_sweep, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ms_phi, ctx->ev[3], ctx->ev[6]);
+  cudaEventElapsedTime(&ms_all, ctx->ev[0], ctx->ev[6]);
+  if (savePsi && !ctx->single_psi) {   // legacy layout: the buffers trade roles (see sweep_impl)
+    std::swap(ctx->d_psi, ctx->d_psi1);
+    const size_t G = ctx->G, pitch = G * ctx->rows * 8, off = G * ctx->nc;
+    bool anyBad = false;
+    for (int a = 0; a < ctx->NA; a++) anyBad = anyBad || ctx->nBad[a] > 0;
+    if (anyBad) UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1, pitch, ctx->d_psi, pitch, G * ctx->nc * 8, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->nb > 0)
+      UMT_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_psi1 + off, pitch, ctx->d_psi + off, pitch, G * ctx->nb * 8, ctx->NA, cudaMemcpyDeviceToDevice, ctx->stream));
+    UMT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->last_ms[0] = ms_sweep; ctx->last_ms[1] = ms_phi; ctx->last_ms[2] = 0.0; ctx->last_ms[3] = ms_all;
+  return umt_check_abort(ctx, "umt_control_sweep_sets");
+}
+
+extern "C" int umt_control_sweep_sets(umt_ctx *const *ctxs, int n, const double *const *Sigt, const double *const *STotal, double tau,
+                                      int savePsi, int maxFluxIters, double fluxTol, int *itersDone, double *const *PhiTotal) {
+  if (!ctxs || n < 1 || !PhiTotal) return UMT_ERR_ARG;
+  bool pipeline = true;
+  for (int k = 0; k < n; k++) {
+    if (!ctxs[k] || !PhiTotal[k]) return UMT_ERR_ARG;
+    pipeline = pipeline && ctxs[k]->device >= 0 && ctxs[k]->device == ctxs[0]->device && ctxs[k]->shared.empty();
+  }
+  if (itersDone) *itersDone = 1;
+  if (!pipeline) {   // domains with neighbours: every set runs its own flux iteration and exchange, one after the other
+    int worst = 0;
+    for (int k = 0; k < n; k++) {
+      int it = 0;
+      TRY(umt_control_sweep(ctxs[k], Sigt ? Sigt[k] : nullptr, STotal ? STotal[k] : nullptr, tau, savePsi, maxFluxIters, fluxTol, &it, PhiTotal[k]));
+      worst = std::max(worst, it);
+    }
+    if (itersDone) *itersDone = worst;
+    return UMT_OK;
+  }
+  umt_ctx *c0 = ctxs[0];
+  UMT_CUDA(c0, cudaSetDevice(c0->device));
+  for (int k = 0; k < n; k++) {   // everything that may allocate, build or wait happens before the first copy is queued
+    umt_ctx *ctx = ctxs[k];
+    if (!ctx->have_conn || !ctx->have_geom || !ctx->have_quad) UMT_FAIL(ctx, UMT_ERR_STATE, "umt_control_sweep_sets: connectivity, geometry and quadrature must be set");
+    TRY(ensure_state(ctx));
+    TRY(finalize_schedule(ctx));
+  }
+  // uploads of all sets on ONE stream, in set order: set 0 has the whole link first, set k+1 arrives while set k is swept
+  cudaStream_t up = c0->stream3;
+  for (int k = 0; k < n; k++) {
+    umt_ctx *ctx = ctxs[k];
+    const size_t G = ctx->G;
+    if (Sigt && Sigt[k]) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt[k], sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, up));
+    if (STotal && STotal[k]) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_stotal, STotal[k], sizeof(double) * G * ctx->nc, cudaMemcpyHostToDevice, up));
+    UMT_CUDA(ctx, cudaEventRecord(ctx->evx[2], up));
+    UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evx[2], 0));
+    // a persistent sweep kernel owns every SM it gets: the tally of the previous set goes first, or it would wait a whole sweep
+    if (k > 0) UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctxs[k - 1]->ev[6], 0));
+    ctx->tau = tau;
+    TRY(sweep_enqueue_single(ctx, savePsi, PhiTotal[k]));
+  }
+  int rc = UMT_OK;
+  for (int k = 0; k < n; k++) { const int r = sweep_finish_single(ctxs[k], savePsi); if (r && !rc) rc = r; }
+  return rc;
+}
+
 extern "C" int umt_last_sweep_times(umt_ctx *ctx, double *ms4) {
   if (!ctx || !ms4) return UMT_ERR_ARG;
   for (int i = 0; i < 4; i++) ms4[i] = ctx->last_ms[i];

@@ -428,6 +428,37 @@ def connect_local(contexts):
         raise UmtError(f"umt_connect_local -> {rc}")
 
 
+def control_sweep_sets(contexts, Sigt, STotal, tau, PhiTotal, savePsi=False, maxFluxIters=1, fluxTol=1e-6):
+    """One ControlSweep over the group sets of a domain (umt_control_sweep_sets): contexts[k] holds group set k, Sigt[k] (nz, G_k) and
+    STotal[k] (nc, G_k) in (None keeps the device copies), PhiTotal[k] (nc, G_k) out, filled in place.  Sets are pipelined: upload of
+    set k+1 and download of set k-1 run under the sweep of set k."""
+    lib = load_library()
+    n = len(contexts)
+    assert len(PhiTotal) == n
+    dpp = C.POINTER(C.c_double) * n
+
+    def ptrs(arrs, shape_of):
+        if arrs is None:
+            return None
+        out = []
+        for c, a in zip(contexts, arrs):
+            if a is None:
+                out.append(C.POINTER(C.c_double)())
+            else:
+                assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shape_of(c)
+                out.append(_dp(a))
+        return dpp(*out)
+    it = C.c_int(0)
+    keep = [None if Sigt is None else [None if a is None else _f64(a) for a in Sigt],
+            None if STotal is None else [None if a is None else _f64(a) for a in STotal]]
+    ctxs = (C.c_void_p * n)(*[c.h for c in contexts])
+    rc = lib.umt_control_sweep_sets(ctxs, n, ptrs(keep[0], lambda c: (c.nz, c.G)), ptrs(keep[1], lambda c: (c.nc, c.G)), C.c_double(tau),
+                                    int(bool(savePsi)), int(maxFluxIters), C.c_double(fluxTol), C.byref(it), ptrs(PhiTotal, lambda c: (c.nc, c.G)))
+    if rc:
+        raise UmtError(f"umt_control_sweep_sets -> {rc}: " + "; ".join(lib.umt_last_error(c.h).decode() for c in contexts))
+    return it.value
+
+
 def nccl_unique_id() -> bytes:
     lib = load_library()
     buf = (C.c_ubyte * 128)()
