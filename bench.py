@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--azimuthal", type=int, default=2)
     ap.add_argument("--cpu-dims", type=int, default=0, help="tiles per side of the bounded CPU sample (default: 10 for the cpu_baseline leg, 8 per step for --impl reference)")
     ap.add_argument("--ring", type=int, default=-1, help="Psi1 ring size in angle batches (umt_set_psi1_ring; default: as the free HBM allows)")
-    ap.add_argument("--group-sets", type=int, default=2, help="group sets of the pipelined end-to-end call (umt_control_sweep_sets; 1: one set, umt_control_sweep only)")
+    ap.add_argument("--group-sets", default="32,64,32", help="group sets of the pipelined end-to-end call (umt_control_sweep_sets): a count of equal sets or their sizes; sizes that do not add up to --groups fall back to 2 equal sets; 1: one set, umt_control_sweep only")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing NCCL parity check (N > 1)")
     ap.add_argument("--flux-iters", type=int, default=1, help="incidentFlux max iterations per sweep (driver default 2)")
@@ -451,16 +451,22 @@ def main():
     e2e_what = "umt_control_sweep: Sigt, STotal from pinned host -> whole ControlSweep -> PhiTotal to pinned host (phi reduction and its D2H overlapped)"
     e2e_one_set = None
     host_node = getattr(ctx, "host_numa_node", None)
-    S = args.group_sets
-    if world == 1 and S > 1 and G % S == 0 and (G // S) % 2 == 0:
+    sizes = [int(x) for x in str(args.group_sets).split(",")]
+    if len(sizes) > 1 and sum(sizes) != G:
+        sizes = [2]
+    if len(sizes) == 1:
+        sizes = [G // sizes[0]] * sizes[0] if sizes[0] > 0 and G % sizes[0] == 0 else [G]
+    S = len(sizes)
+    if world == 1 and S > 1 and sum(sizes) == G and all(g > 0 and g % 2 == 0 for g in sizes):
         # The same domain and groups as `S` group sets, one context each (the reference's phase-space sets split the groups the same
         # way), through umt_control_sweep_sets: upload of set k+1 and download of set k-1 run under the sweep of set k.
         e2e_one_set = {"value": total_unknowns / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "what": e2e_what}
         ctx.close()
-        Gs = G // S
         bounds = PR.group_bounds(G)
+        g0s = [sum(sizes[:k]) for k in range(S)]
         sets, hs, ht, hp = [], [], [], []
         for k in range(S):
+            Gs = sizes[k]
             c = teton.SweepContext.from_mesh(mesh, Gs, device=local)
             c.compute_geometry(mesh.px)
             c.build_product_quadrature(args.polar, args.azimuthal, 1)
@@ -469,7 +475,7 @@ def main():
             b = c.host_array((nc, Gs)); b[:] = 0.0
             hs.append(a); ht.append(b); hp.append(c.host_array((nc, Gs)))
             c.upload_state(None, None, a, b, tau)
-            c.init_teton(np.full(nz, PR.TR0), bounds[k * Gs:(k + 1) * Gs + 1], PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
+            c.init_teton(np.full(nz, PR.TR0), bounds[g0s[k]:g0s[k] + Gs + 1], PR.SPEED_LIGHT, PR.RAD_CONSTANT, PR.wtiso(3), 0.0)
             c.init_phi_total()
             c.init_radiation_field()
             sets.append(c)
@@ -482,7 +488,7 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         set_ms = [c.last_times() for c in sets]
-        e2e_what = (f"umt_control_sweep_sets: the {G} groups as {S} group sets of {Gs} (one context each), Sigt/STotal of every set from pinned host -> "
+        e2e_what = (f"umt_control_sweep_sets: the {G} groups as {S} group sets of {'+'.join(map(str, sizes))} (one context each), Sigt/STotal of every set from pinned host -> "
                     f"sweep -> PhiTotal to pinned host, sets pipelined (upload of set k+1 and download of set k-1 under the sweep of set k); "
                     f"sweep kernels {', '.join('%.1f' % t['sweep_ms'] for t in set_ms)} ms")
         for c in sets:

@@ -127,6 +127,18 @@ module teton_b200_mod
          integer(C_INT)        :: itersDone
       end function
 
+!     the same over the group sets of the domain, one context per group set: ctxs(n), Sigt(n), STotal(n), PhiTotal(n) are arrays of
+!     C pointers (c_loc of GSet%Sigt, GSet%STotal of group set k and of the PhiTotal block of its groups); the sets are pipelined
+      integer(C_INT) function umt_control_sweep_sets(ctxs, n, Sigt, STotal, tau, savePsi, maxFluxIters, fluxTol, itersDone, PhiTotal) &
+                              bind(C, name="umt_control_sweep_sets")
+         import :: C_INT, C_PTR, C_DOUBLE
+         type(C_PTR)           :: ctxs(*), Sigt(*), STotal(*), PhiTotal(*)
+         integer(C_INT), value :: n
+         real(C_DOUBLE), value :: tau, fluxTol
+         integer(C_INT), value :: savePsi, maxFluxIters
+         integer(C_INT)        :: itersDone
+      end function
+
       integer(C_INT) function umt_download_phi(ctx, PhiTotal) bind(C, name="umt_download_phi")
          import :: C_INT, C_PTR, C_DOUBLE
          type(C_PTR), value :: ctx
