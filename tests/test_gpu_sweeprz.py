@@ -79,3 +79,38 @@ def test_optional_rz_kernels_match_oracle(kernel):
         _run_case(M.tiled_mesh((4, 2, 0)), 2, 2, 64, driver_like=True, sweeps=(False, True))
     finally:
         del os.environ["UMT_RZ_KERNEL"]
+
+
+def test_control_sweep_sets_rz_group_sets():
+    """umt_control_sweep_sets on r-z contexts (two group sets, pipelined) == the same contexts swept one at a time, bit for bit, and
+    the oracle's sweep of all groups."""
+    import copy
+    from umt_b200 import teton
+    m = M.tiled_mesh((4, 4, 0))
+    sizes = [32, 16]
+    p = T.make_problem_rz(m, 2, 2, sum(sizes))
+    bounds = np.cumsum([0] + sizes)
+
+    def subset(k):
+        q = copy.copy(p)
+        sl = slice(bounds[k], bounds[k + 1])
+        q.G = sizes[k]
+        q.Psi, q.PsiB = np.ascontiguousarray(p.Psi[:, :, sl]), np.ascontiguousarray(p.PsiB[:, :, sl])
+        q.Sigt, q.STotal = np.ascontiguousarray(p.Sigt[:, sl]), np.ascontiguousarray(p.STotal[:, sl])
+        return q
+    subs = [subset(k) for k in range(2)]
+    sets = [T.gpu_context_rz(q) for q in subs]
+    ones = [T.gpu_context_rz(q) for q in subs]
+    for save in (False, True):
+        phi_ref = T.oracle_sweep_rz(p, save)
+        out = [np.full((m.ncornr, g), -1.0) for g in sizes]
+        assert teton.control_sweep_sets(sets, [q.Sigt for q in subs], [q.STotal for q in subs], p.tau, out, savePsi=save) == 1
+        for k, (c, q) in enumerate(zip(ones, subs)):
+            ref = np.zeros((m.ncornr, sizes[k]))
+            c.control_sweep(q.Sigt, q.STotal, p.tau, ref, savePsi=save)
+            assert np.array_equal(out[k], ref), (save, k)
+            assert T.relerr(out[k], phi_ref[:, bounds[k]:bounds[k + 1]]) <= TOL, (save, k)
+    for k, c in enumerate(sets):
+        assert T.mixed_err(c.download_psi(), p.Psi[:, :, bounds[k]:bounds[k + 1]], TOL) <= 1.0
+    for c in sets + ones:
+        c.close()

@@ -18,7 +18,7 @@ if [ -z "$QUICK" ]; then
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:sweep3d_plan -s 1 -c 1 -o gpurun_out/${TAG}_sweep3d_d8_full -f python bench.py --dims 8 --steps 1 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; tail -2 gpurun_out/${TAG}_ncu_full.log
 MEMTESTS="tests/test_gpu_psi_layout.py tests/test_gpu_sweep3d.py tests/test_gpu_sweeprz.py tests/test_gpu_gta.py tests/test_gpu_exchange.py tests/test_gpu_watchdog.py"
 else   # QUICK=1: what changed since the last full run only
-MEMTESTS="tests/test_gpu_gta.py tests/test_gpu_exchange.py"
+MEMTESTS="tests/test_gpu_gta.py tests/test_gpu_exchange.py tests/test_gpu_sweeprz.py::test_control_sweep_sets_rz_group_sets"
 fi
 timeout 500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest $MEMTESTS -m gpu -q -x --timeout=450 --timeout-method=thread -p no:cacheprovider -k "not strongly and not fullsize" > gpurun_out/${TAG}_memcheck.log 2>&1; tail -4 gpurun_out/${TAG}_memcheck.log
 timeout 100 python -u tools/perf_rz_gta.py gta 20 > gpurun_out/${TAG}_gta_solve_d20.log 2>&1; tail -1 gpurun_out/${TAG}_gta_solve_d20.log
