@@ -62,6 +62,12 @@ def test_host_only_context_refuses_compute():
                  lambda: ctx.download_phi(), lambda: ctx.init_phi_total()):
         with pytest.raises(teton.UmtError):
             call()
+    # the group-set call refuses as well (no CPU fallback), and says which entry point it was
+    ctx2 = _host_ctx(m)
+    out = [np.zeros((m.ncornr, 2)), np.zeros((m.ncornr, 2))]
+    with pytest.raises(teton.UmtError, match="umt_control_sweep"):
+        teton.control_sweep_sets([ctx, ctx2], None, None, 1.0, out)
+    ctx2.close()
     ctx.close()
 
 
