@@ -1337,7 +1337,7 @@ extern "C" int umt_control_sweep_sets(umt_ctx *const *ctxs, int n, const double 
   }
   // uploads of all sets on ONE stream, in set order: set 0 has the whole link first, set k+1 arrives while set k is swept
   cudaStream_t up = c0->stream3;
-  for (int k = 0; k < n; k++) {
+  auto enqueue = [&](int k) -> int {
     umt_ctx *ctx = ctxs[k];
     const size_t G = ctx->G;
     if (Sigt && Sigt[k]) UMT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sigt, Sigt[k], sizeof(double) * G * ctx->nz, cudaMemcpyHostToDevice, up));
@@ -1347,10 +1347,13 @@ extern "C" int umt_control_sweep_sets(umt_ctx *const *ctxs, int n, const double 
     // a persistent sweep kernel owns every SM it gets: the tally of the previous set goes first, or it would wait a whole sweep
     if (k > 0) UMT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctxs[k - 1]->ev[6], 0));
     ctx->tau = tau;
-    TRY(sweep_enqueue_single(ctx, savePsi, PhiTotal[k]));
-  }
-  int rc = UMT_OK;
-  for (int k = 0; k < n; k++) { const int r = sweep_finish_single(ctxs[k], savePsi); if (r && !rc) rc = r; }
+    return sweep_enqueue_single(ctx, savePsi, PhiTotal[k]);
+  };
+  int rc = UMT_OK, nQueued = 0;
+  for (; nQueued < n && rc == UMT_OK; nQueued++) rc = enqueue(nQueued);
+  if (rc) nQueued--;   // the set that failed to enqueue is not waited for; the ones before it are brought to a consistent end
+  for (int k = 0; k < nQueued; k++) { const int r = sweep_finish_single(ctxs[k], savePsi); if (r && !rc) rc = r; }
+  if (rc) cudaStreamSynchronize(up);
   return rc;
 }
 
